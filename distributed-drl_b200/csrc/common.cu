@@ -1,0 +1,44 @@
+// common.cu — error plumbing, launch counter, device queries.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace ddrl {
+
+std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+std::atomic<int64_t> g_launches{0};
+
+int sm_count(int device) {
+  static std::mutex mu;
+  static int cache[64];
+  static bool have[64];
+  std::lock_guard<std::mutex> lk(mu);
+  if (device >= 0 && device < 64 && have[device]) return cache[device];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0)
+    n = 148;
+  if (device >= 0 && device < 64) { cache[device] = n; have[device] = true; }
+  return n;
+}
+
+}  // namespace ddrl
+
+extern "C" {
+int ddrl_abi_version(void) { return DDRL_ABI_VERSION; }
+const char* ddrl_last_error(void) { return ddrl::last_error_ref().c_str(); }
+int64_t ddrl_launch_count(void) { return ddrl::g_launches.load(std::memory_order_relaxed); }
+}

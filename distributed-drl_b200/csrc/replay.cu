@@ -1,0 +1,524 @@
+// replay.cu — HBM-resident replay ring: batched store, Philox index generation + row gather.
+//
+// Replaces the numpy ring of the reference's ReplayBuffer (example/dsac.py:14-48,
+// algos/sac1/sac1.py:28-63).  The reference keeps five arrays (obs1/obs2/acts/rews/done); here a
+// transition is ONE packed, 16-byte aligned row
+//     [ obs1 (D) | obs2 (D) | acts (A) | rew | done | 0-pad ]      row_f = round_up(2D+A+2, 4) floats
+// so a sampled transition is a single contiguous read (2..7 DRAM sectors instead of >= 5 scattered
+// ones) and a batched store is a single streaming write.  The API-visible arrays (the dict
+// sample_batch returns) are produced by the gather kernels in the reference's five-array form.
+//
+// Kernels (all HBM-bandwidth bound; algorithmic bytes per transition = 2 * 4 * (2D+A+2)):
+//   rb_gather_narrow<LANES>  rows of <= 32 float4: LANES lanes per row, one 128-bit load per lane,
+//                            4 rows in flight per lane group; indices drawn 32 at a time per warp
+//   rb_gather_wide           rows of  > 32 float4: one warp per row, 4 x 128-bit loads in flight
+//   rb_store_rows<T>         SoA inputs -> packed rows, flat (row, chunk) mapping, 128-bit stores
+#include "common.cuh"
+
+namespace ddrl {
+
+enum IdxMode : int { IDX_INJECT = 0, IDX_PHILOX = 1, IDX_IDENTITY = 2 };
+
+struct GatherArgs {
+  const float4* ring;
+  int D, A, row_f4;
+  uint64_t size;       // sampling range [0,size)
+  int64_t total;       // rows to produce
+  const int64_t* idx_in;
+  int idx_mode;
+  uint64_t seed, counter;
+  uint32_t rng_stream;
+  float *o1, *o2, *oa, *orw, *od;
+  int64_t* oidx;
+};
+
+__device__ __forceinline__ void route_scalar(const GatherArgs& a, int64_t b, int f, float x) {
+  const int D = a.D, A = a.A;
+  if (f < D) a.o1[b * D + f] = x;
+  else if (f < 2 * D) a.o2[b * D + (f - D)] = x;
+  else if (f < 2 * D + A) a.oa[b * A + (f - 2 * D)] = x;
+  else if (f == 2 * D + A) a.orw[b] = x;
+  else if (f == 2 * D + A + 1) a.od[b] = x;
+}
+
+// chunk c (float4) of packed row -> the five output arrays
+__device__ __forceinline__ void route_chunk(const GatherArgs& a, bool aligned, int64_t b, int c,
+                                            const float4& v) {
+  const int D4 = a.D >> 2;
+  if (aligned && c < D4) {
+    st_f4(reinterpret_cast<float4*>(a.o1 + b * a.D) + c, v);
+  } else if (aligned && c < 2 * D4) {
+    st_f4(reinterpret_cast<float4*>(a.o2 + b * a.D) + (c - D4), v);
+  } else {
+    const int f = c * 4;
+    route_scalar(a, b, f + 0, v.x);
+    route_scalar(a, b, f + 1, v.y);
+    route_scalar(a, b, f + 2, v.z);
+    route_scalar(a, b, f + 3, v.w);
+  }
+}
+
+__device__ __forceinline__ int64_t draw_index(const GatherArgs& a, int64_t ordinal) {
+  if (a.idx_mode == IDX_INJECT) return a.idx_in[ordinal];
+  if (a.idx_mode == IDX_PHILOX)
+    return philox_index((uint64_t)ordinal, a.seed, a.counter, a.rng_stream, a.size);
+  return ordinal;
+}
+
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+  int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffff), src);
+  int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
+  return ((int64_t)hi << 32) | (uint32_t)lo;
+}
+
+// ---- rows that fit in LANES float4 (LANES in {2,4,8,16,32}) ---------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(256, 4) rb_gather_narrow(const GatherArgs a) {
+  constexpr int RPP = 32 / LANES;  // rows per pass of a warp
+  constexpr int U = (LANES >= 4) ? 4 : LANES;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LANES, l = lane % LANES;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool aligned = (a.D & 3) == 0;
+  const bool lane_live = l < a.row_f4;
+
+  for (int64_t base = warp * 32; base < a.total; base += nwarps * 32) {
+    const int64_t mine = base + lane;
+    int64_t myidx = 0;
+    if (mine < a.total) {
+      myidx = draw_index(a, mine);
+      if (a.oidx) a.oidx[mine] = myidx;
+    }
+#pragma unroll 1
+    for (int p0 = 0; p0 < LANES; p0 += U) {
+      float4 v[U];
+      int64_t b[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = (p0 + u) * RPP + g;
+        const int64_t src = shfl_i64(myidx, r);
+        b[u] = base + r;
+        ok[u] = lane_live && b[u] < a.total;
+        if (ok[u]) v[u] = ld_nc_f4(a.ring + src * a.row_f4 + l);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) route_chunk(a, aligned, b[u], l, v[u]);
+    }
+  }
+}
+
+// ---- wide rows: one warp per row ------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) rb_gather_wide(const GatherArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool aligned = (a.D & 3) == 0;
+  // a warp owns 8 consecutive rows per step (enough to amortise the index draw, small enough to
+  // spread a 4096-row batch over the whole chip)
+  constexpr int ROWS = 8;
+  for (int64_t base = warp * ROWS; base < a.total; base += nwarps * ROWS) {
+    const int64_t mine = base + lane;
+    int64_t myidx = 0;
+    if (lane < ROWS && mine < a.total) {
+      myidx = draw_index(a, mine);
+      if (a.oidx) a.oidx[mine] = myidx;
+    }
+    for (int r = 0; r < ROWS; ++r) {
+      const int64_t b = base + r;
+      const int64_t src = shfl_i64(myidx, r);
+      if (b >= a.total) break;  // warp-uniform
+      const float4* row = a.ring + src * a.row_f4;
+      for (int c0 = lane; c0 < a.row_f4; c0 += 32 * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + 32 * k;
+          if (c < a.row_f4) v[k] = ld_nc_f4(row + c);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + 32 * k;
+          if (c < a.row_f4) route_chunk(a, aligned, b, c, v[k]);
+        }
+      }
+    }
+  }
+}
+
+// ---- batched store --------------------------------------------------------------------------
+template <typename T>
+struct StoreArgs {
+  float4* ring;
+  int D, A, row_f4;
+  int64_t cap, ptr0;
+  int64_t first, n;   // rows [first, n) of the inputs are written (first > 0 iff n > cap)
+  const T *obs, *act, *rew, *nxt, *done;
+  int vec_ok;         // inputs are float, 16 B aligned and D % 4 == 0
+};
+
+template <typename T>
+__device__ __forceinline__ float fetch_field(const StoreArgs<T>& s, int64_t i, int f) {
+  const int D = s.D, A = s.A;
+  if (f < D) return (float)s.obs[i * D + f];
+  if (f < 2 * D) return (float)s.nxt[i * D + (f - D)];
+  if (f < 2 * D + A) return (float)s.act[i * A + (f - 2 * D)];
+  if (f == 2 * D + A) return (float)s.rew[i];
+  if (f == 2 * D + A + 1) return (float)s.done[i];
+  return 0.0f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) rb_store_rows(const StoreArgs<T> s) {
+  const int64_t nchunks = (s.n - s.first) * s.row_f4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int D4 = s.D >> 2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nchunks; e += stride) {
+    const int64_t i = s.first + e / s.row_f4;
+    const int c = (int)(e % s.row_f4);
+    int64_t pos = (s.ptr0 + i) % s.cap;
+    float4 v;
+    bool done_vec = false;
+    if constexpr (sizeof(T) == 4) {
+      if (s.vec_ok && c < 2 * D4) {
+        const float* src = (c < D4) ? (const float*)s.obs + i * s.D + 4 * c
+                                    : (const float*)s.nxt + i * s.D + 4 * (c - D4);
+        v = ld_nc_f4(reinterpret_cast<const float4*>(src));
+        done_vec = true;
+      }
+    }
+    if (!done_vec) {
+      const int f = 4 * c;
+      v.x = fetch_field(s, i, f + 0);
+      v.y = fetch_field(s, i, f + 1);
+      v.z = fetch_field(s, i, f + 2);
+      v.w = fetch_field(s, i, f + 3);
+    }
+    st_f4(s.ring + pos * s.row_f4 + c, v);
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct Staging {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    size_t want = need + need / 2;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(%zu) for staging failed: %s", want,
+                                      cudaGetErrorString(e));
+    bytes = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace ddrl
+
+struct ddrl_rb {
+  int device = 0, D = 0, A = 0, row_f = 0, row_f4 = 0, sms = 148;
+  int64_t cap = 0, ptr = 0, size = 0, steps = 0, sample_times = 0;
+  float* ring = nullptr;
+  ddrl::Staging st_in, st_out, st_idx;
+};
+
+using namespace ddrl;
+
+static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
+  if (a.total <= 0) return 0;
+  const int threads = 256;
+  const int max_blocks = rb->sms * 8;
+  if (rb->row_f4 <= 32) {
+    int lanes = 2;
+    while (lanes < rb->row_f4) lanes <<= 1;
+    const int64_t rows_per_block = (threads / 32) * 32;
+    int64_t blocks = (a.total + rows_per_block - 1) / rows_per_block;
+    if (blocks > max_blocks) blocks = max_blocks;
+    switch (lanes) {
+      case 2: rb_gather_narrow<2><<<(int)blocks, threads, 0, st>>>(a); break;
+      case 4: rb_gather_narrow<4><<<(int)blocks, threads, 0, st>>>(a); break;
+      case 8: rb_gather_narrow<8><<<(int)blocks, threads, 0, st>>>(a); break;
+      case 16: rb_gather_narrow<16><<<(int)blocks, threads, 0, st>>>(a); break;
+      default: rb_gather_narrow<32><<<(int)blocks, threads, 0, st>>>(a); break;
+    }
+  } else {
+    const int64_t rows_per_block = (threads / 32) * 8;
+    int64_t blocks = (a.total + rows_per_block - 1) / rows_per_block;
+    if (blocks > max_blocks) blocks = max_blocks;
+    rb_gather_wide<<<(int)blocks, threads, 0, st>>>(a);
+  }
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int launch_store(ddrl_rb* rb, const void* obs, const void* act, const void* rew,
+                        const void* nxt, const void* done, int64_t ptr0, int64_t n,
+                        cudaStream_t st) {
+  StoreArgs<T> s;
+  s.ring = reinterpret_cast<float4*>(rb->ring);
+  s.D = rb->D; s.A = rb->A; s.row_f4 = rb->row_f4;
+  s.cap = rb->cap; s.ptr0 = ptr0;
+  s.first = n > rb->cap ? n - rb->cap : 0;
+  s.n = n;
+  s.obs = (const T*)obs; s.act = (const T*)act; s.rew = (const T*)rew;
+  s.nxt = (const T*)nxt; s.done = (const T*)done;
+  s.vec_ok = sizeof(T) == 4 && (rb->D % 4 == 0) && (((uintptr_t)obs | (uintptr_t)nxt) % 16 == 0);
+  const int64_t nchunks = (s.n - s.first) * s.row_f4;
+  const int threads = 256;
+  int64_t blocks = (nchunks + threads * 4 - 1) / (threads * 4);  // ~4 chunks per thread
+  if (blocks < 1) blocks = 1;
+  if (blocks > rb->sms * 8) blocks = rb->sms * 8;
+  rb_store_rows<T><<<(int)blocks, threads, 0, st>>>(s);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" {
+
+int ddrl_rb_create(int device, int obs_dim, int act_dim, int64_t capacity, ddrl_rb_t* out) {
+  if (!out) return fail(DDRL_EINVAL, "ddrl_rb_create: out is NULL");
+  *out = nullptr;
+  if (obs_dim < 1 || act_dim < 1 || capacity < 1)
+    return fail(DDRL_EINVAL, "ddrl_rb_create: obs_dim=%d act_dim=%d capacity=%lld must be >= 1",
+                obs_dim, act_dim, (long long)capacity);
+  int ndev = 0;
+  DDRL_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+    return fail(DDRL_EINVAL, "ddrl_rb_create: device %d out of range (%d devices)", device, ndev);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DDRL_ECUDA, "ddrl_rb_create: cannot select device %d", device);
+  ddrl_rb* rb = new ddrl_rb();
+  rb->device = device;
+  rb->D = obs_dim; rb->A = act_dim;
+  rb->row_f = ((2 * obs_dim + act_dim + 2) + 3) / 4 * 4;
+  rb->row_f4 = rb->row_f / 4;
+  rb->cap = capacity;
+  rb->sms = sm_count(device);
+  const size_t bytes = (size_t)capacity * rb->row_f * sizeof(float);
+  cudaError_t e = cudaMalloc(&rb->ring, bytes);
+  if (e != cudaSuccess) {
+    delete rb;
+    return fail(DDRL_ENOMEM, "ddrl_rb_create: cudaMalloc(%zu bytes) failed: %s", bytes,
+                cudaGetErrorString(e));
+  }
+  e = cudaMemset(rb->ring, 0, bytes);
+  if (e != cudaSuccess) {
+    cudaFree(rb->ring);
+    delete rb;
+    return fail(DDRL_ECUDA, "ddrl_rb_create: cudaMemset failed: %s", cudaGetErrorString(e));
+  }
+  *out = rb;
+  return 0;
+}
+
+int ddrl_rb_destroy(ddrl_rb_t rb) {
+  if (!rb) return 0;
+  DeviceGuard guard(rb->device);
+  cudaDeviceSynchronize();
+  if (rb->ring) cudaFree(rb->ring);
+  rb->st_in.release(); rb->st_out.release(); rb->st_idx.release();
+  delete rb;
+  return 0;
+}
+
+static int store_common(ddrl_rb_t rb, const void* obs, const void* act, const void* rew,
+                        const void* nxt, const void* done, int64_t n, int in_dtype,
+                        cudaStream_t st) {
+  int rc;
+  if (in_dtype == DDRL_F32) rc = launch_store<float>(rb, obs, act, rew, nxt, done, rb->ptr, n, st);
+  else rc = launch_store<double>(rb, obs, act, rew, nxt, done, rb->ptr, n, st);
+  if (rc) return rc;
+  rb->ptr = (rb->ptr + n) % rb->cap;
+  rb->size = (rb->size + n < rb->cap) ? rb->size + n : rb->cap;
+  rb->steps += n;
+  return 0;
+}
+
+int ddrl_rb_store_batch(ddrl_rb_t rb, const void* d_obs, const void* d_act, const void* d_rew,
+                        const void* d_next_obs, const void* d_done, int64_t n, int in_dtype,
+                        void* stream) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_store_batch: NULL handle");
+  if (n < 0) return fail(DDRL_EINVAL, "ddrl_rb_store_batch: n=%lld < 0", (long long)n);
+  if (in_dtype != DDRL_F32 && in_dtype != DDRL_F64)
+    return fail(DDRL_EINVAL, "ddrl_rb_store_batch: in_dtype must be DDRL_F32 or DDRL_F64");
+  if (n == 0) return 0;
+  if (!d_obs || !d_act || !d_rew || !d_next_obs || !d_done)
+    return fail(DDRL_EINVAL, "ddrl_rb_store_batch: NULL input array");
+  DeviceGuard guard(rb->device);
+  return store_common(rb, d_obs, d_act, d_rew, d_next_obs, d_done, n, in_dtype, (cudaStream_t)stream);
+}
+
+int ddrl_rb_store_batch_host(ddrl_rb_t rb, const void* h_obs, const void* h_act, const void* h_rew,
+                             const void* h_next_obs, const void* h_done, int64_t n, int in_dtype,
+                             void* stream) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host: NULL handle");
+  if (n < 0) return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host: n=%lld < 0", (long long)n);
+  if (in_dtype != DDRL_F32 && in_dtype != DDRL_F64)
+    return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host: in_dtype must be DDRL_F32 or DDRL_F64");
+  if (n == 0) return 0;
+  if (!h_obs || !h_act || !h_rew || !h_next_obs || !h_done)
+    return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host: NULL input array");
+  DeviceGuard guard(rb->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = in_dtype == DDRL_F32 ? 4 : 8;
+  auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t b_obs = up256((size_t)n * rb->D * es), b_act = up256((size_t)n * rb->A * es),
+               b_s = up256((size_t)n * es);
+  // the staging block may still be read by a previous store on this stream: stream order protects
+  // re-use, growth (cudaFree) synchronises the device.
+  int rc = rb->st_in.ensure(2 * b_obs + b_act + 2 * b_s);
+  if (rc) return rc;
+  char* base = (char*)rb->st_in.p;
+  char* d_obs = base;
+  char* d_nxt = d_obs + b_obs;
+  char* d_act = d_nxt + b_obs;
+  char* d_rew = d_act + b_act;
+  char* d_done = d_rew + b_s;
+  DDRL_CUDA(cudaMemcpyAsync(d_obs, h_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_nxt, h_next_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_act, h_act, (size_t)n * rb->A * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_rew, h_rew, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_done, h_done, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  return store_common(rb, d_obs, d_act, d_rew, d_nxt, d_done, n, in_dtype, st);
+}
+
+static int sample_check(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const char* who) {
+  if (!rb) return fail(DDRL_EINVAL, "%s: NULL handle", who);
+  if (batch < 0 || n_batches < 0)
+    return fail(DDRL_EINVAL, "%s: batch=%lld n_batches=%lld must be >= 0", who, (long long)batch,
+                (long long)n_batches);
+  if ((double)batch * (double)n_batches >= 4294967296.0)
+    return fail(DDRL_EINVAL, "%s: batch*n_batches must be < 2^32", who);
+  if (rb->size == 0 && batch * n_batches > 0)
+    return fail(DDRL_EEMPTY, "%s: ring is empty (the reference raises ValueError: high <= 0)", who);
+  return 0;
+}
+
+int ddrl_rb_sample(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* d_idx_in,
+                   uint64_t seed, uint64_t counter, uint32_t rng_stream, float* d_out_obs1,
+                   float* d_out_obs2, float* d_out_acts, float* d_out_rews, float* d_out_done,
+                   int64_t* d_out_idx, void* stream) {
+  int rc = sample_check(rb, batch, n_batches, "ddrl_rb_sample");
+  if (rc) return rc;
+  const int64_t total = batch * n_batches;
+  if (total > 0 && (!d_out_obs1 || !d_out_obs2 || !d_out_acts || !d_out_rews || !d_out_done))
+    return fail(DDRL_EINVAL, "ddrl_rb_sample: NULL output array");
+  DeviceGuard guard(rb->device);
+  GatherArgs a;
+  a.ring = reinterpret_cast<const float4*>(rb->ring);
+  a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4;
+  a.size = (uint64_t)rb->size; a.total = total;
+  a.idx_in = d_idx_in; a.idx_mode = d_idx_in ? IDX_INJECT : IDX_PHILOX;
+  a.seed = seed; a.counter = counter; a.rng_stream = rng_stream;
+  a.o1 = d_out_obs1; a.o2 = d_out_obs2; a.oa = d_out_acts; a.orw = d_out_rews; a.od = d_out_done;
+  a.oidx = d_out_idx;
+  rc = launch_gather(rb, a, (cudaStream_t)stream);
+  if (rc) return rc;
+  rb->sample_times += n_batches;
+  return 0;
+}
+
+int64_t ddrl_rb_sample_block_bytes(ddrl_rb_t rb, int64_t n) {
+  if (!rb || n < 0) return -1;
+  int64_t f = n * (2 * (int64_t)rb->D + rb->A + 2) * 4;
+  f = (f + 7) / 8 * 8;
+  return f + n * 8;
+}
+
+int ddrl_rb_sample_host(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_idx_in,
+                        uint64_t seed, uint64_t counter, uint32_t rng_stream, void* h_out_block,
+                        int64_t block_bytes, void* stream) {
+  int rc = sample_check(rb, batch, n_batches, "ddrl_rb_sample_host");
+  if (rc) return rc;
+  const int64_t n = batch * n_batches;
+  const int64_t need = ddrl_rb_sample_block_bytes(rb, n);
+  if (!h_out_block || block_bytes < need)
+    return fail(DDRL_EINVAL, "ddrl_rb_sample_host: output block too small (%lld < %lld)",
+                (long long)block_bytes, (long long)need);
+  if (n == 0) return 0;
+  DeviceGuard guard(rb->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = rb->st_out.ensure((size_t)need);
+  if (rc) return rc;
+  const int64_t* d_idx_in = nullptr;
+  if (h_idx_in) {
+    rc = rb->st_idx.ensure((size_t)n * 8);
+    if (rc) return rc;
+    DDRL_CUDA(cudaMemcpyAsync(rb->st_idx.p, h_idx_in, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    d_idx_in = (const int64_t*)rb->st_idx.p;
+  }
+  float* o1 = (float*)rb->st_out.p;
+  float* o2 = o1 + n * rb->D;
+  float* oa = o2 + n * rb->D;
+  float* orw = oa + n * rb->A;
+  float* od = orw + n;
+  int64_t* oidx = (int64_t*)((char*)rb->st_out.p + (need - n * 8));
+  rc = ddrl_rb_sample(rb, batch, n_batches, d_idx_in, seed, counter, rng_stream, o1, o2, oa, orw, od,
+                      oidx, stream);
+  if (rc) return rc;
+  DDRL_CUDA(cudaMemcpyAsync(h_out_block, rb->st_out.p, (size_t)need, cudaMemcpyDeviceToHost, st));
+  DDRL_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity, int64_t* steps,
+                   int64_t* sample_times) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_counts: NULL handle");
+  if (ptr) *ptr = rb->ptr;
+  if (size) *size = rb->size;
+  if (capacity) *capacity = rb->cap;
+  if (steps) *steps = rb->steps;
+  if (sample_times) *sample_times = rb->sample_times;
+  return 0;
+}
+
+int ddrl_rb_layout(ddrl_rb_t rb, int* obs_dim, int* act_dim, int* row_floats, void** d_ring) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_layout: NULL handle");
+  if (obs_dim) *obs_dim = rb->D;
+  if (act_dim) *act_dim = rb->A;
+  if (row_floats) *row_floats = rb->row_f;
+  if (d_ring) *d_ring = rb->ring;
+  return 0;
+}
+
+int ddrl_rb_export(ddrl_rb_t rb, float* d_obs1, float* d_obs2, float* d_acts, float* d_rews,
+                   float* d_done, void* stream) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_export: NULL handle");
+  if (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done)
+    return fail(DDRL_EINVAL, "ddrl_rb_export: NULL output array");
+  DeviceGuard guard(rb->device);
+  GatherArgs a;
+  a.ring = reinterpret_cast<const float4*>(rb->ring);
+  a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4;
+  a.size = (uint64_t)rb->cap; a.total = rb->cap;
+  a.idx_in = nullptr; a.idx_mode = IDX_IDENTITY;
+  a.seed = a.counter = 0; a.rng_stream = 0;
+  a.o1 = d_obs1; a.o2 = d_obs2; a.oa = d_acts; a.orw = d_rews; a.od = d_done; a.oidx = nullptr;
+  return launch_gather(rb, a, (cudaStream_t)stream);
+}
+
+int ddrl_rb_import(ddrl_rb_t rb, const float* d_obs1, const float* d_obs2, const float* d_acts,
+                   const float* d_rews, const float* d_done, int64_t ptr, int64_t size,
+                   int64_t steps, int64_t sample_times, void* stream) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_import: NULL handle");
+  if (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done)
+    return fail(DDRL_EINVAL, "ddrl_rb_import: NULL input array");
+  if (ptr < 0 || ptr >= rb->cap || size < 0 || size > rb->cap || steps < 0 || sample_times < 0)
+    return fail(DDRL_EINVAL, "ddrl_rb_import: inconsistent counters ptr=%lld size=%lld cap=%lld",
+                (long long)ptr, (long long)size, (long long)rb->cap);
+  DeviceGuard guard(rb->device);
+  int rc = launch_store<float>(rb, d_obs1, d_acts, d_rews, d_obs2, d_done, 0, rb->cap,
+                               (cudaStream_t)stream);
+  if (rc) return rc;
+  rb->ptr = ptr; rb->size = size; rb->steps = steps; rb->sample_times = sample_times;
+  return 0;
+}
+
+}  // extern "C"

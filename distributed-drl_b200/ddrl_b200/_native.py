@@ -1,0 +1,70 @@
+"""ctypes binding of libddrl_b200.so (C ABI declared in include/ddrl_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the caller
+gets an exception.  Nothing here imports the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libddrl_b200.so")
+
+F32, F64, U8 = 0, 1, 2
+OK, EINVAL, ECUDA, EEMPTY, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libddrl_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+_vp, _i64, _u64, _u32, _int = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int
+_pi64, _pint = C.POINTER(C.c_int64), C.POINTER(C.c_int)
+
+# name -> (restype, argtypes).  Kept in one table so tests can check it against the header.
+SIGNATURES = {
+    "ddrl_abi_version": (_int, []),
+    "ddrl_last_error": (C.c_char_p, []),
+    "ddrl_launch_count": (_i64, []),
+    "ddrl_rb_create": (_int, [_int, _int, _int, _i64, C.POINTER(_vp)]),
+    "ddrl_rb_destroy": (_int, [_vp]),
+    "ddrl_rb_store_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "ddrl_rb_store_batch_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "ddrl_rb_sample": (_int, [_vp, _i64, _i64, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_rb_sample_host": (_int, [_vp, _i64, _i64, _vp, _u64, _u64, _u32, _vp, _i64, _vp]),
+    "ddrl_rb_sample_block_bytes": (_i64, [_vp, _i64]),
+    "ddrl_rb_counts": (_int, [_vp, _pi64, _pi64, _pi64, _pi64, _pi64]),
+    "ddrl_rb_layout": (_int, [_vp, _pint, _pint, _pint, C.POINTER(_vp)]),
+    "ddrl_rb_export": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_rb_import": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+}
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing — build it with `python distributed-drl_b200/build.py` "
+                "(or __graft_entry__.build()).  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(rc, lib().ddrl_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().ddrl_launch_count())

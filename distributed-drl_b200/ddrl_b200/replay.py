@@ -1,0 +1,354 @@
+"""ReplayBuffer — the reference's replay API over an HBM-resident ring.
+
+Mirrors (paths relative to the reference tree):
+    ReplayBuffer(obs_dim, act_dim, size)            example/dsac.py:20-27, algos/sac1/sac1.py:34-41
+    .store(obs, act, rew, next_obs, done)           example/dsac.py:29-37
+    .sample_batch(batch_size)                       example/dsac.py:39-45  (default 128: sac1.py:53)
+    .get_counts()                                   algos/sac1/sac1.py:62-63 / example/dsac.py:47-48
+    .save() / .load()  (.npy + buffer_infos)        algos/dqn/train.py:82-108
+
+All data lives in GPU memory (libddrl_b200, csrc/replay.cu); this file is host-side marshalling
+only.  Additive fast paths that the reference does not have: store_batch (vectorised producers),
+sample_many (several batches per launch), device=True outputs (no D2H), injected index streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class ReplayBuffer:
+    """Drop-in for the reference ReplayBuffer.
+
+    Extra keyword arguments (all optional, defaults keep the reference call pattern working):
+      device        CUDA device index (default: torch.cuda.current_device())
+      flavor        "sac1" | "dsac" | "dqn": which reference variant's get_counts()/acts shape to mimic
+      index_source  "philox": indices drawn on the GPU (Philox4x32-10 keyed by `seed`)
+                    "numpy" : indices drawn on the host with np.random.randint exactly where the
+                              reference draws them (bit-identical batches to the reference under the
+                              same np.random.seed), then injected
+      seed          Philox key; default: drawn once from numpy's global RandomState at first use, so
+                    `np.random.seed(opt.seed)` (algos/sac1/actor_learner.py:24) makes runs repeatable
+      rng_stream    Philox sub-stream (rank of the shard in multi-GPU runs)
+      stage_rows    rows of pinned host staging for single-transition store()
+    """
+
+    def __init__(self, obs_dim, act_dim, size, *, device=None, flavor="sac1", index_source="philox",
+                 seed=None, rng_stream=0, stage_rows=1024):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ddrl_b200.ReplayBuffer needs a CUDA device (no CPU fallback)")
+        if flavor not in ("sac1", "dsac", "dqn"):
+            raise ValueError(f"unknown flavor {flavor!r}")
+        if index_source not in ("philox", "numpy"):
+            raise ValueError(f"unknown index_source {index_source!r}")
+        self._lib = N.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.flavor = flavor
+        self.obs_dim = int(obs_dim)
+        self._scalar_act = flavor == "dqn" or act_dim in (0, None)
+        self.act_dim = 1 if self._scalar_act else int(act_dim)
+        self.max_size = int(size)
+        self.index_source = index_source
+        self._seed = None if seed is None else int(seed) & (2 ** 64 - 1)
+        self._rng_stream = int(rng_stream) & 0xFFFFFFFF
+        self._counter = 0
+        h = C.c_void_p()
+        N.check(self._lib.ddrl_rb_create(self.device, self.obs_dim, self.act_dim, self.max_size, C.byref(h)))
+        self._h = h
+        # pinned staging for store(): two sets, alternated so a set is never rewritten while its
+        # H2D copy may still be in flight
+        self._stage_rows = max(1, int(stage_rows))
+        self._stages = [self._new_stage() for _ in range(2)]
+        self._cur = 0
+        self._staged = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _new_stage(self):
+        S, D, A = self._stage_rows, self.obs_dim, self.act_dim
+        pin = dict(dtype=torch.float32, pin_memory=True)
+        t = dict(obs=torch.empty((S, D), **pin), nxt=torch.empty((S, D), **pin),
+                 act=torch.empty((S, A), **pin), rew=torch.empty(S, **pin), done=torch.empty(S, **pin))
+        st = {k: (v, v.numpy()) for k, v in t.items()}
+        st["event"] = None
+        return st
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.ddrl_rb_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def close(self):
+        self.__del__()
+
+    # ------------------------------------------------------------------------------------------
+    # store
+    # ------------------------------------------------------------------------------------------
+    def store(self, obs, act, rew, next_obs, done):
+        """One transition (reference signature).  Arguments are captured by value at call time
+        (numpy assignment into pinned staging performs the same casts as the reference's
+        ``buf[ptr] = x``); rows reach the GPU ring in batches, at the latest before the next
+        sample / export / get of ring state."""
+        st = self._stages[self._cur]
+        k = self._staged
+        if k == 0 and st["event"] is not None:
+            st["event"].synchronize()
+            st["event"] = None
+        st["obs"][1][k] = obs
+        st["nxt"][1][k] = next_obs
+        st["act"][1][k] = act
+        st["rew"][1][k] = rew
+        st["done"][1][k] = done
+        self._staged = k + 1
+        if self._staged == self._stage_rows:
+            self.flush()
+
+    def flush(self):
+        """Push staged single-transition stores to the GPU ring."""
+        k = self._staged
+        if k == 0:
+            return
+        st = self._stages[self._cur]
+        s = self._stream()
+        N.check(self._lib.ddrl_rb_store_batch_host(
+            self._h, _ptr(st["obs"][0]), _ptr(st["act"][0]), _ptr(st["rew"][0]), _ptr(st["nxt"][0]),
+            _ptr(st["done"][0]), k, N.F32, C.c_void_p(s.cuda_stream)))
+        ev = torch.cuda.Event()
+        ev.record(s)
+        st["event"] = ev
+        self._staged = 0
+        self._cur ^= 1
+
+    def store_batch(self, obs, act, rew, next_obs, done):
+        """n transitions at once (== n sequential store() calls in row order).  Accepts numpy
+        arrays (copied through pinned staging by the library call) or torch tensors; CUDA tensors
+        on this device are consumed in place with no host round-trip (float32 or float64, cast on the GPU)."""
+        self.flush()
+        arrs = [obs, act, rew, next_obs, done]
+        if all(isinstance(a, torch.Tensor) and a.is_cuda for a in arrs):
+            return self._store_device(*arrs)
+        np_arrs = []
+        for a in arrs:
+            if isinstance(a, torch.Tensor):
+                a = a.detach().cpu().numpy()
+            np_arrs.append(np.asarray(a))
+        n = int(np_arrs[2].shape[0])
+        D, A = self.obs_dim, self.act_dim
+        shapes = [(n, D), (n, A), (n,), (n, D), (n,)]
+        # host-side cast to float32 is numpy's own assignment cast, i.e. the reference's semantics
+        host = [np.ascontiguousarray(a.reshape(sh), dtype=np.float32) for a, sh in zip(np_arrs, shapes)]
+        s = self._stream()
+        N.check(self._lib.ddrl_rb_store_batch_host(
+            self._h, *[C.c_void_p(a.ctypes.data) for a in host], n, N.F32, C.c_void_p(s.cuda_stream)))
+        # pageable source memory: the copies above are staged synchronously by the driver for
+        # small sizes only; make the by-value contract unconditional
+        s.synchronize()
+
+    def _store_device(self, obs, act, rew, next_obs, done):
+        n = int(rew.shape[0])
+        D, A = self.obs_dim, self.act_dim
+        dt = torch.float64 if obs.dtype == torch.float64 else torch.float32
+        dev = torch.device("cuda", self.device)
+        shapes = [(n, D), (n, A), (n,), (n, D), (n,)]
+        ts = [t.to(device=dev, dtype=dt).reshape(sh).contiguous() for t, sh in zip((obs, act, rew, next_obs, done), shapes)]
+        s = self._stream()
+        N.check(self._lib.ddrl_rb_store_batch(self._h, *[_ptr(t) for t in ts], n,
+                                              N.F64 if dt == torch.float64 else N.F32,
+                                              C.c_void_p(s.cuda_stream)))
+        # keep the inputs alive until the stream has consumed them
+        for t in ts:
+            t.record_stream(s)
+
+    # ------------------------------------------------------------------------------------------
+    # sample
+    # ------------------------------------------------------------------------------------------
+    def _philox_seed(self):
+        if self._seed is None:
+            # one draw from the same global RandomState the reference samples from
+            self._seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+        return self._seed
+
+    def _counts_native(self):
+        v = [C.c_int64() for _ in range(5)]
+        N.check(self._lib.ddrl_rb_counts(self._h, *[C.byref(x) for x in v]))
+        return [int(x.value) for x in v]  # ptr, size, capacity, steps, sample_times
+
+    def _shape_out(self, n_batches, batch, many):
+        lead = (n_batches, batch) if many else (batch,)
+        return lead
+
+    def _sample(self, batch_size, n_batches, idxs, device, many, return_idxs):
+        self.flush()
+        batch_size, n_batches = int(batch_size), int(n_batches)
+        n = batch_size * n_batches
+        if self.size == 0:
+            # the reference's np.random.randint(0, 0, ...) raises exactly this
+            raise ValueError("high <= 0")
+        if idxs is None and self.index_source == "numpy":
+            idxs = np.random.randint(0, self.size, size=n)
+        s = self._stream()
+        D, A = self.obs_dim, self.act_dim
+        lead = (n_batches, batch_size) if many else (batch_size,)
+        act_shape = lead if self._scalar_act else lead + (A,)
+        seed = 0 if idxs is not None else self._philox_seed()
+        counter = self._counter
+        if device:
+            dev = torch.device("cuda", self.device)
+            d_idx = None
+            if idxs is not None:
+                d_idx = torch.as_tensor(idxs, dtype=torch.int64).reshape(-1).to(dev, non_blocking=False).contiguous()
+                if d_idx.numel() != n:
+                    raise ValueError(f"idxs has {d_idx.numel()} entries, expected {n}")
+            f32 = dict(dtype=torch.float32, device=dev)
+            out = dict(obs1=torch.empty(lead + (D,), **f32), obs2=torch.empty(lead + (D,), **f32),
+                       acts=torch.empty(act_shape, **f32), rews=torch.empty(lead, **f32),
+                       done=torch.empty(lead, **f32))
+            o_idx = torch.empty(lead, dtype=torch.int64, device=dev) if return_idxs else None
+            N.check(self._lib.ddrl_rb_sample(
+                self._h, batch_size, n_batches, _ptr(d_idx), seed, counter, self._rng_stream,
+                _ptr(out["obs1"]), _ptr(out["obs2"]), _ptr(out["acts"]), _ptr(out["rews"]),
+                _ptr(out["done"]), _ptr(o_idx), C.c_void_p(s.cuda_stream)))
+            if d_idx is not None:
+                d_idx.record_stream(s)
+            if return_idxs:
+                out["idxs"] = o_idx
+        else:
+            h_idx = None
+            if idxs is not None:
+                if isinstance(idxs, torch.Tensor):
+                    idxs = idxs.detach().cpu().numpy()
+                h_idx = np.ascontiguousarray(np.asarray(idxs).reshape(-1), dtype=np.int64)
+                if h_idx.size != n:
+                    raise ValueError(f"idxs has {h_idx.size} entries, expected {n}")
+            nbytes = int(self._lib.ddrl_rb_sample_block_bytes(self._h, n))
+            block = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            N.check(self._lib.ddrl_rb_sample_host(
+                self._h, batch_size, n_batches, C.c_void_p(h_idx.ctypes.data) if h_idx is not None else None,
+                seed, counter, self._rng_stream, _ptr(block), nbytes, C.c_void_p(s.cuda_stream)))
+            raw = block.numpy()
+            nf = n * (2 * D + A + 2)
+            f = raw[: nf * 4].view(np.float32)
+            o = 0
+            out = {}
+            for key, width, shape in (("obs1", D, lead + (D,)), ("obs2", D, lead + (D,)),
+                                      ("acts", A, act_shape), ("rews", 1, lead), ("done", 1, lead)):
+                out[key] = f[o:o + n * width].reshape(shape)
+                o += n * width
+            if return_idxs:
+                out["idxs"] = raw[nbytes - n * 8:].view(np.int64).reshape(lead)
+        if idxs is None:
+            self._counter += 1
+        return out
+
+    def sample_batch(self, batch_size=128, *, idxs=None, device=False, return_idxs=False):
+        """Reference signature.  Returns dict(obs1, obs2, acts, rews, done): float32 numpy arrays
+        (fresh, C-contiguous) or, with device=True, CUDA tensors that never leave the GPU."""
+        if self.flavor == "dqn" and batch_size is None:
+            raise TypeError("dqn flavour: pass opt.batch_size explicitly")
+        return self._sample(batch_size, 1, idxs, device, False, return_idxs)
+
+    def sample_many(self, n_batches, batch_size=128, *, idxs=None, device=True, return_idxs=False):
+        """n_batches sample_batch() calls in ONE kernel launch; outputs are stacked
+        [n_batches, batch_size, ...].  Counts as n_batches samples (sample_times += n_batches)."""
+        return self._sample(batch_size, n_batches, idxs, device, True, return_idxs)
+
+    # ------------------------------------------------------------------------------------------
+    # counters / state
+    # ------------------------------------------------------------------------------------------
+    @property
+    def ptr(self):
+        return (self._counts_native()[0] + self._staged) % self.max_size
+
+    @property
+    def size(self):
+        return min(self._counts_native()[1] + self._staged, self.max_size)
+
+    @property
+    def steps(self):
+        return self._counts_native()[3] + self._staged
+
+    @property
+    def sample_times(self):
+        return self._counts_native()[4]
+
+    rollout_steps = steps  # example/dsac.py naming
+
+    def get_counts(self):
+        p, size, cap, steps, samples = self._counts_native()
+        steps += self._staged
+        size = min(size + self._staged, cap)
+        if self.flavor == "dsac":
+            return steps                      # example/dsac.py:47-48
+        return samples, steps, size           # algos/sac1/sac1.py:62-63 ; dqn: (learner_steps, actor_steps, size)
+
+    def ring_arrays(self):
+        """The reference's five arrays (obs1_buf, obs2_buf, acts_buf, rews_buf, done_buf) as numpy,
+        unpacked from the GPU ring — for checkpoints and parity tests, not a hot path."""
+        self.flush()
+        dev = torch.device("cuda", self.device)
+        cap, D, A = self.max_size, self.obs_dim, self.act_dim
+        f32 = dict(dtype=torch.float32, device=dev)
+        o1, o2 = torch.empty((cap, D), **f32), torch.empty((cap, D), **f32)
+        oa, orw, od = torch.empty((cap, A), **f32), torch.empty(cap, **f32), torch.empty(cap, **f32)
+        s = self._stream()
+        N.check(self._lib.ddrl_rb_export(self._h, _ptr(o1), _ptr(o2), _ptr(oa), _ptr(orw), _ptr(od),
+                                         C.c_void_p(s.cuda_stream)))
+        s.synchronize()
+        acts = oa.cpu().numpy()
+        if self._scalar_act:
+            acts = acts.reshape(cap)
+        return dict(obs1_buf=o1.cpu().numpy(), obs2_buf=o2.cpu().numpy(), acts_buf=acts,
+                    rews_buf=orw.cpu().numpy(), done_buf=od.cpu().numpy())
+
+    def load_ring_arrays(self, obs1_buf, obs2_buf, acts_buf, rews_buf, done_buf, ptr, size, steps=0,
+                         sample_times=0):
+        self.flush()
+        dev = torch.device("cuda", self.device)
+        cap, D, A = self.max_size, self.obs_dim, self.act_dim
+        def up(a, shape):
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(shape))).to(dev)
+        ts = [up(obs1_buf, (cap, D)), up(obs2_buf, (cap, D)), up(acts_buf, (cap, A)), up(rews_buf, (cap,)),
+              up(done_buf, (cap,))]
+        s = self._stream()
+        N.check(self._lib.ddrl_rb_import(self._h, *[_ptr(t) for t in ts], int(ptr), int(size), int(steps),
+                                         int(sample_times), C.c_void_p(s.cuda_stream)))
+        s.synchronize()
+
+    # -- algos/dqn/train.py:82-108 on-disk format -------------------------------------------------
+    def save(self, checkpoint_dir, buffer_index=0):
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        arrs = self.ring_arrays()
+        for name, a in arrs.items():
+            np.save(os.path.join(checkpoint_dir, f"{name}-{buffer_index}"), a)
+        p, size, cap, steps, samples = self._counts_native()
+        np.save(os.path.join(checkpoint_dir, f"buffer_infos-{buffer_index}"),
+                np.array((p, size, cap, steps, samples)))
+
+    def load(self, checkpoint_dir, buffer_index=0):
+        ld = lambda n: np.load(os.path.join(checkpoint_dir, f"{n}-{buffer_index}.npy"))
+        infos = ld("buffer_infos")
+        if int(infos[2]) != self.max_size:
+            raise ValueError(f"checkpoint capacity {int(infos[2])} != buffer capacity {self.max_size}")
+        self.load_ring_arrays(ld("obs1_buf"), ld("obs2_buf"), ld("acts_buf"), ld("rews_buf"), ld("done_buf"),
+                              ptr=int(infos[0]), size=int(infos[1]), steps=int(infos[3]),
+                              sample_times=int(infos[4]))
+
+    # handle for native consumers (fused sample->update)
+    @property
+    def native_handle(self):
+        self.flush()
+        return self._h
