@@ -1,0 +1,764 @@
+// sac.cu — SAC1 learner step on the GPU (parity mode, fp32).
+//
+// Replaces Learner.train / get_weights / set_weights of algos/sac1/actor_learner.py:20-142 (graph in
+// :27-101, nets in algos/sac1/core.py:15-121), i.e. one `sess.run(step_ops)`:
+//   forward  3 policy passes (main@x, main@x2, target@x2) and 5 Q passes
+//            (main Q1,Q2@(x,a); main Q1@(x,pi(x)); target Q1,Q2@(x2,pi_targ(x2)))
+//   losses   pi_loss, q1_loss, q2_loss with the Bellman target  r + gamma (1-d)(min Q_targ - alpha logp2)
+//   backward pi-loss wrt main/pi (through Q1's inputs only), value-loss wrt main/q1,q2 — both at theta_t
+//   update   TF1 Adam(pi), TF1 Adam(q), then polyak over all main tensors (policy included) with the
+//            post-update weights; optional entropy-alpha Adam step.
+//
+// Parameters, Adam moments, target weights and gradients are FLAT fp32 buffers with one contiguous
+// [K+1, N] block per dense layer (kernel rows + bias row; see sac_gemm.cuh), so the optimiser, the
+// target averaging, the gradient all-reduce and the parameter broadcast are each one pass / one
+// collective over one buffer.  The policy's mu and log_std heads share one [h2+1, 2A] block.
+// The whole step is captured once per batch size into a CUDA graph; per-step values (input pointers,
+// step counters, Philox counter) live in device memory and are written by a 1-thread kernel.
+#include <cmath>
+#include <map>
+#include <vector>
+
+#include "sac_gemm.cuh"
+
+namespace ddrl {
+
+// ------------------------------------------------------------------------------------------------
+// device-resident per-step state
+// ------------------------------------------------------------------------------------------------
+struct StepDyn {   // written by k_set_params before every step (by-value kernel arguments)
+  const float *obs1, *obs2, *acts, *rews, *done;  // external batch (NULL: already in internal buffers)
+  const float* noise;                              // external [3,B,A] noise or NULL (Philox)
+  float *out_scalars, *out_q1, *out_q2, *out_logp; // nullable
+  unsigned long long seed;
+  float grad_scale;
+};
+struct StepState {  // persistent
+  StepDyn dyn;
+  int t_pi, t_q, t_alpha;
+  unsigned long long noise_counter;
+  float log_alpha, alpha_m, alpha_v;
+  float alpha_cur;      // alpha used by this step (pre-update)
+  int auto_alpha;
+  float alpha_const;
+};
+
+__global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
+  st->dyn = dyn;
+  if (advance) {
+    st->t_pi += 1;
+    st->t_q += 1;
+    st->noise_counter += 1;
+    st->alpha_cur = st->auto_alpha ? expf(st->log_alpha) : st->alpha_const;
+  }
+}
+
+// copy the external batch into the learner's own buffers and materialise the noise
+__global__ void __launch_bounds__(256) k_prologue(const StepState* __restrict__ st, int B, int D, int A,
+                                                  float* X, float* X2, float* ACT, float* R, float* DN,
+                                                  float* NOISE) {
+  const StepDyn& d = st->dyn;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  if (d.obs1) {
+    for (int64_t i = tid; i < (int64_t)B * D; i += nthr) { X[i] = d.obs1[i]; X2[i] = d.obs2[i]; }
+    for (int64_t i = tid; i < (int64_t)B * A; i += nthr) ACT[i] = d.acts[i];
+    for (int64_t i = tid; i < B; i += nthr) { R[i] = d.rews[i]; DN[i] = d.done[i]; }
+  }
+  const int64_t n = 3LL * B * A;
+  if (d.noise) {
+    for (int64_t i = tid; i < n; i += nthr) NOISE[i] = d.noise[i];
+  } else {
+    // Philox4x32-10 -> two Box-Muller pairs per counter (oracle/replay_oracle.py: philox_normals)
+    const unsigned long long ctr = st->noise_counter;
+    for (int64_t q = tid; q < (n + 3) / 4; q += nthr) {
+      const Philox4 p = philox4x32_10((uint32_t)q, (uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5AC1u,
+                                      (uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+      const float u0 = ((float)p.x + 0.5f) * 2.3283064365386963e-10f;
+      const float u1 = ((float)p.y + 0.5f) * 2.3283064365386963e-10f;
+      const float u2 = ((float)p.z + 0.5f) * 2.3283064365386963e-10f;
+      const float u3 = ((float)p.w + 0.5f) * 2.3283064365386963e-10f;
+      const float r0 = sqrtf(-2.0f * logf(fmaxf(u0, 1e-30f))), r1 = sqrtf(-2.0f * logf(fmaxf(u2, 1e-30f)));
+      float s0, c0, s1, c1;
+      sincospif(2.0f * u1, &s0, &c0);
+      sincospif(2.0f * u3, &s1, &c1);
+      const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+      for (int j = 0; j < 4; ++j)
+        if (4 * q + j < n) NOISE[4 * q + j] = z[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// policy head, element-wise part (algos/sac1/core.py:45-46,71-87,104-106).  The float32 operation
+// ORDER of the reference graph is kept (separate mul/add, (pi - mu), 1 - pi^2): the graph is
+// ill-conditioned where std << |mu| or |u| is large, and only the same sequence of roundings gives
+// the reference's numbers there.
+// ------------------------------------------------------------------------------------------------
+struct PolEl {
+  float ls_t, log_std, std, u, diff, den, z, pi, omp, clipped;
+};
+__device__ __forceinline__ PolEl policy_elem(float mu, float ls_pre, float eps) {
+  PolEl e;
+  e.ls_t = tanhf(ls_pre);
+  e.log_std = __fadd_rn(-20.0f, __fmul_rn(11.0f, __fadd_rn(e.ls_t, 1.0f)));  // LOG_STD_MIN + 0.5*(MAX-MIN)*(t+1)
+  e.std = expf(e.log_std);
+  e.u = __fadd_rn(mu, __fmul_rn(eps, e.std));                                // pi = mu + noise * std
+  e.diff = __fsub_rn(e.u, mu);
+  e.den = __fadd_rn(e.std, 1e-8f);
+  e.z = __fdiv_rn(e.diff, e.den);
+  e.pi = tanhf(e.u);
+  e.omp = __fsub_rn(1.0f, __fmul_rn(e.pi, e.pi));
+  e.clipped = fminf(fmaxf(e.omp, 0.0f), 1.0f);
+  return e;
+}
+__device__ __forceinline__ float logp_term(const PolEl& e) {
+  // -0.5 * (z^2 + 2 log_std + log(2 pi))  -  log(clip(1 - pi^2, 0, 1) + 1e-6)
+  const float pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)),
+                                               1.8378770664093453f));
+  return __fsub_rn(pre, logf(__fadd_rn(e.clipped, 1e-6f)));
+}
+
+// rows [0,B): pass a = main pi(x); [B,2B): pass b = main pi(x2); [2B,3B): pass c = target pi(x2)
+__global__ void __launch_bounds__(256) k_policy_fwd(int B, int A, float act_scale, const float* __restrict__ HDa,
+                                                    const float* __restrict__ HDb, const float* __restrict__ HDc,
+                                                    const float* __restrict__ NOISE, float* A1, float* A3,
+                                                    float* LOGP1, float* LOGP2) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 3 * B) return;
+  const int pass = g / B, row = g % B;
+  const float* hd = (pass == 0 ? HDa : pass == 1 ? HDb : HDc) + (size_t)row * 2 * A;
+  const float* eps = NOISE + ((size_t)pass * B + row) * A;
+  // reduce_sum over the action axis of the two terms separately, then subtract (core.py:32,86)
+  float gauss = 0.0f, squash = 0.0f;
+  for (int j = 0; j < A; ++j) {
+    const PolEl e = policy_elem(hd[j], hd[A + j], eps[j]);
+    const float pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)),
+                                                 1.8378770664093453f));
+    gauss = __fadd_rn(gauss, pre);
+    squash = __fadd_rn(squash, logf(__fadd_rn(e.clipped, 1e-6f)));
+    if (pass == 0) A1[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
+    else if (pass == 2) A3[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
+  }
+  const float logp = __fsub_rn(gauss, squash);
+  if (pass == 0) LOGP1[row] = logp;
+  else if (pass == 1) LOGP2[row] = logp;
+}
+
+// gradient of pi_loss = mean(alpha*logp1 - q1_pi) wrt the head pre-activations of pass a, by the
+// chain rule of the reference op graph (see DESIGN.md "policy head backward").
+__global__ void __launch_bounds__(256) k_policy_bwd(const StepState* __restrict__ st, int B, int A, float act_scale,
+                                                    const float* __restrict__ HDa, const float* __restrict__ NOISE,
+                                                    const float* __restrict__ dA1, float* dHD) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  const float dlogp = st->alpha_cur / (float)B;
+  const float* hd = HDa + (size_t)row * 2 * A;
+  const float* eps = NOISE + (size_t)row * A;
+  for (int j = 0; j < A; ++j) {
+    const float mu = hd[j];
+    const PolEl e = policy_elem(mu, hd[A + j], eps[j]);
+    // logp -= log(clip_pass(1 - pi^2) + 1e-6):  d/dpi = +2 pi / (clipped + 1e-6) * dlogp
+    const float dpi = act_scale * dA1[(size_t)row * A + j] + dlogp * (2.0f * e.pi) / (e.clipped + 1e-6f);
+    float du = dpi * e.omp;                          // tanh'(u) = 1 - pi^2 (unclipped, as TF's TanhGrad)
+    // gaussian term: pre = -0.5 (z^2 + 2 log_std + c)
+    const float dz = -dlogp * e.z;
+    const float ddiff = dz / e.den;                  // d(pi_raw - mu)
+    du += ddiff;
+    const float dstd_den = -dz * e.z / e.den;        // through the denominator exp(log_std)+EPS
+    const float dmu = (du) - ddiff;                  // pi_raw path + (x - mu) path
+    const float dstd = du * eps[j] + dstd_den;       // pi_raw = mu + eps*std
+    const float dlog_std = dstd * e.std - dlogp;     // exp'  and the direct 2*log_std term
+    const float dls_t = 11.0f * dlog_std;
+    dHD[(size_t)row * 2 * A + j] = dmu;
+    dHD[(size_t)row * 2 * A + A + j] = dls_t * (1.0f - e.ls_t * e.ls_t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses + output-layer gradients (algos/sac1/actor_learner.py:58-69); single CTA, deterministic.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x < 32) {
+    r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) k_losses(StepState* st, int B, float gamma, float lr, float target_entropy,
+                                                 const float* __restrict__ R, const float* __restrict__ DN,
+                                                 const float* __restrict__ LOGP1, const float* __restrict__ LOGP2,
+                                                 const float* __restrict__ Qd, const float* __restrict__ Qe,
+                                                 const float* __restrict__ Qf, const float* __restrict__ Qg,
+                                                 const float* __restrict__ Qh, float* dQd, float* dQe, float* dQf,
+                                                 float* SCAL) {
+  __shared__ double sh[32];
+  const float alpha = st->alpha_cur;
+  const StepDyn& d = st->dyn;
+  const float invB = 1.0f / (float)B;
+  double s_pi = 0.0, s_q1 = 0.0, s_q2 = 0.0, s_lp = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float min_q = fminf(Qg[i], Qh[i]);
+    const float v_backup = __fsub_rn(min_q, __fmul_rn(alpha, LOGP2[i]));
+    const float q_backup = __fadd_rn(R[i], __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.0f, DN[i])), v_backup));
+    const float e1 = __fsub_rn(q_backup, Qd[i]), e2 = __fsub_rn(q_backup, Qe[i]);
+    s_pi += (double)__fsub_rn(__fmul_rn(alpha, LOGP1[i]), Qf[i]);
+    s_q1 += (double)__fmul_rn(e1, e1);
+    s_q2 += (double)__fmul_rn(e2, e2);
+    s_lp += (double)LOGP1[i];
+    dQd[i] = -e1 * invB;
+    dQe[i] = -e2 * invB;
+    dQf[i] = -invB;
+    if (d.out_q1) d.out_q1[i] = Qd[i];
+    if (d.out_q2) d.out_q2[i] = Qe[i];
+    if (d.out_logp) d.out_logp[i] = LOGP1[i];
+  }
+  s_pi = block_sum(s_pi, sh);
+  s_q1 = block_sum(s_q1, sh);
+  s_q2 = block_sum(s_q2, sh);
+  s_lp = block_sum(s_lp, sh);
+  if (threadIdx.x == 0) {
+    const float pi_loss = (float)(s_pi / B), q1_loss = (float)(0.5 * s_q1 / B), q2_loss = (float)(0.5 * s_q2 / B);
+    SCAL[0] = pi_loss; SCAL[1] = q1_loss; SCAL[2] = q2_loss; SCAL[3] = alpha;
+    SCAL[4] = (float)(s_lp / B);     // mean logp1 (alpha gradient, all-reduced across ranks by the host)
+    if (d.out_scalars) {
+      d.out_scalars[0] = pi_loss; d.out_scalars[1] = q1_loss; d.out_scalars[2] = q2_loss; d.out_scalars[3] = alpha;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimiser: TF1 Adam (epsilon-hat form) for pi and q parameter ranges, then polyak with the new
+// weights (actor_learner.py:73-87); gradients arrive as S split-K partials (S = 1 after all-reduce).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const float* __restrict__ Gp, float* G) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    float g = Gp[i];
+    for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
+    G[i] = g;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, int64_t P_pi, int S,
+                                                     const float* __restrict__ Gp, float lr, float polyak,
+                                                     float target_entropy, const float* __restrict__ SCAL,
+                                                     float* W, float* Wt, float* Mo, float* Vo) {
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const double tp = (double)st->t_pi, tq = (double)st->t_q;
+  const float lr_pi = (float)((double)lr * sqrt(1.0 - pow((double)b2, tp)) / (1.0 - pow((double)b1, tp)));
+  const float lr_q = (float)((double)lr * sqrt(1.0 - pow((double)b2, tq)) / (1.0 - pow((double)b1, tq)));
+  const float gs = st->dyn.grad_scale;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    float g = Gp[i];
+    for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
+    g *= gs;
+    const float m = b1 * Mo[i] + (1.0f - b1) * g;
+    const float v = b2 * Vo[i] + (1.0f - b2) * g * g;
+    Mo[i] = m; Vo[i] = v;
+    const float w = W[i] - (i < P_pi ? lr_pi : lr_q) * m / (sqrtf(v) + eps);
+    W[i] = w;
+    Wt[i] = polyak * Wt[i] + (1.0f - polyak) * w;
+  }
+  // entropy-alpha (reference-intended semantics): one scalar Adam step, unordered wrt
+  // the rest; uses the pre-update mean(logp1) of this step.
+  if (blockIdx.x == 0 && threadIdx.x == 0 && st->auto_alpha) {
+    st->t_alpha += 1;
+    const double ta = (double)st->t_alpha;
+    const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
+    const float g = -(SCAL[4] + target_entropy);
+    st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * g;
+    st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * g * g;
+    st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
+  }
+}
+
+// external (TF variable order: kernel, bias per dense layer; mu head then log_std head) <-> internal
+// flat layout.  Only the policy head block differs: internal [h2+1, 2A] = [Wmu|Wls ; bmu|bls].
+__global__ void __launch_bounds__(256) k_convert_layout(int64_t P, int64_t head_off, int h2, int A, int to_internal,
+                                                        const float* __restrict__ src, float* dst, float* dst2) {
+  const int64_t head_sz = (int64_t)(h2 + 1) * 2 * A;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    int64_t j = i;  // i: external index, j: internal index
+    if (i >= head_off && i < head_off + head_sz) {
+      int64_t e = i - head_off;  // external: Wmu [h2,A], bmu [A], Wls [h2,A], bls [A]
+      const int64_t half = (int64_t)h2 * A + A;
+      const int which = e >= half;
+      if (which) e -= half;
+      const int64_t r = e / A, c = e % A;  // r == h2 is the bias row
+      j = head_off + r * 2 * A + which * A + c;
+    }
+    if (to_internal) { const float v = src[i]; dst[j] = v; if (dst2) dst2[j] = v; }
+    else dst[i] = src[j];
+  }
+}
+
+}  // namespace ddrl
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace ddrl;
+
+namespace {
+
+struct Group {
+  int cfg = 0;  // 0: 64x64 tiles, 1: 128x16 tiles
+  std::vector<GemmProb> probs;
+  GemmProb* d_probs = nullptr;
+  int tiles = 0;
+};
+
+struct Plan {
+  int B = 0, S = 1;
+  std::vector<Group> fwd1, fwd2, bwd;  // see build_plan
+  std::vector<std::vector<Group>> stages;  // ordered stages; element-wise kernels sit between them
+  cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr;
+  int64_t kernels[3] = {0, 0, 0};  // kernels inside each captured graph (for the launch counter)
+};
+
+}  // namespace
+
+struct ddrl_sac {
+  int device = 0, D = 0, A = 0, h1 = 0, h2 = 0, maxB = 0, sms = 148;
+  float gamma = 0.99f, polyak = 0.995f, lr = 1e-3f, alpha = 0.2f, act_scale = 1.0f;
+  int auto_alpha = 0;
+  int64_t P = 0, P_pi = 0, P_q = 0;
+  // offsets of the [K+1,N] blocks in the flat buffers
+  int64_t o_pi1 = 0, o_pi2 = 0, o_pih = 0, o_q1[3] = {0, 0, 0}, o_q2[3] = {0, 0, 0};
+  int Smax = 1;
+  float *W = nullptr, *Wt = nullptr, *Mo = nullptr, *Vo = nullptr, *Gp = nullptr, *G = nullptr;
+  StepState* st = nullptr;
+  float* SCAL = nullptr;
+  // batch + activations
+  float *X = nullptr, *X2 = nullptr, *ACT = nullptr, *R = nullptr, *DN = nullptr, *NOISE = nullptr;
+  float *H1[8] = {}, *H2[8] = {}, *HD[3] = {}, *Q[5] = {};  // passes a..h ; heads a..c ; q d..h
+  float *A1 = nullptr, *A3 = nullptr, *LOGP1 = nullptr, *LOGP2 = nullptr;
+  float *dQ[3] = {}, *dZ2[3] = {}, *dZ1[3] = {}, *dA1 = nullptr, *dHD = nullptr, *dZ2a = nullptr, *dZ1a = nullptr;
+  std::vector<void*> allocs;
+  std::map<int, Plan> plans;
+  bool use_graph = true;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy
+                                      // default stream, which cannot be captured); replay on the caller's
+};
+
+namespace {
+
+int dalloc(ddrl_sac* h, float** p, size_t nfloats) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, nfloats * sizeof(float) + 16);
+  if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(%zu floats) failed: %s", nfloats, cudaGetErrorString(e));
+  cudaMemset(q, 0, nfloats * sizeof(float) + 16);
+  h->allocs.push_back(q);
+  *p = (float*)q;
+  return 0;
+}
+
+GemmProb mk(Seg a0, Seg a1, int ones, int a_trans, const float* Bp, int ldb, int b_trans, float* C, int ldc, int M,
+            int N, int K, int epi = EPI_NONE, const float* mask = nullptr, int ldmask = 0) {
+  GemmProb p{};
+  p.a0 = a0; p.a1 = a1; p.a_ones = ones; p.a_trans = a_trans;
+  p.B = Bp; p.ldb = ldb; p.b_trans = b_trans;
+  p.C = C; p.ldc = ldc; p.c_split_stride = 0;
+  p.M = M; p.N = N; p.K = K;
+  p.epi = epi; p.mask = mask; p.ldmask = ldmask;
+  p.splits = 1; p.k_per_split = K;
+  return p;
+}
+Seg seg(const float* p, int ld, int w) { return Seg{p, ld, w}; }
+Seg none() { return Seg{nullptr, 0, 0}; }
+
+int finalize_group(Group& g) {
+  const int BM = g.cfg == 0 ? 64 : 128, BN = g.cfg == 0 ? 64 : 16;
+  int t = 0;
+  for (auto& p : g.probs) {
+    p.tiles_m = (p.M + BM - 1) / BM;
+    p.tiles_n = (p.N + BN - 1) / BN;
+    p.tile_begin = t;
+    t += p.tiles_m * p.tiles_n * p.splits;
+  }
+  g.tiles = t;
+  cudaError_t e = cudaMalloc(&g.d_probs, g.probs.size() * sizeof(GemmProb));
+  if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(plan) failed: %s", cudaGetErrorString(e));
+  e = cudaMemcpy(g.d_probs, g.probs.data(), g.probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaMemcpy(plan) failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int launch_group(const Group& g, cudaStream_t s) {
+  if (g.tiles == 0) return 0;
+  if (g.cfg == 0) gemm_grouped_f32<64, 64, 4, 4><<<g.tiles, 256, 0, s>>>(g.d_probs, (int)g.probs.size());
+  else gemm_grouped_f32<128, 16, 4, 2><<<g.tiles, 256, 0, s>>>(g.d_probs, (int)g.probs.size());
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+// stage indices (element-wise kernels run after the stage listed)
+enum { ST_L1 = 0, ST_L2, ST_HEADS /*-> policy_fwd*/, ST_QL1, ST_QL2, ST_QHEADS /*-> losses*/, ST_B1, ST_B2, ST_B3
+       /*-> policy_bwd*/, ST_P1, ST_P2, ST_P3, ST_COUNT };
+
+void add(std::vector<Group>& stage, const GemmProb& p) {
+  const int cfg = p.N <= 16 ? 1 : 0;
+  for (auto& g : stage)
+    if (g.cfg == cfg) { g.probs.push_back(p); return; }
+  Group g; g.cfg = cfg; g.probs.push_back(p);
+  stage.push_back(g);
+}
+
+int build_plan(ddrl_sac* h, int B, Plan& pl) {
+  const int D = h->D, A = h->A, h1 = h->h1, h2 = h->h2;
+  pl.B = B;
+  const int kps = 256;
+  pl.S = (B + kps - 1) / kps;
+  if (pl.S > h->Smax) return fail(DDRL_EINVAL, "batch %d exceeds max_batch %d", B, h->maxB);
+  pl.stages.assign(ST_COUNT, {});
+  float *W = h->W, *Wt = h->Wt, *Gp = h->Gp;
+  auto wg = [&](GemmProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
+  enum { a = 0, b, c, d, e, f, g, hh };
+  // ---- forward, policies and the two data-action Q passes
+  const float* xin[5] = {h->X, h->X2, h->X2, h->X, h->X};
+  const float* wsrc[5] = {W + h->o_pi1, W + h->o_pi1, Wt + h->o_pi1, W + h->o_q1[0], W + h->o_q2[0]};
+  const float* wsrc2[5] = {W + h->o_pi2, W + h->o_pi2, Wt + h->o_pi2, W + h->o_q1[1], W + h->o_q2[1]};
+  for (int p = 0; p < 5; ++p) {
+    const bool isq = p >= 3;
+    add(pl.stages[ST_L1], mk(seg(xin[p], D, D), isq ? seg(h->ACT, A, A) : none(), 1, 0, wsrc[p], h1, 0, h->H1[p], h1,
+                             B, h1, D + (isq ? A : 0) + 1, EPI_RELU));
+    add(pl.stages[ST_L2], mk(seg(h->H1[p], h1, h1), none(), 1, 0, wsrc2[p], h2, 0, h->H2[p], h2, B, h2, h1 + 1, EPI_RELU));
+  }
+  const float* whead[3] = {W + h->o_pih, W + h->o_pih, Wt + h->o_pih};
+  for (int p = 0; p < 3; ++p)
+    add(pl.stages[ST_HEADS], mk(seg(h->H2[p], h2, h2), none(), 1, 0, whead[p], 2 * A, 0, h->HD[p], 2 * A, B, 2 * A, h2 + 1));
+  add(pl.stages[ST_HEADS], mk(seg(h->H2[d], h2, h2), none(), 1, 0, W + h->o_q1[2], 1, 0, h->Q[0], 1, B, 1, h2 + 1));
+  add(pl.stages[ST_HEADS], mk(seg(h->H2[e], h2, h2), none(), 1, 0, W + h->o_q2[2], 1, 0, h->Q[1], 1, B, 1, h2 + 1));
+  // ---- forward, policy-action Q passes: f = Q1(x,a1), g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3)
+  const float* xin2[3] = {h->X, h->X2, h->X2};
+  const float* ain2[3] = {h->A1, h->A3, h->A3};
+  const float* w1[3] = {W + h->o_q1[0], Wt + h->o_q1[0], Wt + h->o_q2[0]};
+  const float* w2[3] = {W + h->o_q1[1], Wt + h->o_q1[1], Wt + h->o_q2[1]};
+  const float* w3[3] = {W + h->o_q1[2], Wt + h->o_q1[2], Wt + h->o_q2[2]};
+  for (int p = 0; p < 3; ++p) {
+    add(pl.stages[ST_QL1], mk(seg(xin2[p], D, D), seg(ain2[p], A, A), 1, 0, w1[p], h1, 0, h->H1[f + p], h1, B, h1,
+                              D + A + 1, EPI_RELU));
+    add(pl.stages[ST_QL2], mk(seg(h->H1[f + p], h1, h1), none(), 1, 0, w2[p], h2, 0, h->H2[f + p], h2, B, h2, h1 + 1, EPI_RELU));
+    add(pl.stages[ST_QHEADS], mk(seg(h->H2[f + p], h2, h2), none(), 1, 0, w3[p], 1, 0, h->Q[2 + p], 1, B, 1, h2 + 1));
+  }
+  // ---- backward of the three differentiated Q passes: 0 = d (Q1 data), 1 = e (Q2 data), 2 = f (Q1 pi-path)
+  const int pass[3] = {d, e, f};
+  const int64_t* oq[3] = {h->o_q1, h->o_q2, h->o_q1};
+  for (int i = 0; i < 3; ++i) {
+    // dZ2 = dq (x) w3^T  masked by relu'(H2)
+    add(pl.stages[ST_B1], mk(seg(h->dQ[i], 1, 1), none(), 0, 0, W + oq[i][2], 1, 1, h->dZ2[i], h2, B, h2, 1, EPI_MASK,
+                             h->H2[pass[i]], h2));
+    // dZ1 = dZ2 . W2^T  masked by relu'(H1)
+    add(pl.stages[ST_B2], mk(seg(h->dZ2[i], h2, h2), none(), 0, 0, W + oq[i][1], h2, 1, h->dZ1[i], h1, B, h1, h2, EPI_MASK,
+                             h->H1[pass[i]], h1));
+    if (i < 2) {
+      // d[W3;b3] = [H2|1]^T dq ; d[W2;b2] = [H1|1]^T dZ2 ; d[W1;b1] = [x|a|1]^T dZ1
+      add(pl.stages[ST_B1], wg(mk(seg(h->H2[pass[i]], h2, h2), none(), 1, 1, h->dQ[i], 1, 0, Gp + oq[i][2], 1, h2 + 1, 1, B)));
+      add(pl.stages[ST_B2], wg(mk(seg(h->H1[pass[i]], h1, h1), none(), 1, 1, h->dZ2[i], h2, 0, Gp + oq[i][1], h2, h1 + 1, h2, B)));
+      add(pl.stages[ST_B3], wg(mk(seg(h->X, D, D), seg(h->ACT, A, A), 1, 1, h->dZ1[i], h1, 0, Gp + oq[i][0], h1, D + A + 1, h1, B)));
+    }
+  }
+  // dA1 = dZ1(f) . W1q1[D:D+A,:]^T
+  add(pl.stages[ST_B3], mk(seg(h->dZ1[2], h1, h1), none(), 0, 0, W + h->o_q1[0] + (int64_t)D * h1, h1, 1, h->dA1, A, B, A, h1));
+  // ---- policy backward (pass a)
+  add(pl.stages[ST_P1], mk(seg(h->dHD, 2 * A, 2 * A), none(), 0, 0, W + h->o_pih, 2 * A, 1, h->dZ2a, h2, B, h2, 2 * A, EPI_MASK,
+                           h->H2[a], h2));
+  add(pl.stages[ST_P1], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, 2 * A, h2 + 1, 2 * A, B)));
+  add(pl.stages[ST_P2], mk(seg(h->dZ2a, h2, h2), none(), 0, 0, W + h->o_pi2, h2, 1, h->dZ1a, h1, B, h1, h2, EPI_MASK, h->H1[a], h1));
+  add(pl.stages[ST_P2], wg(mk(seg(h->H1[a], h1, h1), none(), 1, 1, h->dZ2a, h2, 0, Gp + h->o_pi2, h2, h1 + 1, h2, B)));
+  add(pl.stages[ST_P3], wg(mk(seg(h->X, D, D), none(), 1, 1, h->dZ1a, h1, 0, Gp + h->o_pi1, h1, D + 1, h1, B)));
+  for (auto& st : pl.stages)
+    for (auto& g2 : st) {
+      int rc = finalize_group(g2);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+int run_stage(const Plan& pl, int s, cudaStream_t st) {
+  for (const auto& g : pl.stages[s]) {
+    int rc = launch_group(g, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+  const int B = pl.B, D = h->D, A = h->A;
+  int rc;
+  {
+    const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
+    int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
+    k_prologue<<<blocks, 256, 0, s>>>(h->st, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN, h->NOISE);
+    DDRL_LAUNCH_CHECK();
+  }
+  if ((rc = run_stage(pl, ST_L1, s))) return rc;
+  if ((rc = run_stage(pl, ST_L2, s))) return rc;
+  if ((rc = run_stage(pl, ST_HEADS, s))) return rc;
+  k_policy_fwd<<<(3 * B + 255) / 256, 256, 0, s>>>(B, A, h->act_scale, h->HD[0], h->HD[1], h->HD[2], h->NOISE, h->A1,
+                                                   h->A3, h->LOGP1, h->LOGP2);
+  DDRL_LAUNCH_CHECK();
+  if ((rc = run_stage(pl, ST_QL1, s))) return rc;
+  if ((rc = run_stage(pl, ST_QL2, s))) return rc;
+  if ((rc = run_stage(pl, ST_QHEADS, s))) return rc;
+  k_losses<<<1, 1024, 0, s>>>(h->st, B, h->gamma, h->lr, -(float)A, h->R, h->DN, h->LOGP1, h->LOGP2, h->Q[0], h->Q[1],
+                              h->Q[2], h->Q[3], h->Q[4], h->dQ[0], h->dQ[1], h->dQ[2], h->SCAL);
+  DDRL_LAUNCH_CHECK();
+  if ((rc = run_stage(pl, ST_B1, s))) return rc;
+  if ((rc = run_stage(pl, ST_B2, s))) return rc;
+  if ((rc = run_stage(pl, ST_B3, s))) return rc;
+  k_policy_bwd<<<(B + 255) / 256, 256, 0, s>>>(h->st, B, A, h->act_scale, h->HD[0], h->NOISE, h->dA1, h->dHD);
+  DDRL_LAUNCH_CHECK();
+  if ((rc = run_stage(pl, ST_P1, s))) return rc;
+  if ((rc = run_stage(pl, ST_P2, s))) return rc;
+  if ((rc = run_stage(pl, ST_P3, s))) return rc;
+  return 0;
+}
+
+int enqueue_reduce(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+  k_grad_reduce<<<blocks, 256, 0, s>>>(h->P, pl.S, h->Gp, h->G);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s) {
+  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+  k_adam_polyak<<<blocks, 256, 0, s>>>(h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak, -(float)h->A, h->SCAL, h->W,
+                                       h->Wt, h->Mo, h->Vo);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+enum { MODE_FULL = 0, MODE_GRADS = 1, MODE_APPLY = 2 };
+
+int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
+  int rc = 0;
+  if (mode == MODE_FULL) {
+    if ((rc = enqueue_grads(h, pl, s))) return rc;
+    return enqueue_apply(h, pl.S, h->Gp, s);
+  }
+  if (mode == MODE_GRADS) {
+    if ((rc = enqueue_grads(h, pl, s))) return rc;
+    return enqueue_reduce(h, pl, s);
+  }
+  return enqueue_apply(h, 1, h->G, s);
+}
+
+int run_mode(ddrl_sac* h, Plan& pl, int mode, cudaStream_t s) {
+  cudaGraphExec_t* slot = mode == MODE_FULL ? &pl.exec_full : mode == MODE_GRADS ? &pl.exec_grads : &pl.exec_apply;
+  if (!h->use_graph) return enqueue_mode(h, pl, mode, s);
+  if (!*slot) {
+    cudaGraph_t graph = nullptr;
+    if (!h->cap_stream) DDRL_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const int64_t before = g_launches.load();
+    DDRL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_mode(h, pl, mode, h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    pl.kernels[mode] = g_launches.load() - before;
+    g_launches.store(before);  // captured, not executed
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(slot, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  }
+  DDRL_CUDA(cudaGraphLaunch(*slot, s));
+  g_launches.fetch_add(pl.kernels[mode], std::memory_order_relaxed);
+  return 0;
+}
+
+int get_plan(ddrl_sac* h, int B, Plan** out) {
+  auto it = h->plans.find(B);
+  if (it == h->plans.end()) {
+    Plan pl;
+    int rc = build_plan(h, B, pl);
+    if (rc) return rc;
+    it = h->plans.emplace(B, std::move(pl)).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int max_batch, float gamma, float polyak,
+                    float lr, float alpha, float act_scale, ddrl_sac_t* out) {
+  if (!out) return fail(DDRL_EINVAL, "ddrl_sac_create: out is NULL");
+  *out = nullptr;
+  if (obs_dim < 1 || act_dim < 1 || h1 < 1 || h2 < 1 || max_batch < 1)
+    return fail(DDRL_EINVAL, "ddrl_sac_create: obs_dim, act_dim, h1, h2, max_batch must be >= 1");
+  int ndev = 0;
+  DDRL_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DDRL_EINVAL, "ddrl_sac_create: device %d out of range", device);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DDRL_ECUDA, "ddrl_sac_create: cannot select device %d", device);
+  ddrl_sac* h = new ddrl_sac();
+  h->device = device; h->D = obs_dim; h->A = act_dim; h->h1 = h1; h->h2 = h2; h->maxB = max_batch;
+  h->gamma = gamma; h->polyak = polyak; h->lr = lr; h->act_scale = act_scale;
+  h->auto_alpha = alpha < 0.0f; h->alpha = alpha;
+  h->sms = sm_count(device);
+  const char* ng = getenv("DDRL_NO_GRAPH");
+  h->use_graph = !(ng && ng[0] == '1');
+  const int D = obs_dim, A = act_dim;
+  int64_t o = 0;
+  h->o_pi1 = o; o += (int64_t)(D + 1) * h1;
+  h->o_pi2 = o; o += (int64_t)(h1 + 1) * h2;
+  h->o_pih = o; o += (int64_t)(h2 + 1) * 2 * A;
+  h->P_pi = o;
+  for (int q = 0; q < 2; ++q) {
+    int64_t* oq = q == 0 ? h->o_q1 : h->o_q2;
+    oq[0] = o; o += (int64_t)(D + A + 1) * h1;
+    oq[1] = o; o += (int64_t)(h1 + 1) * h2;
+    oq[2] = o; o += (int64_t)(h2 + 1);
+  }
+  h->P = o; h->P_q = (o - h->P_pi) / 2;
+  h->Smax = (max_batch + 255) / 256;
+  int rc = 0;
+  const size_t P = (size_t)h->P, M = (size_t)max_batch;
+  auto A_ = [&](float** p, size_t n) { if (!rc) rc = dalloc(h, p, n); };
+  A_(&h->W, P); A_(&h->Wt, P); A_(&h->Mo, P); A_(&h->Vo, P); A_(&h->G, P); A_(&h->Gp, P * h->Smax);
+  A_(&h->SCAL, 8);
+  A_(&h->X, M * D); A_(&h->X2, M * D); A_(&h->ACT, M * A); A_(&h->R, M); A_(&h->DN, M); A_(&h->NOISE, 3 * M * A + 4);
+  for (int p = 0; p < 8; ++p) { A_(&h->H1[p], M * h1); A_(&h->H2[p], M * h2); }
+  for (int p = 0; p < 3; ++p) A_(&h->HD[p], M * 2 * A);
+  for (int p = 0; p < 5; ++p) A_(&h->Q[p], M);
+  A_(&h->A1, M * A); A_(&h->A3, M * A); A_(&h->LOGP1, M); A_(&h->LOGP2, M);
+  for (int p = 0; p < 3; ++p) { A_(&h->dQ[p], M); A_(&h->dZ2[p], M * h2); A_(&h->dZ1[p], M * h1); }
+  A_(&h->dA1, M * A); A_(&h->dHD, M * 2 * A); A_(&h->dZ2a, M * h2); A_(&h->dZ1a, M * h1);
+  float* stp = nullptr;
+  A_(&stp, (sizeof(StepState) + 3) / 4);
+  if (rc) { ddrl_sac_destroy(h); return rc; }
+  h->st = reinterpret_cast<StepState*>(stp);
+  StepState init{};
+  init.auto_alpha = h->auto_alpha;
+  init.alpha_const = alpha;
+  init.alpha_cur = h->auto_alpha ? 1.0f : alpha;
+  cudaError_t e = cudaMemcpy(h->st, &init, sizeof(init), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { ddrl_sac_destroy(h); return fail(DDRL_ECUDA, "init state: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return 0;
+}
+
+int ddrl_sac_destroy(ddrl_sac_t h) {
+  if (!h) return 0;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->plans) {
+    Plan& pl = kv.second;
+    for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply}) if (ex) cudaGraphExecDestroy(ex);
+    for (auto& st : pl.stages) for (auto& g : st) if (g.d_probs) cudaFree(g.d_probs);
+  }
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  delete h;
+  return 0;
+}
+
+int64_t ddrl_sac_param_count(ddrl_sac_t h) { return h ? h->P : -1; }
+
+int ddrl_sac_set_weights(ddrl_sac_t h, const float* d_flat, int also_target, void* stream) {
+  if (!h || !d_flat) return fail(DDRL_EINVAL, "ddrl_sac_set_weights: NULL argument");
+  DeviceGuard guard(h->device);
+  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+  k_convert_layout<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->P, h->o_pih, h->h2, h->A, 1, d_flat, h->W,
+                                                             also_target ? h->Wt : nullptr);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ddrl_sac_get_weights(ddrl_sac_t h, float* d_flat, int which, void* stream) {
+  if (!h || !d_flat) return fail(DDRL_EINVAL, "ddrl_sac_get_weights: NULL argument");
+  const float* src = which == 0 ? h->W : which == 1 ? h->Wt : which == 2 ? h->Mo : which == 3 ? h->Vo : which == 4 ? h->G : nullptr;
+  if (!src) return fail(DDRL_EINVAL, "ddrl_sac_get_weights: which=%d not in 0..4", which);
+  DeviceGuard guard(h->device);
+  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+  k_convert_layout<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->P, h->o_pih, h->h2, h->A, 0, src, d_flat, nullptr);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+static int step_common(ddrl_sac_t h, int mode, const float* d_obs1, const float* d_obs2, const float* d_acts,
+                       const float* d_rews, const float* d_done, int batch, const float* d_noise, uint64_t seed,
+                       float grad_scale, float* d_out_scalars, float* d_out_q1, float* d_out_q2, float* d_out_logp,
+                       void* stream, const char* who) {
+  if (!h) return fail(DDRL_EINVAL, "%s: NULL handle", who);
+  if (batch < 1 || batch > h->maxB) return fail(DDRL_EINVAL, "%s: batch=%d not in [1, %d]", who, batch, h->maxB);
+  if (mode != MODE_APPLY && (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done))
+    return fail(DDRL_EINVAL, "%s: NULL batch array", who);
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  if (mode != MODE_APPLY) {
+    StepDyn dyn{};
+    dyn.obs1 = d_obs1; dyn.obs2 = d_obs2; dyn.acts = d_acts; dyn.rews = d_rews; dyn.done = d_done;
+    dyn.noise = d_noise;
+    dyn.out_scalars = d_out_scalars; dyn.out_q1 = d_out_q1; dyn.out_q2 = d_out_q2; dyn.out_logp = d_out_logp;
+    dyn.seed = seed; dyn.grad_scale = grad_scale;
+    k_set_params<<<1, 1, 0, s>>>(h->st, dyn, 1);
+    DDRL_LAUNCH_CHECK();
+  }
+  return run_mode(h, *pl, mode, s);
+}
+
+int ddrl_sac_step(ddrl_sac_t h, const float* d_obs1, const float* d_obs2, const float* d_acts, const float* d_rews,
+                  const float* d_done, int batch, const float* d_noise, uint64_t seed, float* d_out_scalars,
+                  float* d_out_q1, float* d_out_q2, float* d_out_logp, void* stream) {
+  return step_common(h, MODE_FULL, d_obs1, d_obs2, d_acts, d_rews, d_done, batch, d_noise, seed, 1.0f, d_out_scalars,
+                     d_out_q1, d_out_q2, d_out_logp, stream, "ddrl_sac_step");
+}
+
+int ddrl_sac_compute_grads(ddrl_sac_t h, const float* d_obs1, const float* d_obs2, const float* d_acts,
+                           const float* d_rews, const float* d_done, int batch, const float* d_noise, uint64_t seed,
+                           float grad_scale, float* d_out_scalars, float* d_out_q1, float* d_out_q2, float* d_out_logp,
+                           void* stream) {
+  return step_common(h, MODE_GRADS, d_obs1, d_obs2, d_acts, d_rews, d_done, batch, d_noise, seed, grad_scale,
+                     d_out_scalars, d_out_q1, d_out_q2, d_out_logp, stream, "ddrl_sac_compute_grads");
+}
+
+int ddrl_sac_grad_buffer(ddrl_sac_t h, float** d_grads, int64_t* count, float** d_alpha_stat) {
+  if (!h) return fail(DDRL_EINVAL, "ddrl_sac_grad_buffer: NULL handle");
+  if (d_grads) *d_grads = h->G;
+  if (count) *count = h->P;
+  if (d_alpha_stat) *d_alpha_stat = h->SCAL + 4;
+  return 0;
+}
+
+int ddrl_sac_apply_grads(ddrl_sac_t h, int batch, void* stream) {
+  return step_common(h, MODE_APPLY, nullptr, nullptr, nullptr, nullptr, nullptr, batch, nullptr, 0, 1.0f, nullptr,
+                     nullptr, nullptr, nullptr, stream, "ddrl_sac_apply_grads");
+}
+
+int ddrl_sac_state(ddrl_sac_t h, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream) {
+  if (!h) return fail(DDRL_EINVAL, "ddrl_sac_state: NULL handle");
+  DeviceGuard guard(h->device);
+  StepState s{};
+  DDRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  DDRL_CUDA(cudaMemcpy(&s, h->st, sizeof(s), cudaMemcpyDeviceToHost));
+  if (t_pi) *t_pi = s.t_pi;
+  if (t_q) *t_q = s.t_q;
+  if (t_alpha) *t_alpha = s.t_alpha;
+  if (log_alpha) *log_alpha = s.log_alpha;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// sac_gemm.cuh — grouped fp32 GEMM used by the SAC1 learner step (parity mode: plain FFMA, no
+// TF32/bf16 rounding, so losses and updated weights stay within 1e-5 of the float64 oracle).
+//
+// One launch executes a GROUP of independent problems  C = epi( opA · opB )  (the 3 policy passes,
+// 5 Q passes, or the dgrad/wgrad set of one backward level), each described by a GemmProb.
+//   - A is always stored [batch, features] row-major and may be a VIRTUAL CONCAT of two tensors
+//     plus a constant-one column:  A = [ a0 | a1 | 1 ].  The one column turns the bias into the last
+//     row of the weight block, so every layer's parameters are one contiguous [K+1, N] block
+//     (kernel rows, then the bias row) and  dense(x) = [x|1] · [W;b],  d[W;b] = [x|1]^T · dZ.
+//     a_trans = 0 : opA = A        (forward / dgrad:  M = batch,     K = features)
+//     a_trans = 1 : opA = A^T      (wgrad:            M = features,  K = batch; optional split-K)
+//   - B is row-major [K,N] (b_trans = 0) or stored [N,K] (b_trans = 1: dgrad against W^T).
+//   - epilogue: none | relu | multiply by (mask > 0)   (relu backward).
+#pragma once
+#include "common.cuh"
+
+namespace ddrl {
+
+struct Seg {
+  const float* p;
+  int ld;
+  int w;
+};
+
+enum Epi : int { EPI_NONE = 0, EPI_RELU = 1, EPI_MASK = 2 };
+
+struct GemmProb {
+  Seg a0, a1;
+  int a_ones;
+  int a_trans;
+  const float* B;
+  int ldb;
+  int b_trans;
+  float* C;
+  int ldc;
+  long long c_split_stride;  // floats between split-K partial outputs
+  int M, N, K;
+  int epi;
+  const float* mask;
+  int ldmask;
+  int splits, k_per_split;
+  int tiles_m, tiles_n, tile_begin;
+};
+
+__device__ __forceinline__ float fetch_a(const GemmProb& P, int row, int feat) {
+  if (feat < P.a0.w) return P.a0.p[(size_t)row * P.a0.ld + feat];
+  feat -= P.a0.w;
+  if (feat < P.a1.w) return P.a1.p[(size_t)row * P.a1.ld + feat];
+  return (P.a_ones && feat == P.a1.w) ? 1.0f : 0.0f;
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) gemm_grouped_f32(const GemmProb* __restrict__ probs, int nprob) {
+  constexpr int BK = 16;
+  constexpr int TX = BN / TN;
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads per tile");
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ GemmProb P;
+
+  const int tid = threadIdx.x;
+  {
+    int pi = 0;
+    const int tile = blockIdx.x;
+    while (pi + 1 < nprob && tile >= probs[pi + 1].tile_begin) ++pi;
+    // cooperative copy of the descriptor into shared memory
+    const int* src = reinterpret_cast<const int*>(probs + pi);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = tid; i < (int)(sizeof(GemmProb) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+
+  int t = blockIdx.x - P.tile_begin;
+  const int per_split = P.tiles_m * P.tiles_n;
+  const int split = t / per_split;
+  t -= split * per_split;
+  const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
+  const int kbeg = split * P.k_per_split;
+  const int kend = min(P.K, kbeg + P.k_per_split);
+  const int tx = tid % TX, ty = tid / TX;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    if (!P.a_trans) {
+      for (int i = tid; i < BM * BK; i += 256) {
+        const int kl = i % BK, ml = i / BK;
+        const int m = m0 + ml, k = k0 + kl;
+        As[kl][ml] = (m < P.M && k < kend) ? fetch_a(P, m, k) : 0.0f;
+      }
+    } else {
+      for (int i = tid; i < BM * BK; i += 256) {
+        const int ml = i % BM, kl = i / BM;
+        const int m = m0 + ml, k = k0 + kl;
+        As[kl][ml] = (m < P.M && k < kend) ? fetch_a(P, k, m) : 0.0f;
+      }
+    }
+    if (!P.b_trans) {
+      for (int i = tid; i < BN * BK; i += 256) {
+        const int nl = i % BN, kl = i / BN;
+        const int n = n0 + nl, k = k0 + kl;
+        Bs[kl][nl] = (n < P.N && k < kend) ? P.B[(size_t)k * P.ldb + n] : 0.0f;
+      }
+    } else {
+      for (int i = tid; i < BN * BK; i += 256) {
+        const int kl = i % BK, nl = i / BK;
+        const int n = n0 + nl, k = k0 + kl;
+        Bs[kl][nl] = (n < P.N && k < kend) ? P.B[(size_t)n * P.ldb + k] : 0.0f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  float* C = P.C + (size_t)split * P.c_split_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= P.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= P.N) continue;
+      float v = acc[i][j];
+      if (P.epi == EPI_RELU) v = fmaxf(v, 0.0f);
+      else if (P.epi == EPI_MASK) v = (P.mask[(size_t)m * P.ldmask + n] > 0.0f) ? v : 0.0f;
+      C[(size_t)m * P.ldc + n] = v;
+    }
+  }
+}
+
+}  // namespace ddrl

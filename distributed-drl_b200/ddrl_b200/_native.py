@@ -25,6 +25,7 @@ _lib = None
 
 _vp, _i64, _u64, _u32, _int = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int
 _pi64, _pint = C.POINTER(C.c_int64), C.POINTER(C.c_int)
+_f, _pf = C.c_float, C.POINTER(C.c_float)
 
 # name -> (restype, argtypes).  Kept in one table so tests can check it against the header.
 SIGNATURES = {
@@ -42,6 +43,16 @@ SIGNATURES = {
     "ddrl_rb_layout": (_int, [_vp, _pint, _pint, _pint, C.POINTER(_vp)]),
     "ddrl_rb_export": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ddrl_rb_import": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "ddrl_sac_create": (_int, [_int, _int, _int, _int, _int, _int, _f, _f, _f, _f, _f, C.POINTER(_vp)]),
+    "ddrl_sac_destroy": (_int, [_vp]),
+    "ddrl_sac_param_count": (_i64, [_vp]),
+    "ddrl_sac_set_weights": (_int, [_vp, _vp, _int, _vp]),
+    "ddrl_sac_get_weights": (_int, [_vp, _vp, _int, _vp]),
+    "ddrl_sac_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_sac_compute_grads": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _u64, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_sac_grad_buffer": (_int, [_vp, C.POINTER(_vp), _pi64, C.POINTER(_vp)]),
+    "ddrl_sac_apply_grads": (_int, [_vp, _int, _vp]),
+    "ddrl_sac_state": (_int, [_vp, _pint, _pint, _pint, _pf, _vp]),
 }
 
 

@@ -1,0 +1,292 @@
+"""Learner — the reference's SAC1 learner API over the CUDA step in libddrl_b200 (csrc/sac.cu).
+
+Mirrors algos/sac1/actor_learner.py:
+    Learner(opt, job)                  :20-123   (opt fields read: seed, obs_dim, act_dim,
+                                                   ac_kwargs["action_space"].high[0], alpha, gamma, lr, polyak)
+    .train(batch)                      :135-142  one sess.run(step_ops)
+    .get_weights() -> (keys, values)   :129-133  all "main" variables, TF1 names
+    .set_weights(keys, values)         :125-127  assign + target_init
+and example/model.py's Model(args).train(replay_buffer, args) (:92-101).
+
+Additions: hidden sizes are a parameter (opt.ac_kwargs["hidden_sizes"], default core.py:91's
+(400, 300)); batches may already be on the GPU (ReplayBuffer.sample_batch(device=True)); with
+torch.distributed initialised the step becomes data-parallel (gradient all-reduce over NCCL between
+the backward and the optimiser), which the reference stubs out (:144-148).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_KEYS_BATCH = ("obs1", "obs2", "acts", "rews", "done")
+
+
+def param_names():
+    """TF1 variable names in creation order (tf.layers.dense default naming inside the
+    main/pi, main/q1, main/q2 scopes): dense_2 is the mu head, dense_3 the log_std head."""
+    names = []
+    for suffix in ("dense", "dense_1", "dense_2", "dense_3"):
+        names += [f"main/pi/{suffix}/kernel", f"main/pi/{suffix}/bias"]
+    for q in ("q1", "q2"):
+        for suffix in ("dense", "dense_1", "dense_2"):
+            names += [f"main/{q}/{suffix}/kernel", f"main/{q}/{suffix}/bias"]
+    return names
+
+
+def param_shapes(obs_dim, act_dim, hidden):
+    h1, h2 = hidden
+    D, A = int(obs_dim), int(act_dim)
+    pi = [(D, h1), (h1,), (h1, h2), (h2,), (h2, A), (A,), (h2, A), (A,)]
+    q = [(D + A, h1), (h1,), (h1, h2), (h2,), (h2, 1), (1,)]
+    return OrderedDict(zip(param_names(), pi + q + q))
+
+
+def glorot_init(obs_dim, act_dim, hidden, seed):
+    """tf.layers.dense defaults: glorot_uniform kernels, zero biases (one-off, host side)."""
+    g = np.random.Generator(np.random.PCG64(int(seed)))
+    out = OrderedDict()
+    for n, s in param_shapes(obs_dim, act_dim, hidden).items():
+        if len(s) == 2:
+            lim = math.sqrt(6.0 / (s[0] + s[1]))
+            out[n] = g.uniform(-lim, lim, s).astype(np.float32)
+        else:
+            out[n] = np.zeros(s, dtype=np.float32)
+    return out
+
+
+class _DevPtr:
+    """Zero-copy torch view of a device buffer owned by the native handle."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _opt_get(opt, name, default=None):
+    if isinstance(opt, dict):
+        return opt.get(name, default)
+    return getattr(opt, name, default)
+
+
+class Learner(object):
+    def __init__(self, opt, job="learner", *, device=None, max_batch=None, process_group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ddrl_b200.Learner needs a CUDA device (no CPU fallback)")
+        self.opt = opt
+        self.job = job
+        self._lib = N.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._dev = torch.device("cuda", self.device)
+        ac = _opt_get(opt, "ac_kwargs", {}) or {}
+        self.obs_dim, self.act_dim = int(_opt_get(opt, "obs_dim")), int(_opt_get(opt, "act_dim"))
+        self.hidden = tuple(int(h) for h in ac.get("hidden_sizes", (400, 300)))
+        if len(self.hidden) != 2:
+            raise ValueError("two hidden layers (the reference's mlp_actor_critic shape) are supported")
+        space = ac.get("action_space", None)
+        self.act_scale = float(space.high[0]) if space is not None else float(_opt_get(opt, "act_scale", 1.0))
+        alpha = _opt_get(opt, "alpha", 0.2)
+        self.auto_alpha = alpha == "auto"
+        self.alpha = -1.0 if self.auto_alpha else float(alpha)
+        gamma = _opt_get(opt, "gamma", 0.99)
+        if isinstance(gamma, (tuple, list)):      # example/dsac.py:198's trailing comma makes gamma a tuple
+            gamma = gamma[0]
+        self.gamma, self.polyak, self.lr = float(gamma), float(_opt_get(opt, "polyak", 0.995)), float(_opt_get(opt, "lr", 1e-3))
+        self.seed = int(_opt_get(opt, "seed", 0) or 0)
+        self.max_batch = int(max_batch or _opt_get(opt, "batch_size", 256) or 256)
+        h = C.c_void_p()
+        N.check(self._lib.ddrl_sac_create(self.device, self.obs_dim, self.act_dim, self.hidden[0], self.hidden[1],
+                                          self.max_batch, self.gamma, self.polyak, self.lr, self.alpha,
+                                          self.act_scale, C.byref(h)))
+        self._h = h
+        self.names = param_names()
+        self.shapes = param_shapes(self.obs_dim, self.act_dim, self.hidden)
+        self.P = int(self._lib.ddrl_sac_param_count(self._h))
+        assert self.P == sum(int(np.prod(s)) for s in self.shapes.values())
+        gp, cnt, ap = C.c_void_p(), C.c_int64(), C.c_void_p()
+        N.check(self._lib.ddrl_sac_grad_buffer(self._h, C.byref(gp), C.byref(cnt), C.byref(ap)))
+        self._grad = torch.as_tensor(_DevPtr(gp.value, int(cnt.value)), device=self._dev)
+        self._alpha_stat = torch.as_tensor(_DevPtr(ap.value, 1), device=self._dev)
+        self._pg = process_group
+        self._outs = None
+        self._stage = {}
+        self.steps = 0
+        init = glorot_init(self.obs_dim, self.act_dim, self.hidden, self.seed)
+        self.set_weights(list(init.keys()), list(init.values()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.ddrl_sac_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device)
+
+    def _world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self._pg)
+        return 1
+
+    # ---- weights -------------------------------------------------------------------------------
+    def _flat_from(self, keys, values):
+        """flat float32 vector in canonical order, starting from the current weights so that a
+        subset of keys can be assigned (the reference assigns by name)."""
+        given = dict(zip(keys, values))
+        unknown = [k for k in given if k not in self.shapes]
+        if unknown:
+            raise KeyError(f"unknown variable names {unknown[:3]}")
+        if len(given) == len(self.names):
+            base = None
+        else:
+            base = self.get_flat_weights().cpu().numpy()
+        parts, o = [], 0
+        for n in self.names:
+            size = int(np.prod(self.shapes[n]))
+            if n in given:
+                v = given[n]
+                v = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+                if tuple(v.shape) != tuple(self.shapes[n]):
+                    raise ValueError(f"{n}: shape {v.shape} != {self.shapes[n]}")
+                parts.append(np.ascontiguousarray(v, dtype=np.float32).reshape(-1))
+            else:
+                parts.append(base[o:o + size])
+            o += size
+        return np.concatenate(parts)
+
+    def set_weights(self, variable_names, weights):
+        flat = torch.from_numpy(self._flat_from(variable_names, weights)).to(self._dev)
+        self.set_flat_weights(flat)
+
+    def set_flat_weights(self, flat, also_target=True):
+        """flat: CUDA float32 [P] in canonical order (device-to-device; used by the NCCL parameter
+        broadcast).  Re-initialises the target like the reference's set_weights."""
+        flat = flat.to(self._dev, torch.float32).contiguous()
+        assert flat.numel() == self.P
+        s = self._stream()
+        N.check(self._lib.ddrl_sac_set_weights(self._h, C.c_void_p(flat.data_ptr()), 1 if also_target else 0,
+                                               C.c_void_p(s.cuda_stream)))
+        flat.record_stream(s)
+
+    def get_flat_weights(self, which="main"):
+        code = {"main": 0, "target": 1, "adam_m": 2, "adam_v": 3, "grad": 4}[which]
+        out = torch.empty(self.P, dtype=torch.float32, device=self._dev)
+        N.check(self._lib.ddrl_sac_get_weights(self._h, C.c_void_p(out.data_ptr()), code,
+                                               C.c_void_p(self._stream().cuda_stream)))
+        return out
+
+    def _split(self, flat_np):
+        vals, o = [], 0
+        for n in self.names:
+            size = int(np.prod(self.shapes[n]))
+            vals.append(flat_np[o:o + size].reshape(self.shapes[n]).copy())
+            o += size
+        return vals
+
+    def get_weights(self):
+        flat = self.get_flat_weights("main").cpu().numpy()
+        return list(self.names), self._split(flat)
+
+    def get_target_weights(self):
+        return list(self.names), self._split(self.get_flat_weights("target").cpu().numpy())
+
+    # ---- training ------------------------------------------------------------------------------
+    def _to_device(self, batch):
+        """numpy batches go through pinned staging (one H2D per array); CUDA tensors pass through."""
+        out = []
+        s = self._stream()
+        for k in _KEYS_BATCH:
+            v = batch[k]
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                out.append(v.to(torch.float32).contiguous())
+                continue
+            a = v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            key = (k, a.shape)
+            st = self._stage.get(key)
+            if st is None:
+                st = (torch.empty(a.shape, dtype=torch.float32, pin_memory=True),
+                      torch.empty(a.shape, dtype=torch.float32, device=self._dev), [None])
+                self._stage[key] = st
+            pin, dev, ev = st
+            if ev[0] is not None:
+                ev[0].synchronize()
+            pin.numpy()[...] = a
+            dev.copy_(pin, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(s)
+            ev[0] = e
+            out.append(dev)
+        return out
+
+    def train(self, batch, noise=None, sync_outputs=False, split=False):
+        """One SAC1 update on `batch` (dict obs1/obs2/acts/rews/done).  `noise` ([3,B,A]) injects the
+        three normal draws (parity tests); default: drawn on the GPU.  Returns the reference's fetch
+        list as a dict of CUDA tensors (pi_loss, q1_loss, q2_loss, alpha in `scalars`; q1, q2,
+        logp_pi), valid until the next call, without synchronising."""
+        x, x2, a, r, d = self._to_device(batch)
+        B = int(r.shape[0])
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch} (pass max_batch= to Learner)")
+        if self._outs is None or self._outs["q1"].shape[0] != B:
+            f = dict(dtype=torch.float32, device=self._dev)
+            self._outs = dict(scalars=torch.zeros(4, **f), q1=torch.empty(B, **f), q2=torch.empty(B, **f),
+                              logp_pi=torch.empty(B, **f))
+        o = self._outs
+        nz = None
+        if noise is not None:
+            nz = torch.as_tensor(noise, dtype=torch.float32).to(self._dev).contiguous()
+            assert tuple(nz.shape) == (3, B, self.act_dim)
+        s = self._stream()
+        sp = C.c_void_p(s.cuda_stream)
+        args = [C.c_void_p(t.data_ptr()) for t in (x, x2, a, r, d)]
+        nzp = C.c_void_p(nz.data_ptr()) if nz is not None else None
+        outs = [C.c_void_p(o[k].data_ptr()) for k in ("scalars", "q1", "q2", "logp_pi")]
+        world = self._world()
+        if world == 1 and split:       # same arithmetic through the data-parallel entry points
+            N.check(self._lib.ddrl_sac_compute_grads(self._h, *args, B, nzp, self.seed, 1.0, *outs, sp))
+            N.check(self._lib.ddrl_sac_apply_grads(self._h, B, sp))
+        elif world == 1:
+            N.check(self._lib.ddrl_sac_step(self._h, *args, B, nzp, self.seed, *outs, sp))
+        else:
+            import torch.distributed as dist
+            N.check(self._lib.ddrl_sac_compute_grads(self._h, *args, B, nzp, self.seed, 1.0 / world, *outs, sp))
+            dist.all_reduce(self._grad, op=dist.ReduceOp.SUM, group=self._pg)
+            if self.auto_alpha:
+                dist.all_reduce(self._alpha_stat, op=dist.ReduceOp.SUM, group=self._pg)
+                self._alpha_stat.div_(world)
+            N.check(self._lib.ddrl_sac_apply_grads(self._h, B, sp))
+        for t in (x, x2, a, r, d):
+            t.record_stream(s)
+        if nz is not None:
+            nz.record_stream(s)
+        self.steps += 1
+        if sync_outputs:
+            s.synchronize()
+        return o
+
+    def train_from_buffer(self, replay_buffer, batch_size):
+        """sample_batch + train without the batch leaving the GPU (example/model.py:92-101's
+        Model.train(replay_buffer, args) shape)."""
+        return self.train(replay_buffer.sample_batch(batch_size, device=True))
+
+    def state(self):
+        t_pi, t_q, t_a, la = C.c_int(), C.c_int(), C.c_int(), C.c_float()
+        N.check(self._lib.ddrl_sac_state(self._h, C.byref(t_pi), C.byref(t_q), C.byref(t_a), C.byref(la),
+                                         C.c_void_p(self._stream().cuda_stream)))
+        return dict(t_pi=t_pi.value, t_q=t_q.value, t_alpha=t_a.value, log_alpha=la.value)
+
+    # reference stubs (actor_learner.py:144-148)
+    def compute_gradients(self, x, y):
+        pass
+
+    def apply_gradients(self, gradients):
+        pass

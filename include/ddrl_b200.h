@@ -120,6 +120,60 @@ int ddrl_rb_import(ddrl_rb_t rb, const float* d_obs1, const float* d_obs2, const
                    const float* d_rews, const float* d_done, int64_t ptr, int64_t size,
                    int64_t steps, int64_t sample_times, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SAC1 learner — replaces Learner (algos/sac1/actor_learner.py:19-148; nets algos/sac1/core.py:15-121)
+ *
+ * All state (main / target weights, Adam moments, gradients, activations) is device-resident in
+ * flat fp32 buffers.  "flat" weight vectors exchanged through this API are in the reference's
+ * variable order  main/pi/dense{,_1,_2,_3}/{kernel,bias}, main/q1/dense{,_1,_2}/{kernel,bias},
+ * main/q2/...  (kernel [in,out] row-major, then bias), P = ddrl_sac_param_count() floats.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ddrl_sac* ddrl_sac_t;
+
+/* Learner.__init__ (actor_learner.py:20-123).  hidden sizes (h1,h2) are parameters (the reference
+ * hard-wires core.py:91's (400,300) default); alpha < 0 selects the entropy-alpha ('auto') branch
+ * (actor_learner.py:46-55, reference-intended semantics); act_scale = action_space.high[0]
+ * (core.py:104-106).  Buffers are sized for batches up to max_batch.  Weights start at zero: call
+ * ddrl_sac_set_weights. */
+int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int max_batch, float gamma,
+                    float polyak, float lr, float alpha, float act_scale, ddrl_sac_t* out);
+int ddrl_sac_destroy(ddrl_sac_t sac);
+int64_t ddrl_sac_param_count(ddrl_sac_t sac);
+
+/* Learner.set_weights (actor_learner.py:125-127): assign main weights; also_target != 0 runs
+ * target_init (target <- main), which the reference always does for the Learner. */
+int ddrl_sac_set_weights(ddrl_sac_t sac, const float* d_flat, int also_target, void* stream);
+/* Learner.get_weights (actor_learner.py:129-133) for which = 0 (main); 1 = target, 2 = Adam m,
+ * 3 = Adam v, 4 = last reduced gradient (diagnostics / parity tests). */
+int ddrl_sac_get_weights(ddrl_sac_t sac, float* d_flat, int which, void* stream);
+
+/* Learner.train(batch) (actor_learner.py:135-142) = one sess.run(step_ops): forward, both losses,
+ * backward, Adam(pi), Adam(q), polyak (and the alpha step in 'auto' mode), replayed as one CUDA
+ * graph.  Batch arrays are the ReplayBuffer.sample_batch dict ([B,D],[B,D],[B,A],[B],[B] f32).
+ * d_noise: the three N(0,1) draws of the step, [3,B,A] (eps for pi(x), pi(x2), target pi(x2)), or
+ * NULL to draw them on the device (Philox4x32-10 + Box-Muller keyed by `seed` and the step count).
+ * Fetches (all nullable, pre-update values like the reference's, actor_learner.py:97-101):
+ * d_out_scalars[4] = pi_loss, q1_loss, q2_loss, alpha;  d_out_q1, d_out_q2, d_out_logp: [B]. */
+int ddrl_sac_step(ddrl_sac_t sac, const float* d_obs1, const float* d_obs2, const float* d_acts,
+                  const float* d_rews, const float* d_done, int batch, const float* d_noise,
+                  uint64_t seed, float* d_out_scalars, float* d_out_q1, float* d_out_q2,
+                  float* d_out_logp, void* stream);
+
+/* Data-parallel split of the same step (the reference's compute_gradients / apply_gradients stubs,
+ * actor_learner.py:144-148, are empty): compute_grads leaves the flat gradient in the buffer
+ * returned by ddrl_sac_grad_buffer (all-reduce it across ranks, e.g. NCCL SUM), apply_grads
+ * multiplies it by the grad_scale given to compute_grads (1/world_size) and runs Adam + polyak.
+ * d_alpha_stat points at mean(logp_pi) of the local batch (average it too in 'auto' mode). */
+int ddrl_sac_compute_grads(ddrl_sac_t sac, const float* d_obs1, const float* d_obs2,
+                           const float* d_acts, const float* d_rews, const float* d_done, int batch,
+                           const float* d_noise, uint64_t seed, float grad_scale,
+                           float* d_out_scalars, float* d_out_q1, float* d_out_q2,
+                           float* d_out_logp, void* stream);
+int ddrl_sac_grad_buffer(ddrl_sac_t sac, float** d_grads, int64_t* count, float** d_alpha_stat);
+int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
+/* optimiser step counters and log_alpha (synchronises `stream`).  Any out may be NULL. */
+int ddrl_sac_state(ddrl_sac_t sac, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,182 @@
+"""GPU parity: the CUDA SAC1 step (ddrl_b200.Learner through the C ABI) vs the float64 oracle
+(oracle/sac1_oracle.py) on identical weights, batch and injected noise.
+
+Tolerance (BASELINE.json north_star): 1e-5 relative, fp32, on losses and updated weights.  It is
+asserted as  max|got - want| <= 1e-5 * max|want|  per tensor group, on conditioned weights (see
+oracle.sac1_oracle.conditioned_params for why the Glorot-init regime cannot carry a 1e-5 bar in
+float32 for ANY implementation, the reference included).  The oracle is unpinned by the reference
+(TensorFlow absent): this is parity with the restated algorithm."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.sac1_oracle import SAC1Oracle, conditioned_params, init_params, make_batch, param_names
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def L():
+    import __graft_entry__
+    __graft_entry__.build()
+    from ddrl_b200 import Learner
+    return Learner
+
+
+def make_opt(D, A, hidden, B, alpha=0.2, act_scale=1.0, lr=1e-3, gamma=0.99, polyak=0.995, seed=0):
+    space = SimpleNamespace(high=np.array([act_scale] * A, dtype=np.float32), shape=(A,))
+    return SimpleNamespace(obs_dim=D, act_dim=A, ac_kwargs=dict(hidden_sizes=hidden, action_space=space), alpha=alpha,
+                           gamma=gamma, lr=lr, polyak=polyak, seed=seed, batch_size=B)
+
+
+def build_pair(L, D, A, hidden, B, params, **kw):
+    opt = make_opt(D, A, hidden, B, **kw)
+    learner = L(opt, "learner")
+    keys = list(params.keys())
+    learner.set_weights(keys, [params[k] for k in keys])
+    oracle = SAC1Oracle(D, A, hidden=hidden, gamma=opt.gamma, polyak=opt.polyak, lr=opt.lr, alpha=opt.alpha,
+                        act_scale=kw.get("act_scale", 1.0), params=params, dtype=torch.float64)
+    return learner, oracle
+
+
+CASES = [
+    (8, 2, (64, 64), 64, 1.0),        # small
+    (8, 2, (256, 256), 256, 1.0),     # C1 shapes
+    (24, 4, (400, 300), 256, 1.0),    # the reference's own default net (core.py:91), BipedalWalker dims
+    (24, 4, (256, 256), 1024, 1.0),   # C2 shapes
+    (5, 3, (33, 17), 37, 0.4),        # odd everything, action scale != 1
+    (376, 17, (256, 256), 300, 0.4),  # C3 row shapes (Humanoid), act_dim > 8 -> wide head tiles
+]
+
+
+@pytest.mark.parametrize("D,A,hidden,B,scale", CASES)
+def test_one_step_matches_oracle(L, D, A, hidden, B, scale):
+    params = conditioned_params(D, A, hidden, seed=100 + D)
+    learner, oracle = build_pair(L, D, A, hidden, B, params, act_scale=scale)
+    batch, noise = make_batch(D, A, B, seed=200 + D)
+    want_g = oracle.flat_grads(batch, noise)
+    want = oracle.step(batch, noise)
+    got = learner.train(batch, noise=noise, split=True, sync_outputs=True)
+    sc = got["scalars"].cpu().numpy()
+    for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
+        assert abs(sc[i] - float(want[k])) <= TOL * abs(float(want[k])), (k, sc[i], float(want[k]))
+    assert sc[3] == np.float32(0.2)
+    for k in ("q1", "q2", "logp_pi"):
+        assert rel(got[k].cpu().numpy(), want[k]) <= TOL, k
+    assert rel(learner.get_flat_weights("grad").cpu().numpy(), want_g) <= 2 * TOL
+    assert rel(learner.get_flat_weights("main").cpu().numpy(), oracle.flat("main")) <= TOL
+    assert rel(learner.get_flat_weights("target").cpu().numpy(), oracle.flat("target")) <= TOL
+    # weights come back through the reference's (keys, values) contract, TF1 names and shapes
+    keys, values = learner.get_weights()
+    assert keys == param_names()
+    okeys, ovalues = oracle.get_weights()
+    for k, v, ov in zip(keys, values, ovalues):
+        assert v.shape == ov.shape and v.dtype == np.float32, k
+    st = learner.state()
+    assert (st["t_pi"], st["t_q"]) == (1, 1)
+
+
+def test_fused_graph_step_equals_split_step(L):
+    D, A, hidden, B = 24, 4, (256, 256), 512
+    params = conditioned_params(D, A, hidden, seed=7)
+    a, _ = build_pair(L, D, A, hidden, B, params)
+    b, _ = build_pair(L, D, A, hidden, B, params)
+    for it in range(3):
+        batch, noise = make_batch(D, A, B, seed=300 + it)
+        oa = {k: v.clone() for k, v in a.train(batch, noise=noise).items()}
+        ob = b.train(batch, noise=noise, split=True)
+        for k in oa:
+            assert torch.equal(oa[k], ob[k]), (it, k)
+    assert torch.equal(a.get_flat_weights("main"), b.get_flat_weights("main"))
+    assert torch.equal(a.get_flat_weights("target"), b.get_flat_weights("target"))
+
+
+def test_multi_step_tracks_oracle(L):
+    D, A, hidden, B = 24, 4, (128, 128), 256
+    params = conditioned_params(D, A, hidden, seed=11)
+    learner, oracle = build_pair(L, D, A, hidden, B, params, lr=3e-4)
+    for it in range(10):
+        batch, noise = make_batch(D, A, B, seed=400 + it)
+        want = oracle.step(batch, noise)
+        got = learner.train(batch, noise=noise, sync_outputs=True)
+        sc = got["scalars"].cpu().numpy()
+        for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
+            assert abs(sc[i] - float(want[k])) <= 1e-4 * abs(float(want[k])), (it, k)
+    # looser, stated bound after 10 chained updates (rounding differences compound through Adam)
+    assert rel(learner.get_flat_weights("main").cpu().numpy(), oracle.flat("main")) <= 1e-4
+    assert rel(learner.get_flat_weights("target").cpu().numpy(), oracle.flat("target")) <= 1e-4
+    assert rel(learner.get_flat_weights("adam_m").cpu().numpy(),
+               np.concatenate([m.reshape(-1).numpy() for m in oracle.opt_pi.m + oracle.opt_q.m])) <= 1e-4
+    assert learner.state()["t_q"] == 10
+
+
+def test_auto_alpha_matches_intended_semantics(L):
+    D, A, hidden, B = 8, 2, (64, 64), 128
+    params = conditioned_params(D, A, hidden, seed=21)
+    learner, oracle = build_pair(L, D, A, hidden, B, params, alpha="auto")
+    for it in range(4):
+        batch, noise = make_batch(D, A, B, seed=500 + it)
+        want = oracle.step(batch, noise)
+        got = learner.train(batch, noise=noise, sync_outputs=True)
+        sc = got["scalars"].cpu().numpy()
+        assert abs(sc[3] - float(want["alpha"])) <= TOL * float(want["alpha"]), it
+        assert abs(sc[0] - float(want["pi_loss"])) <= 5e-5 * abs(float(want["pi_loss"])), it
+    st = learner.state()
+    assert st["t_alpha"] == 4
+    assert abs(st["log_alpha"] - float(oracle.log_alpha)) <= 1e-5 * max(abs(float(oracle.log_alpha)), 1e-3)
+
+
+def test_set_weights_resets_target_and_accepts_subsets(L):
+    D, A, hidden, B = 8, 2, (32, 32), 32
+    params = conditioned_params(D, A, hidden, seed=31)
+    learner, _ = build_pair(L, D, A, hidden, B, params)
+    batch, noise = make_batch(D, A, B, seed=1)
+    learner.train(batch, noise=noise)
+    assert not torch.equal(learner.get_flat_weights("main"), learner.get_flat_weights("target"))
+    keys, values = learner.get_weights()
+    pi_keys = [k for k in keys if "/pi/" in k]                       # an Actor pulls only these 8
+    learner.set_weights(pi_keys, [values[keys.index(k)] * 0 + 0.5 for k in pi_keys])
+    assert torch.equal(learner.get_flat_weights("main"), learner.get_flat_weights("target"))
+    k2, v2 = learner.get_weights()
+    assert all(np.all(v == 0.5) for k, v in zip(k2, v2) if "/pi/" in k)
+    assert all(np.array_equal(v, values[keys.index(k)]) for k, v in zip(k2, v2) if "/pi/" not in k)
+    with pytest.raises(KeyError):
+        learner.set_weights(["main/pi/nope"], [np.zeros(1)])
+
+
+def test_device_noise_is_standard_normal_and_training_runs(L):
+    D, A, hidden, B = 24, 4, (256, 256), 1024
+    opt = make_opt(D, A, hidden, B, seed=5)
+    learner = L(opt, "learner")
+    batch, _ = make_batch(D, A, B, seed=3)
+    dev_batch = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+    first = learner.train(dev_batch, sync_outputs=True)["scalars"].clone()
+    for _ in range(20):
+        out = learner.train(dev_batch)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["scalars"]).all() and torch.isfinite(learner.get_flat_weights("main")).all()
+    assert float(out["scalars"][1]) < float(first[1])          # the Q loss on a fixed batch goes down
+
+
+def test_default_init_regime_against_float32_oracle(L):
+    """Glorot-init log_std head: float32 itself is rounding-dominated (conditioned_params docstring);
+    the kernel keeps the reference graph's op order, so it still tracks a float32 evaluation of the
+    same graph to ~1e-3, while float64 is no longer a meaningful target."""
+    D, A, hidden, B = 24, 4, (64, 64), 256
+    params = init_params(D, A, hidden, seed=9)
+    learner, _ = build_pair(L, D, A, hidden, B, params)
+    o32 = SAC1Oracle(D, A, hidden=hidden, params=params, dtype=torch.float32)
+    batch, noise = make_batch(D, A, B, seed=10)
+    want = o32.step(batch, noise)
+    got = learner.train(batch, noise=noise, sync_outputs=True)
+    sc = got["scalars"].cpu().numpy()
+    for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
+        assert abs(sc[i] - float(want[k])) <= 2e-3 * abs(float(want[k])), k
