@@ -41,6 +41,7 @@ struct StepState {  // persistent
   float alpha_cur;      // alpha used by this step (pre-update)
   int auto_alpha;
   float alpha_const;
+  float lr, lr_pi, lr_q;  // base rate and TF1 Adam's bias-corrected rates for this step
 };
 
 __global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
@@ -50,6 +51,10 @@ __global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
     st->t_q += 1;
     st->noise_counter += 1;
     st->alpha_cur = st->auto_alpha ? expf(st->log_alpha) : st->alpha_const;
+    // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)   (tensorflow/python/training/adam.py, 1.x)
+    const double tp = (double)st->t_pi, tq = (double)st->t_q;
+    st->lr_pi = (float)((double)st->lr * sqrt(1.0 - pow(0.999, tp)) / (1.0 - pow(0.9, tp)));
+    st->lr_q = (float)((double)st->lr * sqrt(1.0 - pow(0.999, tq)) / (1.0 - pow(0.9, tq)));
   }
 }
 
@@ -257,9 +262,7 @@ __global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, i
                                                      float target_entropy, const float* __restrict__ SCAL,
                                                      float* W, float* Wt, float* Mo, float* Vo) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-  const double tp = (double)st->t_pi, tq = (double)st->t_q;
-  const float lr_pi = (float)((double)lr * sqrt(1.0 - pow((double)b2, tp)) / (1.0 - pow((double)b1, tp)));
-  const float lr_q = (float)((double)lr * sqrt(1.0 - pow((double)b2, tq)) / (1.0 - pow((double)b1, tq)));
+  const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
@@ -651,6 +654,7 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   init.auto_alpha = h->auto_alpha;
   init.alpha_const = alpha;
   init.alpha_cur = h->auto_alpha ? 1.0f : alpha;
+  init.lr = lr;
   cudaError_t e = cudaMemcpy(h->st, &init, sizeof(init), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { ddrl_sac_destroy(h); return fail(DDRL_ECUDA, "init state: %s", cudaGetErrorString(e)); }
   *out = h;

@@ -49,26 +49,72 @@ __device__ __forceinline__ float fetch_a(const GemmProb& P, int row, int feat) {
   return (P.a_ones && feat == P.a1.w) ? 1.0f : 0.0f;
 }
 
+// global -> register fetch of one (BM x BK) A tile slice and one (BK x BN) B tile slice
+template <int BM, int BN, int BK>
+struct TileRegs {
+  float a[BM * BK / 256];
+  float b[BN * BK / 256];
+};
+
+template <int BM, int BN, int BK>
+__device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, int n0, int k0, int kend,
+                                            TileRegs<BM, BN, BK>& r) {
+  if (!P.a_trans) {
+#pragma unroll
+    for (int e = 0; e < BM * BK / 256; ++e) {
+      const int i = tid + e * 256;
+      const int kl = i % BK, ml = i / BK;
+      const int m = m0 + ml, k = k0 + kl;
+      r.a[e] = (m < P.M && k < kend) ? fetch_a(P, m, k) : 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < BM * BK / 256; ++e) {
+      const int i = tid + e * 256;
+      const int ml = i % BM, kl = i / BM;
+      const int m = m0 + ml, k = k0 + kl;
+      r.a[e] = (m < P.M && k < kend) ? fetch_a(P, k, m) : 0.0f;
+    }
+  }
+  if (!P.b_trans) {
+#pragma unroll
+    for (int e = 0; e < BN * BK / 256; ++e) {
+      const int i = tid + e * 256;
+      const int nl = i % BN, kl = i / BN;
+      const int n = n0 + nl, k = k0 + kl;
+      r.b[e] = (n < P.N && k < kend) ? P.B[(size_t)k * P.ldb + n] : 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < BN * BK / 256; ++e) {
+      const int i = tid + e * 256;
+      const int kl = i % BK, nl = i / BK;
+      const int n = n0 + nl, k = k0 + kl;
+      r.b[e] = (n < P.N && k < kend) ? P.B[(size_t)n * P.ldb + k] : 0.0f;
+    }
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_grouped_f32(const GemmProb* __restrict__ probs, int nprob) {
-  constexpr int BK = 16;
+  constexpr int BK = 32;
   constexpr int TX = BN / TN;
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads per tile");
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
-  __shared__ GemmProb P;
+  __shared__ GemmProb Psh;
 
   const int tid = threadIdx.x;
   {
     int pi = 0;
     const int tile = blockIdx.x;
     while (pi + 1 < nprob && tile >= probs[pi + 1].tile_begin) ++pi;
-    // cooperative copy of the descriptor into shared memory
     const int* src = reinterpret_cast<const int*>(probs + pi);
-    int* dst = reinterpret_cast<int*>(&P);
+    int* dst = reinterpret_cast<int*>(&Psh);
     for (int i = tid; i < (int)(sizeof(GemmProb) / 4); i += 256) dst[i] = src[i];
   }
   __syncthreads();
+  const GemmProb P = Psh;  // registers / uniform
 
   int t = blockIdx.x - P.tile_begin;
   const int per_split = P.tiles_m * P.tiles_n;
@@ -85,34 +131,26 @@ __global__ void __launch_bounds__(256) gemm_grouped_f32(const GemmProb* __restri
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
+  TileRegs<BM, BN, BK> r;
+  fetch_tiles<BM, BN, BK>(P, tid, m0, n0, kbeg, kend, r);
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // registers -> shared (same index maps as fetch_tiles)
     if (!P.a_trans) {
-      for (int i = tid; i < BM * BK; i += 256) {
-        const int kl = i % BK, ml = i / BK;
-        const int m = m0 + ml, k = k0 + kl;
-        As[kl][ml] = (m < P.M && k < kend) ? fetch_a(P, m, k) : 0.0f;
-      }
+#pragma unroll
+      for (int e = 0; e < BM * BK / 256; ++e) { const int i = tid + e * 256; As[i % BK][i / BK] = r.a[e]; }
     } else {
-      for (int i = tid; i < BM * BK; i += 256) {
-        const int ml = i % BM, kl = i / BM;
-        const int m = m0 + ml, k = k0 + kl;
-        As[kl][ml] = (m < P.M && k < kend) ? fetch_a(P, k, m) : 0.0f;
-      }
+#pragma unroll
+      for (int e = 0; e < BM * BK / 256; ++e) { const int i = tid + e * 256; As[i / BM][i % BM] = r.a[e]; }
     }
     if (!P.b_trans) {
-      for (int i = tid; i < BN * BK; i += 256) {
-        const int nl = i % BN, kl = i / BN;
-        const int n = n0 + nl, k = k0 + kl;
-        Bs[kl][nl] = (n < P.N && k < kend) ? P.B[(size_t)k * P.ldb + n] : 0.0f;
-      }
+#pragma unroll
+      for (int e = 0; e < BN * BK / 256; ++e) { const int i = tid + e * 256; Bs[i / BN][i % BN] = r.b[e]; }
     } else {
-      for (int i = tid; i < BN * BK; i += 256) {
-        const int kl = i % BK, nl = i / BK;
-        const int n = n0 + nl, k = k0 + kl;
-        Bs[kl][nl] = (n < P.N && k < kend) ? P.B[(size_t)n * P.ldb + k] : 0.0f;
-      }
+#pragma unroll
+      for (int e = 0; e < BN * BK / 256; ++e) { const int i = tid + e * 256; Bs[i % BK][i / BK] = r.b[e]; }
     }
     __syncthreads();
+    if (k0 + BK < kend) fetch_tiles<BM, BN, BK>(P, tid, m0, n0, k0 + BK, kend, r);  // in flight during the FMAs
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[TM], b[TN];
