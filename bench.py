@@ -1,0 +1,388 @@
+"""bench.py — the learner-side hot path on N GPUs of one node (BASELINE.json metric / config C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one iteration of the reference's learner hot loop (algos/sac1/sac1.py:146-148):
+    batch = replay_buffer.sample_batch(B);  agent.train(batch)
+on synthetic transitions of the named shape (C2: obs 24, act 4, replay 1e6 rows per GPU, batch 1024,
+256x256 MLPs).  Per rank: one replay shard + one learner; N > 1 adds the NCCL gradient all-reduce.
+
+Printed JSON line (rank 0):
+  value / unit        whole-job transitions/s consumed by the learners (N * B * K / t), everything
+                      resident in HBM, timed with CUDA events between barriers, max over ranks
+  e2e                 the same metric through the reference-facing API with HOST buffers: per step
+                      store_batch(B new rows from pinned host memory) -> sample_batch(B) returned as
+                      host numpy arrays -> train(host batch) -> read the losses back
+  roofline            dominant kernel class of the step (the SAC1 update: FLOP model of SURVEY §8d
+                      against the measured bf16 tensor peak; parity mode computes in fp32 FFMA)
+  roofline_replay     the sample_batch gather kernel alone (sample_many launches): algorithmic bytes
+                      2*row_bytes per transition against the measured HBM copy peak
+  cpu_baseline        the oracle port (numpy ring + torch-CPU float32 SAC1 step) on this box's cores
+--impl reference times that same CPU port as the reference arm (the reference is pure Python on
+TensorFlow 1.x / Ray, which cannot be installed; oracle/ is its restatement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "distributed-drl_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # name: obs_dim, act_dim, replay rows per GPU, batch, hidden, act_scale
+    "C1": dict(D=8, A=2, replay=1_000_000, B=256, hidden=(256, 256), act_scale=1.0,
+               desc="SAC1 LunarLanderContinuous-v2 shapes"),
+    "C2": dict(D=24, A=4, replay=1_000_000, B=1024, hidden=(256, 256), act_scale=1.0,
+               desc="SAC1 BipedalWalker-shaped synthetic transitions"),
+    "C3": dict(D=376, A=17, replay=10_000_000, B=4096, hidden=(256, 256), act_scale=0.4,
+               desc="SAC1 Humanoid-shaped synthetic transitions"),
+}
+
+
+def flops_per_update(D, A, h1, h2, B):
+    """5*L_pi + 10*L_q."""
+    l_pi = 2 * B * (D * h1 + h1 * h2 + 2 * h2 * A)
+    l_q = 2 * B * ((D + A) * h1 + h1 * h2 + h2)
+    return 5 * l_pi + 10 * l_q
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tf=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm_gbs=6650.0, bf16_tf=1400.0, source="B200_PROFILING.md fallback")
+
+
+def make_opt(cfg, seed=0):
+    space = SimpleNamespace(high=np.full(cfg["A"], cfg["act_scale"], np.float32), shape=(cfg["A"],))
+    return SimpleNamespace(obs_dim=cfg["D"], act_dim=cfg["A"], ac_kwargs=dict(hidden_sizes=cfg["hidden"], action_space=space),
+                           alpha=0.2, gamma=0.99, lr=1e-3, polyak=0.995, seed=seed, batch_size=cfg["B"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.dev), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(cfg, steps, warmup, threads, ring_rows=None, seed=1002):
+    """numpy ring sample_batch + torch-CPU float32 SAC1 step (oracle/), `steps` timed iterations.
+    Returns (seconds per step, description)."""
+    import torch
+    from oracle.replay_oracle import ReplayRingOracle
+    from oracle.sac1_oracle import SAC1Oracle, init_params
+    torch.set_num_threads(threads)
+    D, A, B = cfg["D"], cfg["A"], cfg["B"]
+    rows = int(ring_rows or min(cfg["replay"], 1_000_000))
+    g = np.random.Generator(np.random.PCG64(seed))
+    ring = ReplayRingOracle(D, A, rows)
+    ring.obs1_buf[:] = g.standard_normal((rows, D), dtype=np.float32)
+    ring.obs2_buf[:] = g.standard_normal((rows, D), dtype=np.float32)
+    ring.acts_buf[:] = g.uniform(-1, 1, (rows, A)).astype(np.float32)
+    ring.rews_buf[:] = g.standard_normal(rows, dtype=np.float32)
+    ring.done_buf[:] = (g.random(rows) < 0.01).astype(np.float32)
+    ring.size, ring.ptr = rows, 0
+    learner = SAC1Oracle(D, A, hidden=cfg["hidden"], params=init_params(D, A, cfg["hidden"], seed), dtype=torch.float32,
+                         act_scale=cfg["act_scale"])
+    np.random.seed(seed)
+
+    def one():
+        batch = ring.sample_batch(B)
+        noise = g.standard_normal((3, B, A), dtype=np.float32)
+        learner.step(batch, noise)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, f"{steps} steps of sample_batch({B}) + float32 SAC1 update, ring {rows} rows, {threads} torch threads"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 60))
+    sec, sample = cpu_port_run(cfg, steps, max(1, min(args.warmup, 5)), cores)
+    value = cfg["B"] / sec
+    line = dict(metric="learner-path transitions/s (replay sample_batch -> SAC1 update)", value=value, unit="transitions/s",
+                impl="reference", n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 5), ms_per_step=sec * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                updates_per_s=1.0 / sec,
+                config=dict(workload=f"{args.config}: {cfg['desc']} (obs {cfg['D']}, act {cfg['A']}, batch {cfg['B']}, "
+                                     f"{cfg['hidden'][0]}x{cfg['hidden'][1]} MLP)", replay_rows=min(cfg["replay"], 1_000_000)),
+                cpu_baseline=dict(value=value, unit="transitions/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="transitions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="reference = oracle/ CPU port (numpy ring + torch-CPU float32 SAC1 step); the reference's own "
+                     "TensorFlow 1.x / Ray stack is not installable here")
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if rank == 0:
+        __graft_entry__.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from ddrl_b200 import Learner, ReplayBuffer, _native
+
+    cfg = CONFIGS[args.config]
+    D, A, B, hidden = cfg["D"], cfg["A"], cfg["B"], cfg["hidden"]
+    rows = cfg["replay"]
+    row_bytes = 4 * (2 * D + A + 2)
+    dev = torch.device("cuda", local)
+    peaks = measured_peaks()
+
+    # ---- replay shard of this rank, filled on the device with a counter-based generator ----------
+    rb = ReplayBuffer(D, A, rows, device=local, seed=1000 + 2, rng_stream=rank)
+    gen = torch.Generator(device=dev).manual_seed(1002 + rank)
+    chunk = 250_000
+    for lo in range(0, rows, chunk):
+        n = min(chunk, rows - lo)
+        rb.store_batch(torch.randn((n, D), device=dev, generator=gen), torch.rand((n, A), device=dev, generator=gen) * 2 - 1,
+                       torch.randn(n, device=dev, generator=gen), torch.randn((n, D), device=dev, generator=gen),
+                       (torch.rand(n, device=dev, generator=gen) < 0.01).float())
+    learner = Learner(make_opt(cfg, seed=7), "learner", device=local)   # same seed -> same initial weights on every rank
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = _native.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _native.launch_count() - before
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / 1e3, launches
+
+    # ---- (1) device-resident hot loop: sample_batch -> train --------------------------------------
+    def step_device():
+        learner.train(rb.sample_batch(B, device=True))
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    sec, launches = timed(step_device, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    value = world * B * args.steps / sec
+    ms_per_step = sec / args.steps * 1e3
+
+    # ---- (2) end to end through the reference-facing API with host buffers --------------------------
+    g = np.random.Generator(np.random.PCG64(5 + rank))
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    new = [pin(g.standard_normal((B, D), dtype=np.float32)), pin(g.uniform(-1, 1, (B, A)).astype(np.float32)),
+           pin(g.standard_normal(B, dtype=np.float32)), pin(g.standard_normal((B, D), dtype=np.float32)),
+           pin((g.random(B) < 0.01).astype(np.float32))]
+    sink = []
+
+    def step_e2e():
+        rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side
+        batch = rb.sample_batch(B)                            # D2H: the reference returns host arrays
+        out = learner.train(batch)                            # H2D: host batch fed like feed_dict
+        sink.append(out["scalars"].cpu())                     # D2H: the fetched losses
+
+    e2e_steps = max(5, min(args.steps, 200))
+    sec_e2e, _ = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 10)))
+    e2e_value = world * B * e2e_steps / sec_e2e
+    h2d = 2 * B * row_bytes
+    d2h = B * row_bytes + 16
+
+    # ---- (3) the gather kernel alone: sample_many launches, outputs >> L2 ---------------------------
+    n_batches = max(1, min(2048, int(1.5e9 // (B * row_bytes))))
+    outs = rb.sample_many(n_batches, B)                       # allocate once; reuse the same call below
+    del outs
+    torch.cuda.synchronize()
+    reps = 10
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    import ctypes as C
+    f32 = dict(dtype=torch.float32, device=dev)
+    n_rows = n_batches * B
+    o = [torch.empty((n_rows, D), **f32), torch.empty((n_rows, D), **f32), torch.empty((n_rows, A), **f32),
+         torch.empty(n_rows, **f32), torch.empty(n_rows, **f32)]
+    s = torch.cuda.current_stream(local)
+    lib = _native.lib()
+    for i in range(3 + reps):
+        if i >= 3:
+            ev[i - 3][0].record(s)
+        _native.check(lib.ddrl_rb_sample(rb.native_handle, B, n_batches, None, 77, i, rank,
+                                         *[C.c_void_p(t.data_ptr()) for t in o], None, C.c_void_p(s.cuda_stream)))
+        if i >= 3:
+            ev[i - 3][1].record(s)
+    torch.cuda.synchronize()
+    gather_s = float(np.mean([a.elapsed_time(b) for a, b in ev])) / 1e3
+    gather_gbs = 2 * row_bytes * n_rows / gather_s / 1e9
+    # batched store of the same volume
+    n_store = min(n_rows, rows)
+    src = [torch.randn((n_store, D), **f32), torch.rand((n_store, A), **f32), torch.randn(n_store, **f32),
+           torch.randn((n_store, D), **f32), torch.zeros(n_store, **f32)]
+    for i in range(3 + reps):
+        if i >= 3:
+            ev[i - 3][0].record(s)
+        rb.store_batch(*src)
+        if i >= 3:
+            ev[i - 3][1].record(s)
+    torch.cuda.synchronize()
+    store_s = float(np.mean([a.elapsed_time(b) for a, b in ev])) / 1e3
+    store_gbs = 2 * row_bytes * n_store / store_s / 1e9
+    del o, src
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fl = flops_per_update(D, A, hidden[0], hidden[1], B)
+    upd_per_s_rank = args.steps / sec
+    tf = fl * upd_per_s_rank / 1e12
+    line = dict(
+        metric="learner-path transitions/s (replay sample_batch -> SAC1 update)", value=value, unit="transitions/s",
+        n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
+        scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        updates_per_s=upd_per_s_rank, global_batch=world * B,
+        config=dict(workload=f"{args.config}: {cfg['desc']} (obs {D}, act {A}, batch {B} per GPU, {hidden[0]}x{hidden[1]} MLP)",
+                    replay_rows_per_gpu=rows, replay_bytes_per_gpu=rows * ((row_bytes + 15) // 16 * 16),
+                    parallelism=f"dp{world}: replay sharded per GPU, NCCL grad all-reduce" if world > 1 else "single GPU",
+                    l2="replay ring larger than L2, rows drawn at random; weights (3.5 MB) are L2-resident by design",
+                    noise="Philox on device", index_source="Philox on device"),
+        clocks=clk,
+        e2e=dict(value=e2e_value, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
+                 ms_per_step=sec_e2e / e2e_steps * 1e3,
+                 path="store_batch(host) -> sample_batch() -> numpy -> Learner.train(numpy) -> losses.cpu()"),
+        gpu_launches=int(launches),
+        roofline=dict(kernel="SAC1 update (gemm_grouped_f32 x ~20 + element-wise), whole step", bound="tensor",
+                      achieved=tf, peak=peaks["bf16_tf"], unit="TFLOP/s", frac=tf / peaks["bf16_tf"], traffic=None,
+                      flops_per_update=fl, peak_source=peaks["source"],
+                      note="parity mode computes in fp32 FFMA (1e-5 bar forbids bf16/tf32 rounding); fraction is "
+                           "against the bf16 tensor peak as SURVEY 8(d) defines it"),
+        roofline_replay=dict(kernel="rb_gather_* (sample_batch)", bound="hbm", achieved=gather_gbs, peak=peaks["hbm_gbs"],
+                             unit="GB/s", frac=gather_gbs / peaks["hbm_gbs"], traffic=None,
+                             bytes_per_transition=2 * row_bytes, transitions_per_launch=n_rows,
+                             transitions_per_s=n_rows / gather_s, peak_source=peaks["source"],
+                             store_gbs=store_gbs, store_frac=store_gbs / peaks["hbm_gbs"], store_rows_per_launch=n_store),
+    )
+    # ---- (4) CPU baseline on this box's cores (N = 1 only) -------------------------------------------
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        probe, _ = cpu_port_run(cfg, 2, 1, cores)
+        n = int(max(3, min(200, 15.0 / max(probe, 1e-4))))
+        sec_cpu, sample = cpu_port_run(cfg, n, 1, cores)
+        line["cpu_baseline"] = dict(value=B / sec_cpu, unit="transitions/s", cores=cores, kind="port", sample=sample,
+                                    ms_per_step=sec_cpu * 1e3)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
