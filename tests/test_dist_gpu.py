@@ -1,0 +1,74 @@
+"""GPU, >= 2 devices, NCCL: the data-parallel SAC1 step (compute_grads -> all-reduce -> apply_grads)
+equals the single-GPU step on the concatenated batch, replicas stay bit-identical, and the
+ParameterServer broadcast delivers the learner's flat weights to every rank."""
+import os
+import socket
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.sac1_oracle import conditioned_params, make_batch
+
+pytestmark = pytest.mark.gpu
+
+D, A, HID, B = 24, 4, (128, 128), 256
+
+
+def _opt(batch):
+    space = SimpleNamespace(high=np.ones(A, np.float32), shape=(A,))
+    return SimpleNamespace(obs_dim=D, act_dim=A, ac_kwargs=dict(hidden_sizes=HID, action_space=space), alpha=0.2,
+                           gamma=0.99, lr=1e-3, polyak=0.995, seed=0, batch_size=batch)
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from ddrl_b200 import Learner
+    from ddrl_b200.dist import DistributedParameterServer
+    params = conditioned_params(D, A, HID, seed=3)
+    L = Learner(_opt(B // world), "learner", device=rank)
+    L.set_weights(list(params), list(params.values()))
+    for it in range(3):
+        batch, noise = make_batch(D, A, B, seed=40 + it)
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        L.train({k: v[lo:hi] for k, v in batch.items()}, noise=noise[:, lo:hi].copy())
+    keys, values = L.get_weights()
+    ps = DistributedParameterServer(keys, values, src=0, device=torch.device("cuda", rank))
+    if rank == 0:
+        ps.push_flat(L.get_flat_weights() * 0 + 3.0)
+    ps.sync()
+    ret[rank] = (L.get_flat_weights("main").cpu().numpy(), L.get_flat_weights("target").cpu().numpy(),
+                 float(ps.pull_flat().min()), float(ps.pull_flat().max()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_step_equals_single_gpu_on_concatenated_batch():
+    import torch.multiprocessing as mp
+    import __graft_entry__
+    __graft_entry__.build()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    from ddrl_b200 import Learner
+    params = conditioned_params(D, A, HID, seed=3)
+    single = Learner(_opt(B), "learner", device=0)
+    single.set_weights(list(params), list(params.values()))
+    for it in range(3):
+        batch, noise = make_batch(D, A, B, seed=40 + it)
+        single.train(batch, noise=noise)
+    want_m = single.get_flat_weights("main").cpu().numpy()
+    want_t = single.get_flat_weights("target").cpu().numpy()
+    assert np.array_equal(ret[0][0], ret[1][0]) and np.array_equal(ret[0][1], ret[1][1])
+    for r in (0, 1):
+        # same arithmetic up to the summation order of the batch reduction (2 x 128 rows vs 256 rows)
+        assert np.abs(ret[r][0] - want_m).max() <= 2e-5 * np.abs(want_m).max()
+        assert np.abs(ret[r][1] - want_t).max() <= 2e-5 * np.abs(want_t).max()
+        assert ret[r][2] == 3.0 and ret[r][3] == 3.0
