@@ -13,6 +13,9 @@
 //                            4 rows in flight per lane group; indices drawn 32 at a time per warp
 //   rb_gather_wide           rows of  > 32 float4: one warp per row, 4 x 128-bit loads in flight
 //   rb_store_rows<T>         SoA inputs -> packed rows, flat (row, chunk) mapping, 128-bit stores
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ddrl {
@@ -21,7 +24,8 @@ enum IdxMode : int { IDX_INJECT = 0, IDX_PHILOX = 1, IDX_IDENTITY = 2 };
 
 struct GatherArgs {
   const float4* ring;
-  int D, A, row_f4;
+  int D, A, row_f4;    // row_f4: row stride in float4 (rows may be padded to a 64/128-byte multiple)
+  int used_f4;         // float4 chunks of a row that carry data: ceil((2D+A+2)/4)
   uint64_t size;       // sampling range [0,size)
   int64_t total;       // rows to produce
   const int64_t* idx_in;
@@ -72,16 +76,59 @@ __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
 }
 
 // ---- rows that fit in LANES float4 (LANES in {2,4,8,16,32}) ---------------------------------
-template <int LANES>
-__global__ void __launch_bounds__(256, 4) rb_gather_narrow(const GatherArgs a) {
+// A lane always handles the same chunk l of a row, so where its four floats go is loop-invariant:
+// it is resolved once into (base pointer, per-row stride) pairs; the row loop is then
+// shuffle -> 128-bit load -> 128-bit store (or up to four 32-bit stores for the acts/rew/done tail).
+struct LaneRoute {
+  float* vbase;      // non-null: the whole chunk goes to one 16-byte aligned destination
+  int vstride;       // floats between consecutive output rows of that destination
+  float* sbase[4];   // otherwise: per-float destinations (null = padding, dropped)
+  int sstride[4];
+};
+
+__device__ __forceinline__ LaneRoute make_route(const GatherArgs& a, int c) {
+  LaneRoute r;
+  r.vbase = nullptr; r.vstride = 0;
+  const int D = a.D, A = a.A, D4 = a.D >> 2;
+  const bool aligned = (D & 3) == 0;
+  if (aligned && c < D4) { r.vbase = a.o1 + 4 * c; r.vstride = D; }
+  else if (aligned && c < 2 * D4) { r.vbase = a.o2 + 4 * (c - D4); r.vstride = D; }
+  else if (aligned && (A & 3) == 0 && c < 2 * D4 + (A >> 2)) { r.vbase = a.oa + 4 * (c - 2 * D4); r.vstride = A; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int f = 4 * c + j;
+    r.sbase[j] = nullptr; r.sstride[j] = 0;
+    if (f < D) { r.sbase[j] = a.o1 + f; r.sstride[j] = D; }
+    else if (f < 2 * D) { r.sbase[j] = a.o2 + (f - D); r.sstride[j] = D; }
+    else if (f < 2 * D + A) { r.sbase[j] = a.oa + (f - 2 * D); r.sstride[j] = A; }
+    else if (f == 2 * D + A) { r.sbase[j] = a.orw; r.sstride[j] = 1; }
+    else if (f == 2 * D + A + 1) { r.sbase[j] = a.od; r.sstride[j] = 1; }
+  }
+  return r;
+}
+
+__device__ __forceinline__ void route_store(const LaneRoute& r, int64_t b, const float4& v) {
+  if (r.vbase) {
+    st_f4(reinterpret_cast<float4*>(r.vbase + b * r.vstride), v);
+  } else {
+    if (r.sbase[0]) r.sbase[0][b * r.sstride[0]] = v.x;
+    if (r.sbase[1]) r.sbase[1][b * r.sstride[1]] = v.y;
+    if (r.sbase[2]) r.sbase[2][b * r.sstride[2]] = v.z;
+    if (r.sbase[3]) r.sbase[3][b * r.sstride[3]] = v.w;
+  }
+}
+
+template <int LANES, int U>
+__global__ void __launch_bounds__(256, U >= 8 ? 2 : ((LANES == 8 || LANES == 16) ? 4 : 3)) rb_gather_narrow(const GatherArgs a) {
   constexpr int RPP = 32 / LANES;  // rows per pass of a warp
-  constexpr int U = (LANES >= 4) ? 4 : LANES;
+  static_assert(U <= LANES && LANES % U == 0, "U rows in flight per lane group");
   const int lane = threadIdx.x & 31;
   const int g = lane / LANES, l = lane % LANES;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const bool aligned = (a.D & 3) == 0;
-  const bool lane_live = l < a.row_f4;
+  const bool lane_live = l < a.used_f4;
+  const LaneRoute route = make_route(a, l);
+  const float4* lane_ring = a.ring + l;
 
   for (int64_t base = warp * 32; base < a.total; base += nwarps * 32) {
     const int64_t mine = base + lane;
@@ -93,19 +140,17 @@ __global__ void __launch_bounds__(256, 4) rb_gather_narrow(const GatherArgs a) {
 #pragma unroll 1
     for (int p0 = 0; p0 < LANES; p0 += U) {
       float4 v[U];
-      int64_t b[U];
       bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int r = (p0 + u) * RPP + g;
         const int64_t src = shfl_i64(myidx, r);
-        b[u] = base + r;
-        ok[u] = lane_live && b[u] < a.total;
-        if (ok[u]) v[u] = ld_nc_f4(a.ring + src * a.row_f4 + l);
+        ok[u] = lane_live && (base + r) < a.total;
+        if (ok[u]) v[u] = ld_nc_f4(lane_ring + src * a.row_f4);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (ok[u]) route_chunk(a, aligned, b[u], l, v[u]);
+        if (ok[u]) route_store(route, base + (p0 + u) * RPP + g, v[u]);
     }
   }
 }
@@ -131,20 +176,121 @@ __global__ void __launch_bounds__(256, 4) rb_gather_wide(const GatherArgs a) {
       const int64_t src = shfl_i64(myidx, r);
       if (b >= a.total) break;  // warp-uniform
       const float4* row = a.ring + src * a.row_f4;
-      for (int c0 = lane; c0 < a.row_f4; c0 += 32 * 4) {
+      for (int c0 = lane; c0 < a.used_f4; c0 += 32 * 4) {
         float4 v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int c = c0 + 32 * k;
-          if (c < a.row_f4) v[k] = ld_nc_f4(row + c);
+          if (c < a.used_f4) v[k] = ld_nc_f4(row + c);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int c = c0 + 32 * k;
-          if (c < a.row_f4) route_chunk(a, aligned, b, c, v[k]);
+          if (c < a.used_f4) route_chunk(a, aligned, b, c, v[k]);
         }
       }
     }
+  }
+}
+
+// ---- bulk-async staged gather (TMA engine, no register staging) -------------------------------
+// The packed row is ONE contiguous 16-byte-aligned run, so a sampled row is ONE `cp.async.bulk`
+// (global -> shared, completion counted in bytes on an mbarrier).  A CTA keeps STAGES tiles of R rows
+// in flight (tens of KB per CTA, ~150+ KB per SM) — the memory-level parallelism a random 224-byte
+// gather needs to approach the HBM roofline, which per-thread register loads cannot hold — and
+// drains each landed tile to the five output arrays with 128-bit stores.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(const void* p) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_u32(p)));
+  return r;
+}
+
+template <int STAGES, bool NARROW>
+__global__ void __launch_bounds__(256) rb_gather_bulk(const GatherArgs a, int R, int lanes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int row_bytes = a.used_f4 * 16;
+  const int stage_bytes = (R * row_bytes + 127) / 128 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (a.total + R - 1) / R;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int stage) {
+    const int64_t row0 = tile * R;
+    const int rows = (int)min((int64_t)R, a.total - row0);
+    if (tid == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)(rows * row_bytes));
+    if (tid < rows) {
+      const int64_t ord = row0 + tid;
+      const int64_t idx = draw_index(a, ord);
+      if (a.oidx) a.oidx[ord] = idx;
+      bulk_g2s(smem + (size_t)stage * stage_bytes + (size_t)tid * row_bytes, a.ring + idx * a.row_f4, (uint32_t)row_bytes,
+               &bars[stage]);
+    }
+  };
+
+  // prologue: fill the pipeline
+  int64_t next = blockIdx.x;
+  for (int s = 0; s < STAGES; ++s, next += gridDim.x)
+    if (next < ntiles) issue(next, s);
+
+  const bool aligned = (a.D & 3) == 0;
+  LaneRoute route;
+  int l = 0, rsub = 0, rows_per_pass = 1;
+  if (NARROW) {
+    l = tid % lanes; rsub = tid / lanes; rows_per_pass = 256 / lanes;
+    route = make_route(a, l);
+  }
+  const int q = 256 / a.used_f4, rem = 256 % a.used_f4;
+
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * R;
+    const int rows = (int)min((int64_t)R, a.total - row0);
+    mbar_wait(&bars[stage], parity);
+    const unsigned char* sbase = smem + (size_t)stage * stage_bytes;
+    if (NARROW) {
+      if (l < a.used_f4) {
+#pragma unroll 4
+        for (int r = rsub; r < rows; r += rows_per_pass)
+          route_store(route, row0 + r, lds_f4(sbase + (size_t)r * row_bytes + l * 16));
+      }
+    } else {
+      int r = tid / a.used_f4, c = tid - r * a.used_f4;
+      while (r < rows) {
+        route_chunk(a, aligned, row0 + r, c, lds_f4(sbase + (size_t)r * row_bytes + c * 16));
+        r += q; c += rem;
+        if (c >= a.used_f4) { c -= a.used_f4; ++r; }
+      }
+    }
+    __syncthreads();   // every thread is done reading this stage before it is refilled
+    if (next < ntiles) issue(next, stage);
+    next += gridDim.x;
+    if (++stage == STAGES) { stage = 0; parity ^= 1; }
   }
 }
 
@@ -152,7 +298,7 @@ __global__ void __launch_bounds__(256, 4) rb_gather_wide(const GatherArgs a) {
 template <typename T>
 struct StoreArgs {
   float4* ring;
-  int D, A, row_f4;
+  int D, A, row_f4, used_f4;
   int64_t cap, ptr0;
   int64_t first, n;   // rows [first, n) of the inputs are written (first > 0 iff n > cap)
   const T *obs, *act, *rew, *nxt, *done;
@@ -172,7 +318,7 @@ __device__ __forceinline__ float fetch_field(const StoreArgs<T>& s, int64_t i, i
 
 template <typename T>
 __global__ void __launch_bounds__(256) rb_store_rows(const StoreArgs<T> s) {
-  const int64_t nchunks = (s.n - s.first) * s.row_f4;
+  const int64_t nchunks = (s.n - s.first) * s.row_f4;    // whole padded rows: full 128-byte lines
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int D4 = s.D >> 2;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nchunks; e += stride) {
@@ -222,7 +368,9 @@ struct Staging {
 }  // namespace ddrl
 
 struct ddrl_rb {
-  int device = 0, D = 0, A = 0, row_f = 0, row_f4 = 0, sms = 148;
+  int device = 0, D = 0, A = 0, row_f = 0, row_f4 = 0, used_f4 = 0, sms = 148, gather_u = 8;
+  int gather_mode = 0;            // 0 auto, 1 always bulk-async, 2 never (DDRL_GATHER_MODE)
+  int64_t bulk_min_bytes = 4 << 20;
   int64_t cap = 0, ptr = 0, size = 0, steps = 0, sample_times = 0;
   float* ring = nullptr;
   ddrl::Staging st_in, st_out, st_idx;
@@ -230,22 +378,65 @@ struct ddrl_rb {
 
 using namespace ddrl;
 
+static int launch_gather_bulk(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
+  constexpr int STAGES = 4;
+  const int row_bytes = rb->used_f4 * 16;
+  // ~16 KB of rows per stage, at most one row per thread, at least 4 rows
+  int R = 16384 / row_bytes;
+  if (R > 256) R = 256;
+  if (R < 4) R = 4;
+  const int stage_bytes = (R * row_bytes + 127) / 128 * 128;
+  const size_t smem = (size_t)STAGES * stage_bytes + STAGES * sizeof(uint64_t);
+  const bool narrow = rb->used_f4 <= 32;
+  int lanes = 2;
+  while (lanes < rb->used_f4) lanes <<= 1;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[narrow]) {
+    cudaError_t e = narrow ? cudaFuncSetAttribute(rb_gather_bulk<STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                           : cudaFuncSetAttribute(rb_gather_bulk<STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+    attr_set[narrow] = true;
+  }
+  const int64_t ntiles = (a.total + R - 1) / R;
+  int per_sm = (int)(220 * 1024 / (smem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = std::min<int64_t>(ntiles, (int64_t)rb->sms * per_sm);
+  if (narrow) rb_gather_bulk<STAGES, true><<<(int)blocks, 256, smem, st>>>(a, R, lanes);
+  else rb_gather_bulk<STAGES, false><<<(int)blocks, 256, smem, st>>>(a, R, lanes);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
   if (a.total <= 0) return 0;
+  // bulk-async pipeline for anything big enough to fill the chip; register path for small launches
+  // (measured on B200, C2 rows: 5.5 TB/s bulk vs 4.5 TB/s registers; C3 rows: 5.4 vs 5.65 TB/s, so wide
+  // rows keep the one-warp-per-row register kernel)
+  if (rb->gather_mode == 1 ||
+      (rb->gather_mode == 0 && rb->used_f4 <= 32 && a.total * rb->used_f4 * 16 >= (int64_t)rb->bulk_min_bytes))
+    return launch_gather_bulk(rb, a, st);
   const int threads = 256;
   const int max_blocks = rb->sms * 8;
-  if (rb->row_f4 <= 32) {
+  if (rb->used_f4 <= 32) {
     int lanes = 2;
-    while (lanes < rb->row_f4) lanes <<= 1;
+    while (lanes < rb->used_f4) lanes <<= 1;
     const int64_t rows_per_block = (threads / 32) * 32;
     int64_t blocks = (a.total + rows_per_block - 1) / rows_per_block;
     if (blocks > max_blocks) blocks = max_blocks;
+    const bool u8 = rb->gather_u >= 8;
     switch (lanes) {
-      case 2: rb_gather_narrow<2><<<(int)blocks, threads, 0, st>>>(a); break;
-      case 4: rb_gather_narrow<4><<<(int)blocks, threads, 0, st>>>(a); break;
-      case 8: rb_gather_narrow<8><<<(int)blocks, threads, 0, st>>>(a); break;
-      case 16: rb_gather_narrow<16><<<(int)blocks, threads, 0, st>>>(a); break;
-      default: rb_gather_narrow<32><<<(int)blocks, threads, 0, st>>>(a); break;
+      case 2: rb_gather_narrow<2, 2><<<(int)blocks, threads, 0, st>>>(a); break;
+      case 4: rb_gather_narrow<4, 4><<<(int)blocks, threads, 0, st>>>(a); break;
+      case 8: rb_gather_narrow<8, 4><<<(int)blocks, threads, 0, st>>>(a); break;
+      case 16:
+        if (u8) rb_gather_narrow<16, 8><<<(int)blocks, threads, 0, st>>>(a);
+        else rb_gather_narrow<16, 4><<<(int)blocks, threads, 0, st>>>(a);
+        break;
+      default:
+        if (u8) rb_gather_narrow<32, 8><<<(int)blocks, threads, 0, st>>>(a);
+        else rb_gather_narrow<32, 4><<<(int)blocks, threads, 0, st>>>(a);
+        break;
     }
   } else {
     const int64_t rows_per_block = (threads / 32) * 8;
@@ -263,7 +454,7 @@ static int launch_store(ddrl_rb* rb, const void* obs, const void* act, const voi
                         cudaStream_t st) {
   StoreArgs<T> s;
   s.ring = reinterpret_cast<float4*>(rb->ring);
-  s.D = rb->D; s.A = rb->A; s.row_f4 = rb->row_f4;
+  s.D = rb->D; s.A = rb->A; s.row_f4 = rb->row_f4; s.used_f4 = rb->used_f4;
   s.cap = rb->cap; s.ptr0 = ptr0;
   s.first = n > rb->cap ? n - rb->cap : 0;
   s.n = n;
@@ -297,8 +488,21 @@ int ddrl_rb_create(int device, int obs_dim, int act_dim, int64_t capacity, ddrl_
   ddrl_rb* rb = new ddrl_rb();
   rb->device = device;
   rb->D = obs_dim; rb->A = act_dim;
-  rb->row_f = ((2 * obs_dim + act_dim + 2) + 3) / 4 * 4;
-  rb->row_f4 = rb->row_f / 4;
+  rb->used_f4 = ((2 * obs_dim + act_dim + 2) + 3) / 4;
+  {
+    // Row stride.  DRAM is fetched in 64..128-byte granules: a row that straddles granules drags in
+    // bytes of its neighbours (measured: 302 B read per 224 B row at C2).  Rows longer than 128 B are
+    // therefore padded to a 128-byte multiple (C2 224 -> 256 B, C3 3088 -> 3200 B); shorter rows stay
+    // 16-byte packed (C1: 80 B, L2-resident at 1e6 rows).  DDRL_ROW_ALIGN=<bytes> overrides.
+    int align = (rb->used_f4 * 16 > 128) ? 128 : 16;
+    if (const char* e = getenv("DDRL_ROW_ALIGN")) { int v = atoi(e); if (v >= 16 && v % 16 == 0) align = v; }
+    const int bytes = (rb->used_f4 * 16 + align - 1) / align * align;
+    rb->row_f4 = bytes / 16;
+    rb->row_f = rb->row_f4 * 4;
+    if (const char* e = getenv("DDRL_GATHER_U")) rb->gather_u = atoi(e);
+    if (const char* e = getenv("DDRL_GATHER_MODE")) rb->gather_mode = atoi(e);
+    if (const char* e = getenv("DDRL_BULK_MIN_BYTES")) rb->bulk_min_bytes = atoll(e);
+  }
   rb->cap = capacity;
   rb->sms = sm_count(device);
   const size_t bytes = (size_t)capacity * rb->row_f * sizeof(float);
@@ -413,7 +617,7 @@ int ddrl_rb_sample(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t
   DeviceGuard guard(rb->device);
   GatherArgs a;
   a.ring = reinterpret_cast<const float4*>(rb->ring);
-  a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4;
+  a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4; a.used_f4 = rb->used_f4;
   a.size = (uint64_t)rb->size; a.total = total;
   a.idx_in = d_idx_in; a.idx_mode = d_idx_in ? IDX_INJECT : IDX_PHILOX;
   a.seed = seed; a.counter = counter; a.rng_stream = rng_stream;
@@ -496,7 +700,7 @@ int ddrl_rb_export(ddrl_rb_t rb, float* d_obs1, float* d_obs2, float* d_acts, fl
   DeviceGuard guard(rb->device);
   GatherArgs a;
   a.ring = reinterpret_cast<const float4*>(rb->ring);
-  a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4;
+  a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4; a.used_f4 = rb->used_f4;
   a.size = (uint64_t)rb->cap; a.total = rb->cap;
   a.idx_in = nullptr; a.idx_mode = IDX_IDENTITY;
   a.seed = a.counter = 0; a.rng_stream = 0;
