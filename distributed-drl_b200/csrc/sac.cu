@@ -124,123 +124,213 @@ __device__ __forceinline__ float logp_term(const PolEl& e) {
   return __fsub_rn(pre, logf(__fadd_rn(e.clipped, 1e-6f)));
 }
 
-// rows [0,B): pass a = main pi(x); [B,2B): pass b = main pi(x2); [2B,3B): pass c = target pi(x2)
-__global__ void __launch_bounds__(256) k_policy_fwd(int B, int A, float act_scale, const float* __restrict__ HDa,
-                                                    const float* __restrict__ HDb, const float* __restrict__ HDc,
-                                                    const float* __restrict__ NOISE, float* A1, float* A3,
-                                                    float* LOGP1, float* LOGP2) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= 3 * B) return;
-  const int pass = g / B, row = g % B;
-  const float* hd = (pass == 0 ? HDa : pass == 1 ? HDb : HDc) + (size_t)row * 2 * A;
-  const float* eps = NOISE + ((size_t)pass * B + row) * A;
-  // reduce_sum over the action axis of the two terms separately, then subtract (core.py:32,86)
-  float gauss = 0.0f, squash = 0.0f;
-  for (int j = 0; j < A; ++j) {
-    const PolEl e = policy_elem(hd[j], hd[A + j], eps[j]);
-    const float pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)),
-                                                 1.8378770664093453f));
-    gauss = __fadd_rn(gauss, pre);
-    squash = __fadd_rn(squash, logf(__fadd_rn(e.clipped, 1e-6f)));
-    if (pass == 0) A1[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
-    else if (pass == 2) A3[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
-  }
-  const float logp = __fsub_rn(gauss, squash);
-  if (pass == 0) LOGP1[row] = logp;
-  else if (pass == 1) LOGP2[row] = logp;
+// ------------------------------------------------------------------------------------------------
+// Row-wise kernels: one warp per batch row.  The skinny layers (policy heads N = 2A, Q heads N = 1,
+// their dgrads with K = 2A / 1 / A) are dot products against a few KB of weights — they are fused with
+// the element-wise math that consumes them instead of being launched as 1-tile-wide GEMMs.
+// ------------------------------------------------------------------------------------------------
+constexpr int ROW_WARPS = 8;      // warps (= rows) per CTA
+constexpr int MAX_HEAD = 64;      // 2A <= 64
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-// gradient of pi_loss = mean(alpha*logp1 - q1_pi) wrt the head pre-activations of pass a, by the
-// chain rule of the reference op graph (see DESIGN.md "policy head backward").
-__global__ void __launch_bounds__(256) k_policy_bwd(const StepState* __restrict__ st, int B, int A, float act_scale,
-                                                    const float* __restrict__ HDa, const float* __restrict__ NOISE,
-                                                    const float* __restrict__ dA1, float* dHD) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+// out[j] = sum_k x[k] * Wt(k, j) (+ bias row), j in [0, n): weights row-major [K+1, ldw] when !w_trans
+// (forward: W[k*ldw + j]), or [n, ldw] when w_trans (dgrad against W^T: W[j*ldw + k]).  Results land in
+// sout[0..n) (shared, per warp), identical in every lane.
+__device__ __forceinline__ void warp_dots(const float* __restrict__ x, int K, const float* __restrict__ W, int ldw, int n,
+                                          bool w_trans, bool bias, float* sout, int lane) {
+  for (int j0 = 0; j0 < n; j0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0f;
+    for (int k = lane; k < K; k += 32) {
+      const float xv = x[k];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = j0 + jj;
+        if (j < n) acc[jj] = fmaf(xv, w_trans ? W[(size_t)j * ldw + k] : W[(size_t)k * ldw + j], acc[jj]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      float v = warp_sum(acc[jj]);
+      const int j = j0 + jj;
+      if (j < n) {
+        if (bias) v += W[(size_t)K * ldw + j];
+        if (lane == 0) sout[j] = v;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// policy heads + squashed-Gaussian sample / log-likelihood for the three policy passes
+// (pass 0: main pi(x) -> A1, LOGP1, HD;  pass 1: main pi(x2) -> LOGP2;  pass 2: target pi(x2) -> A3)
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_fwd(
+    int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
+    const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2) {
+  __shared__ float s_out[ROW_WARPS][MAX_HEAD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * ROW_WARPS + w;
+  if (g >= 3 * B) return;
+  const int pass = g / B, row = g % B;
+  const float* x = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
+  warp_dots(x, h2, pass == 2 ? Whead_t : Whead, 2 * A, 2 * A, false, true, s_out[w], lane);
+  const float* eps = NOISE + ((size_t)pass * B + row) * A;
+  float gauss = 0.0f, squash = 0.0f;
+  for (int j0 = 0; j0 < A; j0 += 32) {
+    const int j = j0 + lane;
+    float pre = 0.0f, sq = 0.0f;
+    if (j < A) {
+      const PolEl e = policy_elem(s_out[w][j], s_out[w][A + j], eps[j]);
+      pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
+      sq = logf(__fadd_rn(e.clipped, 1e-6f));
+      if (pass == 0) A1[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
+      else if (pass == 2) A3[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
+    }
+    // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
+    const int cnt = min(32, A - j0);
+    for (int t = 0; t < cnt; ++t) {
+      gauss = __fadd_rn(gauss, __shfl_sync(0xffffffffu, pre, t));
+      squash = __fadd_rn(squash, __shfl_sync(0xffffffffu, sq, t));
+    }
+  }
+  if (pass == 0) {
+    for (int j = lane; j < 2 * A; j += 32) HD[(size_t)row * 2 * A + j] = s_out[w][j];
+    if (lane == 0) LOGP1[row] = __fsub_rn(gauss, squash);
+  } else if (pass == 1 && lane == 0) {
+    LOGP2[row] = __fsub_rn(gauss, squash);
+  }
+}
+
+// Q heads of all five Q passes, Bellman target, the three losses (actor_learner.py:58-69), the
+// output-layer gradients dq, and dZ2 = dq (x) w3^T masked by relu'(H2) for the three differentiated
+// passes.  Loss sums: per-CTA partials in double, combined in CTA order by the last CTA to finish
+// (deterministic).
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
+    StepState* st, int B, int h2, float gamma, const float* __restrict__ H2d, const float* __restrict__ H2e,
+    const float* __restrict__ H2f, const float* __restrict__ H2g, const float* __restrict__ H2h,
+    const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
+    const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
+    const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
+    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL) {
+  __shared__ double s_part[ROW_WARPS][4];
+  __shared__ bool s_last;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + w;
+  const float alpha = st->alpha_cur;
+  const StepDyn& d = st->dyn;
+  double t_pi = 0.0, t_q1 = 0.0, t_q2 = 0.0, t_lp = 0.0;
+  if (row < B) {
+    const float *hd = H2d + (size_t)row * h2, *he = H2e + (size_t)row * h2, *hf = H2f + (size_t)row * h2,
+                *hg = H2g + (size_t)row * h2, *hh = H2h + (size_t)row * h2;
+    float qd = 0.f, qe = 0.f, qf = 0.f, qg = 0.f, qh = 0.f;
+    for (int k = lane; k < h2; k += 32) {
+      const float w1 = W3q1[k], w2 = W3q2[k];
+      qd = fmaf(hd[k], w1, qd);
+      qe = fmaf(he[k], w2, qe);
+      qf = fmaf(hf[k], w1, qf);
+      qg = fmaf(hg[k], W3q1t[k], qg);
+      qh = fmaf(hh[k], W3q2t[k], qh);
+    }
+    qd = warp_sum(qd) + W3q1[h2];
+    qe = warp_sum(qe) + W3q2[h2];
+    qf = warp_sum(qf) + W3q1[h2];
+    qg = warp_sum(qg) + W3q1t[h2];
+    qh = warp_sum(qh) + W3q2t[h2];
+    const float invB = 1.0f / (float)B;
+    const float lp1 = LOGP1[row];
+    const float min_q = fminf(qg, qh);
+    const float v_backup = __fsub_rn(min_q, __fmul_rn(alpha, LOGP2[row]));
+    const float q_backup = __fadd_rn(R[row], __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.0f, DN[row])), v_backup));
+    const float e1 = __fsub_rn(q_backup, qd), e2 = __fsub_rn(q_backup, qe);
+    const float dqd = -e1 * invB, dqe = -e2 * invB, dqf = -invB;
+    for (int k = lane; k < h2; k += 32) {
+      const float w1 = W3q1[k], w2 = W3q2[k];
+      dZ2d[(size_t)row * h2 + k] = hd[k] > 0.0f ? dqd * w1 : 0.0f;
+      dZ2e[(size_t)row * h2 + k] = he[k] > 0.0f ? dqe * w2 : 0.0f;
+      dZ2f[(size_t)row * h2 + k] = hf[k] > 0.0f ? dqf * w1 : 0.0f;
+    }
+    if (lane == 0) {
+      dQd[row] = dqd; dQe[row] = dqe;
+      if (d.out_q1) d.out_q1[row] = qd;
+      if (d.out_q2) d.out_q2[row] = qe;
+      if (d.out_logp) d.out_logp[row] = lp1;
+      t_pi = (double)__fsub_rn(__fmul_rn(alpha, lp1), qf);
+      t_q1 = (double)__fmul_rn(e1, e1);
+      t_q2 = (double)__fmul_rn(e2, e2);
+      t_lp = (double)lp1;
+    }
+  }
+  if (lane == 0) { s_part[w][0] = t_pi; s_part[w][1] = t_q1; s_part[w][2] = t_q2; s_part[w][3] = t_lp; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double acc = 0.0;
+    for (int i = 0; i < ROW_WARPS; ++i) acc += s_part[i][threadIdx.x];
+    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x < 4) {
+    __threadfence();
+    double acc = 0.0;
+    for (unsigned int i = 0; i < gridDim.x; ++i) acc += partials[(size_t)i * 4 + threadIdx.x];
+    const float v = (float)((threadIdx.x == 1 || threadIdx.x == 2 ? 0.5 : 1.0) * acc / B);
+    if (threadIdx.x < 3) { SCAL[threadIdx.x] = v; if (d.out_scalars) d.out_scalars[threadIdx.x] = v; }
+    else SCAL[4] = v;   // mean logp1 (entropy-alpha gradient; all-reduced across ranks by the host)
+    if (threadIdx.x == 0) { SCAL[3] = alpha; if (d.out_scalars) d.out_scalars[3] = alpha; *ticket = 0u; }
+  }
+}
+
+// gradient of pi_loss = mean(alpha*logp1 - q1_pi) wrt the policy head pre-activations (chain rule of
+// the reference op graph), fused with its two skinny neighbours:
+//   dA1  = dZ1(Q1(x,pi)) . W1q1[D:D+A, :]^T                 (input gradient of Q1 wrt the action)
+//   dZ2a = [dmu | dls] . Whead[0:h2, :]^T  masked by relu'(H2a)
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
+    const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
+    const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
+    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a) {
+  __shared__ float s_da[ROW_WARPS][MAX_HEAD];
+  __shared__ float s_dhd[ROW_WARPS][MAX_HEAD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + w;
   if (row >= B) return;
+  warp_dots(dZ1f + (size_t)row * h1, h1, W1q1_act, h1, A, true, false, s_da[w], lane);
   const float dlogp = st->alpha_cur / (float)B;
   const float* hd = HDa + (size_t)row * 2 * A;
   const float* eps = NOISE + (size_t)row * A;
-  for (int j = 0; j < A; ++j) {
+  for (int j = lane; j < A; j += 32) {
     const float mu = hd[j];
     const PolEl e = policy_elem(mu, hd[A + j], eps[j]);
     // logp -= log(clip_pass(1 - pi^2) + 1e-6):  d/dpi = +2 pi / (clipped + 1e-6) * dlogp
-    const float dpi = act_scale * dA1[(size_t)row * A + j] + dlogp * (2.0f * e.pi) / (e.clipped + 1e-6f);
+    const float dpi = act_scale * s_da[w][j] + dlogp * (2.0f * e.pi) / (e.clipped + 1e-6f);
     float du = dpi * e.omp;                          // tanh'(u) = 1 - pi^2 (unclipped, as TF's TanhGrad)
-    // gaussian term: pre = -0.5 (z^2 + 2 log_std + c)
-    const float dz = -dlogp * e.z;
+    const float dz = -dlogp * e.z;                   // gaussian term: pre = -0.5 (z^2 + 2 log_std + c)
     const float ddiff = dz / e.den;                  // d(pi_raw - mu)
     du += ddiff;
     const float dstd_den = -dz * e.z / e.den;        // through the denominator exp(log_std)+EPS
-    const float dmu = (du) - ddiff;                  // pi_raw path + (x - mu) path
+    const float dmu = du - ddiff;                    // pi_raw path + (x - mu) path
     const float dstd = du * eps[j] + dstd_den;       // pi_raw = mu + eps*std
-    const float dlog_std = dstd * e.std - dlogp;     // exp'  and the direct 2*log_std term
-    const float dls_t = 11.0f * dlog_std;
+    const float dlog_std = dstd * e.std - dlogp;     // exp' and the direct 2*log_std term
+    const float dls = 11.0f * dlog_std * (1.0f - e.ls_t * e.ls_t);
+    s_dhd[w][j] = dmu; s_dhd[w][A + j] = dls;
     dHD[(size_t)row * 2 * A + j] = dmu;
-    dHD[(size_t)row * 2 * A + A + j] = dls_t * (1.0f - e.ls_t * e.ls_t);
+    dHD[(size_t)row * 2 * A + A + j] = dls;
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// losses + output-layer gradients (algos/sac1/actor_learner.py:58-69); single CTA, deterministic.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  double r = 0.0;
-  if (threadIdx.x < 32) {
-    r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) sh[0] = r;
-  __syncthreads();
-  r = sh[0];
-  __syncthreads();
-  return r;
-}
-
-__global__ void __launch_bounds__(1024) k_losses(StepState* st, int B, float gamma, float lr, float target_entropy,
-                                                 const float* __restrict__ R, const float* __restrict__ DN,
-                                                 const float* __restrict__ LOGP1, const float* __restrict__ LOGP2,
-                                                 const float* __restrict__ Qd, const float* __restrict__ Qe,
-                                                 const float* __restrict__ Qf, const float* __restrict__ Qg,
-                                                 const float* __restrict__ Qh, float* dQd, float* dQe, float* dQf,
-                                                 float* SCAL) {
-  __shared__ double sh[32];
-  const float alpha = st->alpha_cur;
-  const StepDyn& d = st->dyn;
-  const float invB = 1.0f / (float)B;
-  double s_pi = 0.0, s_q1 = 0.0, s_q2 = 0.0, s_lp = 0.0;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    const float min_q = fminf(Qg[i], Qh[i]);
-    const float v_backup = __fsub_rn(min_q, __fmul_rn(alpha, LOGP2[i]));
-    const float q_backup = __fadd_rn(R[i], __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.0f, DN[i])), v_backup));
-    const float e1 = __fsub_rn(q_backup, Qd[i]), e2 = __fsub_rn(q_backup, Qe[i]);
-    s_pi += (double)__fsub_rn(__fmul_rn(alpha, LOGP1[i]), Qf[i]);
-    s_q1 += (double)__fmul_rn(e1, e1);
-    s_q2 += (double)__fmul_rn(e2, e2);
-    s_lp += (double)LOGP1[i];
-    dQd[i] = -e1 * invB;
-    dQe[i] = -e2 * invB;
-    dQf[i] = -invB;
-    if (d.out_q1) d.out_q1[i] = Qd[i];
-    if (d.out_q2) d.out_q2[i] = Qe[i];
-    if (d.out_logp) d.out_logp[i] = LOGP1[i];
-  }
-  s_pi = block_sum(s_pi, sh);
-  s_q1 = block_sum(s_q1, sh);
-  s_q2 = block_sum(s_q2, sh);
-  s_lp = block_sum(s_lp, sh);
-  if (threadIdx.x == 0) {
-    const float pi_loss = (float)(s_pi / B), q1_loss = (float)(0.5 * s_q1 / B), q2_loss = (float)(0.5 * s_q2 / B);
-    SCAL[0] = pi_loss; SCAL[1] = q1_loss; SCAL[2] = q2_loss; SCAL[3] = alpha;
-    SCAL[4] = (float)(s_lp / B);     // mean logp1 (alpha gradient, all-reduced across ranks by the host)
-    if (d.out_scalars) {
-      d.out_scalars[0] = pi_loss; d.out_scalars[1] = q1_loss; d.out_scalars[2] = q2_loss; d.out_scalars[3] = alpha;
-    }
+  __syncwarp();
+  const int n2 = 2 * A;
+  for (int n = lane; n < h2; n += 32) {
+    float acc = 0.0f;
+    const float* wr = Whead + (size_t)n * n2;
+    for (int j = 0; j < n2; ++j) acc = fmaf(s_dhd[w][j], wr[j], acc);
+    dZ2a[(size_t)row * h2 + n] = H2a[(size_t)row * h2 + n] > 0.0f ? acc : 0.0f;
   }
 }
 
@@ -320,7 +410,6 @@ using namespace ddrl;
 namespace {
 
 struct Group {
-  int cfg = 0;  // 0: 64x64 tiles, 1: 128x16 tiles
   std::vector<GemmProb> probs;
   GemmProb* d_probs = nullptr;
   int tiles = 0;
@@ -347,6 +436,8 @@ struct ddrl_sac {
   float *W = nullptr, *Wt = nullptr, *Mo = nullptr, *Vo = nullptr, *Gp = nullptr, *G = nullptr;
   StepState* st = nullptr;
   float* SCAL = nullptr;
+  double* partials = nullptr;       // per-CTA loss partial sums of k_qheads_losses
+  unsigned int* ticket = nullptr;   // its last-CTA-done counter
   // batch + activations
   float *X = nullptr, *X2 = nullptr, *ACT = nullptr, *R = nullptr, *DN = nullptr, *NOISE = nullptr;
   float *H1[8] = {}, *H2[8] = {}, *HD[3] = {}, *Q[5] = {};  // passes a..h ; heads a..c ; q d..h
@@ -386,9 +477,9 @@ Seg seg(const float* p, int ld, int w) { return Seg{p, ld, w}; }
 Seg none() { return Seg{nullptr, 0, 0}; }
 
 int finalize_group(Group& g) {
-  const int BM = g.cfg == 0 ? 64 : 128, BN = g.cfg == 0 ? 64 : 16;
   int t = 0;
   for (auto& p : g.probs) {
+    const int BM = p.cfg == 0 ? 64 : 128, BN = p.cfg == 0 ? 64 : 16;
     p.tiles_m = (p.M + BM - 1) / BM;
     p.tiles_n = (p.N + BN - 1) / BN;
     p.tile_begin = t;
@@ -404,22 +495,19 @@ int finalize_group(Group& g) {
 
 int launch_group(const Group& g, cudaStream_t s) {
   if (g.tiles == 0) return 0;
-  if (g.cfg == 0) gemm_grouped_f32<64, 64, 4, 4><<<g.tiles, 256, 0, s>>>(g.d_probs, (int)g.probs.size());
-  else gemm_grouped_f32<128, 16, 4, 2><<<g.tiles, 256, 0, s>>>(g.d_probs, (int)g.probs.size());
+  gemm_grouped_f32<<<g.tiles, 256, 0, s>>>(g.d_probs, (int)g.probs.size());
   DDRL_LAUNCH_CHECK();
   return 0;
 }
 
-// stage indices (element-wise kernels run after the stage listed)
-enum { ST_L1 = 0, ST_L2, ST_HEADS /*-> policy_fwd*/, ST_QL1, ST_QL2, ST_QHEADS /*-> losses*/, ST_B1, ST_B2, ST_B3
-       /*-> policy_bwd*/, ST_P1, ST_P2, ST_P3, ST_COUNT };
+// GEMM stages; the row-wise kernels (policy heads, Q heads + losses, policy backward) sit between them
+enum { ST_L1 = 0, ST_L2 /*-> k_policy_heads_fwd*/, ST_QL1, ST_QL2 /*-> k_qheads_losses*/, ST_BQ
+       /*-> k_policy_bwd_rows*/, ST_BP, ST_BP3, ST_COUNT };
 
-void add(std::vector<Group>& stage, const GemmProb& p) {
-  const int cfg = p.N <= 16 ? 1 : 0;
-  for (auto& g : stage)
-    if (g.cfg == cfg) { g.probs.push_back(p); return; }
-  Group g; g.cfg = cfg; g.probs.push_back(p);
-  stage.push_back(g);
+void add(std::vector<Group>& stage, GemmProb p) {
+  p.cfg = p.N <= 16 ? 1 : 0;
+  if (stage.empty()) stage.emplace_back();
+  stage[0].probs.push_back(p);
 }
 
 int build_plan(ddrl_sac* h, int B, Plan& pl) {
@@ -432,7 +520,7 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
   float *W = h->W, *Wt = h->Wt, *Gp = h->Gp;
   auto wg = [&](GemmProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
   enum { a = 0, b, c, d, e, f, g, hh };
-  // ---- forward, policies and the two data-action Q passes
+  // ---- forward: policies (a: main@x, b: main@x2, c: target@x2) and the data-action Q passes (d, e)
   const float* xin[5] = {h->X, h->X2, h->X2, h->X, h->X};
   const float* wsrc[5] = {W + h->o_pi1, W + h->o_pi1, Wt + h->o_pi1, W + h->o_q1[0], W + h->o_q2[0]};
   const float* wsrc2[5] = {W + h->o_pi2, W + h->o_pi2, Wt + h->o_pi2, W + h->o_q1[1], W + h->o_q2[1]};
@@ -442,49 +530,35 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
                              B, h1, D + (isq ? A : 0) + 1, EPI_RELU));
     add(pl.stages[ST_L2], mk(seg(h->H1[p], h1, h1), none(), 1, 0, wsrc2[p], h2, 0, h->H2[p], h2, B, h2, h1 + 1, EPI_RELU));
   }
-  const float* whead[3] = {W + h->o_pih, W + h->o_pih, Wt + h->o_pih};
-  for (int p = 0; p < 3; ++p)
-    add(pl.stages[ST_HEADS], mk(seg(h->H2[p], h2, h2), none(), 1, 0, whead[p], 2 * A, 0, h->HD[p], 2 * A, B, 2 * A, h2 + 1));
-  add(pl.stages[ST_HEADS], mk(seg(h->H2[d], h2, h2), none(), 1, 0, W + h->o_q1[2], 1, 0, h->Q[0], 1, B, 1, h2 + 1));
-  add(pl.stages[ST_HEADS], mk(seg(h->H2[e], h2, h2), none(), 1, 0, W + h->o_q2[2], 1, 0, h->Q[1], 1, B, 1, h2 + 1));
   // ---- forward, policy-action Q passes: f = Q1(x,a1), g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3)
   const float* xin2[3] = {h->X, h->X2, h->X2};
   const float* ain2[3] = {h->A1, h->A3, h->A3};
   const float* w1[3] = {W + h->o_q1[0], Wt + h->o_q1[0], Wt + h->o_q2[0]};
   const float* w2[3] = {W + h->o_q1[1], Wt + h->o_q1[1], Wt + h->o_q2[1]};
-  const float* w3[3] = {W + h->o_q1[2], Wt + h->o_q1[2], Wt + h->o_q2[2]};
   for (int p = 0; p < 3; ++p) {
     add(pl.stages[ST_QL1], mk(seg(xin2[p], D, D), seg(ain2[p], A, A), 1, 0, w1[p], h1, 0, h->H1[f + p], h1, B, h1,
                               D + A + 1, EPI_RELU));
     add(pl.stages[ST_QL2], mk(seg(h->H1[f + p], h1, h1), none(), 1, 0, w2[p], h2, 0, h->H2[f + p], h2, B, h2, h1 + 1, EPI_RELU));
-    add(pl.stages[ST_QHEADS], mk(seg(h->H2[f + p], h2, h2), none(), 1, 0, w3[p], 1, 0, h->Q[2 + p], 1, B, 1, h2 + 1));
   }
   // ---- backward of the three differentiated Q passes: 0 = d (Q1 data), 1 = e (Q2 data), 2 = f (Q1 pi-path)
   const int pass[3] = {d, e, f};
   const int64_t* oq[3] = {h->o_q1, h->o_q2, h->o_q1};
   for (int i = 0; i < 3; ++i) {
-    // dZ2 = dq (x) w3^T  masked by relu'(H2)
-    add(pl.stages[ST_B1], mk(seg(h->dQ[i], 1, 1), none(), 0, 0, W + oq[i][2], 1, 1, h->dZ2[i], h2, B, h2, 1, EPI_MASK,
-                             h->H2[pass[i]], h2));
-    // dZ1 = dZ2 . W2^T  masked by relu'(H1)
-    add(pl.stages[ST_B2], mk(seg(h->dZ2[i], h2, h2), none(), 0, 0, W + oq[i][1], h2, 1, h->dZ1[i], h1, B, h1, h2, EPI_MASK,
+    // dZ1 = dZ2 . W2^T  masked by relu'(H1)        (dZ2 comes from k_qheads_losses)
+    add(pl.stages[ST_BQ], mk(seg(h->dZ2[i], h2, h2), none(), 0, 0, W + oq[i][1], h2, 1, h->dZ1[i], h1, B, h1, h2, EPI_MASK,
                              h->H1[pass[i]], h1));
     if (i < 2) {
       // d[W3;b3] = [H2|1]^T dq ; d[W2;b2] = [H1|1]^T dZ2 ; d[W1;b1] = [x|a|1]^T dZ1
-      add(pl.stages[ST_B1], wg(mk(seg(h->H2[pass[i]], h2, h2), none(), 1, 1, h->dQ[i], 1, 0, Gp + oq[i][2], 1, h2 + 1, 1, B)));
-      add(pl.stages[ST_B2], wg(mk(seg(h->H1[pass[i]], h1, h1), none(), 1, 1, h->dZ2[i], h2, 0, Gp + oq[i][1], h2, h1 + 1, h2, B)));
-      add(pl.stages[ST_B3], wg(mk(seg(h->X, D, D), seg(h->ACT, A, A), 1, 1, h->dZ1[i], h1, 0, Gp + oq[i][0], h1, D + A + 1, h1, B)));
+      add(pl.stages[ST_BQ], wg(mk(seg(h->H2[pass[i]], h2, h2), none(), 1, 1, h->dQ[i], 1, 0, Gp + oq[i][2], 1, h2 + 1, 1, B)));
+      add(pl.stages[ST_BQ], wg(mk(seg(h->H1[pass[i]], h1, h1), none(), 1, 1, h->dZ2[i], h2, 0, Gp + oq[i][1], h2, h1 + 1, h2, B)));
+      add(pl.stages[ST_BP], wg(mk(seg(h->X, D, D), seg(h->ACT, A, A), 1, 1, h->dZ1[i], h1, 0, Gp + oq[i][0], h1, D + A + 1, h1, B)));
     }
   }
-  // dA1 = dZ1(f) . W1q1[D:D+A,:]^T
-  add(pl.stages[ST_B3], mk(seg(h->dZ1[2], h1, h1), none(), 0, 0, W + h->o_q1[0] + (int64_t)D * h1, h1, 1, h->dA1, A, B, A, h1));
-  // ---- policy backward (pass a)
-  add(pl.stages[ST_P1], mk(seg(h->dHD, 2 * A, 2 * A), none(), 0, 0, W + h->o_pih, 2 * A, 1, h->dZ2a, h2, B, h2, 2 * A, EPI_MASK,
-                           h->H2[a], h2));
-  add(pl.stages[ST_P1], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, 2 * A, h2 + 1, 2 * A, B)));
-  add(pl.stages[ST_P2], mk(seg(h->dZ2a, h2, h2), none(), 0, 0, W + h->o_pi2, h2, 1, h->dZ1a, h1, B, h1, h2, EPI_MASK, h->H1[a], h1));
-  add(pl.stages[ST_P2], wg(mk(seg(h->H1[a], h1, h1), none(), 1, 1, h->dZ2a, h2, 0, Gp + h->o_pi2, h2, h1 + 1, h2, B)));
-  add(pl.stages[ST_P3], wg(mk(seg(h->X, D, D), none(), 1, 1, h->dZ1a, h1, 0, Gp + h->o_pi1, h1, D + 1, h1, B)));
+  // ---- policy backward (pass a); dHD and dZ2a come from k_policy_bwd_rows
+  add(pl.stages[ST_BP], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, 2 * A, h2 + 1, 2 * A, B)));
+  add(pl.stages[ST_BP], mk(seg(h->dZ2a, h2, h2), none(), 0, 0, W + h->o_pi2, h2, 1, h->dZ1a, h1, B, h1, h2, EPI_MASK, h->H1[a], h1));
+  add(pl.stages[ST_BP], wg(mk(seg(h->H1[a], h1, h1), none(), 1, 1, h->dZ2a, h2, 0, Gp + h->o_pi2, h2, h1 + 1, h2, B)));
+  add(pl.stages[ST_BP3], wg(mk(seg(h->X, D, D), none(), 1, 1, h->dZ1a, h1, 0, Gp + h->o_pi1, h1, D + 1, h1, B)));
   for (auto& st : pl.stages)
     for (auto& g2 : st) {
       int rc = finalize_group(g2);
@@ -512,24 +586,25 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   }
   if ((rc = run_stage(pl, ST_L1, s))) return rc;
   if ((rc = run_stage(pl, ST_L2, s))) return rc;
-  if ((rc = run_stage(pl, ST_HEADS, s))) return rc;
-  k_policy_fwd<<<(3 * B + 255) / 256, 256, 0, s>>>(B, A, h->act_scale, h->HD[0], h->HD[1], h->HD[2], h->NOISE, h->A1,
-                                                   h->A3, h->LOGP1, h->LOGP2);
+  const int h1 = h->h1, h2 = h->h2;
+  k_policy_heads_fwd<<<(3 * B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
+      B, A, h2, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0], h->A1,
+      h->A3, h->LOGP1, h->LOGP2);
   DDRL_LAUNCH_CHECK();
   if ((rc = run_stage(pl, ST_QL1, s))) return rc;
   if ((rc = run_stage(pl, ST_QL2, s))) return rc;
-  if ((rc = run_stage(pl, ST_QHEADS, s))) return rc;
-  k_losses<<<1, 1024, 0, s>>>(h->st, B, h->gamma, h->lr, -(float)A, h->R, h->DN, h->LOGP1, h->LOGP2, h->Q[0], h->Q[1],
-                              h->Q[2], h->Q[3], h->Q[4], h->dQ[0], h->dQ[1], h->dQ[2], h->SCAL);
+  k_qheads_losses<<<(B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
+      h->st, B, h2, h->gamma, h->H2[3], h->H2[4], h->H2[5], h->H2[6], h->H2[7], h->W + h->o_q1[2], h->W + h->o_q2[2],
+      h->Wt + h->o_q1[2], h->Wt + h->o_q2[2], h->R, h->DN, h->LOGP1, h->LOGP2, h->dQ[0], h->dQ[1], h->dZ2[0], h->dZ2[1],
+      h->dZ2[2], h->partials, h->ticket, h->SCAL);
   DDRL_LAUNCH_CHECK();
-  if ((rc = run_stage(pl, ST_B1, s))) return rc;
-  if ((rc = run_stage(pl, ST_B2, s))) return rc;
-  if ((rc = run_stage(pl, ST_B3, s))) return rc;
-  k_policy_bwd<<<(B + 255) / 256, 256, 0, s>>>(h->st, B, A, h->act_scale, h->HD[0], h->NOISE, h->dA1, h->dHD);
+  if ((rc = run_stage(pl, ST_BQ, s))) return rc;
+  k_policy_bwd_rows<<<(B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
+      h->st, B, A, h1, h2, h->act_scale, h->HD[0], h->NOISE, h->dZ1[2], h->W + h->o_q1[0] + (int64_t)D * h1,
+      h->W + h->o_pih, h->H2[0], h->dHD, h->dZ2a);
   DDRL_LAUNCH_CHECK();
-  if ((rc = run_stage(pl, ST_P1, s))) return rc;
-  if ((rc = run_stage(pl, ST_P2, s))) return rc;
-  if ((rc = run_stage(pl, ST_P3, s))) return rc;
+  if ((rc = run_stage(pl, ST_BP, s))) return rc;
+  if ((rc = run_stage(pl, ST_BP3, s))) return rc;
   return 0;
 }
 
@@ -608,6 +683,8 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   *out = nullptr;
   if (obs_dim < 1 || act_dim < 1 || h1 < 1 || h2 < 1 || max_batch < 1)
     return fail(DDRL_EINVAL, "ddrl_sac_create: obs_dim, act_dim, h1, h2, max_batch must be >= 1");
+  if (2 * act_dim > MAX_HEAD)
+    return fail(DDRL_EINVAL, "ddrl_sac_create: act_dim=%d > %d is not supported", act_dim, MAX_HEAD / 2);
   int ndev = 0;
   DDRL_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(DDRL_EINVAL, "ddrl_sac_create: device %d out of range", device);
@@ -639,6 +716,14 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   auto A_ = [&](float** p, size_t n) { if (!rc) rc = dalloc(h, p, n); };
   A_(&h->W, P); A_(&h->Wt, P); A_(&h->Mo, P); A_(&h->Vo, P); A_(&h->G, P); A_(&h->Gp, P * h->Smax);
   A_(&h->SCAL, 8);
+  {
+    float* tmp = nullptr;
+    A_(&tmp, 2 * 4 * ((size_t)(max_batch + ROW_WARPS - 1) / ROW_WARPS) + 4);
+    h->partials = reinterpret_cast<double*>(tmp);
+    tmp = nullptr;
+    A_(&tmp, 4);
+    h->ticket = reinterpret_cast<unsigned int*>(tmp);
+  }
   A_(&h->X, M * D); A_(&h->X2, M * D); A_(&h->ACT, M * A); A_(&h->R, M); A_(&h->DN, M); A_(&h->NOISE, 3 * M * A + 4);
   for (int p = 0; p < 8; ++p) { A_(&h->H1[p], M * h1); A_(&h->H2[p], M * h2); }
   for (int p = 0; p < 3; ++p) A_(&h->HD[p], M * 2 * A);

@@ -40,6 +40,7 @@ struct GemmProb {
   int ldmask;
   int splits, k_per_split;
   int tiles_m, tiles_n, tile_begin;
+  int cfg;  // tile shape: 0 = 64x64 (4x4 per thread), 1 = 128x16 (4x2 per thread, skinny N)
 };
 
 __device__ __forceinline__ float fetch_a(const GemmProb& P, int row, int feat) {
@@ -95,28 +96,19 @@ __device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, 
   }
 }
 
+constexpr int GEMM_BK = 32;
+constexpr int GEMM_SMEM_FLOATS = GEMM_BK * (128 + 4) + GEMM_BK * (64 + 4);
+
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(256) gemm_grouped_f32(const GemmProb* __restrict__ probs, int nprob) {
-  constexpr int BK = 32;
+__device__ __forceinline__ void gemm_tile(const GemmProb& P, float* smem_raw, int tile_in_prob) {
+  constexpr int BK = GEMM_BK;
   constexpr int TX = BN / TN;
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads per tile");
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
-  __shared__ GemmProb Psh;
-
+  float (*As)[BM + 4] = reinterpret_cast<float (*)[BM + 4]>(smem_raw);
+  float (*Bs)[BN + 4] = reinterpret_cast<float (*)[BN + 4]>(smem_raw + BK * (BM + 4));
   const int tid = threadIdx.x;
-  {
-    int pi = 0;
-    const int tile = blockIdx.x;
-    while (pi + 1 < nprob && tile >= probs[pi + 1].tile_begin) ++pi;
-    const int* src = reinterpret_cast<const int*>(probs + pi);
-    int* dst = reinterpret_cast<int*>(&Psh);
-    for (int i = tid; i < (int)(sizeof(GemmProb) / 4); i += 256) dst[i] = src[i];
-  }
-  __syncthreads();
-  const GemmProb P = Psh;  // registers / uniform
 
-  int t = blockIdx.x - P.tile_begin;
+  int t = tile_in_prob;
   const int per_split = P.tiles_m * P.tiles_n;
   const int split = t / per_split;
   t -= split * per_split;
@@ -181,6 +173,24 @@ __global__ void __launch_bounds__(256) gemm_grouped_f32(const GemmProb* __restri
       C[(size_t)m * P.ldc + n] = v;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) gemm_grouped_f32(const GemmProb* __restrict__ probs, int nprob) {
+  __shared__ __align__(16) float smem_raw[GEMM_SMEM_FLOATS];
+  __shared__ GemmProb Psh;
+  const int tid = threadIdx.x;
+  {
+    int pi = 0;
+    const int tile = blockIdx.x;
+    while (pi + 1 < nprob && tile >= probs[pi + 1].tile_begin) ++pi;
+    const int* src = reinterpret_cast<const int*>(probs + pi);
+    int* dst = reinterpret_cast<int*>(&Psh);
+    for (int i = tid; i < (int)(sizeof(GemmProb) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  const GemmProb P = Psh;  // registers / uniform
+  if (P.cfg == 0) gemm_tile<64, 64, 4, 4>(P, smem_raw, blockIdx.x - P.tile_begin);
+  else gemm_tile<128, 16, 4, 2>(P, smem_raw, blockIdx.x - P.tile_begin);
 }
 
 }  // namespace ddrl
