@@ -316,33 +316,58 @@ __device__ __forceinline__ float fetch_field(const StoreArgs<T>& s, int64_t i, i
   return 0.0f;
 }
 
+// Flat (row, chunk) map over the CTA's block of rows: consecutive threads write consecutive 16-byte
+// chunks of the ring (full 128-byte lines, whole padded rows), row/chunk recovered with a 32-bit
+// multiply-shift instead of a division, four independent chunks in flight per thread.
 template <typename T>
-__global__ void __launch_bounds__(256) rb_store_rows(const StoreArgs<T> s) {
-  const int64_t nchunks = (s.n - s.first) * s.row_f4;    // whole padded rows: full 128-byte lines
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ float4 load_chunk(const StoreArgs<T>& s, int64_t i, int c) {
   const int D4 = s.D >> 2;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nchunks; e += stride) {
-    const int64_t i = s.first + e / s.row_f4;
-    const int c = (int)(e % s.row_f4);
-    int64_t pos = (s.ptr0 + i) % s.cap;
-    float4 v;
-    bool done_vec = false;
-    if constexpr (sizeof(T) == 4) {
-      if (s.vec_ok && c < 2 * D4) {
-        const float* src = (c < D4) ? (const float*)s.obs + i * s.D + 4 * c
-                                    : (const float*)s.nxt + i * s.D + 4 * (c - D4);
-        v = ld_nc_f4(reinterpret_cast<const float4*>(src));
-        done_vec = true;
+  if constexpr (sizeof(T) == 4) {
+    if (s.vec_ok && c < 2 * D4) {
+      const float* src = (c < D4) ? (const float*)s.obs + i * s.D + 4 * c : (const float*)s.nxt + i * s.D + 4 * (c - D4);
+      return ld_nc_f4(reinterpret_cast<const float4*>(src));
+    }
+    if (s.vec_ok && (s.A & 3) == 0 && c < 2 * D4 + (s.A >> 2) && (((uintptr_t)s.act) & 15) == 0)
+      return ld_nc_f4(reinterpret_cast<const float4*>((const float*)s.act + i * s.A + 4 * (c - 2 * D4)));
+  }
+  if (c >= s.used_f4) return make_float4(0.f, 0.f, 0.f, 0.f);   // row padding
+  float4 v;
+  const int f = 4 * c;
+  v.x = fetch_field(s, i, f + 0);
+  v.y = fetch_field(s, i, f + 1);
+  v.z = fetch_field(s, i, f + 2);
+  v.w = fetch_field(s, i, f + 3);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) rb_store_rows(const StoreArgs<T> s, int rows_per_block, uint32_t magic) {
+  const int64_t nrows = s.n - s.first;
+  const uint32_t rf4 = (uint32_t)s.row_f4;
+  for (int64_t r0 = (int64_t)blockIdx.x * rows_per_block; r0 < nrows; r0 += (int64_t)gridDim.x * rows_per_block) {
+    const uint32_t rows = (uint32_t)min((int64_t)rows_per_block, nrows - r0);
+    const uint32_t nchunks = rows * rf4;
+    for (uint32_t e0 = threadIdx.x; e0 < nchunks; e0 += 4 * 256) {
+      float4 v[4];
+      int64_t dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t e = e0 + u * 256;
+        dst[u] = -1;
+        if (e < nchunks) {
+          const uint32_t lr = __umulhi(e, magic);          // e / row_f4 (exact for e < 2^22, see host)
+          const uint32_t c = e - lr * rf4;
+          const int64_t i = s.first + r0 + lr;
+          int64_t pos = s.ptr0 + i;                        // ptr0 < cap and i - first < cap
+          while (pos >= s.cap) pos -= s.cap;
+          v[u] = load_chunk(s, i, (int)c);
+          dst[u] = pos * s.row_f4 + c;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst[u] >= 0) st_f4(s.ring + dst[u], v[u]);
     }
-    if (!done_vec) {
-      const int f = 4 * c;
-      v.x = fetch_field(s, i, f + 0);
-      v.y = fetch_field(s, i, f + 1);
-      v.z = fetch_field(s, i, f + 2);
-      v.w = fetch_field(s, i, f + 3);
-    }
-    st_f4(s.ring + pos * s.row_f4 + c, v);
   }
 }
 
@@ -461,12 +486,17 @@ static int launch_store(ddrl_rb* rb, const void* obs, const void* act, const voi
   s.obs = (const T*)obs; s.act = (const T*)act; s.rew = (const T*)rew;
   s.nxt = (const T*)nxt; s.done = (const T*)done;
   s.vec_ok = sizeof(T) == 4 && (rb->D % 4 == 0) && (((uintptr_t)obs | (uintptr_t)nxt) % 16 == 0);
-  const int64_t nchunks = (s.n - s.first) * s.row_f4;
+  // rows per CTA pass: ~4 chunks per thread, at least one row
+  int rows_per_block = (4 * 256 + rb->row_f4 - 1) / rb->row_f4;
+  if (rows_per_block < 1) rows_per_block = 1;
+  // magic for e / row_f4 by multiply-high: ceil(2^32 / d) is exact while e * d < 2^32 / ... ; e stays
+  // below rows_per_block * row_f4 <= 1024 + row_f4, so the error term e * (d - 2^32 mod d) / 2^32 < 1
+  const uint32_t magic = (uint32_t)((0x100000000ull + rb->row_f4 - 1) / rb->row_f4);
   const int threads = 256;
-  int64_t blocks = (nchunks + threads * 4 - 1) / (threads * 4);  // ~4 chunks per thread
+  int64_t blocks = ((s.n - s.first) + rows_per_block - 1) / rows_per_block;
   if (blocks < 1) blocks = 1;
   if (blocks > rb->sms * 8) blocks = rb->sms * 8;
-  rb_store_rows<T><<<(int)blocks, threads, 0, st>>>(s);
+  rb_store_rows<T><<<(int)blocks, threads, 0, st>>>(s, rows_per_block, magic);
   DDRL_LAUNCH_CHECK();
   return 0;
 }
