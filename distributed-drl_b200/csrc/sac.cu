@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "sac_gemm.cuh"
+#include "sac_gemm_tc.cuh"
 
 namespace ddrl {
 
@@ -380,21 +381,27 @@ __global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, i
 }
 
 // external (TF variable order: kernel, bias per dense layer; mu head then log_std head) <-> internal
-// flat layout.  Only the policy head block differs: internal [h2+1, 2A] = [Wmu|Wls ; bmu|bls].
-__global__ void __launch_bounds__(256) k_convert_layout(int64_t P, int64_t head_off, int h2, int A, int to_internal,
+// flat layout.  Internal blocks start on 16-byte boundaries (vector loads in the GEMM operand fetch)
+// and the policy head block is fused: internal [h2+1, 2A] = [Wmu|Wls ; bmu|bls].
+struct LayoutMap {
+  int nblk, head_idx, h2, A;
+  long long ext_off[9], int_off[9], size[9];
+};
+__global__ void __launch_bounds__(256) k_convert_layout(LayoutMap mp, int64_t Pext, int to_internal,
                                                         const float* __restrict__ src, float* dst, float* dst2) {
-  const int64_t head_sz = (int64_t)(h2 + 1) * 2 * A;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
-    int64_t j = i;  // i: external index, j: internal index
-    if (i >= head_off && i < head_off + head_sz) {
-      int64_t e = i - head_off;  // external: Wmu [h2,A], bmu [A], Wls [h2,A], bls [A]
-      const int64_t half = (int64_t)h2 * A + A;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Pext; i += stride) {
+    int b = 0;
+    while (b + 1 < mp.nblk && i >= mp.ext_off[b + 1]) ++b;
+    int64_t e = i - mp.ext_off[b];
+    if (b == mp.head_idx) {   // external: Wmu [h2,A], bmu [A], Wls [h2,A], bls [A]
+      const int64_t half = (int64_t)mp.h2 * mp.A + mp.A;
       const int which = e >= half;
       if (which) e -= half;
-      const int64_t r = e / A, c = e % A;  // r == h2 is the bias row
-      j = head_off + r * 2 * A + which * A + c;
+      const int64_t r = e / mp.A, c = e % mp.A;  // r == h2 is the bias row
+      e = r * 2 * mp.A + which * mp.A + c;
     }
+    const int64_t j = mp.int_off[b] + e;
     if (to_internal) { const float v = src[i]; dst[j] = v; if (dst2) dst2[j] = v; }
     else dst[i] = src[j];
   }
@@ -410,9 +417,9 @@ using namespace ddrl;
 namespace {
 
 struct Group {
-  std::vector<GemmProb> probs;
-  GemmProb* d_probs = nullptr;
-  int tiles = 0;
+  std::vector<GemmProb> probs, probs_tc;   // FFMA tiles (cfg 0/1) and tcgen05 tiles (cfg 2)
+  GemmGroup grp{}, grp_tc{};               // the same, packed as kernel parameters
+  int tiles = 0, tiles_tc = 0;
 };
 
 struct Plan {
@@ -429,7 +436,8 @@ struct ddrl_sac {
   int device = 0, D = 0, A = 0, h1 = 0, h2 = 0, maxB = 0, sms = 148;
   float gamma = 0.99f, polyak = 0.995f, lr = 1e-3f, alpha = 0.2f, act_scale = 1.0f;
   int auto_alpha = 0;
-  int64_t P = 0, P_pi = 0, P_q = 0;
+  int64_t P = 0, P_pi = 0, Pext = 0;   // P: internal (padded) float count; Pext: the reference's parameter count
+  LayoutMap map{};
   // offsets of the [K+1,N] blocks in the flat buffers
   int64_t o_pi1 = 0, o_pi2 = 0, o_pih = 0, o_q1[3] = {0, 0, 0}, o_q2[3] = {0, 0, 0};
   int Smax = 1;
@@ -446,6 +454,7 @@ struct ddrl_sac {
   std::vector<void*> allocs;
   std::map<int, Plan> plans;
   bool use_graph = true;
+  bool use_tc = false;   // tcgen05 3xTF32 GEMMs (DDRL_GEMM=tc) instead of FFMA tiles
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy
                                       // default stream, which cannot be captured); replay on the caller's
 };
@@ -476,27 +485,38 @@ GemmProb mk(Seg a0, Seg a1, int ones, int a_trans, const float* Bp, int ldb, int
 Seg seg(const float* p, int ld, int w) { return Seg{p, ld, w}; }
 Seg none() { return Seg{nullptr, 0, 0}; }
 
-int finalize_group(Group& g) {
+int pack(std::vector<GemmProb>& v, GemmGroup* g, int* tiles) {
+  if ((int)v.size() > GEMM_MAX_PROBS) return fail(DDRL_EINVAL, "too many GEMM problems in one stage (%d)", (int)v.size());
   int t = 0;
-  for (auto& p : g.probs) {
-    const int BM = p.cfg == 0 ? 64 : 128, BN = p.cfg == 0 ? 64 : 16;
+  g->nprob = (int)v.size();
+  for (size_t i = 0; i < v.size(); ++i) {
+    GemmProb& p = v[i];
+    const int BM = p.cfg == 0 ? 64 : 128, BN = p.cfg == 0 ? 64 : (p.cfg == 1 ? 16 : 128);
     p.tiles_m = (p.M + BM - 1) / BM;
     p.tiles_n = (p.N + BN - 1) / BN;
     p.tile_begin = t;
     t += p.tiles_m * p.tiles_n * p.splits;
+    g->p[i] = p;
   }
-  g.tiles = t;
-  cudaError_t e = cudaMalloc(&g.d_probs, g.probs.size() * sizeof(GemmProb));
-  if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(plan) failed: %s", cudaGetErrorString(e));
-  e = cudaMemcpy(g.d_probs, g.probs.data(), g.probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaMemcpy(plan) failed: %s", cudaGetErrorString(e));
+  *tiles = t;
   return 0;
 }
 
+int finalize_group(Group& g) {
+  int rc = pack(g.probs, &g.grp, &g.tiles);
+  if (rc) return rc;
+  return pack(g.probs_tc, &g.grp_tc, &g.tiles_tc);
+}
+
 int launch_group(const Group& g, cudaStream_t s) {
-  if (g.tiles == 0) return 0;
-  gemm_grouped_f32<<<g.tiles, 256, 0, s>>>(g.d_probs, (int)g.probs.size());
-  DDRL_LAUNCH_CHECK();
+  if (g.tiles_tc > 0) {
+    tc::gemm_grouped_tc<<<g.tiles_tc, 256, tc::SMEM_BYTES, s>>>(g.grp_tc);
+    DDRL_LAUNCH_CHECK();
+  }
+  if (g.tiles > 0) {
+    gemm_grouped_f32<<<g.tiles, 256, 0, s>>>(g.grp);
+    DDRL_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -504,10 +524,11 @@ int launch_group(const Group& g, cudaStream_t s) {
 enum { ST_L1 = 0, ST_L2 /*-> k_policy_heads_fwd*/, ST_QL1, ST_QL2 /*-> k_qheads_losses*/, ST_BQ
        /*-> k_policy_bwd_rows*/, ST_BP, ST_BP3, ST_COUNT };
 
+bool g_plan_tc = false;   // set by build_plan from the handle (tcgen05 path on / off)
 void add(std::vector<Group>& stage, GemmProb p) {
-  p.cfg = p.N <= 16 ? 1 : 0;
+  p.cfg = p.N <= 16 ? 1 : (g_plan_tc ? 2 : 0);
   if (stage.empty()) stage.emplace_back();
-  stage[0].probs.push_back(p);
+  (p.cfg == 2 ? stage[0].probs_tc : stage[0].probs).push_back(p);
 }
 
 int build_plan(ddrl_sac* h, int B, Plan& pl) {
@@ -517,6 +538,7 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
   pl.S = (B + kps - 1) / kps;
   if (pl.S > h->Smax) return fail(DDRL_EINVAL, "batch %d exceeds max_batch %d", B, h->maxB);
   pl.stages.assign(ST_COUNT, {});
+  g_plan_tc = h->use_tc;
   float *W = h->W, *Wt = h->Wt, *Gp = h->Gp;
   auto wg = [&](GemmProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
   enum { a = 0, b, c, d, e, f, g, hh };
@@ -697,19 +719,32 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   h->sms = sm_count(device);
   const char* ng = getenv("DDRL_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
-  const int D = obs_dim, A = act_dim;
-  int64_t o = 0;
-  h->o_pi1 = o; o += (int64_t)(D + 1) * h1;
-  h->o_pi2 = o; o += (int64_t)(h1 + 1) * h2;
-  h->o_pih = o; o += (int64_t)(h2 + 1) * 2 * A;
-  h->P_pi = o;
-  for (int q = 0; q < 2; ++q) {
-    int64_t* oq = q == 0 ? h->o_q1 : h->o_q2;
-    oq[0] = o; o += (int64_t)(D + A + 1) * h1;
-    oq[1] = o; o += (int64_t)(h1 + 1) * h2;
-    oq[2] = o; o += (int64_t)(h2 + 1);
+  if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] == 't');
+  if (const char* dbg = getenv("DDRL_TC_DEBUG")) { int v = atoi(dbg); cudaMemcpyToSymbol(tc::g_tc_debug, &v, sizeof(int)); }
+  if (h->use_tc) {
+    cudaError_t ea = cudaFuncSetAttribute(tc::gemm_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (ea != cudaSuccess) { delete h; return fail(DDRL_ECUDA, "cudaFuncSetAttribute(tc smem): %s", cudaGetErrorString(ea)); }
   }
-  h->P = o; h->P_q = (o - h->P_pi) / 2;
+  const int D = obs_dim, A = act_dim;
+  {
+    // blocks in the reference's variable order; internal starts rounded up to 4 floats
+    const int64_t sizes[9] = {(int64_t)(D + 1) * h1, (int64_t)(h1 + 1) * h2, (int64_t)(h2 + 1) * 2 * A,
+                              (int64_t)(D + A + 1) * h1, (int64_t)(h1 + 1) * h2, (int64_t)(h2 + 1),
+                              (int64_t)(D + A + 1) * h1, (int64_t)(h1 + 1) * h2, (int64_t)(h2 + 1)};
+    int64_t* slots[9] = {&h->o_pi1, &h->o_pi2, &h->o_pih, &h->o_q1[0], &h->o_q1[1], &h->o_q1[2],
+                         &h->o_q2[0], &h->o_q2[1], &h->o_q2[2]};
+    int64_t o = 0, e = 0;
+    h->map.nblk = 9; h->map.head_idx = 2; h->map.h2 = h2; h->map.A = A;
+    for (int b = 0; b < 9; ++b) {
+      o = (o + 3) / 4 * 4;
+      if (b == 3) h->P_pi = o;
+      *slots[b] = o;
+      h->map.ext_off[b] = e; h->map.int_off[b] = o; h->map.size[b] = sizes[b];
+      o += sizes[b]; e += sizes[b];
+    }
+    h->P = (o + 3) / 4 * 4;
+    h->Pext = e;
+  }
   h->Smax = (max_batch + 255) / 256;
   int rc = 0;
   const size_t P = (size_t)h->P, M = (size_t)max_batch;
@@ -753,7 +788,6 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
   for (auto& kv : h->plans) {
     Plan& pl = kv.second;
     for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply}) if (ex) cudaGraphExecDestroy(ex);
-    for (auto& st : pl.stages) for (auto& g : st) if (g.d_probs) cudaFree(g.d_probs);
   }
   for (void* p : h->allocs) cudaFree(p);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -761,14 +795,13 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
   return 0;
 }
 
-int64_t ddrl_sac_param_count(ddrl_sac_t h) { return h ? h->P : -1; }
+int64_t ddrl_sac_param_count(ddrl_sac_t h) { return h ? h->Pext : -1; }
 
 int ddrl_sac_set_weights(ddrl_sac_t h, const float* d_flat, int also_target, void* stream) {
   if (!h || !d_flat) return fail(DDRL_EINVAL, "ddrl_sac_set_weights: NULL argument");
   DeviceGuard guard(h->device);
-  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
-  k_convert_layout<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->P, h->o_pih, h->h2, h->A, 1, d_flat, h->W,
-                                                             also_target ? h->Wt : nullptr);
+  int blocks = (int)std::min<int64_t>((h->Pext + 255) / 256, h->sms * 8);
+  k_convert_layout<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->map, h->Pext, 1, d_flat, h->W, also_target ? h->Wt : nullptr);
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -778,8 +811,8 @@ int ddrl_sac_get_weights(ddrl_sac_t h, float* d_flat, int which, void* stream) {
   const float* src = which == 0 ? h->W : which == 1 ? h->Wt : which == 2 ? h->Mo : which == 3 ? h->Vo : which == 4 ? h->G : nullptr;
   if (!src) return fail(DDRL_EINVAL, "ddrl_sac_get_weights: which=%d not in 0..4", which);
   DeviceGuard guard(h->device);
-  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
-  k_convert_layout<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->P, h->o_pih, h->h2, h->A, 0, src, d_flat, nullptr);
+  int blocks = (int)std::min<int64_t>((h->Pext + 255) / 256, h->sms * 8);
+  k_convert_layout<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->map, h->Pext, 0, src, d_flat, nullptr);
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -835,6 +868,18 @@ int ddrl_sac_grad_buffer(ddrl_sac_t h, float** d_grads, int64_t* count, float** 
 int ddrl_sac_apply_grads(ddrl_sac_t h, int batch, void* stream) {
   return step_common(h, MODE_APPLY, nullptr, nullptr, nullptr, nullptr, nullptr, batch, nullptr, 0, 1.0f, nullptr,
                      nullptr, nullptr, nullptr, stream, "ddrl_sac_apply_grads");
+}
+
+int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* stream) {
+  if (!h) return fail(DDRL_EINVAL, "ddrl_sac_debug_stage: NULL handle");
+  DeviceGuard guard(h->device);
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  if (stage < 0 || stage >= ST_COUNT) return fail(DDRL_EINVAL, "ddrl_sac_debug_stage: stage %d not in [0,%d)", stage, (int)ST_COUNT);
+  for (int i = 0; i < reps; ++i)
+    if ((rc = run_stage(*pl, stage, (cudaStream_t)stream))) return rc;
+  return 0;
 }
 
 int ddrl_sac_state(ddrl_sac_t h, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream) {

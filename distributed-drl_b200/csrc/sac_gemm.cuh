@@ -43,11 +43,23 @@ struct GemmProb {
   int cfg;  // tile shape: 0 = 64x64 (4x4 per thread), 1 = 128x16 (4x2 per thread, skinny N)
 };
 
-__device__ __forceinline__ float fetch_a(const GemmProb& P, int row, int feat) {
-  if (feat < P.a0.w) return P.a0.p[(size_t)row * P.a0.ld + feat];
-  feat -= P.a0.w;
-  if (feat < P.a1.w) return P.a1.p[(size_t)row * P.a1.ld + feat];
-  return (P.a_ones && feat == P.a1.w) ? 1.0f : 0.0f;
+// predicated (branch-free) global load: all operand loads of a tile are issued back to back; a
+// branchy formulation serialises them on the L2 latency (measured: 8000+ cycles per k-block)
+__device__ __forceinline__ float ld_pred(const float* p, bool pred) {
+  float v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.f32 %0, [%1];\n\t}"
+      : "=f"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+
+// element (row, feat) of the virtual concat A = [a0 | a1 | 1]; `ok` = inside the tile's bounds
+__device__ __forceinline__ float fetch_a(const GemmProb& P, int row, int feat, bool ok = true) {
+  const bool s0 = feat < P.a0.w;
+  const int f1 = feat - P.a0.w;
+  const bool s1 = !s0 && f1 < P.a1.w;
+  const float* p = s0 ? P.a0.p + (size_t)row * P.a0.ld + feat : P.a1.p + (size_t)row * P.a1.ld + f1;
+  const float v = ld_pred(p, ok && (s0 || s1));
+  return (ok && !s0 && !s1 && P.a_ones && f1 == P.a1.w) ? 1.0f : v;
 }
 
 // global -> register fetch of one (BM x BK) A tile slice and one (BK x BN) B tile slice
@@ -66,7 +78,7 @@ __device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, 
       const int i = tid + e * 256;
       const int kl = i % BK, ml = i / BK;
       const int m = m0 + ml, k = k0 + kl;
-      r.a[e] = (m < P.M && k < kend) ? fetch_a(P, m, k) : 0.0f;
+      r.a[e] = fetch_a(P, m, k, m < P.M && k < kend);
     }
   } else {
 #pragma unroll
@@ -74,7 +86,7 @@ __device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, 
       const int i = tid + e * 256;
       const int ml = i % BM, kl = i / BM;
       const int m = m0 + ml, k = k0 + kl;
-      r.a[e] = (m < P.M && k < kend) ? fetch_a(P, k, m) : 0.0f;
+      r.a[e] = fetch_a(P, k, m, m < P.M && k < kend);
     }
   }
   if (!P.b_trans) {
@@ -83,7 +95,7 @@ __device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, 
       const int i = tid + e * 256;
       const int nl = i % BN, kl = i / BN;
       const int n = n0 + nl, k = k0 + kl;
-      r.b[e] = (n < P.N && k < kend) ? P.B[(size_t)k * P.ldb + n] : 0.0f;
+      r.b[e] = ld_pred(P.B + (size_t)k * P.ldb + n, n < P.N && k < kend);
     }
   } else {
 #pragma unroll
@@ -91,7 +103,7 @@ __device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, 
       const int i = tid + e * 256;
       const int kl = i % BK, nl = i / BK;
       const int n = n0 + nl, k = k0 + kl;
-      r.b[e] = (n < P.N && k < kend) ? P.B[(size_t)n * P.ldb + k] : 0.0f;
+      r.b[e] = ld_pred(P.B + (size_t)n * P.ldb + k, n < P.N && k < kend);
     }
   }
 }
@@ -175,20 +187,19 @@ __device__ __forceinline__ void gemm_tile(const GemmProb& P, float* smem_raw, in
   }
 }
 
-__global__ void __launch_bounds__(256) gemm_grouped_f32(const GemmProb* __restrict__ probs, int nprob) {
+// The problem descriptors travel as kernel parameters (constant bank): a CTA finds its problem
+// without any dependent global load (a descriptor array in global memory cost ~4 us per launch).
+constexpr int GEMM_MAX_PROBS = 12;
+struct GemmGroup {
+  int nprob;
+  GemmProb p[GEMM_MAX_PROBS];
+};
+
+__global__ void __launch_bounds__(256, 3) gemm_grouped_f32(const __grid_constant__ GemmGroup grp) {
   __shared__ __align__(16) float smem_raw[GEMM_SMEM_FLOATS];
-  __shared__ GemmProb Psh;
-  const int tid = threadIdx.x;
-  {
-    int pi = 0;
-    const int tile = blockIdx.x;
-    while (pi + 1 < nprob && tile >= probs[pi + 1].tile_begin) ++pi;
-    const int* src = reinterpret_cast<const int*>(probs + pi);
-    int* dst = reinterpret_cast<int*>(&Psh);
-    for (int i = tid; i < (int)(sizeof(GemmProb) / 4); i += 256) dst[i] = src[i];
-  }
-  __syncthreads();
-  const GemmProb P = Psh;  // registers / uniform
+  int pi = 0;
+  while (pi + 1 < grp.nprob && (int)blockIdx.x >= grp.p[pi + 1].tile_begin) ++pi;
+  const GemmProb P = grp.p[pi];   // into registers (indexed constant-bank reads in the inner loops are slow)
   if (P.cfg == 0) gemm_tile<64, 64, 4, 4>(P, smem_raw, blockIdx.x - P.tile_begin);
   else gemm_tile<128, 16, 4, 2>(P, smem_raw, blockIdx.x - P.tile_begin);
 }

@@ -171,6 +171,8 @@ int ddrl_sac_compute_grads(ddrl_sac_t sac, const float* d_obs1, const float* d_o
                            float* d_out_logp, void* stream);
 int ddrl_sac_grad_buffer(ddrl_sac_t sac, float** d_grads, int64_t* count, float** d_alpha_stat);
 int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
+/* profiling aid: enqueue GEMM stage `stage` (0..6: L1, L2, QL1, QL2, BQ, BP, BP3) of the step `reps` times */
+int ddrl_sac_debug_stage(ddrl_sac_t sac, int batch, int stage, int reps, void* stream);
 /* optimiser step counters and log_alpha (synchronises `stream`).  Any out may be NULL. */
 int ddrl_sac_state(ddrl_sac_t sac, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream);
 
