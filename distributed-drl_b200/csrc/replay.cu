@@ -15,6 +15,7 @@
 //   rb_store_rows<T>         SoA inputs -> packed rows, flat (row, chunk) mapping, 128-bit stores
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -34,7 +35,21 @@ struct GatherArgs {
   uint32_t rng_stream;
   float *o1, *o2, *oa, *orw, *od;
   int64_t* oidx;
+  // global-uniform mode over a replay sharded across GPUs: index g addresses row g - cum[s] of shard s,
+  // whose ring is a peer mapping (cudaIpc) read directly over NVLink.  nshards == 0: local ring only.
+  int nshards;
+  const float4* rings[8];
+  int64_t cum[9];
 };
+
+__device__ __forceinline__ const float4* row_ptr(const GatherArgs& a, int64_t g) {
+  if (a.nshards == 0) return a.ring + g * a.row_f4;
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < a.nshards && g >= a.cum[i]) s = i;
+  return a.rings[s] + (g - a.cum[s]) * a.row_f4;
+}
 
 __device__ __forceinline__ void route_scalar(const GatherArgs& a, int64_t b, int f, float x) {
   const int D = a.D, A = a.A;
@@ -128,7 +143,6 @@ __global__ void __launch_bounds__(256, U >= 8 ? 2 : ((LANES == 8 || LANES == 16)
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const bool lane_live = l < a.used_f4;
   const LaneRoute route = make_route(a, l);
-  const float4* lane_ring = a.ring + l;
 
   for (int64_t base = warp * 32; base < a.total; base += nwarps * 32) {
     const int64_t mine = base + lane;
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(256, U >= 8 ? 2 : ((LANES == 8 || LANES == 16)
         const int r = (p0 + u) * RPP + g;
         const int64_t src = shfl_i64(myidx, r);
         ok[u] = lane_live && (base + r) < a.total;
-        if (ok[u]) v[u] = ld_nc_f4(lane_ring + src * a.row_f4);
+        if (ok[u]) v[u] = ld_nc_f4(row_ptr(a, src) + l);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -175,7 +189,7 @@ __global__ void __launch_bounds__(256, 4) rb_gather_wide(const GatherArgs a) {
       const int64_t b = base + r;
       const int64_t src = shfl_i64(myidx, r);
       if (b >= a.total) break;  // warp-uniform
-      const float4* row = a.ring + src * a.row_f4;
+      const float4* row = row_ptr(a, src);
       for (int c0 = lane; c0 < a.used_f4; c0 += 32 * 4) {
         float4 v[4];
 #pragma unroll
@@ -247,7 +261,7 @@ __global__ void __launch_bounds__(256) rb_gather_bulk(const GatherArgs a, int R,
       const int64_t ord = row0 + tid;
       const int64_t idx = draw_index(a, ord);
       if (a.oidx) a.oidx[ord] = idx;
-      bulk_g2s(smem + (size_t)stage * stage_bytes + (size_t)tid * row_bytes, a.ring + idx * a.row_f4, (uint32_t)row_bytes,
+      bulk_g2s(smem + (size_t)stage * stage_bytes + (size_t)tid * row_bytes, row_ptr(a, idx), (uint32_t)row_bytes,
                &bars[stage]);
     }
   };
@@ -399,6 +413,9 @@ struct ddrl_rb {
   int64_t cap = 0, ptr = 0, size = 0, steps = 0, sample_times = 0;
   float* ring = nullptr;
   ddrl::Staging st_in, st_out, st_idx;
+  int nshards = 0, my_shard = 0;
+  const float4* peer[8] = {};
+  bool peer_opened[8] = {};
 };
 
 using namespace ddrl;
@@ -438,8 +455,10 @@ static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
   // bulk-async pipeline for anything big enough to fill the chip; register path for small launches
   // (measured on B200, C2 rows: 5.5 TB/s bulk vs 4.5 TB/s registers; C3 rows: 5.4 vs 5.65 TB/s, so wide
   // rows keep the one-warp-per-row register kernel)
-  if (rb->gather_mode == 1 ||
-      (rb->gather_mode == 0 && rb->used_f4 <= 32 && a.total * rb->used_f4 * 16 >= (int64_t)rb->bulk_min_bytes))
+  // peer (NVLink) rows go through the register kernels: plain ld.global on the mapped peer pointer
+  if (a.nshards == 0 &&
+      (rb->gather_mode == 1 ||
+       (rb->gather_mode == 0 && rb->used_f4 <= 32 && a.total * rb->used_f4 * 16 >= (int64_t)rb->bulk_min_bytes)))
     return launch_gather_bulk(rb, a, st);
   const int threads = 256;
   const int max_blocks = rb->sms * 8;
@@ -556,6 +575,7 @@ int ddrl_rb_destroy(ddrl_rb_t rb) {
   if (!rb) return 0;
   DeviceGuard guard(rb->device);
   cudaDeviceSynchronize();
+  for (int s = 0; s < 8; ++s) if (rb->peer_opened[s]) cudaIpcCloseMemHandle(const_cast<float4*>(rb->peer[s]));
   if (rb->ring) cudaFree(rb->ring);
   rb->st_in.release(); rb->st_out.release(); rb->st_idx.release();
   delete rb;
@@ -653,6 +673,7 @@ int ddrl_rb_sample(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t
   a.seed = seed; a.counter = counter; a.rng_stream = rng_stream;
   a.o1 = d_out_obs1; a.o2 = d_out_obs2; a.oa = d_out_acts; a.orw = d_out_rews; a.od = d_out_done;
   a.oidx = d_out_idx;
+  a.nshards = 0;
   rc = launch_gather(rb, a, (cudaStream_t)stream);
   if (rc) return rc;
   rb->sample_times += n_batches;
@@ -702,6 +723,70 @@ int ddrl_rb_sample_host(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const in
   return 0;
 }
 
+int ddrl_rb_ipc_export(ddrl_rb_t rb, void* h_handle64) {
+  if (!rb || !h_handle64) return fail(DDRL_EINVAL, "ddrl_rb_ipc_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  DeviceGuard guard(rb->device);
+  cudaIpcMemHandle_t hd;
+  DDRL_CUDA(cudaIpcGetMemHandle(&hd, rb->ring));
+  memcpy(h_handle64, &hd, 64);
+  return 0;
+}
+
+int ddrl_rb_peer_attach(ddrl_rb_t rb, int n_shards, int shard, const void* h_handle64) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_peer_attach: NULL handle");
+  if (n_shards < 1 || n_shards > 8 || shard < 0 || shard >= n_shards)
+    return fail(DDRL_EINVAL, "ddrl_rb_peer_attach: shard %d of %d (max 8 shards)", shard, n_shards);
+  DeviceGuard guard(rb->device);
+  rb->nshards = n_shards;
+  if (!h_handle64) {          // this rank's own shard
+    rb->my_shard = shard;
+    rb->peer[shard] = reinterpret_cast<const float4*>(rb->ring);
+    return 0;
+  }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, h_handle64, 64);
+  void* p = nullptr;
+  DDRL_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  rb->peer[shard] = reinterpret_cast<const float4*>(p);
+  rb->peer_opened[shard] = true;
+  return 0;
+}
+
+int ddrl_rb_sample_global(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_shard_sizes,
+                          const int64_t* d_idx_in, uint64_t seed, uint64_t counter, uint32_t rng_stream,
+                          float* d_out_obs1, float* d_out_obs2, float* d_out_acts, float* d_out_rews,
+                          float* d_out_done, int64_t* d_out_idx, void* stream) {
+  if (!rb || !h_shard_sizes) return fail(DDRL_EINVAL, "ddrl_rb_sample_global: NULL argument");
+  if (rb->nshards < 1) return fail(DDRL_ESTATE, "ddrl_rb_sample_global: no shards attached (ddrl_rb_peer_attach)");
+  const int64_t total = batch * n_batches;
+  if (batch < 0 || n_batches < 0 || (double)batch * (double)n_batches >= 4294967296.0)
+    return fail(DDRL_EINVAL, "ddrl_rb_sample_global: bad batch / n_batches");
+  if (total > 0 && (!d_out_obs1 || !d_out_obs2 || !d_out_acts || !d_out_rews || !d_out_done))
+    return fail(DDRL_EINVAL, "ddrl_rb_sample_global: NULL output array");
+  GatherArgs a;
+  a.ring = reinterpret_cast<const float4*>(rb->ring);
+  a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4; a.used_f4 = rb->used_f4;
+  a.nshards = rb->nshards;
+  a.cum[0] = 0;
+  for (int s = 0; s < 8; ++s) {
+    a.rings[s] = s < rb->nshards ? rb->peer[s] : nullptr;
+    if (s < rb->nshards && !rb->peer[s]) return fail(DDRL_ESTATE, "ddrl_rb_sample_global: shard %d not attached", s);
+    a.cum[s + 1] = a.cum[s] + (s < rb->nshards ? h_shard_sizes[s] : 0);
+  }
+  if (a.cum[rb->nshards] == 0 && total > 0)
+    return fail(DDRL_EEMPTY, "ddrl_rb_sample_global: all shards are empty (the reference raises ValueError: high <= 0)");
+  a.size = (uint64_t)a.cum[rb->nshards]; a.total = total;
+  a.idx_in = d_idx_in; a.idx_mode = d_idx_in ? IDX_INJECT : IDX_PHILOX;
+  a.seed = seed; a.counter = counter; a.rng_stream = rng_stream;
+  a.o1 = d_out_obs1; a.o2 = d_out_obs2; a.oa = d_out_acts; a.orw = d_out_rews; a.od = d_out_done; a.oidx = d_out_idx;
+  DeviceGuard guard(rb->device);
+  int rc = launch_gather(rb, a, (cudaStream_t)stream);
+  if (rc) return rc;
+  rb->sample_times += n_batches;
+  return 0;
+}
+
 int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity, int64_t* steps,
                    int64_t* sample_times) {
   if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_counts: NULL handle");
@@ -735,6 +820,7 @@ int ddrl_rb_export(ddrl_rb_t rb, float* d_obs1, float* d_obs2, float* d_acts, fl
   a.idx_in = nullptr; a.idx_mode = IDX_IDENTITY;
   a.seed = a.counter = 0; a.rng_stream = 0;
   a.o1 = d_obs1; a.o2 = d_obs2; a.oa = d_acts; a.orw = d_rews; a.od = d_done; a.oidx = nullptr;
+  a.nshards = 0;
   return launch_gather(rb, a, (cudaStream_t)stream);
 }
 

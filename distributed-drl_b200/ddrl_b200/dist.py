@@ -121,3 +121,110 @@ class DistributedParameterServer:
         import pickle
         with open(name + "weights.pickle", "wb") as f:
             pickle.dump(dict(self.get_weights()), f)
+
+
+class ShardedReplayBuffer:
+    """One replay ring per rank (GPU) of a node + the two sampling modes of SURVEY.md §8(e).
+
+    local  : each learner samples its own shard — the reference's behaviour (one shard per call,
+             algos/sac1/sac_ray.py:137-141), no communication at all;
+    global : indices are uniform over ALL stored transitions of ALL shards; rows that live on another
+             GPU are read by the gather kernel straight from the peer's ring over NVLink (CUDA IPC
+             mapping, ddrl_rb_peer_attach), still without a data-path collective.
+    `connect()` is the only collective (an all_gather of the 64-byte IPC handles); `refresh_sizes()`
+    all-gathers the shard fill counts (call it after store phases; sizes are constant once full)."""
+
+    def __init__(self, obs_dim, act_dim, total_size, group=None, device=None, **kw):
+        import ctypes as C
+        from .replay import ReplayBuffer
+        self._C = C
+        self.group = group
+        self.world, self.rank = world_size(group), rank(group)
+        if self.world > 8:
+            raise ValueError("one node: at most 8 shards")
+        self.map = ShardMap(total_size, self.world)
+        kw.setdefault("rng_stream", self.rank)
+        self.local = ReplayBuffer(obs_dim, act_dim, self.map.cap, device=device, **kw)
+        self.sizes = [0] * self.world
+        self._connected = False
+
+    # local pass-throughs (the reference call surface)
+    def store(self, *a):
+        return self.local.store(*a)
+
+    def store_batch(self, *a):
+        return self.local.store_batch(*a)
+
+    def get_counts(self):
+        return self.local.get_counts()
+
+    def connect(self):
+        from . import _native as N
+        C = self._C
+        lib = N.lib()
+        self.local.flush()
+        buf = (C.c_ubyte * 64)()
+        N.check(lib.ddrl_rb_ipc_export(self.local._h, buf))
+        mine = bytes(buf)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=self.group)
+        else:
+            handles = [mine]
+        for s, h in enumerate(handles):
+            if s == self.rank:
+                N.check(lib.ddrl_rb_peer_attach(self.local._h, self.world, s, None))
+            else:
+                N.check(lib.ddrl_rb_peer_attach(self.local._h, self.world, s, C.c_char_p(h)))
+        self._connected = True
+        self.refresh_sizes()
+
+    def refresh_sizes(self):
+        self.local.flush()
+        torch.cuda.synchronize(self.local.device)     # our own stores are visible before peers learn the size
+        mine = int(self.local.size)
+        if self.world > 1:
+            out = [None] * self.world
+            dist.all_gather_object(out, mine, group=self.group)
+            self.sizes = [int(x) for x in out]
+        else:
+            self.sizes = [mine]
+        return self.sizes
+
+    def sample_batch(self, batch_size=128, *, mode="local", idxs=None, device=True, return_idxs=False):
+        if mode == "local":
+            return self.local.sample_batch(batch_size, idxs=idxs, device=device, return_idxs=return_idxs)
+        if mode != "global":
+            raise ValueError(mode)
+        if not self._connected:
+            raise RuntimeError("call connect() on every rank before global sampling")
+        from . import _native as N
+        C = self._C
+        rb = self.local
+        rb.flush()
+        n = int(batch_size)
+        if sum(self.sizes) == 0:
+            raise ValueError("high <= 0")
+        dev = torch.device("cuda", rb.device)
+        D, A = rb.obs_dim, rb.act_dim
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = dict(obs1=torch.empty((n, D), **f32), obs2=torch.empty((n, D), **f32), acts=torch.empty((n, A), **f32),
+                   rews=torch.empty(n, **f32), done=torch.empty(n, **f32))
+        o_idx = torch.empty(n, dtype=torch.int64, device=dev) if return_idxs else None
+        d_idx = None
+        if idxs is not None:
+            d_idx = torch.as_tensor(idxs, dtype=torch.int64).reshape(-1).to(dev).contiguous()
+        sizes = (C.c_int64 * self.world)(*self.sizes)
+        s = torch.cuda.current_stream(rb.device)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        seed = 0 if idxs is not None else rb._philox_seed()
+        N.check(N.lib().ddrl_rb_sample_global(rb._h, n, 1, sizes, p(d_idx), seed, rb._counter, rb._rng_stream,
+                                              p(out["obs1"]), p(out["obs2"]), p(out["acts"]), p(out["rews"]),
+                                              p(out["done"]), p(o_idx), C.c_void_p(s.cuda_stream)))
+        if idxs is None:
+            rb._counter += 1
+        if return_idxs:
+            out["idxs"] = o_idx
+        if not device:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        return out

@@ -104,6 +104,25 @@ int ddrl_rb_sample_host(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const in
 /* bytes ddrl_rb_sample_host writes for n = batch*n_batches rows */
 int64_t ddrl_rb_sample_block_bytes(ddrl_rb_t rb, int64_t n);
 
+/* Replay sharded over the GPUs of one node (the reference shards replay into several buffer actors and
+ * picks one shard per call, algos/sac1/sac_ray.py:137-141,246).  Each rank owns one ring; for the
+ * GLOBAL-UNIFORM mode every rank maps its peers' rings (CUDA IPC) and the gather kernel reads remote
+ * rows directly over NVLink — no collective on the data path.
+ *   ddrl_rb_ipc_export   64-byte handle of this ring (exchange it with torch.distributed all_gather)
+ *   ddrl_rb_peer_attach  register shard `shard` of `n_shards` (<= 8): h_handle64 == NULL marks this
+ *                        rank's own ring, otherwise the peer's exported handle is opened
+ *   ddrl_rb_sample_global  like ddrl_rb_sample, but indices address the concatenation of all shards:
+ *                        g in [0, sum(h_shard_sizes)) -> shard s, row g - sum(sizes[:s]); h_shard_sizes
+ *                        are the current fill counts of the shards (host array, n_shards entries).
+ *                        The caller orders remote stores against this call (e.g. a barrier between
+ *                        the store phase and the sample phase of a synchronous step). */
+int ddrl_rb_ipc_export(ddrl_rb_t rb, void* h_handle64);
+int ddrl_rb_peer_attach(ddrl_rb_t rb, int n_shards, int shard, const void* h_handle64);
+int ddrl_rb_sample_global(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_shard_sizes,
+                          const int64_t* d_idx_in, uint64_t seed, uint64_t counter, uint32_t rng_stream,
+                          float* d_out_obs1, float* d_out_obs2, float* d_out_acts, float* d_out_rews,
+                          float* d_out_done, int64_t* d_out_idx, void* stream);
+
 /* ReplayBuffer.get_counts()  (algos/sac1/sac1.py:62-63) plus ptr / capacity.  Any out may be NULL. */
 int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity, int64_t* steps,
                    int64_t* sample_times);

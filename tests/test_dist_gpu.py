@@ -72,3 +72,56 @@ def test_two_gpu_step_equals_single_gpu_on_concatenated_batch():
         assert np.abs(ret[r][0] - want_m).max() <= 2e-5 * np.abs(want_m).max()
         assert np.abs(ret[r][1] - want_t).max() <= 2e-5 * np.abs(want_t).max()
         assert ret[r][2] == 3.0 and ret[r][3] == 3.0
+
+
+def _global_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from ddrl_b200.dist import ShardedReplayBuffer
+    from oracle.make_golden import make_inputs
+    Dd, Aa, total = 24, 4, 600                       # 300 rows per shard
+    srb = ShardedReplayBuffer(Dd, Aa, total, device=rank, seed=9)
+    n_local = 300 if rank == 0 else 220              # ragged fill: shard 1 is not full
+    obs, act, rew, nxt, done = make_inputs(Dd, Aa, n_local, seed=50 + rank)
+    srb.store_batch(obs, act, rew, nxt, done)
+    srb.connect()
+    dist.barrier()
+    g = np.random.Generator(np.random.PCG64(3))
+    idx = g.integers(0, 520, 257)                    # global indices over 300 + 220 stored rows
+    out = srb.sample_batch(257, mode="global", idxs=idx, device=False)
+    drawn = srb.sample_batch(64, mode="global", device=True, return_idxs=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ret[rank] = (out, srb.sizes, drawn["idxs"].cpu().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_global_uniform_gather_reads_peer_shards_over_p2p():
+    import torch.multiprocessing as mp
+    import __graft_entry__
+    __graft_entry__.build()
+    from oracle.make_golden import make_inputs
+    from oracle.replay_oracle import ReplayRingOracle
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_global_worker, args=(2, port, ret), nprocs=2, join=True)
+    # oracle: the concatenation of both shards' stored rows (300 + 220)
+    ora = ReplayRingOracle(24, 4, 520)
+    for r, n in ((0, 300), (1, 220)):
+        obs, act, rew, nxt, done = make_inputs(24, 4, n, seed=50 + r)
+        ora.store_batch(obs, act, rew, nxt, done)
+    g = np.random.Generator(np.random.PCG64(3))
+    idx = g.integers(0, 520, 257)
+    want = ora.sample_batch(257, idxs=idx)
+    for r in (0, 1):
+        out, sizes, drawn = ret[r]
+        assert sizes == [300, 220]
+        for k in want:
+            assert np.array_equal(out[k].view(np.uint32), want[k].view(np.uint32)), (r, k)
+        assert drawn.min() >= 0 and drawn.max() < 520
