@@ -336,6 +336,59 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
 }
 
 // ------------------------------------------------------------------------------------------------
+// Actor inference (Actor.get_action, algos/sac1/actor_learner.py:195-197): mu / pi of the MAIN policy
+// for n observations — one warp per observation, the whole 2-layer MLP + heads in one kernel (n is 1
+// per env step in the reference; vectorised rollouts pass n = number of envs).
+// ------------------------------------------------------------------------------------------------
+constexpr int ACT_MAX_H = 512;
+__global__ void __launch_bounds__(128) k_actor_forward(int n, int D, int A, int h1, int h2, float act_scale, int deterministic,
+                                                       const float* __restrict__ OBS, const float* __restrict__ W1,
+                                                       const float* __restrict__ W2, const float* __restrict__ Whead,
+                                                       const float* __restrict__ noise, unsigned long long seed,
+                                                       unsigned long long counter, float* OUT) {
+  __shared__ float s_h1[4][ACT_MAX_H];
+  __shared__ float s_h2[4][ACT_MAX_H];
+  __shared__ float s_out[4][MAX_HEAD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + w;
+  if (row >= n) return;
+  const float* x = OBS + (size_t)row * D;
+  for (int j = lane; j < h1; j += 32) {          // W1: [D+1, h1], bias = last row
+    float acc = W1[(size_t)D * h1 + j];
+    for (int k = 0; k < D; ++k) acc = fmaf(x[k], W1[(size_t)k * h1 + j], acc);
+    s_h1[w][j] = fmaxf(acc, 0.0f);
+  }
+  __syncwarp();
+  for (int j = lane; j < h2; j += 32) {
+    float acc = W2[(size_t)h1 * h2 + j];
+    for (int k = 0; k < h1; ++k) acc = fmaf(s_h1[w][k], W2[(size_t)k * h2 + j], acc);
+    s_h2[w][j] = fmaxf(acc, 0.0f);
+  }
+  __syncwarp();
+  warp_dots(s_h2[w], h2, Whead, 2 * A, 2 * A, false, true, s_out[w], lane);
+  for (int j = lane; j < A; j += 32) {
+    float eps = 0.0f;
+    if (!deterministic) {
+      if (noise) eps = noise[(size_t)row * A + j];
+      else {
+        const unsigned long long e = (unsigned long long)row * A + j;
+        const Philox4 p = philox4x32_10((uint32_t)(e >> 2), (uint32_t)counter, (uint32_t)(counter >> 32), 0xAC70u,
+                                        (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint32_t ua = (e & 2) ? p.z : p.x, ub = (e & 2) ? p.w : p.y;
+        const float u0 = ((float)ua + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)ub + 0.5f) * 2.3283064365386963e-10f;
+        const float r = sqrtf(-2.0f * logf(fmaxf(u0, 1e-30f)));
+        float sn, cs;
+        sincospif(2.0f * u1, &sn, &cs);
+        eps = (e & 1) ? r * sn : r * cs;
+      }
+    }
+    const float mu = s_out[w][j];
+    const PolEl e = policy_elem(mu, s_out[w][A + j], eps);
+    OUT[(size_t)row * A + j] = __fmul_rn(deterministic ? tanhf(mu) : e.pi, act_scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // optimiser: TF1 Adam (epsilon-hat form) for pi and q parameter ranges, then polyak with the new
 // weights (actor_learner.py:73-87); gradients arrive as S split-K partials (S = 1 after all-reduce).
 // ------------------------------------------------------------------------------------------------
@@ -868,6 +921,20 @@ int ddrl_sac_grad_buffer(ddrl_sac_t h, float** d_grads, int64_t* count, float** 
 int ddrl_sac_apply_grads(ddrl_sac_t h, int batch, void* stream) {
   return step_common(h, MODE_APPLY, nullptr, nullptr, nullptr, nullptr, nullptr, batch, nullptr, 0, 1.0f, nullptr,
                      nullptr, nullptr, nullptr, stream, "ddrl_sac_apply_grads");
+}
+
+int ddrl_sac_act(ddrl_sac_t h, const float* d_obs, int n, int deterministic, const float* d_noise, uint64_t seed,
+                 uint64_t counter, float* d_out_act, void* stream) {
+  if (!h || !d_obs || !d_out_act) return fail(DDRL_EINVAL, "ddrl_sac_act: NULL argument");
+  if (n < 1) return fail(DDRL_EINVAL, "ddrl_sac_act: n=%d < 1", n);
+  if (h->h1 > ACT_MAX_H || h->h2 > ACT_MAX_H)
+    return fail(DDRL_EINVAL, "ddrl_sac_act: hidden sizes above %d are not supported", ACT_MAX_H);
+  DeviceGuard guard(h->device);
+  k_actor_forward<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, h->D, h->A, h->h1, h->h2, h->act_scale, deterministic, d_obs,
+                                                                 h->W + h->o_pi1, h->W + h->o_pi2, h->W + h->o_pih, d_noise, seed,
+                                                                 counter, d_out_act);
+  DDRL_LAUNCH_CHECK();
+  return 0;
 }
 
 int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* stream) {

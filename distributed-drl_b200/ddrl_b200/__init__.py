@@ -8,7 +8,7 @@ All numerics run in libddrl_b200.so (hand-written sm_100a CUDA, C ABI in include
 """
 from .replay import ReplayBuffer  # noqa: F401
 from .ps import ParameterServer  # noqa: F401
-from .learner import Learner  # noqa: F401
+from .learner import Actor, Learner  # noqa: F401
 from . import _native  # noqa: F401
 
-__all__ = ["ReplayBuffer", "ParameterServer", "Learner"]
+__all__ = ["ReplayBuffer", "ParameterServer", "Learner", "Actor"]

@@ -290,3 +290,59 @@ class Learner(object):
 
     def apply_gradients(self, gradients):
         pass
+
+
+class Actor(object):
+    """The reference's rollout-side policy (algos/sac1/actor_learner.py:151-229): holds the main
+    policy only, `set_weights` does NOT touch a target net, `get_action(o, deterministic)` returns
+    one action.  Inference runs on the GPU (ddrl_sac_act); `get_actions` is the vectorised form for
+    many environments per call."""
+
+    def __init__(self, opt, job="worker", *, device=None):
+        self._learner = Learner(opt, job, device=device, max_batch=1)
+        self.opt = opt
+        self.names = [n for n in self._learner.names if "/pi/" in n]
+        self._calls = 0
+        self._obs_stage = {}
+
+    def set_weights(self, variable_names, weights):
+        # assign by name; the rollout policy has no target network to re-initialise
+        L = self._learner
+        flat = torch.from_numpy(L._flat_from(variable_names, weights)).to(L._dev)
+        L.set_flat_weights(flat, also_target=False)
+
+    def get_weights(self):
+        keys, values = self._learner.get_weights()
+        keep = [i for i, k in enumerate(keys) if "/pi/" in k]       # variables reachable from self.pi
+        return [keys[i] for i in keep], [values[i] for i in keep]
+
+    def get_actions(self, obs, deterministic=False, noise=None):
+        L = self._learner
+        o = torch.as_tensor(np.asarray(obs, dtype=np.float32)).reshape(-1, L.obs_dim).to(L._dev).contiguous() \
+            if not (isinstance(obs, torch.Tensor) and obs.is_cuda) else obs.to(torch.float32).reshape(-1, L.obs_dim).contiguous()
+        n = int(o.shape[0])
+        out = torch.empty((n, L.act_dim), dtype=torch.float32, device=L._dev)
+        nz = None
+        if noise is not None:
+            nz = torch.as_tensor(noise, dtype=torch.float32).to(L._dev).contiguous()
+        s = L._stream()
+        self._calls += 1
+        N.check(L._lib.ddrl_sac_act(L._h, C.c_void_p(o.data_ptr()), n, 1 if deterministic else 0,
+                                    C.c_void_p(nz.data_ptr()) if nz is not None else None, L.seed + 7919, self._calls,
+                                    C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream)))
+        o.record_stream(s)
+        return out
+
+    def get_action(self, o, deterministic=False):
+        return self.get_actions(np.asarray(o).reshape(1, -1), deterministic)[0].cpu().numpy()
+
+    def test(self, test_env, replay_buffer=None, n=25):
+        rew = []
+        for _ in range(n):
+            o, d, ep_ret, ep_len = test_env.reset(), False, 0.0, 0
+            while not (d or ep_len == _opt_get(self.opt, "max_ep_len", 1000)):
+                o, r, d, _ = test_env.step(self.get_action(o, True))
+                ep_ret += r
+                ep_len += 1
+            rew.append(ep_ret)
+        return sum(rew) / n

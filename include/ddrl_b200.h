@@ -190,6 +190,11 @@ int ddrl_sac_compute_grads(ddrl_sac_t sac, const float* d_obs1, const float* d_o
                            float* d_out_logp, void* stream);
 int ddrl_sac_grad_buffer(ddrl_sac_t sac, float** d_grads, int64_t* count, float** d_alpha_stat);
 int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
+/* Actor.get_action(o, deterministic) (algos/sac1/actor_learner.py:195-197) for n observations at once:
+ * d_out_act[n, A] = act_scale * tanh(mu) (deterministic) or act_scale * tanh(mu + eps * std); eps from
+ * d_noise [n, A] or, when NULL, Philox keyed by (seed, counter).  Uses the handle's main policy weights. */
+int ddrl_sac_act(ddrl_sac_t sac, const float* d_obs, int n, int deterministic, const float* d_noise,
+                 uint64_t seed, uint64_t counter, float* d_out_act, void* stream);
 /* profiling aid: enqueue GEMM stage `stage` (0..6: L1, L2, QL1, QL2, BQ, BP, BP3) of the step `reps` times */
 int ddrl_sac_debug_stage(ddrl_sac_t sac, int batch, int stage, int reps, void* stream);
 /* optimiser step counters and log_alpha (synchronises `stream`).  Any out may be NULL. */
