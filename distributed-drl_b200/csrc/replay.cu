@@ -308,6 +308,69 @@ __global__ void __launch_bounds__(256) rb_gather_bulk(const GatherArgs a, int R,
   }
 }
 
+// ---- frame-deduplicated stack gather (Atari-shaped replay, BASELINE config C4) ------------------
+// The frame ring holds ONE frame (frame_f4 x 16 bytes) per env step; transition i is
+// obs1 = frames[i-S+1 .. i], obs2 = frames[i-S+2 .. i+1]  (S = stack depth), i.e. S+1 consecutive frames
+// instead of the 2S a naive obs1/obs2 row stores.  One warp per sampled transition streams the two
+// overlapping windows to the output rows; the S-1 shared frames are read twice but hit L1/L2.
+struct FrameArgs {
+  const float4* frames;     // [cap, frame_f4]
+  const float* act; const float* rew; const float* done;   // [cap] per-transition scalars
+  int frame_f4, stack;
+  int64_t cap, size, total;
+  const int64_t* idx_in;
+  int idx_mode;
+  uint64_t seed, counter;
+  uint32_t rng_stream;
+  float4 *o1, *o2;          // [total, stack*frame_f4]
+  float *oa, *orw, *od;
+  int64_t* oidx;
+};
+
+__global__ void __launch_bounds__(256, 4) fb_gather_frames(const FrameArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int row_f4 = a.stack * a.frame_f4;
+  for (int64_t b = warp; b < a.total; b += nwarps) {
+    int64_t i;
+    if (a.idx_mode == IDX_INJECT) i = a.idx_in[b];
+    else {  // valid stack windows only: i in [stack-1, size-2]
+      const uint64_t span = (uint64_t)(a.size - a.stack);
+      i = (a.stack - 1) + philox_index((uint64_t)b, a.seed, a.counter, a.rng_stream, span);
+    }
+    if (lane == 0) {
+      if (a.oidx) a.oidx[b] = i;
+      a.oa[b] = a.act[i]; a.orw[b] = a.rew[i]; a.od[b] = a.done[i];
+    }
+    const int64_t first = i - (a.stack - 1);          // oldest frame of obs1 (ring position, may wrap)
+    for (int c0 = lane; c0 < 2 * row_f4; c0 += 32 * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < 2 * row_f4) {
+          const int which = c >= row_f4;               // 0: obs1, 1: obs2 (window shifted by one frame)
+          const int cc = c - which * row_f4;
+          const int f = cc / a.frame_f4, within = cc - f * a.frame_f4;
+          int64_t fr = first + f + which;
+          fr %= a.cap; if (fr < 0) fr += a.cap;
+          v[k] = ld_nc_f4(a.frames + fr * a.frame_f4 + within);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < 2 * row_f4) {
+          const int which = c >= row_f4;
+          const int cc = c - which * row_f4;
+          st_f4((which ? a.o2 : a.o1) + b * row_f4 + cc, v[k]);
+        }
+      }
+    }
+  }
+}
+
 // ---- batched store --------------------------------------------------------------------------
 template <typename T>
 struct StoreArgs {
@@ -784,6 +847,38 @@ int ddrl_rb_sample_global(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const 
   int rc = launch_gather(rb, a, (cudaStream_t)stream);
   if (rc) return rc;
   rb->sample_times += n_batches;
+  return 0;
+}
+
+int ddrl_fb_sample_stack(int device, const void* d_frames, int64_t frame_bytes, int stack, int64_t capacity, int64_t size,
+                         const float* d_act, const float* d_rew, const float* d_done, int64_t batch,
+                         const int64_t* d_idx_in, uint64_t seed, uint64_t counter, uint32_t rng_stream,
+                         void* d_out_obs1, void* d_out_obs2, float* d_out_acts, float* d_out_rews, float* d_out_done,
+                         int64_t* d_out_idx, void* stream) {
+  if (!d_frames || !d_act || !d_rew || !d_done || !d_out_obs1 || !d_out_obs2 || !d_out_acts || !d_out_rews || !d_out_done)
+    return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: NULL array");
+  if (frame_bytes < 16 || frame_bytes % 16 != 0) return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: frame_bytes must be a multiple of 16");
+  if (stack < 1 || capacity < stack + 1 || size > capacity || batch < 0)
+    return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: bad stack / capacity / size / batch");
+  if (size < stack + 1 && batch > 0)
+    return fail(DDRL_EEMPTY, "ddrl_fb_sample_stack: fewer than stack+1 frames stored");
+  if (batch == 0) return 0;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DDRL_ECUDA, "ddrl_fb_sample_stack: cannot select device %d", device);
+  FrameArgs a;
+  a.frames = reinterpret_cast<const float4*>(d_frames);
+  a.act = d_act; a.rew = d_rew; a.done = d_done;
+  a.frame_f4 = (int)(frame_bytes / 16); a.stack = stack;
+  a.cap = capacity; a.size = size; a.total = batch;
+  a.idx_in = d_idx_in; a.idx_mode = d_idx_in ? IDX_INJECT : IDX_PHILOX;
+  a.seed = seed; a.counter = counter; a.rng_stream = rng_stream;
+  a.o1 = reinterpret_cast<float4*>(d_out_obs1); a.o2 = reinterpret_cast<float4*>(d_out_obs2);
+  a.oa = d_out_acts; a.orw = d_out_rews; a.od = d_out_done; a.oidx = d_out_idx;
+  const int sms = sm_count(device);
+  int64_t blocks = (batch + 7) / 8;
+  if (blocks > sms * 8) blocks = sms * 8;
+  fb_gather_frames<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  DDRL_LAUNCH_CHECK();
   return 0;
 }
 

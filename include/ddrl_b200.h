@@ -123,6 +123,20 @@ int ddrl_rb_sample_global(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const 
                           float* d_out_obs1, float* d_out_obs2, float* d_out_acts, float* d_out_rews,
                           float* d_out_done, int64_t* d_out_idx, void* stream);
 
+/* Frame-stack replay (BASELINE.json config 4; a synthetic extension — the reference has no uint8 frame
+ * buffer, its nearest relatives are the dqn-family ring algos/dqn/train.py:37-80 and the env-side
+ * FrameStack algos/trading_env.py:289-325).  Frames live in a caller-owned ring d_frames[capacity]
+ * of frame_bytes each (one frame per env step) with per-transition scalars d_act/d_rew/d_done[capacity];
+ * transition i is obs1 = frames[i-stack+1..i], obs2 = frames[i-stack+2..i+1] (ring positions, no
+ * episode-boundary handling).  Gathers `batch` transitions: injected indices (caller guarantees
+ * stack-1 <= i <= size-2 when the ring has not wrapped) or Philox-drawn uniformly over that range.
+ * Outputs: obs1, obs2 [batch, stack*frame_bytes] bytes; acts, rews, done [batch] f32. */
+int ddrl_fb_sample_stack(int device, const void* d_frames, int64_t frame_bytes, int stack, int64_t capacity,
+                         int64_t size, const float* d_act, const float* d_rew, const float* d_done,
+                         int64_t batch, const int64_t* d_idx_in, uint64_t seed, uint64_t counter,
+                         uint32_t rng_stream, void* d_out_obs1, void* d_out_obs2, float* d_out_acts,
+                         float* d_out_rews, float* d_out_done, int64_t* d_out_idx, void* stream);
+
 /* ReplayBuffer.get_counts()  (algos/sac1/sac1.py:62-63) plus ptr / capacity.  Any out may be NULL. */
 int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity, int64_t* steps,
                    int64_t* sample_times);
