@@ -43,10 +43,12 @@ struct StepState {  // persistent
   int auto_alpha;
   float alpha_const;
   float lr, lr_pi, lr_q;  // base rate and TF1 Adam's bias-corrected rates for this step
+  unsigned int mega_barrier;   // arrival counter of the persistent step kernel's grid barriers
 };
 
 __global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
   st->dyn = dyn;
+  st->mega_barrier = 0u;
   if (advance) {
     st->t_pi += 1;
     st->t_q += 1;
@@ -60,12 +62,11 @@ __global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
 }
 
 // copy the external batch into the learner's own buffers and materialise the noise
-__global__ void __launch_bounds__(256) k_prologue(const StepState* __restrict__ st, int B, int D, int A,
-                                                  float* X, float* X2, float* ACT, float* R, float* DN,
-                                                  float* NOISE) {
+__device__ __forceinline__ void d_prologue(int vb, int vgrid, const StepState* __restrict__ st, int B, int D, int A,
+                                           float* X, float* X2, float* ACT, float* R, float* DN, float* NOISE) {
   const StepDyn& d = st->dyn;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)vb * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)vgrid * blockDim.x;
   if (d.obs1) {
     for (int64_t i = tid; i < (int64_t)B * D; i += nthr) { X[i] = d.obs1[i]; X2[i] = d.obs2[i]; }
     for (int64_t i = tid; i < (int64_t)B * A; i += nthr) ACT[i] = d.acts[i];
@@ -93,6 +94,10 @@ __global__ void __launch_bounds__(256) k_prologue(const StepState* __restrict__ 
         if (4 * q + j < n) NOISE[4 * q + j] = z[j];
     }
   }
+}
+__global__ void __launch_bounds__(256) k_prologue(const StepState* __restrict__ st, int B, int D, int A, float* X, float* X2,
+                                                  float* ACT, float* R, float* DN, float* NOISE) {
+  d_prologue(blockIdx.x, gridDim.x, st, B, D, A, X, X2, ACT, R, DN, NOISE);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -171,13 +176,13 @@ __device__ __forceinline__ void warp_dots(const float* __restrict__ x, int K, co
 
 // policy heads + squashed-Gaussian sample / log-likelihood for the three policy passes
 // (pass 0: main pi(x) -> A1, LOGP1, HD;  pass 1: main pi(x2) -> LOGP2;  pass 2: target pi(x2) -> A3)
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_fwd(
-    int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
+__device__ __forceinline__ void d_policy_heads_fwd(
+    int vb, int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
     const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2) {
   __shared__ float s_out[ROW_WARPS][MAX_HEAD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * ROW_WARPS + w;
+  const int g = vb * ROW_WARPS + w;
   if (g >= 3 * B) return;
   const int pass = g / B, row = g % B;
   const float* x = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
@@ -208,13 +213,19 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_fwd(
     LOGP2[row] = __fsub_rn(gauss, squash);
   }
 }
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_fwd(
+    int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
+    const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2) {
+  d_policy_heads_fwd(blockIdx.x, B, A, h2, act_scale, H2a, H2b, H2c, Whead, Whead_t, NOISE, HD, A1, A3, LOGP1, LOGP2);
+}
 
 // Q heads of all five Q passes, Bellman target, the three losses (actor_learner.py:58-69), the
 // output-layer gradients dq, and dZ2 = dq (x) w3^T masked by relu'(H2) for the three differentiated
 // passes.  Loss sums: per-CTA partials in double, combined in CTA order by the last CTA to finish
 // (deterministic).
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
-    StepState* st, int B, int h2, float gamma, const float* __restrict__ H2d, const float* __restrict__ H2e,
+__device__ __forceinline__ void d_qheads_losses(
+    int vb, int vgrid, StepState* st, int B, int h2, float gamma, const float* __restrict__ H2d, const float* __restrict__ H2e,
     const float* __restrict__ H2f, const float* __restrict__ H2g, const float* __restrict__ H2h,
     const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
     const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
   __shared__ double s_part[ROW_WARPS][4];
   __shared__ bool s_last;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * ROW_WARPS + w;
+  const int row = vb * ROW_WARPS + w;
   const float alpha = st->alpha_cur;
   const StepDyn& d = st->dyn;
   double t_pi = 0.0, t_q1 = 0.0, t_q2 = 0.0, t_lp = 0.0;
@@ -273,35 +284,46 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
   if (threadIdx.x < 4) {
     double acc = 0.0;
     for (int i = 0; i < ROW_WARPS; ++i) acc += s_part[i][threadIdx.x];
-    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = acc;
+    partials[(size_t)vb * 4 + threadIdx.x] = acc;
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)vgrid - 1);
   __syncthreads();
   if (s_last && threadIdx.x < 4) {
     __threadfence();
     double acc = 0.0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) acc += partials[(size_t)i * 4 + threadIdx.x];
+    for (unsigned int i = 0; i < (unsigned int)vgrid; ++i) acc += partials[(size_t)i * 4 + threadIdx.x];
     const float v = (float)((threadIdx.x == 1 || threadIdx.x == 2 ? 0.5 : 1.0) * acc / B);
     if (threadIdx.x < 3) { SCAL[threadIdx.x] = v; if (d.out_scalars) d.out_scalars[threadIdx.x] = v; }
     else SCAL[4] = v;   // mean logp1 (entropy-alpha gradient; all-reduced across ranks by the host)
     if (threadIdx.x == 0) { SCAL[3] = alpha; if (d.out_scalars) d.out_scalars[3] = alpha; *ticket = 0u; }
   }
+  __syncthreads();   // shared scratch is reused by the next virtual block
+}
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
+    StepState* st, int B, int h2, float gamma, const float* __restrict__ H2d, const float* __restrict__ H2e,
+    const float* __restrict__ H2f, const float* __restrict__ H2g, const float* __restrict__ H2h,
+    const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
+    const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
+    const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
+    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL) {
+  d_qheads_losses(blockIdx.x, gridDim.x, st, B, h2, gamma, H2d, H2e, H2f, H2g, H2h, W3q1, W3q2, W3q1t, W3q2t, R, DN, LOGP1, LOGP2,
+                  dQd, dQe, dZ2d, dZ2e, dZ2f, partials, ticket, SCAL);
 }
 
 // gradient of pi_loss = mean(alpha*logp1 - q1_pi) wrt the policy head pre-activations (chain rule of
 // the reference op graph), fused with its two skinny neighbours:
 //   dA1  = dZ1(Q1(x,pi)) . W1q1[D:D+A, :]^T                 (input gradient of Q1 wrt the action)
 //   dZ2a = [dmu | dls] . Whead[0:h2, :]^T  masked by relu'(H2a)
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
-    const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
+__device__ __forceinline__ void d_policy_bwd_rows(
+    int vb, const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
     const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
     const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a) {
   __shared__ float s_da[ROW_WARPS][MAX_HEAD];
   __shared__ float s_dhd[ROW_WARPS][MAX_HEAD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * ROW_WARPS + w;
+  const int row = vb * ROW_WARPS + w;
   if (row >= B) return;
   warp_dots(dZ1f + (size_t)row * h1, h1, W1q1_act, h1, A, true, false, s_da[w], lane);
   const float dlogp = st->alpha_cur / (float)B;
@@ -333,6 +355,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
     for (int j = 0; j < n2; ++j) acc = fmaf(s_dhd[w][j], wr[j], acc);
     dZ2a[(size_t)row * h2 + n] = H2a[(size_t)row * h2 + n] > 0.0f ? acc : 0.0f;
   }
+}
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
+    const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
+    const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
+    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a) {
+  d_policy_bwd_rows(blockIdx.x, st, B, A, h1, h2, act_scale, HDa, NOISE, dZ1f, W1q1_act, Whead, H2a, dHD, dZ2a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,24 +420,27 @@ __global__ void __launch_bounds__(128) k_actor_forward(int n, int D, int A, int 
 // optimiser: TF1 Adam (epsilon-hat form) for pi and q parameter ranges, then polyak with the new
 // weights (actor_learner.py:73-87); gradients arrive as S split-K partials (S = 1 after all-reduce).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const float* __restrict__ Gp, float* G) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+__device__ __forceinline__ void d_grad_reduce(int vb, int vgrid, int64_t P, int S, const float* __restrict__ Gp, float* G) {
+  const int64_t stride = (int64_t)vgrid * blockDim.x;
+  for (int64_t i = (int64_t)vb * blockDim.x + threadIdx.x; i < P; i += stride) {
     float g = Gp[i];
     for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
     G[i] = g;
   }
 }
+__global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const float* __restrict__ Gp, float* G) {
+  d_grad_reduce(blockIdx.x, gridDim.x, P, S, Gp, G);
+}
 
-__global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, int64_t P_pi, int S,
+__device__ __forceinline__ void d_adam_polyak(int vb, int vgrid, StepState* st, int64_t P, int64_t P_pi, int S,
                                                      const float* __restrict__ Gp, float lr, float polyak,
                                                      float target_entropy, const float* __restrict__ SCAL,
                                                      float* W, float* Wt, float* Mo, float* Vo) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+  const int64_t stride = (int64_t)vgrid * blockDim.x;
+  for (int64_t i = (int64_t)vb * blockDim.x + threadIdx.x; i < P; i += stride) {
     float g = Gp[i];
     for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
     g *= gs;
@@ -422,7 +453,7 @@ __global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, i
   }
   // entropy-alpha (reference-intended semantics): one scalar Adam step, unordered wrt
   // the rest; uses the pre-update mean(logp1) of this step.
-  if (blockIdx.x == 0 && threadIdx.x == 0 && st->auto_alpha) {
+  if (vb == 0 && threadIdx.x == 0 && st->auto_alpha) {
     st->t_alpha += 1;
     const double ta = (double)st->t_alpha;
     const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
@@ -431,6 +462,11 @@ __global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, i
     st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * g * g;
     st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
   }
+}
+__global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, int64_t P_pi, int S, const float* __restrict__ Gp,
+                                                     float lr, float polyak, float target_entropy, const float* __restrict__ SCAL,
+                                                     float* W, float* Wt, float* Mo, float* Vo) {
+  d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo);
 }
 
 // external (TF variable order: kernel, bias per dense layer; mu head then log_std head) <-> internal
@@ -460,6 +496,103 @@ __global__ void __launch_bounds__(256) k_convert_layout(LayoutMap mp, int64_t Pe
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent whole-step kernel.  The step is 12 dependent phases of 5..45 us; as separate launches
+// each pays launch latency, a cold ramp and a tail where most SMs idle.  Here ONE cooperative grid
+// (a multiple of the SM count, all CTAs resident) walks the phases with grid-wide barriers in
+// between: tiles of a GEMM phase and row blocks of a row-wise phase are dealt round-robin to the CTAs.
+// ------------------------------------------------------------------------------------------------
+struct MegaArgs {
+  StepState* st;
+  const GemmGroup* stages;   // [ST_COUNT] in device memory
+  int tiles[8];
+  int mode;                  // 0: full step (ends with Adam + polyak), 1: gradients only (ends with the split-K reduce)
+  int B, D, A, h1, h2, S;
+  float act_scale, gamma, lr, polyak;
+  int64_t P, P_pi;
+  float *X, *X2, *ACT, *R, *DN, *NOISE;
+  float* H2[8];
+  float *HD0, *A1, *A3, *LOGP1, *LOGP2;
+  float *dQ0, *dQ1, *dZ2_0, *dZ2_1, *dZ2_2, *dZ1_2, *dHD, *dZ2a;
+  double* partials;
+  unsigned int* ticket;
+  unsigned int* barrier;     // zeroed by k_set_params
+  float *SCAL, *W, *Wt, *Mo, *Vo, *Gp, *G;
+  int64_t o_pih, o_q1_0, o_q1_2, o_q2_2;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void mega_gemm_phase(const GemmGroup* __restrict__ grp, int ntiles, float* smem_raw) {
+  __shared__ GemmGroup s_grp;     // the phase's descriptors, fetched once per CTA with coalesced loads
+  if ((int)blockIdx.x >= ntiles) return;
+  {
+    const int* src = reinterpret_cast<const int*>(grp);
+    int* dst = reinterpret_cast<int*>(&s_grp);
+    for (int i = threadIdx.x; i < (int)(sizeof(GemmGroup) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int pi = 0;
+    const int np = s_grp.nprob;
+    while (pi + 1 < np && tile >= s_grp.p[pi + 1].tile_begin) ++pi;
+    const GemmProb P = s_grp.p[pi];
+    if (P.cfg == 0) gemm_tile<64, 64, 4, 4>(P, smem_raw, tile - P.tile_begin);
+    else gemm_tile<128, 16, 4, 2>(P, smem_raw, tile - P.tile_begin);
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) k_sac_mega(const __grid_constant__ MegaArgs a) {
+  __shared__ __align__(16) float smem_raw[GEMM_SMEM_FLOATS];
+  const unsigned int G = gridDim.x;
+  unsigned int epoch = 0;
+  const int B = a.B, A = a.A, h1 = a.h1, h2 = a.h2;
+  const int nrow_blocks = (B + ROW_WARPS - 1) / ROW_WARPS;
+
+  d_prologue(blockIdx.x, G, a.st, B, a.D, A, a.X, a.X2, a.ACT, a.R, a.DN, a.NOISE);
+  grid_barrier(a.barrier, ++epoch * G);
+  mega_gemm_phase(a.stages + 0, a.tiles[0], smem_raw);                      // L1
+  grid_barrier(a.barrier, ++epoch * G);
+  mega_gemm_phase(a.stages + 1, a.tiles[1], smem_raw);                      // L2
+  grid_barrier(a.barrier, ++epoch * G);
+  for (int vb = blockIdx.x; vb < (3 * B + ROW_WARPS - 1) / ROW_WARPS; vb += G)
+    d_policy_heads_fwd(vb, B, A, h2, a.act_scale, a.H2[0], a.H2[1], a.H2[2], a.W + a.o_pih, a.Wt + a.o_pih, a.NOISE, a.HD0,
+                       a.A1, a.A3, a.LOGP1, a.LOGP2);
+  grid_barrier(a.barrier, ++epoch * G);
+  mega_gemm_phase(a.stages + 2, a.tiles[2], smem_raw);                      // QL1
+  grid_barrier(a.barrier, ++epoch * G);
+  mega_gemm_phase(a.stages + 3, a.tiles[3], smem_raw);                      // QL2
+  grid_barrier(a.barrier, ++epoch * G);
+  for (int vb = blockIdx.x; vb < nrow_blocks; vb += G)
+    d_qheads_losses(vb, nrow_blocks, a.st, B, h2, a.gamma, a.H2[3], a.H2[4], a.H2[5], a.H2[6], a.H2[7], a.W + a.o_q1_2,
+                    a.W + a.o_q2_2, a.Wt + a.o_q1_2, a.Wt + a.o_q2_2, a.R, a.DN, a.LOGP1, a.LOGP2, a.dQ0, a.dQ1, a.dZ2_0,
+                    a.dZ2_1, a.dZ2_2, a.partials, a.ticket, a.SCAL);
+  grid_barrier(a.barrier, ++epoch * G);
+  mega_gemm_phase(a.stages + 4, a.tiles[4], smem_raw);                      // BQ
+  grid_barrier(a.barrier, ++epoch * G);
+  for (int vb = blockIdx.x; vb < nrow_blocks; vb += G)
+    d_policy_bwd_rows(vb, a.st, B, A, h1, h2, a.act_scale, a.HD0, a.NOISE, a.dZ1_2, a.W + a.o_q1_0 + (int64_t)a.D * h1,
+                      a.W + a.o_pih, a.H2[0], a.dHD, a.dZ2a);
+  grid_barrier(a.barrier, ++epoch * G);
+  mega_gemm_phase(a.stages + 5, a.tiles[5], smem_raw);                      // BP
+  grid_barrier(a.barrier, ++epoch * G);
+  mega_gemm_phase(a.stages + 6, a.tiles[6], smem_raw);                      // BP3
+  grid_barrier(a.barrier, ++epoch * G);
+  if (a.mode == 0) d_adam_polyak(blockIdx.x, G, a.st, a.P, a.P_pi, a.S, a.Gp, a.lr, a.polyak, -(float)A, a.SCAL, a.W, a.Wt, a.Mo, a.Vo);
+  else d_grad_reduce(blockIdx.x, G, a.P, a.S, a.Gp, a.G);
+}
+
 }  // namespace ddrl
 
 // =================================================================================================
@@ -481,6 +614,8 @@ struct Plan {
   std::vector<std::vector<Group>> stages;  // ordered stages; element-wise kernels sit between them
   cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr;
   int64_t kernels[3] = {0, 0, 0};  // kernels inside each captured graph (for the launch counter)
+  GemmGroup* d_stages = nullptr;   // [ST_COUNT] descriptors for the persistent step kernel
+  int mega_grid = 0;
 };
 
 }  // namespace
@@ -508,6 +643,8 @@ struct ddrl_sac {
   std::map<int, Plan> plans;
   bool use_graph = true;
   bool use_tc = false;   // tcgen05 3xTF32 GEMMs (DDRL_GEMM=tc) instead of FFMA tiles
+  bool use_mega = false; // DDRL_MEGA=1: one persistent cooperative kernel per step instead of one launch per phase in a CUDA graph
+                         // (measured slower on B200 at the named shapes: 258 vs 203 us at C2 — kept for experiments)
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy
                                       // default stream, which cannot be captured); replay on the caller's
 };
@@ -577,6 +714,7 @@ int launch_group(const Group& g, cudaStream_t s) {
 enum { ST_L1 = 0, ST_L2 /*-> k_policy_heads_fwd*/, ST_QL1, ST_QL2 /*-> k_qheads_losses*/, ST_BQ
        /*-> k_policy_bwd_rows*/, ST_BP, ST_BP3, ST_COUNT };
 
+constexpr int MODE_GRADS_ = 1;
 bool g_plan_tc = false;   // set by build_plan from the handle (tcgen05 path on / off)
 void add(std::vector<Group>& stage, GemmProb p) {
   p.cfg = p.N <= 16 ? 1 : (g_plan_tc ? 2 : 0);
@@ -639,6 +777,42 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
       int rc = finalize_group(g2);
       if (rc) return rc;
     }
+  if (h->use_mega) {
+    std::vector<GemmGroup> host(ST_COUNT);
+    for (int i = 0; i < ST_COUNT; ++i) host[i] = pl.stages[i].empty() ? GemmGroup{} : pl.stages[i][0].grp;
+    cudaError_t e = cudaMalloc(&pl.d_stages, sizeof(GemmGroup) * ST_COUNT);
+    if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(stages) failed: %s", cudaGetErrorString(e));
+    e = cudaMemcpy(pl.d_stages, host.data(), sizeof(GemmGroup) * ST_COUNT, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaMemcpy(stages) failed: %s", cudaGetErrorString(e));
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sac_mega, 256, 0);
+    if (e != cudaSuccess || per_sm < 1) return fail(DDRL_ECUDA, "occupancy query for the step kernel failed");
+    if (per_sm > 2) per_sm = 2;
+    pl.mega_grid = per_sm * h->sms;
+  }
+  return 0;
+}
+
+int launch_mega(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
+  MegaArgs a{};
+  a.st = h->st; a.stages = pl.d_stages;
+  for (int i = 0; i < ST_COUNT; ++i) a.tiles[i] = pl.stages[i].empty() ? 0 : pl.stages[i][0].tiles;
+  a.mode = mode == MODE_GRADS_ ? 1 : 0;
+  a.B = pl.B; a.D = h->D; a.A = h->A; a.h1 = h->h1; a.h2 = h->h2; a.S = pl.S;
+  a.act_scale = h->act_scale; a.gamma = h->gamma; a.lr = h->lr; a.polyak = h->polyak;
+  a.P = h->P; a.P_pi = h->P_pi;
+  a.X = h->X; a.X2 = h->X2; a.ACT = h->ACT; a.R = h->R; a.DN = h->DN; a.NOISE = h->NOISE;
+  for (int i = 0; i < 8; ++i) a.H2[i] = h->H2[i];
+  a.HD0 = h->HD[0]; a.A1 = h->A1; a.A3 = h->A3; a.LOGP1 = h->LOGP1; a.LOGP2 = h->LOGP2;
+  a.dQ0 = h->dQ[0]; a.dQ1 = h->dQ[1]; a.dZ2_0 = h->dZ2[0]; a.dZ2_1 = h->dZ2[1]; a.dZ2_2 = h->dZ2[2]; a.dZ1_2 = h->dZ1[2];
+  a.dHD = h->dHD; a.dZ2a = h->dZ2a;
+  a.partials = h->partials; a.ticket = h->ticket;
+  a.barrier = &h->st->mega_barrier;
+  a.SCAL = h->SCAL; a.W = h->W; a.Wt = h->Wt; a.Mo = h->Mo; a.Vo = h->Vo; a.Gp = h->Gp; a.G = h->G;
+  a.o_pih = h->o_pih; a.o_q1_0 = h->o_q1[0]; a.o_q1_2 = h->o_q1[2]; a.o_q2_2 = h->o_q2[2];
+  void* args[] = {&a};
+  DDRL_CUDA(cudaLaunchCooperativeKernel((const void*)k_sac_mega, dim3(pl.mega_grid), dim3(256), args, 0, s));
+  DDRL_LAUNCH_CHECK();
   return 0;
 }
 
@@ -715,6 +889,7 @@ int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
 
 int run_mode(ddrl_sac* h, Plan& pl, int mode, cudaStream_t s) {
   cudaGraphExec_t* slot = mode == MODE_FULL ? &pl.exec_full : mode == MODE_GRADS ? &pl.exec_grads : &pl.exec_apply;
+  if (h->use_mega && mode != MODE_APPLY) return launch_mega(h, pl, mode, s);
   if (!h->use_graph) return enqueue_mode(h, pl, mode, s);
   if (!*slot) {
     cudaGraph_t graph = nullptr;
@@ -773,6 +948,8 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   const char* ng = getenv("DDRL_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
   if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] == 't');
+  if (const char* mg = getenv("DDRL_MEGA")) h->use_mega = (mg[0] != '0');
+  if (h->use_tc) h->use_mega = false;   // the tcgen05 tiles need 130 KB of shared memory and TMEM per CTA
   if (const char* dbg = getenv("DDRL_TC_DEBUG")) { int v = atoi(dbg); cudaMemcpyToSymbol(tc::g_tc_debug, &v, sizeof(int)); }
   if (h->use_tc) {
     cudaError_t ea = cudaFuncSetAttribute(tc::gemm_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
@@ -841,6 +1018,7 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
   for (auto& kv : h->plans) {
     Plan& pl = kv.second;
     for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply}) if (ex) cudaGraphExecDestroy(ex);
+    if (pl.d_stages) cudaFree(pl.d_stages);
   }
   for (void* p : h->allocs) cudaFree(p);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
