@@ -88,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.dev), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.dev), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -119,7 +119,7 @@ class ClockSampler:
             except Exception:
                 pass
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), sm_mhz_min=min(sm) if sm else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -254,6 +254,7 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.05)
     sec, launches = timed(step_device, args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
     value = world * B * args.steps / sec
@@ -343,7 +344,7 @@ def run_ours(args):
                  ms_per_step=sec_e2e / e2e_steps * 1e3,
                  path="store_batch(host) -> sample_batch() -> numpy -> Learner.train(numpy) -> losses.cpu()"),
         gpu_launches=int(launches),
-        roofline=dict(kernel="SAC1 update (gemm_grouped_f32 x ~20 + element-wise), whole step", bound="tensor",
+        roofline=dict(kernel="SAC1 update, whole step (gemm_grouped_f32 x 7 + 3 row-wise kernels + Adam/polyak, one CUDA graph)", bound="tensor",
                       achieved=tf, peak=peaks["bf16_tf"], unit="TFLOP/s", frac=tf / peaks["bf16_tf"], traffic=None,
                       flops_per_update=fl, peak_source=peaks["source"],
                       note="parity mode computes in fp32 FFMA (1e-5 bar forbids bf16/tf32 rounding); fraction is "
@@ -370,8 +371,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")

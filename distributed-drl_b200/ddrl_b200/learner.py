@@ -74,7 +74,9 @@ def _opt_get(opt, name, default=None):
 
 
 class Learner(object):
-    def __init__(self, opt, job="learner", *, device=None, max_batch=None, process_group=None):
+    def __init__(self, opt, job="learner", *, device=None, max_batch=None, process_group=None, gemm=None):
+        """gemm: None (default, fp32 FFMA tiles) | "ffma" | "tc" (tcgen05 tensor cores with the 3xTF32 split;
+        same 1e-5 class accuracy, see tests/test_sac_gpu.py::test_tcgen05_path_matches_oracle)."""
         if not torch.cuda.is_available():
             raise RuntimeError("ddrl_b200.Learner needs a CUDA device (no CPU fallback)")
         self.opt = opt
@@ -99,9 +101,20 @@ class Learner(object):
         self.seed = int(_opt_get(opt, "seed", 0) or 0)
         self.max_batch = int(max_batch or _opt_get(opt, "batch_size", 256) or 256)
         h = C.c_void_p()
-        N.check(self._lib.ddrl_sac_create(self.device, self.obs_dim, self.act_dim, self.hidden[0], self.hidden[1],
-                                          self.max_batch, self.gamma, self.polyak, self.lr, self.alpha,
-                                          self.act_scale, C.byref(h)))
+        import os
+        prev = os.environ.get("DDRL_GEMM")
+        if gemm is not None:
+            os.environ["DDRL_GEMM"] = "tc" if gemm == "tc" else "ffma"
+        try:
+            N.check(self._lib.ddrl_sac_create(self.device, self.obs_dim, self.act_dim, self.hidden[0], self.hidden[1],
+                                              self.max_batch, self.gamma, self.polyak, self.lr, self.alpha,
+                                              self.act_scale, C.byref(h)))
+        finally:
+            if gemm is not None:
+                if prev is None:
+                    os.environ.pop("DDRL_GEMM", None)
+                else:
+                    os.environ["DDRL_GEMM"] = prev
         self._h = h
         self.names = param_names()
         self.shapes = param_shapes(self.obs_dim, self.act_dim, self.hidden)

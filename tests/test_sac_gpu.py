@@ -37,9 +37,9 @@ def make_opt(D, A, hidden, B, alpha=0.2, act_scale=1.0, lr=1e-3, gamma=0.99, pol
                            gamma=gamma, lr=lr, polyak=polyak, seed=seed, batch_size=B)
 
 
-def build_pair(L, D, A, hidden, B, params, **kw):
+def build_pair(L, D, A, hidden, B, params, gemm=None, **kw):
     opt = make_opt(D, A, hidden, B, **kw)
-    learner = L(opt, "learner")
+    learner = L(opt, "learner", gemm=gemm)
     keys = list(params.keys())
     learner.set_weights(keys, [params[k] for k in keys])
     oracle = SAC1Oracle(D, A, hidden=hidden, gamma=opt.gamma, polyak=opt.polyak, lr=opt.lr, alpha=opt.alpha,
@@ -197,3 +197,27 @@ def test_default_init_regime_against_float32_oracle(L):
     sc = got["scalars"].cpu().numpy()
     for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
         assert abs(sc[i] - float(want[k])) <= 2e-3 * abs(float(want[k])), k
+
+
+@pytest.mark.parametrize("D,A,hidden,B,scale", [(24, 4, (256, 256), 1024, 1.0), (376, 17, (256, 256), 300, 0.4),
+                                                 (5, 3, (33, 17), 37, 0.4)])
+def test_tcgen05_path_matches_oracle(L, D, A, hidden, B, scale):
+    """The tensor-core path (tcgen05.mma kind::tf32, three MMAs per product: a_lo*b_hi + a_hi*b_lo +
+    a_hi*b_hi, fp32 accumulation in TMEM) keeps the fp32-class tolerance: losses 1e-5, gradients 2e-5
+    of max|g|, well-determined weights 1e-5; epsilon-dominated Adam entries get a stated 1e-4."""
+    params = conditioned_params(D, A, hidden, seed=100 + D)
+    learner, oracle = build_pair(L, D, A, hidden, B, params, gemm="tc", act_scale=scale)
+    batch, noise = make_batch(D, A, B, seed=200 + D)
+    want_g = oracle.flat_grads(batch, noise)
+    want = oracle.step(batch, noise)
+    got = learner.train(batch, noise=noise, split=True, sync_outputs=True)
+    sc = got["scalars"].cpu().numpy()
+    for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
+        assert abs(sc[i] - float(want[k])) <= TOL * abs(float(want[k])), (k, sc[i], float(want[k]))
+    for k in ("q1", "q2", "logp_pi"):
+        assert rel(got[k].cpu().numpy(), want[k]) <= TOL, k
+    assert rel(learner.get_flat_weights("grad").cpu().numpy(), want_g) <= 2 * TOL
+    got_w, want_w = learner.get_flat_weights("main").cpu().numpy(), oracle.flat("main")
+    solid = np.abs(want_g) > 1e-4 * np.abs(want_g).max()
+    assert rel(got_w[solid], want_w[solid]) <= TOL
+    assert rel(got_w, want_w) <= 1e-4
