@@ -62,12 +62,42 @@ __global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
 }
 
 // copy the external batch into the learner's own buffers and materialise the noise
+// tensor-core mode: the three concatenated inputs [x|a], [x|a1], [x2|a3] as pre-split hi/lo planes
+// ([2][maxB][pitch]; the action columns of the last two are filled by the policy-head kernel)
+struct XaOut {
+  float *xa_d, *xa_f, *xa_g;   // nullptr: FFMA mode (plain X / X2 / ACT copies instead)
+  int pitch;
+  long long plane;
+};
+__device__ __forceinline__ void put_split(float* hi_plane, long long plane, size_t idx, float v) {
+  float hi, lo;
+  tc::split_tf32(v, hi, lo);
+  hi_plane[idx] = hi;
+  hi_plane[plane + idx] = lo;
+}
 __device__ __forceinline__ void d_prologue(int vb, int vgrid, const StepState* __restrict__ st, int B, int D, int A,
-                                           float* X, float* X2, float* ACT, float* R, float* DN, float* NOISE) {
+                                           float* X, float* X2, float* ACT, float* R, float* DN, float* NOISE,
+                                           XaOut xa = XaOut{nullptr, nullptr, nullptr, 0, 0}) {
   const StepDyn& d = st->dyn;
   const int64_t tid = (int64_t)vb * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)vgrid * blockDim.x;
-  if (d.obs1) {
+  if (d.obs1 && xa.xa_d) {
+    for (int64_t i = tid; i < (int64_t)B * D; i += nthr) {
+      const int64_t r = i / D, c = i - r * D;
+      const size_t o = (size_t)r * xa.pitch + c;
+      const float v1 = d.obs1[i], v2 = d.obs2[i];
+      float hi, lo;
+      tc::split_tf32(v1, hi, lo);
+      xa.xa_d[o] = hi; xa.xa_d[xa.plane + o] = lo;
+      xa.xa_f[o] = hi; xa.xa_f[xa.plane + o] = lo;
+      put_split(xa.xa_g, xa.plane, o, v2);
+    }
+    for (int64_t i = tid; i < (int64_t)B * A; i += nthr) {
+      const int64_t r = i / A, c = i - r * A;
+      put_split(xa.xa_d, xa.plane, (size_t)r * xa.pitch + D + c, d.acts[i]);
+    }
+    for (int64_t i = tid; i < B; i += nthr) { R[i] = d.rews[i]; DN[i] = d.done[i]; }
+  } else if (d.obs1) {
     for (int64_t i = tid; i < (int64_t)B * D; i += nthr) { X[i] = d.obs1[i]; X2[i] = d.obs2[i]; }
     for (int64_t i = tid; i < (int64_t)B * A; i += nthr) ACT[i] = d.acts[i];
     for (int64_t i = tid; i < B; i += nthr) { R[i] = d.rews[i]; DN[i] = d.done[i]; }
@@ -96,8 +126,8 @@ __device__ __forceinline__ void d_prologue(int vb, int vgrid, const StepState* _
   }
 }
 __global__ void __launch_bounds__(256) k_prologue(const StepState* __restrict__ st, int B, int D, int A, float* X, float* X2,
-                                                  float* ACT, float* R, float* DN, float* NOISE) {
-  d_prologue(blockIdx.x, gridDim.x, st, B, D, A, X, X2, ACT, R, DN, NOISE);
+                                                  float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
+  d_prologue(blockIdx.x, gridDim.x, st, B, D, A, X, X2, ACT, R, DN, NOISE, xa);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -148,13 +178,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // (forward: W[k*ldw + j]), or [n, ldw] when w_trans (dgrad against W^T: W[j*ldw + k]).  Results land in
 // sout[0..n) (shared, per warp), identical in every lane.
 __device__ __forceinline__ void warp_dots(const float* __restrict__ x, int K, const float* __restrict__ W, int ldw, int n,
-                                          bool w_trans, bool bias, float* sout, int lane) {
+                                          bool w_trans, bool bias, float* sout, int lane,
+                                          const float* __restrict__ x_lo = nullptr) {
   for (int j0 = 0; j0 < n; j0 += 8) {
     float acc[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0f;
     for (int k = lane; k < K; k += 32) {
-      const float xv = x[k];
+      const float xv = x_lo ? x[k] + x_lo[k] : x[k];   // hi + lo is exact
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int j = j0 + jj;
@@ -179,7 +210,8 @@ __device__ __forceinline__ void warp_dots(const float* __restrict__ x, int K, co
 __device__ __forceinline__ void d_policy_heads_fwd(
     int vb, int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
-    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2) {
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2,
+    XaOut xa = XaOut{nullptr, nullptr, nullptr, 0, 0}, int D = 0) {
   __shared__ float s_out[ROW_WARPS][MAX_HEAD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = vb * ROW_WARPS + w;
@@ -196,8 +228,14 @@ __device__ __forceinline__ void d_policy_heads_fwd(
       const PolEl e = policy_elem(s_out[w][j], s_out[w][A + j], eps[j]);
       pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
       sq = logf(__fadd_rn(e.clipped, 1e-6f));
-      if (pass == 0) A1[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
-      else if (pass == 2) A3[(size_t)row * A + j] = __fmul_rn(e.pi, act_scale);
+      const float act = __fmul_rn(e.pi, act_scale);
+      if (pass == 0) {
+        A1[(size_t)row * A + j] = act;
+        if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + j, act);
+      } else if (pass == 2) {
+        A3[(size_t)row * A + j] = act;
+        if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + j, act);
+      }
     }
     // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
     const int cnt = min(32, A - j0);
@@ -216,8 +254,8 @@ __device__ __forceinline__ void d_policy_heads_fwd(
 __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_fwd(
     int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
-    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2) {
-  d_policy_heads_fwd(blockIdx.x, B, A, h2, act_scale, H2a, H2b, H2c, Whead, Whead_t, NOISE, HD, A1, A3, LOGP1, LOGP2);
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D) {
+  d_policy_heads_fwd(blockIdx.x, B, A, h2, act_scale, H2a, H2b, H2c, Whead, Whead_t, NOISE, HD, A1, A3, LOGP1, LOGP2, xa, D);
 }
 
 // Q heads of all five Q passes, Bellman target, the three losses (actor_learner.py:58-69), the
@@ -230,8 +268,9 @@ __device__ __forceinline__ void d_qheads_losses(
     const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
     const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
     const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
-    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL) {
+    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz = 0, long long zlo = 0) {
   __shared__ double s_part[ROW_WARPS][4];
+  if (ldz == 0) ldz = h2;   // zlo != 0: hi/lo planes for the tensor-core GEMMs (lo plane zlo floats after hi)
   __shared__ bool s_last;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = vb * ROW_WARPS + w;
@@ -264,9 +303,10 @@ __device__ __forceinline__ void d_qheads_losses(
     const float dqd = -e1 * invB, dqe = -e2 * invB, dqf = -invB;
     for (int k = lane; k < h2; k += 32) {
       const float w1 = W3q1[k], w2 = W3q2[k];
-      dZ2d[(size_t)row * h2 + k] = hd[k] > 0.0f ? dqd * w1 : 0.0f;
-      dZ2e[(size_t)row * h2 + k] = he[k] > 0.0f ? dqe * w2 : 0.0f;
-      dZ2f[(size_t)row * h2 + k] = hf[k] > 0.0f ? dqf * w1 : 0.0f;
+      const float zd = hd[k] > 0.0f ? dqd * w1 : 0.0f, ze = he[k] > 0.0f ? dqe * w2 : 0.0f, zf = hf[k] > 0.0f ? dqf * w1 : 0.0f;
+      const size_t o = (size_t)row * ldz + k;
+      if (zlo) { put_split(dZ2d, zlo, o, zd); put_split(dZ2e, zlo, o, ze); put_split(dZ2f, zlo, o, zf); }
+      else { dZ2d[o] = zd; dZ2e[o] = ze; dZ2f[o] = zf; }
     }
     if (lane == 0) {
       dQd[row] = dqd; dQe[row] = dqe;
@@ -307,9 +347,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
     const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
     const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
     const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
-    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL) {
+    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz, long long zlo) {
   d_qheads_losses(blockIdx.x, gridDim.x, st, B, h2, gamma, H2d, H2e, H2f, H2g, H2h, W3q1, W3q2, W3q1t, W3q2t, R, DN, LOGP1, LOGP2,
-                  dQd, dQe, dZ2d, dZ2e, dZ2f, partials, ticket, SCAL);
+                  dQd, dQe, dZ2d, dZ2e, dZ2f, partials, ticket, SCAL, ldz, zlo);
 }
 
 // gradient of pi_loss = mean(alpha*logp1 - q1_pi) wrt the policy head pre-activations (chain rule of
@@ -319,13 +359,16 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
 __device__ __forceinline__ void d_policy_bwd_rows(
     int vb, const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
     const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
-    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a) {
+    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a, int ld1 = 0, long long lo1 = 0,
+    int ldz = 0, long long zlo = 0) {
   __shared__ float s_da[ROW_WARPS][MAX_HEAD];
   __shared__ float s_dhd[ROW_WARPS][MAX_HEAD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = vb * ROW_WARPS + w;
   if (row >= B) return;
-  warp_dots(dZ1f + (size_t)row * h1, h1, W1q1_act, h1, A, true, false, s_da[w], lane);
+  if (ld1 == 0) ld1 = h1;
+  if (ldz == 0) ldz = h2;
+  warp_dots(dZ1f + (size_t)row * ld1, h1, W1q1_act, h1, A, true, false, s_da[w], lane, lo1 ? dZ1f + lo1 + (size_t)row * ld1 : nullptr);
   const float dlogp = st->alpha_cur / (float)B;
   const float* hd = HDa + (size_t)row * 2 * A;
   const float* eps = NOISE + (size_t)row * A;
@@ -353,14 +396,17 @@ __device__ __forceinline__ void d_policy_bwd_rows(
     float acc = 0.0f;
     const float* wr = Whead + (size_t)n * n2;
     for (int j = 0; j < n2; ++j) acc = fmaf(s_dhd[w][j], wr[j], acc);
-    dZ2a[(size_t)row * h2 + n] = H2a[(size_t)row * h2 + n] > 0.0f ? acc : 0.0f;
+    const float z = H2a[(size_t)row * h2 + n] > 0.0f ? acc : 0.0f;
+    if (zlo) put_split(dZ2a, zlo, (size_t)row * ldz + n, z);
+    else dZ2a[(size_t)row * ldz + n] = z;
   }
 }
 __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
     const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
     const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
-    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a) {
-  d_policy_bwd_rows(blockIdx.x, st, B, A, h1, h2, act_scale, HDa, NOISE, dZ1f, W1q1_act, Whead, H2a, dHD, dZ2a);
+    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a, int ld1, long long lo1, int ldz,
+    long long zlo) {
+  d_policy_bwd_rows(blockIdx.x, st, B, A, h1, h2, act_scale, HDa, NOISE, dZ1f, W1q1_act, Whead, H2a, dHD, dZ2a, ld1, lo1, ldz, zlo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -432,10 +478,38 @@ __global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const flo
   d_grad_reduce(blockIdx.x, gridDim.x, P, S, Gp, G);
 }
 
+// hi/lo planes of the weight blocks the tensor-core GEMMs read (kernel rows only; the bias row is added in
+// the GEMM epilogue from the fp32 master copy): block b = rows x N[b] at sp_off[b], row pitch pitch[b]
+struct SplitMap {
+  int nblk;
+  int N[6], pitch[6];
+  long long int_off[6], size[6], sp_off[6];
+  long long plane;
+};
+__device__ __forceinline__ void write_split(const SplitMap& mp, int64_t i, float w, float* __restrict__ Wsp) {
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    if (b < mp.nblk && i >= mp.int_off[b] && i < mp.int_off[b] + mp.size[b]) {
+      const int64_t e = i - mp.int_off[b];
+      const int64_t r = e / mp.N[b], c = e - r * mp.N[b];
+      put_split(Wsp, mp.plane, (size_t)(mp.sp_off[b] + r * mp.pitch[b] + c), w);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_split_weights(SplitMap mp, int64_t P, const float* __restrict__ W,
+                                                       const float* __restrict__ Wt, float* Wsp, float* Wtsp) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    write_split(mp, i, W[i], Wsp);
+    write_split(mp, i, Wt[i], Wtsp);
+  }
+}
+
 __device__ __forceinline__ void d_adam_polyak(int vb, int vgrid, StepState* st, int64_t P, int64_t P_pi, int S,
                                                      const float* __restrict__ Gp, float lr, float polyak,
                                                      float target_entropy, const float* __restrict__ SCAL,
-                                                     float* W, float* Wt, float* Mo, float* Vo) {
+                                                     float* W, float* Wt, float* Mo, float* Vo,
+                                                     const SplitMap* mp = nullptr, float* Wsp = nullptr, float* Wtsp = nullptr) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
@@ -449,7 +523,9 @@ __device__ __forceinline__ void d_adam_polyak(int vb, int vgrid, StepState* st, 
     Mo[i] = m; Vo[i] = v;
     const float w = W[i] - (i < P_pi ? lr_pi : lr_q) * m / (sqrtf(v) + eps);
     W[i] = w;
-    Wt[i] = polyak * Wt[i] + (1.0f - polyak) * w;
+    const float wt = polyak * Wt[i] + (1.0f - polyak) * w;
+    Wt[i] = wt;
+    if (mp) { write_split(*mp, i, w, Wsp); write_split(*mp, i, wt, Wtsp); }
   }
   // entropy-alpha (reference-intended semantics): one scalar Adam step, unordered wrt
   // the rest; uses the pre-update mean(logp1) of this step.
@@ -467,6 +543,12 @@ __global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, i
                                                      float lr, float polyak, float target_entropy, const float* __restrict__ SCAL,
                                                      float* W, float* Wt, float* Mo, float* Vo) {
   d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo);
+}
+__global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_t P, int64_t P_pi, int S, const float* __restrict__ Gp,
+                                                           float lr, float polyak, float target_entropy,
+                                                           const float* __restrict__ SCAL, float* W, float* Wt, float* Mo, float* Vo,
+                                                           const __grid_constant__ SplitMap mp, float* Wsp, float* Wtsp) {
+  d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo, &mp, Wsp, Wtsp);
 }
 
 // external (TF variable order: kernel, bias per dense layer; mu head then log_std head) <-> internal
@@ -603,8 +685,10 @@ using namespace ddrl;
 namespace {
 
 struct Group {
-  std::vector<GemmProb> probs, probs_tc;   // FFMA tiles (cfg 0/1) and tcgen05 tiles (cfg 2)
-  GemmGroup grp{}, grp_tc{};               // the same, packed as kernel parameters
+  std::vector<GemmProb> probs;          // FFMA tiles (cfg 0/1)
+  std::vector<tc::TcProb> probs_tc;     // tcgen05 tiles
+  GemmGroup grp{};                      // the same, packed as kernel parameters
+  tc::TcGroup grp_tc{};
   int tiles = 0, tiles_tc = 0;
 };
 
@@ -639,6 +723,13 @@ struct ddrl_sac {
   float *H1[8] = {}, *H2[8] = {}, *HD[3] = {}, *Q[5] = {};  // passes a..h ; heads a..c ; q d..h
   float *A1 = nullptr, *A3 = nullptr, *LOGP1 = nullptr, *LOGP2 = nullptr;
   float *dQ[3] = {}, *dZ2[3] = {}, *dZ1[3] = {}, *dA1 = nullptr, *dHD = nullptr, *dZ2a = nullptr, *dZ1a = nullptr;
+  // tensor-core mode: H1 / dZ1 / dZ2 / dZ2a / dZ1a are hi/lo plane pairs [2][maxB][ld], ld rounded up to 4 floats
+  // (16-byte TMA strides); lo* = floats from the hi plane to the lo plane (0 in FFMA mode, where ld = width)
+  int ld1 = 0, ld2 = 0, ldx = 0;
+  long long lo1 = 0, lo2 = 0, lox = 0;
+  float* XA[3] = {};                    // [x|a], [x|a1], [x2|a3] split planes
+  float *Wsp = nullptr, *Wtsp = nullptr;  // split planes of the main / target weight blocks (SplitMap)
+  SplitMap smap{};
   std::vector<void*> allocs;
   std::map<int, Plan> plans;
   bool use_graph = true;
@@ -675,13 +766,29 @@ GemmProb mk(Seg a0, Seg a1, int ones, int a_trans, const float* Bp, int ldb, int
 Seg seg(const float* p, int ld, int w) { return Seg{p, ld, w}; }
 Seg none() { return Seg{nullptr, 0, 0}; }
 
+int pack_tc(std::vector<tc::TcProb>& v, tc::TcGroup* g, int* tiles) {
+  if ((int)v.size() > tc::MAX_PROBS) return fail(DDRL_EINVAL, "too many tensor-core problems in one stage (%d)", (int)v.size());
+  int t = 0;
+  g->nprob = (int)v.size();
+  for (size_t i = 0; i < v.size(); ++i) {
+    tc::TcProb& p = v[i];
+    p.tiles_m = (p.M + tc::BM - 1) / tc::BM;
+    p.tiles_n = (p.N + tc::BN - 1) / tc::BN;
+    p.tile_begin = t;
+    t += p.tiles_m * p.tiles_n * p.splits;
+    g->p[i] = p;
+  }
+  *tiles = t;
+  return 0;
+}
+
 int pack(std::vector<GemmProb>& v, GemmGroup* g, int* tiles) {
   if ((int)v.size() > GEMM_MAX_PROBS) return fail(DDRL_EINVAL, "too many GEMM problems in one stage (%d)", (int)v.size());
   int t = 0;
   g->nprob = (int)v.size();
   for (size_t i = 0; i < v.size(); ++i) {
     GemmProb& p = v[i];
-    const int BM = p.cfg == 0 ? 64 : 128, BN = p.cfg == 0 ? 64 : (p.cfg == 1 ? 16 : 128);
+    const int BM = p.cfg == 0 ? 64 : 128, BN = p.cfg == 0 ? 64 : 16;
     p.tiles_m = (p.M + BM - 1) / BM;
     p.tiles_n = (p.N + BN - 1) / BN;
     p.tile_begin = t;
@@ -695,7 +802,7 @@ int pack(std::vector<GemmProb>& v, GemmGroup* g, int* tiles) {
 int finalize_group(Group& g) {
   int rc = pack(g.probs, &g.grp, &g.tiles);
   if (rc) return rc;
-  return pack(g.probs_tc, &g.grp_tc, &g.tiles_tc);
+  return pack_tc(g.probs_tc, &g.grp_tc, &g.tiles_tc);
 }
 
 int launch_group(const Group& g, cudaStream_t s) {
@@ -715,12 +822,72 @@ enum { ST_L1 = 0, ST_L2 /*-> k_policy_heads_fwd*/, ST_QL1, ST_QL2 /*-> k_qheads_
        /*-> k_policy_bwd_rows*/, ST_BP, ST_BP3, ST_COUNT };
 
 constexpr int MODE_GRADS_ = 1;
-bool g_plan_tc = false;   // set by build_plan from the handle (tcgen05 path on / off)
 void add(std::vector<Group>& stage, GemmProb p) {
-  p.cfg = p.N <= 16 ? 1 : (g_plan_tc ? 2 : 0);
+  p.cfg = p.N <= 16 ? 1 : 0;
   if (stage.empty()) stage.emplace_back();
-  (p.cfg == 2 ? stage[0].probs_tc : stage[0].probs).push_back(p);
+  stage[0].probs.push_back(p);
 }
+void add_tc(std::vector<Group>& stage, const tc::TcProb& p) {
+  if (stage.empty()) stage.emplace_back();
+  stage[0].probs_tc.push_back(p);
+}
+
+// ---- TMA tensor maps over the pre-split operands ([2][rows][pitch] floats, plane 0 = hi, 1 = lo) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+struct View {          // a pre-split 2-D tensor: `rows` x `cols` valid elements, row pitch `ld`, lo plane `lo` floats after hi
+  const float* p;
+  int ld;
+  long long lo;
+  int rows, cols;
+};
+// operand whose contraction index runs along the COLUMNS of the stored tensor (K-major): box = 128 rows x 32 cols
+// operand whose contraction index runs along the ROWS (MN-major): box = 32 rows (k) x 32 cols (mn)
+int make_map(CUtensorMap* m, const View& v, bool mn_major) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  if ((v.ld & 3) || (v.lo & 3) || (reinterpret_cast<uintptr_t>(v.p) & 15))
+    return fail(DDRL_EINVAL, "tensor map operand is not 16-byte aligned (ld=%d)", v.ld);
+  cuuint64_t dims[3] = {(cuuint64_t)v.cols, (cuuint64_t)v.rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)v.ld * 4, (cuuint64_t)v.lo * 4};
+  cuuint32_t box[3] = {32, mn_major ? 32u : 128u, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(v.p), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, v.rows, v.cols, v.ld);
+  return 0;
+}
+// C[M,N] = epi( opA . opB + bias ):  a / b are the stored tensors, a_mn / b_mn say which index is contracted
+int mk_tc(tc::TcProb* out, const View& a, bool a_mn, const View& b, bool b_mn, float* C, float* C_lo, int ldc, int M, int N,
+          int K, int epi = EPI_NONE, const float* bias = nullptr, const float* mask = nullptr, const float* mask_lo = nullptr,
+          int ldmask = 0) {
+  tc::TcProb p{};
+  int rc = make_map(&p.ta, a, a_mn);
+  if (rc) return rc;
+  if ((rc = make_map(&p.tb, b, b_mn))) return rc;
+  p.C = C; p.C_lo = C_lo; p.ldc = ldc; p.c_split_stride = 0;
+  p.mask = mask; p.mask_lo = mask_lo; p.ldmask = ldmask; p.bias = bias;
+  p.M = M; p.N = N; p.K = K; p.epi = epi; p.a_mn = a_mn; p.b_mn = b_mn;
+  p.splits = 1; p.k_per_split = (K + tc::BK - 1) / tc::BK * tc::BK;
+  *out = p;
+  return 0;
+}
+
+int build_plan_tc(ddrl_sac* h, int B, Plan& pl);
 
 int build_plan(ddrl_sac* h, int B, Plan& pl) {
   const int D = h->D, A = h->A, h1 = h->h1, h2 = h->h2;
@@ -729,7 +896,7 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
   pl.S = (B + kps - 1) / kps;
   if (pl.S > h->Smax) return fail(DDRL_EINVAL, "batch %d exceeds max_batch %d", B, h->maxB);
   pl.stages.assign(ST_COUNT, {});
-  g_plan_tc = h->use_tc;
+  if (h->use_tc) return build_plan_tc(h, B, pl);
   float *W = h->W, *Wt = h->Wt, *Gp = h->Gp;
   auto wg = [&](GemmProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
   enum { a = 0, b, c, d, e, f, g, hh };
@@ -793,6 +960,88 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
   return 0;
 }
 
+// Tensor-core plan: every GEMM with N > 16 runs on tcgen05 from the pre-split planes; the skinny weight
+// gradients (Q heads, policy heads) and the bias gradients (column sums of dZ) stay on FFMA tiles.
+int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
+  const int D = h->D, A = h->A, h1 = h->h1, h2 = h->h2;
+  float *W = h->W, *Gp = h->Gp;
+  const SplitMap& sm = h->smap;
+  int rc = 0;
+  const int kps = 256;
+  auto wg_tc = [&](tc::TcProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
+  auto wg = [&](GemmProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
+  enum { a = 0, b, c, d, e, f, g, hh };
+  enum { PI1 = 0, PI2, Q1_0, Q1_1, Q2_0, Q2_1 };   // SplitMap block indices
+  const int64_t ioff[6] = {h->o_pi1, h->o_pi2, h->o_q1[0], h->o_q1[1], h->o_q2[0], h->o_q2[1]};
+  const int Kb[6] = {D, h1, D + A, h1, D + A, h1};
+  const int Nb[6] = {h1, h2, h1, h2, h1, h2};
+  auto wview = [&](int blk, bool target) {
+    return View{(target ? h->Wtsp : h->Wsp) + sm.sp_off[blk], sm.pitch[blk], sm.plane, Kb[blk], Nb[blk]};
+  };
+  auto bias_of = [&](int blk, bool target) { return (target ? h->Wt : W) + ioff[blk] + (int64_t)Kb[blk] * Nb[blk]; };
+  auto xa = [&](int which, int cols) { return View{h->XA[which], h->ldx, h->lox, B, cols}; };
+  auto h1v = [&](int p) { return View{h->H1[p], h->ld1, h->lo1, B, h1}; };
+  auto dz2v = [&](const float* p) { return View{p, h->ld2, h->lo2, B, h2}; };
+  auto dz1v = [&](const float* p) { return View{p, h->ld1, h->lo1, B, h1}; };
+  auto fwd = [&](int stage, const View& act, int blk, bool target, float* C, float* C_lo, int ldc) {
+    tc::TcProb p;
+    if (!rc && !(rc = mk_tc(&p, act, false, wview(blk, target), true, C, C_lo, ldc, B, Nb[blk], Kb[blk], EPI_RELU,
+                            bias_of(blk, target))))
+      add_tc(pl.stages[stage], p);
+  };
+  auto dgrad = [&](int stage, const float* dz2, int blk, float* dz1, int mask_pass) {
+    tc::TcProb p;   // dZ1 = dZ2 . W2^T masked by relu'(H1)
+    if (!rc && !(rc = mk_tc(&p, dz2v(dz2), false, wview(blk, false), false, dz1, dz1 + h->lo1, h->ld1, B, Kb[blk], Nb[blk],
+                            EPI_MASK, nullptr, h->H1[mask_pass], h->H1[mask_pass] + h->lo1, h->ld1)))
+      add_tc(pl.stages[stage], p);
+  };
+  auto wgrad = [&](int stage, const View& act, const View& dz, int blk) {
+    tc::TcProb p;   // d[W] = act^T . dZ (kernel rows); the bias row is the column sum of dZ, on FFMA tiles
+    if (!rc && !(rc = mk_tc(&p, act, true, dz, true, Gp + ioff[blk], nullptr, Nb[blk], Kb[blk], Nb[blk], B)))
+      add_tc(pl.stages[stage], wg_tc(p));
+    GemmProb cs = mk(none(), none(), 1, 1, dz.p, dz.ld, 0, Gp + ioff[blk] + (int64_t)Kb[blk] * Nb[blk], Nb[blk], 1, Nb[blk], B);
+    cs.B2 = dz.p + dz.lo;
+    add(pl.stages[stage], wg(cs));
+  };
+  // ---- forward: policies (a: main@x, b: main@x2, c: target@x2) and the data-action Q passes (d, e)
+  fwd(ST_L1, xa(0, D), PI1, false, h->H1[a], h->H1[a] + h->lo1, h->ld1);
+  fwd(ST_L1, xa(2, D), PI1, false, h->H1[b], h->H1[b] + h->lo1, h->ld1);
+  fwd(ST_L1, xa(2, D), PI1, true, h->H1[c], h->H1[c] + h->lo1, h->ld1);
+  fwd(ST_L1, xa(0, D + A), Q1_0, false, h->H1[d], h->H1[d] + h->lo1, h->ld1);
+  fwd(ST_L1, xa(0, D + A), Q2_0, false, h->H1[e], h->H1[e] + h->lo1, h->ld1);
+  const int blk2[5] = {PI2, PI2, PI2, Q1_1, Q2_1};
+  for (int p = 0; p < 5; ++p) fwd(ST_L2, h1v(p), blk2[p], p == c, h->H2[p], nullptr, h2);
+  // ---- forward, policy-action Q passes: f = Q1(x,a1), g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3)
+  fwd(ST_QL1, xa(1, D + A), Q1_0, false, h->H1[f], h->H1[f] + h->lo1, h->ld1);
+  fwd(ST_QL1, xa(2, D + A), Q1_0, true, h->H1[g], h->H1[g] + h->lo1, h->ld1);
+  fwd(ST_QL1, xa(2, D + A), Q2_0, true, h->H1[hh], h->H1[hh] + h->lo1, h->ld1);
+  fwd(ST_QL2, h1v(f), Q1_1, false, h->H2[f], nullptr, h2);
+  fwd(ST_QL2, h1v(g), Q1_1, true, h->H2[g], nullptr, h2);
+  fwd(ST_QL2, h1v(hh), Q2_1, true, h->H2[hh], nullptr, h2);
+  // ---- backward of the three differentiated Q passes: 0 = d (Q1 data), 1 = e (Q2 data), 2 = f (Q1 pi-path)
+  const int pass[3] = {d, e, f};
+  const int w2blk[3] = {Q1_1, Q2_1, Q1_1}, w1blk[3] = {Q1_0, Q2_0, Q1_0};
+  const int64_t* oq[3] = {h->o_q1, h->o_q2, h->o_q1};
+  for (int i = 0; i < 3; ++i) {
+    dgrad(ST_BQ, h->dZ2[i], w2blk[i], h->dZ1[i], pass[i]);
+    if (i < 2) {
+      add(pl.stages[ST_BQ], wg(mk(seg(h->H2[pass[i]], h2, h2), none(), 1, 1, h->dQ[i], 1, 0, Gp + oq[i][2], 1, h2 + 1, 1, B)));
+      wgrad(ST_BQ, h1v(pass[i]), dz2v(h->dZ2[i]), w2blk[i]);
+      wgrad(ST_BP, xa(0, D + A), dz1v(h->dZ1[i]), w1blk[i]);
+    }
+  }
+  // ---- policy backward (pass a); dHD and dZ2a come from k_policy_bwd_rows
+  add(pl.stages[ST_BP], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, 2 * A, h2 + 1, 2 * A, B)));
+  dgrad(ST_BP, h->dZ2a, PI2, h->dZ1a, a);
+  wgrad(ST_BP, h1v(a), dz2v(h->dZ2a), PI2);
+  wgrad(ST_BP3, xa(0, D), dz1v(h->dZ1a), PI1);
+  if (rc) return rc;
+  for (auto& st : pl.stages)
+    for (auto& g2 : st)
+      if ((rc = finalize_group(g2))) return rc;
+  return 0;
+}
+
 int launch_mega(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
   MegaArgs a{};
   a.st = h->st; a.stages = pl.d_stages;
@@ -824,13 +1073,17 @@ int run_stage(const Plan& pl, int s, cudaStream_t st) {
   return 0;
 }
 
+XaOut xa_out(const ddrl_sac* h) {
+  return h->use_tc ? XaOut{h->XA[0], h->XA[1], h->XA[2], h->ldx, h->lox} : XaOut{nullptr, nullptr, nullptr, 0, 0};
+}
+
 int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   const int B = pl.B, D = h->D, A = h->A;
   int rc;
   {
     const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
     int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
-    k_prologue<<<blocks, 256, 0, s>>>(h->st, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN, h->NOISE);
+    k_prologue<<<blocks, 256, 0, s>>>(h->st, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN, h->NOISE, xa_out(h));
     DDRL_LAUNCH_CHECK();
   }
   if ((rc = run_stage(pl, ST_L1, s))) return rc;
@@ -838,19 +1091,19 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   const int h1 = h->h1, h2 = h->h2;
   k_policy_heads_fwd<<<(3 * B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
       B, A, h2, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0], h->A1,
-      h->A3, h->LOGP1, h->LOGP2);
+      h->A3, h->LOGP1, h->LOGP2, xa_out(h), D);
   DDRL_LAUNCH_CHECK();
   if ((rc = run_stage(pl, ST_QL1, s))) return rc;
   if ((rc = run_stage(pl, ST_QL2, s))) return rc;
   k_qheads_losses<<<(B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
       h->st, B, h2, h->gamma, h->H2[3], h->H2[4], h->H2[5], h->H2[6], h->H2[7], h->W + h->o_q1[2], h->W + h->o_q2[2],
       h->Wt + h->o_q1[2], h->Wt + h->o_q2[2], h->R, h->DN, h->LOGP1, h->LOGP2, h->dQ[0], h->dQ[1], h->dZ2[0], h->dZ2[1],
-      h->dZ2[2], h->partials, h->ticket, h->SCAL);
+      h->dZ2[2], h->partials, h->ticket, h->SCAL, h->ld2, h->lo2);
   DDRL_LAUNCH_CHECK();
   if ((rc = run_stage(pl, ST_BQ, s))) return rc;
   k_policy_bwd_rows<<<(B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
       h->st, B, A, h1, h2, h->act_scale, h->HD[0], h->NOISE, h->dZ1[2], h->W + h->o_q1[0] + (int64_t)D * h1,
-      h->W + h->o_pih, h->H2[0], h->dHD, h->dZ2a);
+      h->W + h->o_pih, h->H2[0], h->dHD, h->dZ2a, h->ld1, h->lo1, h->ld2, h->lo2);
   DDRL_LAUNCH_CHECK();
   if ((rc = run_stage(pl, ST_BP, s))) return rc;
   if ((rc = run_stage(pl, ST_BP3, s))) return rc;
@@ -866,8 +1119,12 @@ int enqueue_reduce(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 
 int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s) {
   int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
-  k_adam_polyak<<<blocks, 256, 0, s>>>(h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak, -(float)h->A, h->SCAL, h->W,
-                                       h->Wt, h->Mo, h->Vo);
+  if (h->use_tc)
+    k_adam_polyak_split<<<blocks, 256, 0, s>>>(h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak, -(float)h->A, h->SCAL, h->W,
+                                               h->Wt, h->Mo, h->Vo, h->smap, h->Wsp, h->Wtsp);
+  else
+    k_adam_polyak<<<blocks, 256, 0, s>>>(h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak, -(float)h->A, h->SCAL, h->W,
+                                         h->Wt, h->Mo, h->Vo);
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -950,7 +1207,6 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] == 't');
   if (const char* mg = getenv("DDRL_MEGA")) h->use_mega = (mg[0] != '0');
   if (h->use_tc) h->use_mega = false;   // the tcgen05 tiles need 130 KB of shared memory and TMEM per CTA
-  if (const char* dbg = getenv("DDRL_TC_DEBUG")) { int v = atoi(dbg); cudaMemcpyToSymbol(tc::g_tc_debug, &v, sizeof(int)); }
   if (h->use_tc) {
     cudaError_t ea = cudaFuncSetAttribute(tc::gemm_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (ea != cudaSuccess) { delete h; return fail(DDRL_ECUDA, "cudaFuncSetAttribute(tc smem): %s", cudaGetErrorString(ea)); }
@@ -978,6 +1234,14 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   h->Smax = (max_batch + 255) / 256;
   int rc = 0;
   const size_t P = (size_t)h->P, M = (size_t)max_batch;
+  auto r4 = [](int v) { return (v + 3) / 4 * 4; };
+  h->ld1 = h->use_tc ? r4(h1) : h1;
+  h->ld2 = h->use_tc ? r4(h2) : h2;
+  h->ldx = r4(D + A);
+  h->lo1 = h->use_tc ? (long long)M * h->ld1 : 0;
+  h->lo2 = h->use_tc ? (long long)M * h->ld2 : 0;
+  h->lox = (long long)M * h->ldx;
+  const size_t planes = h->use_tc ? 2 : 1;
   auto A_ = [&](float** p, size_t n) { if (!rc) rc = dalloc(h, p, n); };
   A_(&h->W, P); A_(&h->Wt, P); A_(&h->Mo, P); A_(&h->Vo, P); A_(&h->G, P); A_(&h->Gp, P * h->Smax);
   A_(&h->SCAL, 8);
@@ -990,12 +1254,29 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     h->ticket = reinterpret_cast<unsigned int*>(tmp);
   }
   A_(&h->X, M * D); A_(&h->X2, M * D); A_(&h->ACT, M * A); A_(&h->R, M); A_(&h->DN, M); A_(&h->NOISE, 3 * M * A + 4);
-  for (int p = 0; p < 8; ++p) { A_(&h->H1[p], M * h1); A_(&h->H2[p], M * h2); }
+  for (int p = 0; p < 8; ++p) { A_(&h->H1[p], planes * M * h->ld1); A_(&h->H2[p], M * h2); }
   for (int p = 0; p < 3; ++p) A_(&h->HD[p], M * 2 * A);
   for (int p = 0; p < 5; ++p) A_(&h->Q[p], M);
   A_(&h->A1, M * A); A_(&h->A3, M * A); A_(&h->LOGP1, M); A_(&h->LOGP2, M);
-  for (int p = 0; p < 3; ++p) { A_(&h->dQ[p], M); A_(&h->dZ2[p], M * h2); A_(&h->dZ1[p], M * h1); }
-  A_(&h->dA1, M * A); A_(&h->dHD, M * 2 * A); A_(&h->dZ2a, M * h2); A_(&h->dZ1a, M * h1);
+  for (int p = 0; p < 3; ++p) { A_(&h->dQ[p], M); A_(&h->dZ2[p], planes * M * h->ld2); A_(&h->dZ1[p], planes * M * h->ld1); }
+  A_(&h->dA1, M * A); A_(&h->dHD, M * 2 * A); A_(&h->dZ2a, planes * M * h->ld2); A_(&h->dZ1a, planes * M * h->ld1);
+  if (h->use_tc) {
+    for (int i = 0; i < 3; ++i) A_(&h->XA[i], 2 * M * h->ldx);
+    SplitMap& sm = h->smap;
+    const int64_t ioff[6] = {h->o_pi1, h->o_pi2, h->o_q1[0], h->o_q1[1], h->o_q2[0], h->o_q2[1]};
+    const int Kb[6] = {D, h1, D + A, h1, D + A, h1};
+    const int Nb[6] = {h1, h2, h1, h2, h1, h2};
+    long long o = 0;
+    sm.nblk = 6;
+    for (int b = 0; b < 6; ++b) {
+      sm.N[b] = Nb[b]; sm.pitch[b] = r4(Nb[b]);
+      sm.int_off[b] = ioff[b]; sm.size[b] = (long long)Kb[b] * Nb[b];   // kernel rows only
+      sm.sp_off[b] = o;
+      o += (long long)Kb[b] * sm.pitch[b];
+    }
+    sm.plane = o;
+    A_(&h->Wsp, 2 * (size_t)o); A_(&h->Wtsp, 2 * (size_t)o);
+  }
   float* stp = nullptr;
   A_(&stp, (sizeof(StepState) + 3) / 4);
   if (rc) { ddrl_sac_destroy(h); return rc; }
@@ -1034,6 +1315,10 @@ int ddrl_sac_set_weights(ddrl_sac_t h, const float* d_flat, int also_target, voi
   int blocks = (int)std::min<int64_t>((h->Pext + 255) / 256, h->sms * 8);
   k_convert_layout<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->map, h->Pext, 1, d_flat, h->W, also_target ? h->Wt : nullptr);
   DDRL_LAUNCH_CHECK();
+  if (h->use_tc) {
+    k_split_weights<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->smap, h->P, h->W, h->Wt, h->Wsp, h->Wtsp);
+    DDRL_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -1125,6 +1410,48 @@ int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* str
   for (int i = 0; i < reps; ++i)
     if ((rc = run_stage(*pl, stage, (cudaStream_t)stream))) return rc;
   return 0;
+}
+
+// Test entry for the tensor-core GEMM alone: C[M,N] = opA . opB from plain fp32 device matrices.  The stored
+// tensors are A [a_rows, a_cols] and B [b_rows, b_cols] (row-major, dense); a_mn / b_mn = 1 when the contraction
+// index is the ROW of the stored tensor.  Splits into hi/lo planes, builds the TMA maps, runs one launch.
+__global__ void k_split_planes(const float* __restrict__ src, int rows, int cols, int ld, long long plane, float* dst) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    put_split(dst, plane, (size_t)r * ld + c, src[i]);
+  }
+}
+int ddrl_debug_tc_gemm(int device, const float* dA, int a_rows, int a_cols, int a_mn, const float* dB, int b_rows, int b_cols,
+                       int b_mn, float* dC, int M, int N, int K, int splits, void* stream) {
+  if (!dA || !dB || !dC) return fail(DDRL_EINVAL, "ddrl_debug_tc_gemm: NULL argument");
+  DeviceGuard guard(device);
+  cudaStream_t s = (cudaStream_t)stream;
+  DDRL_CUDA(cudaFuncSetAttribute(tc::gemm_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  auto r4 = [](int v) { return (v + 3) / 4 * 4; };
+  const int lda = r4(a_cols), ldb = r4(b_cols);
+  const long long pa = (long long)a_rows * lda, pb = (long long)b_rows * ldb;
+  float *sa = nullptr, *sb = nullptr;
+  DDRL_CUDA(cudaMalloc(&sa, 2 * pa * sizeof(float)));
+  DDRL_CUDA(cudaMalloc(&sb, 2 * pb * sizeof(float)));
+  cudaMemsetAsync(sa, 0, 2 * pa * sizeof(float), s);
+  cudaMemsetAsync(sb, 0, 2 * pb * sizeof(float), s);
+  k_split_planes<<<256, 256, 0, s>>>(dA, a_rows, a_cols, lda, pa, sa);
+  k_split_planes<<<256, 256, 0, s>>>(dB, b_rows, b_cols, ldb, pb, sb);
+  Group g;
+  tc::TcProb p;
+  int rc = mk_tc(&p, View{sa, lda, pa, a_rows, a_cols}, a_mn != 0, View{sb, ldb, pb, b_rows, b_cols}, b_mn != 0, dC, nullptr, N, M,
+                 N, K);
+  if (!rc) {
+    if (splits > 1) { p.splits = splits; p.k_per_split = ((K + splits - 1) / splits + tc::BK - 1) / tc::BK * tc::BK; p.c_split_stride = (long long)M * N; }
+    g.probs_tc.push_back(p);
+    rc = finalize_group(g);
+  }
+  if (!rc) rc = launch_group(g, s);
+  cudaStreamSynchronize(s);
+  cudaFree(sa);
+  cudaFree(sb);
+  return rc;
 }
 
 int ddrl_sac_state(ddrl_sac_t h, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream) {

@@ -1,48 +1,91 @@
-// sac_gemm_tc.cuh — tcgen05 (5th-gen tensor core) version of the grouped GEMM of sac_gemm.cuh, with
-// fp32-class accuracy through the 3xTF32 split:
-//     a = a_hi + a_lo,  a_hi = tf32(a) (top 19 bits), a_lo = a - a_hi (exact in fp32)
-//     a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi          (three kind::tf32 MMAs, fp32 accumulation in TMEM)
-// which keeps the SAC1 step inside the 1e-5 parity bar (plain TF32 would not: 10-bit mantissa).
+// sac_gemm_tc.cuh — tcgen05 (5th-gen tensor core) grouped GEMM of the SAC1 learner step with fp32-class
+// accuracy through the 3xTF32 split
+//     x = x_hi + x_lo,  x_hi = top 19 bits of x (a valid tf32),  x_lo = x - x_hi (exact in fp32)
+//     a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi       (three kind::tf32 MMAs, fp32 accumulation in TMEM)
+// which keeps the step inside the 1e-5 parity bar (plain TF32 would not: 10-bit mantissa).
 //
-// One CTA per 128 x 128 output tile (M = 128 TMEM lanes, N = 128 fp32 TMEM columns):
-//   all 256 threads   fetch the fp32 operands (same virtual-concat / transpose addressing as the FFMA
-//                     kernel), split them and write four K-major SWIZZLE_128B tiles (A_hi, A_lo, B_hi,
-//                     B_lo; 128 rows x 32 tf32 = 128 B per row) into one of two 64 KB stages; the next
-//                     k-block's global loads are in flight while the current one is split and stored
-//   thread 0          issues 12 tcgen05.mma (4 k-steps of 8 x 3 products) per k-block and commits them
-//                     to the stage's mbarrier, which is what frees the stage for refilling
-//   epilogue          8 warps read their TMEM lane quarter with tcgen05.ld (32 lanes x 32 columns per
-//                     load), apply relu / relu-mask and write full 128-byte row segments.
-// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+// Every operand already lives in HBM/L2 as a PRE-SPLIT pair of planes [2][rows][pitch] (plane 0 = hi,
+// plane 1 = lo): producers (the epilogue below, the row-wise kernels, the prologue, the optimiser) write
+// both planes, so this kernel never passes an operand through registers.  All three GEMM kinds of the
+// step read the tensors in their NATURAL row-major layout — no transposed copies exist anywhere:
+//     forward   H  = act . W      A = act [B,K]   K-major      B = W  [K,N]   MN-major
+//     dgrad     dX = dZ  . W^T    A = dZ  [B,N]   K-major      B = W  [K,N]   K-major (contraction = N)
+//     wgrad     dW = act^T . dZ   A = act [B,K]   MN-major     B = dZ [B,N]   MN-major (contraction = B)
+// (the major-ness is a bit of the instruction descriptor plus the shared-memory descriptor's strides).
+//
+// One CTA per 128 x 128 output tile, warp-specialised, 3-stage TMA -> tcgen05 pipeline:
+//   warp 0 / lane 0   TMA producer: per k-block (32 tf32 = one 128-byte swizzle row) loads A_hi, A_lo,
+//                     B_hi, B_lo with cp.async.bulk.tensor (SWIZZLE_128B) into a 64 KB stage; out-of-range
+//                     rows / columns / k are zero-filled by the TMA unit (ragged M, N, K need no code)
+//   warp 1 / lane 0   MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 per stage, then
+//                     tcgen05.commit to the stage's "empty" barrier; the last commit signals the epilogue
+//   all 8 warps       epilogue: tcgen05.ld (32 lanes x 32 columns), bias / relu / relu-mask, then either a
+//                     plain fp32 store or the hi/lo pair the next GEMM consumes.
+// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor) and
+// cute/atom/mma_traits_sm100.hpp (canonical K-major / MN-major SWIZZLE_128B layouts).
 #pragma once
+#include <cuda.h>
+
 #include "sac_gemm.cuh"
 
 namespace ddrl {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;            // BK tf32 = 128 bytes = one swizzle row
-constexpr int TILE_BYTES = 128 * 128;                 // one operand tile (128 rows x 128 B)
+constexpr int TILE_BYTES = 128 * 128;                 // one operand plane tile (128 x 32 tf32)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int STAGES = 2;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 64 /*barriers, tmem ptr*/;
+constexpr int STAGES = 3;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers, tmem ptr*/;
 constexpr int TMEM_COLS = 128;
-__device__ int g_tc_debug = 0;   // experiment switch: 1 skip operand fetch, 2 skip split+store, 4 skip MMA, 8 skip fence.proxy
+constexpr int MAX_PROBS = 10;
+
+struct alignas(64) TcProb {
+  CUtensorMap ta, tb;          // 3-D (inner, rows, plane) maps over the pre-split operands
+  float* C;                    // plain output, or the hi plane when C_lo != nullptr
+  float* C_lo;
+  const float* mask;           // relu-mask source (hi plane) and its lo plane
+  const float* mask_lo;
+  const float* bias;           // nullable: added per output column before the activation
+  long long c_split_stride;    // floats between split-K partial outputs
+  int ldc, ldmask;
+  int M, N, K;
+  int epi;
+  int a_mn, b_mn;              // 1: operand is MN-major (its contraction index is the ROW of the stored tensor)
+  int splits, k_per_split;
+  int tiles_m, tiles_n, tile_begin;
+};
+struct TcGroup {
+  int nprob;
+  TcProb p[MAX_PROBS];
+};
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// K-major, SWIZZLE_128B operand tile: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_byte_addr) {
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);   // sign, 8 exponent, 10 mantissa bits
+  lo = x - hi;                                               // exact; the MMA reads its top 19 bits
+}
+
+// SWIZZLE_128B shared-memory matrix descriptor (version 1).
+//   K-major : rows of 128 B (32 tf32 of K), 8-row groups SBO = 1024 B apart, LBO unused
+//   MN-major: 32-bit operands have ONE legal MN-major layout, SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:
+//             "for mn-major tf32 operands, SW128_32B is the only available smem layout"): 32 consecutive MN
+//             elements per 128-byte row with its 32-byte chunks XOR-swizzled by (row & 3)
+//             (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), 4 k-rows per 512-byte atom, k-atoms SBO = 512 B
+//             apart, the next 32 MN elements LBO = 4096 B further (one TMA box of 32 k x 32 mn)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_byte_addr, bool mn_major) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_byte_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(mn_major ? (4096 >> 4) : 1) << 16;
+  d |= (uint64_t)((mn_major ? 512 : 1024) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(mn_major ? 1 : 2) << 61;
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
-__device__ __forceinline__ uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::tf32, fp32 accumulate, M = 128, N = 128
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -56,6 +99,9 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -64,6 +110,11 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra TC_DONE;\n\t"
       "bra TC_WAIT;\n\t"
       "TC_DONE:\n\t}" ::"r"(s_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(s_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -80,85 +131,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// operand element accessors in (row-of-operand, k) coordinates
-__device__ __forceinline__ float op_a(const GemmProb& P, int m, int k, int kend) {
-  const bool ok = m < P.M && k < kend;
-  return P.a_trans ? fetch_a(P, k, m, ok) : fetch_a(P, m, k, ok);
-}
-__device__ __forceinline__ float op_b(const GemmProb& P, int n, int k, int kend) {
-  const bool ok = n < P.N && k < kend;
-  return ld_pred(P.b_trans ? P.B + (size_t)n * P.ldb + k : P.B + (size_t)k * P.ldb + n, ok);
-}
-
-struct Frag {          // raw fp32 operands of one k-block held by one thread: 4 (row, 4-k chunk) items per operand
-  float a[4][4];
-  float b[4][4];
-};
-
-// item j of thread tid: r_lo = id % 8, kc = (id / 8) % 8, r_hi = id / 64  (id = tid + 256 j): within a quarter warp the
-// eight rows of one swizzle group with one k-chunk -> conflict-free 16-byte shared stores after the XOR swizzle
-__device__ __forceinline__ void item_coords(int tid, int j, int& r, int& kc) {
-  const int id = tid + 256 * j;
-  r = (id >> 6) * 8 + (id & 7);
-  kc = (id >> 3) & 7;
-}
-
-__device__ __forceinline__ void fetch_frag(const GemmProb& P, int tid, int m0, int n0, int k0, int kend, Frag& f) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int r, kc;
-    item_coords(tid, j, r, kc);
-    const int k = k0 + 4 * kc;
-    bool done = false;
-    if (!P.a_trans && k + 3 < kend && m0 + r < P.M && k + 3 < P.a0.w && (P.a0.ld & 3) == 0 &&
-        ((reinterpret_cast<uintptr_t>(P.a0.p) & 15) == 0)) {
-      const float4 v = *reinterpret_cast<const float4*>(P.a0.p + (size_t)(m0 + r) * P.a0.ld + k);
-      f.a[j][0] = v.x; f.a[j][1] = v.y; f.a[j][2] = v.z; f.a[j][3] = v.w;
-      done = true;
-    }
-    if (!done) {
-#pragma unroll
-      for (int t = 0; t < 4; ++t) f.a[j][t] = op_a(P, m0 + r, k + t, kend);
-    }
-    done = false;
-    if (P.b_trans && k + 3 < kend && n0 + r < P.N && (P.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.B) & 15) == 0)) {
-      const float4 v = *reinterpret_cast<const float4*>(P.B + (size_t)(n0 + r) * P.ldb + k);
-      f.b[j][0] = v.x; f.b[j][1] = v.y; f.b[j][2] = v.z; f.b[j][3] = v.w;
-      done = true;
-    }
-    if (!done) {
-#pragma unroll
-      for (int t = 0; t < 4; ++t) f.b[j][t] = op_b(P, n0 + r, k + t, kend);
-    }
-  }
-}
-
-__device__ __forceinline__ void split_store(unsigned char* tile_hi, unsigned char* tile_lo, int r, int kc, const float* x) {
-  float hi[4], lo[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    hi[t] = __uint_as_float(__float_as_uint(x[t]) & 0xFFFFE000u);   // tf32: sign, 8 exponent, 10 mantissa bits
-    lo[t] = x[t] - hi[t];                                            // exact; the MMA reads its top 19 bits
-  }
-  const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((kc ^ (r & 7)) << 4);
-  *reinterpret_cast<float4*>(tile_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<float4*>(tile_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-}
-
-__global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant__ GemmGroup grp) {
+__global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant__ TcGroup grp) {
   extern __shared__ unsigned char smem_dyn[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_ready = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+
   int pi = 0;
   while (pi + 1 < grp.nprob && (int)blockIdx.x >= grp.p[pi + 1].tile_begin) ++pi;
-  const GemmProb P = grp.p[pi];   // into registers (indexed constant-bank reads in the inner loops are slow)
+  const TcProb& P = grp.p[pi];
+  const int M = P.M, N = P.N, K = P.K, a_mn = P.a_mn, b_mn = P.b_mn;
+
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) bar_init(&bars[s], 1);
+    for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+    bar_init(acc_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -173,98 +165,142 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   t -= split * per_split;
   const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
   const int kbeg = split * P.k_per_split;
-  const int kend = min(P.K, kbeg + P.k_per_split);
+  const int kend = min(K, kbeg + P.k_per_split);
   const int nkb = (kend - kbeg + BK - 1) / BK;
-  const uint32_t idesc = make_idesc();
 
-  // Three register sets: the operands of k-blocks kb+1 and kb+2 are in flight while kb is split and
-  // stored, so the L2 round trip of the operand fetch is hidden behind two k-blocks of work.
-  uint32_t phase_bits = 0;   // bit s = parity the next wait on stage s expects
-  const int dbg = g_tc_debug;
-  auto step = [&](int kb, const Frag& cur, Frag& pre) {
-    const int s = kb & 1;
-    if (kb + 2 < nkb && !(dbg & 1)) fetch_frag(P, tid, m0, n0, kbeg + (kb + 2) * BK, kend, pre);
-    if (kb >= STAGES && !(dbg & 4)) {   // the MMAs that read this stage two k-blocks ago must have retired
-      bar_wait(&bars[s], (phase_bits >> s) & 1u);
-      phase_bits ^= 1u << s;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    unsigned char* st = base + s * STAGE_BYTES;
-    if (!(dbg & 2)) {
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer ----
+      const CUtensorMap* ta = &P.ta;
+      const CUtensorMap* tb = &P.tb;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        if (kb >= STAGES) bar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
+        bar_expect_tx(&full[s], STAGE_BYTES);
+        const uint32_t st = s_addr(base + s * STAGE_BYTES);
+        const int k0 = kbeg + kb * BK;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int r, kc;
-        item_coords(tid, j, r, kc);
-        split_store(st, st + TILE_BYTES, r, kc, cur.a[j]);
-        split_store(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, r, kc, cur.b[j]);
+        for (int hl = 0; hl < 2; ++hl) {
+          const uint32_t da = st + hl * TILE_BYTES, db = st + (2 + hl) * TILE_BYTES;
+          if (!a_mn) tma_load_3d(da, ta, k0, m0, hl, &full[s]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_3d(da + j * 4096, ta, m0 + 32 * j, k0, hl, &full[s]);
+          }
+          if (!b_mn) tma_load_3d(db, tb, k0, n0, hl, &full[s]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_3d(db + j * 4096, tb, n0 + 32 * j, k0, hl, &full[s]);
+          }
+        }
       }
     }
-    if (!(dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-    __syncthreads();
-    if (tid == 0 && !(dbg & 4)) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = s_addr(st), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      const uint32_t idesc = make_idesc(a_mn, b_mn);
+      const uint32_t a_step = a_mn ? 1024u : 32u, b_step = b_mn ? 1024u : 32u;   // 8 tf32 of K
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        bar_wait(&full[s], (kb / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = s_addr(base + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES,
+                       b_lo = a_hi + 3 * TILE_BYTES;
 #pragma unroll
-      for (int ks = 0; ks < BK / 8; ++ks) {
-        const uint32_t ko = ks * 32;   // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
-        mma_tf32(tmem_d, make_sdesc(a_lo + ko), make_sdesc(b_hi + ko), idesc, (kb | ks) ? 1u : 0u);
-        mma_tf32(tmem_d, make_sdesc(a_hi + ko), make_sdesc(b_lo + ko), idesc, 1u);
-        mma_tf32(tmem_d, make_sdesc(a_hi + ko), make_sdesc(b_hi + ko), idesc, 1u);
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t ao = ks * a_step, bo = ks * b_step;
+          mma_tf32(tmem_d, make_sdesc(a_lo + ao, a_mn), make_sdesc(b_hi + bo, b_mn), idesc, (kb | ks) ? 1u : 0u);
+          mma_tf32(tmem_d, make_sdesc(a_hi + ao, a_mn), make_sdesc(b_lo + bo, b_mn), idesc, 1u);
+          mma_tf32(tmem_d, make_sdesc(a_hi + ao, a_mn), make_sdesc(b_hi + bo, b_mn), idesc, 1u);
+        }
+        mma_commit(&empty[s]);          // frees the stage when these MMAs have read it
       }
-      mma_commit(&bars[s]);
+      mma_commit(acc_ready);            // covers every MMA issued before it
     }
-  };
-  Frag f0, f1, f2;
-  fetch_frag(P, tid, m0, n0, kbeg, kend, f0);
-  if (nkb > 1) fetch_frag(P, tid, m0, n0, kbeg + BK, kend, f1);
-  for (int kb = 0; kb < nkb; kb += 3) {
-    step(kb, f0, f2);
-    if (kb + 1 < nkb) step(kb + 1, f1, f0);
-    if (kb + 2 < nkb) step(kb + 2, f2, f1);
+    __syncwarp();
   }
-  // the last commit covers every MMA issued before it
-  if (!(dbg & 4)) {
-    const int s = (nkb - 1) & 1;
-    bar_wait(&bars[s], (phase_bits >> s) & 1u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  }
+
+  bar_wait(acc_ready, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*(w/4)..+64
   {
     const int q = warp & 3, half = warp >> 2;
     const int m = m0 + 32 * q + lane;
+    const int epi = P.epi, ldc = P.ldc;
     float* C = P.C + (size_t)split * P.c_split_stride;
+    float* C_lo = P.C_lo;
+    const float* bias = P.bias;
 #pragma unroll
     for (int cb = 0; cb < 2; ++cb) {
       const int c0 = half * 64 + cb * 32;
+      const int n_base = n0 + c0;
+      if (n_base >= N) continue;                     // warp-uniform
       float v[32];
       tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
-      if (m < P.M) {
-        const int n_base = n0 + c0;
-        if (P.epi == EPI_RELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-        } else if (P.epi == EPI_MASK) {
-          const float* mk = P.mask + (size_t)m * P.ldmask + n_base;
+      if (m < M) {
+        const bool full_n = n_base + 31 < N;
+        if (bias) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (n_base + i < P.N) v[i] = mk[i] > 0.0f ? v[i] : 0.0f;
+            if (full_n || n_base + i < N) v[i] += __ldg(bias + n_base + i);
         }
-        float* dst = C + (size_t)m * P.ldc + n_base;
-        if (n_base + 31 < P.N && (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        if (epi == EPI_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        } else if (epi == EPI_MASK) {
+          const float* mk = P.mask + (size_t)m * P.ldmask + n_base;
+          const float* ml = P.mask_lo ? P.mask_lo + (size_t)m * P.ldmask + n_base : nullptr;
+          if (full_n) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(mk + i);
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ml) b = *reinterpret_cast<const float4*>(ml + i);
+              v[i] = (a.x > 0.0f || b.x > 0.0f) ? v[i] : 0.0f;
+              v[i + 1] = (a.y > 0.0f || b.y > 0.0f) ? v[i + 1] : 0.0f;
+              v[i + 2] = (a.z > 0.0f || b.z > 0.0f) ? v[i + 2] : 0.0f;
+              v[i + 3] = (a.w > 0.0f || b.w > 0.0f) ? v[i + 3] : 0.0f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n_base + i < N) v[i] = (mk[i] > 0.0f || (ml && ml[i] > 0.0f)) ? v[i] : 0.0f;
+          }
+        }
+        float* dst = C + (size_t)m * ldc + n_base;
+        const bool vec = full_n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (C_lo) {
+          float* dlo = C_lo + (size_t)m * ldc + n_base;
+          float lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) split_tf32(v[i], v[i], lo[i]);
+          if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              *reinterpret_cast<float4*>(dlo + i) = make_float4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n_base + i < N) { dst[i] = v[i]; dlo[i] = lo[i]; }
+          }
+        } else if (vec) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (n_base + i < P.N) dst[i] = v[i];
+            if (n_base + i < N) dst[i] = v[i];
         }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
   }
 }

@@ -211,6 +211,11 @@ int ddrl_sac_act(ddrl_sac_t sac, const float* d_obs, int n, int deterministic, c
                  uint64_t seed, uint64_t counter, float* d_out_act, void* stream);
 /* profiling aid: enqueue GEMM stage `stage` (0..6: L1, L2, QL1, QL2, BQ, BP, BP3) of the step `reps` times */
 int ddrl_sac_debug_stage(ddrl_sac_t sac, int batch, int stage, int reps, void* stream);
+/* Test entry for the tcgen05 3xTF32 GEMM alone: C[M,N] (splits > 1: `splits` partial outputs M*N floats apart)
+ * = opA . opB from dense row-major fp32 device matrices A [a_rows,a_cols], B [b_rows,b_cols]; a_mn / b_mn = 1
+ * when the contraction index is the ROW of the stored tensor (MN-major operand), 0 when it is the column. */
+int ddrl_debug_tc_gemm(int device, const float* d_a, int a_rows, int a_cols, int a_mn, const float* d_b, int b_rows,
+                       int b_cols, int b_mn, float* d_c, int m, int n, int k, int splits, void* stream);
 /* optimiser step counters and log_alpha (synchronises `stream`).  Any out may be NULL. */
 int ddrl_sac_state(ddrl_sac_t sac, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream);
 
