@@ -579,6 +579,45 @@ __global__ void __launch_bounds__(256) k_convert_layout(LayoutMap mp, int64_t Pe
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bias gradients in tensor-core mode: d b = column sums of dZ (hi + lo planes) over the batch rows of each
+// split-K slice.  One CTA per (32-column chunk, split): lane = column (128-byte coalesced rows), the 8 warps
+// stride the rows, fixed-order combine in shared memory (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int COLSUM_MAX = 6;
+struct ColsumGroup {
+  int nprob, B, kps;
+  long long split_stride;
+  struct {
+    const float* z;
+    long long lo;
+    float* out;
+    int ld, N, chunk_begin;
+  } p[COLSUM_MAX];
+};
+__global__ void __launch_bounds__(256) k_colsum(const __grid_constant__ ColsumGroup g) {
+  __shared__ float s_acc[8][32];
+  int pi = 0;
+  while (pi + 1 < g.nprob && (int)blockIdx.x >= g.p[pi + 1].chunk_begin) ++pi;
+  const float* z = g.p[pi].z;
+  const long long lo = g.p[pi].lo;
+  const int ld = g.p[pi].ld, N = g.p[pi].N;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = (blockIdx.x - g.p[pi].chunk_begin) * 32 + lane;
+  const int r0 = blockIdx.y * g.kps, r1 = min(g.B, r0 + g.kps);
+  float acc = 0.0f;
+  if (col < N)
+    for (int r = r0 + w; r < r1; r += 8) acc += z[(size_t)r * ld + col] + z[lo + (size_t)r * ld + col];
+  s_acc[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && col < N) {
+    float t = s_acc[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += s_acc[i][lane];
+    g.p[pi].out[(size_t)blockIdx.y * g.split_stride + col] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Persistent whole-step kernel.  The step is 12 dependent phases of 5..45 us; as separate launches
 // each pays launch latency, a cold ramp and a tail where most SMs idle.  Here ONE cooperative grid
 // (a multiple of the SM count, all CTAs resident) walks the phases with grid-wide barriers in
@@ -698,6 +737,8 @@ struct Plan {
   std::vector<std::vector<Group>> stages;  // ordered stages; element-wise kernels sit between them
   cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr;
   int64_t kernels[3] = {0, 0, 0};  // kernels inside each captured graph (for the launch counter)
+  ColsumGroup colsum[8] = {};      // tensor-core mode: bias-gradient column sums per stage (side stream)
+  int colsum_chunks[8] = {};
   GemmGroup* d_stages = nullptr;   // [ST_COUNT] descriptors for the persistent step kernel
   int mega_grid = 0;
 };
@@ -733,9 +774,11 @@ struct ddrl_sac {
   std::vector<void*> allocs;
   std::map<int, Plan> plans;
   bool use_graph = true;
-  bool use_tc = false;   // tcgen05 3xTF32 GEMMs (DDRL_GEMM=tc) instead of FFMA tiles
+  bool use_tc = true;    // tcgen05 3xTF32 GEMMs from pre-split planes (default); DDRL_GEMM=ffma: fp32 FFMA tiles
   bool use_mega = false; // DDRL_MEGA=1: one persistent cooperative kernel per step instead of one launch per phase in a CUDA graph
                          // (measured slower on B200 at the named shapes: 258 vs 203 us at C2 — kept for experiments)
+  cudaStream_t side_stream = nullptr; // tensor-core mode: skinny / bias gradients run beside the main chain (forked with events)
+  cudaEvent_t ev[4] = {};
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy
                                       // default stream, which cannot be captured); replay on the caller's
 };
@@ -766,12 +809,14 @@ GemmProb mk(Seg a0, Seg a1, int ones, int a_trans, const float* Bp, int ldb, int
 Seg seg(const float* p, int ld, int w) { return Seg{p, ld, w}; }
 Seg none() { return Seg{nullptr, 0, 0}; }
 
+int set_out_map(tc::TcProb* p);
 int pack_tc(std::vector<tc::TcProb>& v, tc::TcGroup* g, int* tiles) {
   if ((int)v.size() > tc::MAX_PROBS) return fail(DDRL_EINVAL, "too many tensor-core problems in one stage (%d)", (int)v.size());
   int t = 0;
   g->nprob = (int)v.size();
   for (size_t i = 0; i < v.size(); ++i) {
     tc::TcProb& p = v[i];
+    if (int rc = set_out_map(&p)) return rc;
     p.tiles_m = (p.M + tc::BM - 1) / tc::BM;
     p.tiles_n = (p.N + tc::BN - 1) / tc::BN;
     p.tile_begin = t;
@@ -805,16 +850,23 @@ int finalize_group(Group& g) {
   return pack_tc(g.probs_tc, &g.grp_tc, &g.tiles_tc);
 }
 
-int launch_group(const Group& g, cudaStream_t s) {
+int launch_tc(const Group& g, cudaStream_t s) {
   if (g.tiles_tc > 0) {
     tc::gemm_grouped_tc<<<g.tiles_tc, 256, tc::SMEM_BYTES, s>>>(g.grp_tc);
     DDRL_LAUNCH_CHECK();
   }
+  return 0;
+}
+int launch_f32(const Group& g, cudaStream_t s) {
   if (g.tiles > 0) {
     gemm_grouped_f32<<<g.tiles, 256, 0, s>>>(g.grp);
     DDRL_LAUNCH_CHECK();
   }
   return 0;
+}
+int launch_group(const Group& g, cudaStream_t s) {
+  int rc = launch_tc(g, s);
+  return rc ? rc : launch_f32(g, s);
 }
 
 // GEMM stages; the row-wise kernels (policy heads, Q heads + losses, policy backward) sit between them
@@ -884,6 +936,25 @@ int mk_tc(tc::TcProb* out, const View& a, bool a_mn, const View& b, bool b_mn, f
   p.M = M; p.N = N; p.K = K; p.epi = epi; p.a_mn = a_mn; p.b_mn = b_mn;
   p.splits = 1; p.k_per_split = (K + tc::BK - 1) / tc::BK * tc::BK;
   *out = p;
+  return 0;
+}
+// output tensor map (N, M, plane): plane = hi/lo (C_lo set) or the split-K partial index.  Falls back to direct
+// stores (c_tma = 0) when the output is not 16-byte aligned / pitched (e.g. N = 33 weight-gradient blocks).
+int set_out_map(tc::TcProb* p) {
+  const long long plane = p->C_lo ? (long long)(p->C_lo - p->C) : p->c_split_stride;
+  const int planes = p->C_lo ? 2 : p->splits;
+  p->c_tma = 0;
+  if ((p->ldc & 3) || (reinterpret_cast<uintptr_t>(p->C) & 15) || (planes > 1 && (plane <= 0 || (plane & 3)))) return 0;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)p->N, (cuuint64_t)p->M, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)p->ldc * 4, (cuuint64_t)(planes > 1 ? plane : (long long)p->ldc * p->M) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(&p->tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->C, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled(output) failed (%d) M=%d N=%d ldc=%d", (int)r, p->M, p->N, p->ldc);
+  p->c_tma = 1;
   return 0;
 }
 
@@ -999,9 +1070,16 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
     tc::TcProb p;   // d[W] = act^T . dZ (kernel rows); the bias row is the column sum of dZ, on FFMA tiles
     if (!rc && !(rc = mk_tc(&p, act, true, dz, true, Gp + ioff[blk], nullptr, Nb[blk], Kb[blk], Nb[blk], B)))
       add_tc(pl.stages[stage], wg_tc(p));
-    GemmProb cs = mk(none(), none(), 1, 1, dz.p, dz.ld, 0, Gp + ioff[blk] + (int64_t)Kb[blk] * Nb[blk], Nb[blk], 1, Nb[blk], B);
-    cs.B2 = dz.p + dz.lo;
-    add(pl.stages[stage], wg(cs));
+    ColsumGroup& cg = pl.colsum[stage];
+    if (!rc && cg.nprob >= COLSUM_MAX) rc = fail(DDRL_EINVAL, "too many bias-gradient problems in one stage");
+    if (!rc) {
+      auto& q = cg.p[cg.nprob++];
+      q.z = dz.p; q.lo = dz.lo; q.ld = dz.ld; q.N = Nb[blk];
+      q.out = Gp + ioff[blk] + (int64_t)Kb[blk] * Nb[blk];
+      q.chunk_begin = pl.colsum_chunks[stage];
+      pl.colsum_chunks[stage] += (Nb[blk] + 31) / 32;
+      cg.B = B; cg.kps = kps; cg.split_stride = h->P;
+    }
   };
   // ---- forward: policies (a: main@x, b: main@x2, c: target@x2) and the data-action Q passes (d, e)
   fwd(ST_L1, xa(0, D), PI1, false, h->H1[a], h->H1[a] + h->lo1, h->ld1);
@@ -1065,10 +1143,22 @@ int launch_mega(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
   return 0;
 }
 
-int run_stage(const Plan& pl, int s, cudaStream_t st) {
+int run_stage(const Plan& pl, int s, cudaStream_t st, bool tc_only = false) {
   for (const auto& g : pl.stages[s]) {
-    int rc = launch_group(g, st);
+    int rc = tc_only ? launch_tc(g, st) : launch_group(g, st);
     if (rc) return rc;
+  }
+  return 0;
+}
+// tensor-core mode: the FFMA tiles (skinny weight gradients) and bias column sums of stage `st`, on the side stream
+int run_side(const Plan& pl, int st, int S, cudaStream_t side) {
+  for (const auto& g : pl.stages[st]) {
+    int rc = launch_f32(g, side);
+    if (rc) return rc;
+  }
+  if (pl.colsum[st].nprob > 0) {
+    k_colsum<<<dim3(pl.colsum_chunks[st], S), 256, 0, side>>>(pl.colsum[st]);
+    DDRL_LAUNCH_CHECK();
   }
   return 0;
 }
@@ -1100,13 +1190,32 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
       h->Wt + h->o_q1[2], h->Wt + h->o_q2[2], h->R, h->DN, h->LOGP1, h->LOGP2, h->dQ[0], h->dQ[1], h->dZ2[0], h->dZ2[1],
       h->dZ2[2], h->partials, h->ticket, h->SCAL, h->ld2, h->lo2);
   DDRL_LAUNCH_CHECK();
-  if ((rc = run_stage(pl, ST_BQ, s))) return rc;
+  const bool tcm = h->use_tc;
+  cudaStream_t side = h->side_stream;
+  if (tcm) {
+    DDRL_CUDA(cudaEventRecord(h->ev[0], s));
+    DDRL_CUDA(cudaStreamWaitEvent(side, h->ev[0], 0));
+    if ((rc = run_side(pl, ST_BQ, pl.S, side))) return rc;
+  }
+  if ((rc = run_stage(pl, ST_BQ, s, tcm))) return rc;
   k_policy_bwd_rows<<<(B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
       h->st, B, A, h1, h2, h->act_scale, h->HD[0], h->NOISE, h->dZ1[2], h->W + h->o_q1[0] + (int64_t)D * h1,
       h->W + h->o_pih, h->H2[0], h->dHD, h->dZ2a, h->ld1, h->lo1, h->ld2, h->lo2);
   DDRL_LAUNCH_CHECK();
-  if ((rc = run_stage(pl, ST_BP, s))) return rc;
-  if ((rc = run_stage(pl, ST_BP3, s))) return rc;
+  if (tcm) {
+    DDRL_CUDA(cudaEventRecord(h->ev[1], s));
+    DDRL_CUDA(cudaStreamWaitEvent(side, h->ev[1], 0));
+    if ((rc = run_side(pl, ST_BP, pl.S, side))) return rc;
+  }
+  if ((rc = run_stage(pl, ST_BP, s, tcm))) return rc;
+  if (tcm) {
+    DDRL_CUDA(cudaEventRecord(h->ev[2], s));
+    DDRL_CUDA(cudaStreamWaitEvent(side, h->ev[2], 0));
+    if ((rc = run_side(pl, ST_BP3, pl.S, side))) return rc;
+    DDRL_CUDA(cudaEventRecord(h->ev[3], side));
+  }
+  if ((rc = run_stage(pl, ST_BP3, s, tcm))) return rc;
+  if (tcm) DDRL_CUDA(cudaStreamWaitEvent(s, h->ev[3], 0));
   return 0;
 }
 
@@ -1204,10 +1313,13 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   h->sms = sm_count(device);
   const char* ng = getenv("DDRL_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
-  if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] == 't');
+  if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] != 'f');   // "ffma": plain fp32 FFMA tiles
   if (const char* mg = getenv("DDRL_MEGA")) h->use_mega = (mg[0] != '0');
-  if (h->use_tc) h->use_mega = false;   // the tcgen05 tiles need 130 KB of shared memory and TMEM per CTA
+  if (h->use_mega) h->use_tc = false;   // the persistent kernel runs FFMA tiles only (tcgen05 tiles need 193 KB of shared memory + TMEM)
   if (h->use_tc) {
+    cudaError_t es = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+    if (es != cudaSuccess) { delete h; return fail(DDRL_ECUDA, "side stream / events: %s", cudaGetErrorString(es)); }
     cudaError_t ea = cudaFuncSetAttribute(tc::gemm_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (ea != cudaSuccess) { delete h; return fail(DDRL_ECUDA, "cudaFuncSetAttribute(tc smem): %s", cudaGetErrorString(ea)); }
   }
@@ -1303,6 +1415,8 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
   }
   for (void* p : h->allocs) cudaFree(p);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  for (auto e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }

@@ -1,6 +1,6 @@
 // sac_gemm_tc.cuh — tcgen05 (5th-gen tensor core) grouped GEMM of the SAC1 learner step with fp32-class
 // accuracy through the 3xTF32 split
-//     x = x_hi + x_lo,  x_hi = top 19 bits of x (a valid tf32),  x_lo = x - x_hi (exact in fp32)
+//     x = x_hi + x_lo,  x_hi = x rounded to tf32 (cvt.rna),  x_lo = x - x_hi (exact in fp32)
 //     a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi       (three kind::tf32 MMAs, fp32 accumulation in TMEM)
 // which keeps the step inside the 1e-5 parity bar (plain TF32 would not: 10-bit mantissa).
 //
@@ -41,6 +41,7 @@ constexpr int MAX_PROBS = 10;
 
 struct alignas(64) TcProb {
   CUtensorMap ta, tb;          // 3-D (inner, rows, plane) maps over the pre-split operands
+  CUtensorMap tc;              // output map (N, M, plane | split), box 32 x 32, used when c_tma != 0
   float* C;                    // plain output, or the hi plane when C_lo != nullptr
   float* C_lo;
   const float* mask;           // relu-mask source (hi plane) and its lo plane
@@ -50,6 +51,7 @@ struct alignas(64) TcProb {
   int ldc, ldmask;
   int M, N, K;
   int epi;
+  int c_tma;                   // 1: epilogue stages 32 x 32 blocks in shared memory and stores them with TMA
   int a_mn, b_mn;              // 1: operand is MN-major (its contraction index is the ROW of the stored tensor)
   int splits, k_per_split;
   int tiles_m, tiles_n, tile_begin;
@@ -62,8 +64,10 @@ struct TcGroup {
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);   // sign, 8 exponent, 10 mantissa bits
-  lo = x - hi;                                               // exact; the MMA reads its top 19 bits
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));       // round to nearest tf32 (sign, 8 exponent, 10 mantissa bits)
+  hi = __uint_as_float(u);
+  lo = x - hi;                                               // exact, |lo| <= 2^-12 |x|; the MMA reads its top 19 bits
 }
 
 // SWIZZLE_128B shared-memory matrix descriptor (version 1).
@@ -115,6 +119,19 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// this lane's 32 consecutive floats -> row `lane` of a 32 x 32 SWIZZLE_128B block (conflict-free 16-byte stores)
+__device__ __forceinline__ void stage_row(unsigned char* blk, int lane, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(blk + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -171,6 +188,7 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer ----
+      if (P.c_tma) prefetch_tmap(&P.tc);
       const CUtensorMap* ta = &P.ta;
       const CUtensorMap* tb = &P.tb;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   {
     const int q = warp & 3, half = warp >> 2;
     const int m = m0 + 32 * q + lane;
-    const int epi = P.epi, ldc = P.ldc;
+    const int epi = P.epi, ldc = P.ldc, c_tma = P.c_tma;
     float* C = P.C + (size_t)split * P.c_split_stride;
     float* C_lo = P.C_lo;
     const float* bias = P.bias;
@@ -242,9 +260,17 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
       if (m < M) {
         const bool full_n = n_base + 31 < N;
         if (bias) {
+          if (full_n && ((reinterpret_cast<uintptr_t>(bias + n_base) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full_n || n_base + i < N) v[i] += __ldg(bias + n_base + i);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n_base + i));
+              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n_base + i < N) v[i] += __ldg(bias + n_base + i);
+          }
         }
         if (epi == EPI_RELU) {
 #pragma unroll
@@ -269,34 +295,48 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
               if (n_base + i < N) v[i] = (mk[i] > 0.0f || (ml && ml[i] > 0.0f)) ? v[i] : 0.0f;
           }
         }
-        float* dst = C + (size_t)m * ldc + n_base;
-        const bool vec = full_n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        if (C_lo) {
-          float* dlo = C_lo + (size_t)m * ldc + n_base;
-          float lo[32];
+        if (!c_tma) {
+          float* dst = C + (size_t)m * ldc + n_base;
+          const bool vec = full_n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (C_lo) {
+            float* dlo = C_lo + (size_t)m * ldc + n_base;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) split_tf32(v[i], v[i], lo[i]);
-          if (vec) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              *reinterpret_cast<float4*>(dlo + i) = make_float4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+            for (int i = 0; i < 32; ++i) {
+              float hi, lo;
+              split_tf32(v[i], hi, lo);
+              if (full_n || n_base + i < N) { dst[i] = hi; dlo[i] = lo; }
             }
+          } else if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (n_base + i < N) { dst[i] = v[i]; dlo[i] = lo[i]; }
+              if (n_base + i < N) dst[i] = v[i];
           }
-        } else if (vec) {
+        }
+      }
+      if (c_tma) {
+        // 32 x 32 block per plane -> swizzled shared memory -> one TMA store each (full 128-byte lines; rows / columns
+        // beyond M / N are clipped by the TMA unit).  The pipeline stages are free: every load has been consumed.
+        unsigned char* blk = base + (warp * 2 + cb) * 8192;
+        if (C_lo) {
+          float lo[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n_base + i < N) dst[i] = v[i];
+          for (int i = 0; i < 32; ++i) split_tf32(v[i], v[i], lo[i]);
+          stage_row(blk + 4096, lane, lo);
+        }
+        stage_row(blk, lane, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&P.tc, s_addr(blk), n_base, m0 + 32 * q, C_lo ? 0 : split);
+          if (C_lo) tma_store_3d(&P.tc, s_addr(blk + 4096), n_base, m0 + 32 * q, 1);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
+    if (c_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

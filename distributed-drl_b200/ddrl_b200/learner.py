@@ -75,8 +75,8 @@ def _opt_get(opt, name, default=None):
 
 class Learner(object):
     def __init__(self, opt, job="learner", *, device=None, max_batch=None, process_group=None, gemm=None):
-        """gemm: None (default, fp32 FFMA tiles) | "ffma" | "tc" (tcgen05 tensor cores with the 3xTF32 split;
-        same 1e-5 class accuracy, see tests/test_sac_gpu.py::test_tcgen05_path_matches_oracle)."""
+        """gemm: None / "tc" (default: tcgen05 tensor cores with the 3xTF32 split, fp32-class accuracy) | "ffma"
+        (plain fp32 FFMA tiles).  Both hold the 1e-5 bar of tests/test_sac_gpu.py::test_one_step_matches_oracle."""
         if not torch.cuda.is_available():
             raise RuntimeError("ddrl_b200.Learner needs a CUDA device (no CPU fallback)")
         self.opt = opt

@@ -57,10 +57,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("gemm", ["tc", "ffma"])
 @pytest.mark.parametrize("D,A,hidden,B,scale", CASES)
-def test_one_step_matches_oracle(L, D, A, hidden, B, scale):
+def test_one_step_matches_oracle(L, D, A, hidden, B, scale, gemm):
+    """gemm="tc" (the default): tcgen05.mma kind::tf32 with the 3xTF32 split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,
+    fp32 accumulation in TMEM) from TMA-fed pre-split operands; gemm="ffma": plain fp32 FFMA tiles.  Same bar."""
     params = conditioned_params(D, A, hidden, seed=100 + D)
-    learner, oracle = build_pair(L, D, A, hidden, B, params, act_scale=scale)
+    learner, oracle = build_pair(L, D, A, hidden, B, params, gemm=gemm, act_scale=scale)
     batch, noise = make_batch(D, A, B, seed=200 + D)
     opt_lr = 1e-3
     want_g = oracle.flat_grads(batch, noise)
@@ -86,11 +89,14 @@ def test_one_step_matches_oracle(L, D, A, hidden, B, scale):
     #     step is lr*g/(|g| + 1e-8*sqrt(1000)...): for |g| within a few orders of 1e-8 a 1e-7 relative
     #     gradient difference moves the update by more than 1e-5*|w| in ANY float32 evaluation
     #     (the float32 oracle itself is 0.96e-5 away from float64 on the Humanoid-shaped case).
+    #     The epsilon-dominated remainder gets a stated 5e-5 (FFMA) / 1e-4 (3xTF32: products carry ~2^-22 instead
+    #     of 2^-24 relative error, which the same Adam amplification turns into a 2x looser bound).
     solid = np.abs(want_g) > 1e-4 * np.abs(want_g).max()
+    loose = 1e-4 if gemm == "tc" else 5 * TOL
     assert rel(got_w[solid], want_w[solid]) <= TOL
-    assert rel(got_w, want_w) <= 5 * TOL
+    assert rel(got_w, want_w) <= loose
     got_t, want_t = learner.get_flat_weights("target").cpu().numpy(), oracle.flat("target")
-    assert rel(got_t[solid], want_t[solid]) <= TOL and rel(got_t, want_t) <= 5 * TOL
+    assert rel(got_t[solid], want_t[solid]) <= TOL and rel(got_t, want_t) <= loose
     # weights come back through the reference's (keys, values) contract, TF1 names and shapes
     keys, values = learner.get_weights()
     assert keys == param_names()
@@ -197,27 +203,3 @@ def test_default_init_regime_against_float32_oracle(L):
     sc = got["scalars"].cpu().numpy()
     for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
         assert abs(sc[i] - float(want[k])) <= 2e-3 * abs(float(want[k])), k
-
-
-@pytest.mark.parametrize("D,A,hidden,B,scale", [(24, 4, (256, 256), 1024, 1.0), (376, 17, (256, 256), 300, 0.4),
-                                                 (5, 3, (33, 17), 37, 0.4)])
-def test_tcgen05_path_matches_oracle(L, D, A, hidden, B, scale):
-    """The tensor-core path (tcgen05.mma kind::tf32, three MMAs per product: a_lo*b_hi + a_hi*b_lo +
-    a_hi*b_hi, fp32 accumulation in TMEM) keeps the fp32-class tolerance: losses 1e-5, gradients 2e-5
-    of max|g|, well-determined weights 1e-5; epsilon-dominated Adam entries get a stated 1e-4."""
-    params = conditioned_params(D, A, hidden, seed=100 + D)
-    learner, oracle = build_pair(L, D, A, hidden, B, params, gemm="tc", act_scale=scale)
-    batch, noise = make_batch(D, A, B, seed=200 + D)
-    want_g = oracle.flat_grads(batch, noise)
-    want = oracle.step(batch, noise)
-    got = learner.train(batch, noise=noise, split=True, sync_outputs=True)
-    sc = got["scalars"].cpu().numpy()
-    for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
-        assert abs(sc[i] - float(want[k])) <= TOL * abs(float(want[k])), (k, sc[i], float(want[k]))
-    for k in ("q1", "q2", "logp_pi"):
-        assert rel(got[k].cpu().numpy(), want[k]) <= TOL, k
-    assert rel(learner.get_flat_weights("grad").cpu().numpy(), want_g) <= 2 * TOL
-    got_w, want_w = learner.get_flat_weights("main").cpu().numpy(), oracle.flat("main")
-    solid = np.abs(want_g) > 1e-4 * np.abs(want_g).max()
-    assert rel(got_w[solid], want_w[solid]) <= TOL
-    assert rel(got_w, want_w) <= 1e-4
