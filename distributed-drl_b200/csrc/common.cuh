@@ -53,10 +53,31 @@ struct DeviceGuard {
 
 int sm_count(int device);
 
+#ifdef __CUDACC__
+extern bool g_use_pdl;   // DDRL_PDL=1 turns programmatic dependent launch on (off by default: slower inside graphs)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its stream predecessor is
+// still running.  pdl_wait() blocks until the predecessor grid has completed and its writes are visible (a no-op
+// for a normal launch); EVERY kernel of a chain calls it before touching global memory, so completion is
+// transitive.  pdl_trigger() lets the successor's CTAs be scheduled as soon as this grid's CTAs are all resident.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // 128-bit streaming load that does not allocate in L1 (rows of a random gather are not re-used)
 __device__ __forceinline__ float4 ld_nc_f4(const float4* p) {

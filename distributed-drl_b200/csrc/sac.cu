@@ -127,6 +127,8 @@ __device__ __forceinline__ void d_prologue(int vb, int vgrid, const StepState* _
 }
 __global__ void __launch_bounds__(256) k_prologue(const StepState* __restrict__ st, int B, int D, int A, float* X, float* X2,
                                                   float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
+  pdl_trigger();
+  pdl_wait();
   d_prologue(blockIdx.x, gridDim.x, st, B, D, A, X, X2, ACT, R, DN, NOISE, xa);
 }
 
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_fwd(
     int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
     const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D) {
+  pdl_trigger();
+  pdl_wait();
   d_policy_heads_fwd(blockIdx.x, B, A, h2, act_scale, H2a, H2b, H2c, Whead, Whead_t, NOISE, HD, A1, A3, LOGP1, LOGP2, xa, D);
 }
 
@@ -348,6 +352,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
     const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
     const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
     float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz, long long zlo) {
+  pdl_trigger();
+  pdl_wait();
   d_qheads_losses(blockIdx.x, gridDim.x, st, B, h2, gamma, H2d, H2e, H2f, H2g, H2h, W3q1, W3q2, W3q1t, W3q2t, R, DN, LOGP1, LOGP2,
                   dQd, dQe, dZ2d, dZ2e, dZ2f, partials, ticket, SCAL, ldz, zlo);
 }
@@ -406,6 +412,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
     const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
     const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a, int ld1, long long lo1, int ldz,
     long long zlo) {
+  pdl_trigger();
+  pdl_wait();
   d_policy_bwd_rows(blockIdx.x, st, B, A, h1, h2, act_scale, HDa, NOISE, dZ1f, W1q1_act, Whead, H2a, dHD, dZ2a, ld1, lo1, ldz, zlo);
 }
 
@@ -475,6 +483,8 @@ __device__ __forceinline__ void d_grad_reduce(int vb, int vgrid, int64_t P, int 
   }
 }
 __global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const float* __restrict__ Gp, float* G) {
+  pdl_trigger();
+  pdl_wait();
   d_grad_reduce(blockIdx.x, gridDim.x, P, S, Gp, G);
 }
 
@@ -542,12 +552,16 @@ __device__ __forceinline__ void d_adam_polyak(int vb, int vgrid, StepState* st, 
 __global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, int64_t P_pi, int S, const float* __restrict__ Gp,
                                                      float lr, float polyak, float target_entropy, const float* __restrict__ SCAL,
                                                      float* W, float* Wt, float* Mo, float* Vo) {
+  pdl_trigger();
+  pdl_wait();
   d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo);
 }
 __global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_t P, int64_t P_pi, int S, const float* __restrict__ Gp,
                                                            float lr, float polyak, float target_entropy,
                                                            const float* __restrict__ SCAL, float* W, float* Wt, float* Mo, float* Vo,
                                                            const __grid_constant__ SplitMap mp, float* Wsp, float* Wtsp) {
+  pdl_trigger();
+  pdl_wait();
   d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo, &mp, Wsp, Wtsp);
 }
 
@@ -852,14 +866,14 @@ int finalize_group(Group& g) {
 
 int launch_tc(const Group& g, cudaStream_t s) {
   if (g.tiles_tc > 0) {
-    tc::gemm_grouped_tc<<<g.tiles_tc, 256, tc::SMEM_BYTES, s>>>(g.grp_tc);
+    DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc, dim3(g.tiles_tc), dim3(256), tc::SMEM_BYTES, s, g.grp_tc));
     DDRL_LAUNCH_CHECK();
   }
   return 0;
 }
 int launch_f32(const Group& g, cudaStream_t s) {
   if (g.tiles > 0) {
-    gemm_grouped_f32<<<g.tiles, 256, 0, s>>>(g.grp);
+    DDRL_CUDA(launch_pdl(gemm_grouped_f32, dim3(g.tiles), dim3(256), 0, s, g.grp));
     DDRL_LAUNCH_CHECK();
   }
   return 0;
@@ -1167,29 +1181,50 @@ XaOut xa_out(const ddrl_sac* h) {
   return h->use_tc ? XaOut{h->XA[0], h->XA[1], h->XA[2], h->ldx, h->lox} : XaOut{nullptr, nullptr, nullptr, 0, 0};
 }
 
-int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+int launch_prologue(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   const int B = pl.B, D = h->D, A = h->A;
-  int rc;
-  {
-    const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
-    int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
-    k_prologue<<<blocks, 256, 0, s>>>(h->st, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN, h->NOISE, xa_out(h));
-    DDRL_LAUNCH_CHECK();
-  }
-  if ((rc = run_stage(pl, ST_L1, s))) return rc;
-  if ((rc = run_stage(pl, ST_L2, s))) return rc;
-  const int h1 = h->h1, h2 = h->h2;
-  k_policy_heads_fwd<<<(3 * B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
-      B, A, h2, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0], h->A1,
-      h->A3, h->LOGP1, h->LOGP2, xa_out(h), D);
+  const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
+  int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
+  DDRL_CUDA(launch_pdl(k_prologue, dim3(blocks), dim3(256), 0, s, h->st, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN, h->NOISE,
+                       xa_out(h)));
   DDRL_LAUNCH_CHECK();
-  if ((rc = run_stage(pl, ST_QL1, s))) return rc;
-  if ((rc = run_stage(pl, ST_QL2, s))) return rc;
-  k_qheads_losses<<<(B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
+  return 0;
+}
+int launch_heads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+  const int B = pl.B, D = h->D, A = h->A, h2 = h->h2;
+  DDRL_CUDA(launch_pdl(k_policy_heads_fwd, dim3((3 * B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
+      B, A, h2, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0], h->A1,
+      h->A3, h->LOGP1, h->LOGP2, xa_out(h), D));
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+int launch_qheads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+  const int B = pl.B, h2 = h->h2;
+  DDRL_CUDA(launch_pdl(k_qheads_losses, dim3((B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
       h->st, B, h2, h->gamma, h->H2[3], h->H2[4], h->H2[5], h->H2[6], h->H2[7], h->W + h->o_q1[2], h->W + h->o_q2[2],
       h->Wt + h->o_q1[2], h->Wt + h->o_q2[2], h->R, h->DN, h->LOGP1, h->LOGP2, h->dQ[0], h->dQ[1], h->dZ2[0], h->dZ2[1],
-      h->dZ2[2], h->partials, h->ticket, h->SCAL, h->ld2, h->lo2);
+      h->dZ2[2], h->partials, h->ticket, h->SCAL, h->ld2, h->lo2));
   DDRL_LAUNCH_CHECK();
+  return 0;
+}
+int launch_pbwd(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+  const int B = pl.B, D = h->D, A = h->A, h1 = h->h1, h2 = h->h2;
+  DDRL_CUDA(launch_pdl(k_policy_bwd_rows, dim3((B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
+      h->st, B, A, h1, h2, h->act_scale, h->HD[0], h->NOISE, h->dZ1[2], h->W + h->o_q1[0] + (int64_t)D * h1,
+      h->W + h->o_pih, h->H2[0], h->dHD, h->dZ2a, h->ld1, h->lo1, h->ld2, h->lo2));
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+  int rc;
+  if ((rc = launch_prologue(h, pl, s))) return rc;
+  if ((rc = run_stage(pl, ST_L1, s))) return rc;
+  if ((rc = run_stage(pl, ST_L2, s))) return rc;
+  if ((rc = launch_heads(h, pl, s))) return rc;
+  if ((rc = run_stage(pl, ST_QL1, s))) return rc;
+  if ((rc = run_stage(pl, ST_QL2, s))) return rc;
+  if ((rc = launch_qheads(h, pl, s))) return rc;
   const bool tcm = h->use_tc;
   cudaStream_t side = h->side_stream;
   if (tcm) {
@@ -1198,10 +1233,7 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
     if ((rc = run_side(pl, ST_BQ, pl.S, side))) return rc;
   }
   if ((rc = run_stage(pl, ST_BQ, s, tcm))) return rc;
-  k_policy_bwd_rows<<<(B + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(
-      h->st, B, A, h1, h2, h->act_scale, h->HD[0], h->NOISE, h->dZ1[2], h->W + h->o_q1[0] + (int64_t)D * h1,
-      h->W + h->o_pih, h->H2[0], h->dHD, h->dZ2a, h->ld1, h->lo1, h->ld2, h->lo2);
-  DDRL_LAUNCH_CHECK();
+  if ((rc = launch_pbwd(h, pl, s))) return rc;
   if (tcm) {
     DDRL_CUDA(cudaEventRecord(h->ev[1], s));
     DDRL_CUDA(cudaStreamWaitEvent(side, h->ev[1], 0));
@@ -1221,7 +1253,7 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 
 int enqueue_reduce(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
-  k_grad_reduce<<<blocks, 256, 0, s>>>(h->P, pl.S, h->Gp, h->G);
+  DDRL_CUDA(launch_pdl(k_grad_reduce, dim3(blocks), dim3(256), 0, s, h->P, pl.S, h->Gp, h->G));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1229,11 +1261,11 @@ int enqueue_reduce(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s) {
   int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
   if (h->use_tc)
-    k_adam_polyak_split<<<blocks, 256, 0, s>>>(h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak, -(float)h->A, h->SCAL, h->W,
-                                               h->Wt, h->Mo, h->Vo, h->smap, h->Wsp, h->Wtsp);
+    DDRL_CUDA(launch_pdl(k_adam_polyak_split, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak,
+                         -(float)h->A, h->SCAL, h->W, h->Wt, h->Mo, h->Vo, h->smap, h->Wsp, h->Wtsp));
   else
-    k_adam_polyak<<<blocks, 256, 0, s>>>(h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak, -(float)h->A, h->SCAL, h->W,
-                                         h->Wt, h->Mo, h->Vo);
+    DDRL_CUDA(launch_pdl(k_adam_polyak, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak,
+                         -(float)h->A, h->SCAL, h->W, h->Wt, h->Mo, h->Vo));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1520,9 +1552,20 @@ int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* str
   Plan* pl = nullptr;
   int rc = get_plan(h, batch, &pl);
   if (rc) return rc;
-  if (stage < 0 || stage >= ST_COUNT) return fail(DDRL_EINVAL, "ddrl_sac_debug_stage: stage %d not in [0,%d)", stage, (int)ST_COUNT);
-  for (int i = 0; i < reps; ++i)
-    if ((rc = run_stage(*pl, stage, (cudaStream_t)stream))) return rc;
+  // 0..6: GEMM stages (tensor-core tiles only in tc mode); 7 prologue, 8 policy heads, 9 Q heads + losses, 10 policy
+  // backward rows, 11 optimiser (state advances!), 12..14: side-stream work of BQ / BP / BP3
+  if (stage < 0 || stage > 14) return fail(DDRL_EINVAL, "ddrl_sac_debug_stage: stage %d not in [0,14]", stage);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < reps; ++i) {
+    if (stage < ST_COUNT) rc = run_stage(*pl, stage, s, h->use_tc);
+    else if (stage == 7) rc = launch_prologue(h, *pl, s);
+    else if (stage == 8) rc = launch_heads(h, *pl, s);
+    else if (stage == 9) rc = launch_qheads(h, *pl, s);
+    else if (stage == 10) rc = launch_pbwd(h, *pl, s);
+    else if (stage == 11) rc = enqueue_apply(h, pl->S, h->Gp, s);
+    else rc = h->use_tc ? run_side(*pl, ST_BQ + (stage - 12), pl->S, s) : 0;
+    if (rc) return rc;
+  }
   return 0;
 }
 

@@ -200,6 +200,8 @@ struct GemmGroup {
 
 __global__ void __launch_bounds__(256, 3) gemm_grouped_f32(const __grid_constant__ GemmGroup grp) {
   __shared__ __align__(16) float smem_raw[GEMM_SMEM_FLOATS];
+  pdl_trigger();
+  pdl_wait();
   int pi = 0;
   while (pi + 1 < grp.nprob && (int)blockIdx.x >= grp.p[pi + 1].tile_begin) ++pi;
   const GemmProb P = grp.p[pi];   // into registers (indexed constant-bank reads in the inner loops are slow)

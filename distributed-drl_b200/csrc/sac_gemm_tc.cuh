@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   const int M = P.M, N = P.N, K = P.K, a_mn = P.a_mn, b_mn = P.b_mn;
 
   if (tid == 0) {
+    prefetch_tmap(&P.ta);
+    prefetch_tmap(&P.tb);
     for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
     bar_init(acc_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -171,10 +173,12 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();     // the next kernel of the chain may set up (barriers, TMEM, descriptor prefetch) under this one
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  pdl_wait();        // everything above touched no global data; operands are complete and visible from here on
 
   int t = blockIdx.x - P.tile_begin;
   const int per_split = P.tiles_m * P.tiles_n;

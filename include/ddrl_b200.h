@@ -209,7 +209,8 @@ int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
  * d_noise [n, A] or, when NULL, Philox keyed by (seed, counter).  Uses the handle's main policy weights. */
 int ddrl_sac_act(ddrl_sac_t sac, const float* d_obs, int n, int deterministic, const float* d_noise,
                  uint64_t seed, uint64_t counter, float* d_out_act, void* stream);
-/* profiling aid: enqueue GEMM stage `stage` (0..6: L1, L2, QL1, QL2, BQ, BP, BP3) of the step `reps` times */
+/* profiling aid: enqueue one phase of the step `reps` times (0..6: GEMM stages L1, L2, QL1, QL2, BQ, BP, BP3;
+ * 7 prologue, 8 policy heads, 9 Q heads + losses, 10 policy backward rows, 11 optimiser, 12..14 side-stream work) */
 int ddrl_sac_debug_stage(ddrl_sac_t sac, int batch, int stage, int reps, void* stream);
 /* Test entry for the tcgen05 3xTF32 GEMM alone: C[M,N] (splits > 1: `splits` partial outputs M*N floats apart)
  * = opA . opB from dense row-major fp32 device matrices A [a_rows,a_cols], B [b_rows,b_cols]; a_mn / b_mn = 1

@@ -18,7 +18,7 @@ batch = dict(obs1=torch.randn(B, D, device=dev), obs2=torch.randn(B, D, device=d
              rews=torch.randn(B, device=dev), done=torch.zeros(B, device=dev))
 L.train(batch); torch.cuda.synchronize()
 lib = _native.lib(); s = torch.cuda.current_stream()
-names = ["L1", "L2", "QL1", "QL2", "BQ", "BP", "BP3"]
+names = ["L1", "L2", "QL1", "QL2", "BQ", "BP", "BP3", "prologue", "heads", "qheads", "pbwd", "adam", "sideBQ", "sideBP", "sideBP3"]
 for st, nm in enumerate(names):
     reps = 50
     _native.check(lib.ddrl_sac_debug_stage(L._h, B, st, 5, C.c_void_p(s.cuda_stream)))
@@ -27,4 +27,4 @@ for st, nm in enumerate(names):
     e0.record()
     _native.check(lib.ddrl_sac_debug_stage(L._h, B, st, reps, C.c_void_p(s.cuda_stream)))
     e1.record(); torch.cuda.synchronize()
-    print(f"{os.environ.get('DDRL_GEMM','simt'):5s} {cfg} stage {nm:4s}: {e0.elapsed_time(e1)/reps*1e3:8.1f} us", flush=True)
+    print(f"{os.environ.get('DDRL_GEMM','simt'):5s} {cfg} stage {nm:8s}: {e0.elapsed_time(e1)/reps*1e3:8.1f} us", flush=True)
