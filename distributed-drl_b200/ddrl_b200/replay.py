@@ -26,6 +26,14 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class HostBatch(dict):
+    """sample_batch()'s host result: the reference's dict of five numpy arrays.  The arrays are views of ONE
+    pinned block (`block`, the layout ddrl_rb_sample_host wrote), which lets Learner.train() feed the batch
+    back to the GPU with a single H2D copy instead of five."""
+    block = None      # pinned torch.uint8 tensor backing the arrays
+    n = 0             # rows
+
+
 class ReplayBuffer:
     """Drop-in for the reference ReplayBuffer.
 
@@ -70,6 +78,10 @@ class ReplayBuffer:
         self._stages = [self._new_stage() for _ in range(2)]
         self._cur = 0
         self._staged = 0
+        # pinned staging for store_batch() from host arrays (vectorised producers): two sets, by-value capture
+        self._bstage_rows = 8192
+        self._bstages = None
+        self._bcur = 0
 
     # ------------------------------------------------------------------------------------------
     def _new_stage(self):
@@ -149,9 +161,35 @@ class ReplayBuffer:
         n = int(np_arrs[2].shape[0])
         D, A = self.obs_dim, self.act_dim
         shapes = [(n, D), (n, A), (n,), (n, D), (n,)]
+        s = self._stream()
+        if self._bstages is None and n <= self._bstage_rows:
+            R = self._bstage_rows
+            pin = dict(dtype=torch.float32, pin_memory=True)
+            def mk():
+                ts = [torch.empty((R, D), **pin), torch.empty((R, A), **pin), torch.empty(R, **pin),
+                      torch.empty((R, D), **pin), torch.empty(R, **pin)]
+                return dict(bufs=[(t, t.numpy()) for t in ts], event=None)
+            self._bstages = [mk(), mk()]
+        if n <= self._bstage_rows:
+            # by-value capture into our own pinned staging (numpy assignment = the reference's cast), then
+            # asynchronous H2D copies: no stream synchronisation on the producer's call path
+            st = self._bstages[self._bcur]
+            self._bcur ^= 1
+            if st["event"] is not None:
+                st["event"].synchronize()
+            views = []
+            for (t, v), a, sh in zip(st["bufs"], np_arrs, shapes):
+                dst = v[:n] if len(sh) == 1 else v[:n].reshape(sh)
+                np.copyto(dst, a.reshape(sh), casting="unsafe")
+                views.append(t)
+            N.check(self._lib.ddrl_rb_store_batch_host(
+                self._h, *[_ptr(t) for t in views], n, N.F32, C.c_void_p(s.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(s)
+            st["event"] = ev
+            return
         # host-side cast to float32 is numpy's own assignment cast, i.e. the reference's semantics
         host = [np.ascontiguousarray(a.reshape(sh), dtype=np.float32) for a, sh in zip(np_arrs, shapes)]
-        s = self._stream()
         N.check(self._lib.ddrl_rb_store_batch_host(
             self._h, *[C.c_void_p(a.ctypes.data) for a in host], n, N.F32, C.c_void_p(s.cuda_stream)))
         # pageable source memory: the copies above are staged synchronously by the driver for
@@ -243,7 +281,8 @@ class ReplayBuffer:
             nf = n * (2 * D + A + 2)
             f = raw[: nf * 4].view(np.float32)
             o = 0
-            out = {}
+            out = HostBatch()
+            out.block, out.n = block, n
             for key, width, shape in (("obs1", D, lead + (D,)), ("obs2", D, lead + (D,)),
                                       ("acts", A, act_shape), ("rews", 1, lead), ("done", 1, lead)):
                 out[key] = f[o:o + n * width].reshape(shape)
