@@ -43,12 +43,10 @@ struct StepState {  // persistent
   int auto_alpha;
   float alpha_const;
   float lr, lr_pi, lr_q;  // base rate and TF1 Adam's bias-corrected rates for this step
-  unsigned int mega_barrier;   // arrival counter of the persistent step kernel's grid barriers
 };
 
 __global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
   st->dyn = dyn;
-  st->mega_barrier = 0u;
   if (advance) {
     st->t_pi += 1;
     st->t_q += 1;
@@ -209,89 +207,263 @@ __device__ __forceinline__ void warp_dots(const float* __restrict__ x, int K, co
 
 // policy heads + squashed-Gaussian sample / log-likelihood for the three policy passes
 // (pass 0: main pi(x) -> A1, LOGP1, HD;  pass 1: main pi(x2) -> LOGP2;  pass 2: target pi(x2) -> A3)
-__device__ __forceinline__ void d_policy_heads_fwd(
-    int vb, int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
+// One THREAD per (row, head output): the row of H2 sits in shared memory, the weight column W[:, j] is read
+// with the same address across the rows of a CTA (L1 broadcast) and consecutive j are consecutive floats.
+// R = 256 / 2A rows per CTA.  ldh = row pitch of the head block (2A rounded up to 4 floats).
+constexpr int HEADS_THREADS = 256;
+constexpr size_t HEADS_SMEM_MAX = 96 * 1024;
+// RB = rows per thread (register blocking: one weight load feeds RB rows).  A CTA covers R = RB * (256 / 2A) rows.
+template <int RB>
+__global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
+    int B, int A, int h2, int ldh, int R, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
-    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2,
-    XaOut xa = XaOut{nullptr, nullptr, nullptr, 0, 0}, int D = 0) {
-  __shared__ float s_out[ROW_WARPS][MAX_HEAD];
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D) {
+  extern __shared__ __align__(16) float hsm[];
+  pdl_trigger();
+  pdl_wait();
+  const int n = 2 * A, ldx = (h2 + 3) / 4 * 4 + 4;
+  float* xs = hsm;                    // [R][ldx]
+  float* s_out = xs + R * ldx;        // [R][n]   head pre-activations
+  float* s_pre = s_out + R * n;       // [R][A]   gaussian log-likelihood terms
+  float* s_sq = s_pre + R * A;        // [R][A]   squash correction terms
+  const int tid = threadIdx.x;
+  const int total = 3 * B, g0 = blockIdx.x * R;
+  const bool vec = (h2 & 3) == 0;
+  {
+    // stage the R rows of H2 (a CTA's rows may straddle two passes)
+    const int q = vec ? h2 >> 2 : h2;
+    for (int r = tid / q, c = tid - (tid / q) * q; r < R; ) {
+      const int g = g0 + r;
+      if (g < total) {
+        const int pass = g / B, row = g - pass * B;
+        const float* src = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
+        if (vec) *reinterpret_cast<float4*>(xs + r * ldx + 4 * c) = *reinterpret_cast<const float4*>(src + 4 * c);
+        else xs[r * ldx + c] = src[c];
+      } else if (vec) {
+        *reinterpret_cast<float4*>(xs + r * ldx + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        xs[r * ldx + c] = 0.0f;
+      }
+      c += HEADS_THREADS;
+      while (c >= q) { c -= q; ++r; }
+    }
+  }
+  __syncthreads();
+  const int groups = R / RB;                       // row groups of RB rows; thread = (row group, output j)
+  const int rg = tid / n, j = tid - rg * n;
+  if (rg < groups) {
+    // all RB rows of a thread use the same weight column: groups start at multiples of RB and the host picks
+    // RB = 4 only when B % 4 == 0, so a group never straddles the main / target boundary at row 2B
+    const int g_first = g0 + rg * RB;
+    const int pass_w = min(g_first, total - 1) / B;
+    const float* W = (pass_w == 2 ? Whead_t : Whead) + j;
+    const float* x = xs + rg * RB * ldx;
+    float acc[RB][2];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) acc[rb][0] = acc[rb][1] = 0.0f;
+    int k = 0;
+    if (vec) {
+      for (; k + 8 <= h2; k += 8) {
+        float wv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wv[i] = W[(size_t)(k + i) * ldh];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          const float4 xa4 = *reinterpret_cast<const float4*>(x + rb * ldx + k);
+          const float4 xb4 = *reinterpret_cast<const float4*>(x + rb * ldx + k + 4);
+          acc[rb][0] = fmaf(xa4.w, wv[3], fmaf(xa4.z, wv[2], fmaf(xa4.y, wv[1], fmaf(xa4.x, wv[0], acc[rb][0]))));
+          acc[rb][1] = fmaf(xb4.w, wv[7], fmaf(xb4.z, wv[6], fmaf(xb4.y, wv[5], fmaf(xb4.x, wv[4], acc[rb][1]))));
+        }
+      }
+    }
+    for (; k < h2; ++k) {
+      const float wk = W[(size_t)k * ldh];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) acc[rb][0] = fmaf(x[rb * ldx + k], wk, acc[rb][0]);
+    }
+    const float bias = W[(size_t)h2 * ldh];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      const int r = rg * RB + rb, g = g0 + r;
+      if (g < total) {
+        const float v = (acc[rb][0] + acc[rb][1]) + bias;
+        s_out[r * n + j] = v;
+        if (g < B) HD[(size_t)g * n + j] = v;      // pass 0
+      }
+    }
+  }
+  __syncthreads();
+  // element-wise part: one thread per (row, action)
+  for (int i = tid; i < R * A; i += HEADS_THREADS) {
+    const int r = i / A, ja = i - r * A, g = g0 + r;
+    if (g >= total) continue;
+    const int pass = g / B, row = g - pass * B;
+    const float eps = NOISE[((size_t)pass * B + row) * A + ja];
+    const PolEl e = policy_elem(s_out[r * n + ja], s_out[r * n + A + ja], eps);
+    s_pre[i] = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
+    s_sq[i] = logf(__fadd_rn(e.clipped, 1e-6f));
+    const float act = __fmul_rn(e.pi, act_scale);
+    if (pass == 0) {
+      A1[(size_t)row * A + ja] = act;
+      if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + ja, act);
+    } else if (pass == 2) {
+      A3[(size_t)row * A + ja] = act;
+      if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + ja, act);
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < R; r += HEADS_THREADS) {
+    const int g = g0 + r;
+    if (g >= 2 * B) continue;                       // pass 2 (target policy) needs no log-likelihood
+    // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
+    float gauss = 0.0f, squash = 0.0f;
+    for (int t = 0; t < A; ++t) {
+      gauss = __fadd_rn(gauss, s_pre[r * A + t]);
+      squash = __fadd_rn(squash, s_sq[r * A + t]);
+    }
+    (g < B ? LOGP1 : LOGP2)[g < B ? g : g - B] = __fsub_rn(gauss, squash);
+  }
+}
+
+// 128-bit helpers for the warp-per-row kernels below: lane handles 4 consecutive features per step of 128
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// Narrow policy heads (2A <= 16): one WARP per row, lanes split the h2 features four at a time, the head block
+// rows (ldh = 4 * Q floats, zero padded) are read as Q 128-bit loads per feature; then 2A warp reductions.
+template <int Q>
+__device__ __forceinline__ void heads_row_dots(const float* __restrict__ x, int K, const float* __restrict__ W, int n, float* sout,
+                                               int lane) {
+  constexpr int LDH = 4 * Q;
+  float acc[LDH];
+#pragma unroll
+  for (int j = 0; j < LDH; ++j) acc[j] = 0.0f;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 x4 = ld4(x + k);
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+    float4 w[4][Q];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) w[i][q] = ld4(W + (size_t)(k + i) * LDH + 4 * q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        acc[4 * q] = fmaf(xv[i], w[i][q].x, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(xv[i], w[i][q].y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xv[i], w[i][q].z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xv[i], w[i][q].w, acc[4 * q + 3]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < LDH; ++j) {
+    const float v = warp_sum(acc[j]);
+    if (j < n && lane == 0) sout[j] = v + W[(size_t)K * LDH + j];
+  }
+  __syncwarp();
+}
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_rows(
+    int B, int A, int h2, int ldh, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
+    const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D) {
+  __shared__ float s_out[ROW_WARPS][16];
+  pdl_trigger();
+  pdl_wait();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = vb * ROW_WARPS + w;
+  const int g = blockIdx.x * ROW_WARPS + w;
   if (g >= 3 * B) return;
   const int pass = g / B, row = g % B;
   const float* x = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
-  warp_dots(x, h2, pass == 2 ? Whead_t : Whead, 2 * A, 2 * A, false, true, s_out[w], lane);
+  const float* W = pass == 2 ? Whead_t : Whead;
+  switch (ldh) {
+    case 4: heads_row_dots<1>(x, h2, W, 2 * A, s_out[w], lane); break;
+    case 8: heads_row_dots<2>(x, h2, W, 2 * A, s_out[w], lane); break;
+    case 12: heads_row_dots<3>(x, h2, W, 2 * A, s_out[w], lane); break;
+    default: heads_row_dots<4>(x, h2, W, 2 * A, s_out[w], lane); break;
+  }
   const float* eps = NOISE + ((size_t)pass * B + row) * A;
-  float gauss = 0.0f, squash = 0.0f;
-  for (int j0 = 0; j0 < A; j0 += 32) {
-    const int j = j0 + lane;
-    float pre = 0.0f, sq = 0.0f;
-    if (j < A) {
-      const PolEl e = policy_elem(s_out[w][j], s_out[w][A + j], eps[j]);
-      pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
-      sq = logf(__fadd_rn(e.clipped, 1e-6f));
-      const float act = __fmul_rn(e.pi, act_scale);
-      if (pass == 0) {
-        A1[(size_t)row * A + j] = act;
-        if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + j, act);
-      } else if (pass == 2) {
-        A3[(size_t)row * A + j] = act;
-        if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + j, act);
-      }
-    }
-    // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
-    const int cnt = min(32, A - j0);
-    for (int t = 0; t < cnt; ++t) {
-      gauss = __fadd_rn(gauss, __shfl_sync(0xffffffffu, pre, t));
-      squash = __fadd_rn(squash, __shfl_sync(0xffffffffu, sq, t));
+  float pre = 0.0f, sq = 0.0f;
+  if (lane < A) {
+    const PolEl e = policy_elem(s_out[w][lane], s_out[w][A + lane], eps[lane]);
+    pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
+    sq = logf(__fadd_rn(e.clipped, 1e-6f));
+    const float act = __fmul_rn(e.pi, act_scale);
+    if (pass == 0) {
+      A1[(size_t)row * A + lane] = act;
+      if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + lane, act);
+    } else if (pass == 2) {
+      A3[(size_t)row * A + lane] = act;
+      if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + lane, act);
     }
   }
+  // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
+  float gauss = 0.0f, squash = 0.0f;
+  for (int t = 0; t < A; ++t) {
+    gauss = __fadd_rn(gauss, __shfl_sync(0xffffffffu, pre, t));
+    squash = __fadd_rn(squash, __shfl_sync(0xffffffffu, sq, t));
+  }
   if (pass == 0) {
-    for (int j = lane; j < 2 * A; j += 32) HD[(size_t)row * 2 * A + j] = s_out[w][j];
+    if (lane < 2 * A) HD[(size_t)row * 2 * A + lane] = s_out[w][lane];
     if (lane == 0) LOGP1[row] = __fsub_rn(gauss, squash);
   } else if (pass == 1 && lane == 0) {
     LOGP2[row] = __fsub_rn(gauss, squash);
   }
 }
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_fwd(
-    int B, int A, int h2, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
-    const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
-    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D) {
-  pdl_trigger();
-  pdl_wait();
-  d_policy_heads_fwd(blockIdx.x, B, A, h2, act_scale, H2a, H2b, H2c, Whead, Whead_t, NOISE, HD, A1, A3, LOGP1, LOGP2, xa, D);
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc))));
+}
+__device__ __forceinline__ void st_split4(float* hi_plane, long long plane, size_t idx, const float4& v) {
+  float4 hi, lo;
+  tc::split_tf32(v.x, hi.x, lo.x); tc::split_tf32(v.y, hi.y, lo.y); tc::split_tf32(v.z, hi.z, lo.z); tc::split_tf32(v.w, hi.w, lo.w);
+  *reinterpret_cast<float4*>(hi_plane + idx) = hi;
+  *reinterpret_cast<float4*>(hi_plane + plane + idx) = lo;
 }
 
 // Q heads of all five Q passes, Bellman target, the three losses (actor_learner.py:58-69), the
 // output-layer gradients dq, and dZ2 = dq (x) w3^T masked by relu'(H2) for the three differentiated
 // passes.  Loss sums: per-CTA partials in double, combined in CTA order by the last CTA to finish
-// (deterministic).
-__device__ __forceinline__ void d_qheads_losses(
-    int vb, int vgrid, StepState* st, int B, int h2, float gamma, const float* __restrict__ H2d, const float* __restrict__ H2e,
+// (deterministic).  One warp per row; when h2 % 4 == 0 every access is a 128-bit load / store.
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
+    StepState* st, int B, int h2, float gamma, const float* __restrict__ H2d, const float* __restrict__ H2e,
     const float* __restrict__ H2f, const float* __restrict__ H2g, const float* __restrict__ H2h,
     const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
     const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
     const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
-    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz = 0, long long zlo = 0) {
+    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz, long long zlo) {
   __shared__ double s_part[ROW_WARPS][4];
-  if (ldz == 0) ldz = h2;   // zlo != 0: hi/lo planes for the tensor-core GEMMs (lo plane zlo floats after hi)
   __shared__ bool s_last;
+  pdl_trigger();
+  pdl_wait();
+  if (ldz == 0) ldz = h2;   // zlo != 0: hi/lo planes for the tensor-core GEMMs (lo plane zlo floats after hi)
+  const int vb = blockIdx.x, vgrid = gridDim.x;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = vb * ROW_WARPS + w;
   const float alpha = st->alpha_cur;
   const StepDyn& d = st->dyn;
+  const bool vec = (h2 & 3) == 0 && (ldz & 3) == 0;
   double t_pi = 0.0, t_q1 = 0.0, t_q2 = 0.0, t_lp = 0.0;
   if (row < B) {
     const float *hd = H2d + (size_t)row * h2, *he = H2e + (size_t)row * h2, *hf = H2f + (size_t)row * h2,
                 *hg = H2g + (size_t)row * h2, *hh = H2h + (size_t)row * h2;
     float qd = 0.f, qe = 0.f, qf = 0.f, qg = 0.f, qh = 0.f;
-    for (int k = lane; k < h2; k += 32) {
-      const float w1 = W3q1[k], w2 = W3q2[k];
-      qd = fmaf(hd[k], w1, qd);
-      qe = fmaf(he[k], w2, qe);
-      qf = fmaf(hf[k], w1, qf);
-      qg = fmaf(hg[k], W3q1t[k], qg);
-      qh = fmaf(hh[k], W3q2t[k], qh);
+    if (vec) {
+      for (int k = lane * 4; k < h2; k += 128) {
+        const float4 w1 = ld4(W3q1 + k), w2 = ld4(W3q2 + k), w1t = ld4(W3q1t + k), w2t = ld4(W3q2t + k);
+        qd = dot4(ld4(hd + k), w1, qd);
+        qe = dot4(ld4(he + k), w2, qe);
+        qf = dot4(ld4(hf + k), w1, qf);
+        qg = dot4(ld4(hg + k), w1t, qg);
+        qh = dot4(ld4(hh + k), w2t, qh);
+      }
+    } else {
+      for (int k = lane; k < h2; k += 32) {
+        const float w1 = W3q1[k], w2 = W3q2[k];
+        qd = fmaf(hd[k], w1, qd);
+        qe = fmaf(he[k], w2, qe);
+        qf = fmaf(hf[k], w1, qf);
+        qg = fmaf(hg[k], W3q1t[k], qg);
+        qh = fmaf(hh[k], W3q2t[k], qh);
+      }
     }
     qd = warp_sum(qd) + W3q1[h2];
     qe = warp_sum(qe) + W3q2[h2];
@@ -305,12 +477,31 @@ __device__ __forceinline__ void d_qheads_losses(
     const float q_backup = __fadd_rn(R[row], __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.0f, DN[row])), v_backup));
     const float e1 = __fsub_rn(q_backup, qd), e2 = __fsub_rn(q_backup, qe);
     const float dqd = -e1 * invB, dqe = -e2 * invB, dqf = -invB;
-    for (int k = lane; k < h2; k += 32) {
-      const float w1 = W3q1[k], w2 = W3q2[k];
-      const float zd = hd[k] > 0.0f ? dqd * w1 : 0.0f, ze = he[k] > 0.0f ? dqe * w2 : 0.0f, zf = hf[k] > 0.0f ? dqf * w1 : 0.0f;
-      const size_t o = (size_t)row * ldz + k;
-      if (zlo) { put_split(dZ2d, zlo, o, zd); put_split(dZ2e, zlo, o, ze); put_split(dZ2f, zlo, o, zf); }
-      else { dZ2d[o] = zd; dZ2e[o] = ze; dZ2f[o] = zf; }
+    if (vec) {
+      for (int k = lane * 4; k < h2; k += 128) {
+        const float4 w1 = ld4(W3q1 + k), w2 = ld4(W3q2 + k), xd = ld4(hd + k), xe = ld4(he + k), xf = ld4(hf + k);
+        const float4 zd = make_float4(xd.x > 0.f ? dqd * w1.x : 0.f, xd.y > 0.f ? dqd * w1.y : 0.f, xd.z > 0.f ? dqd * w1.z : 0.f,
+                                      xd.w > 0.f ? dqd * w1.w : 0.f);
+        const float4 ze = make_float4(xe.x > 0.f ? dqe * w2.x : 0.f, xe.y > 0.f ? dqe * w2.y : 0.f, xe.z > 0.f ? dqe * w2.z : 0.f,
+                                      xe.w > 0.f ? dqe * w2.w : 0.f);
+        const float4 zf = make_float4(xf.x > 0.f ? dqf * w1.x : 0.f, xf.y > 0.f ? dqf * w1.y : 0.f, xf.z > 0.f ? dqf * w1.z : 0.f,
+                                      xf.w > 0.f ? dqf * w1.w : 0.f);
+        const size_t o = (size_t)row * ldz + k;
+        if (zlo) { st_split4(dZ2d, zlo, o, zd); st_split4(dZ2e, zlo, o, ze); st_split4(dZ2f, zlo, o, zf); }
+        else {
+          *reinterpret_cast<float4*>(dZ2d + o) = zd;
+          *reinterpret_cast<float4*>(dZ2e + o) = ze;
+          *reinterpret_cast<float4*>(dZ2f + o) = zf;
+        }
+      }
+    } else {
+      for (int k = lane; k < h2; k += 32) {
+        const float w1 = W3q1[k], w2 = W3q2[k];
+        const float zd = hd[k] > 0.0f ? dqd * w1 : 0.0f, ze = he[k] > 0.0f ? dqe * w2 : 0.0f, zf = hf[k] > 0.0f ? dqf * w1 : 0.0f;
+        const size_t o = (size_t)row * ldz + k;
+        if (zlo) { put_split(dZ2d, zlo, o, zd); put_split(dZ2e, zlo, o, ze); put_split(dZ2f, zlo, o, zf); }
+        else { dZ2d[o] = zd; dZ2e[o] = ze; dZ2f[o] = zf; }
+      }
     }
     if (lane == 0) {
       dQd[row] = dqd; dQe[row] = dqe;
@@ -343,41 +534,56 @@ __device__ __forceinline__ void d_qheads_losses(
     else SCAL[4] = v;   // mean logp1 (entropy-alpha gradient; all-reduced across ranks by the host)
     if (threadIdx.x == 0) { SCAL[3] = alpha; if (d.out_scalars) d.out_scalars[3] = alpha; *ticket = 0u; }
   }
-  __syncthreads();   // shared scratch is reused by the next virtual block
-}
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
-    StepState* st, int B, int h2, float gamma, const float* __restrict__ H2d, const float* __restrict__ H2e,
-    const float* __restrict__ H2f, const float* __restrict__ H2g, const float* __restrict__ H2h,
-    const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
-    const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
-    const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
-    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz, long long zlo) {
-  pdl_trigger();
-  pdl_wait();
-  d_qheads_losses(blockIdx.x, gridDim.x, st, B, h2, gamma, H2d, H2e, H2f, H2g, H2h, W3q1, W3q2, W3q1t, W3q2t, R, DN, LOGP1, LOGP2,
-                  dQd, dQe, dZ2d, dZ2e, dZ2f, partials, ticket, SCAL, ldz, zlo);
 }
 
 // gradient of pi_loss = mean(alpha*logp1 - q1_pi) wrt the policy head pre-activations (chain rule of
 // the reference op graph), fused with its two skinny neighbours:
 //   dA1  = dZ1(Q1(x,pi)) . W1q1[D:D+A, :]^T                 (input gradient of Q1 wrt the action)
 //   dZ2a = [dmu | dls] . Whead[0:h2, :]^T  masked by relu'(H2a)
-__device__ __forceinline__ void d_policy_bwd_rows(
-    int vb, const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
+// One warp per row; 128-bit loads when the widths allow (h1 % 4 == 0; head block rows are ldh = 4-float padded).
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
+    const StepState* __restrict__ st, int B, int A, int h1, int h2, int ldh, float act_scale, const float* __restrict__ HDa,
     const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
-    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a, int ld1 = 0, long long lo1 = 0,
-    int ldz = 0, long long zlo = 0) {
-  __shared__ float s_da[ROW_WARPS][MAX_HEAD];
-  __shared__ float s_dhd[ROW_WARPS][MAX_HEAD];
+    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a, int ld1, long long lo1, int ldz,
+    long long zlo) {
+  __shared__ __align__(16) float s_da[ROW_WARPS][MAX_HEAD];
+  __shared__ __align__(16) float s_dhd[ROW_WARPS][MAX_HEAD + 4];
+  pdl_trigger();
+  pdl_wait();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = vb * ROW_WARPS + w;
+  const int row = blockIdx.x * ROW_WARPS + w;
   if (row >= B) return;
   if (ld1 == 0) ld1 = h1;
   if (ldz == 0) ldz = h2;
-  warp_dots(dZ1f + (size_t)row * ld1, h1, W1q1_act, h1, A, true, false, s_da[w], lane, lo1 ? dZ1f + lo1 + (size_t)row * ld1 : nullptr);
+  const float* zhi = dZ1f + (size_t)row * ld1;
+  const float* zlo1 = lo1 ? zhi + lo1 : nullptr;
+  if ((h1 & 3) == 0 && (ld1 & 3) == 0) {
+    for (int j0 = 0; j0 < A; j0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0f;
+      for (int k = lane * 4; k < h1; k += 128) {
+        float4 x = ld4(zhi + k);
+        if (zlo1) { const float4 l = ld4(zlo1 + k); x.x += l.x; x.y += l.y; x.z += l.z; x.w += l.w; }   // hi + lo is exact
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          if (j0 + jj < A) acc[jj] = dot4(x, ld4(W1q1_act + (size_t)(j0 + jj) * h1 + k), acc[jj]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float v = warp_sum(acc[jj]);
+        if (j0 + jj < A && lane == 0) s_da[w][j0 + jj] = v;
+      }
+    }
+    __syncwarp();
+  } else {
+    warp_dots(zhi, h1, W1q1_act, h1, A, true, false, s_da[w], lane, zlo1);
+  }
   const float dlogp = st->alpha_cur / (float)B;
   const float* hd = HDa + (size_t)row * 2 * A;
   const float* eps = NOISE + (size_t)row * A;
+  for (int j = lane; j < ldh; j += 32) s_dhd[w][j] = 0.0f;   // padding columns of the head block multiply zeros
+  __syncwarp();
   for (int j = lane; j < A; j += 32) {
     const float mu = hd[j];
     const PolEl e = policy_elem(mu, hd[A + j], eps[j]);
@@ -397,24 +603,17 @@ __device__ __forceinline__ void d_policy_bwd_rows(
     dHD[(size_t)row * 2 * A + A + j] = dls;
   }
   __syncwarp();
-  const int n2 = 2 * A;
   for (int n = lane; n < h2; n += 32) {
-    float acc = 0.0f;
-    const float* wr = Whead + (size_t)n * n2;
-    for (int j = 0; j < n2; ++j) acc = fmaf(s_dhd[w][j], wr[j], acc);
-    const float z = H2a[(size_t)row * h2 + n] > 0.0f ? acc : 0.0f;
+    const float* wr = Whead + (size_t)n * ldh;
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int j = 0; j < ldh; j += 8) {               // ldh is a multiple of 4; rows are 16-byte aligned
+      a0 = dot4(ld4(s_dhd[w] + j), ld4(wr + j), a0);
+      if (j + 4 < ldh) a1 = dot4(ld4(s_dhd[w] + j + 4), ld4(wr + j + 4), a1);
+    }
+    const float z = H2a[(size_t)row * h2 + n] > 0.0f ? a0 + a1 : 0.0f;
     if (zlo) put_split(dZ2a, zlo, (size_t)row * ldz + n, z);
     else dZ2a[(size_t)row * ldz + n] = z;
   }
-}
-__global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
-    const StepState* __restrict__ st, int B, int A, int h1, int h2, float act_scale, const float* __restrict__ HDa,
-    const float* __restrict__ NOISE, const float* __restrict__ dZ1f, const float* __restrict__ W1q1_act,
-    const float* __restrict__ Whead, const float* __restrict__ H2a, float* dHD, float* dZ2a, int ld1, long long lo1, int ldz,
-    long long zlo) {
-  pdl_trigger();
-  pdl_wait();
-  d_policy_bwd_rows(blockIdx.x, st, B, A, h1, h2, act_scale, HDa, NOISE, dZ1f, W1q1_act, Whead, H2a, dHD, dZ2a, ld1, lo1, ldz, zlo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,7 +622,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_bwd_rows(
 // per env step in the reference; vectorised rollouts pass n = number of envs).
 // ------------------------------------------------------------------------------------------------
 constexpr int ACT_MAX_H = 512;
-__global__ void __launch_bounds__(128) k_actor_forward(int n, int D, int A, int h1, int h2, float act_scale, int deterministic,
+__global__ void __launch_bounds__(128) k_actor_forward(int n, int D, int A, int h1, int h2, int ldh, float act_scale, int deterministic,
                                                        const float* __restrict__ OBS, const float* __restrict__ W1,
                                                        const float* __restrict__ W2, const float* __restrict__ Whead,
                                                        const float* __restrict__ noise, unsigned long long seed,
@@ -447,7 +646,7 @@ __global__ void __launch_bounds__(128) k_actor_forward(int n, int D, int A, int 
     s_h2[w][j] = fmaxf(acc, 0.0f);
   }
   __syncwarp();
-  warp_dots(s_h2[w], h2, Whead, 2 * A, 2 * A, false, true, s_out[w], lane);
+  warp_dots(s_h2[w], h2, Whead, ldh, 2 * A, false, true, s_out[w], lane);
   for (int j = lane; j < A; j += 32) {
     float eps = 0.0f;
     if (!deterministic) {
@@ -567,9 +766,9 @@ __global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_
 
 // external (TF variable order: kernel, bias per dense layer; mu head then log_std head) <-> internal
 // flat layout.  Internal blocks start on 16-byte boundaries (vector loads in the GEMM operand fetch)
-// and the policy head block is fused: internal [h2+1, 2A] = [Wmu|Wls ; bmu|bls].
+// and the policy head block is fused: internal [h2+1, ldh] = [Wmu|Wls|0.. ; bmu|bls|0..], ldh = 2A rounded up to 4.
 struct LayoutMap {
-  int nblk, head_idx, h2, A;
+  int nblk, head_idx, h2, A, ldh;   // ldh: row pitch of the fused head block (2A rounded up to 4 floats)
   long long ext_off[9], int_off[9], size[9];
 };
 __global__ void __launch_bounds__(256) k_convert_layout(LayoutMap mp, int64_t Pext, int to_internal,
@@ -584,7 +783,7 @@ __global__ void __launch_bounds__(256) k_convert_layout(LayoutMap mp, int64_t Pe
       const int which = e >= half;
       if (which) e -= half;
       const int64_t r = e / mp.A, c = e % mp.A;  // r == h2 is the bias row
-      e = r * 2 * mp.A + which * mp.A + c;
+      e = r * mp.ldh + which * mp.A + c;
     }
     const int64_t j = mp.int_off[b] + e;
     if (to_internal) { const float v = src[i]; dst[j] = v; if (dst2) dst2[j] = v; }
@@ -631,103 +830,6 @@ __global__ void __launch_bounds__(256) k_colsum(const __grid_constant__ ColsumGr
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Persistent whole-step kernel.  The step is 12 dependent phases of 5..45 us; as separate launches
-// each pays launch latency, a cold ramp and a tail where most SMs idle.  Here ONE cooperative grid
-// (a multiple of the SM count, all CTAs resident) walks the phases with grid-wide barriers in
-// between: tiles of a GEMM phase and row blocks of a row-wise phase are dealt round-robin to the CTAs.
-// ------------------------------------------------------------------------------------------------
-struct MegaArgs {
-  StepState* st;
-  const GemmGroup* stages;   // [ST_COUNT] in device memory
-  int tiles[8];
-  int mode;                  // 0: full step (ends with Adam + polyak), 1: gradients only (ends with the split-K reduce)
-  int B, D, A, h1, h2, S;
-  float act_scale, gamma, lr, polyak;
-  int64_t P, P_pi;
-  float *X, *X2, *ACT, *R, *DN, *NOISE;
-  float* H2[8];
-  float *HD0, *A1, *A3, *LOGP1, *LOGP2;
-  float *dQ0, *dQ1, *dZ2_0, *dZ2_1, *dZ2_2, *dZ1_2, *dHD, *dZ2a;
-  double* partials;
-  unsigned int* ticket;
-  unsigned int* barrier;     // zeroed by k_set_params
-  float *SCAL, *W, *Wt, *Mo, *Vo, *Gp, *G;
-  int64_t o_pih, o_q1_0, o_q1_2, o_q2_2;
-};
-
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target);
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ void mega_gemm_phase(const GemmGroup* __restrict__ grp, int ntiles, float* smem_raw) {
-  __shared__ GemmGroup s_grp;     // the phase's descriptors, fetched once per CTA with coalesced loads
-  if ((int)blockIdx.x >= ntiles) return;
-  {
-    const int* src = reinterpret_cast<const int*>(grp);
-    int* dst = reinterpret_cast<int*>(&s_grp);
-    for (int i = threadIdx.x; i < (int)(sizeof(GemmGroup) / 4); i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int pi = 0;
-    const int np = s_grp.nprob;
-    while (pi + 1 < np && tile >= s_grp.p[pi + 1].tile_begin) ++pi;
-    const GemmProb P = s_grp.p[pi];
-    if (P.cfg == 0) gemm_tile<64, 64, 4, 4>(P, smem_raw, tile - P.tile_begin);
-    else gemm_tile<128, 16, 4, 2>(P, smem_raw, tile - P.tile_begin);
-  }
-}
-
-__global__ void __launch_bounds__(256, 2) k_sac_mega(const __grid_constant__ MegaArgs a) {
-  __shared__ __align__(16) float smem_raw[GEMM_SMEM_FLOATS];
-  const unsigned int G = gridDim.x;
-  unsigned int epoch = 0;
-  const int B = a.B, A = a.A, h1 = a.h1, h2 = a.h2;
-  const int nrow_blocks = (B + ROW_WARPS - 1) / ROW_WARPS;
-
-  d_prologue(blockIdx.x, G, a.st, B, a.D, A, a.X, a.X2, a.ACT, a.R, a.DN, a.NOISE);
-  grid_barrier(a.barrier, ++epoch * G);
-  mega_gemm_phase(a.stages + 0, a.tiles[0], smem_raw);                      // L1
-  grid_barrier(a.barrier, ++epoch * G);
-  mega_gemm_phase(a.stages + 1, a.tiles[1], smem_raw);                      // L2
-  grid_barrier(a.barrier, ++epoch * G);
-  for (int vb = blockIdx.x; vb < (3 * B + ROW_WARPS - 1) / ROW_WARPS; vb += G)
-    d_policy_heads_fwd(vb, B, A, h2, a.act_scale, a.H2[0], a.H2[1], a.H2[2], a.W + a.o_pih, a.Wt + a.o_pih, a.NOISE, a.HD0,
-                       a.A1, a.A3, a.LOGP1, a.LOGP2);
-  grid_barrier(a.barrier, ++epoch * G);
-  mega_gemm_phase(a.stages + 2, a.tiles[2], smem_raw);                      // QL1
-  grid_barrier(a.barrier, ++epoch * G);
-  mega_gemm_phase(a.stages + 3, a.tiles[3], smem_raw);                      // QL2
-  grid_barrier(a.barrier, ++epoch * G);
-  for (int vb = blockIdx.x; vb < nrow_blocks; vb += G)
-    d_qheads_losses(vb, nrow_blocks, a.st, B, h2, a.gamma, a.H2[3], a.H2[4], a.H2[5], a.H2[6], a.H2[7], a.W + a.o_q1_2,
-                    a.W + a.o_q2_2, a.Wt + a.o_q1_2, a.Wt + a.o_q2_2, a.R, a.DN, a.LOGP1, a.LOGP2, a.dQ0, a.dQ1, a.dZ2_0,
-                    a.dZ2_1, a.dZ2_2, a.partials, a.ticket, a.SCAL);
-  grid_barrier(a.barrier, ++epoch * G);
-  mega_gemm_phase(a.stages + 4, a.tiles[4], smem_raw);                      // BQ
-  grid_barrier(a.barrier, ++epoch * G);
-  for (int vb = blockIdx.x; vb < nrow_blocks; vb += G)
-    d_policy_bwd_rows(vb, a.st, B, A, h1, h2, a.act_scale, a.HD0, a.NOISE, a.dZ1_2, a.W + a.o_q1_0 + (int64_t)a.D * h1,
-                      a.W + a.o_pih, a.H2[0], a.dHD, a.dZ2a);
-  grid_barrier(a.barrier, ++epoch * G);
-  mega_gemm_phase(a.stages + 5, a.tiles[5], smem_raw);                      // BP
-  grid_barrier(a.barrier, ++epoch * G);
-  mega_gemm_phase(a.stages + 6, a.tiles[6], smem_raw);                      // BP3
-  grid_barrier(a.barrier, ++epoch * G);
-  if (a.mode == 0) d_adam_polyak(blockIdx.x, G, a.st, a.P, a.P_pi, a.S, a.Gp, a.lr, a.polyak, -(float)A, a.SCAL, a.W, a.Wt, a.Mo, a.Vo);
-  else d_grad_reduce(blockIdx.x, G, a.P, a.S, a.Gp, a.G);
-}
-
 }  // namespace ddrl
 
 // =================================================================================================
@@ -753,8 +855,6 @@ struct Plan {
   int64_t kernels[3] = {0, 0, 0};  // kernels inside each captured graph (for the launch counter)
   ColsumGroup colsum[8] = {};      // tensor-core mode: bias-gradient column sums per stage (side stream)
   int colsum_chunks[8] = {};
-  GemmGroup* d_stages = nullptr;   // [ST_COUNT] descriptors for the persistent step kernel
-  int mega_grid = 0;
 };
 
 }  // namespace
@@ -780,7 +880,7 @@ struct ddrl_sac {
   float *dQ[3] = {}, *dZ2[3] = {}, *dZ1[3] = {}, *dA1 = nullptr, *dHD = nullptr, *dZ2a = nullptr, *dZ1a = nullptr;
   // tensor-core mode: H1 / dZ1 / dZ2 / dZ2a / dZ1a are hi/lo plane pairs [2][maxB][ld], ld rounded up to 4 floats
   // (16-byte TMA strides); lo* = floats from the hi plane to the lo plane (0 in FFMA mode, where ld = width)
-  int ld1 = 0, ld2 = 0, ldx = 0;
+  int ld1 = 0, ld2 = 0, ldx = 0, ldh = 0;   // ldh: head block row pitch
   long long lo1 = 0, lo2 = 0, lox = 0;
   float* XA[3] = {};                    // [x|a], [x|a1], [x2|a3] split planes
   float *Wsp = nullptr, *Wtsp = nullptr;  // split planes of the main / target weight blocks (SplitMap)
@@ -789,8 +889,6 @@ struct ddrl_sac {
   std::map<int, Plan> plans;
   bool use_graph = true;
   bool use_tc = true;    // tcgen05 3xTF32 GEMMs from pre-split planes (default); DDRL_GEMM=ffma: fp32 FFMA tiles
-  bool use_mega = false; // DDRL_MEGA=1: one persistent cooperative kernel per step instead of one launch per phase in a CUDA graph
-                         // (measured slower on B200 at the named shapes: 258 vs 203 us at C2 — kept for experiments)
   cudaStream_t side_stream = nullptr; // tensor-core mode: skinny / bias gradients run beside the main chain (forked with events)
   cudaEvent_t ev[4] = {};
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy
@@ -887,7 +985,6 @@ int launch_group(const Group& g, cudaStream_t s) {
 enum { ST_L1 = 0, ST_L2 /*-> k_policy_heads_fwd*/, ST_QL1, ST_QL2 /*-> k_qheads_losses*/, ST_BQ
        /*-> k_policy_bwd_rows*/, ST_BP, ST_BP3, ST_COUNT };
 
-constexpr int MODE_GRADS_ = 1;
 void add(std::vector<Group>& stage, GemmProb p) {
   p.cfg = p.N <= 16 ? 1 : 0;
   if (stage.empty()) stage.emplace_back();
@@ -1020,7 +1117,7 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
     }
   }
   // ---- policy backward (pass a); dHD and dZ2a come from k_policy_bwd_rows
-  add(pl.stages[ST_BP], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, 2 * A, h2 + 1, 2 * A, B)));
+  add(pl.stages[ST_BP], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, h->ldh, h2 + 1, 2 * A, B)));
   add(pl.stages[ST_BP], mk(seg(h->dZ2a, h2, h2), none(), 0, 0, W + h->o_pi2, h2, 1, h->dZ1a, h1, B, h1, h2, EPI_MASK, h->H1[a], h1));
   add(pl.stages[ST_BP], wg(mk(seg(h->H1[a], h1, h1), none(), 1, 1, h->dZ2a, h2, 0, Gp + h->o_pi2, h2, h1 + 1, h2, B)));
   add(pl.stages[ST_BP3], wg(mk(seg(h->X, D, D), none(), 1, 1, h->dZ1a, h1, 0, Gp + h->o_pi1, h1, D + 1, h1, B)));
@@ -1029,19 +1126,6 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
       int rc = finalize_group(g2);
       if (rc) return rc;
     }
-  if (h->use_mega) {
-    std::vector<GemmGroup> host(ST_COUNT);
-    for (int i = 0; i < ST_COUNT; ++i) host[i] = pl.stages[i].empty() ? GemmGroup{} : pl.stages[i][0].grp;
-    cudaError_t e = cudaMalloc(&pl.d_stages, sizeof(GemmGroup) * ST_COUNT);
-    if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(stages) failed: %s", cudaGetErrorString(e));
-    e = cudaMemcpy(pl.d_stages, host.data(), sizeof(GemmGroup) * ST_COUNT, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaMemcpy(stages) failed: %s", cudaGetErrorString(e));
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sac_mega, 256, 0);
-    if (e != cudaSuccess || per_sm < 1) return fail(DDRL_ECUDA, "occupancy query for the step kernel failed");
-    if (per_sm > 2) per_sm = 2;
-    pl.mega_grid = per_sm * h->sms;
-  }
   return 0;
 }
 
@@ -1123,7 +1207,7 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
     }
   }
   // ---- policy backward (pass a); dHD and dZ2a come from k_policy_bwd_rows
-  add(pl.stages[ST_BP], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, 2 * A, h2 + 1, 2 * A, B)));
+  add(pl.stages[ST_BP], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, h->ldh, h2 + 1, 2 * A, B)));
   dgrad(ST_BP, h->dZ2a, PI2, h->dZ1a, a);
   wgrad(ST_BP, h1v(a), dz2v(h->dZ2a), PI2);
   wgrad(ST_BP3, xa(0, D), dz1v(h->dZ1a), PI1);
@@ -1131,29 +1215,6 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
   for (auto& st : pl.stages)
     for (auto& g2 : st)
       if ((rc = finalize_group(g2))) return rc;
-  return 0;
-}
-
-int launch_mega(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
-  MegaArgs a{};
-  a.st = h->st; a.stages = pl.d_stages;
-  for (int i = 0; i < ST_COUNT; ++i) a.tiles[i] = pl.stages[i].empty() ? 0 : pl.stages[i][0].tiles;
-  a.mode = mode == MODE_GRADS_ ? 1 : 0;
-  a.B = pl.B; a.D = h->D; a.A = h->A; a.h1 = h->h1; a.h2 = h->h2; a.S = pl.S;
-  a.act_scale = h->act_scale; a.gamma = h->gamma; a.lr = h->lr; a.polyak = h->polyak;
-  a.P = h->P; a.P_pi = h->P_pi;
-  a.X = h->X; a.X2 = h->X2; a.ACT = h->ACT; a.R = h->R; a.DN = h->DN; a.NOISE = h->NOISE;
-  for (int i = 0; i < 8; ++i) a.H2[i] = h->H2[i];
-  a.HD0 = h->HD[0]; a.A1 = h->A1; a.A3 = h->A3; a.LOGP1 = h->LOGP1; a.LOGP2 = h->LOGP2;
-  a.dQ0 = h->dQ[0]; a.dQ1 = h->dQ[1]; a.dZ2_0 = h->dZ2[0]; a.dZ2_1 = h->dZ2[1]; a.dZ2_2 = h->dZ2[2]; a.dZ1_2 = h->dZ1[2];
-  a.dHD = h->dHD; a.dZ2a = h->dZ2a;
-  a.partials = h->partials; a.ticket = h->ticket;
-  a.barrier = &h->st->mega_barrier;
-  a.SCAL = h->SCAL; a.W = h->W; a.Wt = h->Wt; a.Mo = h->Mo; a.Vo = h->Vo; a.Gp = h->Gp; a.G = h->G;
-  a.o_pih = h->o_pih; a.o_q1_0 = h->o_q1[0]; a.o_q1_2 = h->o_q1[2]; a.o_q2_2 = h->o_q2[2];
-  void* args[] = {&a};
-  DDRL_CUDA(cudaLaunchCooperativeKernel((const void*)k_sac_mega, dim3(pl.mega_grid), dim3(256), args, 0, s));
-  DDRL_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1192,8 +1253,24 @@ int launch_prologue(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 }
 int launch_heads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   const int B = pl.B, D = h->D, A = h->A, h2 = h->h2;
-  DDRL_CUDA(launch_pdl(k_policy_heads_fwd, dim3((3 * B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
-      B, A, h2, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0], h->A1,
+  if (2 * A <= 16 && (h2 & 3) == 0) {     // narrow heads: warp per row
+    DDRL_CUDA(launch_pdl(k_policy_heads_rows, dim3((3 * B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
+        B, A, h2, h->ldh, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0],
+        h->A1, h->A3, h->LOGP1, h->LOGP2, xa_out(h), D));
+    DDRL_LAUNCH_CHECK();
+    return 0;
+  }
+  const int groups = std::min(32, HEADS_THREADS / (2 * A));    // row groups per CTA (2A <= 64 -> >= 4)
+  auto smem_of = [&](int r) { return ((size_t)r * ((h2 + 3) / 4 * 4 + 4) + (size_t)r * 4 * A) * sizeof(float); };
+  // 4 rows per thread when there is enough work to still fill the GPU and a 4-row group never straddles the
+  // main / target weight boundary (B % 4 == 0); otherwise one row per thread
+  const bool rb4 = (B % 4 == 0) && (3LL * B / (4 * groups) >= 2LL * h->sms) && smem_of(4 * groups) <= HEADS_SMEM_MAX;
+  int R = rb4 ? 4 * groups : groups;
+  if (!rb4) while (R > 1 && smem_of(R) > HEADS_SMEM_MAX) R /= 2;
+  const size_t smem = smem_of(R);
+  if (smem > HEADS_SMEM_MAX) return fail(DDRL_EINVAL, "hidden size %d is too wide for the policy-head kernel", h2);
+  DDRL_CUDA(launch_pdl(rb4 ? k_policy_heads_fwd<4> : k_policy_heads_fwd<1>, dim3((3 * B + R - 1) / R), dim3(HEADS_THREADS), smem, s,
+      B, A, h2, h->ldh, R, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0], h->A1,
       h->A3, h->LOGP1, h->LOGP2, xa_out(h), D));
   DDRL_LAUNCH_CHECK();
   return 0;
@@ -1210,7 +1287,7 @@ int launch_qheads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 int launch_pbwd(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   const int B = pl.B, D = h->D, A = h->A, h1 = h->h1, h2 = h->h2;
   DDRL_CUDA(launch_pdl(k_policy_bwd_rows, dim3((B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
-      h->st, B, A, h1, h2, h->act_scale, h->HD[0], h->NOISE, h->dZ1[2], h->W + h->o_q1[0] + (int64_t)D * h1,
+      h->st, B, A, h1, h2, h->ldh, h->act_scale, h->HD[0], h->NOISE, h->dZ1[2], h->W + h->o_q1[0] + (int64_t)D * h1,
       h->W + h->o_pih, h->H2[0], h->dHD, h->dZ2a, h->ld1, h->lo1, h->ld2, h->lo2));
   DDRL_LAUNCH_CHECK();
   return 0;
@@ -1287,7 +1364,6 @@ int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
 
 int run_mode(ddrl_sac* h, Plan& pl, int mode, cudaStream_t s) {
   cudaGraphExec_t* slot = mode == MODE_FULL ? &pl.exec_full : mode == MODE_GRADS ? &pl.exec_grads : &pl.exec_apply;
-  if (h->use_mega && mode != MODE_APPLY) return launch_mega(h, pl, mode, s);
   if (!h->use_graph) return enqueue_mode(h, pl, mode, s);
   if (!*slot) {
     cudaGraph_t graph = nullptr;
@@ -1346,8 +1422,11 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   const char* ng = getenv("DDRL_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
   if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] != 'f');   // "ffma": plain fp32 FFMA tiles
-  if (const char* mg = getenv("DDRL_MEGA")) h->use_mega = (mg[0] != '0');
-  if (h->use_mega) h->use_tc = false;   // the persistent kernel runs FFMA tiles only (tcgen05 tiles need 193 KB of shared memory + TMEM)
+  {
+    cudaError_t eh = cudaFuncSetAttribute(k_policy_heads_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM_MAX);
+    if (eh == cudaSuccess) eh = cudaFuncSetAttribute(k_policy_heads_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM_MAX);
+    if (eh != cudaSuccess) { delete h; return fail(DDRL_ECUDA, "cudaFuncSetAttribute(heads smem): %s", cudaGetErrorString(eh)); }
+  }
   if (h->use_tc) {
     cudaError_t es = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
@@ -1358,19 +1437,21 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   const int D = obs_dim, A = act_dim;
   {
     // blocks in the reference's variable order; internal starts rounded up to 4 floats
-    const int64_t sizes[9] = {(int64_t)(D + 1) * h1, (int64_t)(h1 + 1) * h2, (int64_t)(h2 + 1) * 2 * A,
+    h->ldh = (2 * A + 3) / 4 * 4;
+    const int64_t sizes[9] = {(int64_t)(D + 1) * h1, (int64_t)(h1 + 1) * h2, (int64_t)(h2 + 1) * h->ldh,
                               (int64_t)(D + A + 1) * h1, (int64_t)(h1 + 1) * h2, (int64_t)(h2 + 1),
                               (int64_t)(D + A + 1) * h1, (int64_t)(h1 + 1) * h2, (int64_t)(h2 + 1)};
     int64_t* slots[9] = {&h->o_pi1, &h->o_pi2, &h->o_pih, &h->o_q1[0], &h->o_q1[1], &h->o_q1[2],
                          &h->o_q2[0], &h->o_q2[1], &h->o_q2[2]};
     int64_t o = 0, e = 0;
-    h->map.nblk = 9; h->map.head_idx = 2; h->map.h2 = h2; h->map.A = A;
+    h->map.nblk = 9; h->map.head_idx = 2; h->map.h2 = h2; h->map.A = A; h->map.ldh = h->ldh;
     for (int b = 0; b < 9; ++b) {
       o = (o + 3) / 4 * 4;
       if (b == 3) h->P_pi = o;
       *slots[b] = o;
       h->map.ext_off[b] = e; h->map.int_off[b] = o; h->map.size[b] = sizes[b];
-      o += sizes[b]; e += sizes[b];
+      o += sizes[b];
+      e += b == 2 ? (int64_t)(h2 + 1) * 2 * A : sizes[b];   // the reference's head tensors are unpadded
     }
     h->P = (o + 3) / 4 * 4;
     h->Pext = e;
@@ -1443,7 +1524,6 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
   for (auto& kv : h->plans) {
     Plan& pl = kv.second;
     for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply}) if (ex) cudaGraphExecDestroy(ex);
-    if (pl.d_stages) cudaFree(pl.d_stages);
   }
   for (void* p : h->allocs) cudaFree(p);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -1539,7 +1619,7 @@ int ddrl_sac_act(ddrl_sac_t h, const float* d_obs, int n, int deterministic, con
   if (h->h1 > ACT_MAX_H || h->h2 > ACT_MAX_H)
     return fail(DDRL_EINVAL, "ddrl_sac_act: hidden sizes above %d are not supported", ACT_MAX_H);
   DeviceGuard guard(h->device);
-  k_actor_forward<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, h->D, h->A, h->h1, h->h2, h->act_scale, deterministic, d_obs,
+  k_actor_forward<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n, h->D, h->A, h->h1, h->h2, h->ldh, h->act_scale, deterministic, d_obs,
                                                                  h->W + h->o_pi1, h->W + h->o_pi2, h->W + h->o_pih, d_noise, seed,
                                                                  counter, d_out_act);
   DDRL_LAUNCH_CHECK();
