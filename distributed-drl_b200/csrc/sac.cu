@@ -13,8 +13,10 @@
 // [K+1, N] block per dense layer (kernel rows + bias row; see sac_gemm.cuh), so the optimiser, the
 // target averaging, the gradient all-reduce and the parameter broadcast are each one pass / one
 // collective over one buffer.  The policy's mu and log_std heads share one [h2+1, 2A] block.
-// The whole step is captured once per batch size into a CUDA graph; per-step values (input pointers,
-// step counters, Philox counter) live in device memory and are written by a 1-thread kernel.
+// The step after the prologue is captured once per batch size into a CUDA graph (tensor-core GEMM stages and
+// row-wise kernels on the main stream, bias / skinny gradients on a forked side stream); the prologue kernel is
+// launched directly because it carries the per-step values (input pointers, Adam step numbers and bias-corrected
+// rates computed on the host, Philox counter) as by-value arguments and publishes them in device memory.
 #include <cmath>
 #include <map>
 #include <vector>
@@ -27,12 +29,17 @@ namespace ddrl {
 // ------------------------------------------------------------------------------------------------
 // device-resident per-step state
 // ------------------------------------------------------------------------------------------------
-struct StepDyn {   // written by k_set_params before every step (by-value kernel arguments)
-  const float *obs1, *obs2, *acts, *rews, *done;  // external batch (NULL: already in internal buffers)
+struct StepDyn {   // per-step values: by-value argument of the prologue kernel, which runs OUTSIDE the captured graph
+  const float *obs1, *obs2, *acts, *rews, *done;  // external batch
   const float* noise;                              // external [3,B,A] noise or NULL (Philox)
   float *out_scalars, *out_q1, *out_q2, *out_logp; // nullable
   unsigned long long seed;
   float grad_scale;
+  // advanced on the host (the handle mirrors the step count): Adam step numbers, TF1 Adam's bias-corrected
+  // rates lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) (tensorflow/python/training/adam.py, 1.x), noise counter
+  int t_pi, t_q;
+  float lr_pi, lr_q;
+  unsigned long long noise_counter;
 };
 struct StepState {  // persistent
   StepDyn dyn;
@@ -44,20 +51,6 @@ struct StepState {  // persistent
   float alpha_const;
   float lr, lr_pi, lr_q;  // base rate and TF1 Adam's bias-corrected rates for this step
 };
-
-__global__ void k_set_params(StepState* st, StepDyn dyn, int advance) {
-  st->dyn = dyn;
-  if (advance) {
-    st->t_pi += 1;
-    st->t_q += 1;
-    st->noise_counter += 1;
-    st->alpha_cur = st->auto_alpha ? expf(st->log_alpha) : st->alpha_const;
-    // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)   (tensorflow/python/training/adam.py, 1.x)
-    const double tp = (double)st->t_pi, tq = (double)st->t_q;
-    st->lr_pi = (float)((double)st->lr * sqrt(1.0 - pow(0.999, tp)) / (1.0 - pow(0.9, tp)));
-    st->lr_q = (float)((double)st->lr * sqrt(1.0 - pow(0.999, tq)) / (1.0 - pow(0.9, tq)));
-  }
-}
 
 // copy the external batch into the learner's own buffers and materialise the noise
 // tensor-core mode: the three concatenated inputs [x|a], [x|a1], [x2|a3] as pre-split hi/lo planes
@@ -73,10 +66,14 @@ __device__ __forceinline__ void put_split(float* hi_plane, long long plane, size
   hi_plane[idx] = hi;
   hi_plane[plane + idx] = lo;
 }
-__device__ __forceinline__ void d_prologue(int vb, int vgrid, const StepState* __restrict__ st, int B, int D, int A,
-                                           float* X, float* X2, float* ACT, float* R, float* DN, float* NOISE,
-                                           XaOut xa = XaOut{nullptr, nullptr, nullptr, 0, 0}) {
-  const StepDyn& d = st->dyn;
+__device__ __forceinline__ void d_prologue(int vb, int vgrid, StepState* st, const StepDyn& d, int B, int D, int A,
+                                           float* X, float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
+  if (vb == 0 && threadIdx.x == 0) {
+    // publish the step's values for the kernels of the captured graph that follow
+    st->dyn = d;
+    st->t_pi = d.t_pi; st->t_q = d.t_q; st->lr_pi = d.lr_pi; st->lr_q = d.lr_q; st->noise_counter = d.noise_counter;
+    st->alpha_cur = st->auto_alpha ? expf(st->log_alpha) : st->alpha_const;
+  }
   const int64_t tid = (int64_t)vb * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)vgrid * blockDim.x;
   if (d.obs1 && xa.xa_d) {
@@ -105,7 +102,7 @@ __device__ __forceinline__ void d_prologue(int vb, int vgrid, const StepState* _
     for (int64_t i = tid; i < n; i += nthr) NOISE[i] = d.noise[i];
   } else {
     // Philox4x32-10 -> two Box-Muller pairs per counter (oracle/replay_oracle.py: philox_normals)
-    const unsigned long long ctr = st->noise_counter;
+    const unsigned long long ctr = d.noise_counter;
     for (int64_t q = tid; q < (n + 3) / 4; q += nthr) {
       const Philox4 p = philox4x32_10((uint32_t)q, (uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5AC1u,
                                       (uint32_t)d.seed, (uint32_t)(d.seed >> 32));
@@ -123,11 +120,11 @@ __device__ __forceinline__ void d_prologue(int vb, int vgrid, const StepState* _
     }
   }
 }
-__global__ void __launch_bounds__(256) k_prologue(const StepState* __restrict__ st, int B, int D, int A, float* X, float* X2,
-                                                  float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
+__global__ void __launch_bounds__(256) k_prologue(StepState* st, const __grid_constant__ StepDyn dyn, int B, int D, int A, float* X,
+                                                  float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
   pdl_trigger();
   pdl_wait();
-  d_prologue(blockIdx.x, gridDim.x, st, B, D, A, X, X2, ACT, R, DN, NOISE, xa);
+  d_prologue(blockIdx.x, gridDim.x, st, dyn, B, D, A, X, X2, ACT, R, DN, NOISE, xa);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -830,6 +827,67 @@ __global__ void __launch_bounds__(256) k_colsum(const __grid_constant__ ColsumGr
   }
 }
 
+// Skinny weight gradients in tensor-core mode (Q heads: N = 1, policy heads: N = 2A): d[W;b][f, j] =
+// sum_b [act|1][b, f] * z[b, j] over the batch rows of each split-K slice.  One CTA per (32-feature chunk, split):
+// lane = feature (128-byte coalesced rows of act), z[b, :] is a broadcast load, the 8 warps stride the rows and
+// combine in shared memory in fixed order (deterministic).
+constexpr int SKINNY_MAX = 4;
+struct SkinnyGroup {
+  int nprob, B, kps;
+  long long split_stride;
+  struct {
+    const float* act;   // [B, K] plain fp32, pitch ld_act; feature K is the constant-one column (bias row)
+    const float* z;     // [B, n], pitch ldz
+    float* out;         // [K + 1, ldc]
+    int ld_act, K, ldz, n, ldc, chunk_begin;
+  } p[SKINNY_MAX];
+};
+template <int NJ>   // NJ >= n: outputs accumulated per thread in one pass over the rows
+__device__ __forceinline__ void skinny_body(const SkinnyGroup& g, int pi, float (*s_acc)[8][33]) {
+  const float* act = g.p[pi].act;
+  const float* z = g.p[pi].z;
+  const int K = g.p[pi].K, ld_act = g.p[pi].ld_act, ldz = g.p[pi].ldz, n = g.p[pi].n, ldc = g.p[pi].ldc;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int f = (blockIdx.x - g.p[pi].chunk_begin) * 32 + lane;
+  const int r0 = blockIdx.y * g.kps, r1 = min(g.B, r0 + g.kps);
+  float* out = g.p[pi].out + (size_t)blockIdx.y * g.split_stride;
+  float acc[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) acc[j] = 0.0f;
+  if (f <= K) {
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float a = f < K ? act[(size_t)r * ld_act + f] : 1.0f;
+      const float* zr = z + (size_t)r * ldz;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (j < n) acc[j] = fmaf(a, zr[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j0 = 0; j0 < NJ; j0 += 8) {
+    if (j0 >= n) break;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) s_acc[w][jj][lane] = acc[j0 + jj];
+    __syncthreads();
+    if (j0 + w < n && f <= K) {       // warp w sums output j0 + w over the 8 warps, in fixed order
+      float t = s_acc[0][w][lane];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) t += s_acc[i][w][lane];
+      out[(size_t)f * ldc + j0 + w] = t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_skinny_wgrad(const __grid_constant__ SkinnyGroup g) {
+  __shared__ float s_acc[8][8][33];
+  int pi = 0;
+  while (pi + 1 < g.nprob && (int)blockIdx.x >= g.p[pi + 1].chunk_begin) ++pi;
+  const int n = g.p[pi].n;   // block-uniform
+  if (n <= 8) skinny_body<8>(g, pi, s_acc);
+  else if (n <= 24) skinny_body<24>(g, pi, s_acc);
+  else skinny_body<MAX_HEAD>(g, pi, s_acc);
+}
+
 }  // namespace ddrl
 
 // =================================================================================================
@@ -855,6 +913,8 @@ struct Plan {
   int64_t kernels[3] = {0, 0, 0};  // kernels inside each captured graph (for the launch counter)
   ColsumGroup colsum[8] = {};      // tensor-core mode: bias-gradient column sums per stage (side stream)
   int colsum_chunks[8] = {};
+  SkinnyGroup skinny[8] = {};      // tensor-core mode: skinny weight gradients per stage (side stream)
+  int skinny_chunks[8] = {};
 };
 
 }  // namespace
@@ -883,12 +943,16 @@ struct ddrl_sac {
   int ld1 = 0, ld2 = 0, ldx = 0, ldh = 0;   // ldh: head block row pitch
   long long lo1 = 0, lo2 = 0, lox = 0;
   float* XA[3] = {};                    // [x|a], [x|a1], [x2|a3] split planes
+  uint32_t* H1bits[8] = {};             // relu'(H1) of each pass as bit masks [maxB][ldbits] (written by the L1 epilogue)
+  int ldbits = 0;
   float *Wsp = nullptr, *Wtsp = nullptr;  // split planes of the main / target weight blocks (SplitMap)
   SplitMap smap{};
   std::vector<void*> allocs;
   std::map<int, Plan> plans;
   bool use_graph = true;
   bool use_tc = true;    // tcgen05 3xTF32 GEMMs from pre-split planes (default); DDRL_GEMM=ffma: fp32 FFMA tiles
+  int t_host = 0;                     // number of updates enqueued so far (Adam step count, noise counter)
+  StepDyn last_dyn{};
   cudaStream_t side_stream = nullptr; // tensor-core mode: skinny / bias gradients run beside the main chain (forked with events)
   cudaEvent_t ev[4] = {};
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy
@@ -1152,17 +1216,21 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
   auto h1v = [&](int p) { return View{h->H1[p], h->ld1, h->lo1, B, h1}; };
   auto dz2v = [&](const float* p) { return View{p, h->ld2, h->lo2, B, h2}; };
   auto dz1v = [&](const float* p) { return View{p, h->ld1, h->lo1, B, h1}; };
-  auto fwd = [&](int stage, const View& act, int blk, bool target, float* C, float* C_lo, int ldc) {
+  auto fwd = [&](int stage, const View& act, int blk, bool target, float* C, float* C_lo, int ldc, uint32_t* bits = nullptr) {
     tc::TcProb p;
     if (!rc && !(rc = mk_tc(&p, act, false, wview(blk, target), true, C, C_lo, ldc, B, Nb[blk], Kb[blk], EPI_RELU,
-                            bias_of(blk, target))))
+                            bias_of(blk, target)))) {
+      p.relu_bits = bits; p.ldbits = h->ldbits;
       add_tc(pl.stages[stage], p);
+    }
   };
   auto dgrad = [&](int stage, const float* dz2, int blk, float* dz1, int mask_pass) {
     tc::TcProb p;   // dZ1 = dZ2 . W2^T masked by relu'(H1)
     if (!rc && !(rc = mk_tc(&p, dz2v(dz2), false, wview(blk, false), false, dz1, dz1 + h->lo1, h->ld1, B, Kb[blk], Nb[blk],
-                            EPI_MASK, nullptr, h->H1[mask_pass], h->H1[mask_pass] + h->lo1, h->ld1)))
+                            EPI_MASK, nullptr, h->H1[mask_pass], h->H1[mask_pass] + h->lo1, h->ld1))) {
+      p.mask_bits = h->H1bits[mask_pass]; p.ldbits = h->ldbits;
       add_tc(pl.stages[stage], p);
+    }
   };
   auto wgrad = [&](int stage, const View& act, const View& dz, int blk) {
     tc::TcProb p;   // d[W] = act^T . dZ (kernel rows); the bias row is the column sum of dZ, on FFMA tiles
@@ -1179,16 +1247,26 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
       cg.B = B; cg.kps = kps; cg.split_stride = h->P;
     }
   };
+  auto skinny = [&](int stage, const float* act, int ld_act, int K, const float* z, int ldz, int n, float* out, int ldc) {
+    SkinnyGroup& sg = pl.skinny[stage];
+    if (!rc && sg.nprob >= SKINNY_MAX) rc = fail(DDRL_EINVAL, "too many skinny weight-gradient problems in one stage");
+    if (rc) return;
+    auto& q = sg.p[sg.nprob++];
+    q.act = act; q.ld_act = ld_act; q.K = K; q.z = z; q.ldz = ldz; q.n = n; q.out = out; q.ldc = ldc;
+    q.chunk_begin = pl.skinny_chunks[stage];
+    pl.skinny_chunks[stage] += (K + 1 + 31) / 32;
+    sg.B = B; sg.kps = kps; sg.split_stride = h->P;
+  };
   // ---- forward: policies (a: main@x, b: main@x2, c: target@x2) and the data-action Q passes (d, e)
-  fwd(ST_L1, xa(0, D), PI1, false, h->H1[a], h->H1[a] + h->lo1, h->ld1);
+  fwd(ST_L1, xa(0, D), PI1, false, h->H1[a], h->H1[a] + h->lo1, h->ld1, h->H1bits[a]);
   fwd(ST_L1, xa(2, D), PI1, false, h->H1[b], h->H1[b] + h->lo1, h->ld1);
   fwd(ST_L1, xa(2, D), PI1, true, h->H1[c], h->H1[c] + h->lo1, h->ld1);
-  fwd(ST_L1, xa(0, D + A), Q1_0, false, h->H1[d], h->H1[d] + h->lo1, h->ld1);
-  fwd(ST_L1, xa(0, D + A), Q2_0, false, h->H1[e], h->H1[e] + h->lo1, h->ld1);
+  fwd(ST_L1, xa(0, D + A), Q1_0, false, h->H1[d], h->H1[d] + h->lo1, h->ld1, h->H1bits[d]);
+  fwd(ST_L1, xa(0, D + A), Q2_0, false, h->H1[e], h->H1[e] + h->lo1, h->ld1, h->H1bits[e]);
   const int blk2[5] = {PI2, PI2, PI2, Q1_1, Q2_1};
   for (int p = 0; p < 5; ++p) fwd(ST_L2, h1v(p), blk2[p], p == c, h->H2[p], nullptr, h2);
   // ---- forward, policy-action Q passes: f = Q1(x,a1), g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3)
-  fwd(ST_QL1, xa(1, D + A), Q1_0, false, h->H1[f], h->H1[f] + h->lo1, h->ld1);
+  fwd(ST_QL1, xa(1, D + A), Q1_0, false, h->H1[f], h->H1[f] + h->lo1, h->ld1, h->H1bits[f]);
   fwd(ST_QL1, xa(2, D + A), Q1_0, true, h->H1[g], h->H1[g] + h->lo1, h->ld1);
   fwd(ST_QL1, xa(2, D + A), Q2_0, true, h->H1[hh], h->H1[hh] + h->lo1, h->ld1);
   fwd(ST_QL2, h1v(f), Q1_1, false, h->H2[f], nullptr, h2);
@@ -1201,13 +1279,13 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
   for (int i = 0; i < 3; ++i) {
     dgrad(ST_BQ, h->dZ2[i], w2blk[i], h->dZ1[i], pass[i]);
     if (i < 2) {
-      add(pl.stages[ST_BQ], wg(mk(seg(h->H2[pass[i]], h2, h2), none(), 1, 1, h->dQ[i], 1, 0, Gp + oq[i][2], 1, h2 + 1, 1, B)));
+      skinny(ST_BQ, h->H2[pass[i]], h2, h2, h->dQ[i], 1, 1, Gp + oq[i][2], 1);      // d[W3;b3] = [H2|1]^T dq
       wgrad(ST_BQ, h1v(pass[i]), dz2v(h->dZ2[i]), w2blk[i]);
       wgrad(ST_BP, xa(0, D + A), dz1v(h->dZ1[i]), w1blk[i]);
     }
   }
   // ---- policy backward (pass a); dHD and dZ2a come from k_policy_bwd_rows
-  add(pl.stages[ST_BP], wg(mk(seg(h->H2[a], h2, h2), none(), 1, 1, h->dHD, 2 * A, 0, Gp + h->o_pih, h->ldh, h2 + 1, 2 * A, B)));
+  skinny(ST_BP, h->H2[a], h2, h2, h->dHD, 2 * A, 2 * A, Gp + h->o_pih, h->ldh);      // d[Whead;bhead] = [H2a|1]^T dHD
   dgrad(ST_BP, h->dZ2a, PI2, h->dZ1a, a);
   wgrad(ST_BP, h1v(a), dz2v(h->dZ2a), PI2);
   wgrad(ST_BP3, xa(0, D), dz1v(h->dZ1a), PI1);
@@ -1231,6 +1309,10 @@ int run_side(const Plan& pl, int st, int S, cudaStream_t side) {
     int rc = launch_f32(g, side);
     if (rc) return rc;
   }
+  if (pl.skinny[st].nprob > 0) {
+    k_skinny_wgrad<<<dim3(pl.skinny_chunks[st], S), 256, 0, side>>>(pl.skinny[st]);
+    DDRL_LAUNCH_CHECK();
+  }
   if (pl.colsum[st].nprob > 0) {
     k_colsum<<<dim3(pl.colsum_chunks[st], S), 256, 0, side>>>(pl.colsum[st]);
     DDRL_LAUNCH_CHECK();
@@ -1242,12 +1324,12 @@ XaOut xa_out(const ddrl_sac* h) {
   return h->use_tc ? XaOut{h->XA[0], h->XA[1], h->XA[2], h->ldx, h->lox} : XaOut{nullptr, nullptr, nullptr, 0, 0};
 }
 
-int launch_prologue(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+int launch_prologue(ddrl_sac* h, const Plan& pl, const StepDyn& dyn, cudaStream_t s) {
   const int B = pl.B, D = h->D, A = h->A;
   const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
   int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
-  DDRL_CUDA(launch_pdl(k_prologue, dim3(blocks), dim3(256), 0, s, h->st, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN, h->NOISE,
-                       xa_out(h)));
+  DDRL_CUDA(launch_pdl(k_prologue, dim3(blocks), dim3(256), 0, s, h->st, dyn, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN,
+                       h->NOISE, xa_out(h)));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1295,7 +1377,6 @@ int launch_pbwd(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 
 int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   int rc;
-  if ((rc = launch_prologue(h, pl, s))) return rc;
   if ((rc = run_stage(pl, ST_L1, s))) return rc;
   if ((rc = run_stage(pl, ST_L2, s))) return rc;
   if ((rc = launch_heads(h, pl, s))) return rc;
@@ -1487,6 +1568,8 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   A_(&h->dA1, M * A); A_(&h->dHD, M * 2 * A); A_(&h->dZ2a, planes * M * h->ld2); A_(&h->dZ1a, planes * M * h->ld1);
   if (h->use_tc) {
     for (int i = 0; i < 3; ++i) A_(&h->XA[i], 2 * M * h->ldx);
+    h->ldbits = (h1 + 31) / 32;
+    for (int p = 0; p < 8; ++p) { float* t = nullptr; A_(&t, M * h->ldbits); h->H1bits[p] = reinterpret_cast<uint32_t*>(t); }
     SplitMap& sm = h->smap;
     const int64_t ioff[6] = {h->o_pi1, h->o_pi2, h->o_q1[0], h->o_q1[1], h->o_q2[0], h->o_q2[1]};
     const int Kb[6] = {D, h1, D + A, h1, D + A, h1};
@@ -1578,8 +1661,14 @@ static int step_common(ddrl_sac_t h, int mode, const float* d_obs1, const float*
     dyn.noise = d_noise;
     dyn.out_scalars = d_out_scalars; dyn.out_q1 = d_out_q1; dyn.out_q2 = d_out_q2; dyn.out_logp = d_out_logp;
     dyn.seed = seed; dyn.grad_scale = grad_scale;
-    k_set_params<<<1, 1, 0, s>>>(h->st, dyn, 1);
-    DDRL_LAUNCH_CHECK();
+    h->t_host += 1;
+    const double t = (double)h->t_host;
+    dyn.t_pi = dyn.t_q = h->t_host;
+    dyn.lr_pi = dyn.lr_q = (float)((double)h->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+    dyn.noise_counter = (unsigned long long)h->t_host;
+    h->last_dyn = dyn;
+    // the prologue carries the per-step values by value, so it is launched directly; the rest of the step is a graph
+    if ((rc = launch_prologue(h, *pl, dyn, s))) return rc;
   }
   return run_mode(h, *pl, mode, s);
 }
@@ -1638,7 +1727,7 @@ int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* str
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = 0; i < reps; ++i) {
     if (stage < ST_COUNT) rc = run_stage(*pl, stage, s, h->use_tc);
-    else if (stage == 7) rc = launch_prologue(h, *pl, s);
+    else if (stage == 7) rc = launch_prologue(h, *pl, h->last_dyn, s);
     else if (stage == 8) rc = launch_heads(h, *pl, s);
     else if (stage == 9) rc = launch_qheads(h, *pl, s);
     else if (stage == 10) rc = launch_pbwd(h, *pl, s);

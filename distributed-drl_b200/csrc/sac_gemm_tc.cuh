@@ -14,8 +14,8 @@
 // (the major-ness is a bit of the instruction descriptor plus the shared-memory descriptor's strides).
 //
 // One CTA per 128 x 128 output tile, warp-specialised, 3-stage TMA -> tcgen05 pipeline:
-//   warp 0 / lane 0   TMA producer: per k-block (32 tf32 = one 128-byte swizzle row) loads A_hi, A_lo,
-//                     B_hi, B_lo with cp.async.bulk.tensor (SWIZZLE_128B) into a 64 KB stage; out-of-range
+//   warps 0, 2 / lane 0   TMA producers (A planes, B planes): per k-block (32 tf32 = one 128-byte swizzle row)
+//                     load A_hi, A_lo / B_hi, B_lo with cp.async.bulk.tensor into a 64 KB stage; out-of-range
 //                     rows / columns / k are zero-filled by the TMA unit (ragged M, N, K need no code)
 //   warp 1 / lane 0   MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 per stage, then
 //                     tcgen05.commit to the stage's "empty" barrier; the last commit signals the epilogue
@@ -47,6 +47,9 @@ struct alignas(64) TcProb {
   const float* mask;           // relu-mask source (hi plane) and its lo plane
   const float* mask_lo;
   const float* bias;           // nullable: added per output column before the activation
+  uint32_t* relu_bits;         // nullable (EPI_RELU): bit c of word [row * ldbits + n/32] = output (row, n + c) > 0
+  const uint32_t* mask_bits;   // EPI_MASK with bits instead of the mask planes (the producer's relu_bits)
+  int ldbits;
   long long c_split_stride;    // floats between split-K partial outputs
   int ldc, ldmask;
   int M, N, K;
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   if (tid == 0) {
     prefetch_tmap(&P.ta);
     prefetch_tmap(&P.tb);
-    for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 2); bar_init(&empty[s], 1); }   // full: A and B producers
     bar_init(acc_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -189,30 +192,27 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   const int kend = min(K, kbeg + P.k_per_split);
   const int nkb = (kend - kbeg + BK - 1) / BK;
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 2) {
     if (lane == 0) {
-      // ---- TMA producer ----
-      if (P.c_tma) prefetch_tmap(&P.tc);
-      const CUtensorMap* ta = &P.ta;
-      const CUtensorMap* tb = &P.tb;
+      // ---- TMA producers: warp 0 loads the A planes, warp 2 the B planes (an MN-major operand is four
+      //      32 x 32 boxes per plane, so one thread issuing all 16 copies of a k-block would be the bottleneck) ----
+      const bool is_b = warp == 2;
+      const CUtensorMap* tm = is_b ? &P.tb : &P.ta;
+      const int mn = is_b ? b_mn : a_mn, r0 = is_b ? n0 : m0;
+      if (!is_b && P.c_tma) prefetch_tmap(&P.tc);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         if (kb >= STAGES) bar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
-        bar_expect_tx(&full[s], STAGE_BYTES);
-        const uint32_t st = s_addr(base + s * STAGE_BYTES);
+        bar_expect_tx(&full[s], 2 * TILE_BYTES);
+        const uint32_t st = s_addr(base + s * STAGE_BYTES) + (is_b ? 2 * TILE_BYTES : 0);
         const int k0 = kbeg + kb * BK;
 #pragma unroll
         for (int hl = 0; hl < 2; ++hl) {
-          const uint32_t da = st + hl * TILE_BYTES, db = st + (2 + hl) * TILE_BYTES;
-          if (!a_mn) tma_load_3d(da, ta, k0, m0, hl, &full[s]);
+          const uint32_t dst = st + hl * TILE_BYTES;
+          if (!mn) tma_load_3d(dst, tm, k0, r0, hl, &full[s]);
           else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_3d(da + j * 4096, ta, m0 + 32 * j, k0, hl, &full[s]);
-          }
-          if (!b_mn) tma_load_3d(db, tb, k0, n0, hl, &full[s]);
-          else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_3d(db + j * 4096, tb, n0 + 32 * j, k0, hl, &full[s]);
+            for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096, tm, r0 + 32 * j, k0, hl, &full[s]);
           }
         }
       }
@@ -277,8 +277,17 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
           }
         }
         if (epi == EPI_RELU) {
+          uint32_t bits = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          for (int i = 0; i < 32; ++i) {
+            bits |= (v[i] > 0.0f ? 1u : 0u) << i;
+            v[i] = fmaxf(v[i], 0.0f);
+          }
+          if (P.relu_bits) P.relu_bits[(size_t)m * P.ldbits + (n_base >> 5)] = bits;
+        } else if (epi == EPI_MASK && P.mask_bits) {
+          const uint32_t bits = P.mask_bits[(size_t)m * P.ldbits + (n_base >> 5)];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.0f;
         } else if (epi == EPI_MASK) {
           const float* mk = P.mask + (size_t)m * P.ldmask + n_base;
           const float* ml = P.mask_lo ? P.mask_lo + (size_t)m * P.ldmask + n_base : nullptr;
