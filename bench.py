@@ -220,6 +220,12 @@ def run_ours(args):
                        torch.randn(n, device=dev, generator=gen), torch.randn((n, D), device=dev, generator=gen),
                        (torch.rand(n, device=dev, generator=gen) < 0.01).float())
     learner = Learner(make_opt(cfg, seed=7), "learner", device=local)   # same seed -> same initial weights on every rank
+    dp_mode = "single"
+    if world > 1:
+        # gradient exchange: fused into the optimiser kernel over NVLink peer memory (default) or NCCL all-reduce
+        dp_mode = "nccl"
+        if os.environ.get("DDRL_DP", "fused") != "nccl" and learner.connect_peers():
+            dp_mode = "peer-fused"
     torch.cuda.synchronize()
 
     def barrier():
@@ -336,7 +342,9 @@ def run_ours(args):
         updates_per_s=upd_per_s_rank, global_batch=world * B,
         config=dict(workload=f"{args.config}: {cfg['desc']} (obs {D}, act {A}, batch {B} per GPU, {hidden[0]}x{hidden[1]} MLP)",
                     replay_rows_per_gpu=rows, replay_bytes_per_gpu=rows * ((row_bytes + 15) // 16 * 16),
-                    parallelism=f"dp{world}: replay sharded per GPU, NCCL grad all-reduce" if world > 1 else "single GPU",
+                    parallelism=(f"dp{world}: replay sharded per GPU, gradient all-reduce "
+                                 + ("fused into the optimiser kernel over NVLink peer memory (CUDA IPC)" if dp_mode == "peer-fused"
+                                    else "by NCCL")) if world > 1 else "single GPU",
                     l2="replay ring larger than L2, rows drawn at random; weights (3.5 MB) are L2-resident by design",
                     noise="Philox on device", index_source="Philox on device"),
         clocks=clk,

@@ -18,6 +18,7 @@
 // launched directly because it carries the per-step values (input pointers, Adam step numbers and bias-corrected
 // rates computed on the host, Philox counter) as by-value arguments and publishes them in device memory.
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -761,6 +762,109 @@ __global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_
   d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo, &mp, Wsp, Wtsp);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Data-parallel learners without a collective library call: gradient all-reduce FUSED into the optimiser over
+// NVLink peer memory.  Every rank owns one communication buffer [2][Pc] floats (+ 8 arrival flags) that all peers
+// map with CUDA IPC.  Step t: k_grad_reduce_comm leaves this rank's flat gradient (split-K partials summed, plus
+// the entropy statistic) in slot t & 1; k_adam_polyak_peer then
+//   1. signals "my gradient of step t is complete" by storing t into flag[rank] of every peer (st.release.sys),
+//   2. waits until its own flags show t from every peer (ld.acquire.sys),
+//   3. reads all ranks' slot t & 1 directly (128-bit volatile loads over NVLink), sums them in rank order — every
+//      rank computes bit-identical sums — scales by 1/N and applies Adam + polyak (+ the weight split planes).
+// Slots alternate, so a slot is rewritten at step t + 2 only after every peer has passed the barrier of step
+// t + 1, i.e. finished reading it: one flag exchange per step is the only synchronisation.
+// ------------------------------------------------------------------------------------------------
+struct PeerComm {
+  float* buf[8];            // rank r's communication buffer as mapped in this process
+  unsigned int* flags[8];   // rank r's arrival flags (flags[r][i] = last step rank i has published)
+  int world, rank;
+  long long Pc;             // floats per slot (P + 4, multiple of 4)
+};
+__global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __restrict__ st, int64_t P, int S,
+                                                          const float* __restrict__ Gp, const float* __restrict__ SCAL,
+                                                          const __grid_constant__ PeerComm pc) {
+  pdl_trigger();
+  pdl_wait();
+  float* G = pc.buf[pc.rank] + (size_t)(st->t_pi & 1) * pc.Pc;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    float g = Gp[i];
+    for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
+    G[i] = g;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) G[P] = SCAL[4];   // mean logp1 of this rank's batch (entropy-alpha gradient)
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t P, int64_t P_pi, float lr, float polyak,
+                                                          float target_entropy, float* W, float* Wt, float* Mo, float* Vo,
+                                                          const __grid_constant__ SplitMap mp, float* Wsp, float* Wtsp,
+                                                          const __grid_constant__ PeerComm pc, int* err) {
+  pdl_trigger();
+  pdl_wait();
+  const unsigned int epoch = (unsigned int)st->t_pi;
+  if (threadIdx.x < pc.world) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc.flags[threadIdx.x] + pc.rank), "r"(epoch) : "memory");
+    }
+    const unsigned int* mine = pc.flags[pc.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v < epoch && clock64() - t0 > 20000000000LL) { *err = 1; break; }   // ~10 s: a peer died; do not hang the GPU
+    } while (v < epoch);
+  }
+  __syncthreads();
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float lr_pi = st->lr_pi, lr_q = st->lr_q;
+  const float gs = st->dyn.grad_scale;
+  const size_t slot = (size_t)(epoch & 1u) * pc.Pc;
+  const int world = pc.world;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < P; i += stride) {
+    float4 g = ld_volatile_f4(pc.buf[0] + slot + i);
+    for (int r = 1; r < world; ++r) {
+      const float4 q = ld_volatile_f4(pc.buf[r] + slot + i);
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    const float gv[4] = {g.x * gs, g.y * gs, g.z * gs, g.w * gs};
+    const float4 m4 = *reinterpret_cast<const float4*>(Mo + i), v4 = *reinterpret_cast<const float4*>(Vo + i);
+    const float4 w4 = *reinterpret_cast<const float4*>(W + i), t4 = *reinterpret_cast<const float4*>(Wt + i);
+    const float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w},
+                tv[4] = {t4.x, t4.y, t4.z, t4.w};
+    float mo[4], vo[4], wo[4], to[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mo[e] = b1 * mv[e] + (1.0f - b1) * gv[e];
+      vo[e] = b2 * vv[e] + (1.0f - b2) * gv[e] * gv[e];
+      wo[e] = wv[e] - (i + e < P_pi ? lr_pi : lr_q) * mo[e] / (sqrtf(vo[e]) + eps);
+      to[e] = polyak * tv[e] + (1.0f - polyak) * wo[e];
+      if (Wsp) { write_split(mp, i + e, wo[e], Wsp); write_split(mp, i + e, to[e], Wtsp); }
+    }
+    *reinterpret_cast<float4*>(Mo + i) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+    *reinterpret_cast<float4*>(Vo + i) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+    *reinterpret_cast<float4*>(W + i) = make_float4(wo[0], wo[1], wo[2], wo[3]);
+    *reinterpret_cast<float4*>(Wt + i) = make_float4(to[0], to[1], to[2], to[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && st->auto_alpha) {
+    float lp = 0.0f;
+    for (int r = 0; r < world; ++r) lp += *reinterpret_cast<volatile const float*>(pc.buf[r] + slot + P);
+    lp *= gs;                                           // mean over the global batch (equal batch per rank)
+    st->t_alpha += 1;
+    const double ta = (double)st->t_alpha;
+    const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
+    const float g = -(lp + target_entropy);
+    st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * g;
+    st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * g * g;
+    st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
+  }
+}
+
 // external (TF variable order: kernel, bias per dense layer; mu head then log_std head) <-> internal
 // flat layout.  Internal blocks start on 16-byte boundaries (vector loads in the GEMM operand fetch)
 // and the policy head block is fused: internal [h2+1, ldh] = [Wmu|Wls|0.. ; bmu|bls|0..], ldh = 2A rounded up to 4.
@@ -951,6 +1055,10 @@ struct ddrl_sac {
   std::map<int, Plan> plans;
   bool use_graph = true;
   bool use_tc = true;    // tcgen05 3xTF32 GEMMs from pre-split planes (default); DDRL_GEMM=ffma: fp32 FFMA tiles
+  PeerComm pc{};                      // fused data-parallel mode (ddrl_sac_comm_attach): peers' communication buffers
+  float* comm = nullptr;              // this rank's buffer: [2][Pc] floats, then 8 arrival flags
+  bool peer_opened[8] = {};
+  int* d_err = nullptr;
   int t_host = 0;                     // number of updates enqueued so far (Adam step count, noise counter)
   StepDyn last_dyn{};
   cudaStream_t side_stream = nullptr; // tensor-core mode: skinny / bias gradients run beside the main chain (forked with events)
@@ -1411,13 +1519,25 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 
 int enqueue_reduce(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
-  DDRL_CUDA(launch_pdl(k_grad_reduce, dim3(blocks), dim3(256), 0, s, h->P, pl.S, h->Gp, h->G));
+  if (h->pc.world > 1)
+    DDRL_CUDA(launch_pdl(k_grad_reduce_comm, dim3(blocks), dim3(256), 0, s, (const StepState*)h->st, h->P, pl.S,
+                         (const float*)h->Gp, (const float*)h->SCAL, h->pc));
+  else
+    DDRL_CUDA(launch_pdl(k_grad_reduce, dim3(blocks), dim3(256), 0, s, h->P, pl.S, h->Gp, h->G));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
 
 int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s) {
   int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+  if (h->pc.world > 1 && grads == h->G) {     // data-parallel apply: all-reduce fused into the optimiser over peer memory
+    blocks = (int)std::min<int64_t>((h->P / 4 + 255) / 256, h->sms * 8);
+    DDRL_CUDA(launch_pdl(k_adam_polyak_peer, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, h->lr, h->polyak,
+                         -(float)h->A, h->W, h->Wt, h->Mo, h->Vo, h->smap, h->use_tc ? h->Wsp : nullptr,
+                         h->use_tc ? h->Wtsp : nullptr, h->pc, h->d_err));
+    DDRL_LAUNCH_CHECK();
+    return 0;
+  }
   if (h->use_tc)
     DDRL_CUDA(launch_pdl(k_adam_polyak_split, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak,
                          -(float)h->A, h->SCAL, h->W, h->Wt, h->Mo, h->Vo, h->smap, h->Wsp, h->Wtsp));
@@ -1608,6 +1728,9 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
     Plan& pl = kv.second;
     for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply}) if (ex) cudaGraphExecDestroy(ex);
   }
+  for (int r = 0; r < 8; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->pc.buf[r]);
+  if (h->comm) cudaFree(h->comm);
+  if (h->d_err) cudaFree(h->d_err);
   for (void* p : h->allocs) cudaFree(p);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -1693,6 +1816,66 @@ int ddrl_sac_grad_buffer(ddrl_sac_t h, float** d_grads, int64_t* count, float** 
   if (d_grads) *d_grads = h->G;
   if (count) *count = h->P;
   if (d_alpha_stat) *d_alpha_stat = h->SCAL + 4;
+  return 0;
+}
+
+int ddrl_sac_comm_export(ddrl_sac_t h, void* h_handle64) {
+  if (!h || !h_handle64) return fail(DDRL_EINVAL, "ddrl_sac_comm_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  DeviceGuard guard(h->device);
+  if (!h->comm) {
+    const long long Pc = (h->P + 4 + 3) / 4 * 4;
+    const size_t bytes = (size_t)2 * Pc * sizeof(float) + 8 * sizeof(unsigned int);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);   // its own allocation: CUDA IPC shares whole allocations
+    if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(comm buffer) failed: %s", cudaGetErrorString(e));
+    DDRL_CUDA(cudaMemset(p, 0, bytes));
+    h->comm = (float*)p;
+    h->pc.Pc = Pc;
+    if (!h->d_err) {
+      DDRL_CUDA(cudaMalloc((void**)&h->d_err, sizeof(int)));
+      DDRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    }
+  }
+  cudaIpcMemHandle_t hd;
+  DDRL_CUDA(cudaIpcGetMemHandle(&hd, h->comm));
+  memcpy(h_handle64, &hd, 64);
+  return 0;
+}
+
+int ddrl_sac_comm_attach(ddrl_sac_t h, int world, int rank, const void* h_handles) {
+  if (!h || !h_handles) return fail(DDRL_EINVAL, "ddrl_sac_comm_attach: NULL argument");
+  if (world < 2 || world > 8 || rank < 0 || rank >= world)
+    return fail(DDRL_EINVAL, "ddrl_sac_comm_attach: rank %d of %d (2..8 ranks of one node)", rank, world);
+  if (!h->comm) return fail(DDRL_ESTATE, "ddrl_sac_comm_attach: call ddrl_sac_comm_export first");
+  if (h->t_host != 0) return fail(DDRL_ESTATE, "ddrl_sac_comm_attach: attach before the first update (ranks step in lockstep)");
+  DeviceGuard guard(h->device);
+  for (int r = 0; r < world; ++r) {
+    void* p = h->comm;
+    if (r != rank) {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, (const char*)h_handles + 64 * r, 64);
+      p = nullptr;
+      DDRL_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_opened[r] = true;
+    }
+    h->pc.buf[r] = (float*)p;
+    h->pc.flags[r] = reinterpret_cast<unsigned int*>((float*)p + 2 * h->pc.Pc);
+  }
+  h->pc.world = world; h->pc.rank = rank;
+  // graphs captured before the attach hold the single-GPU kernels
+  for (auto& kv : h->plans)
+    for (cudaGraphExec_t* ex : {&kv.second.exec_full, &kv.second.exec_grads, &kv.second.exec_apply})
+      if (*ex) { cudaGraphExecDestroy(*ex); *ex = nullptr; }
+  return 0;
+}
+
+int ddrl_sac_comm_error(ddrl_sac_t h, int* out) {
+  if (!h || !out) return fail(DDRL_EINVAL, "ddrl_sac_comm_error: NULL argument");
+  *out = 0;
+  if (!h->d_err) return 0;
+  DeviceGuard guard(h->device);
+  DDRL_CUDA(cudaMemcpy(out, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -125,6 +125,7 @@ class Learner(object):
         self._grad = torch.as_tensor(_DevPtr(gp.value, int(cnt.value)), device=self._dev)
         self._alpha_stat = torch.as_tensor(_DevPtr(ap.value, 1), device=self._dev)
         self._pg = process_group
+        self._fused = False
         self._outs = None
         self._stage = {}
         self.steps = 0
@@ -148,6 +149,31 @@ class Learner(object):
         if dist.is_available() and dist.is_initialized():
             return dist.get_world_size(self._pg)
         return 1
+
+    def connect_peers(self, group=None):
+        """Fused data-parallel mode (collective; call on every rank of one node before the first train()):
+        exchanges the CUDA IPC handles of the ranks' gradient buffers, after which the all-reduce between
+        compute_grads and apply_grads is done INSIDE the optimiser kernel over NVLink peer memory (no NCCL call
+        on the step path).  Without it, train() uses torch.distributed.all_reduce (NCCL)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2:
+            return False
+        buf = (C.c_ubyte * 64)()
+        N.check(self._lib.ddrl_sac_comm_export(self._h, buf))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(buf), group=group)
+        blob = b"".join(handles)
+        N.check(self._lib.ddrl_sac_comm_attach(self._h, world, rank, C.c_char_p(blob)))
+        self._pg = group
+        self._fused = True
+        dist.barrier(group)
+        return True
+
+    def comm_error(self):
+        e = C.c_int()
+        N.check(self._lib.ddrl_sac_comm_error(self._h, C.byref(e)))
+        return int(e.value)
 
     # ---- weights -------------------------------------------------------------------------------
     def _flat_from(self, keys, values):
@@ -317,10 +343,12 @@ class Learner(object):
         else:
             import torch.distributed as dist
             N.check(self._lib.ddrl_sac_compute_grads(self._h, *args, B, nzp, self.seed, 1.0 / world, *outs, sp))
-            dist.all_reduce(self._grad, op=dist.ReduceOp.SUM, group=self._pg)
-            if self.auto_alpha:
-                dist.all_reduce(self._alpha_stat, op=dist.ReduceOp.SUM, group=self._pg)
-                self._alpha_stat.div_(world)
+            if not self._fused:
+                dist.all_reduce(self._grad, op=dist.ReduceOp.SUM, group=self._pg)
+                if self.auto_alpha:
+                    dist.all_reduce(self._alpha_stat, op=dist.ReduceOp.SUM, group=self._pg)
+                    self._alpha_stat.div_(world)
+            # fused mode: apply_grads exchanges the gradients over NVLink peer memory inside the optimiser kernel
             N.check(self._lib.ddrl_sac_apply_grads(self._h, B, sp))
         for t in (x, x2, a, r, d):
             t.record_stream(s)

@@ -204,6 +204,17 @@ int ddrl_sac_compute_grads(ddrl_sac_t sac, const float* d_obs1, const float* d_o
                            float* d_out_logp, void* stream);
 int ddrl_sac_grad_buffer(ddrl_sac_t sac, float** d_grads, int64_t* count, float** d_alpha_stat);
 int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
+/* Fused data-parallel mode (one process per GPU of one node, 2..8 ranks; replaces the NCCL all-reduce between
+ * compute_grads and apply_grads, i.e. what `north_star` asks of algos/sac1's multi-learner setup, sac1.py:273-276):
+ *   ddrl_sac_comm_export  -> 64-byte CUDA IPC handle of this rank's gradient exchange buffer
+ *   ddrl_sac_comm_attach  -> h_handles = world x 64 bytes (rank order, as exported); maps every peer's buffer.
+ * Afterwards compute_grads leaves the flat gradient in the exchange buffer and apply_grads runs ONE kernel that
+ * exchanges arrival flags with all peers, reads their gradients over NVLink, sums them in rank order (replicas stay
+ * bit-identical), scales by grad_scale and applies Adam + polyak.  All ranks must call the step functions in
+ * lockstep.  ddrl_sac_comm_error reports a peer time-out (a rank died) observed by the kernel. */
+int ddrl_sac_comm_export(ddrl_sac_t sac, void* h_handle64);
+int ddrl_sac_comm_attach(ddrl_sac_t sac, int world, int rank, const void* h_handles);
+int ddrl_sac_comm_error(ddrl_sac_t sac, int* out_error);
 /* Actor.get_action(o, deterministic) (algos/sac1/actor_learner.py:195-197) for n observations at once:
  * d_out_act[n, A] = act_scale * tanh(mu) (deterministic) or act_scale * tanh(mu + eps * std); eps from
  * d_noise [n, A] or, when NULL, Philox keyed by (seed, counter).  Uses the handle's main policy weights. */

@@ -22,7 +22,7 @@ def _opt(batch):
                            gamma=0.99, lr=1e-3, polyak=0.995, seed=0, batch_size=batch)
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, fused=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,6 +33,8 @@ def _worker(rank, world, port, ret):
     params = conditioned_params(D, A, HID, seed=3)
     L = Learner(_opt(B // world), "learner", device=rank)
     L.set_weights(list(params), list(params.values()))
+    if fused:
+        assert L.connect_peers()
     for it in range(3):
         batch, noise = make_batch(D, A, B, seed=40 + it)
         lo, hi = rank * B // world, (rank + 1) * B // world
@@ -43,12 +45,16 @@ def _worker(rank, world, port, ret):
         ps.push_flat(L.get_flat_weights() * 0 + 3.0)
     ps.sync()
     ret[rank] = (L.get_flat_weights("main").cpu().numpy(), L.get_flat_weights("target").cpu().numpy(),
-                 float(ps.pull_flat().min()), float(ps.pull_flat().max()))
+                 float(ps.pull_flat().min()), float(ps.pull_flat().max()), L.comm_error())
+    dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_step_equals_single_gpu_on_concatenated_batch():
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl", "peer-fused"])
+def test_two_gpu_step_equals_single_gpu_on_concatenated_batch(fused):
+    """fused=True: the all-reduce runs inside the optimiser kernel over NVLink peer memory (Learner.connect_peers),
+    no NCCL call on the step path; fused=False: torch.distributed.all_reduce between compute_grads and apply_grads."""
     import torch.multiprocessing as mp
     import __graft_entry__
     __graft_entry__.build()
@@ -56,7 +62,7 @@ def test_two_gpu_step_equals_single_gpu_on_concatenated_batch():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, ret, fused), nprocs=2, join=True)
     from ddrl_b200 import Learner
     params = conditioned_params(D, A, HID, seed=3)
     single = Learner(_opt(B), "learner", device=0)
@@ -72,6 +78,7 @@ def test_two_gpu_step_equals_single_gpu_on_concatenated_batch():
         assert np.abs(ret[r][0] - want_m).max() <= 2e-5 * np.abs(want_m).max()
         assert np.abs(ret[r][1] - want_t).max() <= 2e-5 * np.abs(want_t).max()
         assert ret[r][2] == 3.0 and ret[r][3] == 3.0
+        assert ret[r][4] == 0            # no peer time-out seen by the fused kernel
 
 
 def _global_worker(rank, world, port, ret):
