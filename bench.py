@@ -255,7 +255,9 @@ def run_ours(args):
 
     # ---- (1) device-resident hot loop: sample_batch -> train --------------------------------------
     def step_device():
-        learner.train(rb.sample_batch(B, device=True))
+        # sample_batch(B) + train(batch) as one native call: the step's first kernel gathers the batch from the ring
+        # (Learner.train_from_buffer; bit-identical to train(rb.sample_batch(B, device=True)), tests/test_sac_gpu.py)
+        learner.train_from_buffer(rb, B)
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -285,6 +287,29 @@ def run_ours(args):
     e2e_value = world * B * e2e_steps / sec_e2e
     h2d = 2 * B * row_bytes
     d2h = B * row_bytes + 16
+
+    # ---- (2b) config C5 flavour: 256 vectorised rollout producers store concurrently with learning, weights are
+    #      pushed to the actors' parameter-server replica every 300 learner steps (sac1.py:149) by ONE broadcast --
+    from ddrl_b200.dist import DistributedParameterServer
+    producers = 256
+    rows_per_rank = max(1, producers // world)
+    f32d = dict(dtype=torch.float32, device=dev)
+    prod = [torch.randn((rows_per_rank, D), **f32d), torch.rand((rows_per_rank, A), **f32d) * 2 - 1,
+            torch.randn(rows_per_rank, **f32d), torch.randn((rows_per_rank, D), **f32d), torch.zeros(rows_per_rank, **f32d)]
+    keys, values = learner.get_weights()
+    ps = DistributedParameterServer(keys, values, src=0, device=dev)
+    c5_state = dict(i=0)
+
+    def step_c5():
+        rb.store_batch(*prod)                                 # this rank's share of the 256 producers, one row each
+        learner.train_from_buffer(rb, B)
+        c5_state["i"] += 1
+        if c5_state["i"] % 300 == 0:
+            ps.push_flat(learner.get_flat_weights())          # device-to-device, then one NCCL broadcast of 0.88 MB
+            ps.sync()
+
+    c5_steps = max(300, min(args.steps, 600))
+    sec_c5, _ = timed(step_c5, c5_steps, max(3, min(args.warmup, 10)))
 
     # ---- (3) the gather kernel alone: sample_many launches, outputs >> L2 ---------------------------
     n_batches = max(1, min(2048, int(1.5e9 // (B * row_bytes))))
@@ -351,12 +376,20 @@ def run_ours(args):
         e2e=dict(value=e2e_value, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
                  ms_per_step=sec_e2e / e2e_steps * 1e3,
                  path="store_batch(host) -> sample_batch() -> numpy -> Learner.train(numpy) -> losses.cpu()"),
+        c5=dict(value=world * B * c5_steps / sec_c5, unit="transitions/s", ms_per_step=sec_c5 / c5_steps * 1e3, steps=c5_steps,
+                producers=producers, stored_rows_per_step=rows_per_rank * world, ps_broadcast_every=300,
+                note="config 5 flavour of the same loop: every step each rank also stores its share of 256 producers' "
+                     "transitions; every 300 steps the flat weights are broadcast to the parameter-server replicas"),
         gpu_launches=int(launches),
-        roofline=dict(kernel="SAC1 update, whole step (gemm_grouped_f32 x 7 + 3 row-wise kernels + Adam/polyak, one CUDA graph)", bound="tensor",
+        roofline=dict(kernel="SAC1 update, whole step (gemm_grouped_tc x 7 tcgen05 3xTF32 stages + 3 row-wise kernels + prologue + "
+                             "Adam/polyak; side-stream bias/skinny gradients)", bound="tensor",
                       achieved=tf, peak=peaks["bf16_tf"], unit="TFLOP/s", frac=tf / peaks["bf16_tf"], traffic=None,
                       flops_per_update=fl, peak_source=peaks["source"],
-                      note="parity mode computes in fp32 FFMA (1e-5 bar forbids bf16/tf32 rounding); fraction is "
-                           "against the bf16 tensor peak as SURVEY 8(d) defines it"),
+                      tf32x3_tensor_flops_per_update=3 * fl,
+                      note="fp32-class accuracy (1e-5 bar) needs three tf32 MMAs per product, so the tensor pipe executes "
+                           "3x the algorithmic FLOPs at half the bf16 rate; the step is a chain of 12 dependent launches of "
+                           "5-12 us, i.e. latency-bound; fraction is algorithmic FLOPs against the bf16 tensor peak as "
+                           "SURVEY 8(d) defines it"),
         roofline_replay=dict(kernel="rb_gather_* (sample_batch)", bound="hbm", achieved=gather_gbs, peak=peaks["hbm_gbs"],
                              unit="GB/s", frac=gather_gbs / peaks["hbm_gbs"], traffic=None,
                              bytes_per_transition=2 * row_bytes, transitions_per_launch=n_rows,

@@ -893,6 +893,12 @@ int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity,
   return 0;
 }
 
+int ddrl_rb_note_samples(ddrl_rb_t rb, int64_t n_batches) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_note_samples: NULL handle");
+  rb->sample_times += n_batches;
+  return 0;
+}
+
 int ddrl_rb_layout(ddrl_rb_t rb, int* obs_dim, int* act_dim, int* row_floats, void** d_ring) {
   if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_layout: NULL handle");
   if (obs_dim) *obs_dim = rb->D;

@@ -41,6 +41,12 @@ struct StepDyn {   // per-step values: by-value argument of the prologue kernel,
   int t_pi, t_q;
   float lr_pi, lr_q;
   unsigned long long noise_counter;
+  // fused sample -> update (ddrl_sac_step_from_buffer): the batch is gathered straight from the replay ring by the
+  // prologue, with the same Philox index stream as ddrl_rb_sample (philox_index(row, seed, counter, stream, size))
+  const float* ring;                               // NULL: external batch arrays above
+  int ring_row_f;
+  unsigned int ring_stream;
+  unsigned long long ring_seed, ring_counter, ring_size;
 };
 struct StepState {  // persistent
   StepDyn dyn;
@@ -77,7 +83,29 @@ __device__ __forceinline__ void d_prologue(int vb, int vgrid, StepState* st, con
   }
   const int64_t tid = (int64_t)vb * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)vgrid * blockDim.x;
-  if (d.obs1 && xa.xa_d) {
+  if (d.ring) {
+    // one warp per sampled row: packed ring row [obs1 | obs2 | acts | rew | done] -> the learner's input buffers
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = tid >> 5, nwarps = nthr >> 5;
+    for (int64_t r = warp0; r < B; r += nwarps) {
+      const int64_t idx = philox_index((uint64_t)r, d.ring_seed, d.ring_counter, d.ring_stream, d.ring_size);
+      const float* src = d.ring + (size_t)idx * d.ring_row_f;
+      for (int c = lane; c < 2 * D + A + 2; c += 32) {
+        const float v = src[c];
+        if (c < D) {
+          if (xa.xa_d) { put_split(xa.xa_d, xa.plane, (size_t)r * xa.pitch + c, v); put_split(xa.xa_f, xa.plane, (size_t)r * xa.pitch + c, v); }
+          else X[(size_t)r * D + c] = v;
+        } else if (c < 2 * D) {
+          if (xa.xa_d) put_split(xa.xa_g, xa.plane, (size_t)r * xa.pitch + (c - D), v);
+          else X2[(size_t)r * D + (c - D)] = v;
+        } else if (c < 2 * D + A) {
+          if (xa.xa_d) put_split(xa.xa_d, xa.plane, (size_t)r * xa.pitch + D + (c - 2 * D), v);
+          else ACT[(size_t)r * A + (c - 2 * D)] = v;
+        } else if (c == 2 * D + A) R[r] = v;
+        else DN[r] = v;
+      }
+    }
+  } else if (d.obs1 && xa.xa_d) {
     for (int64_t i = tid; i < (int64_t)B * D; i += nthr) {
       const int64_t r = i / D, c = i - r * D;
       const size_t o = (size_t)r * xa.pitch + c;
@@ -827,11 +855,15 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
   const int world = pc.world;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < P; i += stride) {
-    float4 g = ld_volatile_f4(pc.buf[0] + slot + i);
-    for (int r = 1; r < world; ++r) {
-      const float4 q = ld_volatile_f4(pc.buf[r] + slot + i);
-      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
-    }
+    // all peers' loads are issued before the first add: one NVLink round trip, not `world` of them
+    float4 q[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) q[r] = ld_volatile_f4(pc.buf[r] + slot + i);
+    float4 g = q[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+      if (r < world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
     const float gv[4] = {g.x * gs, g.y * gs, g.z * gs, g.w * gs};
     const float4 m4 = *reinterpret_cast<const float4*>(Mo + i), v4 = *reinterpret_cast<const float4*>(Vo + i);
     const float4 w4 = *reinterpret_cast<const float4*>(W + i), t4 = *reinterpret_cast<const float4*>(Wt + i);
@@ -1013,8 +1045,8 @@ struct Plan {
   int B = 0, S = 1;
   std::vector<Group> fwd1, fwd2, bwd;  // see build_plan
   std::vector<std::vector<Group>> stages;  // ordered stages; element-wise kernels sit between them
-  cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr;
-  int64_t kernels[3] = {0, 0, 0};  // kernels inside each captured graph (for the launch counter)
+  cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr, exec_dp = nullptr;
+  int64_t kernels[4] = {0, 0, 0, 0};  // kernels inside each captured graph (for the launch counter)
   ColsumGroup colsum[8] = {};      // tensor-core mode: bias-gradient column sums per stage (side stream)
   int colsum_chunks[8] = {};
   SkinnyGroup skinny[8] = {};      // tensor-core mode: skinny weight gradients per stage (side stream)
@@ -1548,7 +1580,7 @@ int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s) {
   return 0;
 }
 
-enum { MODE_FULL = 0, MODE_GRADS = 1, MODE_APPLY = 2 };
+enum { MODE_FULL = 0, MODE_GRADS = 1, MODE_APPLY = 2, MODE_DP = 3 };
 
 int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
   int rc = 0;
@@ -1560,11 +1592,16 @@ int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
     if ((rc = enqueue_grads(h, pl, s))) return rc;
     return enqueue_reduce(h, pl, s);
   }
+  if (mode == MODE_DP) {   // fused data-parallel step: gradients -> exchange buffer -> peer all-reduce + optimiser
+    if ((rc = enqueue_grads(h, pl, s))) return rc;
+    if ((rc = enqueue_reduce(h, pl, s))) return rc;
+  }
   return enqueue_apply(h, 1, h->G, s);
 }
 
 int run_mode(ddrl_sac* h, Plan& pl, int mode, cudaStream_t s) {
-  cudaGraphExec_t* slot = mode == MODE_FULL ? &pl.exec_full : mode == MODE_GRADS ? &pl.exec_grads : &pl.exec_apply;
+  cudaGraphExec_t* slot = mode == MODE_FULL ? &pl.exec_full : mode == MODE_GRADS ? &pl.exec_grads
+                          : mode == MODE_APPLY ? &pl.exec_apply : &pl.exec_dp;
   if (!h->use_graph) return enqueue_mode(h, pl, mode, s);
   if (!*slot) {
     cudaGraph_t graph = nullptr;
@@ -1726,7 +1763,7 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
   cudaDeviceSynchronize();
   for (auto& kv : h->plans) {
     Plan& pl = kv.second;
-    for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply}) if (ex) cudaGraphExecDestroy(ex);
+    for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply, pl.exec_dp}) if (ex) cudaGraphExecDestroy(ex);
   }
   for (int r = 0; r < 8; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->pc.buf[r]);
   if (h->comm) cudaFree(h->comm);
@@ -1765,13 +1802,19 @@ int ddrl_sac_get_weights(ddrl_sac_t h, float* d_flat, int which, void* stream) {
   return 0;
 }
 
+struct RingSrc {   // fused sample -> update: where the prologue gathers the batch from
+  const float* ring = nullptr;
+  int row_f = 0;
+  uint32_t stream = 0;
+  uint64_t seed = 0, counter = 0, size = 0;
+};
 static int step_common(ddrl_sac_t h, int mode, const float* d_obs1, const float* d_obs2, const float* d_acts,
                        const float* d_rews, const float* d_done, int batch, const float* d_noise, uint64_t seed,
                        float grad_scale, float* d_out_scalars, float* d_out_q1, float* d_out_q2, float* d_out_logp,
-                       void* stream, const char* who) {
+                       void* stream, const char* who, const RingSrc* rs = nullptr) {
   if (!h) return fail(DDRL_EINVAL, "%s: NULL handle", who);
   if (batch < 1 || batch > h->maxB) return fail(DDRL_EINVAL, "%s: batch=%d not in [1, %d]", who, batch, h->maxB);
-  if (mode != MODE_APPLY && (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done))
+  if (mode != MODE_APPLY && !rs && (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done))
     return fail(DDRL_EINVAL, "%s: NULL batch array", who);
   DeviceGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
@@ -1784,6 +1827,10 @@ static int step_common(ddrl_sac_t h, int mode, const float* d_obs1, const float*
     dyn.noise = d_noise;
     dyn.out_scalars = d_out_scalars; dyn.out_q1 = d_out_q1; dyn.out_q2 = d_out_q2; dyn.out_logp = d_out_logp;
     dyn.seed = seed; dyn.grad_scale = grad_scale;
+    if (rs) {
+      dyn.ring = rs->ring; dyn.ring_row_f = rs->row_f; dyn.ring_stream = rs->stream;
+      dyn.ring_seed = rs->seed; dyn.ring_counter = rs->counter; dyn.ring_size = rs->size;
+    }
     h->t_host += 1;
     const double t = (double)h->t_host;
     dyn.t_pi = dyn.t_q = h->t_host;
@@ -1809,6 +1856,38 @@ int ddrl_sac_compute_grads(ddrl_sac_t h, const float* d_obs1, const float* d_obs
                            void* stream) {
   return step_common(h, MODE_GRADS, d_obs1, d_obs2, d_acts, d_rews, d_done, batch, d_noise, seed, grad_scale,
                      d_out_scalars, d_out_q1, d_out_q2, d_out_logp, stream, "ddrl_sac_compute_grads");
+}
+
+int ddrl_sac_step_dp(ddrl_sac_t h, const float* d_obs1, const float* d_obs2, const float* d_acts, const float* d_rews,
+                     const float* d_done, int batch, const float* d_noise, uint64_t seed, float grad_scale,
+                     float* d_out_scalars, float* d_out_q1, float* d_out_q2, float* d_out_logp, void* stream) {
+  if (h && h->pc.world < 2) return fail(DDRL_ESTATE, "ddrl_sac_step_dp: no peers attached (ddrl_sac_comm_attach)");
+  return step_common(h, MODE_DP, d_obs1, d_obs2, d_acts, d_rews, d_done, batch, d_noise, seed, grad_scale, d_out_scalars,
+                     d_out_q1, d_out_q2, d_out_logp, stream, "ddrl_sac_step_dp");
+}
+
+int ddrl_sac_step_from_buffer(ddrl_sac_t h, ddrl_rb_t rb, int batch, uint64_t rb_seed, uint64_t rb_counter,
+                              uint32_t rb_stream, const float* d_noise, uint64_t seed, float* d_out_scalars, float* d_out_q1,
+                              float* d_out_q2, float* d_out_logp, void* stream) {
+  if (!h || !rb) return fail(DDRL_EINVAL, "ddrl_sac_step_from_buffer: NULL handle");
+  int D = 0, A = 0, row_f = 0;
+  void* ring = nullptr;
+  int rc = ddrl_rb_layout(rb, &D, &A, &row_f, &ring);
+  if (rc) return rc;
+  if (D != h->D || A != h->A)
+    return fail(DDRL_EINVAL, "ddrl_sac_step_from_buffer: buffer rows are (obs %d, act %d), learner expects (%d, %d)", D, A, h->D, h->A);
+  int64_t ptr = 0, size = 0, cap = 0, steps = 0, samples = 0;
+  if ((rc = ddrl_rb_counts(rb, &ptr, &size, &cap, &steps, &samples))) return rc;
+  if (size == 0) return fail(DDRL_EEMPTY, "ddrl_sac_step_from_buffer: ring is empty (the reference raises ValueError: high <= 0)");
+  RingSrc rs;
+  rs.ring = (const float*)ring; rs.row_f = row_f; rs.stream = rb_stream; rs.seed = rb_seed; rs.counter = rb_counter;
+  rs.size = (uint64_t)size;
+  const int mode = h->pc.world > 1 ? MODE_DP : MODE_FULL;
+  const float gs = h->pc.world > 1 ? 1.0f / (float)h->pc.world : 1.0f;
+  rc = step_common(h, mode, nullptr, nullptr, nullptr, nullptr, nullptr, batch, d_noise, seed, gs, d_out_scalars, d_out_q1,
+                   d_out_q2, d_out_logp, stream, "ddrl_sac_step_from_buffer", &rs);
+  if (rc) return rc;
+  return ddrl_rb_note_samples(rb, 1);
 }
 
 int ddrl_sac_grad_buffer(ddrl_sac_t h, float** d_grads, int64_t* count, float** d_alpha_stat) {
@@ -1865,7 +1944,7 @@ int ddrl_sac_comm_attach(ddrl_sac_t h, int world, int rank, const void* h_handle
   h->pc.world = world; h->pc.rank = rank;
   // graphs captured before the attach hold the single-GPU kernels
   for (auto& kv : h->plans)
-    for (cudaGraphExec_t* ex : {&kv.second.exec_full, &kv.second.exec_grads, &kv.second.exec_apply})
+    for (cudaGraphExec_t* ex : {&kv.second.exec_full, &kv.second.exec_grads, &kv.second.exec_apply, &kv.second.exec_dp})
       if (*ex) { cudaGraphExecDestroy(*ex); *ex = nullptr; }
   return 0;
 }

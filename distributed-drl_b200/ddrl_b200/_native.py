@@ -56,6 +56,9 @@ SIGNATURES = {
     "ddrl_sac_compute_grads": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _u64, _f, _vp, _vp, _vp, _vp, _vp]),
     "ddrl_sac_grad_buffer": (_int, [_vp, C.POINTER(_vp), _pi64, C.POINTER(_vp)]),
     "ddrl_sac_apply_grads": (_int, [_vp, _int, _vp]),
+    "ddrl_sac_step_dp": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _u64, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_sac_step_from_buffer": (_int, [_vp, _vp, _int, _u64, _u64, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_rb_note_samples": (_int, [_vp, _i64]),
     "ddrl_sac_comm_export": (_int, [_vp, _vp]),
     "ddrl_sac_comm_attach": (_int, [_vp, _int, _int, _vp]),
     "ddrl_sac_comm_error": (_int, [_vp, _pint]),

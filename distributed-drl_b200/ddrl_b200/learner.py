@@ -340,15 +340,16 @@ class Learner(object):
             N.check(self._lib.ddrl_sac_apply_grads(self._h, B, sp))
         elif world == 1:
             N.check(self._lib.ddrl_sac_step(self._h, *args, B, nzp, self.seed, *outs, sp))
+        elif self._fused:
+            # gradients are exchanged over NVLink peer memory inside the optimiser kernel: one graph, no NCCL call
+            N.check(self._lib.ddrl_sac_step_dp(self._h, *args, B, nzp, self.seed, 1.0 / world, *outs, sp))
         else:
             import torch.distributed as dist
             N.check(self._lib.ddrl_sac_compute_grads(self._h, *args, B, nzp, self.seed, 1.0 / world, *outs, sp))
-            if not self._fused:
-                dist.all_reduce(self._grad, op=dist.ReduceOp.SUM, group=self._pg)
-                if self.auto_alpha:
-                    dist.all_reduce(self._alpha_stat, op=dist.ReduceOp.SUM, group=self._pg)
-                    self._alpha_stat.div_(world)
-            # fused mode: apply_grads exchanges the gradients over NVLink peer memory inside the optimiser kernel
+            dist.all_reduce(self._grad, op=dist.ReduceOp.SUM, group=self._pg)
+            if self.auto_alpha:
+                dist.all_reduce(self._alpha_stat, op=dist.ReduceOp.SUM, group=self._pg)
+                self._alpha_stat.div_(world)
             N.check(self._lib.ddrl_sac_apply_grads(self._h, B, sp))
         for t in (x, x2, a, r, d):
             t.record_stream(s)
@@ -359,10 +360,43 @@ class Learner(object):
             s.synchronize()
         return o
 
-    def train_from_buffer(self, replay_buffer, batch_size):
-        """sample_batch + train without the batch leaving the GPU (example/model.py:92-101's
-        Model.train(replay_buffer, args) shape)."""
-        return self.train(replay_buffer.sample_batch(batch_size, device=True))
+    def train_from_buffer(self, replay_buffer, batch_size, noise=None, sync_outputs=False):
+        """`batch = replay_buffer.sample_batch(B); agent.train(batch)` as ONE native call (example/model.py:92-101's
+        Model.train(replay_buffer, args) shape): the step's first kernel gathers the batch straight from the ring with
+        the buffer's own Philox index stream, so the rows are exactly those sample_batch(B) would have returned at this
+        point and the batch never exists as separate arrays.  Falls back to sample_batch + train for buffers that
+        draw indices with numpy, live on another device, or are sharded wrappers."""
+        rb = getattr(replay_buffer, "local", replay_buffer)
+        B = int(batch_size)
+        world = self._world()
+        if (getattr(rb, "index_source", None) != "philox" or getattr(rb, "device", None) != self.device
+                or (world > 1 and not self._fused) or getattr(rb, "_scalar_act", False)):
+            return self.train(replay_buffer.sample_batch(B, device=True), noise=noise, sync_outputs=sync_outputs)
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch} (pass max_batch= to Learner)")
+        if rb.size == 0:
+            raise ValueError("high <= 0")        # what the reference's np.random.randint(0, 0, ...) raises
+        if self._outs is None or self._outs["q1"].shape[0] != B:
+            f = dict(dtype=torch.float32, device=self._dev)
+            self._outs = dict(scalars=torch.zeros(4, **f), q1=torch.empty(B, **f), q2=torch.empty(B, **f),
+                              logp_pi=torch.empty(B, **f))
+        o = self._outs
+        nz = None
+        if noise is not None:
+            nz = torch.as_tensor(noise, dtype=torch.float32).to(self._dev).contiguous()
+            assert tuple(nz.shape) == (3, B, self.act_dim)
+        s = self._stream()
+        outs = [C.c_void_p(o[k].data_ptr()) for k in ("scalars", "q1", "q2", "logp_pi")]
+        N.check(self._lib.ddrl_sac_step_from_buffer(
+            self._h, rb.native_handle, B, rb._philox_seed(), rb._counter, rb._rng_stream,
+            C.c_void_p(nz.data_ptr()) if nz is not None else None, self.seed, *outs, C.c_void_p(s.cuda_stream)))
+        rb._counter += 1
+        if nz is not None:
+            nz.record_stream(s)
+        self.steps += 1
+        if sync_outputs:
+            s.synchronize()
+        return o
 
     def state(self):
         t_pi, t_q, t_a, la = C.c_int(), C.c_int(), C.c_int(), C.c_float()

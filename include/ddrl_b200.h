@@ -143,6 +143,8 @@ int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity,
 /* geometry of the packed row: floats per padded row, device pointer of the ring (for zero-copy
  * consumers such as the fused sample->update step).  Any out may be NULL. */
 int ddrl_rb_layout(ddrl_rb_t rb, int* obs_dim, int* act_dim, int* row_floats, void** d_ring);
+/* sample_times += n_batches for a consumer that gathered from the ring itself (the fused sample->update step) */
+int ddrl_rb_note_samples(ddrl_rb_t rb, int64_t n_batches);
 
 /* ring <-> the reference's five arrays ([capacity,D],[capacity,D],[capacity,A],[capacity],[capacity]
  * f32, device memory): the on-disk format of algos/dqn/train.py:82-108 (save/load) goes through
@@ -203,6 +205,14 @@ int ddrl_sac_compute_grads(ddrl_sac_t sac, const float* d_obs1, const float* d_o
                            float* d_out_scalars, float* d_out_q1, float* d_out_q2,
                            float* d_out_logp, void* stream);
 int ddrl_sac_grad_buffer(ddrl_sac_t sac, float** d_grads, int64_t* count, float** d_alpha_stat);
+/* Fused `batch = replay_buffer.sample_batch(B); agent.train(batch)` (algos/sac1/sac1.py:146-148; example/model.py:92-101
+ * Model.train(replay_buffer, args)): the step's first kernel gathers the batch straight from the ring, drawing row i as
+ * philox_index(i, rb_seed, rb_counter, rb_stream, size) — the same rows ddrl_rb_sample(rb, batch, 1, NULL, rb_seed,
+ * rb_counter, rb_stream, ...) would return — so the sampled batch never makes a round trip through HBM arrays.
+ * Uses the fused data-parallel exchange when peers are attached.  Counts as one sample_batch call. */
+int ddrl_sac_step_from_buffer(ddrl_sac_t sac, ddrl_rb_t rb, int batch, uint64_t rb_seed, uint64_t rb_counter,
+                              uint32_t rb_stream, const float* d_noise, uint64_t seed, float* d_out_scalars,
+                              float* d_out_q1, float* d_out_q2, float* d_out_logp, void* stream);
 int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
 /* Fused data-parallel mode (one process per GPU of one node, 2..8 ranks; replaces the NCCL all-reduce between
  * compute_grads and apply_grads, i.e. what `north_star` asks of algos/sac1's multi-learner setup, sac1.py:273-276):
@@ -213,6 +223,11 @@ int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
  * bit-identical), scales by grad_scale and applies Adam + polyak.  All ranks must call the step functions in
  * lockstep.  ddrl_sac_comm_error reports a peer time-out (a rank died) observed by the kernel. */
 int ddrl_sac_comm_export(ddrl_sac_t sac, void* h_handle64);
+/* compute_grads + apply_grads of the fused data-parallel mode as ONE captured graph (same arguments as compute_grads) */
+int ddrl_sac_step_dp(ddrl_sac_t sac, const float* d_obs1, const float* d_obs2, const float* d_acts,
+                     const float* d_rews, const float* d_done, int batch, const float* d_noise, uint64_t seed,
+                     float grad_scale, float* d_out_scalars, float* d_out_q1, float* d_out_q2, float* d_out_logp,
+                     void* stream);
 int ddrl_sac_comm_attach(ddrl_sac_t sac, int world, int rank, const void* h_handles);
 int ddrl_sac_comm_error(ddrl_sac_t sac, int* out_error);
 /* Actor.get_action(o, deterministic) (algos/sac1/actor_learner.py:195-197) for n observations at once:

@@ -203,3 +203,32 @@ def test_default_init_regime_against_float32_oracle(L):
     sc = got["scalars"].cpu().numpy()
     for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
         assert abs(sc[i] - float(want[k])) <= 2e-3 * abs(float(want[k])), k
+
+
+def test_train_from_buffer_equals_sample_then_train(L):
+    """The fused sample->update call gathers exactly the rows sample_batch() would return (same Philox stream) and
+    produces bit-identical losses, Q values and updated weights."""
+    from ddrl_b200 import ReplayBuffer
+    D, A, hidden, B, n = 24, 4, (256, 256), 512, 5000
+    params = conditioned_params(D, A, hidden, seed=11)
+    g = np.random.Generator(np.random.PCG64(12))
+    rows = [g.standard_normal((n, D), dtype=np.float32), g.uniform(-1, 1, (n, A)).astype(np.float32),
+            g.standard_normal(n, dtype=np.float32), g.standard_normal((n, D), dtype=np.float32),
+            (g.random(n) < 0.05).astype(np.float32)]
+    res = []
+    for fused in (False, True):
+        rb = ReplayBuffer(D, A, 8192, seed=77, rng_stream=3)
+        rb.store_batch(*rows)
+        learner = L(make_opt(D, A, hidden, B), "learner")
+        learner.set_weights(list(params), list(params.values()))
+        for it in range(3):
+            noise = np.random.Generator(np.random.PCG64(100 + it)).standard_normal((3, B, A), dtype=np.float32)
+            if fused:
+                out = learner.train_from_buffer(rb, B, noise=noise, sync_outputs=True)
+            else:
+                out = learner.train(rb.sample_batch(B, device=True), noise=noise, sync_outputs=True)
+        res.append((out["scalars"].cpu().numpy().copy(), out["q1"].cpu().numpy().copy(),
+                    learner.get_flat_weights("main").cpu().numpy(), rb.get_counts()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
+    assert res[0][3] == res[1][3]          # sample_times / steps / size advance identically
