@@ -73,6 +73,77 @@ __device__ __forceinline__ void put_split(float* hi_plane, long long plane, size
   hi_plane[idx] = hi;
   hi_plane[plane + idx] = lo;
 }
+// Narrow first layers (K = D or D + A <= 32) are not worth a tensor-core launch of their own (a 1-k-block tcgen05
+// stage costs ~9 us of fixed latency): they are computed with FFMA inside the kernels that already hold their
+// inputs — the five data passes here in the prologue, the three policy-action Q passes in the policy-head kernel.
+// One thread per output column keeps its weight column in registers and walks the CTA's rows; outputs go out as the
+// hi/lo planes + relu bit masks the second-layer tcgen05 stage expects.
+constexpr int FUSE_MAXK = 32;
+constexpr int FUSE_RB = 8;          // rows per CTA in the policy-head kernel (= ROW_WARPS)
+constexpr int FUSE_PRB = 16;        // rows per work item in the prologue
+struct L1Fuse {
+  int on, h1, ld1, ldbits;
+  long long lo1;
+  const float* W[5];                // [K + 1, h1] weight blocks (fp32 master copies; pass 2 = target policy)
+  float* H1[5];
+  uint32_t* bits[5];
+};
+__device__ __forceinline__ void fused_dense_relu_store(float acc, int row, int n, int ld1, long long lo1, int ldbits, float* H1,
+                                                       uint32_t* bits) {
+  const unsigned int m = __ballot_sync(0xffffffffu, acc > 0.0f);     // 32 consecutive columns per warp
+  if ((threadIdx.x & 31) == 0) bits[(size_t)row * ldbits + (n >> 5)] = m;
+  put_split(H1, lo1, (size_t)row * ld1 + n, fmaxf(acc, 0.0f));
+}
+// CTA-level dense layer for FUSE_RB rows held in shared memory: thread = output column (weight column in registers,
+// one coalesced L2 round trip), loop over the rows.  `in` rows are zero padded to FUSE_MAXK.
+template <int RB>
+__device__ __forceinline__ void cta_dense_rows(const float (*in)[FUSE_MAXK], int nrows, int row0, int K, const float* __restrict__ W,
+                                               const L1Fuse& f, float* H1, uint32_t* bits) {
+  for (int n = threadIdx.x; n < f.h1; n += blockDim.x) {       // h1 % 32 == 0: whole warps
+    float w[FUSE_MAXK];
+#pragma unroll
+    for (int k = 0; k < FUSE_MAXK; ++k) w[k] = k < K ? W[(size_t)k * f.h1 + n] : 0.0f;
+    const float bias = W[(size_t)K * f.h1 + n];
+#pragma unroll 2
+    for (int r = 0; r < RB; ++r) {
+      if (r >= nrows) break;                                   // block-uniform
+      float a0 = bias, a1 = 0.0f;
+#pragma unroll
+      for (int k = 0; k < FUSE_MAXK; k += 2) { a0 = fmaf(in[r][k], w[k], a0); a1 = fmaf(in[r][k + 1], w[k + 1], a1); }
+      fused_dense_relu_store(a0 + a1, row0 + r, n, f.ld1, f.lo1, f.ldbits, H1, bits);
+    }
+  }
+}
+// work item = (block of FUSE_RB rows, pass): 5 * ceil(B / FUSE_RB) items dealt round-robin to the CTAs
+__device__ __forceinline__ void d_prologue_l1(int vb, int vgrid, const StepDyn& d, const L1Fuse& f, int B, int D, int A) {
+  __shared__ float s_in[FUSE_PRB][FUSE_MAXK];
+  __shared__ long long s_idx[FUSE_PRB];
+  const int tid = threadIdx.x;
+  const int nblk = (B + FUSE_PRB - 1) / FUSE_PRB;
+  for (int item = vb; item < 5 * nblk; item += vgrid) {
+    const int p = item / nblk, r0 = (item - p * nblk) * FUSE_PRB;
+    const int K = p < 3 ? D : D + A;
+    const int nrows = min(FUSE_PRB, B - r0);
+    __syncthreads();
+    if (d.ring && tid < nrows)
+      s_idx[tid] = philox_index((uint64_t)(r0 + tid), d.ring_seed, d.ring_counter, d.ring_stream, d.ring_size);
+    if (d.ring) __syncthreads();
+    for (int i = tid; i < FUSE_PRB * FUSE_MAXK; i += blockDim.x) {
+      const int r = i / FUSE_MAXK, k = i - r * FUSE_MAXK, row = r0 + r;
+      float v = 0.0f;
+      if (r < nrows && k < K) {
+        // pass 0: x   passes 1, 2: x2   passes 3, 4: [x | a]       (ring row = [obs1 | obs2 | acts | rew | done])
+        const int c = (p == 1 || p == 2) ? D + k : (k < D ? k : 2 * D + (k - D));
+        if (d.ring) v = d.ring[(size_t)s_idx[r] * d.ring_row_f + c];
+        else v = c < D ? d.obs1[(size_t)row * D + c] : c < 2 * D ? d.obs2[(size_t)row * D + (c - D)] : d.acts[(size_t)row * A + (c - 2 * D)];
+      }
+      s_in[r][k] = v;
+    }
+    __syncthreads();
+    cta_dense_rows<FUSE_PRB>(s_in, nrows, r0, K, f.W[p], f, f.H1[p], f.bits[p]);
+  }
+}
+
 __device__ __forceinline__ void d_prologue(int vb, int vgrid, StepState* st, const StepDyn& d, int B, int D, int A,
                                            float* X, float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
   if (vb == 0 && threadIdx.x == 0) {
@@ -150,10 +221,12 @@ __device__ __forceinline__ void d_prologue(int vb, int vgrid, StepState* st, con
   }
 }
 __global__ void __launch_bounds__(256) k_prologue(StepState* st, const __grid_constant__ StepDyn dyn, int B, int D, int A, float* X,
-                                                  float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
+                                                  float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa,
+                                                  const __grid_constant__ L1Fuse l1) {
   pdl_trigger();
   pdl_wait();
   d_prologue(blockIdx.x, gridDim.x, st, dyn, B, D, A, X, X2, ACT, R, DN, NOISE, xa);
+  if (l1.on) d_prologue_l1(blockIdx.x, gridDim.x, dyn, l1, B, D, A);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,50 +464,84 @@ __device__ __forceinline__ void heads_row_dots(const float* __restrict__ x, int 
 __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_rows(
     int B, int A, int h2, int ldh, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
-    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D) {
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D,
+    const __grid_constant__ L1Fuse ql1) {
   __shared__ float s_out[ROW_WARPS][16];
+  __shared__ float s_in[ROW_WARPS][FUSE_MAXK];
+  static_assert(ROW_WARPS == FUSE_RB, "the fused Q first layer walks one row per warp of the CTA");
   pdl_trigger();
   pdl_wait();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * ROW_WARPS + w;
-  if (g >= 3 * B) return;
-  const int pass = g / B, row = g % B;
-  const float* x = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
-  const float* W = pass == 2 ? Whead_t : Whead;
-  switch (ldh) {
-    case 4: heads_row_dots<1>(x, h2, W, 2 * A, s_out[w], lane); break;
-    case 8: heads_row_dots<2>(x, h2, W, 2 * A, s_out[w], lane); break;
-    case 12: heads_row_dots<3>(x, h2, W, 2 * A, s_out[w], lane); break;
-    default: heads_row_dots<4>(x, h2, W, 2 * A, s_out[w], lane); break;
-  }
-  const float* eps = NOISE + ((size_t)pass * B + row) * A;
-  float pre = 0.0f, sq = 0.0f;
-  if (lane < A) {
-    const PolEl e = policy_elem(s_out[w][lane], s_out[w][A + lane], eps[lane]);
-    pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
-    sq = logf(__fadd_rn(e.clipped, 1e-6f));
-    const float act = __fmul_rn(e.pi, act_scale);
+  const bool live = g < 3 * B;
+  const int pass = live ? g / B : 0, row = live ? g % B : 0;
+  if (live) {
+    const float* x = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
+    const float* W = pass == 2 ? Whead_t : Whead;
+    switch (ldh) {
+      case 4: heads_row_dots<1>(x, h2, W, 2 * A, s_out[w], lane); break;
+      case 8: heads_row_dots<2>(x, h2, W, 2 * A, s_out[w], lane); break;
+      case 12: heads_row_dots<3>(x, h2, W, 2 * A, s_out[w], lane); break;
+      default: heads_row_dots<4>(x, h2, W, 2 * A, s_out[w], lane); break;
+    }
+    const float* eps = NOISE + ((size_t)pass * B + row) * A;
+    float pre = 0.0f, sq = 0.0f, act_val = 0.0f;
+    if (lane < A) {
+      const PolEl e = policy_elem(s_out[w][lane], s_out[w][A + lane], eps[lane]);
+      pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
+      sq = logf(__fadd_rn(e.clipped, 1e-6f));
+      act_val = __fmul_rn(e.pi, act_scale);
+      if (pass == 0) {
+        A1[(size_t)row * A + lane] = act_val;
+        if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + lane, act_val);
+      } else if (pass == 2) {
+        A3[(size_t)row * A + lane] = act_val;
+        if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + lane, act_val);
+      }
+    }
+    // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
+    float gauss = 0.0f, squash = 0.0f;
+    for (int t = 0; t < A; ++t) {
+      gauss = __fadd_rn(gauss, __shfl_sync(0xffffffffu, pre, t));
+      squash = __fadd_rn(squash, __shfl_sync(0xffffffffu, sq, t));
+    }
     if (pass == 0) {
-      A1[(size_t)row * A + lane] = act;
-      if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + lane, act);
-    } else if (pass == 2) {
-      A3[(size_t)row * A + lane] = act;
-      if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + lane, act);
+      if (lane < 2 * A) HD[(size_t)row * 2 * A + lane] = s_out[w][lane];
+      if (lane == 0) LOGP1[row] = __fsub_rn(gauss, squash);
+    } else if (pass == 1 && lane == 0) {
+      LOGP2[row] = __fsub_rn(gauss, squash);
+    }
+    if (ql1.on && pass != 1) {
+      // input row of the fused policy-action Q first layer: exact hi + lo of the observation planes, then the
+      // action this warp has just drawn (2A <= 16 on this path), zero padded to FUSE_MAXK
+      const float* plane = pass == 0 ? xa.xa_f : xa.xa_g;
+      float v = 0.0f;
+      if (lane < D) { const size_t o = (size_t)row * xa.pitch + lane; v = plane[o] + plane[xa.plane + o]; }
+      s_in[w][lane] = v;
+      __syncwarp();
+      if (lane < A) s_in[w][D + lane] = act_val;
+    }
+  } else if (ql1.on) {
+    s_in[w][lane] = 0.0f;
+  }
+  if (ql1.on) {
+    // f = Q1([x|a1]) for pass-0 CTAs; g = Q1_targ([x2|a3]) and h = Q2_targ([x2|a3]) for pass-2 CTAs.  The host fuses only
+    // when B % ROW_WARPS == 0, so a CTA's rows belong to one pass and are consecutive: the weight column read by a
+    // thread serves all 8 rows.
+    __syncthreads();
+    const int g0 = blockIdx.x * ROW_WARPS;
+    if (g0 < 3 * B) {
+      const int cpass = g0 / B, row0 = g0 - cpass * B;
+      const int nrows = min(ROW_WARPS, B - row0);
+      if (cpass == 0) cta_dense_rows<FUSE_RB>(s_in, nrows, row0, D + A, ql1.W[0], ql1, ql1.H1[0], ql1.bits[0]);
+      else if (cpass == 2) {
+        cta_dense_rows<FUSE_RB>(s_in, nrows, row0, D + A, ql1.W[1], ql1, ql1.H1[1], ql1.bits[1]);
+        cta_dense_rows<FUSE_RB>(s_in, nrows, row0, D + A, ql1.W[2], ql1, ql1.H1[2], ql1.bits[2]);
+      }
     }
   }
-  // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
-  float gauss = 0.0f, squash = 0.0f;
-  for (int t = 0; t < A; ++t) {
-    gauss = __fadd_rn(gauss, __shfl_sync(0xffffffffu, pre, t));
-    squash = __fadd_rn(squash, __shfl_sync(0xffffffffu, sq, t));
-  }
-  if (pass == 0) {
-    if (lane < 2 * A) HD[(size_t)row * 2 * A + lane] = s_out[w][lane];
-    if (lane == 0) LOGP1[row] = __fsub_rn(gauss, squash);
-  } else if (pass == 1 && lane == 0) {
-    LOGP2[row] = __fsub_rn(gauss, squash);
-  }
 }
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc))));
 }
@@ -1047,6 +1154,7 @@ struct Plan {
   std::vector<std::vector<Group>> stages;  // ordered stages; element-wise kernels sit between them
   cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr, exec_dp = nullptr;
   int64_t kernels[4] = {0, 0, 0, 0};  // kernels inside each captured graph (for the launch counter)
+  bool fused = false;              // narrow first layers run inside the prologue / policy-head kernels (no L1 / QL1 stage)
   ColsumGroup colsum[8] = {};      // tensor-core mode: bias-gradient column sums per stage (side stream)
   int colsum_chunks[8] = {};
   SkinnyGroup skinny[8] = {};      // tensor-core mode: skinny weight gradients per stage (side stream)
@@ -1079,6 +1187,8 @@ struct ddrl_sac {
   int ld1 = 0, ld2 = 0, ldx = 0, ldh = 0;   // ldh: head block row pitch
   long long lo1 = 0, lo2 = 0, lox = 0;
   float* XA[3] = {};                    // [x|a], [x|a1], [x2|a3] split planes
+  bool fuse_l1_force = false;           // DDRL_FUSE_L1=2: fuse at every batch size
+  bool fuse_l1 = false;                 // narrow first layers fused into the prologue / policy-head kernels (FFMA)
   uint32_t* H1bits[8] = {};             // relu'(H1) of each pass as bit masks [maxB][ldbits] (written by the L1 epilogue)
   int ldbits = 0;
   float *Wsp = nullptr, *Wtsp = nullptr;  // split planes of the main / target weight blocks (SplitMap)
@@ -1398,17 +1508,24 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
     sg.B = B; sg.kps = kps; sg.split_stride = h->P;
   };
   // ---- forward: policies (a: main@x, b: main@x2, c: target@x2) and the data-action Q passes (d, e)
-  fwd(ST_L1, xa(0, D), PI1, false, h->H1[a], h->H1[a] + h->lo1, h->ld1, h->H1bits[a]);
-  fwd(ST_L1, xa(2, D), PI1, false, h->H1[b], h->H1[b] + h->lo1, h->ld1);
-  fwd(ST_L1, xa(2, D), PI1, true, h->H1[c], h->H1[c] + h->lo1, h->ld1);
-  fwd(ST_L1, xa(0, D + A), Q1_0, false, h->H1[d], h->H1[d] + h->lo1, h->ld1, h->H1bits[d]);
-  fwd(ST_L1, xa(0, D + A), Q2_0, false, h->H1[e], h->H1[e] + h->lo1, h->ld1, h->H1bits[e]);
+  // a CTA of the policy-head kernel must hold rows of one pass; measured: 92 vs 100 us per update at B = 256, no gain at
+  // B = 1024 (the FFMA layers then cost what the two tensor-core stages did), so large batches keep the tcgen05 stages
+  pl.fused = h->fuse_l1 && B % ROW_WARPS == 0 && (B <= 512 || h->fuse_l1_force);
+  if (!pl.fused) {   // otherwise computed with FFMA inside the prologue (l1_fuse_args)
+    fwd(ST_L1, xa(0, D), PI1, false, h->H1[a], h->H1[a] + h->lo1, h->ld1, h->H1bits[a]);
+    fwd(ST_L1, xa(2, D), PI1, false, h->H1[b], h->H1[b] + h->lo1, h->ld1);
+    fwd(ST_L1, xa(2, D), PI1, true, h->H1[c], h->H1[c] + h->lo1, h->ld1);
+    fwd(ST_L1, xa(0, D + A), Q1_0, false, h->H1[d], h->H1[d] + h->lo1, h->ld1, h->H1bits[d]);
+    fwd(ST_L1, xa(0, D + A), Q2_0, false, h->H1[e], h->H1[e] + h->lo1, h->ld1, h->H1bits[e]);
+  }
   const int blk2[5] = {PI2, PI2, PI2, Q1_1, Q2_1};
   for (int p = 0; p < 5; ++p) fwd(ST_L2, h1v(p), blk2[p], p == c, h->H2[p], nullptr, h2);
   // ---- forward, policy-action Q passes: f = Q1(x,a1), g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3)
-  fwd(ST_QL1, xa(1, D + A), Q1_0, false, h->H1[f], h->H1[f] + h->lo1, h->ld1, h->H1bits[f]);
-  fwd(ST_QL1, xa(2, D + A), Q1_0, true, h->H1[g], h->H1[g] + h->lo1, h->ld1);
-  fwd(ST_QL1, xa(2, D + A), Q2_0, true, h->H1[hh], h->H1[hh] + h->lo1, h->ld1);
+  if (!pl.fused) {   // otherwise computed inside the policy-head kernel (ql1_fuse_args)
+    fwd(ST_QL1, xa(1, D + A), Q1_0, false, h->H1[f], h->H1[f] + h->lo1, h->ld1, h->H1bits[f]);
+    fwd(ST_QL1, xa(2, D + A), Q1_0, true, h->H1[g], h->H1[g] + h->lo1, h->ld1);
+    fwd(ST_QL1, xa(2, D + A), Q2_0, true, h->H1[hh], h->H1[hh] + h->lo1, h->ld1);
+  }
   fwd(ST_QL2, h1v(f), Q1_1, false, h->H2[f], nullptr, h2);
   fwd(ST_QL2, h1v(g), Q1_1, true, h->H2[g], nullptr, h2);
   fwd(ST_QL2, h1v(hh), Q2_1, true, h->H2[hh], nullptr, h2);
@@ -1460,6 +1577,22 @@ int run_side(const Plan& pl, int st, int S, cudaStream_t side) {
   return 0;
 }
 
+L1Fuse l1_fuse_args(const ddrl_sac* h, bool on) {       // passes a..e of the prologue
+  L1Fuse f{};
+  if (!on) return f;
+  f.on = 1; f.h1 = h->h1; f.ld1 = h->ld1; f.ldbits = h->ldbits; f.lo1 = h->lo1;
+  const float* w[5] = {h->W + h->o_pi1, h->W + h->o_pi1, h->Wt + h->o_pi1, h->W + h->o_q1[0], h->W + h->o_q2[0]};
+  for (int p = 0; p < 5; ++p) { f.W[p] = w[p]; f.H1[p] = h->H1[p]; f.bits[p] = h->H1bits[p]; }
+  return f;
+}
+L1Fuse ql1_fuse_args(const ddrl_sac* h, bool on) {      // passes f, g, h of the policy-head kernel
+  L1Fuse f{};
+  if (!on) return f;
+  f.on = 1; f.h1 = h->h1; f.ld1 = h->ld1; f.ldbits = h->ldbits; f.lo1 = h->lo1;
+  const float* w[3] = {h->W + h->o_q1[0], h->Wt + h->o_q1[0], h->Wt + h->o_q2[0]};
+  for (int p = 0; p < 3; ++p) { f.W[p] = w[p]; f.H1[p] = h->H1[5 + p]; f.bits[p] = h->H1bits[5 + p]; }
+  return f;
+}
 XaOut xa_out(const ddrl_sac* h) {
   return h->use_tc ? XaOut{h->XA[0], h->XA[1], h->XA[2], h->ldx, h->lox} : XaOut{nullptr, nullptr, nullptr, 0, 0};
 }
@@ -1468,8 +1601,9 @@ int launch_prologue(ddrl_sac* h, const Plan& pl, const StepDyn& dyn, cudaStream_
   const int B = pl.B, D = h->D, A = h->A;
   const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
   int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
+  if (pl.fused) blocks = (int)std::min<int64_t>(std::max<int64_t>(blocks, 5LL * ((B + FUSE_PRB - 1) / FUSE_PRB)), h->sms * 3);
   DDRL_CUDA(launch_pdl(k_prologue, dim3(blocks), dim3(256), 0, s, h->st, dyn, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN,
-                       h->NOISE, xa_out(h)));
+                       h->NOISE, xa_out(h), l1_fuse_args(h, pl.fused)));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1478,7 +1612,7 @@ int launch_heads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   if (2 * A <= 16 && (h2 & 3) == 0) {     // narrow heads: warp per row
     DDRL_CUDA(launch_pdl(k_policy_heads_rows, dim3((3 * B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
         B, A, h2, h->ldh, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0],
-        h->A1, h->A3, h->LOGP1, h->LOGP2, xa_out(h), D));
+        h->A1, h->A3, h->LOGP1, h->LOGP2, xa_out(h), D, ql1_fuse_args(h, pl.fused)));
     DDRL_LAUNCH_CHECK();
     return 0;
   }
@@ -1695,6 +1829,11 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     h->Pext = e;
   }
   h->Smax = (max_batch + 255) / 256;
+  {
+    const char* fz = getenv("DDRL_FUSE_L1");
+    h->fuse_l1 = h->use_tc && D + A <= FUSE_MAXK && h1 % 32 == 0 && 2 * A <= 16 && (h2 & 3) == 0 && !(fz && fz[0] == '0');
+    h->fuse_l1_force = fz && fz[0] == '2';
+  }
   int rc = 0;
   const size_t P = (size_t)h->P, M = (size_t)max_batch;
   auto r4 = [](int v) { return (v + 3) / 4 * 4; };
