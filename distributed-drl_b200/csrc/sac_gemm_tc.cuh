@@ -50,6 +50,14 @@ struct alignas(64) TcProb {
   uint32_t* relu_bits;         // nullable (EPI_RELU): bit c of word [row * ldbits + n/32] = output (row, n + c) > 0
   const uint32_t* mask_bits;   // EPI_MASK with bits instead of the mask planes (the producer's relu_bits)
   int ldbits;
+  // Dependent tiles inside ONE launch (two stages of the step merged into one kernel): a producer problem bumps
+  // sig_ctr[sig_per_mtile ? m-tile : 0] when its tile is globally visible; a consumer problem's TMA producer warp for
+  // the dependent operand (dep_a / dep_b) waits until dep_ctr[dep_per_mtile ? m-tile : 0] >= dep_need.  The step's
+  // prologue kernel zeroes the counters.
+  unsigned int* sig_ctr;
+  const unsigned int* dep_ctr;
+  int* err;
+  int sig_per_mtile, dep_per_mtile, dep_need, dep_a, dep_b;
   long long c_split_stride;    // floats between split-K partial outputs
   int ldc, ldmask;
   int M, N, K;
@@ -200,6 +208,18 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
       const CUtensorMap* tm = is_b ? &P.tb : &P.ta;
       const int mn = is_b ? b_mn : a_mn, r0 = is_b ? n0 : m0;
       if (!is_b && P.c_tma) prefetch_tmap(&P.tc);
+      if (P.dep_ctr && (is_b ? P.dep_b : P.dep_a)) {
+        // this operand is written by other tiles of the same launch
+        const unsigned int target = (unsigned int)P.dep_need;
+        const unsigned int* ctr = P.dep_ctr + (P.dep_per_mtile ? m0 / BM : 0);
+        const long long t0 = clock64();
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+          if (v < target && clock64() - t0 > 4000000000LL) { *P.err = 2; break; }   // ~2 s: never hang the GPU
+        } while (v < target);
+        asm volatile("fence.proxy.async;" ::: "memory");   // the acquire orders generic accesses; TMA reads are async-proxy
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         if (kb >= STAGES) bar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
@@ -349,10 +369,19 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
         }
       }
     }
-    if (c_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (c_tma && lane == 0) {
+      if (P.sig_ctr) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // writes complete, not just smem read
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (P.sig_ctr) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence();
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0 && P.sig_ctr)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.sig_ctr + (P.sig_per_mtile ? m0 / BM : 0)) : "memory");
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
   }
