@@ -448,6 +448,70 @@ __global__ void __launch_bounds__(256) rb_store_rows(const StoreArgs<T> s, int r
   }
 }
 
+// ---- segmented rows (N-step sequence replay, algos/sac1/sac_ray.py:34-83) --------------------------------
+// A row is the concatenation of up to 8 float segments (obs [Ln+1, D] | acts [Ln, A] | rews [Ln] | done [Ln]),
+// padded to a multiple of 4 floats.  One warp per sampled row, 128-bit loads, four in flight; a chunk that lies
+// inside one segment at a 16-byte aligned offset leaves as one 128-bit store, others float by float.
+struct SegArgs {
+  const float4* ring;
+  int row_f4, nseg;
+  int off[8], w[8];      // segment start (floats) inside the row, width (floats)
+  float* out[8];         // dense [batch, w[s]] outputs
+  uint64_t size;
+  int64_t total;
+  const int64_t* idx_in;
+  int idx_mode;
+  uint64_t seed, counter;
+  uint32_t rng_stream;
+  int64_t* oidx;
+};
+__device__ __forceinline__ void seg_route(const SegArgs& a, int64_t b, int f, float x) {
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < a.nseg && f >= a.off[s] && f < a.off[s] + a.w[s]) a.out[s][b * a.w[s] + (f - a.off[s])] = x;
+}
+__global__ void __launch_bounds__(256) rb_gather_segments(const SegArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < a.total; b += nwarps) {
+    int64_t idx = 0;
+    if (lane == 0) {
+      idx = a.idx_mode == IDX_INJECT ? a.idx_in[b] : philox_index((uint64_t)b, a.seed, a.counter, a.rng_stream, a.size);
+      if (a.oidx) a.oidx[b] = idx;
+    }
+    idx = shfl_i64(idx, 0);
+    const float4* src = a.ring + idx * a.row_f4;
+    for (int c0 = lane; c0 < a.row_f4; c0 += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + 32 * u < a.row_f4) v[u] = ld_nc_f4(src + c0 + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        if (c >= a.row_f4) continue;
+        const int f = 4 * c;
+        bool done = false;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < a.nseg && f >= a.off[s] && f + 3 < a.off[s] + a.w[s] && ((a.w[s] | (f - a.off[s])) & 3) == 0 &&
+              ((reinterpret_cast<uintptr_t>(a.out[s]) & 15) == 0)) {
+            st_f4(reinterpret_cast<float4*>(a.out[s] + b * a.w[s] + (f - a.off[s])), v[u]);
+            done = true;
+          }
+        }
+        if (!done) {
+          seg_route(a, b, f + 0, v[u].x);
+          seg_route(a, b, f + 1, v[u].y);
+          seg_route(a, b, f + 2, v[u].z);
+          seg_route(a, b, f + 3, v[u].w);
+        }
+      }
+    }
+  }
+}
+
 // Staged variant for float32 inputs with D % 4 == 0 (the common case): per pass a CTA takes R consecutive
 // rows.  Their obs / next_obs slices are CONTIGUOUS blocks of the SoA inputs (R*D floats each), read with fully
 // coalesced 128-bit loads and scattered into packed-row order in shared memory; one thread per row adds the
@@ -941,6 +1005,36 @@ int ddrl_fb_sample_stack(int device, const void* d_frames, int64_t frame_bytes, 
   int64_t blocks = (batch + 7) / 8;
   if (blocks > sms * 8) blocks = sms * 8;
   fb_gather_frames<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ddrl_seg_sample(int device, const float* d_ring, int row_floats, int64_t size, int nseg, const int* h_seg_off,
+                    const int* h_seg_w, float* const* h_d_out, int64_t batch, const int64_t* d_idx_in, uint64_t seed,
+                    uint64_t counter, uint32_t rng_stream, int64_t* d_out_idx, void* stream) {
+  if (!d_ring || !h_seg_off || !h_seg_w || !h_d_out) return fail(DDRL_EINVAL, "ddrl_seg_sample: NULL argument");
+  if (row_floats < 4 || row_floats % 4 != 0) return fail(DDRL_EINVAL, "ddrl_seg_sample: row_floats must be a positive multiple of 4");
+  if (nseg < 1 || nseg > 8) return fail(DDRL_EINVAL, "ddrl_seg_sample: 1..8 segments");
+  if (batch < 0) return fail(DDRL_EINVAL, "ddrl_seg_sample: batch < 0");
+  if (size <= 0 && batch > 0) return fail(DDRL_EEMPTY, "ddrl_seg_sample: ring is empty (the reference raises ValueError: high <= 0)");
+  if (batch == 0) return 0;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DDRL_ECUDA, "ddrl_seg_sample: cannot select device %d", device);
+  SegArgs a{};
+  a.ring = reinterpret_cast<const float4*>(d_ring);
+  a.row_f4 = row_floats / 4; a.nseg = nseg;
+  for (int s = 0; s < nseg; ++s) {
+    if (h_seg_off[s] < 0 || h_seg_w[s] < 1 || h_seg_off[s] + h_seg_w[s] > row_floats || !h_d_out[s])
+      return fail(DDRL_EINVAL, "ddrl_seg_sample: segment %d is outside the row or has no output", s);
+    a.off[s] = h_seg_off[s]; a.w[s] = h_seg_w[s]; a.out[s] = h_d_out[s];
+  }
+  a.size = (uint64_t)size; a.total = batch;
+  a.idx_in = d_idx_in; a.idx_mode = d_idx_in ? IDX_INJECT : IDX_PHILOX;
+  a.seed = seed; a.counter = counter; a.rng_stream = rng_stream; a.oidx = d_out_idx;
+  const int sms = sm_count(device);
+  int64_t blocks = (batch + 7) / 8;
+  if (blocks > sms * 8) blocks = sms * 8;
+  rb_gather_segments<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
   DDRL_LAUNCH_CHECK();
   return 0;
 }

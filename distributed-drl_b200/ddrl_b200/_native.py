@@ -43,6 +43,7 @@ SIGNATURES = {
     "ddrl_rb_peer_attach": (_int, [_vp, _int, _int, _vp]),
     "ddrl_rb_sample_global": (_int, [_vp, _i64, _i64, _vp, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ddrl_fb_sample_stack": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_seg_sample": (_int, [_int, _vp, _int, _i64, _int, _pint, _pint, C.POINTER(_vp), _i64, _vp, _u64, _u64, _u32, _vp, _vp]),
     "ddrl_rb_counts": (_int, [_vp, _pi64, _pi64, _pi64, _pi64, _pi64]),
     "ddrl_rb_layout": (_int, [_vp, _pint, _pint, _pint, C.POINTER(_vp)]),
     "ddrl_rb_export": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

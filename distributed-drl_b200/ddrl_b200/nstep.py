@@ -1,0 +1,125 @@
+"""N-step sequence replay — the SQN_N_STEP ring of the reference's later-generation SAC driver
+(algos/sac1/sac_ray.py:34-83; `Ln` from algos/sac1/hyperparams.py:84), HBM-resident.
+
+Reference call surface (one Ray actor per buffer shard):
+    ReplayBuffer(opt)                                   opt.Ln, opt.obs_shape, opt.act_shape, opt.buffer_size,
+                                                        opt.batch_size, opt.num_buffers
+    .store(o_queue, a_r_d_queue, worker_index)          o_queue: Ln+1 entries (obs,), a_r_d_queue: Ln entries (a, r, d)
+    .sample_batch()                                     -> dict(obs [B, Ln+1, ...], acts [B, Ln, ...], rews [B, Ln], done [B, Ln])
+    .get_counts()                                       -> (sample_times, steps, size); both counters advance by
+                                                        opt.num_buffers per call (sac_ray.py:71-79)
+Only the float32 observation layout is mirrored (the reference also has an lz4-packed string layout for image
+observations, sac_ray.py:42-43, which is an encoding of the same rows).
+
+One packed row per sequence [obs | acts | rews | done], padded to 4 floats; sample_batch is ONE launch of the
+segmented gather (ddrl_seg_sample) that produces the four dense arrays of the reference's dict.  Additive:
+store_batch (vectorised producers), device=True outputs, injected index streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+class NStepReplayBuffer:
+    def __init__(self, opt, *, device=None, seed=None, rng_stream=0, index_source="philox"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ddrl_b200.NStepReplayBuffer needs a CUDA device (no CPU fallback)")
+        if index_source not in ("philox", "numpy"):
+            raise ValueError(index_source)
+        self.opt = opt
+        self._lib = N.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._dev = torch.device("cuda", self.device)
+        self.Ln = int(opt.Ln)
+        self.obs_shape, self.act_shape = tuple(opt.obs_shape), tuple(opt.act_shape)
+        self.D, self.A = int(np.prod(self.obs_shape)), int(np.prod(self.act_shape)) if self.act_shape else 1
+        self.widths = [(self.Ln + 1) * self.D, self.Ln * self.A, self.Ln, self.Ln]
+        self.offsets = [0, self.widths[0], self.widths[0] + self.widths[1], self.widths[0] + self.widths[1] + self.Ln]
+        self.used = sum(self.widths)
+        self.row_f = (self.used + 3) // 4 * 4
+        self.max_size = int(opt.buffer_size)
+        self.batch_size = int(opt.batch_size)
+        self.num_buffers = int(getattr(opt, "num_buffers", 1))
+        self.ring = torch.zeros((self.max_size, self.row_f), dtype=torch.float32, device=self._dev)
+        self.ptr = self.size = self.steps = self.sample_times = 0
+        self.index_source = index_source
+        self._seed = None if seed is None else int(seed) & (2 ** 64 - 1)
+        self._rng_stream, self._counter = int(rng_stream) & 0xFFFFFFFF, 0
+
+    # ---- store -----------------------------------------------------------------------------------
+    def _pack(self, obs, acts, rews, done):
+        """[n, Ln+1, ...], [n, Ln, ...], [n, Ln], [n, Ln] -> packed float32 rows [n, row_f] (numpy assignment casts)."""
+        n = int(np.asarray(rews).shape[0])
+        rows = np.zeros((n, self.row_f), dtype=np.float32)
+        o = self.offsets
+        rows[:, o[0]:o[0] + self.widths[0]] = np.asarray(obs).reshape(n, -1)
+        rows[:, o[1]:o[1] + self.widths[1]] = np.asarray(acts).reshape(n, -1)
+        rows[:, o[2]:o[2] + self.Ln] = np.asarray(rews).reshape(n, -1)
+        rows[:, o[3]:o[3] + self.Ln] = np.asarray(done).reshape(n, -1)
+        return rows
+
+    def store_batch(self, obs, acts, rews, done):
+        """n sequences at once (== n store() calls in row order); only the last `capacity` survive."""
+        rows = torch.from_numpy(self._pack(obs, acts, rews, done))
+        n = int(rows.shape[0])
+        skip = max(0, n - self.max_size)
+        rows = rows[skip:].to(self._dev)
+        m = n - skip
+        start = (self.ptr + skip) % self.max_size
+        first = min(m, self.max_size - start)
+        self.ring[start:start + first].copy_(rows[:first])              # contiguous device copies, wrap-around split
+        if m > first:
+            self.ring[:m - first].copy_(rows[first:])
+        self.ptr = (self.ptr + n) % self.max_size
+        self.size = min(self.size + n, self.max_size)
+        self.steps += n * self.num_buffers
+
+    def store(self, o_queue, a_r_d_queue, worker_index=0):
+        obs, = np.stack(o_queue, axis=1)                               # sac_ray.py:55
+        a, r, d = zip(*a_r_d_queue)
+        self.store_batch(np.asarray(list(obs), dtype=np.float32)[None], np.asarray(list(a), dtype=np.float32)[None],
+                         np.asarray(list(r), dtype=np.float32)[None], np.asarray(list(d), dtype=np.float32)[None])
+
+    # ---- sample -----------------------------------------------------------------------------------
+    def sample_batch(self, batch_size=None, *, idxs=None, device=False, return_idxs=False):
+        B = self.batch_size if batch_size is None else int(batch_size)
+        if self.size == 0:
+            raise ValueError("high <= 0")
+        if idxs is None and self.index_source == "numpy":
+            idxs = np.random.randint(0, self.size, size=B)             # sac_ray.py:74
+        f32 = dict(dtype=torch.float32, device=self._dev)
+        outs = [torch.empty((B, w), **f32) for w in self.widths]
+        o_idx = torch.empty(B, dtype=torch.int64, device=self._dev) if return_idxs else None
+        d_idx = None
+        if idxs is not None:
+            d_idx = torch.as_tensor(np.asarray(idxs), dtype=torch.int64).reshape(-1).to(self._dev).contiguous()
+            if d_idx.numel() != B:
+                raise ValueError(f"idxs has {d_idx.numel()} entries, expected {B}")
+        if self._seed is None:
+            self._seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+        s = torch.cuda.current_stream(self.device)
+        off = (C.c_int * 4)(*self.offsets)
+        wid = (C.c_int * 4)(*self.widths)
+        ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in outs])
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        N.check(self._lib.ddrl_seg_sample(self.device, C.c_void_p(self.ring.data_ptr()), self.row_f, self.size, 4, off, wid,
+                                          ptrs, B, p(d_idx), self._seed if idxs is None else 0, self._counter,
+                                          self._rng_stream, p(o_idx), C.c_void_p(s.cuda_stream)))
+        if idxs is None:
+            self._counter += 1
+        self.sample_times += self.num_buffers
+        out = dict(obs=outs[0].view((B, self.Ln + 1) + self.obs_shape), acts=outs[1].view((B, self.Ln) + self.act_shape),
+                   rews=outs[2], done=outs[3])
+        if return_idxs:
+            out["idxs"] = o_idx
+        if not device:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        return out
+
+    def get_counts(self):
+        return self.sample_times, self.steps, self.size

@@ -137,6 +137,15 @@ int ddrl_fb_sample_stack(int device, const void* d_frames, int64_t frame_bytes, 
                          uint32_t rng_stream, void* d_out_obs1, void* d_out_obs2, float* d_out_acts,
                          float* d_out_rews, float* d_out_done, int64_t* d_out_idx, void* stream);
 
+/* N-step sequence replay — sample_batch of the SQN_N_STEP ring (algos/sac1/sac_ray.py:34-83: rows of obs [Ln+1, D],
+ * acts [Ln, A], rews [Ln], done [Ln]).  The ring is a caller-owned device array [capacity, row_floats] whose rows are
+ * the concatenation of `nseg` float segments (start h_seg_off[s], width h_seg_w[s], row_floats a multiple of 4);
+ * batch rows drawn like ddrl_rb_sample (injected indices or Philox) are gathered into one dense output
+ * [batch, h_seg_w[s]] per segment (h_d_out[s], device pointers in a host array). */
+int ddrl_seg_sample(int device, const float* d_ring, int row_floats, int64_t size, int nseg, const int* h_seg_off,
+                    const int* h_seg_w, float* const* h_d_out, int64_t batch, const int64_t* d_idx_in, uint64_t seed,
+                    uint64_t counter, uint32_t rng_stream, int64_t* d_out_idx, void* stream);
+
 /* ReplayBuffer.get_counts()  (algos/sac1/sac1.py:62-63) plus ptr / capacity.  Any out may be NULL. */
 int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity, int64_t* steps,
                    int64_t* sample_times);

@@ -80,6 +80,27 @@ def run_reference_ps(seed=2001):
                 pull_k2=pulled[0], pull_k1=pulled[1], pull_k0=pulled[2])
 
 
+def run_reference_nstep():
+    """tests/golden/nstep_scalar_act.npz: the reference's N-step ring (algos/sac1/sac_ray.py:34-83) driven with
+    the sequences and index stream of tests/test_oracle_nstep.py::drive."""
+    from types import SimpleNamespace
+    from oracle.nstep_oracle import make_sequences
+    cls = ref_extract.load_reference_class("algos/sac1/sac_ray.py", "ReplayBuffer")
+    opt = SimpleNamespace(Ln=8, obs_shape=(115,), act_shape=(), buffer_size=37, batch_size=64, num_buffers=3)
+    buf = cls(opt)
+    for oq, aq in make_sequences(opt, 50, 5):
+        buf.store(oq, aq, 0)
+    idx = np.random.Generator(np.random.PCG64(6)).integers(0, 37, 64)
+    saved = np.random.randint
+    try:
+        np.random.randint = lambda lo, hi, size: idx
+        out = buf.sample_batch()
+    finally:
+        np.random.randint = saved
+    return dict(idx=idx, obs=out["obs"], acts=out["acts"], rews=out["rews"], done=out["done"],
+                counts=np.array(buf.get_counts()))
+
+
 def main():
     if not ref_extract.reference_available():
         raise SystemExit("reference tree not found; golden vectors can only be regenerated where it is mounted")
@@ -89,6 +110,8 @@ def main():
         print("wrote", name)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "ps_sac1.npz"), **run_reference_ps())
     print("wrote ps_sac1")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "nstep_scalar_act.npz"), **run_reference_nstep())
+    print("wrote nstep_scalar_act")
 
 
 if __name__ == "__main__":
