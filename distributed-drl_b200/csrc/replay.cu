@@ -207,6 +207,41 @@ __global__ void __launch_bounds__(256, 4) rb_gather_wide(const GatherArgs a) {
   }
 }
 
+// ---- very wide rows (frame observations: 113 KB per row): a row is cut into 16 KB segments and every (row,
+// segment) pair is one warp's work, so a 512-row batch still spreads over the whole chip -----------------------
+constexpr int XW_SEG = 1024;     // float4 per segment
+__global__ void __launch_bounds__(256, 4) rb_gather_xwide(const GatherArgs a, int nseg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool aligned = (a.D & 3) == 0;
+  for (int64_t item = warp; item < a.total * nseg; item += nwarps) {
+    const int64_t b = item / nseg;
+    const int sg = (int)(item - b * nseg);
+    int64_t src = 0;
+    if (lane == 0) {
+      src = draw_index(a, b);
+      if (a.oidx && sg == 0) a.oidx[b] = src;
+    }
+    src = shfl_i64(src, 0);
+    const float4* row = row_ptr(a, src);
+    const int cend = min(a.used_f4, (sg + 1) * XW_SEG);
+    for (int c0 = sg * XW_SEG + lane; c0 < cend; c0 += 32 * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < cend) v[k] = ld_nc_f4(row + c);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < cend) route_chunk(a, aligned, b, c, v[k]);
+      }
+    }
+  }
+}
+
 // ---- bulk-async staged gather (TMA engine, no register staging) -------------------------------
 // The packed row is ONE contiguous 16-byte-aligned run, so a sampled row is ONE `cp.async.bulk`
 // (global -> shared, completion counted in bytes on an mbarrier).  A CTA keeps STAGES tiles of R rows
@@ -654,6 +689,11 @@ static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
         else rb_gather_narrow<32, 4><<<(int)blocks, threads, 0, st>>>(a);
         break;
     }
+  } else if (rb->used_f4 >= 2 * XW_SEG) {
+    const int nseg = (rb->used_f4 + XW_SEG - 1) / XW_SEG;
+    int64_t blocks = (a.total * nseg + threads / 32 - 1) / (threads / 32);
+    if (blocks > max_blocks) blocks = max_blocks;
+    rb_gather_xwide<<<(int)blocks, threads, 0, st>>>(a, nseg);
   } else {
     const int64_t rows_per_block = (threads / 32) * 8;
     int64_t blocks = (a.total + rows_per_block - 1) / rows_per_block;
