@@ -248,18 +248,20 @@ class Learner(object):
             # our own ReplayBuffer.sample_batch() host result: five views of one pinned block -> ONE H2D copy
             n = int(batch.n)
             nb = n * (2 * D + A + 2) * 4
-            dev = self._stage.get(("block", nb))
-            if dev is None:
+            ent = self._stage.get(("block", nb))
+            if ent is None:
                 dev = torch.empty(nb, dtype=torch.uint8, device=self._dev)
-                self._stage[("block", nb)] = dev
+                f = dev.view(torch.float32)
+                views, o = [], 0
+                for width, shape in ((D, (n, D)), (D, (n, D)), (A, (n, A)), (1, (n,)), (1, (n,))):
+                    views.append(f[o:o + n * width].view(shape))
+                    o += n * width
+                ent = (dev, views)
+                self._stage[("block", nb)] = ent
+            dev, views = ent
             dev.copy_(blk[:nb], non_blocking=True)
             self._keep = blk    # (torch's pinned-memory allocator also defers reuse until the copy has run)
-            f = dev.view(torch.float32)
-            o = 0
-            for width, shape in ((D, (n, D)), (D, (n, D)), (A, (n, A)), (1, (n,)), (1, (n,))):
-                out.append(f[o:o + n * width].view(shape))
-                o += n * width
-            return out
+            return views
         if all(isinstance(batch[k], np.ndarray) for k in _KEYS_BATCH):
             # generic host dict: pack into one pinned block (numpy assignment casts), ONE H2D copy
             n = int(np.asarray(batch["rews"]).shape[0])
