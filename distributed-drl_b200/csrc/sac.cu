@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_
 // NVLink peer memory.  Every rank owns one communication buffer [2][Pc] floats (+ 8 arrival flags) that all peers
 // map with CUDA IPC.  Step t: k_grad_reduce_comm leaves this rank's flat gradient (split-K partials summed, plus
 // the entropy statistic) in slot t & 1; k_adam_polyak_peer then
-//   1. signals "my gradient of step t is complete" by storing t into flag[rank] of every peer (st.release.sys),
+//   1. (the reduce kernel's last CTA has already stored t into flag[rank] of every peer, st.release.sys)
 //   2. waits until its own flags show t from every peer (ld.acquire.sys),
 //   3. reads all ranks' slot t & 1 directly (128-bit volatile loads over NVLink), sums them in rank order — every
 //      rank computes bit-identical sums — scales by 1/N and applies Adam + polyak (+ the weight split planes).
@@ -920,7 +920,7 @@ struct PeerComm {
 };
 __global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __restrict__ st, int64_t P, int S,
                                                           const float* __restrict__ Gp, const float* __restrict__ SCAL,
-                                                          const __grid_constant__ PeerComm pc) {
+                                                          const __grid_constant__ PeerComm pc, unsigned int* ticket) {
   pdl_trigger();
   pdl_wait();
   float* G = pc.buf[pc.rank] + (size_t)(st->t_pi & 1) * pc.Pc;
@@ -931,6 +931,19 @@ __global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __res
     G[i] = g;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) G[P] = SCAL[4];   // mean logp1 of this rank's batch (entropy-alpha gradient)
+  // the last CTA to finish publishes "my gradient of step t is complete" to every peer, so the flags travel while
+  // the optimiser kernel is being launched
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x < pc.world) {
+    if (threadIdx.x == 0) *ticket = 0u;
+    __threadfence_system();
+    const unsigned int epoch = (unsigned int)st->t_pi;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc.flags[threadIdx.x] + pc.rank), "r"(epoch) : "memory");
+  }
 }
 __device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
   float4 r;
@@ -944,11 +957,7 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
   pdl_trigger();
   pdl_wait();
   const unsigned int epoch = (unsigned int)st->t_pi;
-  if (threadIdx.x < pc.world) {
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc.flags[threadIdx.x] + pc.rank), "r"(epoch) : "memory");
-    }
+  if (threadIdx.x < pc.world) {     // (this rank's own flags were published by k_grad_reduce_comm)
     const unsigned int* mine = pc.flags[pc.rank] + threadIdx.x;
     const long long t0 = clock64();
     unsigned int v;
@@ -1727,7 +1736,7 @@ int enqueue_reduce(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
   if (h->pc.world > 1)
     DDRL_CUDA(launch_pdl(k_grad_reduce_comm, dim3(blocks), dim3(256), 0, s, (const StepState*)h->st, h->P, pl.S,
-                         (const float*)h->Gp, (const float*)h->SCAL, h->pc));
+                         (const float*)h->Gp, (const float*)h->SCAL, h->pc, h->ticket + 1));
   else
     DDRL_CUDA(launch_pdl(k_grad_reduce, dim3(blocks), dim3(256), 0, s, h->P, pl.S, h->Gp, h->G));
   DDRL_LAUNCH_CHECK();
