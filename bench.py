@@ -59,6 +59,11 @@ def flops_per_update(D, A, h1, h2, B):
     return 5 * l_pi + 10 * l_q
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_grouped_tc launch (second-layer stage) from the committed
+# ncu --set full capture (profiles/r01c_gemm_tc_c2_l2_ncu_full_summary.txt); only captured for C2
+NCU_TRAFFIC = {"C2": 12662784}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -350,6 +355,20 @@ def run_ours(args):
     store_gbs = 2 * row_bytes * n_store / store_s / 1e9
     del o, src
 
+    # ---- (3b) the dominant kernel alone, live: gemm_grouped_tc of the second-layer stage (5 passes of
+    #      [B, h1] x [h1, h2] from pre-split planes, one launch), CUDA events on the launching stream -------------
+    tc_reps = 100
+    _native.check(lib.ddrl_sac_debug_stage(learner._h, B, 1, 10, C.c_void_p(s.cuda_stream)))
+    torch.cuda.synchronize()
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record(s)
+    _native.check(lib.ddrl_sac_debug_stage(learner._h, B, 1, tc_reps, C.c_void_p(s.cuda_stream)))
+    t1e.record(s)
+    torch.cuda.synchronize()
+    tc_launch_s = t0e.elapsed_time(t1e) / 1e3 / tc_reps
+    tc_flops = 5 * 2 * B * hidden[0] * hidden[1]
+    tc_bytes = 5 * (2 * 4 * B * hidden[0] + 2 * 4 * hidden[0] * hidden[1] + 4 * B * hidden[1])   # A hi/lo, W hi/lo, H2 out
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -381,7 +400,21 @@ def run_ours(args):
                 note="config 5 flavour of the same loop: every step each rank also stores its share of 256 producers' "
                      "transitions; every 300 steps the flat weights are broadcast to the parameter-server replicas"),
         gpu_launches=int(launches),
-        roofline=dict(kernel="SAC1 update, whole step (gemm_grouped_tc x 7 tcgen05 3xTF32 stages + 3 row-wise kernels + prologue + "
+        roofline=dict(kernel="gemm_grouped_tc, second-layer stage of the SAC1 update: 5 x [B,256]x[256,256] in one launch "
+                             "(TMA -> tcgen05.mma kind::tf32 x3 -> TMEM -> TMA store)", bound="tensor",
+                      achieved=tc_flops / tc_launch_s / 1e12, peak=peaks["bf16_tf"], unit="TFLOP/s",
+                      frac=tc_flops / tc_launch_s / 1e12 / peaks["bf16_tf"],
+                      traffic=NCU_TRAFFIC.get(args.config), us_per_launch=tc_launch_s * 1e6, flops_per_launch=tc_flops,
+                      algorithmic_bytes_per_launch=tc_bytes, tensor_pipe_flops_per_launch=3 * tc_flops,
+                      peak_source=peaks["source"],
+                      note="algorithmic FLOPs (one product per multiply-add) over the CUDA-event launch time, against the "
+                           "measured bf16 tensor peak; fp32-class accuracy (1e-5 bar) costs three tf32 MMAs per product at half "
+                           "the bf16 rate, so the tensor pipe executes 6x this figure in bf16-equivalents; at these sizes "
+                           "(80 tiles of 128x128x256) the launch is bound by its TMA -> MMA -> epilogue latency chain "
+                           "(ncu: tensor pipe 27% active); traffic = dram bytes read+written per launch from "
+                           "profiles/r01c_gemm_tc_c2_l2_ncu_full_summary.txt (cold-cache replay; operands are L2-resident "
+                           "in the real step)"),
+        roofline_step=dict(kernel="SAC1 update, whole step (gemm_grouped_tc x 7 tcgen05 3xTF32 stages + 3 row-wise kernels + prologue + "
                              "Adam/polyak; side-stream bias/skinny gradients)", bound="tensor",
                       achieved=tf, peak=peaks["bf16_tf"], unit="TFLOP/s", frac=tf / peaks["bf16_tf"], traffic=None,
                       flops_per_update=fl, peak_source=peaks["source"],

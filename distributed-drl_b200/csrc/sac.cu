@@ -2236,6 +2236,27 @@ int ddrl_debug_tc_gemm(int device, const float* dA, int a_rows, int a_cols, int 
   return rc;
 }
 
+// profiling aid: run GEMM stage `stage` once with per-CTA phase time stamps (ns, %globaltimer): d_trace [tiles, 8]
+int ddrl_sac_trace_stage(ddrl_sac_t h, int batch, int stage, unsigned long long* d_trace, int max_tiles, int* tiles, void* stream) {
+  if (!h || !d_trace || !tiles) return fail(DDRL_EINVAL, "ddrl_sac_trace_stage: NULL argument");
+  if (stage < 0 || stage >= ST_COUNT) return fail(DDRL_EINVAL, "ddrl_sac_trace_stage: stage %d", stage);
+  DeviceGuard guard(h->device);
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  *tiles = 0;
+  for (auto& g : pl->stages[stage]) {
+    if (g.tiles_tc <= 0) continue;
+    if (g.tiles_tc > max_tiles) return fail(DDRL_EINVAL, "ddrl_sac_trace_stage: %d tiles > max_tiles", g.tiles_tc);
+    tc::TcGroup grp = g.grp_tc;
+    grp.trace = d_trace;
+    DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc, dim3(g.tiles_tc), dim3(256), tc::SMEM_BYTES, (cudaStream_t)stream, grp));
+    DDRL_LAUNCH_CHECK();
+    *tiles = g.tiles_tc;
+  }
+  return 0;
+}
+
 int ddrl_sac_state(ddrl_sac_t h, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream) {
   if (!h) return fail(DDRL_EINVAL, "ddrl_sac_state: NULL handle");
   DeviceGuard guard(h->device);

@@ -35,7 +35,7 @@ constexpr int BM = 128, BN = 128, BK = 32;            // BK tf32 = 128 bytes = o
 constexpr int TILE_BYTES = 128 * 128;                 // one operand plane tile (128 x 32 tf32)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
 constexpr int STAGES = 3;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers, tmem ptr*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers, tmem ptr*/ + 512 /*bias of the tile*/;
 constexpr int TMEM_COLS = 128;
 constexpr int MAX_PROBS = 10;
 
@@ -69,8 +69,15 @@ struct alignas(64) TcProb {
 };
 struct TcGroup {
   int nprob;
+  unsigned long long* trace;   // nullable (tools/tc_trace.py): per CTA 8 globaltimer stamps of the kernel's phases
   TcProb p[MAX_PROBS];
 };
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i) do { if (grp.trace && lane == 0) grp.trace[(size_t)blockIdx.x * 8 + (i)] = gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -144,6 +151,16 @@ __device__ __forceinline__ void stage_row(unsigned char* blk, int lane, const fl
   for (int c = 0; c < 8; ++c)
     *reinterpret_cast<float4*>(blk + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {   // caller issues tcgen05.wait::ld before use
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+        "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+        "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+        "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
@@ -167,11 +184,41 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   uint64_t* empty = full + STAGES;
   uint64_t* acc_ready = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+  float* s_bias = reinterpret_cast<float*>(base + STAGES * STAGE_BYTES + 128);   // [BN]
 
+  if (tid == 0) TC_STAMP(0);          // CTA start
   int pi = 0;
   while (pi + 1 < grp.nprob && (int)blockIdx.x >= grp.p[pi + 1].tile_begin) ++pi;
   const TcProb& P = grp.p[pi];
   const int M = P.M, N = P.N, K = P.K, a_mn = P.a_mn, b_mn = P.b_mn;
+  int t = blockIdx.x - P.tile_begin;
+  const int per_split = P.tiles_m * P.tiles_n;
+  const int split = t / per_split;
+  t -= split * per_split;
+  const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
+  const int kbeg = split * P.k_per_split;
+  const int kend = min(K, kbeg + P.k_per_split);
+  const int nkb = (kend - kbeg + BK - 1) / BK;
+  // one k-block of one operand (both planes) into stage `s`
+  auto load_operand = [&](bool is_b, int kb, int s) {
+    const CUtensorMap* tm = is_b ? &P.tb : &P.ta;
+    const int mn = is_b ? b_mn : a_mn, r0 = is_b ? n0 : m0;
+    bar_expect_tx(&full[s], 2 * TILE_BYTES);
+    const uint32_t st = s_addr(base + s * STAGE_BYTES) + (is_b ? 2 * TILE_BYTES : 0);
+    const int k0 = kbeg + kb * BK;
+#pragma unroll
+    for (int hl = 0; hl < 2; ++hl) {
+      const uint32_t dst = st + hl * TILE_BYTES;
+      if (!mn) tma_load_3d(dst, tm, k0, r0, hl, &full[s]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096, tm, r0 + 32 * j, k0, hl, &full[s]);
+      }
+    }
+  };
+  // tid 0 may start the first k-block before the CTA-wide setup barrier (it initialised the barriers itself)
+  // unless the operand is produced by other tiles of this launch (dependency wait happens in the producer loops)
+  const bool early0 = !P.dep_ctr;
 
   if (tid == 0) {
     prefetch_tmap(&P.ta);
@@ -179,6 +226,11 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
     for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 2); bar_init(&empty[s], 1); }   // full: A and B producers
     bar_init(acc_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (early0) {
+      pdl_wait();
+      load_operand(false, 0, 0);
+      load_operand(true, 0, 0);
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "n"(TMEM_COLS) : "memory");
@@ -190,23 +242,25 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
   pdl_wait();        // everything above touched no global data; operands are complete and visible from here on
-
-  int t = blockIdx.x - P.tile_begin;
-  const int per_split = P.tiles_m * P.tiles_n;
-  const int split = t / per_split;
-  t -= split * per_split;
-  const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
-  const int kbeg = split * P.k_per_split;
-  const int kend = min(K, kbeg + P.k_per_split);
-  const int nkb = (kend - kbeg + BK - 1) / BK;
+  if (tid == 0) TC_STAMP(1);          // setup done (barriers, TMEM)
+  // epilogue operands fetched now, while the main loop runs: the tile's bias row into shared memory (idle warps 4..7),
+  // this thread's relu-mask words into registers
+  if (tid >= 128 && P.bias) s_bias[tid - 128] = (n0 + tid - 128 < N) ? __ldg(P.bias + n0 + tid - 128) : 0.0f;
+  uint32_t mbits[2] = {0u, 0u};
+  if (P.epi == EPI_MASK && P.mask_bits) {
+    const int mrow = m0 + 32 * (warp & 3) + lane;
+    const int w0 = (n0 + (warp >> 2) * 64) >> 5;
+    if (mrow < M) {
+      if (32 * w0 < N) mbits[0] = P.mask_bits[(size_t)mrow * P.ldbits + w0];
+      if (32 * (w0 + 1) < N) mbits[1] = P.mask_bits[(size_t)mrow * P.ldbits + w0 + 1];
+    }
+  }
 
   if (warp == 0 || warp == 2) {
     if (lane == 0) {
       // ---- TMA producers: warp 0 loads the A planes, warp 2 the B planes (an MN-major operand is four
       //      32 x 32 boxes per plane, so one thread issuing all 16 copies of a k-block would be the bottleneck) ----
       const bool is_b = warp == 2;
-      const CUtensorMap* tm = is_b ? &P.tb : &P.ta;
-      const int mn = is_b ? b_mn : a_mn, r0 = is_b ? n0 : m0;
       if (!is_b && P.c_tma) prefetch_tmap(&P.tc);
       if (P.dep_ctr && (is_b ? P.dep_b : P.dep_a)) {
         // this operand is written by other tiles of the same launch
@@ -220,21 +274,10 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
         } while (v < target);
         asm volatile("fence.proxy.async;" ::: "memory");   // the acquire orders generic accesses; TMA reads are async-proxy
       }
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = early0 ? 1 : 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         if (kb >= STAGES) bar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
-        bar_expect_tx(&full[s], 2 * TILE_BYTES);
-        const uint32_t st = s_addr(base + s * STAGE_BYTES) + (is_b ? 2 * TILE_BYTES : 0);
-        const int k0 = kbeg + kb * BK;
-#pragma unroll
-        for (int hl = 0; hl < 2; ++hl) {
-          const uint32_t dst = st + hl * TILE_BYTES;
-          if (!mn) tma_load_3d(dst, tm, k0, r0, hl, &full[s]);
-          else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096, tm, r0 + 32 * j, k0, hl, &full[s]);
-          }
-        }
+        load_operand(is_b, kb, s);
       }
     }
     __syncwarp();
@@ -246,6 +289,7 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         bar_wait(&full[s], (kb / STAGES) & 1);
+        if (kb == 0) TC_STAMP(2);     // first stage landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = s_addr(base + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES,
                        b_lo = a_hi + 3 * TILE_BYTES;
@@ -259,41 +303,43 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
         mma_commit(&empty[s]);          // frees the stage when these MMAs have read it
       }
       mma_commit(acc_ready);            // covers every MMA issued before it
+      TC_STAMP(3);                      // all MMAs issued
     }
     __syncwarp();
   }
 
+  __syncthreads();                    // s_bias is visible; the issuing lanes have left their loops
   bar_wait(acc_ready, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) TC_STAMP(4);          // accumulator complete
 
-  // epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*(w/4)..+64
+  // epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*(w/4)..+64, as two 32-column chunks whose TMEM loads
+  // are both in flight before the first is consumed
   {
     const int q = warp & 3, half = warp >> 2;
     const int m = m0 + 32 * q + lane;
     const int epi = P.epi, ldc = P.ldc, c_tma = P.c_tma;
     float* C = P.C + (size_t)split * P.c_split_stride;
     float* C_lo = P.C_lo;
-    const float* bias = P.bias;
+    const bool has_bias = P.bias != nullptr;
+    float vv[2][32];
+    const bool live0 = n0 + half * 64 < N, live1 = n0 + half * 64 + 32 < N;     // warp-uniform
+    if (live0) tmem_ld32_nowait(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * 64), vv[0]);
+    if (live1) tmem_ld32_nowait(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * 64 + 32), vv[1]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int cb = 0; cb < 2; ++cb) {
       const int c0 = half * 64 + cb * 32;
       const int n_base = n0 + c0;
       if (n_base >= N) continue;                     // warp-uniform
-      float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      float* v = vv[cb];
       if (m < M) {
         const bool full_n = n_base + 31 < N;
-        if (bias) {
-          if (full_n && ((reinterpret_cast<uintptr_t>(bias + n_base) & 15) == 0)) {
+        if (has_bias) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n_base + i));
-              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n_base + i < N) v[i] += __ldg(bias + n_base + i);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + i);   // zero beyond N
+            v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
           }
         }
         if (epi == EPI_RELU) {
@@ -305,28 +351,15 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
           }
           if (P.relu_bits) P.relu_bits[(size_t)m * P.ldbits + (n_base >> 5)] = bits;
         } else if (epi == EPI_MASK && P.mask_bits) {
-          const uint32_t bits = P.mask_bits[(size_t)m * P.ldbits + (n_base >> 5)];
+          const uint32_t bits = mbits[cb];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.0f;
         } else if (epi == EPI_MASK) {
           const float* mk = P.mask + (size_t)m * P.ldmask + n_base;
           const float* ml = P.mask_lo ? P.mask_lo + (size_t)m * P.ldmask + n_base : nullptr;
-          if (full_n) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 a = *reinterpret_cast<const float4*>(mk + i);
-              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ml) b = *reinterpret_cast<const float4*>(ml + i);
-              v[i] = (a.x > 0.0f || b.x > 0.0f) ? v[i] : 0.0f;
-              v[i + 1] = (a.y > 0.0f || b.y > 0.0f) ? v[i + 1] : 0.0f;
-              v[i + 2] = (a.z > 0.0f || b.z > 0.0f) ? v[i + 2] : 0.0f;
-              v[i + 3] = (a.w > 0.0f || b.w > 0.0f) ? v[i + 3] : 0.0f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n_base + i < N) v[i] = (mk[i] > 0.0f || (ml && ml[i] > 0.0f)) ? v[i] : 0.0f;
-          }
+          for (int i = 0; i < 32; ++i)
+            if (n_base + i < N) v[i] = (mk[i] > 0.0f || (ml && ml[i] > 0.0f)) ? v[i] : 0.0f;
         }
         if (!c_tma) {
           float* dst = C + (size_t)m * ldc + n_base;
@@ -378,8 +411,10 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
       __threadfence();
     }
   }
+  if (tid == 0) TC_STAMP(5);          // this warp's epilogue done (stores issued and drained)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0) TC_STAMP(6);          // all warps done
   if (tid == 0 && P.sig_ctr)
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.sig_ctr + (P.sig_per_mtile ? m0 / BM : 0)) : "memory");
   if (warp == 1) {

@@ -66,6 +66,7 @@ SIGNATURES = {
     "ddrl_sac_act": (_int, [_vp, _vp, _int, _int, _vp, _u64, _u64, _vp, _vp]),
     "ddrl_sac_debug_stage": (_int, [_vp, _int, _int, _int, _vp]),
     "ddrl_debug_tc_gemm": (_int, [_int, _vp, _int, _int, _int, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp]),
+    "ddrl_sac_trace_stage": (_int, [_vp, _int, _int, _vp, _int, _pint, _vp]),
     "ddrl_sac_state": (_int, [_vp, _pint, _pint, _pint, _pf, _vp]),
 }
 

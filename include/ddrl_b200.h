@@ -252,6 +252,11 @@ int ddrl_sac_debug_stage(ddrl_sac_t sac, int batch, int stage, int reps, void* s
  * when the contraction index is the ROW of the stored tensor (MN-major operand), 0 when it is the column. */
 int ddrl_debug_tc_gemm(int device, const float* d_a, int a_rows, int a_cols, int a_mn, const float* d_b, int b_rows,
                        int b_cols, int b_mn, float* d_c, int m, int n, int k, int splits, void* stream);
+/* profiling aid: run the tensor-core launch of GEMM stage `stage` once with per-CTA phase time stamps
+ * (d_trace [tiles, 8] of %globaltimer ns: start, setup done, first stage landed, MMAs issued, accumulator complete,
+ * warp-0 epilogue done, all warps done) */
+int ddrl_sac_trace_stage(ddrl_sac_t sac, int batch, int stage, unsigned long long* d_trace, int max_tiles, int* tiles,
+                         void* stream);
 /* optimiser step counters and log_alpha (synchronises `stream`).  Any out may be NULL. */
 int ddrl_sac_state(ddrl_sac_t sac, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream);
 
