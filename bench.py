@@ -13,10 +13,14 @@ Printed JSON line (rank 0):
   value / unit        whole-job transitions/s consumed by the learners (N * B * K / t), everything
                       resident in HBM, timed with CUDA events between barriers, max over ranks
   e2e                 the same metric through the reference-facing API with HOST buffers: per step
-                      store_batch(B new rows from pinned host memory) -> sample_batch(B) returned as
-                      host numpy arrays -> train(host batch) -> read the losses back
-  roofline            dominant kernel class of the step (the SAC1 update: FLOP model of SURVEY §8d
-                      against the measured bf16 tensor peak; parity mode computes in fp32 FFMA)
+                      sample_batch(B) returned as host numpy arrays -> train(host batch) ->
+                      store_batch(B new rows from pinned host memory) -> read the losses back
+  roofline            the dominant kernel, measured live with CUDA events: the second-layer launch of
+                      gemm_grouped_tc (tcgen05, 3xTF32), algorithmic FLOPs against the measured bf16
+                      tensor peak; traffic from the committed ncu capture
+  roofline_step       the whole SAC1 update by the FLOP model of SURVEY §8d
+  c5                  the same loop with 256 producers' rows stored every step and the parameter-server
+                      broadcast every 300 steps (BASELINE config 5 flavour)
   roofline_replay     the sample_batch gather kernel alone (sample_many launches): algorithmic bytes
                       2*row_bytes per transition against the measured HBM copy peak
   cpu_baseline        the oracle port (numpy ring + torch-CPU float32 SAC1 step) on this box's cores
@@ -282,9 +286,10 @@ def run_ours(args):
     sink = []
 
     def step_e2e():
-        rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side
         batch = rb.sample_batch(B)                            # D2H: the reference returns host arrays
         out = learner.train(batch)                            # H2D: host batch fed like feed_dict
+        rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side (the host
+                                                              # stages them while the GPU runs the update)
         sink.append(out["scalars"].cpu())                     # D2H: the fetched losses
 
     e2e_steps = max(5, min(args.steps, 200))
@@ -394,7 +399,7 @@ def run_ours(args):
         clocks=clk,
         e2e=dict(value=e2e_value, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
                  ms_per_step=sec_e2e / e2e_steps * 1e3,
-                 path="store_batch(host) -> sample_batch() -> numpy -> Learner.train(numpy) -> losses.cpu()"),
+                 path="sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host, B new rows) -> losses.cpu()"),
         c5=dict(value=world * B * c5_steps / sec_c5, unit="transitions/s", ms_per_step=sec_c5 / c5_steps * 1e3, steps=c5_steps,
                 producers=producers, stored_rows_per_step=rows_per_rank * world, ps_broadcast_every=300,
                 note="config 5 flavour of the same loop: every step each rank also stores its share of 256 producers' "

@@ -865,11 +865,18 @@ int ddrl_rb_store_batch_host(ddrl_rb_t rb, const void* h_obs, const void* h_act,
   char* d_act = d_nxt + b_obs;
   char* d_rew = d_act + b_act;
   char* d_done = d_rew + b_s;
-  DDRL_CUDA(cudaMemcpyAsync(d_obs, h_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
-  DDRL_CUDA(cudaMemcpyAsync(d_nxt, h_next_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
-  DDRL_CUDA(cudaMemcpyAsync(d_act, h_act, (size_t)n * rb->A * es, cudaMemcpyHostToDevice, st));
-  DDRL_CUDA(cudaMemcpyAsync(d_rew, h_rew, (size_t)n * es, cudaMemcpyHostToDevice, st));
-  DDRL_CUDA(cudaMemcpyAsync(d_done, h_done, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  const char* hb = (const char*)h_obs;
+  if ((const char*)h_next_obs == hb + b_obs && (const char*)h_act == hb + 2 * b_obs && (const char*)h_rew == hb + 2 * b_obs + b_act &&
+      (const char*)h_done == hb + 2 * b_obs + b_act + b_s) {
+    // the caller staged the five arrays in one block with this very layout (ddrl_b200.ReplayBuffer does): ONE copy
+    DDRL_CUDA(cudaMemcpyAsync(d_obs, h_obs, 2 * b_obs + b_act + b_s + (size_t)n * es, cudaMemcpyHostToDevice, st));
+  } else {
+    DDRL_CUDA(cudaMemcpyAsync(d_obs, h_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
+    DDRL_CUDA(cudaMemcpyAsync(d_nxt, h_next_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
+    DDRL_CUDA(cudaMemcpyAsync(d_act, h_act, (size_t)n * rb->A * es, cudaMemcpyHostToDevice, st));
+    DDRL_CUDA(cudaMemcpyAsync(d_rew, h_rew, (size_t)n * es, cudaMemcpyHostToDevice, st));
+    DDRL_CUDA(cudaMemcpyAsync(d_done, h_done, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  }
   return store_common(rb, d_obs, d_act, d_rew, d_nxt, d_done, n, in_dtype, st);
 }
 

@@ -164,26 +164,29 @@ class ReplayBuffer:
         s = self._stream()
         if self._bstages is None and n <= self._bstage_rows:
             R = self._bstage_rows
-            pin = dict(dtype=torch.float32, pin_memory=True)
             def mk():
-                ts = [torch.empty((R, D), **pin), torch.empty((R, A), **pin), torch.empty(R, **pin),
-                      torch.empty((R, D), **pin), torch.empty(R, **pin)]
-                return dict(bufs=[(t, t.numpy()) for t in ts], event=None)
+                blk = torch.empty(4 * R * (2 * D + A + 2) + 5 * 256, dtype=torch.uint8, pin_memory=True)
+                return dict(block=blk, raw=blk.numpy(), event=None)
             self._bstages = [mk(), mk()]
         if n <= self._bstage_rows:
-            # by-value capture into our own pinned staging (numpy assignment = the reference's cast), then
-            # asynchronous H2D copies: no stream synchronisation on the producer's call path
+            # by-value capture into our own pinned staging (numpy assignment = the reference's cast), then ONE
+            # asynchronous H2D copy: the block has the layout of the library's device staging (256-byte aligned
+            # sub-arrays obs | next_obs | acts | rews | done for THIS n), which ddrl_rb_store_batch_host recognises;
+            # no stream synchronisation on the producer's call path
             st = self._bstages[self._bcur]
             self._bcur ^= 1
             if st["event"] is not None:
                 st["event"].synchronize()
-            views = []
-            for (t, v), a, sh in zip(st["bufs"], np_arrs, shapes):
-                dst = v[:n] if len(sh) == 1 else v[:n].reshape(sh)
-                np.copyto(dst, a.reshape(sh), casting="unsafe")
-                views.append(t)
+            up = lambda x: (x + 255) // 256 * 256
+            b_obs, b_act, b_s = up(n * D * 4), up(n * A * 4), up(n * 4)
+            offs = [0, 2 * b_obs, 2 * b_obs + b_act, b_obs, 2 * b_obs + b_act + b_s]      # obs, act, rew, next_obs, done
+            raw = st["raw"]
+            base = st["block"].data_ptr()
+            for off, a, sh in zip(offs, np_arrs, shapes):
+                cnt = int(np.prod(sh))
+                np.copyto(raw[off:off + 4 * cnt].view(np.float32).reshape(sh), a.reshape(sh), casting="unsafe")
             N.check(self._lib.ddrl_rb_store_batch_host(
-                self._h, *[_ptr(t) for t in views], n, N.F32, C.c_void_p(s.cuda_stream)))
+                self._h, *[C.c_void_p(base + off) for off in offs], n, N.F32, C.c_void_p(s.cuda_stream)))
             ev = torch.cuda.Event()
             ev.record(s)
             st["event"] = ev

@@ -29,9 +29,9 @@ N_IT = 300
 for it in range(N_IT + 20):
     if it == 20:
         T.clear(); torch.cuda.synchronize(); t_all = time.perf_counter()
-    t = time.perf_counter(); rb.store_batch(*new); tick("store_batch(host)", t)
     t = time.perf_counter(); batch = rb.sample_batch(B); tick("sample_batch->numpy", t)
     t = time.perf_counter(); out = L.train(batch); tick("train(numpy) enqueue", t)
+    t = time.perf_counter(); rb.store_batch(*new); tick("store_batch(host)", t)
     t = time.perf_counter(); sc = out["scalars"].cpu(); tick("losses.cpu()", t)
 torch.cuda.synchronize()
 tot = time.perf_counter() - t_all
