@@ -914,8 +914,9 @@ __global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_
 // ------------------------------------------------------------------------------------------------
 struct PeerComm {
   float* buf[8];            // rank r's communication buffer as mapped in this process
-  unsigned int* flags[8];   // rank r's arrival flags (flags[r][i] = last step rank i has published)
-  int world, rank;
+  unsigned int* flags[8];   // rank r's arrival flags (flags[r][i] = last step rank i has published); after the 8 whole-
+                            // gradient flags come the per-slice flags [8][nslice] of k_reduce_adam_peer
+  int world, rank, nslice;
   long long Pc;             // floats per slot (P + 4, multiple of 4)
 };
 __global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __restrict__ st, int64_t P, int S,
@@ -1012,6 +1013,91 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
     const float g = -(lp + target_entropy);
     st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * g;
     st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * g * g;
+    st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
+  }
+}
+
+// Experimental one-kernel form of the data-parallel step (DDRL_DP_SLICE=1; correct, but measured slower than the
+// reduce kernel + k_adam_polyak_peer pair at N = 2): the gradient is exchanged SLICE BY SLICE.  CTA b owns 1024 consecutive parameters: it sums its split-K partials into this rank's slot, publishes
+// "slice b of step t is ready" to every peer, waits for slice b of every peer — never for the whole gradient — reads the
+// peers' slices over NVLink and applies Adam + polyak to them.  No CTA depends on another CTA of its own grid, all CTAs
+// of every rank are co-resident (P / 1024 <= 8 CTAs x 148 SMs), so there is no grid-wide barrier and no separate
+// reduce kernel, and the flags of early slices travel while late slices are still being summed.
+__global__ void __launch_bounds__(256) k_reduce_adam_peer(StepState* st, int64_t P, int64_t P_pi, int S,
+                                                          const float* __restrict__ Gp, const float* __restrict__ SCAL,
+                                                          float lr, float polyak, float target_entropy, float* W, float* Wt,
+                                                          float* Mo, float* Vo, const __grid_constant__ SplitMap mp, float* Wsp,
+                                                          float* Wtsp, const __grid_constant__ PeerComm pc, int* err) {
+  pdl_trigger();
+  pdl_wait();
+  const unsigned int epoch = (unsigned int)st->t_pi;
+  const size_t slot = (size_t)(epoch & 1u) * pc.Pc;
+  const int b = blockIdx.x, world = pc.world;
+  const int64_t i = ((int64_t)b * blockDim.x + threadIdx.x) * 4;
+  float* mine = pc.buf[pc.rank] + slot;
+  if (i < P) {
+    float4 g = *reinterpret_cast<const float4*>(Gp + i);
+    for (int s2 = 1; s2 < S; ++s2) {
+      const float4 q = *reinterpret_cast<const float4*>(Gp + (size_t)s2 * P + i);
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    *reinterpret_cast<float4*>(mine + i) = g;
+  }
+  if (b == 0 && threadIdx.x == 0) mine[P] = SCAL[4];      // mean logp1 of this rank's batch, travels with slice 0
+  __syncthreads();                                        // the CTA's slice is written (CTA-scope order) ...
+  if (threadIdx.x < world) {
+    __threadfence_system();                               // ... and published by the few signalling threads (cumulative)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc.flags[threadIdx.x] + 8 + (size_t)pc.rank * pc.nslice + b), "r"(epoch)
+                 : "memory");
+    const unsigned int* f = pc.flags[pc.rank] + 8 + (size_t)threadIdx.x * pc.nslice + b;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v < epoch && clock64() - t0 > 20000000000LL) { *err = 1; break; }   // ~10 s: a peer died; do not hang the GPU
+    } while (v < epoch);
+  }
+  __syncthreads();
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  if (i < P) {
+    const float lr_pi = st->lr_pi, lr_q = st->lr_q, gs = st->dyn.grad_scale;
+    float4 q[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) q[r] = ld_volatile_f4(pc.buf[r] + slot + i);
+    float4 g = q[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+      if (r < world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
+    const float gv[4] = {g.x * gs, g.y * gs, g.z * gs, g.w * gs};
+    const float4 m4 = *reinterpret_cast<const float4*>(Mo + i), v4 = *reinterpret_cast<const float4*>(Vo + i);
+    const float4 w4 = *reinterpret_cast<const float4*>(W + i), t4 = *reinterpret_cast<const float4*>(Wt + i);
+    const float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w},
+                tv[4] = {t4.x, t4.y, t4.z, t4.w};
+    float mo[4], vo[4], wo[4], to[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mo[e] = b1 * mv[e] + (1.0f - b1) * gv[e];
+      vo[e] = b2 * vv[e] + (1.0f - b2) * gv[e] * gv[e];
+      wo[e] = wv[e] - (i + e < P_pi ? lr_pi : lr_q) * mo[e] / (sqrtf(vo[e]) + eps);
+      to[e] = polyak * tv[e] + (1.0f - polyak) * wo[e];
+      if (Wsp) { write_split(mp, i + e, wo[e], Wsp); write_split(mp, i + e, to[e], Wtsp); }
+    }
+    *reinterpret_cast<float4*>(Mo + i) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+    *reinterpret_cast<float4*>(Vo + i) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+    *reinterpret_cast<float4*>(W + i) = make_float4(wo[0], wo[1], wo[2], wo[3]);
+    *reinterpret_cast<float4*>(Wt + i) = make_float4(to[0], to[1], to[2], to[3]);
+  }
+  if (b == 0 && threadIdx.x == 0 && st->auto_alpha) {
+    float lp = 0.0f;
+    for (int r = 0; r < world; ++r) lp += *reinterpret_cast<volatile const float*>(pc.buf[r] + slot + P);
+    lp *= st->dyn.grad_scale;
+    st->t_alpha += 1;
+    const double ta = (double)st->t_alpha;
+    const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
+    const float ga = -(lp + target_entropy);
+    st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * ga;
+    st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * ga * ga;
     st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
   }
 }
@@ -1199,6 +1285,7 @@ struct ddrl_sac {
   int ld1 = 0, ld2 = 0, ldx = 0, ldh = 0;   // ldh: head block row pitch
   long long lo1 = 0, lo2 = 0, lox = 0;
   float* XA[3] = {};                    // [x|a], [x|a1], [x2|a3] split planes
+  bool dp_slice = false;                // DDRL_DP_SLICE=1: slice-wise one-kernel gradient exchange (k_reduce_adam_peer)
   bool merge_stages = false;            // DDRL_MERGE=1: dependent forward GEMM stages share one launch (tile dependency
                                         // counters).  Measured gain 0.7 us of 116 at C2 — the per-stage cost is the
                                         // TMA -> MMA -> epilogue latency chain, not the launch — so it stays opt-in.
@@ -1775,9 +1862,21 @@ int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
     if ((rc = enqueue_grads(h, pl, s))) return rc;
     return enqueue_reduce(h, pl, s);
   }
-  if (mode == MODE_DP) {   // fused data-parallel step: gradients -> exchange buffer -> peer all-reduce + optimiser
+  if (mode == MODE_DP && !h->dp_slice) {   // fused data-parallel step: gradients -> exchange buffer -> peer all-reduce + optimiser
     if ((rc = enqueue_grads(h, pl, s))) return rc;
     if ((rc = enqueue_reduce(h, pl, s))) return rc;
+    return enqueue_apply(h, 1, h->G, s);
+  }
+  if (mode == MODE_DP) {   // DDRL_DP_SLICE=1: ONE kernel: reduce + slice-wise peer exchange + optimiser.  Bit-identical results;
+                           // measured SLOWER at N = 2 (140 vs 127 us per step), so the two-kernel form stays the default
+    if ((rc = enqueue_grads(h, pl, s))) return rc;
+    const int blocks = (int)((h->P / 4 + 255) / 256);
+    if (blocks > h->pc.nslice) return fail(DDRL_ESTATE, "exchange buffer has %d slice flags, need %d", h->pc.nslice, blocks);
+    DDRL_CUDA(launch_pdl(k_reduce_adam_peer, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, pl.S, (const float*)h->Gp,
+                         (const float*)h->SCAL, h->lr, h->polyak, -(float)h->A, h->W, h->Wt, h->Mo, h->Vo, h->smap,
+                         h->use_tc ? h->Wsp : nullptr, h->use_tc ? h->Wtsp : nullptr, h->pc, h->d_err));
+    DDRL_LAUNCH_CHECK();
+    return 0;
   }
   return enqueue_apply(h, 1, h->G, s);
 }
@@ -1882,6 +1981,8 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     const char* fz = getenv("DDRL_FUSE_L1");
     h->fuse_l1 = h->use_tc && D + A <= FUSE_MAXK && h1 % 32 == 0 && 2 * A <= 16 && (h2 & 3) == 0 && !(fz && fz[0] == '0');
     h->fuse_l1_force = fz && fz[0] == '2';
+    const char* dz = getenv("DDRL_DP_SLICE");
+    h->dp_slice = dz && dz[0] == '1';
     const char* mz = getenv("DDRL_MERGE");
     h->merge_stages = mz && mz[0] == '1';
   }
@@ -2098,7 +2199,8 @@ int ddrl_sac_comm_export(ddrl_sac_t h, void* h_handle64) {
   DeviceGuard guard(h->device);
   if (!h->comm) {
     const long long Pc = (h->P + 4 + 3) / 4 * 4;
-    const size_t bytes = (size_t)2 * Pc * sizeof(float) + 8 * sizeof(unsigned int);
+    h->pc.nslice = (int)((h->P / 4 + 255) / 256);
+    const size_t bytes = (size_t)2 * Pc * sizeof(float) + (8 + 8 * (size_t)h->pc.nslice) * sizeof(unsigned int);
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);   // its own allocation: CUDA IPC shares whole allocations
     if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaMalloc(comm buffer) failed: %s", cudaGetErrorString(e));
