@@ -505,7 +505,23 @@ __device__ __forceinline__ void seg_route(const SegArgs& a, int64_t b, int f, fl
   for (int s = 0; s < 8; ++s)
     if (s < a.nseg && f >= a.off[s] && f < a.off[s] + a.w[s]) a.out[s][b * a.w[s] + (f - a.off[s])] = x;
 }
+// which segment a 16-byte chunk belongs to when it can leave as ONE 128-bit store (inside one segment, 16-byte aligned
+// on both sides), else 255: looked up per chunk from a table built once per CTA instead of searched per chunk
+__device__ __forceinline__ int seg_of_chunk(const SegArgs& a, int c) {
+  const int f = 4 * c;
+  int hit = 255;
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < a.nseg && f >= a.off[s] && f + 3 < a.off[s] + a.w[s] && ((a.w[s] | (f - a.off[s])) & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(a.out[s]) & 15) == 0))
+      hit = s;
+  return hit;
+}
+constexpr int SEG_TBL = 4096;
 __global__ void __launch_bounds__(256) rb_gather_segments(const SegArgs a) {
+  __shared__ unsigned char s_seg[SEG_TBL];
+  for (int c = threadIdx.x; c < min(a.row_f4, SEG_TBL); c += blockDim.x) s_seg[c] = (unsigned char)seg_of_chunk(a, c);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -526,17 +542,11 @@ __global__ void __launch_bounds__(256) rb_gather_segments(const SegArgs a) {
       for (int u = 0; u < 4; ++u) {
         const int c = c0 + 32 * u;
         if (c >= a.row_f4) continue;
-        const int f = 4 * c;
-        bool done = false;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          if (s < a.nseg && f >= a.off[s] && f + 3 < a.off[s] + a.w[s] && ((a.w[s] | (f - a.off[s])) & 3) == 0 &&
-              ((reinterpret_cast<uintptr_t>(a.out[s]) & 15) == 0)) {
-            st_f4(reinterpret_cast<float4*>(a.out[s] + b * a.w[s] + (f - a.off[s])), v[u]);
-            done = true;
-          }
-        }
-        if (!done) {
+        const int sg = c < SEG_TBL ? (int)s_seg[c] : seg_of_chunk(a, c);
+        if (sg != 255) {
+          st_f4(reinterpret_cast<float4*>(a.out[sg] + b * a.w[sg] + (4 * c - a.off[sg])), v[u]);
+        } else {
+          const int f = 4 * c;
           seg_route(a, b, f + 0, v[u].x);
           seg_route(a, b, f + 1, v[u].y);
           seg_route(a, b, f + 2, v[u].z);
