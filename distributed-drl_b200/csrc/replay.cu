@@ -134,7 +134,7 @@ __device__ __forceinline__ void route_store(const LaneRoute& r, int64_t b, const
 }
 
 template <int LANES, int U>
-__global__ void __launch_bounds__(256, U >= 8 ? 2 : ((LANES == 8 || LANES == 16) ? 4 : 3)) rb_gather_narrow(const GatherArgs a) {
+__global__ void __launch_bounds__(256, (U >= 8 || LANES <= 4) ? 2 : ((LANES == 8 || LANES == 16) ? 4 : 3)) rb_gather_narrow(const GatherArgs a) {
   constexpr int RPP = 32 / LANES;  // rows per pass of a warp
   static_assert(U <= LANES && LANES % U == 0, "U rows in flight per lane group");
   const int lane = threadIdx.x & 31;

@@ -29,7 +29,6 @@ struct GemmProb {
   int a_ones;
   int a_trans;
   const float* B;
-  const float* B2;   // nullable: second plane added to B on load (hi + lo of a pre-split tensor, exact)
   int ldb;
   int b_trans;
   float* C;
@@ -97,7 +96,6 @@ __device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, 
       const int nl = i % BN, kl = i / BN;
       const int n = n0 + nl, k = k0 + kl;
       r.b[e] = ld_pred(P.B + (size_t)k * P.ldb + n, n < P.N && k < kend);
-      if (P.B2) r.b[e] += ld_pred(P.B2 + (size_t)k * P.ldb + n, n < P.N && k < kend);
     }
   } else {
 #pragma unroll
@@ -106,7 +104,6 @@ __device__ __forceinline__ void fetch_tiles(const GemmProb& P, int tid, int m0, 
       const int kl = i % BK, nl = i / BK;
       const int n = n0 + nl, k = k0 + kl;
       r.b[e] = ld_pred(P.B + (size_t)n * P.ldb + k, n < P.N && k < kend);
-      if (P.B2) r.b[e] += ld_pred(P.B2 + (size_t)n * P.ldb + k, n < P.N && k < kend);
     }
   }
 }
