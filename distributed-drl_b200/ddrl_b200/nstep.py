@@ -25,6 +25,27 @@ import torch
 from . import _native as N
 
 
+def row_layout(Ln, D, A):
+    """(widths, offsets, used floats, padded row floats) of the packed sequence row [obs | acts | rews | done]."""
+    widths = [(Ln + 1) * D, Ln * A, Ln, Ln]
+    offsets = [0, widths[0], widths[0] + widths[1], widths[0] + widths[1] + Ln]
+    used = sum(widths)
+    return widths, offsets, used, (used + 3) // 4 * 4
+
+
+def pack_rows(obs, acts, rews, done, Ln, D, A):
+    """[n, Ln+1, ...], [n, Ln, ...], [n, Ln], [n, Ln] -> packed float32 rows [n, row_f] (numpy assignment casts, as the
+    reference's `buffer[ptr] = np.array(..., dtype=np.float32)` does)."""
+    widths, o, _, row_f = row_layout(Ln, D, A)
+    n = int(np.asarray(rews).shape[0])
+    rows = np.zeros((n, row_f), dtype=np.float32)
+    rows[:, o[0]:o[0] + widths[0]] = np.asarray(obs).reshape(n, -1)
+    rows[:, o[1]:o[1] + widths[1]] = np.asarray(acts).reshape(n, -1)
+    rows[:, o[2]:o[2] + Ln] = np.asarray(rews).reshape(n, -1)
+    rows[:, o[3]:o[3] + Ln] = np.asarray(done).reshape(n, -1)
+    return rows
+
+
 class NStepReplayBuffer:
     def __init__(self, opt, *, device=None, seed=None, rng_stream=0, index_source="philox"):
         if not torch.cuda.is_available():
@@ -38,10 +59,7 @@ class NStepReplayBuffer:
         self.Ln = int(opt.Ln)
         self.obs_shape, self.act_shape = tuple(opt.obs_shape), tuple(opt.act_shape)
         self.D, self.A = int(np.prod(self.obs_shape)), int(np.prod(self.act_shape)) if self.act_shape else 1
-        self.widths = [(self.Ln + 1) * self.D, self.Ln * self.A, self.Ln, self.Ln]
-        self.offsets = [0, self.widths[0], self.widths[0] + self.widths[1], self.widths[0] + self.widths[1] + self.Ln]
-        self.used = sum(self.widths)
-        self.row_f = (self.used + 3) // 4 * 4
+        self.widths, self.offsets, self.used, self.row_f = row_layout(self.Ln, self.D, self.A)
         self.max_size = int(opt.buffer_size)
         self.batch_size = int(opt.batch_size)
         self.num_buffers = int(getattr(opt, "num_buffers", 1))
@@ -53,15 +71,7 @@ class NStepReplayBuffer:
 
     # ---- store -----------------------------------------------------------------------------------
     def _pack(self, obs, acts, rews, done):
-        """[n, Ln+1, ...], [n, Ln, ...], [n, Ln], [n, Ln] -> packed float32 rows [n, row_f] (numpy assignment casts)."""
-        n = int(np.asarray(rews).shape[0])
-        rows = np.zeros((n, self.row_f), dtype=np.float32)
-        o = self.offsets
-        rows[:, o[0]:o[0] + self.widths[0]] = np.asarray(obs).reshape(n, -1)
-        rows[:, o[1]:o[1] + self.widths[1]] = np.asarray(acts).reshape(n, -1)
-        rows[:, o[2]:o[2] + self.Ln] = np.asarray(rews).reshape(n, -1)
-        rows[:, o[3]:o[3] + self.Ln] = np.asarray(done).reshape(n, -1)
-        return rows
+        return pack_rows(obs, acts, rews, done, self.Ln, self.D, self.A)
 
     def store_batch(self, obs, acts, rews, done):
         """n sequences at once (== n store() calls in row order); only the last `capacity` survive."""

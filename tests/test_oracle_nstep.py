@@ -72,3 +72,27 @@ def test_vector_actions_and_empty():
         ora.store(oq, aq)
     assert ora.buffer_a.shape == (4, 3, 2) and ora.size == 4 and ora.ptr == 2
     assert np.array_equal(ora.buffer_o[1], np.stack([x[0] for x in seqs[5][0]]))    # slot 1 holds the 6th sequence
+
+
+def test_packed_row_layout_round_trips_the_oracle_arrays():
+    """Host logic of ddrl_b200.NStepReplayBuffer (no GPU): the packed row [obs | acts | rews | done] holds exactly the
+    oracle's four arrays at the segment offsets ddrl_seg_sample is given, float64 / bool inputs cast like numpy assignment."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "distributed-drl_b200"))
+    from ddrl_b200.nstep import pack_rows, row_layout
+    opt = SimpleNamespace(Ln=3, obs_shape=(5,), act_shape=(2,), buffer_size=8, batch_size=4, num_buffers=1)
+    ora = NStepRingOracle(opt)
+    seqs = make_sequences(opt, 6, 2)
+    for oq, aq in seqs:
+        ora.store(oq, aq)
+    widths, off, used, row_f = row_layout(3, 5, 2)
+    assert (widths, off, used, row_f) == ([20, 6, 3, 3], [0, 20, 26, 29], 32, 32)
+    obs = np.stack([np.stack([o[0] for o in oq]) for oq, _ in seqs]).astype(np.float64)
+    act = np.stack([np.stack([a for a, _, _ in aq]) for _, aq in seqs])
+    rew = np.array([[r for _, r, _ in aq] for _, aq in seqs], dtype=np.float64)
+    done = np.array([[d for _, _, d in aq] for _, aq in seqs])
+    rows = pack_rows(obs, act, rew, done, 3, 5, 2)
+    assert rows.dtype == np.float32 and rows.shape == (6, 32)
+    assert np.array_equal(rows[:, 0:20].reshape(6, 4, 5), ora.buffer_o[:6])
+    assert np.array_equal(rows[:, 20:26].reshape(6, 3, 2), ora.buffer_a[:6])
+    assert np.array_equal(rows[:, 26:29], ora.buffer_r[:6]) and np.array_equal(rows[:, 29:32], ora.buffer_d[:6])
