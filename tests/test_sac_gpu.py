@@ -232,3 +232,25 @@ def test_train_from_buffer_equals_sample_then_train(L):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert np.array_equal(res[0][2], res[1][2])
     assert res[0][3] == res[1][3]          # sample_times / steps / size advance identically
+
+
+@pytest.mark.parametrize("D,A,B,scale", [(24, 4, 1024, 1.0), (376, 17, 4096, 0.4)], ids=["C2-full", "C3-full"])
+def test_full_size_step_matches_oracle(L, D, A, B, scale):
+    """BASELINE.json's full batch sizes (C2: 1024, C3: 4096 rows of the Humanoid shape) through the default tcgen05 path:
+    losses, per-row Q values / log-probabilities and gradients against the float64 oracle at the same bars."""
+    hidden = (256, 256)
+    params = conditioned_params(D, A, hidden, seed=300 + D)
+    learner, oracle = build_pair(L, D, A, hidden, B, params, act_scale=scale)
+    batch, noise = make_batch(D, A, B, seed=400 + D)
+    want_g = oracle.flat_grads(batch, noise)
+    want = oracle.step(batch, noise)
+    got = learner.train(batch, noise=noise, split=True, sync_outputs=True)
+    sc = got["scalars"].cpu().numpy()
+    for i, k in enumerate(("pi_loss", "q1_loss", "q2_loss")):
+        assert abs(sc[i] - float(want[k])) <= TOL * abs(float(want[k])), (k, sc[i], float(want[k]))
+    for k in ("q1", "q2", "logp_pi"):
+        assert rel(got[k].cpu().numpy(), want[k]) <= TOL, k
+    assert rel(learner.get_flat_weights("grad").cpu().numpy(), want_g) <= 2 * TOL
+    got_w, want_w = learner.get_flat_weights("main").cpu().numpy(), oracle.flat("main")
+    solid = np.abs(want_g) > 1e-4 * np.abs(want_g).max()
+    assert rel(got_w[solid], want_w[solid]) <= TOL
