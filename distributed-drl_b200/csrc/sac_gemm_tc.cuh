@@ -17,10 +17,13 @@
 //   warps 0, 2 / lane 0   TMA producers (A planes, B planes): per k-block (32 tf32 = one 128-byte swizzle row)
 //                     load A_hi, A_lo / B_hi, B_lo with cp.async.bulk.tensor into a 64 KB stage; out-of-range
 //                     rows / columns / k are zero-filled by the TMA unit (ragged M, N, K need no code)
-//   warp 1 / lane 0   MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 per stage, then
+//   warp 1 / lane 0   MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 per stage into one of two TMEM
+//                     accumulators (alternating k-blocks: halves the accumulation truncation bias), then
 //                     tcgen05.commit to the stage's "empty" barrier; the last commit signals the epilogue
-//   all 8 warps       epilogue: tcgen05.ld (32 lanes x 32 columns), bias / relu / relu-mask, then either a
-//                     plain fp32 store or the hi/lo pair the next GEMM consumes.
+//   all 8 warps       epilogue: tcgen05.ld (32 lanes x 32 columns) of both accumulators, summed with RN adds, bias
+//                     (prefetched to shared memory during the main loop) / relu (+ bit mask) / relu-mask, then the
+//                     plain fp32 tile or the hi/lo pair the next GEMM consumes goes out through swizzled shared
+//                     memory and TMA stores (direct stores when the output is not 16-byte pitched).
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor) and
 // cute/atom/mma_traits_sm100.hpp (canonical K-major / MN-major SWIZZLE_128B layouts).
 #pragma once
