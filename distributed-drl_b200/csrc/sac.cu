@@ -48,10 +48,8 @@ struct StepDyn {   // per-step values: by-value argument of the prologue kernel,
   unsigned int ring_stream;
   unsigned long long ring_seed, ring_counter, ring_size;
 };
-constexpr int DEP_FLAGS = 128;
 struct StepState {  // persistent
   StepDyn dyn;
-  unsigned int dep_flags[DEP_FLAGS];   // zeroed by every prologue; see TcProb::sig_ctr / dep_ctr
   int t_pi, t_q, t_alpha;
   unsigned long long noise_counter;
   float log_alpha, alpha_m, alpha_v;
@@ -75,80 +73,8 @@ __device__ __forceinline__ void put_split(float* hi_plane, long long plane, size
   hi_plane[idx] = hi;
   hi_plane[plane + idx] = lo;
 }
-// Narrow first layers (K = D or D + A <= 32) are not worth a tensor-core launch of their own (a 1-k-block tcgen05
-// stage costs ~9 us of fixed latency): they are computed with FFMA inside the kernels that already hold their
-// inputs — the five data passes here in the prologue, the three policy-action Q passes in the policy-head kernel.
-// One thread per output column keeps its weight column in registers and walks the CTA's rows; outputs go out as the
-// hi/lo planes + relu bit masks the second-layer tcgen05 stage expects.
-constexpr int FUSE_MAXK = 32;
-constexpr int FUSE_RB = 8;          // rows per CTA in the policy-head kernel (= ROW_WARPS)
-constexpr int FUSE_PRB = 16;        // rows per work item in the prologue
-struct L1Fuse {
-  int on, h1, ld1, ldbits;
-  long long lo1;
-  const float* W[5];                // [K + 1, h1] weight blocks (fp32 master copies; pass 2 = target policy)
-  float* H1[5];
-  uint32_t* bits[5];
-};
-__device__ __forceinline__ void fused_dense_relu_store(float acc, int row, int n, int ld1, long long lo1, int ldbits, float* H1,
-                                                       uint32_t* bits) {
-  const unsigned int m = __ballot_sync(0xffffffffu, acc > 0.0f);     // 32 consecutive columns per warp
-  if ((threadIdx.x & 31) == 0) bits[(size_t)row * ldbits + (n >> 5)] = m;
-  put_split(H1, lo1, (size_t)row * ld1 + n, fmaxf(acc, 0.0f));
-}
-// CTA-level dense layer for FUSE_RB rows held in shared memory: thread = output column (weight column in registers,
-// one coalesced L2 round trip), loop over the rows.  `in` rows are zero padded to FUSE_MAXK.
-template <int RB>
-__device__ __forceinline__ void cta_dense_rows(const float (*in)[FUSE_MAXK], int nrows, int row0, int K, const float* __restrict__ W,
-                                               const L1Fuse& f, float* H1, uint32_t* bits) {
-  for (int n = threadIdx.x; n < f.h1; n += blockDim.x) {       // h1 % 32 == 0: whole warps
-    float w[FUSE_MAXK];
-#pragma unroll
-    for (int k = 0; k < FUSE_MAXK; ++k) w[k] = k < K ? W[(size_t)k * f.h1 + n] : 0.0f;
-    const float bias = W[(size_t)K * f.h1 + n];
-#pragma unroll 2
-    for (int r = 0; r < RB; ++r) {
-      if (r >= nrows) break;                                   // block-uniform
-      float a0 = bias, a1 = 0.0f;
-#pragma unroll
-      for (int k = 0; k < FUSE_MAXK; k += 2) { a0 = fmaf(in[r][k], w[k], a0); a1 = fmaf(in[r][k + 1], w[k + 1], a1); }
-      fused_dense_relu_store(a0 + a1, row0 + r, n, f.ld1, f.lo1, f.ldbits, H1, bits);
-    }
-  }
-}
-// work item = (block of FUSE_RB rows, pass): 5 * ceil(B / FUSE_RB) items dealt round-robin to the CTAs
-__device__ __forceinline__ void d_prologue_l1(int vb, int vgrid, const StepDyn& d, const L1Fuse& f, int B, int D, int A) {
-  __shared__ float s_in[FUSE_PRB][FUSE_MAXK];
-  __shared__ long long s_idx[FUSE_PRB];
-  const int tid = threadIdx.x;
-  const int nblk = (B + FUSE_PRB - 1) / FUSE_PRB;
-  for (int item = vb; item < 5 * nblk; item += vgrid) {
-    const int p = item / nblk, r0 = (item - p * nblk) * FUSE_PRB;
-    const int K = p < 3 ? D : D + A;
-    const int nrows = min(FUSE_PRB, B - r0);
-    __syncthreads();
-    if (d.ring && tid < nrows)
-      s_idx[tid] = philox_index((uint64_t)(r0 + tid), d.ring_seed, d.ring_counter, d.ring_stream, d.ring_size);
-    if (d.ring) __syncthreads();
-    for (int i = tid; i < FUSE_PRB * FUSE_MAXK; i += blockDim.x) {
-      const int r = i / FUSE_MAXK, k = i - r * FUSE_MAXK, row = r0 + r;
-      float v = 0.0f;
-      if (r < nrows && k < K) {
-        // pass 0: x   passes 1, 2: x2   passes 3, 4: [x | a]       (ring row = [obs1 | obs2 | acts | rew | done])
-        const int c = (p == 1 || p == 2) ? D + k : (k < D ? k : 2 * D + (k - D));
-        if (d.ring) v = d.ring[(size_t)s_idx[r] * d.ring_row_f + c];
-        else v = c < D ? d.obs1[(size_t)row * D + c] : c < 2 * D ? d.obs2[(size_t)row * D + (c - D)] : d.acts[(size_t)row * A + (c - 2 * D)];
-      }
-      s_in[r][k] = v;
-    }
-    __syncthreads();
-    cta_dense_rows<FUSE_PRB>(s_in, nrows, r0, K, f.W[p], f, f.H1[p], f.bits[p]);
-  }
-}
-
 __device__ __forceinline__ void d_prologue(int vb, int vgrid, StepState* st, const StepDyn& d, int B, int D, int A,
                                            float* X, float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
-  if (vb == 0 && threadIdx.x < DEP_FLAGS) st->dep_flags[threadIdx.x] = 0u;   // tile dependency counters of merged stages
   if (vb == 0 && threadIdx.x == 0) {
     // publish the step's values for the kernels of the captured graph that follow
     st->dyn = d;
@@ -224,12 +150,10 @@ __device__ __forceinline__ void d_prologue(int vb, int vgrid, StepState* st, con
   }
 }
 __global__ void __launch_bounds__(256) k_prologue(StepState* st, const __grid_constant__ StepDyn dyn, int B, int D, int A, float* X,
-                                                  float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa,
-                                                  const __grid_constant__ L1Fuse l1) {
+                                                  float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
   pdl_trigger();
   pdl_wait();
   d_prologue(blockIdx.x, gridDim.x, st, dyn, B, D, A, X, X2, ACT, R, DN, NOISE, xa);
-  if (l1.on) d_prologue_l1(blockIdx.x, gridDim.x, dyn, l1, B, D, A);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,8 +231,12 @@ __device__ __forceinline__ void warp_dots(const float* __restrict__ x, int K, co
   __syncwarp();
 }
 
-// policy heads + squashed-Gaussian sample / log-likelihood for the three policy passes
+// policy heads + squashed-Gaussian sample / log-likelihood for the policy passes
 // (pass 0: main pi(x) -> A1, LOGP1, HD;  pass 1: main pi(x2) -> LOGP2;  pass 2: target pi(x2) -> A3)
+// A launch covers `npass` of them: slot s of the grid (rows [s B, (s+1) B)) is logical pass pmap.p[s].  The step runs
+// passes 0 and 2 after the first forward stage (their actions feed the second one) and pass 1 after the second
+// forward stage, where main pi(x2) now lives so that both forward stages fit on the chip in one wave.
+struct PassMap { int n, p[3]; };
 // One THREAD per (row, head output): the row of H2 sits in shared memory, the weight column W[:, j] is read
 // with the same address across the rows of a CTA (L1 broadcast) and consecutive j are consecutive floats.
 // R = 256 / 2A rows per CTA.  ldh = row pitch of the head block (2A rounded up to 4 floats).
@@ -319,7 +247,8 @@ template <int RB>
 __global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
     int B, int A, int h2, int ldh, int R, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
-    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D) {
+    const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D,
+    PassMap pmap) {
   extern __shared__ __align__(16) float hsm[];
   pdl_trigger();
   pdl_wait();
@@ -329,7 +258,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
   float* s_pre = s_out + R * n;       // [R][A]   gaussian log-likelihood terms
   float* s_sq = s_pre + R * A;        // [R][A]   squash correction terms
   const int tid = threadIdx.x;
-  const int total = 3 * B, g0 = blockIdx.x * R;
+  const int total = pmap.n * B, g0 = blockIdx.x * R;
   const bool vec = (h2 & 3) == 0;
   {
     // stage the R rows of H2 (a CTA's rows may straddle two passes)
@@ -337,7 +266,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
     for (int r = tid / q, c = tid - (tid / q) * q; r < R; ) {
       const int g = g0 + r;
       if (g < total) {
-        const int pass = g / B, row = g - pass * B;
+        const int slot = g / B, row = g - slot * B, pass = pmap.p[slot];
         const float* src = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
         if (vec) *reinterpret_cast<float4*>(xs + r * ldx + 4 * c) = *reinterpret_cast<const float4*>(src + 4 * c);
         else xs[r * ldx + c] = src[c];
@@ -355,9 +284,9 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
   const int rg = tid / n, j = tid - rg * n;
   if (rg < groups) {
     // all RB rows of a thread use the same weight column: groups start at multiples of RB and the host picks
-    // RB = 4 only when B % 4 == 0, so a group never straddles the main / target boundary at row 2B
+    // RB = 4 only when B % 4 == 0, so a group never straddles a pass boundary
     const int g_first = g0 + rg * RB;
-    const int pass_w = min(g_first, total - 1) / B;
+    const int pass_w = pmap.p[min(g_first, total - 1) / B];
     const float* W = (pass_w == 2 ? Whead_t : Whead) + j;
     const float* x = xs + rg * RB * ldx;
     float acc[RB][2];
@@ -390,7 +319,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
       if (g < total) {
         const float v = (acc[rb][0] + acc[rb][1]) + bias;
         s_out[r * n + j] = v;
-        if (g < B) HD[(size_t)g * n + j] = v;      // pass 0
+        if (pmap.p[g / B] == 0) HD[(size_t)(g % B) * n + j] = v;
       }
     }
   }
@@ -399,7 +328,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
   for (int i = tid; i < R * A; i += HEADS_THREADS) {
     const int r = i / A, ja = i - r * A, g = g0 + r;
     if (g >= total) continue;
-    const int pass = g / B, row = g - pass * B;
+    const int slot = g / B, row = g - slot * B, pass = pmap.p[slot];
     const float eps = NOISE[((size_t)pass * B + row) * A + ja];
     const PolEl e = policy_elem(s_out[r * n + ja], s_out[r * n + A + ja], eps);
     s_pre[i] = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
@@ -416,14 +345,16 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_policy_heads_fwd(
   __syncthreads();
   for (int r = tid; r < R; r += HEADS_THREADS) {
     const int g = g0 + r;
-    if (g >= 2 * B) continue;                       // pass 2 (target policy) needs no log-likelihood
+    if (g >= total) continue;
+    const int pass = pmap.p[g / B];
+    if (pass == 2) continue;                        // the target policy needs no log-likelihood
     // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
     float gauss = 0.0f, squash = 0.0f;
     for (int t = 0; t < A; ++t) {
       gauss = __fadd_rn(gauss, s_pre[r * A + t]);
       squash = __fadd_rn(squash, s_sq[r * A + t]);
     }
-    (g < B ? LOGP1 : LOGP2)[g < B ? g : g - B] = __fsub_rn(gauss, squash);
+    (pass == 0 ? LOGP1 : LOGP2)[g % B] = __fsub_rn(gauss, squash);
   }
 }
 
@@ -464,84 +395,63 @@ __device__ __forceinline__ void heads_row_dots(const float* __restrict__ x, int 
   }
   __syncwarp();
 }
+// one row of the narrow policy head + squashed-Gaussian sample / log-likelihood; all lanes return logp, lanes < A the
+// scaled action in *act_out, lanes < 2A find the head pre-activations in sout
+__device__ __forceinline__ float heads_row_eval(const float* __restrict__ x, int h2, int ldh, int A, const float* __restrict__ W,
+                                                const float* __restrict__ eps, float act_scale, float* sout, int lane,
+                                                float* act_out) {
+  switch (ldh) {
+    case 4: heads_row_dots<1>(x, h2, W, 2 * A, sout, lane); break;
+    case 8: heads_row_dots<2>(x, h2, W, 2 * A, sout, lane); break;
+    case 12: heads_row_dots<3>(x, h2, W, 2 * A, sout, lane); break;
+    default: heads_row_dots<4>(x, h2, W, 2 * A, sout, lane); break;
+  }
+  float pre = 0.0f, sq = 0.0f;
+  *act_out = 0.0f;
+  if (lane < A) {
+    const PolEl e = policy_elem(sout[lane], sout[A + lane], eps[lane]);
+    pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
+    sq = logf(__fadd_rn(e.clipped, 1e-6f));
+    *act_out = __fmul_rn(e.pi, act_scale);
+  }
+  // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
+  float gauss = 0.0f, squash = 0.0f;
+  for (int t = 0; t < A; ++t) {
+    gauss = __fadd_rn(gauss, __shfl_sync(0xffffffffu, pre, t));
+    squash = __fadd_rn(squash, __shfl_sync(0xffffffffu, sq, t));
+  }
+  return __fsub_rn(gauss, squash);
+}
 __global__ void __launch_bounds__(ROW_WARPS * 32) k_policy_heads_rows(
     int B, int A, int h2, int ldh, float act_scale, const float* __restrict__ H2a, const float* __restrict__ H2b,
     const float* __restrict__ H2c, const float* __restrict__ Whead, const float* __restrict__ Whead_t,
     const float* __restrict__ NOISE, float* HD, float* A1, float* A3, float* LOGP1, float* LOGP2, XaOut xa, int D,
-    const __grid_constant__ L1Fuse ql1) {
+    PassMap pmap) {
   __shared__ float s_out[ROW_WARPS][16];
-  __shared__ float s_in[ROW_WARPS][FUSE_MAXK];
-  static_assert(ROW_WARPS == FUSE_RB, "the fused Q first layer walks one row per warp of the CTA");
   pdl_trigger();
   pdl_wait();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * ROW_WARPS + w;
-  const bool live = g < 3 * B;
-  const int pass = live ? g / B : 0, row = live ? g % B : 0;
-  if (live) {
-    const float* x = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
-    const float* W = pass == 2 ? Whead_t : Whead;
-    switch (ldh) {
-      case 4: heads_row_dots<1>(x, h2, W, 2 * A, s_out[w], lane); break;
-      case 8: heads_row_dots<2>(x, h2, W, 2 * A, s_out[w], lane); break;
-      case 12: heads_row_dots<3>(x, h2, W, 2 * A, s_out[w], lane); break;
-      default: heads_row_dots<4>(x, h2, W, 2 * A, s_out[w], lane); break;
-    }
-    const float* eps = NOISE + ((size_t)pass * B + row) * A;
-    float pre = 0.0f, sq = 0.0f, act_val = 0.0f;
-    if (lane < A) {
-      const PolEl e = policy_elem(s_out[w][lane], s_out[w][A + lane], eps[lane]);
-      pre = __fmul_rn(-0.5f, __fadd_rn(__fadd_rn(__fmul_rn(e.z, e.z), __fmul_rn(2.0f, e.log_std)), 1.8378770664093453f));
-      sq = logf(__fadd_rn(e.clipped, 1e-6f));
-      act_val = __fmul_rn(e.pi, act_scale);
-      if (pass == 0) {
-        A1[(size_t)row * A + lane] = act_val;
-        if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + lane, act_val);
-      } else if (pass == 2) {
-        A3[(size_t)row * A + lane] = act_val;
-        if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + lane, act_val);
-      }
-    }
-    // reduce_sum over the action axis, in index order, of the two terms separately (core.py:32,86)
-    float gauss = 0.0f, squash = 0.0f;
-    for (int t = 0; t < A; ++t) {
-      gauss = __fadd_rn(gauss, __shfl_sync(0xffffffffu, pre, t));
-      squash = __fadd_rn(squash, __shfl_sync(0xffffffffu, sq, t));
-    }
+  if (g >= pmap.n * B) return;
+  const int slot = g / B, row = g - slot * B, pass = pmap.p[slot];
+  const float* x = (pass == 0 ? H2a : pass == 1 ? H2b : H2c) + (size_t)row * h2;
+  float act_val;
+  const float logp = heads_row_eval(x, h2, ldh, A, pass == 2 ? Whead_t : Whead, NOISE + ((size_t)pass * B + row) * A, act_scale,
+                                    s_out[w], lane, &act_val);
+  if (lane < A) {
     if (pass == 0) {
-      if (lane < 2 * A) HD[(size_t)row * 2 * A + lane] = s_out[w][lane];
-      if (lane == 0) LOGP1[row] = __fsub_rn(gauss, squash);
-    } else if (pass == 1 && lane == 0) {
-      LOGP2[row] = __fsub_rn(gauss, squash);
+      A1[(size_t)row * A + lane] = act_val;
+      if (xa.xa_f) put_split(xa.xa_f, xa.plane, (size_t)row * xa.pitch + D + lane, act_val);
+    } else if (pass == 2) {
+      A3[(size_t)row * A + lane] = act_val;
+      if (xa.xa_g) put_split(xa.xa_g, xa.plane, (size_t)row * xa.pitch + D + lane, act_val);
     }
-    if (ql1.on && pass != 1) {
-      // input row of the fused policy-action Q first layer: exact hi + lo of the observation planes, then the
-      // action this warp has just drawn (2A <= 16 on this path), zero padded to FUSE_MAXK
-      const float* plane = pass == 0 ? xa.xa_f : xa.xa_g;
-      float v = 0.0f;
-      if (lane < D) { const size_t o = (size_t)row * xa.pitch + lane; v = plane[o] + plane[xa.plane + o]; }
-      s_in[w][lane] = v;
-      __syncwarp();
-      if (lane < A) s_in[w][D + lane] = act_val;
-    }
-  } else if (ql1.on) {
-    s_in[w][lane] = 0.0f;
   }
-  if (ql1.on) {
-    // f = Q1([x|a1]) for pass-0 CTAs; g = Q1_targ([x2|a3]) and h = Q2_targ([x2|a3]) for pass-2 CTAs.  The host fuses only
-    // when B % ROW_WARPS == 0, so a CTA's rows belong to one pass and are consecutive: the weight column read by a
-    // thread serves all 8 rows.
-    __syncthreads();
-    const int g0 = blockIdx.x * ROW_WARPS;
-    if (g0 < 3 * B) {
-      const int cpass = g0 / B, row0 = g0 - cpass * B;
-      const int nrows = min(ROW_WARPS, B - row0);
-      if (cpass == 0) cta_dense_rows<FUSE_RB>(s_in, nrows, row0, D + A, ql1.W[0], ql1, ql1.H1[0], ql1.bits[0]);
-      else if (cpass == 2) {
-        cta_dense_rows<FUSE_RB>(s_in, nrows, row0, D + A, ql1.W[1], ql1, ql1.H1[1], ql1.bits[1]);
-        cta_dense_rows<FUSE_RB>(s_in, nrows, row0, D + A, ql1.W[2], ql1, ql1.H1[2], ql1.bits[2]);
-      }
-    }
+  if (pass == 0) {
+    if (lane < 2 * A) HD[(size_t)row * 2 * A + lane] = s_out[w][lane];
+    if (lane == 0) LOGP1[row] = logp;
+  } else if (pass == 1 && lane == 0) {
+    LOGP2[row] = logp;
   }
 }
 
@@ -564,9 +474,14 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
     const float* __restrict__ H2f, const float* __restrict__ H2g, const float* __restrict__ H2h,
     const float* __restrict__ W3q1, const float* __restrict__ W3q2, const float* __restrict__ W3q1t,
     const float* __restrict__ W3q2t, const float* __restrict__ R, const float* __restrict__ DN,
-    const float* __restrict__ LOGP1, const float* __restrict__ LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
-    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz, long long zlo) {
+    const float* __restrict__ LOGP1, float* LOGP2, float* dQd, float* dQe, float* dZ2d, float* dZ2e,
+    float* dZ2f, double* partials, unsigned int* ticket, float* SCAL, int ldz, long long zlo,
+    // fold_b: the narrow policy head of pass b (main pi(x2) -> logp2) is evaluated here, by the warp that owns the row,
+    // instead of by a launch of its own between the second forward stage and this kernel
+    int fold_b, const float* __restrict__ H2b, const float* __restrict__ Whead, const float* __restrict__ NOISE, int A, int ldh,
+    float act_scale) {
   __shared__ double s_part[ROW_WARPS][4];
+  __shared__ float s_hout[ROW_WARPS][16];
   __shared__ bool s_last;
   pdl_trigger();
   pdl_wait();
@@ -608,8 +523,17 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
     qh = warp_sum(qh) + W3q2t[h2];
     const float invB = 1.0f / (float)B;
     const float lp1 = LOGP1[row];
+    float lp2;
+    if (fold_b) {
+      float unused;
+      lp2 = heads_row_eval(H2b + (size_t)row * h2, h2, ldh, A, Whead, NOISE + ((size_t)B + row) * A, act_scale, s_hout[w], lane,
+                           &unused);
+      if (lane == 0) LOGP2[row] = lp2;
+    } else {
+      lp2 = LOGP2[row];
+    }
     const float min_q = fminf(qg, qh);
-    const float v_backup = __fsub_rn(min_q, __fmul_rn(alpha, LOGP2[row]));
+    const float v_backup = __fsub_rn(min_q, __fmul_rn(alpha, lp2));
     const float q_backup = __fadd_rn(R[row], __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.0f, DN[row])), v_backup));
     const float e1 = __fsub_rn(q_backup, qd), e2 = __fsub_rn(q_backup, qe);
     const float dqd = -e1 * invB, dqe = -e2 * invB, dqf = -invB;
@@ -1241,9 +1165,12 @@ namespace {
 struct Group {
   std::vector<GemmProb> probs;          // FFMA tiles (cfg 0/1)
   std::vector<tc::TcProb> probs_tc;     // tcgen05 tiles
+  std::vector<tc::FusedProb> probs_fz;  // tcgen05 fused first + second layer tiles
   GemmGroup grp{};                      // the same, packed as kernel parameters
   tc::TcGroup grp_tc{};
-  int tiles = 0, tiles_tc = 0;
+  tc::FusedGroup grp_fz{};
+  int tiles = 0, tiles_tc = 0, tiles_fz = 0;
+  int bn = 128;                         // tile width of the tcgen05 launch (64 when 128-wide tiles cannot fill the chip)
 };
 
 struct Plan {
@@ -1252,7 +1179,8 @@ struct Plan {
   std::vector<std::vector<Group>> stages;  // ordered stages; element-wise kernels sit between them
   cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr, exec_dp = nullptr;
   int64_t kernels[4] = {0, 0, 0, 0};  // kernels inside each captured graph (for the launch counter)
-  bool fused = false;              // narrow first layers run inside the prologue / policy-head kernels (no L1 / QL1 stage)
+  bool fused = false;              // first + second layer of every forward pass in ONE tcgen05 launch (fwd_fused_tc)
+  bool fold_b = false;             // pass b's policy head is evaluated inside k_qheads_losses (narrow heads)
   ColsumGroup colsum[8] = {};      // tensor-core mode: bias-gradient column sums per stage (side stream)
   int colsum_chunks[8] = {};
   SkinnyGroup skinny[8] = {};      // tensor-core mode: skinny weight gradients per stage (side stream)
@@ -1286,11 +1214,9 @@ struct ddrl_sac {
   long long lo1 = 0, lo2 = 0, lox = 0;
   float* XA[3] = {};                    // [x|a], [x|a1], [x2|a3] split planes
   bool dp_slice = false;                // DDRL_DP_SLICE=1: slice-wise one-kernel gradient exchange (k_reduce_adam_peer)
-  bool merge_stages = false;            // DDRL_MERGE=1: dependent forward GEMM stages share one launch (tile dependency
-                                        // counters).  Measured gain 0.7 us of 116 at C2 — the per-stage cost is the
-                                        // TMA -> MMA -> epilogue latency chain, not the launch — so it stays opt-in.
-  bool fuse_l1_force = false;           // DDRL_FUSE_L1=2: fuse at every batch size
-  bool fuse_l1 = false;                 // narrow first layers fused into the prologue / policy-head kernels (FFMA)
+  bool fuse_fwd = false;                // narrow inputs: first + second layer of a forward pass in one tcgen05 launch
+                                        // (fwd_fused_tc); DDRL_FUSE_L1=0 keeps the two-launch form
+  int force_bn = 0;                     // DDRL_TC_BN=64|128 overrides the per-stage tile width choice
   uint32_t* H1bits[8] = {};             // relu'(H1) of each pass as bit masks [maxB][ldbits] (written by the L1 epilogue)
   int ldbits = 0;
   float *Wsp = nullptr, *Wtsp = nullptr;  // split planes of the main / target weight blocks (SplitMap)
@@ -1338,7 +1264,7 @@ Seg seg(const float* p, int ld, int w) { return Seg{p, ld, w}; }
 Seg none() { return Seg{nullptr, 0, 0}; }
 
 int set_out_map(tc::TcProb* p);
-int pack_tc(std::vector<tc::TcProb>& v, tc::TcGroup* g, int* tiles) {
+int pack_tc(std::vector<tc::TcProb>& v, tc::TcGroup* g, int* tiles, int bn) {
   if ((int)v.size() > tc::MAX_PROBS) return fail(DDRL_EINVAL, "too many tensor-core problems in one stage (%d)", (int)v.size());
   int t = 0;
   g->nprob = (int)v.size();
@@ -1346,7 +1272,7 @@ int pack_tc(std::vector<tc::TcProb>& v, tc::TcGroup* g, int* tiles) {
     tc::TcProb& p = v[i];
     if (int rc = set_out_map(&p)) return rc;
     p.tiles_m = (p.M + tc::BM - 1) / tc::BM;
-    p.tiles_n = (p.N + tc::BN - 1) / tc::BN;
+    p.tiles_n = (p.N + bn - 1) / bn;
     p.tile_begin = t;
     t += p.tiles_m * p.tiles_n * p.splits;
     g->p[i] = p;
@@ -1372,15 +1298,39 @@ int pack(std::vector<GemmProb>& v, GemmGroup* g, int* tiles) {
   return 0;
 }
 
+int pack_fz(std::vector<tc::FusedProb>& v, tc::FusedGroup* g, int* tiles) {
+  if ((int)v.size() > tc::FZ_MAX_PROBS) return fail(DDRL_EINVAL, "too many fused forward problems in one stage (%d)", (int)v.size());
+  int t = 0;
+  g->nprob = (int)v.size();
+  for (size_t i = 0; i < v.size(); ++i) {
+    tc::FusedProb& p = v[i];
+    p.tiles_m = (p.M + tc::BM - 1) / tc::BM;
+    p.tiles_n = (p.h2 + tc::FZ_BN - 1) / tc::FZ_BN;
+    p.tile_begin = t;
+    t += p.tiles_m * p.tiles_n;
+    g->p[i] = p;
+  }
+  *tiles = t;
+  return 0;
+}
+
 int finalize_group(Group& g) {
   int rc = pack(g.probs, &g.grp, &g.tiles);
   if (rc) return rc;
-  return pack_tc(g.probs_tc, &g.grp_tc, &g.tiles_tc);
+  if ((rc = pack_fz(g.probs_fz, &g.grp_fz, &g.tiles_fz))) return rc;
+  return pack_tc(g.probs_tc, &g.grp_tc, &g.tiles_tc, g.bn);
 }
 
 int launch_tc(const Group& g, cudaStream_t s) {
+  if (g.tiles_fz > 0) {
+    DDRL_CUDA(launch_pdl(tc::fwd_fused_tc, dim3(g.tiles_fz), dim3(tc::FZ_THREADS), tc::FZ_SMEM_BYTES, s, g.grp_fz));
+    DDRL_LAUNCH_CHECK();
+  }
   if (g.tiles_tc > 0) {
-    DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc, dim3(g.tiles_tc), dim3(256), tc::SMEM_BYTES, s, g.grp_tc));
+    if (g.bn == 64)
+      DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc<64>, dim3(g.tiles_tc), dim3(256), tc::Cfg<64>::SMEM_BYTES, s, g.grp_tc));
+    else
+      DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc<128>, dim3(g.tiles_tc), dim3(256), tc::Cfg<128>::SMEM_BYTES, s, g.grp_tc));
     DDRL_LAUNCH_CHECK();
   }
   return 0;
@@ -1432,16 +1382,17 @@ struct View {          // a pre-split 2-D tensor: `rows` x `cols` valid elements
   long long lo;
   int rows, cols;
 };
-// operand whose contraction index runs along the COLUMNS of the stored tensor (K-major): box = 128 rows x 32 cols
+// operand whose contraction index runs along the COLUMNS of the stored tensor (K-major): box = box_rows x 32 cols
+//   (box_rows = 128 for the A operand, the tile width BN for the B operand)
 // operand whose contraction index runs along the ROWS (MN-major): box = 32 rows (k) x 32 cols (mn)
-int make_map(CUtensorMap* m, const View& v, bool mn_major) {
+int make_map(CUtensorMap* m, const View& v, bool mn_major, int box_rows = 128) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if ((v.ld & 3) || (v.lo & 3) || (reinterpret_cast<uintptr_t>(v.p) & 15))
     return fail(DDRL_EINVAL, "tensor map operand is not 16-byte aligned (ld=%d)", v.ld);
   cuuint64_t dims[3] = {(cuuint64_t)v.cols, (cuuint64_t)v.rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)v.ld * 4, (cuuint64_t)v.lo * 4};
-  cuuint32_t box[3] = {32, mn_major ? 32u : 128u, 1};
+  cuuint32_t box[3] = {32, mn_major ? 32u : (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(v.p), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1451,13 +1402,13 @@ int make_map(CUtensorMap* m, const View& v, bool mn_major) {
   return 0;
 }
 // C[M,N] = epi( opA . opB + bias ):  a / b are the stored tensors, a_mn / b_mn say which index is contracted
-int mk_tc(tc::TcProb* out, const View& a, bool a_mn, const View& b, bool b_mn, float* C, float* C_lo, int ldc, int M, int N,
+int mk_tc(tc::TcProb* out, int bn, const View& a, bool a_mn, const View& b, bool b_mn, float* C, float* C_lo, int ldc, int M, int N,
           int K, int epi = EPI_NONE, const float* bias = nullptr, const float* mask = nullptr, const float* mask_lo = nullptr,
           int ldmask = 0) {
   tc::TcProb p{};
   int rc = make_map(&p.ta, a, a_mn);
   if (rc) return rc;
-  if ((rc = make_map(&p.tb, b, b_mn))) return rc;
+  if ((rc = make_map(&p.tb, b, b_mn, bn))) return rc;
   p.C = C; p.C_lo = C_lo; p.ldc = ldc; p.c_split_stride = 0;
   p.mask = mask; p.mask_lo = mask_lo; p.ldmask = ldmask; p.bias = bias;
   p.M = M; p.N = N; p.K = K; p.epi = epi; p.a_mn = a_mn; p.b_mn = b_mn;
@@ -1465,22 +1416,27 @@ int mk_tc(tc::TcProb* out, const View& a, bool a_mn, const View& b, bool b_mn, f
   *out = p;
   return 0;
 }
-// output tensor map (N, M, plane): plane = hi/lo (C_lo set) or the split-K partial index.  Falls back to direct
-// stores (c_tma = 0) when the output is not 16-byte aligned / pitched (e.g. N = 33 weight-gradient blocks).
+// output tensor map (N, M, plane), box 32 x 32, SWIZZLE_128B (the epilogues stage 32 x 32 blocks in shared memory)
+int make_out_map(CUtensorMap* m, float* C, int N, int M, int ldc, int planes, long long plane) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)(planes > 1 ? plane : (long long)ldc * M) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, C, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled(output) failed (%d) M=%d N=%d ldc=%d", (int)r, M, N, ldc);
+  return 0;
+}
+// plane = hi/lo (C_lo set) or the split-K partial index.  Falls back to direct stores (c_tma = 0) when the output is
+// not 16-byte aligned / pitched (e.g. N = 33 weight-gradient blocks).
 int set_out_map(tc::TcProb* p) {
   const long long plane = p->C_lo ? (long long)(p->C_lo - p->C) : p->c_split_stride;
   const int planes = p->C_lo ? 2 : p->splits;
   p->c_tma = 0;
   if ((p->ldc & 3) || (reinterpret_cast<uintptr_t>(p->C) & 15) || (planes > 1 && (plane <= 0 || (plane & 3)))) return 0;
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t dims[3] = {(cuuint64_t)p->N, (cuuint64_t)p->M, (cuuint64_t)planes};
-  cuuint64_t strides[2] = {(cuuint64_t)p->ldc * 4, (cuuint64_t)(planes > 1 ? plane : (long long)p->ldc * p->M) * 4};
-  cuuint32_t box[3] = {32, 32, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(&p->tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->C, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(DDRL_ECUDA, "cuTensorMapEncodeTiled(output) failed (%d) M=%d N=%d ldc=%d", (int)r, p->M, p->N, p->ldc);
+  if (int rc = make_out_map(&p->tc, p->C, p->N, p->M, p->ldc, planes, plane)) return rc;
   p->c_tma = 1;
   return 0;
 }
@@ -1498,25 +1454,21 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
   float *W = h->W, *Wt = h->Wt, *Gp = h->Gp;
   auto wg = [&](GemmProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
   enum { a = 0, b, c, d, e, f, g, hh };
-  // ---- forward: policies (a: main@x, b: main@x2, c: target@x2) and the data-action Q passes (d, e)
-  const float* xin[5] = {h->X, h->X2, h->X2, h->X, h->X};
-  const float* wsrc[5] = {W + h->o_pi1, W + h->o_pi1, Wt + h->o_pi1, W + h->o_q1[0], W + h->o_q2[0]};
-  const float* wsrc2[5] = {W + h->o_pi2, W + h->o_pi2, Wt + h->o_pi2, W + h->o_q1[1], W + h->o_q2[1]};
-  for (int p = 0; p < 5; ++p) {
-    const bool isq = p >= 3;
-    add(pl.stages[ST_L1], mk(seg(xin[p], D, D), isq ? seg(h->ACT, A, A) : none(), 1, 0, wsrc[p], h1, 0, h->H1[p], h1,
-                             B, h1, D + (isq ? A : 0) + 1, EPI_RELU));
-    add(pl.stages[ST_L2], mk(seg(h->H1[p], h1, h1), none(), 1, 0, wsrc2[p], h2, 0, h->H2[p], h2, B, h2, h1 + 1, EPI_RELU));
-  }
-  // ---- forward, policy-action Q passes: f = Q1(x,a1), g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3)
-  const float* xin2[3] = {h->X, h->X2, h->X2};
-  const float* ain2[3] = {h->A1, h->A3, h->A3};
-  const float* w1[3] = {W + h->o_q1[0], Wt + h->o_q1[0], Wt + h->o_q2[0]};
-  const float* w2[3] = {W + h->o_q1[1], Wt + h->o_q1[1], Wt + h->o_q2[1]};
-  for (int p = 0; p < 3; ++p) {
-    add(pl.stages[ST_QL1], mk(seg(xin2[p], D, D), seg(ain2[p], A, A), 1, 0, w1[p], h1, 0, h->H1[f + p], h1, B, h1,
-                              D + A + 1, EPI_RELU));
-    add(pl.stages[ST_QL2], mk(seg(h->H1[f + p], h1, h1), none(), 1, 0, w2[p], h2, 0, h->H2[f + p], h2, B, h2, h1 + 1, EPI_RELU));
+  // ---- forward.  First stage: policies a (main@x), c (target@x2) and the data-action Q passes d, e; second stage:
+  // policy b (main@x2, only its log-likelihood is used, by the losses) and the policy-action Q passes f = Q1(x,a1),
+  // g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3) — four passes per stage
+  const float* xin[8] = {h->X, h->X2, h->X2, h->X, h->X, h->X, h->X2, h->X2};
+  const float* ain[8] = {nullptr, nullptr, nullptr, h->ACT, h->ACT, h->A1, h->A3, h->A3};
+  const float* wsrc[8] = {W + h->o_pi1, W + h->o_pi1, Wt + h->o_pi1, W + h->o_q1[0], W + h->o_q2[0],
+                          W + h->o_q1[0], Wt + h->o_q1[0], Wt + h->o_q2[0]};
+  const float* wsrc2[8] = {W + h->o_pi2, W + h->o_pi2, Wt + h->o_pi2, W + h->o_q1[1], W + h->o_q2[1],
+                           W + h->o_q1[1], Wt + h->o_q1[1], Wt + h->o_q2[1]};
+  for (int p = 0; p < 8; ++p) {
+    const bool first = p == a || p == c || p == d || p == e;
+    const bool isq = ain[p] != nullptr;
+    add(pl.stages[first ? ST_L1 : ST_QL1], mk(seg(xin[p], D, D), isq ? seg(ain[p], A, A) : none(), 1, 0, wsrc[p], h1, 0, h->H1[p], h1,
+                                              B, h1, D + (isq ? A : 0) + 1, EPI_RELU));
+    add(pl.stages[first ? ST_L2 : ST_QL2], mk(seg(h->H1[p], h1, h1), none(), 1, 0, wsrc2[p], h2, 0, h->H2[p], h2, B, h2, h1 + 1, EPI_RELU));
   }
   // ---- backward of the three differentiated Q passes: 0 = d (Q1 data), 1 = e (Q2 data), 2 = f (Q1 pi-path)
   const int pass[3] = {d, e, f};
@@ -1547,6 +1499,14 @@ int build_plan(ddrl_sac* h, int B, Plan& pl) {
 
 // Tensor-core plan: every GEMM with N > 16 runs on tcgen05 from the pre-split planes; the skinny weight
 // gradients (Q heads, policy heads) and the bias gradients (column sums of dZ) stay on FFMA tiles.
+// Stage layout (B = 1024, 256 x 256: every stage is <= 128 tiles of 128 x 64, one per SM, in ONE wave):
+//   ST_L1 / ST_L2     passes a (pi main@x), c (pi target@x2), d, e (Q1, Q2 @ (x, a))      -> heads of a, c
+//   ST_QL1 / ST_QL2   passes b (pi main@x2), f (Q1 @ (x, a1)), g, h (Q targets @ (x2, a3)) -> Q heads + losses (+ head of b)
+//   ST_BQ             dgrad d, e, f; wgrad W2(q1)                                          -> policy backward rows
+//   ST_BP             dgrad a; wgrad W2(pi), W2(q2), W1(q1), W1(q2)
+//   ST_BP3            wgrad W1(pi)
+// With narrow inputs (D + A <= 32, h1 <= 256) the first and second layer of a forward stage are ONE launch of
+// fwd_fused_tc (ST_L1 / ST_QL1 stay empty).
 int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
   const int D = h->D, A = h->A, h1 = h->h1, h2 = h->h2;
   float *W = h->W, *Gp = h->Gp;
@@ -1554,7 +1514,6 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
   int rc = 0;
   const int kps = 256;
   auto wg_tc = [&](tc::TcProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
-  auto wg = [&](GemmProb p) { p.splits = pl.S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
   enum { a = 0, b, c, d, e, f, g, hh };
   enum { PI1 = 0, PI2, Q1_0, Q1_1, Q2_0, Q2_1 };   // SplitMap block indices
   const int64_t ioff[6] = {h->o_pi1, h->o_pi2, h->o_q1[0], h->o_q1[1], h->o_q2[0], h->o_q2[1]};
@@ -1568,26 +1527,53 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
   auto h1v = [&](int p) { return View{h->H1[p], h->ld1, h->lo1, B, h1}; };
   auto dz2v = [&](const float* p) { return View{p, h->ld2, h->lo2, B, h2}; };
   auto dz1v = [&](const float* p) { return View{p, h->ld1, h->lo1, B, h1}; };
+  // The stage definitions below run twice: a dry pass that only counts 128 x 128 tiles per stage (to pick the tile
+  // width: 64 when 128-wide tiles would leave SMs idle), then the pass that builds the tensor maps.
+  bool dry = true;
+  int tiles128[ST_COUNT] = {}, bn_of[ST_COUNT] = {};
+  auto count = [&](int stage, int M, int N, int splits) { tiles128[stage] += ((M + 127) / 128) * ((N + 127) / 128) * splits; };
+  auto push = [&](int stage, const tc::TcProb& p) {
+    if (pl.stages[stage].empty()) pl.stages[stage].emplace_back();
+    pl.stages[stage][0].bn = bn_of[stage];
+    pl.stages[stage][0].probs_tc.push_back(p);
+  };
   auto fwd = [&](int stage, const View& act, int blk, bool target, float* C, float* C_lo, int ldc, uint32_t* bits = nullptr) {
+    if (dry) return count(stage, B, Nb[blk], 1);
     tc::TcProb p;
-    if (!rc && !(rc = mk_tc(&p, act, false, wview(blk, target), true, C, C_lo, ldc, B, Nb[blk], Kb[blk], EPI_RELU,
+    if (!rc && !(rc = mk_tc(&p, bn_of[stage], act, false, wview(blk, target), true, C, C_lo, ldc, B, Nb[blk], Kb[blk], EPI_RELU,
                             bias_of(blk, target)))) {
       p.relu_bits = bits; p.ldbits = h->ldbits;
-      add_tc(pl.stages[stage], p);
+      push(stage, p);
     }
   };
+  auto fused = [&](int stage, const View& x, int blk1, int blk2, bool target, int pass, bool keep_h1, bool keep_bits) {
+    if (dry || rc) return;
+    tc::FusedProb p{};
+    if ((rc = make_map(&p.tx, x, false))) return;
+    if ((rc = make_map(&p.tw1, wview(blk1, target), true))) return;
+    if ((rc = make_map(&p.tw2, wview(blk2, target), true))) return;
+    if (keep_h1 && (rc = make_out_map(&p.th1, h->H1[pass], h1, B, h->ld1, 2, h->lo1))) return;
+    if ((rc = make_out_map(&p.tc, h->H2[pass], h2, B, h2, 1, 0))) return;
+    p.bias1 = bias_of(blk1, target); p.bias2 = bias_of(blk2, target);
+    p.bits = keep_bits ? h->H1bits[pass] : nullptr; p.ldbits = h->ldbits; p.store_h1 = keep_h1 ? 1 : 0;
+    p.M = B; p.K1 = Kb[blk1]; p.h1 = h1; p.h2 = h2;
+    if (pl.stages[stage].empty()) pl.stages[stage].emplace_back();
+    pl.stages[stage][0].probs_fz.push_back(p);
+  };
   auto dgrad = [&](int stage, const float* dz2, int blk, float* dz1, int mask_pass) {
+    if (dry) return count(stage, B, Kb[blk], 1);
     tc::TcProb p;   // dZ1 = dZ2 . W2^T masked by relu'(H1)
-    if (!rc && !(rc = mk_tc(&p, dz2v(dz2), false, wview(blk, false), false, dz1, dz1 + h->lo1, h->ld1, B, Kb[blk], Nb[blk],
-                            EPI_MASK, nullptr, h->H1[mask_pass], h->H1[mask_pass] + h->lo1, h->ld1))) {
+    if (!rc && !(rc = mk_tc(&p, bn_of[stage], dz2v(dz2), false, wview(blk, false), false, dz1, dz1 + h->lo1, h->ld1, B, Kb[blk],
+                            Nb[blk], EPI_MASK, nullptr, h->H1[mask_pass], h->H1[mask_pass] + h->lo1, h->ld1))) {
       p.mask_bits = h->H1bits[mask_pass]; p.ldbits = h->ldbits;
-      add_tc(pl.stages[stage], p);
+      push(stage, p);
     }
   };
   auto wgrad = [&](int stage, const View& act, const View& dz, int blk) {
+    if (dry) return count(stage, Kb[blk], Nb[blk], pl.S);
     tc::TcProb p;   // d[W] = act^T . dZ (kernel rows); the bias row is the column sum of dZ, on FFMA tiles
-    if (!rc && !(rc = mk_tc(&p, act, true, dz, true, Gp + ioff[blk], nullptr, Nb[blk], Kb[blk], Nb[blk], B)))
-      add_tc(pl.stages[stage], wg_tc(p));
+    if (!rc && !(rc = mk_tc(&p, bn_of[stage], act, true, dz, true, Gp + ioff[blk], nullptr, Nb[blk], Kb[blk], Nb[blk], B)))
+      push(stage, wg_tc(p));
     ColsumGroup& cg = pl.colsum[stage];
     if (!rc && cg.nprob >= COLSUM_MAX) rc = fail(DDRL_EINVAL, "too many bias-gradient problems in one stage");
     if (!rc) {
@@ -1600,6 +1586,7 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
     }
   };
   auto skinny = [&](int stage, const float* act, int ld_act, int K, const float* z, int ldz, int n, float* out, int ldc) {
+    if (dry) return;
     SkinnyGroup& sg = pl.skinny[stage];
     if (!rc && sg.nprob >= SKINNY_MAX) rc = fail(DDRL_EINVAL, "too many skinny weight-gradient problems in one stage");
     if (rc) return;
@@ -1609,80 +1596,57 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
     pl.skinny_chunks[stage] += (K + 1 + 31) / 32;
     sg.B = B; sg.kps = kps; sg.split_stride = h->P;
   };
-  // ---- forward: policies (a: main@x, b: main@x2, c: target@x2) and the data-action Q passes (d, e)
-  // a CTA of the policy-head kernel must hold rows of one pass; measured: 92 vs 100 us per update at B = 256, no gain at
-  // B = 1024 (the FFMA layers then cost what the two tensor-core stages did), so large batches keep the tcgen05 stages
-  pl.fused = h->fuse_l1 && B % ROW_WARPS == 0 && (B <= 512 || h->fuse_l1_force);
-  if (!pl.fused) {   // otherwise computed with FFMA inside the prologue (l1_fuse_args)
-    fwd(ST_L1, xa(0, D), PI1, false, h->H1[a], h->H1[a] + h->lo1, h->ld1, h->H1bits[a]);
-    fwd(ST_L1, xa(2, D), PI1, false, h->H1[b], h->H1[b] + h->lo1, h->ld1);
-    fwd(ST_L1, xa(2, D), PI1, true, h->H1[c], h->H1[c] + h->lo1, h->ld1);
-    fwd(ST_L1, xa(0, D + A), Q1_0, false, h->H1[d], h->H1[d] + h->lo1, h->ld1, h->H1bits[d]);
-    fwd(ST_L1, xa(0, D + A), Q2_0, false, h->H1[e], h->H1[e] + h->lo1, h->ld1, h->H1bits[e]);
-  }
-  const int blk2[5] = {PI2, PI2, PI2, Q1_1, Q2_1};
-  for (int p = 0; p < 5; ++p) fwd(ST_L2, h1v(p), blk2[p], p == c, h->H2[p], nullptr, h2);
-  // ---- forward, policy-action Q passes: f = Q1(x,a1), g = Q1_targ(x2,a3), hh = Q2_targ(x2,a3)
-  if (!pl.fused) {   // otherwise computed inside the policy-head kernel (ql1_fuse_args)
-    fwd(ST_QL1, xa(1, D + A), Q1_0, false, h->H1[f], h->H1[f] + h->lo1, h->ld1, h->H1bits[f]);
-    fwd(ST_QL1, xa(2, D + A), Q1_0, true, h->H1[g], h->H1[g] + h->lo1, h->ld1);
-    fwd(ST_QL1, xa(2, D + A), Q2_0, true, h->H1[hh], h->H1[hh] + h->lo1, h->ld1);
-  }
-  fwd(ST_QL2, h1v(f), Q1_1, false, h->H2[f], nullptr, h2);
-  fwd(ST_QL2, h1v(g), Q1_1, true, h->H2[g], nullptr, h2);
-  fwd(ST_QL2, h1v(hh), Q2_1, true, h->H2[hh], nullptr, h2);
-  // ---- backward of the three differentiated Q passes: 0 = d (Q1 data), 1 = e (Q2 data), 2 = f (Q1 pi-path)
-  const int pass[3] = {d, e, f};
-  const int w2blk[3] = {Q1_1, Q2_1, Q1_1}, w1blk[3] = {Q1_0, Q2_0, Q1_0};
-  const int64_t* oq[3] = {h->o_q1, h->o_q2, h->o_q1};
-  for (int i = 0; i < 3; ++i) {
-    dgrad(ST_BQ, h->dZ2[i], w2blk[i], h->dZ1[i], pass[i]);
-    if (i < 2) {
-      skinny(ST_BQ, h->H2[pass[i]], h2, h2, h->dQ[i], 1, 1, Gp + oq[i][2], 1);      // d[W3;b3] = [H2|1]^T dq
-      wgrad(ST_BQ, h1v(pass[i]), dz2v(h->dZ2[i]), w2blk[i]);
-      wgrad(ST_BP, xa(0, D + A), dz1v(h->dZ1[i]), w1blk[i]);
-    }
-  }
-  // ---- policy backward (pass a); dHD and dZ2a come from k_policy_bwd_rows
-  skinny(ST_BP, h->H2[a], h2, h2, h->dHD, 2 * A, 2 * A, Gp + h->o_pih, h->ldh);      // d[Whead;bhead] = [H2a|1]^T dHD
-  dgrad(ST_BP, h->dZ2a, PI2, h->dZ1a, a);
-  wgrad(ST_BP, h1v(a), dz2v(h->dZ2a), PI2);
-  wgrad(ST_BP3, xa(0, D), dz1v(h->dZ1a), PI1);
-  if (rc) return rc;
-  if (h->merge_stages) {
-    // Two dependent stages in ONE launch: the consumer tiles come after the producer tiles in the grid and their TMA
-    // producer warp waits on a counter the producer tiles bump.  Only when the consumers cannot fill every SM (so the
-    // producers always find a free SM whatever the dispatch order) and the counters fit.
-    auto tiles_of = [](const tc::TcProb& p) { return ((p.M + tc::BM - 1) / tc::BM) * ((p.N + tc::BN - 1) / tc::BN) * p.splits; };
-    unsigned int* flags = h->st->dep_flags;
-    int next_flag = 0;
-    auto merge_fwd = [&](int sp, int sc) {     // L1 -> L2 pairs, problem i of both stages is the same pass
-      if (pl.stages[sp].empty() || pl.stages[sc].empty()) return;
-      auto& P = pl.stages[sp][0].probs_tc;
-      auto& Cn = pl.stages[sc][0].probs_tc;
-      if (P.empty() || P.size() != Cn.size() || P.size() + Cn.size() > (size_t)tc::MAX_PROBS) return;
-      int tiles = 0, nflags = 0;
-      for (auto& c : Cn) tiles += tiles_of(c);
-      for (auto& p : P) { tiles += tiles_of(p); nflags += (p.M + tc::BM - 1) / tc::BM; }
-      // all tiles resident at once (one CTA per SM): no second wave (measured: L1+L2 of C2, 160 tiles on 148 SMs, is
-      // 5 us SLOWER merged) and the producers always hold an SM whatever the dispatch order
-      if (tiles > h->sms || next_flag + nflags > DEP_FLAGS) return;
-      for (size_t i = 0; i < P.size(); ++i) {
-        const int tm = (P[i].M + tc::BM - 1) / tc::BM;
-        P[i].sig_ctr = flags + next_flag; P[i].sig_per_mtile = 1;
-        Cn[i].dep_ctr = flags + next_flag; Cn[i].dep_per_mtile = 1; Cn[i].dep_a = 1;
-        Cn[i].dep_need = (P[i].N + tc::BN - 1) / tc::BN;
-        Cn[i].err = h->d_err;
-        next_flag += tm;
+  pl.fused = h->fuse_fwd;
+  // per forward pass: input planes, first / second layer weight block, target net?, is the H1 plane pair / relu mask
+  // needed by the backward (wgrad operand: a, d, e; dgrad mask: a, d, e, f)
+  struct FwdPass { int xa_idx, cols, blk1, blk2; bool target, keep_h1, keep_bits, first; };
+  const FwdPass fp[8] = {
+      {0, D, PI1, PI2, false, true, true, true},            // a  pi main   @ x
+      {2, D, PI1, PI2, false, false, false, false},         // b  pi main   @ x2
+      {2, D, PI1, PI2, true, false, false, true},           // c  pi target @ x2
+      {0, D + A, Q1_0, Q1_1, false, true, true, true},      // d  Q1 main   @ (x, a)
+      {0, D + A, Q2_0, Q2_1, false, true, true, true},      // e  Q2 main   @ (x, a)
+      {1, D + A, Q1_0, Q1_1, false, false, true, false},    // f  Q1 main   @ (x, a1)
+      {2, D + A, Q1_0, Q1_1, true, false, false, false},    // g  Q1 target @ (x2, a3)
+      {2, D + A, Q2_0, Q2_1, true, false, false, false},    // h  Q2 target @ (x2, a3)
+  };
+  auto define_stages = [&]() {
+    for (int p = 0; p < 8; ++p) {
+      const FwdPass& q = fp[p];
+      if (pl.fused) {
+        fused(q.first ? ST_L2 : ST_QL2, xa(q.xa_idx, q.cols), q.blk1, q.blk2, q.target, p, q.keep_h1, q.keep_bits);
+      } else {
+        fwd(q.first ? ST_L1 : ST_QL1, xa(q.xa_idx, q.cols), q.blk1, q.target, h->H1[p], h->H1[p] + h->lo1, h->ld1,
+            q.keep_bits ? h->H1bits[p] : nullptr);
+        fwd(q.first ? ST_L2 : ST_QL2, h1v(p), q.blk2, q.target, h->H2[p], nullptr, h2);
       }
-      for (auto& c : Cn) P.push_back(c);
-      Cn.clear();
-    };
-    merge_fwd(ST_L1, ST_L2);
-    merge_fwd(ST_QL1, ST_QL2);
-    // (BP + BP3 merged was measured slower: the bias column sum of dZ1a on the side stream then starts only after
-    //  the merged kernel instead of running beside BP3.)
+    }
+    // ---- backward of the three differentiated Q passes: 0 = d (Q1 data), 1 = e (Q2 data), 2 = f (Q1 pi-path)
+    const int pass[3] = {d, e, f};
+    const int w2blk[3] = {Q1_1, Q2_1, Q1_1}, w1blk[3] = {Q1_0, Q2_0, Q1_0};
+    const int64_t* oq[3] = {h->o_q1, h->o_q2, h->o_q1};
+    for (int i = 0; i < 3; ++i) {
+      dgrad(ST_BQ, h->dZ2[i], w2blk[i], h->dZ1[i], pass[i]);
+      if (i < 2) {
+        skinny(ST_BQ, h->H2[pass[i]], h2, h2, h->dQ[i], 1, 1, Gp + oq[i][2], 1);      // d[W3;b3] = [H2|1]^T dq
+        wgrad(i == 0 ? ST_BQ : ST_BP, h1v(pass[i]), dz2v(h->dZ2[i]), w2blk[i]);       // W2(q2) rides with the policy stage
+        wgrad(ST_BP, xa(0, D + A), dz1v(h->dZ1[i]), w1blk[i]);
+      }
+    }
+    // ---- policy backward (pass a); dHD and dZ2a come from k_policy_bwd_rows
+    skinny(ST_BP, h->H2[a], h2, h2, h->dHD, 2 * A, 2 * A, Gp + h->o_pih, h->ldh);      // d[Whead;bhead] = [H2a|1]^T dHD
+    dgrad(ST_BP, h->dZ2a, PI2, h->dZ1a, a);
+    wgrad(ST_BP, h1v(a), dz2v(h->dZ2a), PI2);
+    wgrad(ST_BP3, xa(0, D), dz1v(h->dZ1a), PI1);
+  };
+  define_stages();
+  for (int st = 0; st < ST_COUNT; ++st) {
+    bn_of[st] = tiles128[st] < h->sms ? 64 : 128;
+    if (h->force_bn) bn_of[st] = h->force_bn;
   }
+  dry = false;
+  define_stages();
+  if (rc) return rc;
   for (auto& st : pl.stages)
     for (auto& g2 : st)
       if ((rc = finalize_group(g2))) return rc;
@@ -1713,22 +1677,6 @@ int run_side(const Plan& pl, int st, int S, cudaStream_t side) {
   return 0;
 }
 
-L1Fuse l1_fuse_args(const ddrl_sac* h, bool on) {       // passes a..e of the prologue
-  L1Fuse f{};
-  if (!on) return f;
-  f.on = 1; f.h1 = h->h1; f.ld1 = h->ld1; f.ldbits = h->ldbits; f.lo1 = h->lo1;
-  const float* w[5] = {h->W + h->o_pi1, h->W + h->o_pi1, h->Wt + h->o_pi1, h->W + h->o_q1[0], h->W + h->o_q2[0]};
-  for (int p = 0; p < 5; ++p) { f.W[p] = w[p]; f.H1[p] = h->H1[p]; f.bits[p] = h->H1bits[p]; }
-  return f;
-}
-L1Fuse ql1_fuse_args(const ddrl_sac* h, bool on) {      // passes f, g, h of the policy-head kernel
-  L1Fuse f{};
-  if (!on) return f;
-  f.on = 1; f.h1 = h->h1; f.ld1 = h->ld1; f.ldbits = h->ldbits; f.lo1 = h->lo1;
-  const float* w[3] = {h->W + h->o_q1[0], h->Wt + h->o_q1[0], h->Wt + h->o_q2[0]};
-  for (int p = 0; p < 3; ++p) { f.W[p] = w[p]; f.H1[p] = h->H1[5 + p]; f.bits[p] = h->H1bits[5 + p]; }
-  return f;
-}
 XaOut xa_out(const ddrl_sac* h) {
   return h->use_tc ? XaOut{h->XA[0], h->XA[1], h->XA[2], h->ldx, h->lox} : XaOut{nullptr, nullptr, nullptr, 0, 0};
 }
@@ -1736,34 +1684,36 @@ XaOut xa_out(const ddrl_sac* h) {
 int launch_prologue(ddrl_sac* h, const Plan& pl, const StepDyn& dyn, cudaStream_t s) {
   const int B = pl.B, D = h->D, A = h->A;
   const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
-  int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
-  if (pl.fused) blocks = (int)std::min<int64_t>(std::max<int64_t>(blocks, 5LL * ((B + FUSE_PRB - 1) / FUSE_PRB)), h->sms * 3);
+  const int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
   DDRL_CUDA(launch_pdl(k_prologue, dim3(blocks), dim3(256), 0, s, h->st, dyn, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN,
-                       h->NOISE, xa_out(h), l1_fuse_args(h, pl.fused)));
+                       h->NOISE, xa_out(h)));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
-int launch_heads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
+bool narrow_heads(const ddrl_sac* h) { return 2 * h->A <= 16 && (h->h2 & 3) == 0; }
+// policy heads of the passes in `pm` (0: main pi(x), 1: main pi(x2), 2: target pi(x2))
+int launch_heads(ddrl_sac* h, const Plan& pl, cudaStream_t s, PassMap pm) {
   const int B = pl.B, D = h->D, A = h->A, h2 = h->h2;
-  if (2 * A <= 16 && (h2 & 3) == 0) {     // narrow heads: warp per row
-    DDRL_CUDA(launch_pdl(k_policy_heads_rows, dim3((3 * B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
+  const int rows = pm.n * B;
+  if (narrow_heads(h)) {     // warp per row
+    DDRL_CUDA(launch_pdl(k_policy_heads_rows, dim3((rows + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
         B, A, h2, h->ldh, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0],
-        h->A1, h->A3, h->LOGP1, h->LOGP2, xa_out(h), D, ql1_fuse_args(h, pl.fused)));
+        h->A1, h->A3, h->LOGP1, h->LOGP2, xa_out(h), D, pm));
     DDRL_LAUNCH_CHECK();
     return 0;
   }
   const int groups = std::min(32, HEADS_THREADS / (2 * A));    // row groups per CTA (2A <= 64 -> >= 4)
   auto smem_of = [&](int r) { return ((size_t)r * ((h2 + 3) / 4 * 4 + 4) + (size_t)r * 4 * A) * sizeof(float); };
-  // 4 rows per thread when there is enough work to still fill the GPU and a 4-row group never straddles the
-  // main / target weight boundary (B % 4 == 0); otherwise one row per thread
-  const bool rb4 = (B % 4 == 0) && (3LL * B / (4 * groups) >= 2LL * h->sms) && smem_of(4 * groups) <= HEADS_SMEM_MAX;
+  // 4 rows per thread when there is enough work to still fill the GPU and a 4-row group never straddles a pass
+  // boundary (B % 4 == 0); otherwise one row per thread
+  const bool rb4 = (B % 4 == 0) && ((int64_t)rows / (4 * groups) >= 2LL * h->sms) && smem_of(4 * groups) <= HEADS_SMEM_MAX;
   int R = rb4 ? 4 * groups : groups;
   if (!rb4) while (R > 1 && smem_of(R) > HEADS_SMEM_MAX) R /= 2;
   const size_t smem = smem_of(R);
   if (smem > HEADS_SMEM_MAX) return fail(DDRL_EINVAL, "hidden size %d is too wide for the policy-head kernel", h2);
-  DDRL_CUDA(launch_pdl(rb4 ? k_policy_heads_fwd<4> : k_policy_heads_fwd<1>, dim3((3 * B + R - 1) / R), dim3(HEADS_THREADS), smem, s,
+  DDRL_CUDA(launch_pdl(rb4 ? k_policy_heads_fwd<4> : k_policy_heads_fwd<1>, dim3((rows + R - 1) / R), dim3(HEADS_THREADS), smem, s,
       B, A, h2, h->ldh, R, h->act_scale, h->H2[0], h->H2[1], h->H2[2], h->W + h->o_pih, h->Wt + h->o_pih, h->NOISE, h->HD[0], h->A1,
-      h->A3, h->LOGP1, h->LOGP2, xa_out(h), D));
+      h->A3, h->LOGP1, h->LOGP2, xa_out(h), D, pm));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1772,7 +1722,8 @@ int launch_qheads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   DDRL_CUDA(launch_pdl(k_qheads_losses, dim3((B + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, s,
       h->st, B, h2, h->gamma, h->H2[3], h->H2[4], h->H2[5], h->H2[6], h->H2[7], h->W + h->o_q1[2], h->W + h->o_q2[2],
       h->Wt + h->o_q1[2], h->Wt + h->o_q2[2], h->R, h->DN, h->LOGP1, h->LOGP2, h->dQ[0], h->dQ[1], h->dZ2[0], h->dZ2[1],
-      h->dZ2[2], h->partials, h->ticket, h->SCAL, h->ld2, h->lo2));
+      h->dZ2[2], h->partials, h->ticket, h->SCAL, h->ld2, h->lo2,
+      narrow_heads(h) ? 1 : 0, h->H2[1], h->W + h->o_pih, h->NOISE, h->A, h->ldh, h->act_scale));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1789,9 +1740,10 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   int rc;
   if ((rc = run_stage(pl, ST_L1, s))) return rc;
   if ((rc = run_stage(pl, ST_L2, s))) return rc;
-  if ((rc = launch_heads(h, pl, s))) return rc;
+  if ((rc = launch_heads(h, pl, s, PassMap{2, {0, 2, 0}}))) return rc;          // a -> a1, logp1; c -> a3
   if ((rc = run_stage(pl, ST_QL1, s))) return rc;
   if ((rc = run_stage(pl, ST_QL2, s))) return rc;
+  if (!narrow_heads(h) && (rc = launch_heads(h, pl, s, PassMap{1, {1, 0, 0}}))) return rc;   // b -> logp2 (else inside the next kernel)
   if ((rc = launch_qheads(h, pl, s))) return rc;
   const bool tcm = h->use_tc;
   cudaStream_t side = h->side_stream;
@@ -1922,13 +1874,15 @@ int get_plan(ddrl_sac* h, int B, Plan** out) {
 extern "C" {
 
 int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int max_batch, float gamma, float polyak,
-                    float lr, float alpha, float act_scale, ddrl_sac_t* out) {
+                    float lr, float alpha, float act_scale, int gemm_mode, ddrl_sac_t* out) {
   if (!out) return fail(DDRL_EINVAL, "ddrl_sac_create: out is NULL");
   *out = nullptr;
   if (obs_dim < 1 || act_dim < 1 || h1 < 1 || h2 < 1 || max_batch < 1)
     return fail(DDRL_EINVAL, "ddrl_sac_create: obs_dim, act_dim, h1, h2, max_batch must be >= 1");
   if (2 * act_dim > MAX_HEAD)
     return fail(DDRL_EINVAL, "ddrl_sac_create: act_dim=%d > %d is not supported", act_dim, MAX_HEAD / 2);
+  if (gemm_mode < DDRL_GEMM_AUTO || gemm_mode > DDRL_GEMM_FFMA)
+    return fail(DDRL_EINVAL, "ddrl_sac_create: gemm_mode=%d is not DDRL_GEMM_AUTO / _TC / _FFMA", gemm_mode);
   int ndev = 0;
   DDRL_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(DDRL_EINVAL, "ddrl_sac_create: device %d out of range", device);
@@ -1941,7 +1895,9 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   h->sms = sm_count(device);
   const char* ng = getenv("DDRL_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
-  if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] != 'f');   // "ffma": plain fp32 FFMA tiles
+  if (gemm_mode == DDRL_GEMM_TC) h->use_tc = true;
+  else if (gemm_mode == DDRL_GEMM_FFMA) h->use_tc = false;
+  else if (const char* gm = getenv("DDRL_GEMM")) h->use_tc = (gm[0] != 'f');   // "ffma": plain fp32 FFMA tiles
   {
     cudaError_t eh = cudaFuncSetAttribute(k_policy_heads_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM_MAX);
     if (eh == cudaSuccess) eh = cudaFuncSetAttribute(k_policy_heads_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEADS_SMEM_MAX);
@@ -1951,7 +1907,9 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     cudaError_t es = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
     if (es != cudaSuccess) { delete h; return fail(DDRL_ECUDA, "side stream / events: %s", cudaGetErrorString(es)); }
-    cudaError_t ea = cudaFuncSetAttribute(tc::gemm_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t ea = cudaFuncSetAttribute(tc::gemm_grouped_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<128>::SMEM_BYTES);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(tc::gemm_grouped_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<64>::SMEM_BYTES);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(tc::fwd_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FZ_SMEM_BYTES);
     if (ea != cudaSuccess) { delete h; return fail(DDRL_ECUDA, "cudaFuncSetAttribute(tc smem): %s", cudaGetErrorString(ea)); }
   }
   const int D = obs_dim, A = act_dim;
@@ -1979,12 +1937,10 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   h->Smax = (max_batch + 255) / 256;
   {
     const char* fz = getenv("DDRL_FUSE_L1");
-    h->fuse_l1 = h->use_tc && D + A <= FUSE_MAXK && h1 % 32 == 0 && 2 * A <= 16 && (h2 & 3) == 0 && !(fz && fz[0] == '0');
-    h->fuse_l1_force = fz && fz[0] == '2';
+    h->fuse_fwd = h->use_tc && D + A <= tc::BK && h1 % 32 == 0 && h1 <= tc::FZ_MAX_H1 && h2 % 4 == 0 && !(fz && fz[0] == '0');
+    if (const char* bz = getenv("DDRL_TC_BN")) { const int v = atoi(bz); if (v == 64 || v == 128) h->force_bn = v; }
     const char* dz = getenv("DDRL_DP_SLICE");
     h->dp_slice = dz && dz[0] == '1';
-    const char* mz = getenv("DDRL_MERGE");
-    h->merge_stages = mz && mz[0] == '1';
   }
   int rc = 0;
   const size_t P = (size_t)h->P, M = (size_t)max_batch;
@@ -2286,7 +2242,7 @@ int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* str
   for (int i = 0; i < reps; ++i) {
     if (stage < ST_COUNT) rc = run_stage(*pl, stage, s, h->use_tc);
     else if (stage == 7) rc = launch_prologue(h, *pl, h->last_dyn, s);
-    else if (stage == 8) rc = launch_heads(h, *pl, s);
+    else if (stage == 8) rc = launch_heads(h, *pl, s, PassMap{2, {0, 2, 0}});
     else if (stage == 9) rc = launch_qheads(h, *pl, s);
     else if (stage == 10) rc = launch_pbwd(h, *pl, s);
     else if (stage == 11) rc = enqueue_apply(h, pl->S, h->Gp, s);
@@ -2307,11 +2263,13 @@ __global__ void k_split_planes(const float* __restrict__ src, int rows, int cols
   }
 }
 int ddrl_debug_tc_gemm(int device, const float* dA, int a_rows, int a_cols, int a_mn, const float* dB, int b_rows, int b_cols,
-                       int b_mn, float* dC, int M, int N, int K, int splits, void* stream) {
+                       int b_mn, float* dC, int M, int N, int K, int splits, int bn, void* stream) {
   if (!dA || !dB || !dC) return fail(DDRL_EINVAL, "ddrl_debug_tc_gemm: NULL argument");
+  if (bn != 64 && bn != 128) return fail(DDRL_EINVAL, "ddrl_debug_tc_gemm: bn must be 64 or 128");
   DeviceGuard guard(device);
   cudaStream_t s = (cudaStream_t)stream;
-  DDRL_CUDA(cudaFuncSetAttribute(tc::gemm_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  DDRL_CUDA(cudaFuncSetAttribute(tc::gemm_grouped_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<128>::SMEM_BYTES));
+  DDRL_CUDA(cudaFuncSetAttribute(tc::gemm_grouped_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<64>::SMEM_BYTES));
   auto r4 = [](int v) { return (v + 3) / 4 * 4; };
   const int lda = r4(a_cols), ldb = r4(b_cols);
   const long long pa = (long long)a_rows * lda, pb = (long long)b_rows * ldb;
@@ -2324,7 +2282,8 @@ int ddrl_debug_tc_gemm(int device, const float* dA, int a_rows, int a_cols, int 
   k_split_planes<<<256, 256, 0, s>>>(dB, b_rows, b_cols, ldb, pb, sb);
   Group g;
   tc::TcProb p;
-  int rc = mk_tc(&p, View{sa, lda, pa, a_rows, a_cols}, a_mn != 0, View{sb, ldb, pb, b_rows, b_cols}, b_mn != 0, dC, nullptr, N, M,
+  g.bn = bn;
+  int rc = mk_tc(&p, bn, View{sa, lda, pa, a_rows, a_cols}, a_mn != 0, View{sb, ldb, pb, b_rows, b_cols}, b_mn != 0, dC, nullptr, N, M,
                  N, K);
   if (!rc) {
     if (splits > 1) { p.splits = splits; p.k_per_split = ((K + splits - 1) / splits + tc::BK - 1) / tc::BK * tc::BK; p.c_split_stride = (long long)M * N; }
@@ -2352,7 +2311,10 @@ int ddrl_sac_trace_stage(ddrl_sac_t h, int batch, int stage, unsigned long long*
     if (g.tiles_tc > max_tiles) return fail(DDRL_EINVAL, "ddrl_sac_trace_stage: %d tiles > max_tiles", g.tiles_tc);
     tc::TcGroup grp = g.grp_tc;
     grp.trace = d_trace;
-    DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc, dim3(g.tiles_tc), dim3(256), tc::SMEM_BYTES, (cudaStream_t)stream, grp));
+    if (g.bn == 64)
+      DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc<64>, dim3(g.tiles_tc), dim3(256), tc::Cfg<64>::SMEM_BYTES, (cudaStream_t)stream, grp));
+    else
+      DDRL_CUDA(launch_pdl(tc::gemm_grouped_tc<128>, dim3(g.tiles_tc), dim3(256), tc::Cfg<128>::SMEM_BYTES, (cudaStream_t)stream, grp));
     DDRL_LAUNCH_CHECK();
     *tiles = g.tiles_tc;
   }

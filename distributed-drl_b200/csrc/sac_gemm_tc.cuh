@@ -34,14 +34,22 @@
 namespace ddrl {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 32;            // BK tf32 = 128 bytes = one swizzle row
-constexpr int TILE_BYTES = 128 * 128;                 // one operand plane tile (128 x 32 tf32)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int STAGES = 3;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers, tmem ptr*/ + 512 /*bias of the tile*/;
+constexpr int BM = 128, BK = 32;                      // BK tf32 = 128 bytes = one swizzle row
+constexpr int TILE_BYTES = 128 * 128;                 // one A plane tile (128 rows x 32 tf32)
 constexpr int NACC = 2;                               // TMEM accumulators: k-block kb adds into accumulator kb % NACC
-constexpr int TMEM_COLS = NACC * 128;
 constexpr int MAX_PROBS = 10;
+// Tile width BN is a template parameter of the kernel: 128 x 128 tiles when they fill the chip on their own, 128 x 64
+// tiles for the stages of the small-batch configurations (C1 / C2), where 128-wide tiles leave 68 of the 148 SMs idle
+// and the per-CTA main loop (12 MMAs per k-block) is the critical path of a launch.
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE = BN * 128;                       // one B plane tile (BN x 32 tf32)
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE;   // A_hi, A_lo, B_hi, B_lo
+  static constexpr int STAGES = BN == 64 ? 4 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers, tmem ptr*/ + 512 /*bias of the tile*/;
+  static constexpr int TMEM_COLS = NACC * BN;
+  static constexpr int NCB = BN / 64;                           // 32-column chunks per epilogue warp
+};
 
 struct alignas(64) TcProb {
   CUtensorMap ta, tb;          // 3-D (inner, rows, plane) maps over the pre-split operands
@@ -54,14 +62,6 @@ struct alignas(64) TcProb {
   uint32_t* relu_bits;         // nullable (EPI_RELU): bit c of word [row * ldbits + n/32] = output (row, n + c) > 0
   const uint32_t* mask_bits;   // EPI_MASK with bits instead of the mask planes (the producer's relu_bits)
   int ldbits;
-  // Dependent tiles inside ONE launch (two stages of the step merged into one kernel): a producer problem bumps
-  // sig_ctr[sig_per_mtile ? m-tile : 0] when its tile is globally visible; a consumer problem's TMA producer warp for
-  // the dependent operand (dep_a / dep_b) waits until dep_ctr[dep_per_mtile ? m-tile : 0] >= dep_need.  The step's
-  // prologue kernel zeroes the counters.
-  unsigned int* sig_ctr;
-  const unsigned int* dep_ctr;
-  int* err;
-  int sig_per_mtile, dep_per_mtile, dep_need, dep_a, dep_b;
   long long c_split_stride;    // floats between split-K partial outputs
   int ldc, ldmask;
   int M, N, K;
@@ -108,10 +108,10 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_byte_addr, bool mn_
   d |= (uint64_t)(mn_major ? 1 : 2) << 61;
   return d;
 }
-// kind::tf32, fp32 accumulate, M = 128, N = 128
-__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn) {
+// kind::tf32, fp32 accumulate, M = 128, N = n (multiple of 16, <= 256)
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -128,14 +128,19 @@ __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
 }
+// Spin on try_wait (the hardware suspends the thread for a bounded time per attempt).  A barrier that never completes
+// is a protocol bug: trap (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "TC_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra TC_DONE;\n\t"
-      "bra TC_WAIT;\n\t"
-      "TC_DONE:\n\t}" ::"r"(s_addr(bar)), "r"(parity) : "memory");
+  const uint32_t addr = s_addr(bar);
+  uint32_t done;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();
+  } while (!done);
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
@@ -165,7 +170,10 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {   /
         "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
       : "r"(taddr));
 }
+template <int BN>
 __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant__ TcGroup grp) {
+  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, B_TILE = Cfg<BN>::B_TILE, NCB = Cfg<BN>::NCB;
+  constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
   extern __shared__ unsigned char smem_dyn[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -192,22 +200,22 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   auto load_operand = [&](bool is_b, int kb, int s) {
     const CUtensorMap* tm = is_b ? &P.tb : &P.ta;
     const int mn = is_b ? b_mn : a_mn, r0 = is_b ? n0 : m0;
-    bar_expect_tx(&full[s], 2 * TILE_BYTES);
+    const int plane_bytes = is_b ? B_TILE : TILE_BYTES;
+    bar_expect_tx(&full[s], 2 * plane_bytes);
     const uint32_t st = s_addr(base + s * STAGE_BYTES) + (is_b ? 2 * TILE_BYTES : 0);
     const int k0 = kbeg + kb * BK;
 #pragma unroll
     for (int hl = 0; hl < 2; ++hl) {
-      const uint32_t dst = st + hl * TILE_BYTES;
-      if (!mn) tma_load_3d(dst, tm, k0, r0, hl, &full[s]);
+      const uint32_t dst = st + hl * plane_bytes;
+      if (!mn) tma_load_3d(dst, tm, k0, r0, hl, &full[s]);          // the map's box holds BM (A) / BN (B) rows
       else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096, tm, r0 + 32 * j, k0, hl, &full[s]);
+        const int nbox = is_b ? BN / 32 : 4;
+        for (int j = 0; j < nbox; ++j) tma_load_3d(dst + j * 4096, tm, r0 + 32 * j, k0, hl, &full[s]);
       }
     }
   };
-  // tid 0 may start the first k-block before the CTA-wide setup barrier (it initialised the barriers itself)
-  // unless the operand is produced by other tiles of this launch (dependency wait happens in the producer loops)
-  const bool early0 = !P.dep_ctr;
+  // tid 0 starts the first k-block before the CTA-wide setup barrier (it initialised the barriers itself)
+  const bool early0 = true;
 
   if (tid == 0) {
     prefetch_tmap(&P.ta);
@@ -234,14 +242,14 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   if (tid == 0) TC_STAMP(1);          // setup done (barriers, TMEM)
   // epilogue operands fetched now, while the main loop runs: the tile's bias row into shared memory (idle warps 4..7),
   // this thread's relu-mask words into registers
-  if (tid >= 128 && P.bias) s_bias[tid - 128] = (n0 + tid - 128 < N) ? __ldg(P.bias + n0 + tid - 128) : 0.0f;
+  if (tid >= 128 && tid - 128 < BN && P.bias) s_bias[tid - 128] = (n0 + tid - 128 < N) ? __ldg(P.bias + n0 + tid - 128) : 0.0f;
   uint32_t mbits[2] = {0u, 0u};
   if (P.epi == EPI_MASK && P.mask_bits) {
     const int mrow = m0 + 32 * (warp & 3) + lane;
-    const int w0 = (n0 + (warp >> 2) * 64) >> 5;
+    const int w0 = (n0 + (warp >> 2) * 32 * NCB) >> 5;
     if (mrow < M) {
       if (32 * w0 < N) mbits[0] = P.mask_bits[(size_t)mrow * P.ldbits + w0];
-      if (32 * (w0 + 1) < N) mbits[1] = P.mask_bits[(size_t)mrow * P.ldbits + w0 + 1];
+      if (NCB > 1 && 32 * (w0 + 1) < N) mbits[1] = P.mask_bits[(size_t)mrow * P.ldbits + w0 + 1];
     }
   }
 
@@ -251,18 +259,6 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
       //      32 x 32 boxes per plane, so one thread issuing all 16 copies of a k-block would be the bottleneck) ----
       const bool is_b = warp == 2;
       if (!is_b && P.c_tma) prefetch_tmap(&P.tc);
-      if (P.dep_ctr && (is_b ? P.dep_b : P.dep_a)) {
-        // this operand is written by other tiles of the same launch
-        const unsigned int target = (unsigned int)P.dep_need;
-        const unsigned int* ctr = P.dep_ctr + (P.dep_per_mtile ? m0 / BM : 0);
-        const long long t0 = clock64();
-        unsigned int v;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-          if (v < target && clock64() - t0 > 4000000000LL) { *P.err = 2; break; }   // ~2 s: never hang the GPU
-        } while (v < target);
-        asm volatile("fence.proxy.async;" ::: "memory");   // the acquire orders generic accesses; TMA reads are async-proxy
-      }
       for (int kb = early0 ? 1 : 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         if (kb >= STAGES) bar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
@@ -273,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       // ---- MMA issuer ----
-      const uint32_t idesc = make_idesc(a_mn, b_mn);
+      const uint32_t idesc = make_idesc(a_mn, b_mn, BN);
       const uint32_t a_step = a_mn ? 1024u : 32u, b_step = b_mn ? 1024u : 32u;   // 8 tf32 of K
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
@@ -281,11 +277,11 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
         if (kb == 0) TC_STAMP(2);     // first stage landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = s_addr(base + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES,
-                       b_lo = a_hi + 3 * TILE_BYTES;
+                       b_lo = b_hi + B_TILE;
         // The tensor core adds each product into its fp32 accumulator with truncation, a bias that grows with the
         // number of additions (measured: 2e-5 gradient error at K ~ 400 against 1e-7 for FFMA).  Alternate k-blocks go
         // to NACC separate accumulators that the epilogue sums with round-to-nearest adds: the bias shrinks by NACC.
-        const uint32_t acc = tmem_d + (uint32_t)(kb % NACC) * 128u;
+        const uint32_t acc = tmem_d + (uint32_t)(kb % NACC) * (uint32_t)BN;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint32_t ao = ks * a_step, bo = ks * b_step;
@@ -306,8 +302,8 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (tid == 0) TC_STAMP(4);          // accumulator complete
 
-  // epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*(w/4)..+64, as two 32-column chunks whose TMEM loads
-  // are both in flight before the first is consumed
+  // epilogue: warp w owns TMEM lanes 32*(w%4).. and columns (BN/2)*(w/4)..+BN/2, as NCB 32-column chunks whose TMEM
+  // loads are all in flight before the first is consumed
   {
     const int q = warp & 3, half = warp >> 2;
     const int m = m0 + 32 * q + lane;
@@ -315,25 +311,30 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
     float* C = P.C + (size_t)split * P.c_split_stride;
     float* C_lo = P.C_lo;
     const bool has_bias = P.bias != nullptr;
-    float vv[2][32], v2[2][32];
-    const bool live0 = n0 + half * 64 < N, live1 = n0 + half * 64 + 32 < N;     // warp-uniform
+    float vv[NCB][32], v2[NCB][32];
+    const int cbase = half * 32 * NCB;                                            // first column of this warp in the tile
+    bool live[NCB];
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb) live[cb] = n0 + cbase + 32 * cb < N;         // warp-uniform
     const bool two = nkb > 1;                                                    // second accumulator in use
     const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16);
-    if (live0) tmem_ld32_nowait(trow + (uint32_t)(half * 64), vv[0]);
-    if (live1) tmem_ld32_nowait(trow + (uint32_t)(half * 64 + 32), vv[1]);
-    if (two && live0) tmem_ld32_nowait(trow + 128u + (uint32_t)(half * 64), v2[0]);
-    if (two && live1) tmem_ld32_nowait(trow + 128u + (uint32_t)(half * 64 + 32), v2[1]);
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb)
+      if (live[cb]) tmem_ld32_nowait(trow + (uint32_t)(cbase + 32 * cb), vv[cb]);
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb)
+      if (two && live[cb]) tmem_ld32_nowait(trow + (uint32_t)BN + (uint32_t)(cbase + 32 * cb), v2[cb]);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (two) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (live0) vv[0][i] += v2[0][i];
-        if (live1) vv[1][i] += v2[1][i];
-      }
+      for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (live[cb]) vv[cb][i] += v2[cb][i];
     }
 #pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      const int c0 = half * 64 + cb * 32;
+    for (int cb = 0; cb < NCB; ++cb) {
+      const int c0 = cbase + cb * 32;
       const int n_base = n0 + c0;
       if (n_base >= N) continue;                     // warp-uniform
       float* v = vv[cb];
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
       if (c_tma) {
         // 32 x 32 block per plane -> swizzled shared memory -> one TMA store each (full 128-byte lines; rows / columns
         // beyond M / N are clipped by the TMA unit).  The pipeline stages are free: every load has been consumed.
-        unsigned char* blk = base + (warp * 2 + cb) * 8192;
+        unsigned char* blk = base + (warp * NCB + cb) * 8192;
         if (C_lo) {
           float lo[32];
 #pragma unroll
@@ -406,23 +407,245 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
         }
       }
     }
-    if (c_tma && lane == 0) {
-      if (P.sig_ctr) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // writes complete, not just smem read
-      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    if (P.sig_ctr) {
-      asm volatile("fence.proxy.async;" ::: "memory");
-      __threadfence();
-    }
+    if (c_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   if (tid == 0) TC_STAMP(5);          // this warp's epilogue done (stores issued and drained)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid == 0) TC_STAMP(6);          // all warps done
-  if (tid == 0 && P.sig_ctr)
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.sig_ctr + (P.sig_per_mtile ? m0 / BM : 0)) : "memory");
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// =====================================================================================================================
+// Fused first + second layer of a forward pass (narrow inputs: K1 = D or D + A <= 32, h1 <= 256, h1 % 32 == 0):
+//     H1 = relu([x|a] . W1 + b1)      one k-block, M = 128, N = h1: accumulates in TMEM columns [0, h1)
+//     H2 = relu(H1 . W2 + b2)         128 x 64 output tile per CTA, K = h1
+// One CTA = (pass, 128-row block, 64-column block of H2).  H1 never makes a round trip through L2 as an operand: the
+// converter warps read the L1 accumulator with tcgen05.ld, add the bias, apply relu, split into tf32 hi / lo and write
+// the k-block straight into the shared-memory A stage of the second layer in the canonical K-major SWIZZLE_128B
+// layout (the layout a TMA load of that box would have produced); the W2 k-blocks stream in by TMA meanwhile.  The
+// four CTAs of a row block recompute the (cheap, one k-block) first layer; each of them writes a quarter of H1's
+// k-blocks (hi / lo planes by TMA store from the A stage, relu bit masks) for the passes the backward needs.
+//   warp 0 / lane 0    TMA producer: [x|a] and W1 (once), then the W2 k-block ring (4 stages of 16 KB)
+//   warp 1 / lane 0    MMA issuer: first layer (<= 4 k-steps x 3 products, N = h1), then per k-block 12 MMAs (N = 64)
+//   warps 2..9         converters (two groups of four warps = the four TMEM lane quadrants; even / odd k-blocks),
+//                      then the H2 epilogue (bias, relu, TMA store)
+// =====================================================================================================================
+constexpr int FZ_THREADS = 320;
+constexpr int FZ_BN = 64;
+constexpr int FZ_SA = 4, FZ_SB = 4;                        // A-ring (converted H1 k-blocks) / B-ring (W2 k-blocks) depth; FZ_SA is
+                                                           // even so that a converter group (even / odd k-blocks) always rewrites
+                                                           // its OWN stages: its pending H1 TMA store is the only other reader
+constexpr int FZ_A_STAGE = 2 * TILE_BYTES;                 // hi + lo, 128 x 32 tf32 each
+constexpr int FZ_B_STAGE = 2 * FZ_BN * 128;                // hi + lo, 64 x 32 tf32 each
+constexpr int FZ_MAX_H1 = 256;
+constexpr int FZ_SMEM_BYTES = FZ_SA * FZ_A_STAGE + FZ_SB * FZ_B_STAGE + 1024 /*align*/ + 256 /*barriers, tmem ptr*/ +
+                              4 * FZ_MAX_H1 + 4 * FZ_BN;
+constexpr int FZ_TMEM_COLS = 512;                          // H1 accumulator [0, 256) + two 64-column H2 accumulators
+constexpr int FZ_MAX_PROBS = 4;
+struct alignas(64) FusedProb {
+  CUtensorMap tx;              // [x|a] planes, K-major, box 32 x 128
+  CUtensorMap tw1, tw2;        // W1 [K1, h1] / W2 [h1, h2] planes, MN-major, box 32 x 32
+  CUtensorMap th1;             // H1 planes (h1, M, 2), box 32 x 32  (store_h1)
+  CUtensorMap tc;              // H2 (h2, M, 1), box 32 x 32
+  const float *bias1, *bias2;
+  uint32_t* bits;              // nullable: relu'(H1) bit masks [M][ldbits]
+  int ldbits, store_h1;
+  int M, K1, h1, h2;
+  int tiles_m, tiles_n, tile_begin;
+};
+struct FusedGroup {
+  int nprob;
+  FusedProb p[FZ_MAX_PROBS];
+};
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_constant__ FusedGroup grp) {
+  extern __shared__ unsigned char smem_dyn[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* aring = base;                                  // also: [x|a] planes (32 KB) + W1 planes during layer 1
+  unsigned char* bring = base + FZ_SA * FZ_A_STAGE;             // also: H2 staging blocks in the epilogue
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bring + FZ_SB * FZ_B_STAGE);
+  uint64_t* fullA = bars;                  // [FZ_SA]  4 converter warps have written the stage
+  uint64_t* emptyA = fullA + FZ_SA;        // [FZ_SA]  the MMAs that read the stage have completed
+  uint64_t* fullB = emptyA + FZ_SA;        // [FZ_SB]
+  uint64_t* emptyB = fullB + FZ_SB;        // [FZ_SB]
+  uint64_t* bar_in1 = emptyB + FZ_SB;      // layer-1 operands landed
+  uint64_t* bar_h1 = bar_in1 + 1;          // layer-1 accumulator complete
+  uint64_t* acc_ready = bar_h1 + 1;        // layer-2 accumulators complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+  float* s_bias1 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [h1]
+  float* s_bias2 = s_bias1 + FZ_MAX_H1;                                                      // [64]
+
+  int pi = 0;
+  while (pi + 1 < grp.nprob && (int)blockIdx.x >= grp.p[pi + 1].tile_begin) ++pi;
+  const FusedProb& P = grp.p[pi];
+  const int M = P.M, h1 = P.h1, h2 = P.h2;
+  const int t = blockIdx.x - P.tile_begin;
+  const int nt = t % P.tiles_n;
+  const int m0 = (t / P.tiles_n) * BM, n0 = nt * FZ_BN;
+  const int nkb = h1 / BK;                                      // k-blocks of the second layer
+  const int w1_plane = (h1 / 32) * 4096;                        // bytes of one W1 plane in shared memory (32 k x h1)
+
+  if (tid == 0) {
+    prefetch_tmap(&P.tx); prefetch_tmap(&P.tw1); prefetch_tmap(&P.tw2);
+    for (int s = 0; s < FZ_SA; ++s) { bar_init(&fullA[s], 4); bar_init(&emptyA[s], 1); }
+    for (int s = 0; s < FZ_SB; ++s) { bar_init(&fullB[s], 1); bar_init(&emptyB[s], 1); }
+    bar_init(bar_in1, 1); bar_init(bar_h1, 1); bar_init(acc_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "n"(FZ_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_trigger();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer ----
+      bar_expect_tx(bar_in1, 2 * TILE_BYTES + 2 * w1_plane);
+      const uint32_t xa = s_addr(aring), w1s = xa + 2 * TILE_BYTES;
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl) tma_load_3d(xa + hl * TILE_BYTES, &P.tx, 0, m0, hl, bar_in1);
+      for (int hl = 0; hl < 2; ++hl)
+        for (int j = 0; j < h1 / 32; ++j) tma_load_3d(w1s + hl * w1_plane + j * 4096, &P.tw1, 32 * j, 0, hl, bar_in1);
+      if (P.store_h1) prefetch_tmap(&P.th1);
+      prefetch_tmap(&P.tc);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % FZ_SB;
+        if (kb >= FZ_SB) bar_wait(&emptyB[s], ((kb / FZ_SB) - 1) & 1);
+        bar_expect_tx(&fullB[s], FZ_B_STAGE);
+        const uint32_t dst = s_addr(bring + s * FZ_B_STAGE);
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+          for (int j = 0; j < FZ_BN / 32; ++j)
+            tma_load_3d(dst + hl * (FZ_B_STAGE / 2) + j * 4096, &P.tw2, n0 + 32 * j, kb * BK, hl, &fullB[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      bar_wait(bar_in1, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        const uint32_t idesc1 = make_idesc(0, 1, h1);
+        const uint32_t a_hi = s_addr(aring), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = b_hi + w1_plane;
+        const int nks = (P.K1 + 7) / 8;
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t ao = ks * 32u, bo = ks * 1024u;
+          mma_tf32(tmem_d, make_sdesc(a_lo + ao, false), make_sdesc(b_hi + bo, true), idesc1, ks ? 1u : 0u);
+          mma_tf32(tmem_d, make_sdesc(a_hi + ao, false), make_sdesc(b_lo + bo, true), idesc1, 1u);
+          mma_tf32(tmem_d, make_sdesc(a_hi + ao, false), make_sdesc(b_hi + bo, true), idesc1, 1u);
+        }
+        mma_commit(bar_h1);
+      }
+      const uint32_t idesc2 = make_idesc(0, 1, FZ_BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb % FZ_SA, sb = kb % FZ_SB;
+        bar_wait(&fullB[sb], (kb / FZ_SB) & 1);
+        bar_wait(&fullA[sa], (kb / FZ_SA) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = s_addr(aring + sa * FZ_A_STAGE), a_lo = a_hi + TILE_BYTES;
+        const uint32_t b_hi = s_addr(bring + sb * FZ_B_STAGE), b_lo = b_hi + FZ_B_STAGE / 2;
+        const uint32_t acc = tmem_d + (uint32_t)FZ_MAX_H1 + (uint32_t)(kb % NACC) * (uint32_t)FZ_BN;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t ao = ks * 32u, bo = ks * 1024u;
+          mma_tf32(acc, make_sdesc(a_lo + ao, false), make_sdesc(b_hi + bo, true), idesc2, (kb >= NACC || ks) ? 1u : 0u);
+          mma_tf32(acc, make_sdesc(a_hi + ao, false), make_sdesc(b_lo + bo, true), idesc2, 1u);
+          mma_tf32(acc, make_sdesc(a_hi + ao, false), make_sdesc(b_hi + bo, true), idesc2, 1u);
+        }
+        mma_commit(&emptyA[sa]);
+        mma_commit(&emptyB[sb]);
+      }
+      mma_commit(acc_ready);
+    }
+    __syncwarp();
+  } else {
+    // ---- converters: layer-1 accumulator -> relu(+ b1) -> hi / lo planes of the layer-2 A operand ----
+    const int cw = warp - 2;                     // 0..7
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int cg = cw >> 2;                      // converter group: even / odd k-blocks; epilogue column chunk
+    const int ctid = tid - 64;                   // 0..255
+    for (int i = ctid; i < h1; i += 256) s_bias1[i] = __ldg(P.bias1 + i);
+    if (ctid < FZ_BN) s_bias2[ctid] = (n0 + ctid < h2) ? __ldg(P.bias2 + n0 + ctid) : 0.0f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int row = 32 * q + lane;               // row of the tile = TMEM lane
+    const int m = m0 + row;
+    const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16);
+    bar_wait(bar_h1, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int kb = cg; kb < nkb; kb += 2) {
+      const int s = kb % FZ_SA;
+      float v[32], lo[32];
+      tmem_ld32_nowait(trow + (uint32_t)(kb * BK), v);
+      // this warp's previous TMA store out of the A ring has finished reading shared memory
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (kb >= FZ_SA) bar_wait(&emptyA[s], ((kb / FZ_SA) - 1) & 1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = v[i] + s_bias1[kb * BK + i];
+        bits |= (x > 0.0f ? 1u : 0u) << i;
+        split_tf32(fmaxf(x, 0.0f), v[i], lo[i]);
+      }
+      unsigned char* st = aring + s * FZ_A_STAGE;
+      stage_row(st, row, v);
+      stage_row(st + TILE_BYTES, row, lo);
+      if (P.bits && m < M && (kb % P.tiles_n) == nt) P.bits[(size_t)m * P.ldbits + kb] = bits;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        bar_arrive(&fullA[s]);
+        if (P.store_h1 && (kb % P.tiles_n) == nt) {
+          // this warp's 32 rows of the stage are a 32 x 32 SWIZZLE_128B box of each plane
+          tma_store_3d(&P.th1, s_addr(st + 32 * q * 128), kb * BK, m0 + 32 * q, 0);
+          tma_store_3d(&P.th1, s_addr(st + TILE_BYTES + 32 * q * 128), kb * BK, m0 + 32 * q, 1);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    // ---- H2 epilogue: this warp owns rows 32q.. and columns 32 cg..+32 of the 128 x 64 tile ----
+    bar_wait(acc_ready, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int c0 = 32 * cg, n_base = n0 + c0;
+    if (n_base < h2) {                           // warp-uniform
+      float v[32], v2[32];
+      const bool two = nkb > 1;
+      tmem_ld32_nowait(trow + (uint32_t)(FZ_MAX_H1 + c0), v);
+      if (two) tmem_ld32_nowait(trow + (uint32_t)(FZ_MAX_H1 + FZ_BN + c0), v2);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf((two ? v[i] + v2[i] : v[i]) + s_bias2[c0 + i], 0.0f);
+      // staging in the B ring: every W2 load has been consumed, and no TMA store of H1 reads from there
+      unsigned char* blk = bring + cw * 4096;
+      stage_row(blk, lane, v);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&P.tc, s_addr(blk), n_base, m0 + 32 * q, 0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(FZ_TMEM_COLS) : "memory");
   }
 }
 

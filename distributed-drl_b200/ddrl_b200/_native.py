@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libddrl_b200.so")
 
 F32, F64, U8 = 0, 1, 2
+GEMM_AUTO, GEMM_TC, GEMM_FFMA = 0, 1, 2
 OK, EINVAL, ECUDA, EEMPTY, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 
 
@@ -48,7 +49,7 @@ SIGNATURES = {
     "ddrl_rb_layout": (_int, [_vp, _pint, _pint, _pint, C.POINTER(_vp)]),
     "ddrl_rb_export": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ddrl_rb_import": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
-    "ddrl_sac_create": (_int, [_int, _int, _int, _int, _int, _int, _f, _f, _f, _f, _f, C.POINTER(_vp)]),
+    "ddrl_sac_create": (_int, [_int, _int, _int, _int, _int, _int, _f, _f, _f, _f, _f, _int, C.POINTER(_vp)]),
     "ddrl_sac_destroy": (_int, [_vp]),
     "ddrl_sac_param_count": (_i64, [_vp]),
     "ddrl_sac_set_weights": (_int, [_vp, _vp, _int, _vp]),
@@ -65,7 +66,7 @@ SIGNATURES = {
     "ddrl_sac_comm_error": (_int, [_vp, _pint]),
     "ddrl_sac_act": (_int, [_vp, _vp, _int, _int, _vp, _u64, _u64, _vp, _vp]),
     "ddrl_sac_debug_stage": (_int, [_vp, _int, _int, _int, _vp]),
-    "ddrl_debug_tc_gemm": (_int, [_int, _vp, _int, _int, _int, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp]),
+    "ddrl_debug_tc_gemm": (_int, [_int, _vp, _int, _int, _int, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _int, _vp]),
     "ddrl_sac_trace_stage": (_int, [_vp, _int, _int, _vp, _int, _pint, _vp]),
     "ddrl_sac_state": (_int, [_vp, _pint, _pint, _pint, _pf, _vp]),
 }

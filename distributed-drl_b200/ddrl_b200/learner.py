@@ -101,20 +101,12 @@ class Learner(object):
         self.seed = int(_opt_get(opt, "seed", 0) or 0)
         self.max_batch = int(max_batch or _opt_get(opt, "batch_size", 256) or 256)
         h = C.c_void_p()
-        import os
-        prev = os.environ.get("DDRL_GEMM")
-        if gemm is not None:
-            os.environ["DDRL_GEMM"] = "tc" if gemm == "tc" else "ffma"
-        try:
-            N.check(self._lib.ddrl_sac_create(self.device, self.obs_dim, self.act_dim, self.hidden[0], self.hidden[1],
-                                              self.max_batch, self.gamma, self.polyak, self.lr, self.alpha,
-                                              self.act_scale, C.byref(h)))
-        finally:
-            if gemm is not None:
-                if prev is None:
-                    os.environ.pop("DDRL_GEMM", None)
-                else:
-                    os.environ["DDRL_GEMM"] = prev
+        if gemm not in (None, "tc", "ffma"):
+            raise ValueError(f"gemm must be None, 'tc' or 'ffma', not {gemm!r}")
+        mode = N.GEMM_AUTO if gemm is None else N.GEMM_TC if gemm == "tc" else N.GEMM_FFMA
+        N.check(self._lib.ddrl_sac_create(self.device, self.obs_dim, self.act_dim, self.hidden[0], self.hidden[1],
+                                          self.max_batch, self.gamma, self.polyak, self.lr, self.alpha,
+                                          self.act_scale, mode, C.byref(h)))
         self._h = h
         self.names = param_names()
         self.shapes = param_shapes(self.obs_dim, self.act_dim, self.hidden)
@@ -244,7 +236,7 @@ class Learner(object):
         s = self._stream()
         D, A = self.obs_dim, self.act_dim
         blk = getattr(batch, "block", None)
-        if blk is not None and all(isinstance(batch[k], np.ndarray) for k in _KEYS_BATCH):
+        if blk is not None and self._views_of_block(batch, blk):
             # our own ReplayBuffer.sample_batch() host result: five views of one pinned block -> ONE H2D copy
             n = int(batch.n)
             nb = n * (2 * D + A + 2) * 4
@@ -313,6 +305,32 @@ class Learner(object):
             out.append(dev)
         return out
 
+    def _views_of_block(self, batch, blk):
+        """True when the five entries of a HostBatch still ARE the views of its pinned block that sample_batch()
+        returned (same address, dtype, layout).  A caller may rebind an entry (batch["rews"] = batch["rews"] * scale,
+        n-step rewards, clipping ...): such a batch must take the generic packing path, not the stale block."""
+        D, A = self.obs_dim, self.act_dim
+        n = int(getattr(batch, "n", 0))
+        if n <= 0 or blk.numel() < n * (2 * D + A + 2) * 4:
+            return False
+        addr = blk.data_ptr()
+        for k, width in (("obs1", D), ("obs2", D), ("acts", A), ("rews", 1), ("done", 1)):
+            v = batch.get(k)
+            if not (isinstance(v, np.ndarray) and v.dtype == np.float32 and v.size == n * width and v.flags.c_contiguous
+                    and v.ctypes.data == addr):
+                return False
+            addr += 4 * n * width
+        return True
+
+    def _noise_seed(self):
+        """Philox key of the on-GPU policy noise.  Data-parallel replicas share opt.seed (it also seeds the initial
+        weights), so the rank is folded in: every rank draws its own eps1/eps2/eps3 for its shard of the batch."""
+        world = self._world()
+        if world > 1:
+            import torch.distributed as dist
+            return (self.seed + 0x9E3779B97F4A7C15 * (dist.get_rank(self._pg) + 1)) & 0xFFFFFFFFFFFFFFFF
+        return self.seed
+
     def train(self, batch, noise=None, sync_outputs=False, split=False):
         """One SAC1 update on `batch` (dict obs1/obs2/acts/rews/done).  `noise` ([3,B,A]) injects the
         three normal draws (parity tests); default: drawn on the GPU.  Returns the reference's fetch
@@ -344,10 +362,10 @@ class Learner(object):
             N.check(self._lib.ddrl_sac_step(self._h, *args, B, nzp, self.seed, *outs, sp))
         elif self._fused:
             # gradients are exchanged over NVLink peer memory inside the optimiser kernel: one graph, no NCCL call
-            N.check(self._lib.ddrl_sac_step_dp(self._h, *args, B, nzp, self.seed, 1.0 / world, *outs, sp))
+            N.check(self._lib.ddrl_sac_step_dp(self._h, *args, B, nzp, self._noise_seed(), 1.0 / world, *outs, sp))
         else:
             import torch.distributed as dist
-            N.check(self._lib.ddrl_sac_compute_grads(self._h, *args, B, nzp, self.seed, 1.0 / world, *outs, sp))
+            N.check(self._lib.ddrl_sac_compute_grads(self._h, *args, B, nzp, self._noise_seed(), 1.0 / world, *outs, sp))
             dist.all_reduce(self._grad, op=dist.ReduceOp.SUM, group=self._pg)
             if self.auto_alpha:
                 dist.all_reduce(self._alpha_stat, op=dist.ReduceOp.SUM, group=self._pg)
@@ -391,7 +409,7 @@ class Learner(object):
         outs = [C.c_void_p(o[k].data_ptr()) for k in ("scalars", "q1", "q2", "logp_pi")]
         N.check(self._lib.ddrl_sac_step_from_buffer(
             self._h, rb.native_handle, B, rb._philox_seed(), rb._counter, rb._rng_stream,
-            C.c_void_p(nz.data_ptr()) if nz is not None else None, self.seed, *outs, C.c_void_p(s.cuda_stream)))
+            C.c_void_p(nz.data_ptr()) if nz is not None else None, self._noise_seed(), *outs, C.c_void_p(s.cuda_stream)))
         rb._counter += 1
         if nz is not None:
             nz.record_stream(s)

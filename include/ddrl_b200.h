@@ -178,9 +178,13 @@ typedef struct ddrl_sac* ddrl_sac_t;
  * hard-wires core.py:91's (400,300) default); alpha < 0 selects the entropy-alpha ('auto') branch
  * (actor_learner.py:46-55, reference-intended semantics); act_scale = action_space.high[0]
  * (core.py:104-106).  Buffers are sized for batches up to max_batch.  Weights start at zero: call
- * ddrl_sac_set_weights. */
+ * ddrl_sac_set_weights.  gemm_mode: DDRL_GEMM_TC (tcgen05 tensor cores, 3xTF32 split, fp32-class accuracy),
+ * DDRL_GEMM_FFMA (plain fp32 FFMA tiles), DDRL_GEMM_AUTO (tensor cores unless the environment says DDRL_GEMM=ffma). */
+#define DDRL_GEMM_AUTO 0
+#define DDRL_GEMM_TC 1
+#define DDRL_GEMM_FFMA 2
 int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int max_batch, float gamma,
-                    float polyak, float lr, float alpha, float act_scale, ddrl_sac_t* out);
+                    float polyak, float lr, float alpha, float act_scale, int gemm_mode, ddrl_sac_t* out);
 int ddrl_sac_destroy(ddrl_sac_t sac);
 int64_t ddrl_sac_param_count(ddrl_sac_t sac);
 
@@ -244,14 +248,16 @@ int ddrl_sac_comm_error(ddrl_sac_t sac, int* out_error);
  * d_noise [n, A] or, when NULL, Philox keyed by (seed, counter).  Uses the handle's main policy weights. */
 int ddrl_sac_act(ddrl_sac_t sac, const float* d_obs, int n, int deterministic, const float* d_noise,
                  uint64_t seed, uint64_t counter, float* d_out_act, void* stream);
-/* profiling aid: enqueue one phase of the step `reps` times (0..6: GEMM stages L1, L2, QL1, QL2, BQ, BP, BP3;
+/* profiling aid: enqueue one phase of the step `reps` times (0..6: GEMM stages L1, L2, QL1, QL2, BQ, BP, BP3 — with
+ * narrow inputs L1 / QL1 are empty and L2 / QL2 are the fused first + second layer launches;
  * 7 prologue, 8 policy heads, 9 Q heads + losses, 10 policy backward rows, 11 optimiser, 12..14 side-stream work) */
 int ddrl_sac_debug_stage(ddrl_sac_t sac, int batch, int stage, int reps, void* stream);
 /* Test entry for the tcgen05 3xTF32 GEMM alone: C[M,N] (splits > 1: `splits` partial outputs M*N floats apart)
  * = opA . opB from dense row-major fp32 device matrices A [a_rows,a_cols], B [b_rows,b_cols]; a_mn / b_mn = 1
- * when the contraction index is the ROW of the stored tensor (MN-major operand), 0 when it is the column. */
+ * when the contraction index is the ROW of the stored tensor (MN-major operand), 0 when it is the column.
+ * bn = 64 | 128: output tile width of the launch (128 x bn tiles). */
 int ddrl_debug_tc_gemm(int device, const float* d_a, int a_rows, int a_cols, int a_mn, const float* d_b, int b_rows,
-                       int b_cols, int b_mn, float* d_c, int m, int n, int k, int splits, void* stream);
+                       int b_cols, int b_mn, float* d_c, int m, int n, int k, int splits, int bn, void* stream);
 /* profiling aid: run the tensor-core launch of GEMM stage `stage` once with per-CTA phase time stamps
  * (d_trace [tiles, 8] of %globaltimer ns: start, setup done, first stage landed, MMAs issued, accumulator complete,
  * warp-0 epilogue done, all warps done) */
