@@ -2307,6 +2307,15 @@ int ddrl_sac_trace_stage(ddrl_sac_t h, int batch, int stage, unsigned long long*
   if (rc) return rc;
   *tiles = 0;
   for (auto& g : pl->stages[stage]) {
+    if (g.tiles_fz > 0) {
+      if (g.tiles_fz > max_tiles) return fail(DDRL_EINVAL, "ddrl_sac_trace_stage: %d tiles > max_tiles", g.tiles_fz);
+      tc::FusedGroup grp = g.grp_fz;
+      grp.trace = d_trace;
+      DDRL_CUDA(launch_pdl(tc::fwd_fused_tc, dim3(g.tiles_fz), dim3(tc::FZ_THREADS), tc::FZ_SMEM_BYTES, (cudaStream_t)stream, grp));
+      DDRL_LAUNCH_CHECK();
+      *tiles = g.tiles_fz;
+      continue;
+    }
     if (g.tiles_tc <= 0) continue;
     if (g.tiles_tc > max_tiles) return fail(DDRL_EINVAL, "ddrl_sac_trace_stage: %d tiles > max_tiles", g.tiles_tc);
     tc::TcGroup grp = g.grp_tc;

@@ -36,7 +36,14 @@ namespace tc {
 
 constexpr int BM = 128, BK = 32;                      // BK tf32 = 128 bytes = one swizzle row
 constexpr int TILE_BYTES = 128 * 128;                 // one A plane tile (128 rows x 32 tf32)
-constexpr int NACC = 2;                               // TMEM accumulators: k-block kb adds into accumulator kb % NACC
+// TMEM accumulators per tile: MMA j of a k-block adds into accumulator j % NACC and the epilogue sums them with
+// round-to-nearest adds.  The tensor core adds every product into its fp32 accumulator with truncation, a bias that
+// grows with the number of additions (measured: 2e-5 gradient error at K ~ 400 with ONE accumulator against 1e-7 for
+// FFMA); NACC accumulators divide it by NACC.  (Rotating accumulators does not change the speed of the main loop:
+// 4.86 us per 8 k-blocks with 1, 2 or 4 of them, with 128 x 128 and 128 x 64 tiles, with 128 or 16 CTAs on the chip
+// — the loop is bound by shared-memory bandwidth: per k-block the 3xTF32 products read A three times and B three
+// times from shared memory while TMA writes the next stage.)
+constexpr int NACC = 4;
 constexpr int MAX_PROBS = 10;
 // Tile width BN is a template parameter of the kernel: 128 x 128 tiles when they fill the chip on their own, 128 x 64
 // tiles for the stages of the small-batch configurations (C1 / C2), where 128-wide tiles leave 68 of the 148 SMs idle
@@ -81,10 +88,20 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define TC_STAMP(i) do { if (grp.trace && lane == 0) grp.trace[(size_t)blockIdx.x * 8 + (i)] = gtime(); } while (0)
+constexpr int TRACE_SLOTS = 32;   // per CTA: 0..7 phase stamps; fused kernel: 8.. MMA issuer per k-block, 16.. / 24.. converter groups
+#define TC_STAMP(i) do { if (grp.trace && lane == 0) grp.trace[(size_t)blockIdx.x * TRACE_SLOTS + (i)] = gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  The tcgen05 / TMA instructions take their operands from uniform registers: issued
+// from a divergent `if (lane == 0)` region the compiler wraps every single one in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY uniformisation loop (measured: ~100 cycles per tcgen05.mma, the whole main loop), so the issuing warps
+// run their loops convergently and only the instruction itself sits under elect.sync.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));       // round to nearest tf32 (sign, 8 exponent, 10 mantissa bits)
@@ -217,17 +234,20 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   // tid 0 starts the first k-block before the CTA-wide setup barrier (it initialised the barriers itself)
   const bool early0 = true;
 
-  if (tid == 0) {
-    prefetch_tmap(&P.ta);
-    prefetch_tmap(&P.tb);
-    for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 2); bar_init(&empty[s], 1); }   // full: A and B producers
-    bar_init(acc_ready, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (early0) {
-      pdl_wait();
-      load_operand(false, 0, 0);
-      load_operand(true, 0, 0);
+  if (warp == 0) {
+    if (elect_one()) {
+      prefetch_tmap(&P.ta);
+      prefetch_tmap(&P.tb);
+      for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], 2); bar_init(&empty[s], 1); }   // full: A and B producers
+      bar_init(acc_ready, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (early0) {
+        pdl_wait();
+        load_operand(false, 0, 0);
+        load_operand(true, 0, 0);
+      }
     }
+    __syncwarp();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "n"(TMEM_COLS) : "memory");
@@ -254,47 +274,45 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
   }
 
   if (warp == 0 || warp == 2) {
-    if (lane == 0) {
-      // ---- TMA producers: warp 0 loads the A planes, warp 2 the B planes (an MN-major operand is four
-      //      32 x 32 boxes per plane, so one thread issuing all 16 copies of a k-block would be the bottleneck) ----
-      const bool is_b = warp == 2;
-      if (!is_b && P.c_tma) prefetch_tmap(&P.tc);
-      for (int kb = early0 ? 1 : 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES) bar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
-        load_operand(is_b, kb, s);
-      }
+    // ---- TMA producers: warp 0 loads the A planes, warp 2 the B planes (an MN-major operand is four
+    //      32 x 32 boxes per plane, so one thread issuing all 16 copies of a k-block would be the bottleneck) ----
+    const bool is_b = warp == 2;
+    if (!is_b && P.c_tma && elect_one()) prefetch_tmap(&P.tc);
+    for (int kb = early0 ? 1 : 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      if (kb >= STAGES) bar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
+      if (elect_one()) load_operand(is_b, kb, s);
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer ----
-      const uint32_t idesc = make_idesc(a_mn, b_mn, BN);
-      const uint32_t a_step = a_mn ? 1024u : 32u, b_step = b_mn ? 1024u : 32u;   // 8 tf32 of K
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        bar_wait(&full[s], (kb / STAGES) & 1);
-        if (kb == 0) TC_STAMP(2);     // first stage landed
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = s_addr(base + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES,
-                       b_lo = b_hi + B_TILE;
-        // The tensor core adds each product into its fp32 accumulator with truncation, a bias that grows with the
-        // number of additions (measured: 2e-5 gradient error at K ~ 400 against 1e-7 for FFMA).  Alternate k-blocks go
-        // to NACC separate accumulators that the epilogue sums with round-to-nearest adds: the bias shrinks by NACC.
-        const uint32_t acc = tmem_d + (uint32_t)(kb % NACC) * (uint32_t)BN;
+    // ---- MMA issuer (the whole warp walks the loop; one elected lane issues) ----
+    const uint32_t idesc = make_idesc(a_mn, b_mn, BN);
+    const int a_step = a_mn ? 1024 : 32, b_step = b_mn ? 1024 : 32;   // bytes per 8 tf32 of K
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      bar_wait(&full[s], (kb / STAGES) & 1);
+      if (kb == 0) TC_STAMP(2);     // first stage landed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = s_addr(base + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES,
+                     b_lo = b_hi + B_TILE;
+      // 12 MMAs per k-block, MMA j into accumulator j % NACC
+      const uint64_t da_lo = make_sdesc(a_lo, a_mn), da_hi = make_sdesc(a_hi, a_mn), db_lo = make_sdesc(b_lo, b_mn),
+                     db_hi = make_sdesc(b_hi, b_mn);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint32_t ao = ks * a_step, bo = ks * b_step;
-          mma_tf32(acc, make_sdesc(a_lo + ao, a_mn), make_sdesc(b_hi + bo, b_mn), idesc, (kb >= NACC || ks) ? 1u : 0u);
-          mma_tf32(acc, make_sdesc(a_hi + ao, a_mn), make_sdesc(b_lo + bo, b_mn), idesc, 1u);
-          mma_tf32(acc, make_sdesc(a_hi + ao, a_mn), make_sdesc(b_hi + bo, b_mn), idesc, 1u);
+          const uint64_t ao = (uint64_t)((ks * a_step) >> 4), bo = (uint64_t)((ks * b_step) >> 4);   // descriptor address field
+          const int j = 3 * ks;
+          mma_tf32(tmem_d + (uint32_t)((j % NACC) * BN), da_lo + ao, db_hi + bo, idesc, (kb > 0 || j >= NACC) ? 1u : 0u);
+          mma_tf32(tmem_d + (uint32_t)(((j + 1) % NACC) * BN), da_hi + ao, db_lo + bo, idesc, (kb > 0 || j + 1 >= NACC) ? 1u : 0u);
+          mma_tf32(tmem_d + (uint32_t)(((j + 2) % NACC) * BN), da_hi + ao, db_hi + bo, idesc, (kb > 0 || j + 2 >= NACC) ? 1u : 0u);
         }
         mma_commit(&empty[s]);          // frees the stage when these MMAs have read it
+        if (kb == nkb - 1) mma_commit(acc_ready);   // covers every MMA issued before it
       }
-      mma_commit(acc_ready);            // covers every MMA issued before it
-      TC_STAMP(3);                      // all MMAs issued
+      __syncwarp();
     }
-    __syncwarp();
+    TC_STAMP(3);                      // all MMAs issued
   }
 
   __syncthreads();                    // s_bias is visible; the issuing lanes have left their loops
@@ -311,33 +329,25 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
     float* C = P.C + (size_t)split * P.c_split_stride;
     float* C_lo = P.C_lo;
     const bool has_bias = P.bias != nullptr;
-    float vv[NCB][32], v2[NCB][32];
     const int cbase = half * 32 * NCB;                                            // first column of this warp in the tile
-    bool live[NCB];
-#pragma unroll
-    for (int cb = 0; cb < NCB; ++cb) live[cb] = n0 + cbase + 32 * cb < N;         // warp-uniform
-    const bool two = nkb > 1;                                                    // second accumulator in use
     const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16);
-#pragma unroll
-    for (int cb = 0; cb < NCB; ++cb)
-      if (live[cb]) tmem_ld32_nowait(trow + (uint32_t)(cbase + 32 * cb), vv[cb]);
-#pragma unroll
-    for (int cb = 0; cb < NCB; ++cb)
-      if (two && live[cb]) tmem_ld32_nowait(trow + (uint32_t)BN + (uint32_t)(cbase + 32 * cb), v2[cb]);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (two) {
-#pragma unroll
-      for (int cb = 0; cb < NCB; ++cb)
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (live[cb]) vv[cb][i] += v2[cb][i];
-    }
 #pragma unroll
     for (int cb = 0; cb < NCB; ++cb) {
       const int c0 = cbase + cb * 32;
       const int n_base = n0 + c0;
       if (n_base >= N) continue;                     // warp-uniform
-      float* v = vv[cb];
+      // sum of the NACC accumulators in index order (round-to-nearest adds); the next accumulator's TMEM load is in
+      // flight while the previous one is added
+      float v[32], v2[2][32];
+      tmem_ld32_nowait(trow + (uint32_t)c0, v);
+      tmem_ld32_nowait(trow + (uint32_t)(BN + c0), v2[0]);
+#pragma unroll
+      for (int acc = 1; acc < NACC; ++acc) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (acc + 1 < NACC) tmem_ld32_nowait(trow + (uint32_t)((acc + 1) * BN + c0), v2[acc & 1]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += v2[(acc - 1) & 1][i];
+      }
       if (m < M) {
         const bool full_n = n_base + 31 < N;
         if (has_bias) {
@@ -400,14 +410,14 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
         stage_row(blk, lane, v);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_3d(&P.tc, s_addr(blk), n_base, m0 + 32 * q, C_lo ? 0 : split);
           if (C_lo) tma_store_3d(&P.tc, s_addr(blk + 4096), n_base, m0 + 32 * q, 1);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
-    if (c_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (c_tma) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // bulk groups are per thread: a no-op for the others
   }
   if (tid == 0) TC_STAMP(5);          // this warp's epilogue done (stores issued and drained)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -422,28 +432,33 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
 // Fused first + second layer of a forward pass (narrow inputs: K1 = D or D + A <= 32, h1 <= 256, h1 % 32 == 0):
 //     H1 = relu([x|a] . W1 + b1)      one k-block, M = 128, N = h1: accumulates in TMEM columns [0, h1)
 //     H2 = relu(H1 . W2 + b2)         128 x 64 output tile per CTA, K = h1
-// One CTA = (pass, 128-row block, 64-column block of H2).  H1 never makes a round trip through L2 as an operand: the
-// converter warps read the L1 accumulator with tcgen05.ld, add the bias, apply relu, split into tf32 hi / lo and write
-// the k-block straight into the shared-memory A stage of the second layer in the canonical K-major SWIZZLE_128B
-// layout (the layout a TMA load of that box would have produced); the W2 k-blocks stream in by TMA meanwhile.  The
-// four CTAs of a row block recompute the (cheap, one k-block) first layer; each of them writes a quarter of H1's
-// k-blocks (hi / lo planes by TMA store from the A stage, relu bit masks) for the passes the backward needs.
+// One CTA = (pass, 128-row block, 64-column block of H2).  H1 never leaves the SM as an operand: the layer-1 accumulator
+// (TMEM lane = row, column = H1 feature) already HAS the layout of a K-major A operand in tensor memory, so the
+// converter warps read it with tcgen05.ld, add the bias, apply relu, split into tf32 hi / lo and write hi back IN
+// PLACE and lo into a 4-k-block ring of TMEM columns with tcgen05.st; the second layer then runs
+// tcgen05.mma with A FROM TENSOR MEMORY and only W2 (streamed by TMA) from shared memory.  Measured reason: with A in
+// shared memory the 3xTF32 products re-read it three times per k-step and the launch was bound by shared-memory
+// bandwidth (MMA operand reads + converter stores + TMA writes: ~1 us per k-block); from TMEM the second layer is
+// bound by the tensor pipe.  The four CTAs of a row block recompute the (cheap, one k-block) first layer; each of
+// them writes a quarter of H1's k-blocks (hi / lo planes by TMA store, relu bit masks) for the passes the backward needs.
 //   warp 0 / lane 0    TMA producer: [x|a] and W1 (once), then the W2 k-block ring (4 stages of 16 KB)
 //   warp 1 / lane 0    MMA issuer: first layer (<= 4 k-steps x 3 products, N = h1), then per k-block 12 MMAs (N = 64)
 //   warps 2..9         converters (two groups of four warps = the four TMEM lane quadrants; even / odd k-blocks),
 //                      then the H2 epilogue (bias, relu, TMA store)
+// TMEM columns: [0, 256) layer-1 accumulator -> hi plane; [256, 384) lo ring (4 x 32); [384, 512) two 64-column
+// layer-2 accumulators (alternate k-blocks, summed in the epilogue: halves the accumulation truncation bias).
 // =====================================================================================================================
 constexpr int FZ_THREADS = 320;
 constexpr int FZ_BN = 64;
-constexpr int FZ_SA = 4, FZ_SB = 4;                        // A-ring (converted H1 k-blocks) / B-ring (W2 k-blocks) depth; FZ_SA is
-                                                           // even so that a converter group (even / odd k-blocks) always rewrites
-                                                           // its OWN stages: its pending H1 TMA store is the only other reader
-constexpr int FZ_A_STAGE = 2 * TILE_BYTES;                 // hi + lo, 128 x 32 tf32 each
+constexpr int FZ_SA = 4, FZ_SB = 4;                        // lo ring (TMEM) / W2 ring (shared memory) depth; FZ_SA is even
+                                                           // so that a converter group (even / odd k-blocks) owns its stages
 constexpr int FZ_B_STAGE = 2 * FZ_BN * 128;                // hi + lo, 64 x 32 tf32 each
 constexpr int FZ_MAX_H1 = 256;
-constexpr int FZ_SMEM_BYTES = FZ_SA * FZ_A_STAGE + FZ_SB * FZ_B_STAGE + 1024 /*align*/ + 256 /*barriers, tmem ptr*/ +
+constexpr int FZ_IN_BYTES = 2 * TILE_BYTES + 2 * (FZ_MAX_H1 / 32) * 4096;   // [x|a] planes + W1 planes; later: H1 store staging
+constexpr int FZ_SMEM_BYTES = FZ_IN_BYTES + FZ_SB * FZ_B_STAGE + 1024 /*align*/ + 256 /*barriers, tmem ptr*/ +
                               4 * FZ_MAX_H1 + 4 * FZ_BN;
-constexpr int FZ_TMEM_COLS = 512;                          // H1 accumulator [0, 256) + two 64-column H2 accumulators
+constexpr int FZ_TMEM_COLS = 512;
+constexpr int FZ_LO_COL = FZ_MAX_H1, FZ_ACC_COL = FZ_MAX_H1 + FZ_SA * BK, FZ_NACC = 2;
 constexpr int FZ_MAX_PROBS = 4;
 struct alignas(64) FusedProb {
   CUtensorMap tx;              // [x|a] planes, K-major, box 32 x 128
@@ -458,20 +473,37 @@ struct alignas(64) FusedProb {
 };
 struct FusedGroup {
   int nprob;
+  unsigned long long* trace;   // nullable (tools/tc_trace.py): per CTA TRACE_SLOTS globaltimer stamps
   FusedProb p[FZ_MAX_PROBS];
 };
 __device__ __forceinline__ void bar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand is read from tensor memory (lane = row, one column per tf32 of K)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {   // caller issues tcgen05.wait::st
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+        "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+        "f"(v[30]), "f"(v[31]) : "memory");
+}
 __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_constant__ FusedGroup grp) {
   extern __shared__ unsigned char smem_dyn[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* aring = base;                                  // also: [x|a] planes (32 KB) + W1 planes during layer 1
-  unsigned char* bring = base + FZ_SA * FZ_A_STAGE;             // also: H2 staging blocks in the epilogue
+  unsigned char* in1 = base;                                    // [x|a] planes (32 KB) + W1 planes; then H1 store staging
+  unsigned char* bring = base + FZ_IN_BYTES;                    // W2 ring; then H2 staging blocks in the epilogue
   uint64_t* bars = reinterpret_cast<uint64_t*>(bring + FZ_SB * FZ_B_STAGE);
-  uint64_t* fullA = bars;                  // [FZ_SA]  4 converter warps have written the stage
-  uint64_t* emptyA = fullA + FZ_SA;        // [FZ_SA]  the MMAs that read the stage have completed
+  uint64_t* fullA = bars;                  // [FZ_SA]  4 converter warps have written hi (in place) + lo ring stage
+  uint64_t* emptyA = fullA + FZ_SA;        // [FZ_SA]  the MMAs that read the lo ring stage have completed
   uint64_t* fullB = emptyA + FZ_SA;        // [FZ_SB]
   uint64_t* emptyB = fullB + FZ_SB;        // [FZ_SB]
   uint64_t* bar_in1 = emptyB + FZ_SB;      // layer-1 operands landed
@@ -481,6 +513,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
   float* s_bias1 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [h1]
   float* s_bias2 = s_bias1 + FZ_MAX_H1;                                                      // [64]
 
+  if (tid == 0) TC_STAMP(0);          // CTA start
   int pi = 0;
   while (pi + 1 < grp.nprob && (int)blockIdx.x >= grp.p[pi + 1].tile_begin) ++pi;
   const FusedProb& P = grp.p[pi];
@@ -491,12 +524,15 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
   const int nkb = h1 / BK;                                      // k-blocks of the second layer
   const int w1_plane = (h1 / 32) * 4096;                        // bytes of one W1 plane in shared memory (32 k x h1)
 
-  if (tid == 0) {
-    prefetch_tmap(&P.tx); prefetch_tmap(&P.tw1); prefetch_tmap(&P.tw2);
-    for (int s = 0; s < FZ_SA; ++s) { bar_init(&fullA[s], 4); bar_init(&emptyA[s], 1); }
-    for (int s = 0; s < FZ_SB; ++s) { bar_init(&fullB[s], 1); bar_init(&emptyB[s], 1); }
-    bar_init(bar_in1, 1); bar_init(bar_h1, 1); bar_init(acc_ready, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (warp == 0) {
+    if (elect_one()) {
+      prefetch_tmap(&P.tx); prefetch_tmap(&P.tw1); prefetch_tmap(&P.tw2);
+      for (int s = 0; s < FZ_SA; ++s) { bar_init(&fullA[s], 4); bar_init(&emptyA[s], 1); }
+      for (int s = 0; s < FZ_SB; ++s) { bar_init(&fullB[s], 1); bar_init(&emptyB[s], 1); }
+      bar_init(bar_in1, 1); bar_init(bar_h1, 1); bar_init(acc_ready, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "n"(FZ_TMEM_COLS) : "memory");
@@ -508,21 +544,25 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
   pdl_wait();
+  if (tid == 0) TC_STAMP(1);          // setup done (barriers, TMEM)
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- TMA producer ----
+    // ---- TMA producer (the whole warp walks the loop; one elected lane issues) ----
+    if (elect_one()) {
       bar_expect_tx(bar_in1, 2 * TILE_BYTES + 2 * w1_plane);
-      const uint32_t xa = s_addr(aring), w1s = xa + 2 * TILE_BYTES;
+      const uint32_t xa = s_addr(in1), w1s = xa + 2 * TILE_BYTES;
 #pragma unroll
       for (int hl = 0; hl < 2; ++hl) tma_load_3d(xa + hl * TILE_BYTES, &P.tx, 0, m0, hl, bar_in1);
       for (int hl = 0; hl < 2; ++hl)
         for (int j = 0; j < h1 / 32; ++j) tma_load_3d(w1s + hl * w1_plane + j * 4096, &P.tw1, 32 * j, 0, hl, bar_in1);
       if (P.store_h1) prefetch_tmap(&P.th1);
       prefetch_tmap(&P.tc);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % FZ_SB;
-        if (kb >= FZ_SB) bar_wait(&emptyB[s], ((kb / FZ_SB) - 1) & 1);
+    }
+    __syncwarp();
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % FZ_SB;
+      if (kb >= FZ_SB) bar_wait(&emptyB[s], ((kb / FZ_SB) - 1) & 1);
+      if (elect_one()) {
         bar_expect_tx(&fullB[s], FZ_B_STAGE);
         const uint32_t dst = s_addr(bring + s * FZ_B_STAGE);
 #pragma unroll
@@ -531,17 +571,18 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
           for (int j = 0; j < FZ_BN / 32; ++j)
             tma_load_3d(dst + hl * (FZ_B_STAGE / 2) + j * 4096, &P.tw2, n0 + 32 * j, kb * BK, hl, &fullB[s]);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer ----
-      bar_wait(bar_in1, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      {
-        const uint32_t idesc1 = make_idesc(0, 1, h1);
-        const uint32_t a_hi = s_addr(aring), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = b_hi + w1_plane;
-        const int nks = (P.K1 + 7) / 8;
+    // ---- MMA issuer (the whole warp walks the loop; one elected lane issues) ----
+    bar_wait(bar_in1, 0);
+    TC_STAMP(2);                    // layer-1 operands landed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      const uint32_t idesc1 = make_idesc(0, 1, h1);
+      const uint32_t a_hi = s_addr(in1), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = b_hi + w1_plane;
+      const int nks = (P.K1 + 7) / 8;
+      if (elect_one()) {
         for (int ks = 0; ks < nks; ++ks) {
           const uint32_t ao = ks * 32u, bo = ks * 1024u;
           mma_tf32(tmem_d, make_sdesc(a_lo + ao, false), make_sdesc(b_hi + bo, true), idesc1, ks ? 1u : 0u);
@@ -550,32 +591,39 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
         }
         mma_commit(bar_h1);
       }
-      const uint32_t idesc2 = make_idesc(0, 1, FZ_BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int sa = kb % FZ_SA, sb = kb % FZ_SB;
-        bar_wait(&fullB[sb], (kb / FZ_SB) & 1);
-        bar_wait(&fullA[sa], (kb / FZ_SA) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = s_addr(aring + sa * FZ_A_STAGE), a_lo = a_hi + TILE_BYTES;
-        const uint32_t b_hi = s_addr(bring + sb * FZ_B_STAGE), b_lo = b_hi + FZ_B_STAGE / 2;
-        const uint32_t acc = tmem_d + (uint32_t)FZ_MAX_H1 + (uint32_t)(kb % NACC) * (uint32_t)FZ_BN;
+      __syncwarp();
+    }
+    const uint32_t idesc2 = make_idesc(0, 1, FZ_BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int sa = kb % FZ_SA, sb = kb % FZ_SB;
+      bar_wait(&fullB[sb], (kb / FZ_SB) & 1);
+      bar_wait(&fullA[sa], (kb / FZ_SA) & 1);
+      TC_STAMP(8 + kb);             // operands of k-block kb ready
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = tmem_d + (uint32_t)(kb * BK), a_lo = tmem_d + (uint32_t)(FZ_LO_COL + sa * BK);
+      const uint32_t b_hi = s_addr(bring + sb * FZ_B_STAGE), b_lo = b_hi + FZ_B_STAGE / 2;
+      const uint32_t acc = tmem_d + (uint32_t)(FZ_ACC_COL + (kb % FZ_NACC) * FZ_BN);
+      const uint64_t db_lo = make_sdesc(b_lo, true), db_hi = make_sdesc(b_hi, true);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint32_t ao = ks * 32u, bo = ks * 1024u;
-          mma_tf32(acc, make_sdesc(a_lo + ao, false), make_sdesc(b_hi + bo, true), idesc2, (kb >= NACC || ks) ? 1u : 0u);
-          mma_tf32(acc, make_sdesc(a_hi + ao, false), make_sdesc(b_lo + bo, true), idesc2, 1u);
-          mma_tf32(acc, make_sdesc(a_hi + ao, false), make_sdesc(b_hi + bo, true), idesc2, 1u);
+          const uint64_t bo = (uint64_t)((ks * 1024) >> 4);
+          const uint32_t ac = (uint32_t)(ks * 8);                 // 8 tf32 of K = 8 TMEM columns
+          mma_tf32_ts(acc, a_lo + ac, db_hi + bo, idesc2, (kb >= FZ_NACC || ks) ? 1u : 0u);
+          mma_tf32_ts(acc, a_hi + ac, db_lo + bo, idesc2, 1u);
+          mma_tf32_ts(acc, a_hi + ac, db_hi + bo, idesc2, 1u);
         }
         mma_commit(&emptyA[sa]);
         mma_commit(&emptyB[sb]);
+        if (kb == nkb - 1) mma_commit(acc_ready);
       }
-      mma_commit(acc_ready);
+      __syncwarp();
     }
-    __syncwarp();
+    TC_STAMP(4);                    // all MMAs issued
   } else {
-    // ---- converters: layer-1 accumulator -> relu(+ b1) -> hi / lo planes of the layer-2 A operand ----
+    // ---- converters: layer-1 accumulator -> relu(+ b1) -> hi (in place) / lo (ring) A operand of layer 2 in TMEM ----
     const int cw = warp - 2;                     // 0..7
-    const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int cg = cw >> 2;                      // converter group: even / odd k-blocks; epilogue column chunk
     const int ctid = tid - 64;                   // 0..255
     for (int i = ctid; i < h1; i += 256) s_bias1[i] = __ldg(P.bias1 + i);
@@ -584,16 +632,18 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
     const int row = 32 * q + lane;               // row of the tile = TMEM lane
     const int m = m0 + row;
     const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16);
+    unsigned char* stg = in1 + cw * 8192;        // this warp's H1 store staging (hi 4 KB + lo 4 KB): free after layer 1
     bar_wait(bar_h1, 0);
+    if (warp == 2) TC_STAMP(3);       // layer-1 accumulator complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int kb = cg; kb < nkb; kb += 2) {
       const int s = kb % FZ_SA;
       float v[32], lo[32];
       tmem_ld32_nowait(trow + (uint32_t)(kb * BK), v);
-      // this warp's previous TMA store out of the A ring has finished reading shared memory
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      if (kb >= FZ_SA) bar_wait(&emptyA[s], ((kb / FZ_SA) - 1) & 1);
+      if (kb >= FZ_SA) {
+        bar_wait(&emptyA[s], ((kb / FZ_SA) - 1) & 1);          // the MMAs that read lo ring stage s have completed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       uint32_t bits = 0;
 #pragma unroll
@@ -602,48 +652,59 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
         bits |= (x > 0.0f ? 1u : 0u) << i;
         split_tf32(fmaxf(x, 0.0f), v[i], lo[i]);
       }
-      unsigned char* st = aring + s * FZ_A_STAGE;
-      stage_row(st, row, v);
-      stage_row(st + TILE_BYTES, row, lo);
-      if (P.bits && m < M && (kb % P.tiles_n) == nt) P.bits[(size_t)m * P.ldbits + kb] = bits;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tmem_st32(trow + (uint32_t)(kb * BK), v);
+      tmem_st32(trow + (uint32_t)(FZ_LO_COL + s * BK), lo);
+      const bool mine = (kb % P.tiles_n) == nt;                // this CTA's share of H1 for the backward
+      if (P.bits && m < M && mine) P.bits[(size_t)m * P.ldbits + kb] = bits;
+      if (P.store_h1 && mine) {
+        // this warp's previous TMA store has finished reading the staging block (bulk groups are per thread: only
+        // the lane that issued it waits)
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        stage_row(stg, lane, v);
+        stage_row(stg + 4096, lane, lo);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (q == 0) TC_STAMP(16 + kb);  // this warp has converted its rows of k-block kb
+      if (elect_one()) {
         bar_arrive(&fullA[s]);
-        if (P.store_h1 && (kb % P.tiles_n) == nt) {
-          // this warp's 32 rows of the stage are a 32 x 32 SWIZZLE_128B box of each plane
-          tma_store_3d(&P.th1, s_addr(st + 32 * q * 128), kb * BK, m0 + 32 * q, 0);
-          tma_store_3d(&P.th1, s_addr(st + TILE_BYTES + 32 * q * 128), kb * BK, m0 + 32 * q, 1);
+        if (P.store_h1 && mine) {
+          tma_store_3d(&P.th1, s_addr(stg), kb * BK, m0 + 32 * q, 0);
+          tma_store_3d(&P.th1, s_addr(stg + 4096), kb * BK, m0 + 32 * q, 1);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
     // ---- H2 epilogue: this warp owns rows 32q.. and columns 32 cg..+32 of the 128 x 64 tile ----
     bar_wait(acc_ready, 0);
+    if (warp == 2) TC_STAMP(5);       // layer-2 accumulators complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int c0 = 32 * cg, n_base = n0 + c0;
     if (n_base < h2) {                           // warp-uniform
       float v[32], v2[32];
-      const bool two = nkb > 1;
-      tmem_ld32_nowait(trow + (uint32_t)(FZ_MAX_H1 + c0), v);
-      if (two) tmem_ld32_nowait(trow + (uint32_t)(FZ_MAX_H1 + FZ_BN + c0), v2);
+      tmem_ld32_nowait(trow + (uint32_t)(FZ_ACC_COL + c0), v);
+      if (nkb > 1) tmem_ld32_nowait(trow + (uint32_t)(FZ_ACC_COL + FZ_BN + c0), v2);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaxf((two ? v[i] + v2[i] : v[i]) + s_bias2[c0 + i], 0.0f);
-      // staging in the B ring: every W2 load has been consumed, and no TMA store of H1 reads from there
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf((nkb > 1 ? v[i] + v2[i] : v[i]) + s_bias2[c0 + i], 0.0f);
+      // staging in the W2 ring: every W2 load has been consumed
       unsigned char* blk = bring + cw * 4096;
       stage_row(blk, lane, v);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         tma_store_3d(&P.tc, s_addr(blk), n_base, m0 + 32 * q, 0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0) TC_STAMP(6);          // all warps done
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(FZ_TMEM_COLS) : "memory");
   }

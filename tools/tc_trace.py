@@ -21,7 +21,7 @@ for _ in range(3):
     L.train(batch)
 torch.cuda.synchronize()
 lib = _native.lib(); s = torch.cuda.current_stream()
-tr = torch.zeros((1024, 8), dtype=torch.int64, device=dev)
+tr = torch.zeros((1024, 32), dtype=torch.int64, device=dev)
 tiles = C.c_int()
 names = ["start", "setup", "1st stage", "MMAs issued", "acc done", "epi warp0", "all warps"]
 for rep in range(3):
@@ -34,5 +34,12 @@ print(f"{cfg} stage {stage}: {tiles.value} tiles; ns relative to the first CTA s
 for i, nm in enumerate(names):
     col = t[:, i] - t0
     print(f"  {nm:12s} median {np.median(col):8.0f}   max {col.max():8.0f}")
+full = tr[: tiles.value].cpu().numpy().astype(np.float64)
+if full[:, 8:].any():
+    print("  fused kernel, ns after the layer-1 accumulator (median over CTAs): k-block operands ready (MMA issuer) / converted (q0 warp)")
+    ref = full[:, 3]
+    for kb in range(8):
+        if full[:, 8 + kb].any():
+            print(f"    kb {kb}: ready {np.median(full[:, 8 + kb] - ref):7.0f}   converted {np.median(full[:, 16 + kb] - ref):7.0f}")
 print("  per-CTA durations (median ns): setup %.0f, load latency %.0f, mainloop issue %.0f, MMA drain %.0f, epilogue %.0f, join %.0f" % tuple(
     np.median(t[:, i + 1] - t[:, i]) for i in range(6)))
