@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
     int fold_b, const float* __restrict__ H2b, const float* __restrict__ Whead, const float* __restrict__ NOISE, int A, int ldh,
     float act_scale) {
   __shared__ double s_part[ROW_WARPS][4];
+  __shared__ double s_red[ROW_WARPS * 32][4];
   __shared__ float s_hout[ROW_WARPS][16];
   __shared__ bool s_last;
   pdl_trigger();
@@ -497,34 +498,53 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
     const float *hd = H2d + (size_t)row * h2, *he = H2e + (size_t)row * h2, *hf = H2f + (size_t)row * h2,
                 *hg = H2g + (size_t)row * h2, *hh = H2h + (size_t)row * h2;
     float qd = 0.f, qe = 0.f, qf = 0.f, qg = 0.f, qh = 0.f;
-    if (vec) {
+    // h2 <= 256 and 128-bit rows: every lane keeps its (<= 2 x 4) features of the five rows and the four weight vectors
+    // in registers — all loads of the kernel are issued before anything is consumed (one L2 round trip), and the dZ2
+    // pass below needs no second read
+    constexpr int NV = 2;
+    const bool fast = vec && h2 <= 128 * NV;
+    float4 xd[NV], xe[NV], xf[NV], w1[NV], w2[NV];
+    if (fast) {
+      float4 xg[NV], xh[NV], w1t[NV], w2t[NV];
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int k = lane * 4 + 128 * u;
+        const bool ok = k < h2;
+        xd[u] = ok ? ld4(hd + k) : z4; xe[u] = ok ? ld4(he + k) : z4; xf[u] = ok ? ld4(hf + k) : z4;
+        xg[u] = ok ? ld4(hg + k) : z4; xh[u] = ok ? ld4(hh + k) : z4;
+        w1[u] = ok ? ld4(W3q1 + k) : z4; w2[u] = ok ? ld4(W3q2 + k) : z4;
+        w1t[u] = ok ? ld4(W3q1t + k) : z4; w2t[u] = ok ? ld4(W3q2t + k) : z4;
+      }
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        qd = dot4(xd[u], w1[u], qd); qe = dot4(xe[u], w2[u], qe); qf = dot4(xf[u], w1[u], qf);
+        qg = dot4(xg[u], w1t[u], qg); qh = dot4(xh[u], w2t[u], qh);
+      }
+    } else if (vec) {
       for (int k = lane * 4; k < h2; k += 128) {
-        const float4 w1 = ld4(W3q1 + k), w2 = ld4(W3q2 + k), w1t = ld4(W3q1t + k), w2t = ld4(W3q2t + k);
-        qd = dot4(ld4(hd + k), w1, qd);
-        qe = dot4(ld4(he + k), w2, qe);
-        qf = dot4(ld4(hf + k), w1, qf);
-        qg = dot4(ld4(hg + k), w1t, qg);
-        qh = dot4(ld4(hh + k), w2t, qh);
+        const float4 v1 = ld4(W3q1 + k), v2 = ld4(W3q2 + k), v1t = ld4(W3q1t + k), v2t = ld4(W3q2t + k);
+        qd = dot4(ld4(hd + k), v1, qd);
+        qe = dot4(ld4(he + k), v2, qe);
+        qf = dot4(ld4(hf + k), v1, qf);
+        qg = dot4(ld4(hg + k), v1t, qg);
+        qh = dot4(ld4(hh + k), v2t, qh);
       }
     } else {
       for (int k = lane; k < h2; k += 32) {
-        const float w1 = W3q1[k], w2 = W3q2[k];
-        qd = fmaf(hd[k], w1, qd);
-        qe = fmaf(he[k], w2, qe);
-        qf = fmaf(hf[k], w1, qf);
+        const float v1 = W3q1[k], v2 = W3q2[k];
+        qd = fmaf(hd[k], v1, qd);
+        qe = fmaf(he[k], v2, qe);
+        qf = fmaf(hf[k], v1, qf);
         qg = fmaf(hg[k], W3q1t[k], qg);
         qh = fmaf(hh[k], W3q2t[k], qh);
       }
     }
-    qd = warp_sum(qd) + W3q1[h2];
-    qe = warp_sum(qe) + W3q2[h2];
-    qf = warp_sum(qf) + W3q1[h2];
-    qg = warp_sum(qg) + W3q1t[h2];
-    qh = warp_sum(qh) + W3q2t[h2];
     const float invB = 1.0f / (float)B;
-    const float lp1 = LOGP1[row];
+    const float lp1 = LOGP1[row], rew = R[row], dn = DN[row];
     float lp2;
     if (fold_b) {
+      // (its loads are issued while the rows above are still in flight; the reductions below come after)
       float unused;
       lp2 = heads_row_eval(H2b + (size_t)row * h2, h2, ldh, A, Whead, NOISE + ((size_t)B + row) * A, act_scale, s_hout[w], lane,
                            &unused);
@@ -532,32 +552,42 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
     } else {
       lp2 = LOGP2[row];
     }
+    qd = warp_sum(qd) + W3q1[h2];
+    qe = warp_sum(qe) + W3q2[h2];
+    qf = warp_sum(qf) + W3q1[h2];
+    qg = warp_sum(qg) + W3q1t[h2];
+    qh = warp_sum(qh) + W3q2t[h2];
     const float min_q = fminf(qg, qh);
     const float v_backup = __fsub_rn(min_q, __fmul_rn(alpha, lp2));
-    const float q_backup = __fadd_rn(R[row], __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.0f, DN[row])), v_backup));
+    const float q_backup = __fadd_rn(rew, __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.0f, dn)), v_backup));
     const float e1 = __fsub_rn(q_backup, qd), e2 = __fsub_rn(q_backup, qe);
     const float dqd = -e1 * invB, dqe = -e2 * invB, dqf = -invB;
-    if (vec) {
+    auto dz4 = [](const float4& x, const float4& wv, float dq) {
+      return make_float4(x.x > 0.f ? dq * wv.x : 0.f, x.y > 0.f ? dq * wv.y : 0.f, x.z > 0.f ? dq * wv.z : 0.f, x.w > 0.f ? dq * wv.w : 0.f);
+    };
+    auto put3 = [&](size_t o, const float4& zd, const float4& ze, const float4& zf) {
+      if (zlo) { st_split4(dZ2d, zlo, o, zd); st_split4(dZ2e, zlo, o, ze); st_split4(dZ2f, zlo, o, zf); }
+      else {
+        *reinterpret_cast<float4*>(dZ2d + o) = zd;
+        *reinterpret_cast<float4*>(dZ2e + o) = ze;
+        *reinterpret_cast<float4*>(dZ2f + o) = zf;
+      }
+    };
+    if (fast) {
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int k = lane * 4 + 128 * u;
+        if (k < h2) put3((size_t)row * ldz + k, dz4(xd[u], w1[u], dqd), dz4(xe[u], w2[u], dqe), dz4(xf[u], w1[u], dqf));
+      }
+    } else if (vec) {
       for (int k = lane * 4; k < h2; k += 128) {
-        const float4 w1 = ld4(W3q1 + k), w2 = ld4(W3q2 + k), xd = ld4(hd + k), xe = ld4(he + k), xf = ld4(hf + k);
-        const float4 zd = make_float4(xd.x > 0.f ? dqd * w1.x : 0.f, xd.y > 0.f ? dqd * w1.y : 0.f, xd.z > 0.f ? dqd * w1.z : 0.f,
-                                      xd.w > 0.f ? dqd * w1.w : 0.f);
-        const float4 ze = make_float4(xe.x > 0.f ? dqe * w2.x : 0.f, xe.y > 0.f ? dqe * w2.y : 0.f, xe.z > 0.f ? dqe * w2.z : 0.f,
-                                      xe.w > 0.f ? dqe * w2.w : 0.f);
-        const float4 zf = make_float4(xf.x > 0.f ? dqf * w1.x : 0.f, xf.y > 0.f ? dqf * w1.y : 0.f, xf.z > 0.f ? dqf * w1.z : 0.f,
-                                      xf.w > 0.f ? dqf * w1.w : 0.f);
-        const size_t o = (size_t)row * ldz + k;
-        if (zlo) { st_split4(dZ2d, zlo, o, zd); st_split4(dZ2e, zlo, o, ze); st_split4(dZ2f, zlo, o, zf); }
-        else {
-          *reinterpret_cast<float4*>(dZ2d + o) = zd;
-          *reinterpret_cast<float4*>(dZ2e + o) = ze;
-          *reinterpret_cast<float4*>(dZ2f + o) = zf;
-        }
+        const float4 v1 = ld4(W3q1 + k), v2 = ld4(W3q2 + k);
+        put3((size_t)row * ldz + k, dz4(ld4(hd + k), v1, dqd), dz4(ld4(he + k), v2, dqe), dz4(ld4(hf + k), v1, dqf));
       }
     } else {
       for (int k = lane; k < h2; k += 32) {
-        const float w1 = W3q1[k], w2 = W3q2[k];
-        const float zd = hd[k] > 0.0f ? dqd * w1 : 0.0f, ze = he[k] > 0.0f ? dqe * w2 : 0.0f, zf = hf[k] > 0.0f ? dqf * w1 : 0.0f;
+        const float v1 = W3q1[k], v2 = W3q2[k];
+        const float zd = hd[k] > 0.0f ? dqd * v1 : 0.0f, ze = he[k] > 0.0f ? dqe * v2 : 0.0f, zf = hf[k] > 0.0f ? dqf * v1 : 0.0f;
         const size_t o = (size_t)row * ldz + k;
         if (zlo) { put_split(dZ2d, zlo, o, zd); put_split(dZ2e, zlo, o, ze); put_split(dZ2f, zlo, o, zf); }
         else { dZ2d[o] = zd; dZ2e[o] = ze; dZ2f[o] = zf; }
@@ -585,14 +615,29 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) k_qheads_losses(
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)vgrid - 1);
   __syncthreads();
-  if (s_last && threadIdx.x < 4) {
+  if (s_last) {
+    // the last CTA combines the per-CTA partials: thread t sums CTAs t, t + 256, ... (independent loads), then a
+    // fixed-order tree in shared memory — deterministic whatever the order the CTAs finished in
     __threadfence();
-    double acc = 0.0;
-    for (unsigned int i = 0; i < (unsigned int)vgrid; ++i) acc += partials[(size_t)i * 4 + threadIdx.x];
-    const float v = (float)((threadIdx.x == 1 || threadIdx.x == 2 ? 0.5 : 1.0) * acc / B);
-    if (threadIdx.x < 3) { SCAL[threadIdx.x] = v; if (d.out_scalars) d.out_scalars[threadIdx.x] = v; }
-    else SCAL[4] = v;   // mean logp1 (entropy-alpha gradient; all-reduced across ranks by the host)
-    if (threadIdx.x == 0) { SCAL[3] = alpha; if (d.out_scalars) d.out_scalars[3] = alpha; *ticket = 0u; }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (unsigned int i = threadIdx.x; i < (unsigned int)vgrid; i += ROW_WARPS * 32)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] += partials[(size_t)i * 4 + c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s_red[threadIdx.x][c] = acc[c];
+    __syncthreads();
+    for (int stride = ROW_WARPS * 16; stride > 0; stride >>= 1) {
+      if ((int)threadIdx.x < stride)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s_red[threadIdx.x][c] += s_red[threadIdx.x + stride][c];
+      __syncthreads();
+    }
+    if (threadIdx.x < 4) {
+      const float v = (float)((threadIdx.x == 1 || threadIdx.x == 2 ? 0.5 : 1.0) * s_red[0][threadIdx.x] / B);
+      if (threadIdx.x < 3) { SCAL[threadIdx.x] = v; if (d.out_scalars) d.out_scalars[threadIdx.x] = v; }
+      else SCAL[4] = v;   // mean logp1 (entropy-alpha gradient; all-reduced across ranks by the host)
+      if (threadIdx.x == 0) { SCAL[3] = alpha; if (d.out_scalars) d.out_scalars[3] = alpha; *ticket = 0u; }
+    }
   }
 }
 
@@ -733,20 +778,6 @@ __global__ void __launch_bounds__(128) k_actor_forward(int n, int D, int A, int 
 // optimiser: TF1 Adam (epsilon-hat form) for pi and q parameter ranges, then polyak with the new
 // weights (actor_learner.py:73-87); gradients arrive as S split-K partials (S = 1 after all-reduce).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void d_grad_reduce(int vb, int vgrid, int64_t P, int S, const float* __restrict__ Gp, float* G) {
-  const int64_t stride = (int64_t)vgrid * blockDim.x;
-  for (int64_t i = (int64_t)vb * blockDim.x + threadIdx.x; i < P; i += stride) {
-    float g = Gp[i];
-    for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
-    G[i] = g;
-  }
-}
-__global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const float* __restrict__ Gp, float* G) {
-  pdl_trigger();
-  pdl_wait();
-  d_grad_reduce(blockIdx.x, gridDim.x, P, S, Gp, G);
-}
-
 // hi/lo planes of the weight blocks the tensor-core GEMMs read (kernel rows only; the bias row is added in
 // the GEMM epilogue from the fp32 master copy): block b = rows x N[b] at sp_off[b], row pitch pitch[b]
 struct SplitMap {
@@ -754,6 +785,7 @@ struct SplitMap {
   int N[6], pitch[6];
   long long int_off[6], size[6], sp_off[6];
   long long plane;
+  int vec4;        // every N[b] is a multiple of 4: the optimiser may treat 4 consecutive parameters as one row segment
 };
 __device__ __forceinline__ void write_split(const SplitMap& mp, int64_t i, float w, float* __restrict__ Wsp) {
 #pragma unroll
@@ -762,6 +794,18 @@ __device__ __forceinline__ void write_split(const SplitMap& mp, int64_t i, float
       const int64_t e = i - mp.int_off[b];
       const int64_t r = e / mp.N[b], c = e - r * mp.N[b];
       put_split(Wsp, mp.plane, (size_t)(mp.sp_off[b] + r * mp.pitch[b] + c), w);
+    }
+  }
+}
+// four consecutive parameters starting at a multiple of 4 (mp.vec4: every block width is a multiple of 4, so they sit in
+// one row of one block): one 128-bit store per plane
+__device__ __forceinline__ void write_split4(const SplitMap& mp, int64_t i, const float4& w, float* __restrict__ Wsp) {
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    if (b < mp.nblk && i >= mp.int_off[b] && i < mp.int_off[b] + mp.size[b]) {
+      const int e = (int)(i - mp.int_off[b]);
+      const int r = e / mp.N[b], c = e - r * mp.N[b];
+      st_split4(Wsp, mp.plane, (size_t)(mp.sp_off[b] + (long long)r * mp.pitch[b] + c), w);
     }
   }
 }
@@ -774,54 +818,175 @@ __global__ void __launch_bounds__(256) k_split_weights(SplitMap mp, int64_t P, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of a NARROW first layer (policy W1: K = D <= 32 input features): d[W;b][k, n] = sum_r [x|1][r, k] dZ[r, n].
+// As a tensor-core stage this was one more dependent launch of ~10 us for 13 MFLOP at the very end of the backward
+// chain; here it is FFMA: grid = (32-column chunks of n) x (64-row slices of the batch).  lane = column, warp w owns
+// rows w, w + 8, ... of the slice and ALL K + 1 outputs of its column (K + 1 accumulators per thread, 2 loads per
+// 34 FMAs: a load -> few-FMA loop is serialised on the L2 latency by the compiler, measured 47 us); the eight warps'
+// partial sums are combined in shared memory in warp order (deterministic).  The slice's [x|1] rows are staged in
+// shared memory (hi + lo is exact).  Each slice writes its own partial block; the optimiser sums the slices in index
+// order, see NarrowGrad.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_nc_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+constexpr int NW_ROWS = 64;       // batch rows per slice
+constexpr int NW_MAXK = 33;       // K + 1 (bias row) <= 33
+__global__ void __launch_bounds__(256) k_wgrad_narrow(int B, int K, int N, const float* __restrict__ X, int ldx, long long xlo,
+                                                      const float* __restrict__ Z, int ldz, long long zlo, float* Gn) {
+  __shared__ float s_x[NW_ROWS][NW_MAXK + 1];
+  __shared__ float s_acc[8][NW_MAXK][33];
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * NW_ROWS, nr = min(NW_ROWS, B - r0);
+  constexpr int RW = NW_ROWS / 8;             // rows per warp
+  // this thread's dZ values first (hi + lo planes), so that they are in flight while [x|1] is staged
+  float zh[RW], zl[RW];
+  {
+    const float* zr = Z + (size_t)r0 * ldz + min(col, N - 1);
+#pragma unroll
+    for (int u = 0; u < RW; ++u) {
+      const int ru = min(w + 8 * u, nr - 1);  // rows beyond the slice re-read its last row and are dropped below
+      zh[u] = ld_nc_f32(zr + (size_t)ru * ldz);
+      zl[u] = ld_nc_f32(zr + zlo + (size_t)ru * ldz);
+    }
+  }
+  for (int i = threadIdx.x; i < NW_ROWS * (NW_MAXK + 1); i += 256) {
+    const int r = i / (NW_MAXK + 1), k = i - r * (NW_MAXK + 1);
+    float v = 0.0f;
+    if (r < nr && k <= K) v = k < K ? X[(size_t)(r0 + r) * ldx + k] + X[xlo + (size_t)(r0 + r) * ldx + k] : 1.0f;
+    s_x[r][k] = v;
+  }
+  __syncthreads();
+  float acc[NW_MAXK];
+#pragma unroll
+  for (int k = 0; k < NW_MAXK; ++k) acc[k] = 0.0f;
+#pragma unroll
+  for (int u = 0; u < RW; ++u) {
+    const int r = w + 8 * u;
+    const float z = r < nr ? zh[u] + zl[u] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < NW_MAXK; ++k) acc[k] = fmaf(s_x[r][k], z, acc[k]);     // columns k > K of s_x are zero
+  }
+#pragma unroll
+  for (int k = 0; k < NW_MAXK; ++k) s_acc[w][k][lane] = acc[k];
+  __syncthreads();
+  float* out = Gn + (size_t)blockIdx.y * (size_t)(K + 1) * N;
+  for (int i = threadIdx.x; i < (K + 1) * 32; i += 256) {
+    const int k = i >> 5, l = i & 31;
+    float t = s_acc[0][k][l];
+#pragma unroll
+    for (int ww = 1; ww < 8; ++ww) t += s_acc[ww][k][l];
+    if (blockIdx.x * 32 + l < N) out[(size_t)k * N + blockIdx.x * 32 + l] = t;
+  }
+}
+// the parameter range [off, off + size) whose gradient arrives as SN slices from k_wgrad_narrow instead of split-K partials
+struct NarrowGrad {
+  const float* Gn;
+  long long off, size;
+  int SN;
+};
+__device__ __forceinline__ float4 grad4(int64_t i, int64_t P, int S, const float* __restrict__ Gp, const NarrowGrad& ng) {
+  if (ng.SN > 0 && i >= ng.off && i < ng.off + ng.size) {
+    const float* p = ng.Gn + (i - ng.off);
+    float4 g = *reinterpret_cast<const float4*>(p);
+    for (int s = 1; s < ng.SN; ++s) {
+      const float4 q = *reinterpret_cast<const float4*>(p + (size_t)s * ng.size);
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    return g;
+  }
+  float4 g = *reinterpret_cast<const float4*>(Gp + i);
+  for (int s = 1; s < S; ++s) {
+    const float4 q = *reinterpret_cast<const float4*>(Gp + (size_t)s * P + i);
+    g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+  }
+  return g;
+}
+
+__global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const float* __restrict__ Gp, float* G, NarrowGrad ng) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < P; i += stride)
+    *reinterpret_cast<float4*>(G + i) = grad4(i, P, S, Gp, ng);
+}
+
+// one Adam + polyak update of 4 consecutive parameters (i % 4 == 0; P_pi % 4 == 0 so one learning rate applies)
+__device__ __forceinline__ void adam4(int64_t i, const float4& g4, float gs, float lr_i, float polyak, float* W, float* Wt, float* Mo,
+                                      float* Vo, const SplitMap* mp, float* Wsp, float* Wtsp) {
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float4 m4 = *reinterpret_cast<const float4*>(Mo + i), v4 = *reinterpret_cast<const float4*>(Vo + i);
+  const float4 w4 = *reinterpret_cast<const float4*>(W + i), t4 = *reinterpret_cast<const float4*>(Wt + i);
+  const float gv[4] = {g4.x * gs, g4.y * gs, g4.z * gs, g4.w * gs};
+  const float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w},
+              tv[4] = {t4.x, t4.y, t4.z, t4.w};
+  float mo[4], vo[4], wo[4], to[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    mo[e] = b1 * mv[e] + (1.0f - b1) * gv[e];
+    vo[e] = b2 * vv[e] + (1.0f - b2) * gv[e] * gv[e];
+    wo[e] = wv[e] - lr_i * mo[e] / (sqrtf(vo[e]) + eps);
+    to[e] = polyak * tv[e] + (1.0f - polyak) * wo[e];
+  }
+  const float4 wn = make_float4(wo[0], wo[1], wo[2], wo[3]), tn = make_float4(to[0], to[1], to[2], to[3]);
+  *reinterpret_cast<float4*>(Mo + i) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+  *reinterpret_cast<float4*>(Vo + i) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+  *reinterpret_cast<float4*>(W + i) = wn;
+  *reinterpret_cast<float4*>(Wt + i) = tn;
+  if (mp) {
+    if (mp->vec4) { write_split4(*mp, i, wn, Wsp); write_split4(*mp, i, tn, Wtsp); }
+    else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { write_split(*mp, i + e, wo[e], Wsp); write_split(*mp, i + e, to[e], Wtsp); }
+    }
+  }
+}
+// entropy-alpha (reference-intended semantics): one scalar Adam step, unordered wrt the rest; uses the
+// pre-update mean(logp1) of this step
+__device__ __forceinline__ void alpha_step(StepState* st, float lr, float mean_logp, float target_entropy) {
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  st->t_alpha += 1;
+  const double ta = (double)st->t_alpha;
+  const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
+  const float g = -(mean_logp + target_entropy);
+  st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * g;
+  st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * g * g;
+  st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
+}
 __device__ __forceinline__ void d_adam_polyak(int vb, int vgrid, StepState* st, int64_t P, int64_t P_pi, int S,
                                                      const float* __restrict__ Gp, float lr, float polyak,
                                                      float target_entropy, const float* __restrict__ SCAL,
                                                      float* W, float* Wt, float* Mo, float* Vo,
-                                                     const SplitMap* mp = nullptr, float* Wsp = nullptr, float* Wtsp = nullptr) {
-  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+                                                     const NarrowGrad& ng, const SplitMap* mp = nullptr, float* Wsp = nullptr,
+                                                     float* Wtsp = nullptr) {
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
-  const int64_t stride = (int64_t)vgrid * blockDim.x;
-  for (int64_t i = (int64_t)vb * blockDim.x + threadIdx.x; i < P; i += stride) {
-    float g = Gp[i];
-    for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
-    g *= gs;
-    const float m = b1 * Mo[i] + (1.0f - b1) * g;
-    const float v = b2 * Vo[i] + (1.0f - b2) * g * g;
-    Mo[i] = m; Vo[i] = v;
-    const float w = W[i] - (i < P_pi ? lr_pi : lr_q) * m / (sqrtf(v) + eps);
-    W[i] = w;
-    const float wt = polyak * Wt[i] + (1.0f - polyak) * w;
-    Wt[i] = wt;
-    if (mp) { write_split(*mp, i, w, Wsp); write_split(*mp, i, wt, Wtsp); }
-  }
-  // entropy-alpha (reference-intended semantics): one scalar Adam step, unordered wrt
-  // the rest; uses the pre-update mean(logp1) of this step.
-  if (vb == 0 && threadIdx.x == 0 && st->auto_alpha) {
-    st->t_alpha += 1;
-    const double ta = (double)st->t_alpha;
-    const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
-    const float g = -(SCAL[4] + target_entropy);
-    st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * g;
-    st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * g * g;
-    st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
-  }
+  const int64_t stride = (int64_t)vgrid * blockDim.x * 4;
+  for (int64_t i = ((int64_t)vb * blockDim.x + threadIdx.x) * 4; i < P; i += stride)      // P, P_pi are multiples of 4
+    adam4(i, grad4(i, P, S, Gp, ng), gs, i < P_pi ? lr_pi : lr_q, polyak, W, Wt, Mo, Vo, mp, Wsp, Wtsp);
+  if (vb == 0 && threadIdx.x == 0 && st->auto_alpha) alpha_step(st, lr, SCAL[4], target_entropy);
 }
 __global__ void __launch_bounds__(256) k_adam_polyak(StepState* st, int64_t P, int64_t P_pi, int S, const float* __restrict__ Gp,
                                                      float lr, float polyak, float target_entropy, const float* __restrict__ SCAL,
-                                                     float* W, float* Wt, float* Mo, float* Vo) {
+                                                     float* W, float* Wt, float* Mo, float* Vo, NarrowGrad ng) {
   pdl_trigger();
   pdl_wait();
-  d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo);
+  d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo, ng);
 }
 __global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_t P, int64_t P_pi, int S, const float* __restrict__ Gp,
                                                            float lr, float polyak, float target_entropy,
                                                            const float* __restrict__ SCAL, float* W, float* Wt, float* Mo, float* Vo,
-                                                           const __grid_constant__ SplitMap mp, float* Wsp, float* Wtsp) {
+                                                           const __grid_constant__ SplitMap mp, float* Wsp, float* Wtsp,
+                                                           NarrowGrad ng) {
   pdl_trigger();
   pdl_wait();
-  d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo, &mp, Wsp, Wtsp);
+  d_adam_polyak(blockIdx.x, gridDim.x, st, P, P_pi, S, Gp, lr, polyak, target_entropy, SCAL, W, Wt, Mo, Vo, ng, &mp, Wsp, Wtsp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -845,16 +1010,13 @@ struct PeerComm {
 };
 __global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __restrict__ st, int64_t P, int S,
                                                           const float* __restrict__ Gp, const float* __restrict__ SCAL,
-                                                          const __grid_constant__ PeerComm pc, unsigned int* ticket) {
+                                                          const __grid_constant__ PeerComm pc, unsigned int* ticket, NarrowGrad ng) {
   pdl_trigger();
   pdl_wait();
   float* G = pc.buf[pc.rank] + (size_t)(st->t_pi & 1) * pc.Pc;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
-    float g = Gp[i];
-    for (int s = 1; s < S; ++s) g += Gp[(size_t)s * P + i];
-    G[i] = g;
-  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < P; i += stride)
+    *reinterpret_cast<float4*>(G + i) = grad4(i, P, S, Gp, ng);
   if (blockIdx.x == 0 && threadIdx.x == 0) G[P] = SCAL[4];   // mean logp1 of this rank's batch (entropy-alpha gradient)
   // the last CTA to finish publishes "my gradient of step t is complete" to every peer, so the flags travel while
   // the optimiser kernel is being launched
@@ -892,7 +1054,6 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
     } while (v < epoch);
   }
   __syncthreads();
-  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
   const size_t slot = (size_t)(epoch & 1u) * pc.Pc;
@@ -908,121 +1069,12 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
 #pragma unroll
     for (int r = 1; r < 8; ++r)
       if (r < world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
-    const float gv[4] = {g.x * gs, g.y * gs, g.z * gs, g.w * gs};
-    const float4 m4 = *reinterpret_cast<const float4*>(Mo + i), v4 = *reinterpret_cast<const float4*>(Vo + i);
-    const float4 w4 = *reinterpret_cast<const float4*>(W + i), t4 = *reinterpret_cast<const float4*>(Wt + i);
-    const float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w},
-                tv[4] = {t4.x, t4.y, t4.z, t4.w};
-    float mo[4], vo[4], wo[4], to[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      mo[e] = b1 * mv[e] + (1.0f - b1) * gv[e];
-      vo[e] = b2 * vv[e] + (1.0f - b2) * gv[e] * gv[e];
-      wo[e] = wv[e] - (i + e < P_pi ? lr_pi : lr_q) * mo[e] / (sqrtf(vo[e]) + eps);
-      to[e] = polyak * tv[e] + (1.0f - polyak) * wo[e];
-      if (Wsp) { write_split(mp, i + e, wo[e], Wsp); write_split(mp, i + e, to[e], Wtsp); }
-    }
-    *reinterpret_cast<float4*>(Mo + i) = make_float4(mo[0], mo[1], mo[2], mo[3]);
-    *reinterpret_cast<float4*>(Vo + i) = make_float4(vo[0], vo[1], vo[2], vo[3]);
-    *reinterpret_cast<float4*>(W + i) = make_float4(wo[0], wo[1], wo[2], wo[3]);
-    *reinterpret_cast<float4*>(Wt + i) = make_float4(to[0], to[1], to[2], to[3]);
+    adam4(i, g, gs, i < P_pi ? lr_pi : lr_q, polyak, W, Wt, Mo, Vo, Wsp ? &mp : nullptr, Wsp, Wtsp);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && st->auto_alpha) {
     float lp = 0.0f;
     for (int r = 0; r < world; ++r) lp += *reinterpret_cast<volatile const float*>(pc.buf[r] + slot + P);
-    lp *= gs;                                           // mean over the global batch (equal batch per rank)
-    st->t_alpha += 1;
-    const double ta = (double)st->t_alpha;
-    const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
-    const float g = -(lp + target_entropy);
-    st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * g;
-    st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * g * g;
-    st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
-  }
-}
-
-// Experimental one-kernel form of the data-parallel step (DDRL_DP_SLICE=1; correct, but measured slower than the
-// reduce kernel + k_adam_polyak_peer pair at N = 2): the gradient is exchanged SLICE BY SLICE.  CTA b owns 1024 consecutive parameters: it sums its split-K partials into this rank's slot, publishes
-// "slice b of step t is ready" to every peer, waits for slice b of every peer — never for the whole gradient — reads the
-// peers' slices over NVLink and applies Adam + polyak to them.  No CTA depends on another CTA of its own grid, all CTAs
-// of every rank are co-resident (P / 1024 <= 8 CTAs x 148 SMs), so there is no grid-wide barrier and no separate
-// reduce kernel, and the flags of early slices travel while late slices are still being summed.
-__global__ void __launch_bounds__(256) k_reduce_adam_peer(StepState* st, int64_t P, int64_t P_pi, int S,
-                                                          const float* __restrict__ Gp, const float* __restrict__ SCAL,
-                                                          float lr, float polyak, float target_entropy, float* W, float* Wt,
-                                                          float* Mo, float* Vo, const __grid_constant__ SplitMap mp, float* Wsp,
-                                                          float* Wtsp, const __grid_constant__ PeerComm pc, int* err) {
-  pdl_trigger();
-  pdl_wait();
-  const unsigned int epoch = (unsigned int)st->t_pi;
-  const size_t slot = (size_t)(epoch & 1u) * pc.Pc;
-  const int b = blockIdx.x, world = pc.world;
-  const int64_t i = ((int64_t)b * blockDim.x + threadIdx.x) * 4;
-  float* mine = pc.buf[pc.rank] + slot;
-  if (i < P) {
-    float4 g = *reinterpret_cast<const float4*>(Gp + i);
-    for (int s2 = 1; s2 < S; ++s2) {
-      const float4 q = *reinterpret_cast<const float4*>(Gp + (size_t)s2 * P + i);
-      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
-    }
-    *reinterpret_cast<float4*>(mine + i) = g;
-  }
-  if (b == 0 && threadIdx.x == 0) mine[P] = SCAL[4];      // mean logp1 of this rank's batch, travels with slice 0
-  __syncthreads();                                        // the CTA's slice is written (CTA-scope order) ...
-  if (threadIdx.x < world) {
-    __threadfence_system();                               // ... and published by the few signalling threads (cumulative)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc.flags[threadIdx.x] + 8 + (size_t)pc.rank * pc.nslice + b), "r"(epoch)
-                 : "memory");
-    const unsigned int* f = pc.flags[pc.rank] + 8 + (size_t)threadIdx.x * pc.nslice + b;
-    const long long t0 = clock64();
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v < epoch && clock64() - t0 > 20000000000LL) { *err = 1; break; }   // ~10 s: a peer died; do not hang the GPU
-    } while (v < epoch);
-  }
-  __syncthreads();
-  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-  if (i < P) {
-    const float lr_pi = st->lr_pi, lr_q = st->lr_q, gs = st->dyn.grad_scale;
-    float4 q[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < world) q[r] = ld_volatile_f4(pc.buf[r] + slot + i);
-    float4 g = q[0];
-#pragma unroll
-    for (int r = 1; r < 8; ++r)
-      if (r < world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
-    const float gv[4] = {g.x * gs, g.y * gs, g.z * gs, g.w * gs};
-    const float4 m4 = *reinterpret_cast<const float4*>(Mo + i), v4 = *reinterpret_cast<const float4*>(Vo + i);
-    const float4 w4 = *reinterpret_cast<const float4*>(W + i), t4 = *reinterpret_cast<const float4*>(Wt + i);
-    const float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w},
-                tv[4] = {t4.x, t4.y, t4.z, t4.w};
-    float mo[4], vo[4], wo[4], to[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      mo[e] = b1 * mv[e] + (1.0f - b1) * gv[e];
-      vo[e] = b2 * vv[e] + (1.0f - b2) * gv[e] * gv[e];
-      wo[e] = wv[e] - (i + e < P_pi ? lr_pi : lr_q) * mo[e] / (sqrtf(vo[e]) + eps);
-      to[e] = polyak * tv[e] + (1.0f - polyak) * wo[e];
-      if (Wsp) { write_split(mp, i + e, wo[e], Wsp); write_split(mp, i + e, to[e], Wtsp); }
-    }
-    *reinterpret_cast<float4*>(Mo + i) = make_float4(mo[0], mo[1], mo[2], mo[3]);
-    *reinterpret_cast<float4*>(Vo + i) = make_float4(vo[0], vo[1], vo[2], vo[3]);
-    *reinterpret_cast<float4*>(W + i) = make_float4(wo[0], wo[1], wo[2], wo[3]);
-    *reinterpret_cast<float4*>(Wt + i) = make_float4(to[0], to[1], to[2], to[3]);
-  }
-  if (b == 0 && threadIdx.x == 0 && st->auto_alpha) {
-    float lp = 0.0f;
-    for (int r = 0; r < world; ++r) lp += *reinterpret_cast<volatile const float*>(pc.buf[r] + slot + P);
-    lp *= st->dyn.grad_scale;
-    st->t_alpha += 1;
-    const double ta = (double)st->t_alpha;
-    const float lr_a = (float)((double)lr * sqrt(1.0 - pow((double)b2, ta)) / (1.0 - pow((double)b1, ta)));
-    const float ga = -(lp + target_entropy);
-    st->alpha_m = b1 * st->alpha_m + (1.0f - b1) * ga;
-    st->alpha_v = b2 * st->alpha_v + (1.0f - b2) * ga * ga;
-    st->log_alpha -= lr_a * st->alpha_m / (sqrtf(st->alpha_v) + eps);
+    alpha_step(st, lr, lp * gs, target_entropy);          // mean over the global batch (equal batch per rank)
   }
 }
 
@@ -1213,10 +1265,11 @@ struct ddrl_sac {
   int ld1 = 0, ld2 = 0, ldx = 0, ldh = 0;   // ldh: head block row pitch
   long long lo1 = 0, lo2 = 0, lox = 0;
   float* XA[3] = {};                    // [x|a], [x|a1], [x2|a3] split planes
-  bool dp_slice = false;                // DDRL_DP_SLICE=1: slice-wise one-kernel gradient exchange (k_reduce_adam_peer)
   bool fuse_fwd = false;                // narrow inputs: first + second layer of a forward pass in one tcgen05 launch
                                         // (fwd_fused_tc); DDRL_FUSE_L1=0 keeps the two-launch form
   int force_bn = 0;                     // DDRL_TC_BN=64|128 overrides the per-stage tile width choice
+  bool narrow_w1 = false;               // policy W1 gradient (K = D <= 32) by k_wgrad_narrow instead of a tensor-core stage
+  float* Gn = nullptr;                  // its per-slice partial blocks [ceil(maxB / 64)][(D + 1) * h1]
   uint32_t* H1bits[8] = {};             // relu'(H1) of each pass as bit masks [maxB][ldbits] (written by the L1 epilogue)
   int ldbits = 0;
   float *Wsp = nullptr, *Wtsp = nullptr;  // split planes of the main / target weight blocks (SplitMap)
@@ -1637,7 +1690,7 @@ int build_plan_tc(ddrl_sac* h, int B, Plan& pl) {
     skinny(ST_BP, h->H2[a], h2, h2, h->dHD, 2 * A, 2 * A, Gp + h->o_pih, h->ldh);      // d[Whead;bhead] = [H2a|1]^T dHD
     dgrad(ST_BP, h->dZ2a, PI2, h->dZ1a, a);
     wgrad(ST_BP, h1v(a), dz2v(h->dZ2a), PI2);
-    wgrad(ST_BP3, xa(0, D), dz1v(h->dZ1a), PI1);
+    if (!h->narrow_w1) wgrad(ST_BP3, xa(0, D), dz1v(h->dZ1a), PI1);      // else k_wgrad_narrow (enqueue_grads)
   };
   define_stages();
   for (int st = 0; st < ST_COUNT; ++st) {
@@ -1736,6 +1789,14 @@ int launch_pbwd(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   return 0;
 }
 
+NarrowGrad narrow_grad(const ddrl_sac* h, int B) {
+  NarrowGrad ng{};
+  if (h->narrow_w1) {
+    ng.Gn = h->Gn; ng.off = h->o_pi1; ng.size = (long long)(h->D + 1) * h->h1; ng.SN = (B + NW_ROWS - 1) / NW_ROWS;
+  }
+  return ng;
+}
+
 int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
   int rc;
   if ((rc = run_stage(pl, ST_L1, s))) return rc;
@@ -1760,6 +1821,15 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
     if ((rc = run_side(pl, ST_BP, pl.S, side))) return rc;
   }
   if ((rc = run_stage(pl, ST_BP, s, tcm))) return rc;
+  if (tcm && h->narrow_w1) {
+    // d[W1;b1](pi) = [x|1]^T dZ1a on FFMA, per 64-row slice; the side stream only has to join
+    DDRL_CUDA(cudaEventRecord(h->ev[3], side));
+    DDRL_CUDA(launch_pdl(k_wgrad_narrow, dim3((h->h1 + 31) / 32, (pl.B + NW_ROWS - 1) / NW_ROWS), dim3(256), 0, s, pl.B, h->D, h->h1,
+                         (const float*)h->XA[0], h->ldx, h->lox, (const float*)h->dZ1a, h->ld1, h->lo1, h->Gn));
+    DDRL_LAUNCH_CHECK();
+    DDRL_CUDA(cudaStreamWaitEvent(s, h->ev[3], 0));
+    return 0;
+  }
   if (tcm) {
     DDRL_CUDA(cudaEventRecord(h->ev[2], s));
     DDRL_CUDA(cudaStreamWaitEvent(side, h->ev[2], 0));
@@ -1772,20 +1842,21 @@ int enqueue_grads(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
 }
 
 int enqueue_reduce(ddrl_sac* h, const Plan& pl, cudaStream_t s) {
-  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+  const int blocks = (int)std::min<int64_t>((h->P / 4 + 255) / 256, h->sms * 8);
   if (h->pc.world > 1)
     DDRL_CUDA(launch_pdl(k_grad_reduce_comm, dim3(blocks), dim3(256), 0, s, (const StepState*)h->st, h->P, pl.S,
-                         (const float*)h->Gp, (const float*)h->SCAL, h->pc, h->ticket + 1));
+                         (const float*)h->Gp, (const float*)h->SCAL, h->pc, h->ticket + 1, narrow_grad(h, pl.B)));
   else
-    DDRL_CUDA(launch_pdl(k_grad_reduce, dim3(blocks), dim3(256), 0, s, h->P, pl.S, h->Gp, h->G));
+    DDRL_CUDA(launch_pdl(k_grad_reduce, dim3(blocks), dim3(256), 0, s, h->P, pl.S, (const float*)h->Gp, h->G, narrow_grad(h, pl.B)));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
 
-int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s) {
-  int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s, int B = 0) {
+  // B > 0: gradients straight from the backward (split-K partials + the narrow-W1 slices); 0: an already reduced buffer
+  const NarrowGrad ng = B > 0 ? narrow_grad(h, B) : NarrowGrad{};
+  const int blocks = (int)std::min<int64_t>((h->P / 4 + 255) / 256, h->sms * 8);      // four parameters per thread
   if (h->pc.world > 1 && grads == h->G) {     // data-parallel apply: all-reduce fused into the optimiser over peer memory
-    blocks = (int)std::min<int64_t>((h->P / 4 + 255) / 256, h->sms * 8);
     DDRL_CUDA(launch_pdl(k_adam_polyak_peer, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, h->lr, h->polyak,
                          -(float)h->A, h->W, h->Wt, h->Mo, h->Vo, h->smap, h->use_tc ? h->Wsp : nullptr,
                          h->use_tc ? h->Wtsp : nullptr, h->pc, h->d_err));
@@ -1794,10 +1865,10 @@ int enqueue_apply(ddrl_sac* h, int S, const float* grads, cudaStream_t s) {
   }
   if (h->use_tc)
     DDRL_CUDA(launch_pdl(k_adam_polyak_split, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak,
-                         -(float)h->A, h->SCAL, h->W, h->Wt, h->Mo, h->Vo, h->smap, h->Wsp, h->Wtsp));
+                         -(float)h->A, h->SCAL, h->W, h->Wt, h->Mo, h->Vo, h->smap, h->Wsp, h->Wtsp, ng));
   else
     DDRL_CUDA(launch_pdl(k_adam_polyak, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, S, grads, h->lr, h->polyak,
-                         -(float)h->A, h->SCAL, h->W, h->Wt, h->Mo, h->Vo));
+                         -(float)h->A, h->SCAL, h->W, h->Wt, h->Mo, h->Vo, ng));
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1808,27 +1879,16 @@ int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
   int rc = 0;
   if (mode == MODE_FULL) {
     if ((rc = enqueue_grads(h, pl, s))) return rc;
-    return enqueue_apply(h, pl.S, h->Gp, s);
+    return enqueue_apply(h, pl.S, h->Gp, s, pl.B);
   }
   if (mode == MODE_GRADS) {
     if ((rc = enqueue_grads(h, pl, s))) return rc;
     return enqueue_reduce(h, pl, s);
   }
-  if (mode == MODE_DP && !h->dp_slice) {   // fused data-parallel step: gradients -> exchange buffer -> peer all-reduce + optimiser
+  if (mode == MODE_DP) {   // fused data-parallel step: gradients -> exchange buffer -> peer all-reduce + optimiser
     if ((rc = enqueue_grads(h, pl, s))) return rc;
     if ((rc = enqueue_reduce(h, pl, s))) return rc;
     return enqueue_apply(h, 1, h->G, s);
-  }
-  if (mode == MODE_DP) {   // DDRL_DP_SLICE=1: ONE kernel: reduce + slice-wise peer exchange + optimiser.  Bit-identical results;
-                           // measured SLOWER at N = 2 (140 vs 127 us per step), so the two-kernel form stays the default
-    if ((rc = enqueue_grads(h, pl, s))) return rc;
-    const int blocks = (int)((h->P / 4 + 255) / 256);
-    if (blocks > h->pc.nslice) return fail(DDRL_ESTATE, "exchange buffer has %d slice flags, need %d", h->pc.nslice, blocks);
-    DDRL_CUDA(launch_pdl(k_reduce_adam_peer, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, pl.S, (const float*)h->Gp,
-                         (const float*)h->SCAL, h->lr, h->polyak, -(float)h->A, h->W, h->Wt, h->Mo, h->Vo, h->smap,
-                         h->use_tc ? h->Wsp : nullptr, h->use_tc ? h->Wtsp : nullptr, h->pc, h->d_err));
-    DDRL_LAUNCH_CHECK();
-    return 0;
   }
   return enqueue_apply(h, 1, h->G, s);
 }
@@ -1939,8 +1999,8 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     const char* fz = getenv("DDRL_FUSE_L1");
     h->fuse_fwd = h->use_tc && D + A <= tc::BK && h1 % 32 == 0 && h1 <= tc::FZ_MAX_H1 && h2 % 4 == 0 && !(fz && fz[0] == '0');
     if (const char* bz = getenv("DDRL_TC_BN")) { const int v = atoi(bz); if (v == 64 || v == 128) h->force_bn = v; }
-    const char* dz = getenv("DDRL_DP_SLICE");
-    h->dp_slice = dz && dz[0] == '1';
+    const char* nz = getenv("DDRL_NARROW_W1");
+    h->narrow_w1 = h->use_tc && D + 1 <= NW_MAXK && h1 % 4 == 0 && !(nz && nz[0] == '0');
   }
   int rc = 0;
   const size_t P = (size_t)h->P, M = (size_t)max_batch;
@@ -1970,6 +2030,7 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   A_(&h->A1, M * A); A_(&h->A3, M * A); A_(&h->LOGP1, M); A_(&h->LOGP2, M);
   for (int p = 0; p < 3; ++p) { A_(&h->dQ[p], M); A_(&h->dZ2[p], planes * M * h->ld2); A_(&h->dZ1[p], planes * M * h->ld1); }
   A_(&h->dA1, M * A); A_(&h->dHD, M * 2 * A); A_(&h->dZ2a, planes * M * h->ld2); A_(&h->dZ1a, planes * M * h->ld1);
+  if (h->narrow_w1) A_(&h->Gn, (size_t)((max_batch + NW_ROWS - 1) / NW_ROWS) * (size_t)(D + 1) * h1);
   if (h->use_tc) {
     for (int i = 0; i < 3; ++i) A_(&h->XA[i], 2 * M * h->ldx);
     h->ldbits = (h1 + 31) / 32;
@@ -1987,6 +2048,7 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
       o += (long long)Kb[b] * sm.pitch[b];
     }
     sm.plane = o;
+    sm.vec4 = (h1 % 4 == 0 && h2 % 4 == 0) ? 1 : 0;
     A_(&h->Wsp, 2 * (size_t)o); A_(&h->Wtsp, 2 * (size_t)o);
   }
   float* stp = nullptr;
@@ -2245,7 +2307,7 @@ int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* str
     else if (stage == 8) rc = launch_heads(h, *pl, s, PassMap{2, {0, 2, 0}});
     else if (stage == 9) rc = launch_qheads(h, *pl, s);
     else if (stage == 10) rc = launch_pbwd(h, *pl, s);
-    else if (stage == 11) rc = enqueue_apply(h, pl->S, h->Gp, s);
+    else if (stage == 11) rc = enqueue_apply(h, pl->S, h->Gp, s, pl->B);
     else rc = h->use_tc ? run_side(*pl, ST_BQ + (stage - 12), pl->S, s) : 0;
     if (rc) return rc;
   }

@@ -103,10 +103,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));       // round to nearest tf32 (sign, 8 exponent, 10 mantissa bits)
+  // hi = x rounded to tf32 (sign, 8 exponent, 10 mantissa bits), nearest with ties away from zero — what
+  // cvt.rna.tf32.f32 computes, written as two full-rate integer operations (the conversion instruction issues at a
+  // quarter of that rate and was the bottleneck of the converter warps: 512 ns per k-block)
+  const uint32_t u = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   hi = __uint_as_float(u);
-  lo = x - hi;                                               // exact, |lo| <= 2^-12 |x|; the MMA reads its top 19 bits
+  lo = x - hi;                                               // exact, |lo| <= 2^-11 |x|; the MMA reads its top 19 bits
 }
 
 // SWIZZLE_128B shared-memory matrix descriptor (version 1).
@@ -531,6 +533,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
       for (int s = 0; s < FZ_SB; ++s) { bar_init(&fullB[s], 1); bar_init(&emptyB[s], 1); }
       bar_init(bar_in1, 1); bar_init(bar_h1, 1); bar_init(acc_ready, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      // the layer-1 operands are requested right away, under the rest of the CTA's setup (TMEM allocation, barrier)
+      pdl_wait();
+      bar_expect_tx(bar_in1, 2 * TILE_BYTES + 2 * w1_plane);
+      const uint32_t xa = s_addr(in1), w1s = xa + 2 * TILE_BYTES;
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl) tma_load_3d(xa + hl * TILE_BYTES, &P.tx, 0, m0, hl, bar_in1);
+      for (int hl = 0; hl < 2; ++hl)
+        for (int j = 0; j < h1 / 32; ++j) tma_load_3d(w1s + hl * w1_plane + j * 4096, &P.tw1, 32 * j, 0, hl, bar_in1);
     }
     __syncwarp();
   }
@@ -549,12 +559,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
   if (warp == 0) {
     // ---- TMA producer (the whole warp walks the loop; one elected lane issues) ----
     if (elect_one()) {
-      bar_expect_tx(bar_in1, 2 * TILE_BYTES + 2 * w1_plane);
-      const uint32_t xa = s_addr(in1), w1s = xa + 2 * TILE_BYTES;
-#pragma unroll
-      for (int hl = 0; hl < 2; ++hl) tma_load_3d(xa + hl * TILE_BYTES, &P.tx, 0, m0, hl, bar_in1);
-      for (int hl = 0; hl < 2; ++hl)
-        for (int j = 0; j < h1 / 32; ++j) tma_load_3d(w1s + hl * w1_plane + j * 4096, &P.tw1, 32 * j, 0, hl, bar_in1);
       if (P.store_h1) prefetch_tmap(&P.th1);
       prefetch_tmap(&P.tc);
     }
@@ -639,23 +643,32 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
     for (int kb = cg; kb < nkb; kb += 2) {
       const int s = kb % FZ_SA;
       float v[32], lo[32];
+      const bool probe = q == 0 && kb == cg + 2;              // trace: sub-steps of this group's second k-block
+      if (probe) TC_STAMP(24 + 4 * cg);
       tmem_ld32_nowait(trow + (uint32_t)(kb * BK), v);
       if (kb >= FZ_SA) {
         bar_wait(&emptyA[s], ((kb / FZ_SA) - 1) & 1);          // the MMAs that read lo ring stage s have completed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      uint32_t bits = 0;
+      if (probe) TC_STAMP(25 + 4 * cg);
+      const bool mine = (kb % P.tiles_n) == nt;                // this CTA's share of H1 for the backward
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x = v[i] + s_bias1[kb * BK + i];
-        bits |= (x > 0.0f ? 1u : 0u) << i;
-        split_tf32(fmaxf(x, 0.0f), v[i], lo[i]);
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias1 + kb * BK + i);
+        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
       }
+      if (P.bits && mine) {                                    // warp-uniform
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.0f ? 1u : 0u) << i;
+        if (m < M) P.bits[(size_t)m * P.ldbits + kb] = bits;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) split_tf32(fmaxf(v[i], 0.0f), v[i], lo[i]);
       tmem_st32(trow + (uint32_t)(kb * BK), v);
       tmem_st32(trow + (uint32_t)(FZ_LO_COL + s * BK), lo);
-      const bool mine = (kb % P.tiles_n) == nt;                // this CTA's share of H1 for the backward
-      if (P.bits && m < M && mine) P.bits[(size_t)m * P.ldbits + kb] = bits;
+      if (probe) TC_STAMP(26 + 4 * cg);
       if (P.store_h1 && mine) {
         // this warp's previous TMA store has finished reading the staging block (bulk groups are per thread: only
         // the lane that issued it waits)
@@ -666,6 +679,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      if (probe) TC_STAMP(27 + 4 * cg);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (q == 0) TC_STAMP(16 + kb);  // this warp has converted its rows of k-block kb

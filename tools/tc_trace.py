@@ -41,5 +41,10 @@ if full[:, 8:].any():
     for kb in range(8):
         if full[:, 8 + kb].any():
             print(f"    kb {kb}: ready {np.median(full[:, 8 + kb] - ref):7.0f}   converted {np.median(full[:, 16 + kb] - ref):7.0f}")
+if full[:, 24:].any():
+    for cg in (0, 1):
+        c = 24 + 4 * cg
+        print("  converter group %d, second k-block (median ns): ld+wait %.0f, convert+st issue %.0f, wait::st %.0f" % (
+            cg, np.median(full[:, c + 1] - full[:, c]), np.median(full[:, c + 2] - full[:, c + 1]), np.median(full[:, c + 3] - full[:, c + 2])))
 print("  per-CTA durations (median ns): setup %.0f, load latency %.0f, mainloop issue %.0f, MMA drain %.0f, epilogue %.0f, join %.0f" % tuple(
     np.median(t[:, i + 1] - t[:, i]) for i in range(6)))
