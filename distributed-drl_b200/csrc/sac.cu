@@ -893,11 +893,16 @@ struct NarrowGrad {
 };
 __device__ __forceinline__ float4 grad4(int64_t i, int64_t P, int S, const float* __restrict__ Gp, const NarrowGrad& ng) {
   if (ng.SN > 0 && i >= ng.off && i < ng.off + ng.size) {
+    // slices summed in index order; eight loads are in flight at a time (a load -> add loop is one L2 latency per slice)
     const float* p = ng.Gn + (i - ng.off);
-    float4 g = *reinterpret_cast<const float4*>(p);
-    for (int s = 1; s < ng.SN; ++s) {
-      const float4 q = *reinterpret_cast<const float4*>(p + (size_t)s * ng.size);
-      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < ng.SN; s0 += 8) {
+      float4 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        q[u] = s0 + u < ng.SN ? *reinterpret_cast<const float4*>(p + (size_t)(s0 + u) * ng.size) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { g.x += q[u].x; g.y += q[u].y; g.z += q[u].z; g.w += q[u].w; }
     }
     return g;
   }
@@ -908,7 +913,6 @@ __device__ __forceinline__ float4 grad4(int64_t i, int64_t P, int S, const float
   }
   return g;
 }
-
 __global__ void __launch_bounds__(256) k_grad_reduce(int64_t P, int S, const float* __restrict__ Gp, float* G, NarrowGrad ng) {
   pdl_trigger();
   pdl_wait();
@@ -1001,10 +1005,29 @@ __global__ void __launch_bounds__(256) k_adam_polyak_split(StepState* st, int64_
 // Slots alternate, so a slot is rewritten at step t + 2 only after every peer has passed the barrier of step
 // t + 1, i.e. finished reading it: one flag exchange per step is the only synchronisation.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Poll with RELAXED loads and take one acquire fence when the flag is seen: an ld.acquire.sys in the spin loop
+// invalidates the SM's L1 on every iteration, which slowed the kernels running next to a waiting exchange kernel
+// threefold (measured on the narrow-W1 kernel: 5 -> 16 us).  The data behind the flags is read with volatile loads.
+__device__ __forceinline__ void wait_flags(const unsigned int* flags, int world, unsigned int epoch, int* err) {
+  if ((int)threadIdx.x < world) {
+    const unsigned int* f = flags + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned int v;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 20000000000LL) { *err = 1; break; }   // ~10 s: a peer died; do not hang the GPU
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+  }
+  __syncthreads();
+}
 struct PeerComm {
   float* buf[8];            // rank r's communication buffer as mapped in this process
-  unsigned int* flags[8];   // rank r's arrival flags (flags[r][i] = last step rank i has published); after the 8 whole-
-                            // gradient flags come the per-slice flags [8][nslice] of k_reduce_adam_peer
+  unsigned int* flags[8];   // rank r's arrival flags: flags[r][i] = last step whose gradient rank i has published
   int world, rank, nslice;
   long long Pc;             // floats per slot (P + 4, multiple of 4)
 };
@@ -1044,16 +1067,7 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
   pdl_trigger();
   pdl_wait();
   const unsigned int epoch = (unsigned int)st->t_pi;
-  if (threadIdx.x < pc.world) {     // (this rank's own flags were published by k_grad_reduce_comm)
-    const unsigned int* mine = pc.flags[pc.rank] + threadIdx.x;
-    const long long t0 = clock64();
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      if (v < epoch && clock64() - t0 > 20000000000LL) { *err = 1; break; }   // ~10 s: a peer died; do not hang the GPU
-    } while (v < epoch);
-  }
-  __syncthreads();
+  wait_flags(pc.flags[pc.rank], pc.world, epoch, err);     // (this rank's own flag was published by k_grad_reduce_comm)
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
   const size_t slot = (size_t)(epoch & 1u) * pc.Pc;
@@ -1076,6 +1090,73 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
     for (int r = 0; r < world; ++r) lp += *reinterpret_cast<volatile const float*>(pc.buf[r] + slot + P);
     alpha_step(st, lr, lp * gs, target_entropy);          // mean over the global batch (equal batch per rank)
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data-parallel step, default form: the first form above as ONE kernel (the split-K reduction is folded in, which
+// removes a launch from the critical path): every CTA sums its share of the split-K partials (+ the narrow-W1 slices)
+// into this rank's exchange slot; the last CTA to finish publishes the flag on every peer; every CTA waits for all
+// ranks' flags, reads all ranks' slots (128-bit volatile loads over NVLink, all issued before the first add), sums in
+// rank order — every rank computes the same bits, replicas stay bit-identical — and applies Adam + polyak.
+// What was tried instead and measured slower on 2 / 4 / 8 B200 (C2; single-GPU step 96 us):
+//   * reduce-scatter / all-gather inside the kernel (1/N of the data, but a second flag round): every flag round a
+//     kernel has to WAIT for costs ~5 us at 2 ranks and ~10 us at 8 (publish -> NVLink -> poll + the skew between
+//     ranks): 130 vs 124 us per step at N = 8, 130 vs 117 at N = 4;
+//   * the same exchange in a kernel on the side stream under the end of the backward: a kernel that SPINS next to
+//     others slows them (the narrow-W1 kernel went from 5 to 16 us): 133 us at N = 8;
+//   * publishing everything but the policy's first layer early from a non-waiting side-stream kernel and handling that
+//     late block last: each of the small dependent phases costs 3-5 us of latency: 124 vs 112 us at N = 2.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adam_dp(StepState* st, int64_t P, int64_t P_pi, int S, const float* __restrict__ Gp,
+                                                 NarrowGrad ng, const float* __restrict__ SCAL, float lr, float polyak,
+                                                 float target_entropy, float* W, float* Wt, float* Mo, float* Vo,
+                                                 const __grid_constant__ SplitMap mp, float* Wsp, float* Wtsp,
+                                                 const __grid_constant__ PeerComm pc, unsigned int* ticket, int* err,
+                                                 unsigned long long* trace) {
+  __shared__ bool s_last;
+  pdl_trigger();
+  pdl_wait();
+  auto stamp = [&](int i) { if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[i] = tc::gtime(); };
+  stamp(0);
+  const unsigned int epoch = (unsigned int)st->t_pi;
+  const int world = pc.world;
+  const size_t slot = (size_t)(epoch & 1u) * pc.Pc;   // slots alternate: a slot is rewritten at step t + 2, after every
+                                                      // peer's flag of step t + 1, i.e. after it has finished reading step t
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+  float* part = pc.buf[pc.rank] + slot;
+  for (int64_t i = gtid * 4; i < P; i += gthreads * 4) *reinterpret_cast<float4*>(part + i) = grad4(i, P, S, Gp, ng);
+  if (gtid == 0) part[P] = SCAL[4];                 // mean logp1 of this rank's batch (entropy-alpha gradient)
+  stamp(1);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < world) {
+    if (threadIdx.x == 0) *ticket = 0u;
+    st_release_sys(pc.flags[threadIdx.x] + pc.rank, epoch);   // release: cumulative over the CTAs' writes above
+  }
+  wait_flags(pc.flags[pc.rank], world, epoch, err);
+  stamp(2);
+  const float lr_pi = st->lr_pi, lr_q = st->lr_q;
+  const float gs = st->dyn.grad_scale;
+  const SplitMap* mpp = Wsp ? &mp : nullptr;
+  for (int64_t i = gtid * 4; i < P; i += gthreads * 4) {
+    float4 q[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) q[r] = ld_volatile_f4(pc.buf[r] + slot + i);
+    float4 g = q[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+      if (r < world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
+    adam4(i, g, gs, i < P_pi ? lr_pi : lr_q, polyak, W, Wt, Mo, Vo, mpp, Wsp, Wtsp);
+  }
+  if (gtid == 0 && st->auto_alpha) {
+    float lp = 0.0f;
+    for (int r = 0; r < world; ++r) lp += *reinterpret_cast<volatile const float*>(pc.buf[r] + slot + P);
+    alpha_step(st, lr, lp * gs, target_entropy);      // mean over the global batch (equal batch per rank)
+  }
+  stamp(3);
 }
 
 // external (TF variable order: kernel, bias per dense layer; mu head then log_std head) <-> internal
@@ -1268,6 +1349,8 @@ struct ddrl_sac {
   bool fuse_fwd = false;                // narrow inputs: first + second layer of a forward pass in one tcgen05 launch
                                         // (fwd_fused_tc); DDRL_FUSE_L1=0 keeps the two-launch form
   int force_bn = 0;                     // DDRL_TC_BN=64|128 overrides the per-stage tile width choice
+  unsigned long long* dp_trace = nullptr;   // DDRL_DP_TRACE=1: 8 phase time stamps of k_adam_dp's CTA 0 (ddrl_sac_dp_trace)
+  bool dp_v1 = false;                   // DDRL_DP_V1=1: first form of the fused data-parallel step (reduce kernel + full peer read)
   bool narrow_w1 = false;               // policy W1 gradient (K = D <= 32) by k_wgrad_narrow instead of a tensor-core stage
   float* Gn = nullptr;                  // its per-slice partial blocks [ceil(maxB / 64)][(D + 1) * h1]
   uint32_t* H1bits[8] = {};             // relu'(H1) of each pass as bit masks [maxB][ldbits] (written by the L1 epilogue)
@@ -1885,10 +1968,20 @@ int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
     if ((rc = enqueue_grads(h, pl, s))) return rc;
     return enqueue_reduce(h, pl, s);
   }
-  if (mode == MODE_DP) {   // fused data-parallel step: gradients -> exchange buffer -> peer all-reduce + optimiser
+  if (mode == MODE_DP && h->dp_v1) {   // first form: gradients -> exchange buffer -> full peer read + optimiser
     if ((rc = enqueue_grads(h, pl, s))) return rc;
     if ((rc = enqueue_reduce(h, pl, s))) return rc;
     return enqueue_apply(h, 1, h->G, s);
+  }
+  if (mode == MODE_DP) {   // one kernel: split-K reduce + publish + all-peer read over NVLink + optimiser
+    if ((rc = enqueue_grads(h, pl, s))) return rc;
+    const int blocks = (int)std::min<int64_t>((h->P / 4 + 255) / 256, h->sms * 2);      // fully resident: CTAs wait for flags
+    DDRL_CUDA(launch_pdl(k_adam_dp, dim3(blocks), dim3(256), 0, s, h->st, h->P, h->P_pi, pl.S, (const float*)h->Gp,
+                         narrow_grad(h, pl.B), (const float*)h->SCAL, h->lr, h->polyak, -(float)h->A, h->W, h->Wt, h->Mo, h->Vo,
+                         h->smap, h->use_tc ? h->Wsp : nullptr, h->use_tc ? h->Wtsp : nullptr, h->pc, h->ticket + 2, h->d_err,
+                         h->dp_trace));
+    DDRL_LAUNCH_CHECK();
+    return 0;
   }
   return enqueue_apply(h, 1, h->G, s);
 }
@@ -1999,6 +2092,12 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     const char* fz = getenv("DDRL_FUSE_L1");
     h->fuse_fwd = h->use_tc && D + A <= tc::BK && h1 % 32 == 0 && h1 <= tc::FZ_MAX_H1 && h2 % 4 == 0 && !(fz && fz[0] == '0');
     if (const char* bz = getenv("DDRL_TC_BN")) { const int v = atoi(bz); if (v == 64 || v == 128) h->force_bn = v; }
+    if (const char* dt = getenv("DDRL_DP_TRACE")) {
+      if (dt[0] == '1') { float* t = nullptr; dalloc(h, &t, 16); h->dp_trace = reinterpret_cast<unsigned long long*>(t); }
+    }
+    const char* d1 = getenv("DDRL_DP_V1");
+    h->dp_v1 = d1 && d1[0] == '1';
+
     const char* nz = getenv("DDRL_NARROW_W1");
     h->narrow_w1 = h->use_tc && D + 1 <= NW_MAXK && h1 % 4 == 0 && !(nz && nz[0] == '0');
   }
@@ -2020,8 +2119,8 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     A_(&tmp, 2 * 4 * ((size_t)(max_batch + ROW_WARPS - 1) / ROW_WARPS) + 4);
     h->partials = reinterpret_cast<double*>(tmp);
     tmp = nullptr;
-    A_(&tmp, 4);
-    h->ticket = reinterpret_cast<unsigned int*>(tmp);
+    A_(&tmp, 8);
+    h->ticket = reinterpret_cast<unsigned int*>(tmp);   // [0] Q-heads kernel, [1] reduce kernel (first form), [2] k_adam_dp
   }
   A_(&h->X, M * D); A_(&h->X2, M * D); A_(&h->ACT, M * A); A_(&h->R, M); A_(&h->DN, M); A_(&h->NOISE, 3 * M * A + 4);
   for (int p = 0; p < 8; ++p) { A_(&h->H1[p], planes * M * h->ld1); A_(&h->H2[p], M * h2); }
@@ -2217,7 +2316,7 @@ int ddrl_sac_comm_export(ddrl_sac_t h, void* h_handle64) {
   DeviceGuard guard(h->device);
   if (!h->comm) {
     const long long Pc = (h->P + 4 + 3) / 4 * 4;
-    h->pc.nslice = (int)((h->P / 4 + 255) / 256);
+    h->pc.nslice = 1;     // flags: [0, 8) "gradient ready" per source rank
     const size_t bytes = (size_t)2 * Pc * sizeof(float) + (8 + 8 * (size_t)h->pc.nslice) * sizeof(unsigned int);
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);   // its own allocation: CUDA IPC shares whole allocations
@@ -2260,6 +2359,15 @@ int ddrl_sac_comm_attach(ddrl_sac_t h, int world, int rank, const void* h_handle
   for (auto& kv : h->plans)
     for (cudaGraphExec_t* ex : {&kv.second.exec_full, &kv.second.exec_grads, &kv.second.exec_apply, &kv.second.exec_dp})
       if (*ex) { cudaGraphExecDestroy(*ex); *ex = nullptr; }
+  return 0;
+}
+
+int ddrl_sac_dp_trace(ddrl_sac_t h, unsigned long long* h_out8) {
+  if (!h || !h_out8) return fail(DDRL_EINVAL, "ddrl_sac_dp_trace: NULL argument");
+  if (!h->dp_trace) return fail(DDRL_ESTATE, "ddrl_sac_dp_trace: create the handle with DDRL_DP_TRACE=1 in the environment");
+  DeviceGuard guard(h->device);
+  DDRL_CUDA(cudaDeviceSynchronize());
+  DDRL_CUDA(cudaMemcpy(h_out8, h->dp_trace, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -243,6 +243,10 @@ int ddrl_sac_step_dp(ddrl_sac_t sac, const float* d_obs1, const float* d_obs2, c
                      void* stream);
 int ddrl_sac_comm_attach(ddrl_sac_t sac, int world, int rank, const void* h_handles);
 int ddrl_sac_comm_error(ddrl_sac_t sac, int* out_error);
+/* profiling aid (handle created with DDRL_DP_TRACE=1 in the environment): %globaltimer stamps (ns) of the last fused
+ * data-parallel optimiser launch, CTA 0: start, own gradient written, all gradients published, slice scattered, all
+ * slices written, end, 0, 0.  Synchronises the device. */
+int ddrl_sac_dp_trace(ddrl_sac_t sac, unsigned long long* h_out8);
 /* Actor.get_action(o, deterministic) (algos/sac1/actor_learner.py:195-197) for n observations at once:
  * d_out_act[n, A] = act_scale * tanh(mu) (deterministic) or act_scale * tanh(mu + eps * std); eps from
  * d_noise [n, A] or, when NULL, Philox keyed by (seed, counter).  Uses the handle's main policy weights. */

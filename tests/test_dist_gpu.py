@@ -51,13 +51,18 @@ def _worker(rank, world, port, ret, fused=False):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("fused", [False, True], ids=["nccl", "peer-fused"])
-def test_two_gpu_step_equals_single_gpu_on_concatenated_batch(fused):
-    """fused=True: the all-reduce runs inside the optimiser kernel over NVLink peer memory (Learner.connect_peers),
-    no NCCL call on the step path; fused=False: torch.distributed.all_reduce between compute_grads and apply_grads."""
+@pytest.mark.parametrize("mode", ["nccl", "peer-fused", "peer-fused-v1"])
+def test_two_gpu_step_equals_single_gpu_on_concatenated_batch(mode, monkeypatch):
+    """peer-fused: split-K reduce + reduce-scatter / all-gather of the gradient over NVLink peer memory + optimiser in
+    ONE kernel (Learner.connect_peers), no NCCL call on the step path; peer-fused-v1: the first form (reduce kernel,
+    then every rank reads every peer's whole gradient); nccl: torch.distributed.all_reduce between compute_grads and
+    apply_grads."""
     import torch.multiprocessing as mp
     import __graft_entry__
     __graft_entry__.build()
+    fused = mode != "nccl"
+    if mode == "peer-fused-v1":
+        monkeypatch.setenv("DDRL_DP_V1", "1")       # inherited by the spawned ranks
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
