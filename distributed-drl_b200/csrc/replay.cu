@@ -684,12 +684,12 @@ static int launch_gather_bulk(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st)
   const bool narrow = rb->used_f4 <= 32;
   int lanes = 2;
   while (lanes < rb->used_f4) lanes <<= 1;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[narrow]) {
+  {
+    // the attribute is per device / context and the call is cheap: set it on every launch (a process may hold buffers
+    // on several GPUs, from several threads)
     cudaError_t e = narrow ? cudaFuncSetAttribute(rb_gather_bulk<STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
                            : cudaFuncSetAttribute(rb_gather_bulk<STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
-    attr_set[narrow] = true;
   }
   const int64_t ntiles = (a.total + R - 1) / R;
   int per_sm = (int)(220 * 1024 / (smem + 1024));
@@ -775,11 +775,8 @@ static int launch_store(ddrl_rb* rb, const void* obs, const void* act, const voi
       int64_t nb = ((s.n - s.first) + R - 1) / R;
       if (nb < 1) nb = 1;
       if (nb > rb->sms * 6) nb = rb->sms * 6;
-      static bool attr_done = false;
-      if (!attr_done) {
-        DDRL_CUDA(cudaFuncSetAttribute(rb_store_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + 1024));
-        attr_done = true;
-      }
+      // per device / context, cheap: set on every launch
+      DDRL_CUDA(cudaFuncSetAttribute(rb_store_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + 1024));
       rb_store_staged<<<(int)nb, 256, (size_t)2 * R * rb->row_f4 * 16, st>>>(s, R, m1, m2);
       DDRL_LAUNCH_CHECK();
       return 0;

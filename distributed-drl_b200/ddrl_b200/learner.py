@@ -445,6 +445,15 @@ class Actor(object):
         self._calls = 0
         self._obs_stage = {}
 
+    @classmethod
+    def from_learner(cls, learner):
+        """An Actor view of an existing Learner's main policy (example/model.py's Model both trains and acts)."""
+        self = cls.__new__(cls)
+        self._learner, self.opt = learner, learner.opt
+        self.names = [n for n in learner.names if "/pi/" in n]
+        self._calls, self._obs_stage = 0, {}
+        return self
+
     def set_weights(self, variable_names, weights):
         # assign by name; the rollout policy has no target network to re-initialise
         L = self._learner

@@ -7,6 +7,11 @@ actor call are captured by value at call time (numpy arrays are copied, like pic
 object store); remote functions run concurrently (daemon threads — the reference's workers are
 infinite loops); `ray.get` re-raises the task's exception.  There is no process boundary: state
 lives on this process's GPU, which is the point of the one-process-per-GPU design.
+
+Two additions for running the reference's own driver scripts (ddrl_b200.compat.run_reference_script):
+`SUBSTITUTE` maps the NAME of a class decorated with @ray.remote to the class to instantiate instead (the scripts
+define ReplayBuffer / ParameterServer inline; this is how the B200 ones are dropped in without editing them), and
+`stop()` makes every later `.remote()`, `ray.get`, `ray.wait` raise `Stopped` so the scripts' infinite loops end.
 """
 from __future__ import annotations
 
@@ -15,6 +20,37 @@ import threading
 import time
 
 import numpy as np
+
+
+class Stopped(BaseException):
+    """Raised inside tasks and in the driver once stop() has been called (BaseException: the reference's loops have
+    no handler that could swallow it)."""
+
+
+SUBSTITUTE = {}          # class name -> class used instead of the decorated one
+ACTORS = []              # (class name, ActorHandle) of every actor created since reset()
+TASKS = []               # ObjectRef of every remote function call since reset()
+_STOP = threading.Event()
+
+
+def stop():
+    _STOP.set()
+
+
+def stopped():
+    return _STOP.is_set()
+
+
+def reset():
+    _STOP.clear()
+    SUBSTITUTE.clear()
+    del ACTORS[:]
+    del TASKS[:]
+
+
+def _check_stop():
+    if _STOP.is_set():
+        raise Stopped()
 
 
 class ObjectRef:
@@ -44,6 +80,7 @@ class _ActorMethod:
         self._actor, self._name = actor, name
 
     def remote(self, *args, **kwargs):
+        _check_stop()
         ref = ObjectRef()
         args = tuple(_by_value(a) for a in args)
         with self._actor._lock:
@@ -70,7 +107,11 @@ class _RemoteClass:
         self._cls = cls
 
     def remote(self, *args, **kwargs):
-        return ActorHandle(self._cls(*args, **kwargs))
+        _check_stop()
+        cls = SUBSTITUTE.get(self._cls.__name__, self._cls)
+        h = ActorHandle(cls(*args, **kwargs))
+        ACTORS.append((self._cls.__name__, h))
+        return h
 
     def _remote(self, args=(), kwargs=None, **_resources):
         return self.remote(*args, **(kwargs or {}))
@@ -84,17 +125,22 @@ class _RemoteFunction:
         self._fn = fn
 
     def remote(self, *args, **kwargs):
+        _check_stop()
         ref = ObjectRef()
+        ref.name = self._fn.__name__
 
         def run():
             try:
                 ref._set(self._fn(*args, **kwargs))
+            except Stopped:
+                ref._set(None)
             except BaseException as e:  # noqa: BLE001
                 ref._set(exc=e)
 
         t = threading.Thread(target=run, daemon=True, name=f"ray-task-{self._fn.__name__}")
         t.start()
         ref._thread = t
+        TASKS.append(ref)
         return ref
 
     def _remote(self, args=(), kwargs=None, **_resources):
@@ -130,8 +176,11 @@ def put(x):
 def get(ref, timeout=None):
     if isinstance(ref, (list, tuple)):
         return [get(r, timeout) for r in ref]
-    if not ref._ev.wait(timeout):
-        raise TimeoutError("ray_shim.get timed out")
+    t0 = time.time()
+    while not ref._ev.wait(0.05):
+        _check_stop()
+        if timeout is not None and time.time() - t0 >= timeout:
+            raise TimeoutError("ray_shim.get timed out")
     if ref._exc is not None:
         raise ref._exc
     return ref._val
@@ -140,6 +189,7 @@ def get(ref, timeout=None):
 def wait(refs, num_returns=1, timeout=None):
     t0 = time.time()
     while True:
+        _check_stop()
         ready = [r for r in refs if r.ready()]
         if len(ready) >= num_returns or (timeout is not None and time.time() - t0 >= timeout):
             return ready[:num_returns] if len(ready) >= num_returns else ready, [r for r in refs if r not in ready]

@@ -26,6 +26,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def check_indices(idxs, size):
+    """Injected row indices with numpy's fancy-indexing contract (the reference's `buf[idxs]`): negative indices wrap,
+    anything outside [-size, size) raises IndexError — the device kernels dereference what they are given.  Accepts
+    numpy arrays / sequences (checked on the host) and torch tensors (one min/max reduction where they live)."""
+    if isinstance(idxs, torch.Tensor):
+        t = idxs.reshape(-1).to(torch.int64)
+        if t.numel() == 0:
+            return t
+        lo, hi = int(t.min()), int(t.max())
+        if lo < -size or hi >= size:
+            raise IndexError(f"index {hi if hi >= size else lo} is out of bounds for axis 0 with size {size}")
+        return torch.where(t < 0, t + size, t) if lo < 0 else t
+    a = np.asarray(idxs).reshape(-1).astype(np.int64, copy=False)
+    if a.size == 0:
+        return a
+    lo, hi = int(a.min()), int(a.max())
+    if lo < -size or hi >= size:
+        raise IndexError(f"index {hi if hi >= size else lo} is out of bounds for axis 0 with size {size}")
+    return np.where(a < 0, a + size, a) if lo < 0 else a
+
+
 class HostBatch(dict):
     """sample_batch()'s host result: the reference's dict of five numpy arrays.  The arrays are views of ONE
     pinned block (`block`, the layout ddrl_rb_sample_host wrote), which lets Learner.train() feed the batch
@@ -241,6 +262,8 @@ class ReplayBuffer:
             raise ValueError("high <= 0")
         if idxs is None and self.index_source == "numpy":
             idxs = np.random.randint(0, self.size, size=n)
+        elif idxs is not None:
+            idxs = check_indices(idxs, self.max_size)      # `buf[idxs]` indexes the whole array, filled or not
         s = self._stream()
         D, A = self.obs_dim, self.act_dim
         lead = (n_batches, batch_size) if many else (batch_size,)
