@@ -1,35 +1,42 @@
-"""bench.py — the learner-side hot path on N GPUs of one node (BASELINE.json metric / config C2).
+"""bench.py — the learner-side hot path on N GPUs of one node (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3] [--only-primary]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W
 
 One "step" = one iteration of the reference's learner hot loop (algos/sac1/sac1.py:146-148):
     batch = replay_buffer.sample_batch(B);  agent.train(batch)
-on synthetic transitions of the named shape (C2: obs 24, act 4, replay 1e6 rows per GPU, batch 1024,
-256x256 MLPs).  Per rank: one replay shard + one learner; N > 1 adds the NCCL gradient all-reduce.
+on synthetic transitions of the named shape.  The headline (`value`, `ms_per_step`, `e2e`, `roofline`) is config C2
+(BASELINE.json configs[1]: obs 24, act 4, replay 1e6 rows per GPU, batch 1024, 256x256 MLPs); at N = 1 the same JSON
+line also carries `configs: {C1, C2, C3, C4_naive, C4_dedup}` so that every named shape is measured by the same run.
+Per rank: one replay shard + one learner; N > 1 adds the gradient exchange (fused into the optimiser kernel over
+NVLink peer memory; DDRL_DP=nccl: NCCL all-reduce).
 
 Printed JSON line (rank 0):
-  value / unit        whole-job transitions/s consumed by the learners (N * B * K / t), everything
-                      resident in HBM, timed with CUDA events between barriers, max over ranks
+  value / unit        whole-job transitions/s consumed by the learners (N * B * K / t), everything resident in HBM,
+                      timed with CUDA events between barriers, max over ranks
   e2e                 the same metric through the reference-facing API with HOST buffers: per step
-                      sample_batch(B) returned as host numpy arrays -> train(host batch) ->
-                      store_batch(B new rows from pinned host memory) -> read the losses back
-  roofline            the dominant kernel, measured live with CUDA events: the second-layer launch of
-                      gemm_grouped_tc (tcgen05, 3xTF32), algorithmic FLOPs against the measured bf16
-                      tensor peak; traffic from the committed ncu capture
+                      sample_batch(B) returned as host numpy arrays -> train(host batch) -> store_batch(B new rows from
+                      pinned host memory) -> read the losses back
+  roofline            the dominant kernel, measured live with CUDA events: one forward stage of the SAC1 update
+                      (fwd_fused_tc: 4 passes x [first + second layer] in one tcgen05 launch; wide inputs: the
+                      second-layer gemm_grouped_tc launch), algorithmic FLOPs against the measured bf16 tensor peak;
+                      traffic from profiles/ncu_traffic.json (tools/ncu_traffic.py regenerates it from ncu captures)
   roofline_step       the whole SAC1 update by the FLOP model of SURVEY §8d
-  c5                  the same loop with 256 producers' rows stored every step and the parameter-server
-                      broadcast every 300 steps (BASELINE config 5 flavour)
-  roofline_replay     the sample_batch gather kernel alone (sample_many launches): algorithmic bytes
-                      2*row_bytes per transition against the measured HBM copy peak
-  cpu_baseline        the oracle port (numpy ring + torch-CPU float32 SAC1 step) on this box's cores
---impl reference times that same CPU port as the reference arm (the reference is pure Python on
-TensorFlow 1.x / Ray, which cannot be installed; oracle/ is its restatement).
+  roofline_replay     the sample_batch gather kernel alone at the largest launch of the sweep
+  configs             per named shape: value, ms_per_step, e2e, gather / store GB/s and fraction of the HBM peak against
+                      rows per launch, the numpy reference ring on one host thread beside it
+  c5                  the same loop with 256 producers' rows stored every step and the parameter-server broadcast
+                      every 300 steps (BASELINE config 5 flavour)
+  cpu_baseline        the reference's CPU path on this box's cores: numpy ReplayBuffer (the reference's own class when
+                      oracle/_ref was materialised, else its restatement) + the torch-CPU float32 SAC1 step (TensorFlow
+                      1.x cannot be installed): all cores (`value`), one thread (`threads1`), replay alone (`replay_only`)
+--impl reference times that CPU path as the reference arm.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -54,6 +61,8 @@ CONFIGS = {
     "C3": dict(D=376, A=17, replay=10_000_000, B=4096, hidden=(256, 256), act_scale=0.4,
                desc="SAC1 Humanoid-shaped synthetic transitions"),
 }
+# C4: Atari-shaped uint8 84x84x4 frame replay, 1e6 transitions over 8 GPUs = 125 000 per shard, batch 512
+C4 = dict(frame=(84, 84), stack=4, shard=125_000, naive_rows=30_000, B=512)
 
 
 def flops_per_update(D, A, h1, h2, B):
@@ -63,9 +72,14 @@ def flops_per_update(D, A, h1, h2, B):
     return 5 * l_pi + 10 * l_q
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_grouped_tc launch (second-layer stage) from the committed
-# ncu --set full capture (profiles/r01c_gemm_tc_c2_l2_ncu_full_summary.txt); only captured for C2
-NCU_TRAFFIC = {"C2": 12662784}
+def ncu_traffic():
+    """dram bytes read + written per launch of each config's dominant kernel, from the committed table
+    (profiles/ncu_traffic.json, regenerated from ncu --set full captures by tools/ncu_traffic.py)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 def measured_peaks():
@@ -82,6 +96,11 @@ def make_opt(cfg, seed=0):
     space = SimpleNamespace(high=np.full(cfg["A"], cfg["act_scale"], np.float32), shape=(cfg["A"],))
     return SimpleNamespace(obs_dim=cfg["D"], act_dim=cfg["A"], ac_kwargs=dict(hidden_sizes=cfg["hidden"], action_space=space),
                            alpha=0.2, gamma=0.99, lr=1e-3, polyak=0.995, seed=seed, batch_size=cfg["B"])
+
+
+def workload(name, cfg, per_gpu=True):
+    return (f"{name}: {cfg['desc']} (obs {cfg['D']}, act {cfg['A']}, batch {cfg['B']}" + (" per GPU" if per_gpu else "") +
+            f", {cfg['hidden'][0]}x{cfg['hidden'][1]} MLP)")
 
 
 class ClockSampler:
@@ -132,25 +151,70 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
+# reference arm / cpu baseline: the reference's CPU path on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_port_run(cfg, steps, warmup, threads, ring_rows=None, seed=1002):
-    """numpy ring sample_batch + torch-CPU float32 SAC1 step (oracle/), `steps` timed iterations.
-    Returns (seconds per step, description)."""
-    import torch
+def reference_ring_class():
+    """The reference's own numpy ReplayBuffer (algos/sac1/sac1.py:28-63), materialised under oracle/_ref by
+    oracle/materialize_ref.py in the build container — else the restatement oracle/replay_oracle.py."""
+    from oracle import materialize_ref
+    p = materialize_ref.path("ref_replay_sac1.py")
+    if p:
+        ns = {}
+        with open(p) as f:
+            exec(compile(f.read(), p, "exec"), ns)
+        sha = (materialize_ref.manifest() or {}).get("ref_replay_sac1.py", {}).get("sha256", "?")
+        return ns["ReplayBuffer"], "reference", f"the reference's own class, algos/sac1/sac1.py (sha256 {sha[:12]})"
     from oracle.replay_oracle import ReplayRingOracle
-    from oracle.sac1_oracle import SAC1Oracle, init_params
-    torch.set_num_threads(threads)
-    D, A, B = cfg["D"], cfg["A"], cfg["B"]
-    rows = int(ring_rows or min(cfg["replay"], 1_000_000))
+    return (lambda obs_dim, act_dim, size: ReplayRingOracle(obs_dim, act_dim, size)), "port", "oracle/replay_oracle.py restatement"
+
+
+def cpu_ring(cfg, rows, seed=1002):
+    cls, kind, what = reference_ring_class()
+    D, A = cfg["D"], cfg["A"]
     g = np.random.Generator(np.random.PCG64(seed))
-    ring = ReplayRingOracle(D, A, rows)
+    ring = cls(obs_dim=D, act_dim=A, size=rows)
     ring.obs1_buf[:] = g.standard_normal((rows, D), dtype=np.float32)
     ring.obs2_buf[:] = g.standard_normal((rows, D), dtype=np.float32)
     ring.acts_buf[:] = g.uniform(-1, 1, (rows, A)).astype(np.float32)
     ring.rews_buf[:] = g.standard_normal(rows, dtype=np.float32)
     ring.done_buf[:] = (g.random(rows) < 0.01).astype(np.float32)
     ring.size, ring.ptr = rows, 0
+    return ring, kind, what, g
+
+
+def cpu_replay_only(cfg, budget_s=1.5, ring_rows=None):
+    """numpy ring alone, ONE host thread (what a Ray actor process gives the reference): sample_batch(B) and store()."""
+    rows = int(ring_rows or min(cfg["replay"], 1_000_000))
+    ring, kind, what, g = cpu_ring(cfg, rows)
+    B, D, A = cfg["B"], cfg["D"], cfg["A"]
+    np.random.seed(7)
+    for _ in range(3):
+        ring.sample_batch(B)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        ring.sample_batch(B)
+        n += 1
+    ts = (time.perf_counter() - t0) / n
+    o, a, o2 = g.standard_normal(D), g.uniform(-1, 1, A), g.standard_normal(D)
+    m, t0 = 20000, time.perf_counter()
+    for _ in range(m):
+        ring.store(o, a, 0.5, o2, False)
+    tst = (time.perf_counter() - t0) / m
+    row_bytes = 4 * (2 * D + A + 2)
+    return dict(kind=kind, what=what, cores=1, ring_rows=rows, sample_batch_us=ts * 1e6, sample_transitions_per_s=B / ts,
+                sample_gbs=2 * row_bytes * B / ts / 1e9, store_us=tst * 1e6, store_transitions_per_s=1.0 / tst,
+                sample="%d sample_batch(%d) calls, %d store() calls" % (n, B, m))
+
+
+def cpu_port_run(cfg, steps, warmup, threads, ring_rows=None, seed=1002):
+    """reference numpy ring sample_batch + torch-CPU float32 SAC1 step (oracle/), `steps` timed iterations.
+    Returns (seconds per step, description, kind of the replay part)."""
+    import torch
+    from oracle.sac1_oracle import SAC1Oracle, init_params
+    torch.set_num_threads(threads)
+    D, A, B = cfg["D"], cfg["A"], cfg["B"]
+    rows = int(ring_rows or min(cfg["replay"], 1_000_000))
+    ring, kind, what, g = cpu_ring(cfg, rows, seed)
     learner = SAC1Oracle(D, A, hidden=cfg["hidden"], params=init_params(D, A, cfg["hidden"], seed), dtype=torch.float32,
                          act_scale=cfg["act_scale"])
     np.random.seed(seed)
@@ -166,7 +230,22 @@ def cpu_port_run(cfg, steps, warmup, threads, ring_rows=None, seed=1002):
     for _ in range(steps):
         one()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dt, f"{steps} steps of sample_batch({B}) + float32 SAC1 update, ring {rows} rows, {threads} torch threads"
+    return dt, (f"{steps} steps of sample_batch({B}) [{what}] + float32 SAC1 update [torch-CPU port: TensorFlow 1.x is not "
+                f"installable], ring {rows} rows, {threads} torch threads"), kind
+
+
+def cpu_baseline_block(cfg, B):
+    cores = os.cpu_count() or 1
+    probe, _, _ = cpu_port_run(cfg, 2, 1, cores)
+    n = int(max(3, min(200, 10.0 / max(probe, 1e-4))))
+    sec_cpu, sample, kind = cpu_port_run(cfg, n, 1, cores)
+    n1 = int(max(3, min(100, 6.0 / max(probe, 1e-4))))
+    sec_1, sample_1, _ = cpu_port_run(cfg, n1, 1, 1)
+    return dict(value=B / sec_cpu, unit="transitions/s", cores=cores, kind="port", sample=sample, ms_per_step=sec_cpu * 1e3,
+                replay_part=kind,
+                threads1=dict(value=B / sec_1, unit="transitions/s", cores=1, ms_per_step=sec_1 * 1e3, sample=sample_1,
+                              note="the reference pins TensorFlow to one intra/inter-op thread (actor_learner.py:110-111)"),
+                replay_only=cpu_replay_only(cfg))
 
 
 def run_reference(args):
@@ -176,272 +255,379 @@ def run_reference(args):
     cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     steps = max(1, min(args.steps, 60))
-    sec, sample = cpu_port_run(cfg, steps, max(1, min(args.warmup, 5)), cores)
+    sec, sample, kind = cpu_port_run(cfg, steps, max(1, min(args.warmup, 5)), cores)
     value = cfg["B"] / sec
     line = dict(metric="learner-path transitions/s (replay sample_batch -> SAC1 update)", value=value, unit="transitions/s",
                 impl="reference", n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 5), ms_per_step=sec * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 updates_per_s=1.0 / sec,
-                config=dict(workload=f"{args.config}: {cfg['desc']} (obs {cfg['D']}, act {cfg['A']}, batch {cfg['B']}, "
-                                     f"{cfg['hidden'][0]}x{cfg['hidden'][1]} MLP)", replay_rows=min(cfg["replay"], 1_000_000)),
-                cpu_baseline=dict(value=value, unit="transitions/s", cores=cores, kind="port", sample=sample),
+                config=dict(workload=workload(args.config, cfg), replay_rows_per_gpu=min(cfg["replay"], 1_000_000)),
+                cpu_baseline=dict(value=value, unit="transitions/s", cores=cores, kind="port", sample=sample, replay_part=kind,
+                                  replay_only=cpu_replay_only(cfg)),
                 e2e=dict(value=value, unit="transitions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                note="reference = oracle/ CPU port (numpy ring + torch-CPU float32 SAC1 step); the reference's own "
-                     "TensorFlow 1.x / Ray stack is not installable here")
+                note="reference arm = the reference's CPU path: its own numpy ReplayBuffer class (when oracle/_ref was "
+                     "materialised in the build container) + the torch-CPU float32 restatement of the SAC1 step; the "
+                     "reference's TensorFlow 1.x / Ray stack is not installable here")
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if rank == 0:
-        __graft_entry__.build()
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
-    from ddrl_b200 import Learner, ReplayBuffer, _native
-
-    cfg = CONFIGS[args.config]
-    D, A, B, hidden = cfg["D"], cfg["A"], cfg["B"], cfg["hidden"]
-    rows = cfg["replay"]
-    row_bytes = 4 * (2 * D + A + 2)
-    dev = torch.device("cuda", local)
-    peaks = measured_peaks()
-
-    # ---- replay shard of this rank, filled on the device with a counter-based generator ----------
-    rb = ReplayBuffer(D, A, rows, device=local, seed=1000 + 2, rng_stream=rank)
-    gen = torch.Generator(device=dev).manual_seed(1002 + rank)
-    chunk = 250_000
-    for lo in range(0, rows, chunk):
-        n = min(chunk, rows - lo)
-        rb.store_batch(torch.randn((n, D), device=dev, generator=gen), torch.rand((n, A), device=dev, generator=gen) * 2 - 1,
-                       torch.randn(n, device=dev, generator=gen), torch.randn((n, D), device=dev, generator=gen),
-                       (torch.rand(n, device=dev, generator=gen) < 0.01).float())
-    learner = Learner(make_opt(cfg, seed=7), "learner", device=local)   # same seed -> same initial weights on every rank
-    dp_mode = "single"
-    if world > 1:
-        # gradient exchange: fused into the optimiser kernel over NVLink peer memory (default) or NCCL all-reduce
-        dp_mode = "nccl"
-        if os.environ.get("DDRL_DP", "fused") != "nccl" and learner.connect_peers():
-            dp_mode = "peer-fused"
-    torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import __graft_entry__
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        if self.rank == 0:
+            __graft_entry__.build()
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             dist.barrier()
-        torch.cuda.synchronize()
+        from ddrl_b200 import _native
+        self.N = _native
+        self.lib = _native.lib()
+        self.dev = torch.device("cuda", self.local)
+        self.peaks = measured_peaks()
+        self.traffic = ncu_traffic()
 
-    def timed(fn, steps, warmup):
+    # -- plumbing ------------------------------------------------------------------------------------
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        torch = self.torch
         for _ in range(warmup):
             fn()
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        before = _native.launch_count()
+        before = self.N.launch_count()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        launches = _native.launch_count() - before
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        launches = self.N.launch_count() - before
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms / 1e3, launches
 
-    # ---- (1) device-resident hot loop: sample_batch -> train --------------------------------------
-    def step_device():
-        # sample_batch(B) + train(batch) as one native call: the step's first kernel gathers the batch from the ring
-        # (Learner.train_from_buffer; bit-identical to train(rb.sample_batch(B, device=True)), tests/test_sac_gpu.py)
-        learner.train_from_buffer(rb, B)
+    def stream(self):
+        return self.torch.cuda.current_stream(self.local)
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.05)
-    sec, launches = timed(step_device, args.steps, args.warmup)
-    clk = clocks.stop() if rank == 0 else None
-    value = world * B * args.steps / sec
-    ms_per_step = sec / args.steps * 1e3
+    def fill(self, rb, rows, D, A):
+        torch = self.torch
+        gen = torch.Generator(device=self.dev).manual_seed(1002 + self.rank)
+        chunk = 250_000
+        for lo in range(0, rows, chunk):
+            n = min(chunk, rows - lo)
+            rb.store_batch(torch.randn((n, D), device=self.dev, generator=gen), torch.rand((n, A), device=self.dev, generator=gen) * 2 - 1,
+                           torch.randn(n, device=self.dev, generator=gen), torch.randn((n, D), device=self.dev, generator=gen),
+                           (torch.rand(n, device=self.dev, generator=gen) < 0.01).float())
 
-    # ---- (2) end to end through the reference-facing API with host buffers --------------------------
-    g = np.random.Generator(np.random.PCG64(5 + rank))
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    new = [pin(g.standard_normal((B, D), dtype=np.float32)), pin(g.uniform(-1, 1, (B, A)).astype(np.float32)),
-           pin(g.standard_normal(B, dtype=np.float32)), pin(g.standard_normal((B, D), dtype=np.float32)),
-           pin((g.random(B) < 0.01).astype(np.float32))]
-    sink = []
+    def row_stride_bytes(self, rb):
+        rf = C.c_int()
+        self.N.check(self.lib.ddrl_rb_layout(rb.native_handle, None, None, C.byref(rf), None))
+        return 4 * int(rf.value)
 
-    def step_e2e():
-        batch = rb.sample_batch(B)                            # D2H: the reference returns host arrays
-        out = learner.train(batch)                            # H2D: host batch fed like feed_dict
-        rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side (the host
-                                                              # stages them while the GPU runs the update)
-        sink.append(out["scalars"].cpu())                     # D2H: the fetched losses
+    # -- the gather / store kernels alone, against rows per launch --------------------------------------
+    def replay_sweep(self, rb, cfg, sweep=(1, 64, 2048)):
+        torch = self.torch
+        D, A, B, rows = cfg["D"], cfg["A"], cfg["B"], cfg["replay"]
+        row_bytes = 4 * (2 * D + A + 2)
+        nbs = sorted({nb for nb in sweep if nb * B * row_bytes <= 1.6e9} | {1})
+        nmax = max(nbs) * B
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        o = [torch.empty((nmax, D), **f32), torch.empty((nmax, D), **f32), torch.empty((nmax, A), **f32),
+             torch.empty(nmax, **f32), torch.empty(nmax, **f32)]
+        src = [torch.randn((nmax, D), **f32), torch.rand((nmax, A), **f32), torch.randn(nmax, **f32),
+               torch.randn((nmax, D), **f32), torch.zeros(nmax, **f32)]
+        s = self.stream()
+        sp = C.c_void_p(s.cuda_stream)
+        gather, store = [], []
+        for nb in nbs:
+            # `reps` launches back to back between ONE pair of events: the host enqueues ahead of the GPU, so no launch
+            # latency of the host sits inside the timed region
+            reps = max(10, min(300, 3000 // nb))
+            for i in range(3 + reps):
+                if i == 3:
+                    e0 = torch.cuda.Event(enable_timing=True); e0.record(s)
+                self.N.check(self.lib.ddrl_rb_sample(rb.native_handle, B, nb, None, 77, i, self.rank,
+                                                     *[C.c_void_p(t.data_ptr()) for t in o], None, sp))
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(s); torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / 1e3 / reps
+            gbs = 2 * row_bytes * nb * B / t / 1e9
+            gather.append(dict(batches_per_launch=nb, rows_per_launch=nb * B, us_per_launch=t * 1e6, transitions_per_s=nb * B / t,
+                               gbs=gbs, frac=gbs / self.peaks["hbm_gbs"]))
+            m = min(nb * B, rows)
+            a = [t_[:m] for t_ in src]
+            for i in range(3 + reps):
+                if i == 3:
+                    e0 = torch.cuda.Event(enable_timing=True); e0.record(s)
+                self.N.check(self.lib.ddrl_rb_store_batch(rb.native_handle, *[C.c_void_p(t_.data_ptr()) for t_ in a], m, 0, sp))
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(s); torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / 1e3 / reps
+            gbs = 2 * row_bytes * m / t / 1e9
+            store.append(dict(rows_per_launch=m, us_per_launch=t * 1e6, transitions_per_s=m / t, gbs=gbs,
+                              frac=gbs / self.peaks["hbm_gbs"]))
+        del o, src
+        return dict(bytes_per_transition=2 * row_bytes, row_bytes=row_bytes, gather=gather, store=store,
+                    note="algorithmic bytes = 2 x row_bytes per transition (index bytes excluded) over the CUDA-event time "
+                         "of the kernel launches alone, against the measured HBM copy peak")
 
-    e2e_steps = max(5, min(args.steps, 200))
-    sec_e2e, _ = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 10)))
-    e2e_value = world * B * e2e_steps / sec_e2e
-    h2d = 2 * B * row_bytes
-    d2h = B * row_bytes + 16
+    # -- one SAC1 shape: device-resident step, e2e step, replay kernels, dominant kernel -----------------
+    def measure(self, name, steps, warmup, primary):
+        from ddrl_b200 import Learner, ReplayBuffer
+        torch = self.torch
+        cfg = CONFIGS[name]
+        D, A, B, hidden, rows = cfg["D"], cfg["A"], cfg["B"], cfg["hidden"], cfg["replay"]
+        row_bytes = 4 * (2 * D + A + 2)
+        rb = ReplayBuffer(D, A, rows, device=self.local, seed=1000 + 2, rng_stream=self.rank)
+        self.fill(rb, rows, D, A)
+        stride = self.row_stride_bytes(rb)
+        learner = Learner(make_opt(cfg, seed=7), "learner", device=self.local)   # same seed -> same initial weights on every rank
+        dp_mode = "single"
+        if self.world > 1:
+            dp_mode = "nccl"
+            if os.environ.get("DDRL_DP", "fused") != "nccl" and learner.connect_peers():
+                dp_mode = "peer-fused"
+        torch.cuda.synchronize()
 
-    # ---- (2b) config C5 flavour: 256 vectorised rollout producers store concurrently with learning, weights are
-    #      pushed to the actors' parameter-server replica every 300 learner steps (sac1.py:149) by ONE broadcast --
-    from ddrl_b200.dist import DistributedParameterServer
-    producers = 256
-    rows_per_rank = max(1, producers // world)
-    f32d = dict(dtype=torch.float32, device=dev)
-    prod = [torch.randn((rows_per_rank, D), **f32d), torch.rand((rows_per_rank, A), **f32d) * 2 - 1,
-            torch.randn(rows_per_rank, **f32d), torch.randn((rows_per_rank, D), **f32d), torch.zeros(rows_per_rank, **f32d)]
-    keys, values = learner.get_weights()
-    ps = DistributedParameterServer(keys, values, src=0, device=dev)
-    c5_state = dict(i=0)
+        # (1) device-resident hot loop: sample_batch(B) + train(batch) as one native call (the step's first kernel gathers
+        #     the batch from the ring; bit-identical to train(rb.sample_batch(B, device=True)), tests/test_sac_gpu.py)
+        clocks = ClockSampler(self.local)
+        if self.rank == 0 and primary:
+            clocks.start()
+            time.sleep(0.05)
+        sec, launches = self.timed(lambda: learner.train_from_buffer(rb, B), steps, warmup)
+        clk = clocks.stop() if (self.rank == 0 and primary) else None
+        out = dict(workload=workload(name, cfg), value=self.world * B * steps / sec, unit="transitions/s",
+                   ms_per_step=sec / steps * 1e3, updates_per_s=steps / sec, steps=steps, gpu_launches=int(launches),
+                   replay_rows_per_gpu=rows, row_bytes=row_bytes, row_stride_bytes=stride, replay_bytes_per_gpu=rows * stride)
 
-    def step_c5():
-        rb.store_batch(*prod)                                 # this rank's share of the 256 producers, one row each
-        learner.train_from_buffer(rb, B)
-        c5_state["i"] += 1
-        if c5_state["i"] % 300 == 0:
-            ps.push_flat(learner.get_flat_weights())          # device-to-device, then one NCCL broadcast of 0.88 MB
-            ps.sync()
+        # (2) end to end through the reference-facing API with host buffers
+        g = np.random.Generator(np.random.PCG64(5 + self.rank))
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        new = [pin(g.standard_normal((B, D), dtype=np.float32)), pin(g.uniform(-1, 1, (B, A)).astype(np.float32)),
+               pin(g.standard_normal(B, dtype=np.float32)), pin(g.standard_normal((B, D), dtype=np.float32)),
+               pin((g.random(B) < 0.01).astype(np.float32))]
+        sink = []
 
-    c5_steps = max(300, min(args.steps, 600))
-    sec_c5, _ = timed(step_c5, c5_steps, max(3, min(args.warmup, 10)))
+        def step_e2e():
+            batch = rb.sample_batch(B)                            # D2H: the reference returns host arrays
+            res = learner.train(batch)                            # H2D: host batch fed like feed_dict
+            rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side
+            sink.append(res["scalars"].cpu())                     # D2H: the fetched losses
 
-    # ---- (3) the gather kernel alone: sample_many launches, outputs >> L2 ---------------------------
-    n_batches = max(1, min(2048, int(1.5e9 // (B * row_bytes))))
-    outs = rb.sample_many(n_batches, B)                       # allocate once; reuse the same call below
-    del outs
-    torch.cuda.synchronize()
-    reps = 10
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    import ctypes as C
-    f32 = dict(dtype=torch.float32, device=dev)
-    n_rows = n_batches * B
-    o = [torch.empty((n_rows, D), **f32), torch.empty((n_rows, D), **f32), torch.empty((n_rows, A), **f32),
-         torch.empty(n_rows, **f32), torch.empty(n_rows, **f32)]
-    s = torch.cuda.current_stream(local)
-    lib = _native.lib()
-    # `reps` launches back to back between ONE pair of events: the host enqueues ahead of the GPU, so no launch
-    # latency sits inside the timed region (an event pair per call would count the ~30 us the host needs to enqueue)
-    for i in range(3 + reps):
-        if i == 3:
-            ev[0][0].record(s)
-        _native.check(lib.ddrl_rb_sample(rb.native_handle, B, n_batches, None, 77, i, rank,
-                                         *[C.c_void_p(t.data_ptr()) for t in o], None, C.c_void_p(s.cuda_stream)))
-    ev[0][1].record(s)
-    torch.cuda.synchronize()
-    gather_s = ev[0][0].elapsed_time(ev[0][1]) / 1e3 / reps
-    gather_gbs = 2 * row_bytes * n_rows / gather_s / 1e9
-    # batched store of the same volume
-    n_store = min(n_rows, rows)
-    src = [torch.randn((n_store, D), **f32), torch.rand((n_store, A), **f32), torch.randn(n_store, **f32),
-           torch.randn((n_store, D), **f32), torch.zeros(n_store, **f32)]
-    for i in range(3 + reps):
-        if i == 3:
-            ev[1][0].record(s)
-        rb.store_batch(*src)
-    ev[1][1].record(s)
-    torch.cuda.synchronize()
-    store_s = ev[1][0].elapsed_time(ev[1][1]) / 1e3 / reps
-    store_gbs = 2 * row_bytes * n_store / store_s / 1e9
-    del o, src
+        e2e_steps = max(5, min(steps, 200 if primary else 60))
+        sec_e2e, _ = self.timed(step_e2e, e2e_steps, max(3, min(warmup, 10)))
+        out["e2e"] = dict(value=self.world * B * e2e_steps / sec_e2e, unit="transitions/s", h2d_bytes_per_step=2 * B * row_bytes,
+                          d2h_bytes_per_step=B * row_bytes + 16, steps=e2e_steps, ms_per_step=sec_e2e / e2e_steps * 1e3,
+                          path="sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host, B new rows) -> losses.cpu()")
+        extra = {}
+        if primary:
+            # (2b) config C5 flavour: 256 vectorised rollout producers store every step, weights are pushed to the
+            #      actors' parameter-server replica every 300 learner steps (sac1.py:149) by ONE broadcast
+            from ddrl_b200.dist import DistributedParameterServer
+            producers = 256
+            rows_per_rank = max(1, producers // self.world)
+            f32d = dict(dtype=torch.float32, device=self.dev)
+            prod = [torch.randn((rows_per_rank, D), **f32d), torch.rand((rows_per_rank, A), **f32d) * 2 - 1,
+                    torch.randn(rows_per_rank, **f32d), torch.randn((rows_per_rank, D), **f32d), torch.zeros(rows_per_rank, **f32d)]
+            keys, values = learner.get_weights()
+            ps = DistributedParameterServer(keys, values, src=0, device=self.dev)
+            st = dict(i=0)
 
-    # ---- (3b) the dominant kernel alone, live: gemm_grouped_tc of the second-layer stage (5 passes of
-    #      [B, h1] x [h1, h2] from pre-split planes, one launch), CUDA events on the launching stream -------------
-    tc_reps = 100
-    _native.check(lib.ddrl_sac_debug_stage(learner._h, B, 1, 10, C.c_void_p(s.cuda_stream)))
-    torch.cuda.synchronize()
-    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0e.record(s)
-    _native.check(lib.ddrl_sac_debug_stage(learner._h, B, 1, tc_reps, C.c_void_p(s.cuda_stream)))
-    t1e.record(s)
-    torch.cuda.synchronize()
-    tc_launch_s = t0e.elapsed_time(t1e) / 1e3 / tc_reps
-    tc_flops = 5 * 2 * B * hidden[0] * hidden[1]
-    tc_bytes = 5 * (2 * 4 * B * hidden[0] + 2 * 4 * hidden[0] * hidden[1] + 4 * B * hidden[1])   # A hi/lo, W hi/lo, H2 out
+            def step_c5():
+                rb.store_batch(*prod)                             # this rank's share of the 256 producers, one row each
+                learner.train_from_buffer(rb, B)
+                st["i"] += 1
+                if st["i"] % 300 == 0:
+                    ps.push_flat(learner.get_flat_weights())      # device-to-device, then one NCCL broadcast of 0.88 MB
+                    ps.sync()
 
-    if world > 1:
+            c5_steps = max(300, min(steps, 600))
+            sec_c5, _ = self.timed(step_c5, c5_steps, max(3, min(warmup, 10)))
+            extra["c5"] = dict(value=self.world * B * c5_steps / sec_c5, unit="transitions/s", ms_per_step=sec_c5 / c5_steps * 1e3,
+                               steps=c5_steps, producers=producers, stored_rows_per_step=rows_per_rank * self.world,
+                               ps_broadcast_every=300,
+                               note="config 5 flavour of the same loop: every step each rank also stores its share of 256 "
+                                    "producers' transitions; every 300 steps the flat weights are broadcast to the "
+                                    "parameter-server replicas")
+        # (3) the gather / store kernels alone against rows per launch
+        out["replay"] = self.replay_sweep(rb, cfg, sweep=(1, 8, 64, 512, 2048) if primary else (1, 64, 2048))
+        # (4) the dominant kernel alone, live: one forward stage of the update, CUDA events on the launching stream
+        s = self.stream()
+        sp = C.c_void_p(s.cuda_stream)
+        reps = 100
+        self.N.check(self.lib.ddrl_sac_debug_stage(learner._h, B, 1, 10, sp))
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(s)
+        self.N.check(self.lib.ddrl_sac_debug_stage(learner._h, B, 1, reps, sp))
+        t1e.record(s)
+        torch.cuda.synchronize()
+        tc_s = t0e.elapsed_time(t1e) / 1e3 / reps
+        h1, h2 = hidden
+        fused = D + A <= 32 and h1 <= 256 and h1 % 32 == 0 and h2 % 4 == 0
+        if fused:   # passes a, c (policy, K1 = D) and d, e (Q, K1 = D + A): first + second layer
+            flops = 2 * B * (2 * (D * h1 + h1 * h2) + 2 * ((D + A) * h1 + h1 * h2))
+            kname = ("fwd_fused_tc: first + second layer of 4 forward passes in one launch (TMA -> tcgen05.mma kind::tf32 x3, "
+                     "layer-2 A operand from TMEM -> TMA store)")
+        else:       # second-layer launch of the same four passes
+            flops = 2 * B * 4 * h1 * h2
+            kname = "gemm_grouped_tc: second layer of 4 forward passes in one launch (TMA -> tcgen05.mma kind::tf32 x3 -> TMEM -> TMA store)"
+        tr = self.traffic.get(name, {})
+        out["roofline"] = dict(kernel=kname, bound="tensor", achieved=flops / tc_s / 1e12, peak=self.peaks["bf16_tf"], unit="TFLOP/s",
+                               frac=flops / tc_s / 1e12 / self.peaks["bf16_tf"], traffic=tr.get("dram_bytes"),
+                               tensor_pipe_active_pct=tr.get("tensor_pipe_active_pct"), traffic_source=tr.get("source"),
+                               us_per_launch=tc_s * 1e6, flops_per_launch=flops, tensor_pipe_flops_per_launch=3 * flops,
+                               peak_source=self.peaks["source"])
+        fl = flops_per_update(D, A, h1, h2, B)
+        tf = fl * (steps / sec) / 1e12
+        out["roofline_step"] = dict(bound="tensor", achieved=tf, peak=self.peaks["bf16_tf"], unit="TFLOP/s", frac=tf / self.peaks["bf16_tf"],
+                                    traffic=None, flops_per_update=fl, tf32x3_tensor_flops_per_update=3 * fl)
+        extra["clocks"], extra["dp_mode"] = clk, dp_mode
+        del learner, rb
+        torch.cuda.empty_cache()
+        return out, extra
+
+    # -- C4: Atari-shaped uint8 frame replay, one 125 000-transition shard per GPU -----------------------
+    def measure_frames(self):
+        from ddrl_b200.frames import FrameReplayBuffer
+        torch = self.torch
+        fb = C4["frame"][0] * C4["frame"][1]
+        res = {}
+
+        def timeit(fn, iters=30, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters * 1e-3
+
+        rb = FrameReplayBuffer(C4["frame"], C4["stack"], C4["shard"], mode="dedup", seed=1, device=self.local)
+        t_store = []
+        for lo in range(0, C4["shard"], 25_000):
+            fr = torch.randint(0, 256, (25_000, fb), dtype=torch.uint8, device=self.dev)
+            z = torch.zeros(25_000, device=self.dev)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); rb.store_frames(fr, z, z, z); e1.record(); torch.cuda.synchronize()
+            t_store.append(e0.elapsed_time(e1) * 1e-3)
+        gather = []
+        for nb in (C4["B"], 8192):
+            t = timeit(lambda: rb.sample_batch(nb))
+            alg = nb * (5 * fb + 12 + 2 * 4 * fb + 12)      # read 5 frames + scalars, write two stacks + scalars
+            gather.append(dict(batch=nb, us=t * 1e6, transitions_per_s=nb / t, gbs=alg / t / 1e9, frac=alg / t / 1e9 / self.peaks["hbm_gbs"]))
+        st = min(t_store[1:]) if len(t_store) > 1 else t_store[0]
+        res["C4_dedup"] = dict(workload="C4: Atari-shaped uint8 84x84x4 frame replay, frame-deduplicated ring (one frame per transition, "
+                                        "stacks rebuilt from 5 consecutive frames), 125 000-transition shard (1e6 over 8 GPUs), batch 512",
+                               value=gather[0]["transitions_per_s"], unit="transitions/s (sample_batch(512) calls back to back, host API)",
+                               bytes_per_transition=5 * fb + 12 + 2 * 4 * fb + 12, gather=gather,
+                               store=dict(rows_per_launch=25_000, us=st * 1e6, gbs=2 * 25_000 * (fb + 12) / st / 1e9,
+                                          frac=2 * 25_000 * (fb + 12) / st / 1e9 / self.peaks["hbm_gbs"]))
+        del rb
+        torch.cuda.empty_cache()
+        rbn = FrameReplayBuffer(C4["frame"], C4["stack"], C4["naive_rows"], mode="naive", seed=1, device=self.local)
+        for lo in range(0, C4["naive_rows"], 5_000):
+            o = torch.randint(0, 256, (5_000, 4) + C4["frame"], dtype=torch.uint8, device=self.dev)
+            z = torch.zeros(5_000, device=self.dev)
+            rbn.store_batch(o, z, z, o, z)
+        gather = []
+        for nb in (C4["B"], 8192):
+            t = timeit(lambda: rbn.sample_batch(nb))
+            alg = nb * 2 * (2 * 4 * fb + 12)
+            gather.append(dict(batch=nb, us=t * 1e6, transitions_per_s=nb / t, gbs=alg / t / 1e9, frac=alg / t / 1e9 / self.peaks["hbm_gbs"]))
+        res["C4_naive"] = dict(workload="C4: the same frames with obs1 + obs2 stored per transition (56 460-byte rows), 30 000 rows "
+                                        "(1.7 GB, larger than L2), batch 512",
+                               value=gather[0]["transitions_per_s"], unit="transitions/s (sample_batch(512) calls back to back, host API)",
+                               bytes_per_transition=2 * (2 * 4 * fb + 12), gather=gather)
+        del rbn
+        torch.cuda.empty_cache()
+        return res
+
+
+def run_ours(args):
+    b = Bench(args)
+    torch, dist = b.torch, b.dist
+    primary_name = args.config
+    prim, extra = b.measure(primary_name, args.steps, args.warmup, primary=True)
+    configs = {primary_name: prim}
+    if b.world == 1 and not args.only_primary:
+        for name in CONFIGS:
+            if name == primary_name:
+                continue
+            steps = max(50, min(args.steps, 400 if name == "C1" else 150))
+            configs[name], _ = b.measure(name, steps, max(3, min(args.warmup, 20)), primary=False)
+            configs[name]["cpu_replay_1thread"] = cpu_replay_only(CONFIGS[name], budget_s=1.0)
+        configs.update(b.measure_frames())
+    if b.world > 1:
         dist.barrier()
-    if rank != 0:
-        if world > 1:
+    if b.rank != 0:
+        if b.world > 1:
             dist.destroy_process_group()
         return
-
-    fl = flops_per_update(D, A, hidden[0], hidden[1], B)
-    upd_per_s_rank = args.steps / sec
-    tf = fl * upd_per_s_rank / 1e12
+    cfg = CONFIGS[primary_name]
+    world = b.world
+    rep = prim["replay"]["gather"][-1]
+    sto = prim["replay"]["store"][-1]
     line = dict(
-        metric="learner-path transitions/s (replay sample_batch -> SAC1 update)", value=value, unit="transitions/s",
-        n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
+        metric="learner-path transitions/s (replay sample_batch -> SAC1 update)", value=prim["value"], unit="transitions/s",
+        n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=prim["ms_per_step"], higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        updates_per_s=upd_per_s_rank, global_batch=world * B,
-        config=dict(workload=f"{args.config}: {cfg['desc']} (obs {D}, act {A}, batch {B} per GPU, {hidden[0]}x{hidden[1]} MLP)",
-                    replay_rows_per_gpu=rows, replay_bytes_per_gpu=rows * ((row_bytes + 15) // 16 * 16),
+        updates_per_s=prim["updates_per_s"], global_batch=world * cfg["B"],
+        config=dict(workload=workload(primary_name, cfg),
+                    replay_rows_per_gpu=prim["replay_rows_per_gpu"], replay_bytes_per_gpu=prim["replay_bytes_per_gpu"],
+                    row_bytes=prim["row_bytes"], row_stride_bytes=prim["row_stride_bytes"],
                     parallelism=(f"dp{world}: replay sharded per GPU, gradient all-reduce "
-                                 + ("fused into the optimiser kernel over NVLink peer memory (CUDA IPC)" if dp_mode == "peer-fused"
+                                 + ("fused into the optimiser kernel over NVLink peer memory (CUDA IPC)" if extra["dp_mode"] == "peer-fused"
                                     else "by NCCL")) if world > 1 else "single GPU",
                     l2="replay ring larger than L2, rows drawn at random; weights (3.5 MB) are L2-resident by design",
                     noise="Philox on device", index_source="Philox on device"),
-        clocks=clk,
-        e2e=dict(value=e2e_value, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
-                 ms_per_step=sec_e2e / e2e_steps * 1e3,
-                 path="sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host, B new rows) -> losses.cpu()"),
-        c5=dict(value=world * B * c5_steps / sec_c5, unit="transitions/s", ms_per_step=sec_c5 / c5_steps * 1e3, steps=c5_steps,
-                producers=producers, stored_rows_per_step=rows_per_rank * world, ps_broadcast_every=300,
-                note="config 5 flavour of the same loop: every step each rank also stores its share of 256 producers' "
-                     "transitions; every 300 steps the flat weights are broadcast to the parameter-server replicas"),
-        gpu_launches=int(launches),
-        roofline=dict(kernel="gemm_grouped_tc, second-layer stage of the SAC1 update: 5 x [B,256]x[256,256] in one launch "
-                             "(TMA -> tcgen05.mma kind::tf32 x3 -> TMEM -> TMA store)", bound="tensor",
-                      achieved=tc_flops / tc_launch_s / 1e12, peak=peaks["bf16_tf"], unit="TFLOP/s",
-                      frac=tc_flops / tc_launch_s / 1e12 / peaks["bf16_tf"],
-                      traffic=NCU_TRAFFIC.get(args.config), us_per_launch=tc_launch_s * 1e6, flops_per_launch=tc_flops,
-                      algorithmic_bytes_per_launch=tc_bytes, tensor_pipe_flops_per_launch=3 * tc_flops,
-                      peak_source=peaks["source"],
-                      note="algorithmic FLOPs (one product per multiply-add) over the CUDA-event launch time, against the "
-                           "measured bf16 tensor peak; fp32-class accuracy (1e-5 bar) costs three tf32 MMAs per product at half "
-                           "the bf16 rate, so the tensor pipe executes 6x this figure in bf16-equivalents; at these sizes "
-                           "(80 tiles of 128x128x256) the launch is bound by its TMA -> MMA -> epilogue latency chain "
-                           "(ncu: tensor pipe 27% active); traffic = dram bytes read+written per launch from "
-                           "profiles/r01c_gemm_tc_c2_l2_ncu_full_summary.txt (cold-cache replay; operands are L2-resident "
-                           "in the real step)"),
-        roofline_step=dict(kernel="SAC1 update, whole step (gemm_grouped_tc x 7 tcgen05 3xTF32 stages + 3 row-wise kernels + prologue + "
-                             "Adam/polyak; side-stream bias/skinny gradients)", bound="tensor",
-                      achieved=tf, peak=peaks["bf16_tf"], unit="TFLOP/s", frac=tf / peaks["bf16_tf"], traffic=None,
-                      flops_per_update=fl, peak_source=peaks["source"],
-                      tf32x3_tensor_flops_per_update=3 * fl,
-                      note="fp32-class accuracy (1e-5 bar) needs three tf32 MMAs per product, so the tensor pipe executes "
-                           "3x the algorithmic FLOPs at half the bf16 rate; the step is a chain of 12 dependent launches of "
-                           "5-12 us, i.e. latency-bound; fraction is algorithmic FLOPs against the bf16 tensor peak as "
-                           "SURVEY 8(d) defines it"),
-        roofline_replay=dict(kernel="rb_gather_* (sample_batch)", bound="hbm", achieved=gather_gbs, peak=peaks["hbm_gbs"],
-                             unit="GB/s", frac=gather_gbs / peaks["hbm_gbs"], traffic=None,
-                             bytes_per_transition=2 * row_bytes, transitions_per_launch=n_rows,
-                             transitions_per_s=n_rows / gather_s, peak_source=peaks["source"],
-                             store_gbs=store_gbs, store_frac=store_gbs / peaks["hbm_gbs"], store_rows_per_launch=n_store),
+        clocks=extra["clocks"],
+        e2e=prim["e2e"], c5=extra.get("c5"),
+        gpu_launches=prim["gpu_launches"],
+        roofline=dict(prim["roofline"],
+                      note="algorithmic FLOPs (one product per multiply-add) over the CUDA-event launch time, against the measured "
+                           "bf16 tensor peak; fp32-class accuracy (1e-5 bar) costs three tf32 MMAs per product at half the bf16 "
+                           "rate, so the tensor pipe executes 6x this figure in bf16-equivalents; at these sizes (128 tiles of "
+                           "128x64) a launch is bound by its TMA -> MMA -> epilogue latency chain and by the per-instruction floor "
+                           "of the small tcgen05.mma shapes (DESIGN.md §4); traffic = dram bytes read + written per launch "
+                           "(operands are L2-resident in the real step)"),
+        roofline_step=dict(prim["roofline_step"],
+                           kernel="SAC1 update, whole step: prologue + 2 fused forward stages + 2 backward tcgen05 stages + 3 row-wise "
+                                  "kernels + FFMA narrow weight gradient + Adam/polyak; side-stream bias / skinny gradients",
+                           note="the step is a chain of 10 dependent launches of 5-12 us, i.e. latency-bound; fraction is algorithmic "
+                                "FLOPs against the bf16 tensor peak as SURVEY 8(d) defines it"),
+        roofline_replay=dict(kernel="rb_gather_* (sample_batch)", bound="hbm", achieved=rep["gbs"], peak=b.peaks["hbm_gbs"],
+                             unit="GB/s", frac=rep["frac"], traffic=b.traffic.get(primary_name + "_gather", {}).get("dram_bytes"),
+                             bytes_per_transition=prim["replay"]["bytes_per_transition"], transitions_per_launch=rep["rows_per_launch"],
+                             transitions_per_s=rep["transitions_per_s"], peak_source=b.peaks["source"],
+                             store_gbs=sto["gbs"], store_frac=sto["frac"], store_rows_per_launch=sto["rows_per_launch"]),
+        configs=configs if world == 1 else None,
     )
-    # ---- (4) CPU baseline on this box's cores (N = 1 only) -------------------------------------------
+    # ---- CPU baseline on this box's cores (N = 1 only) -------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        probe, _ = cpu_port_run(cfg, 2, 1, cores)
-        n = int(max(3, min(200, 15.0 / max(probe, 1e-4))))
-        sec_cpu, sample = cpu_port_run(cfg, n, 1, cores)
-        line["cpu_baseline"] = dict(value=B / sec_cpu, unit="transitions/s", cores=cores, kind="port", sample=sample,
-                                    ms_per_step=sec_cpu * 1e3)
+        line["cpu_baseline"] = cpu_baseline_block(cfg, cfg["B"])
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -455,6 +641,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-primary", action="store_true", help="N = 1: skip the other named configs (C1, C3, C4)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -45,6 +45,9 @@ struct DeviceGuard {
   int prev = -1;
   bool ok = true;
   explicit DeviceGuard(int dev) {
+    // every entry point opens with a guard: drop a stale per-thread "last error" left by other runtime users of this host
+    // thread (PyTorch probes that fail benignly), so that DDRL_LAUNCH_CHECK only ever reports our own launches
+    (void)cudaGetLastError();
     if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
     if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
   }

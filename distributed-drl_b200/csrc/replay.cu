@@ -343,6 +343,142 @@ __global__ void __launch_bounds__(256) rb_gather_bulk(const GatherArgs a, int R,
   }
 }
 
+// ---- TMA-only gather: no byte of an observation passes through a register -------------------------------------
+// One source run (a packed row, or one frame of the frame ring) is cut into parts of <= 8 KB; a (sampled row, part)
+// unit is ONE bulk copy global -> shared (mbarrier, byte-counted) followed by ONE OR TWO bulk copies shared -> global
+// into the output arrays (the obs1 / obs2 slices of a packed row are contiguous 16-byte aligned pieces of the run; a
+// frame of the deduplicated ring lands in slot f of obs1 and slot f-1 of obs2).  A CTA is one warp that keeps STAGES
+// units in flight; lane 0 issues the bulk copies, the other lanes carry the (A + 2)-float tail / the per-transition
+// scalars.  Tens of CTAs per SM (shared memory is the limit) give ~200 KB in flight per SM without any register
+// staging, which is what a 512-row batch of 56 KB rows needs to cover the chip.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+struct TmaGatherArgs {
+  const char* src;          // ring base
+  int64_t src_stride;       // bytes between ring rows / frames
+  int run_bytes;            // bytes of one source run (packed row: used_f4 * 16; frame ring: frame bytes)
+  int part_bytes, nparts;   // the run is cut into nparts pieces of part_bytes (the last one shorter), multiples of 16
+  int obs_bytes;            // packed row: D * 4;  frame ring: frame bytes
+  int stack;                // frame ring: frames per stacked observation
+  int A;                    // packed row: action floats (tail = A + 2 floats at byte 2 * obs_bytes)
+  int64_t cap, size, base;  // frame ring: capacity, valid frames, ring position of the oldest frame
+  int64_t total;            // transitions to produce
+  const int64_t* idx_in;
+  int idx_mode;
+  uint64_t seed, counter;
+  uint32_t rng_stream;
+  char *o1, *o2;
+  float *oa, *orw, *od;
+  int64_t* oidx;
+  const float *act, *rew, *done;   // frame ring: per-transition scalars [cap]
+};
+
+constexpr int TG_STAGES = 4;
+
+template <bool FRAMES>
+__global__ void __launch_bounds__(32) rb_gather_tma(const TmaGatherArgs a, int slot_stride) {
+  extern __shared__ __align__(128) unsigned char tg_smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tg_smem + (size_t)TG_STAGES * slot_stride);
+  const int lane = threadIdx.x;
+  const int per_b = FRAMES ? (a.stack + 1) * a.nparts : a.nparts;
+  const int64_t nunits = a.total * per_b;
+  const int64_t G = gridDim.x;
+  if (lane == 0) {
+    for (int s = 0; s < TG_STAGES; ++s) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  // unit -> (transition b, frame f, byte offset p0 of the part inside the run, bytes, source ring index)
+  struct Unit { int64_t b, src; int f, p0, bytes; };
+  auto decode = [&](int64_t u) {
+    Unit d;
+    d.b = u / per_b;
+    int r = (int)(u - d.b * per_b);
+    d.f = FRAMES ? r / a.nparts : 0;
+    const int part = r - d.f * a.nparts;
+    d.p0 = part * a.part_bytes;
+    d.bytes = min(a.part_bytes, a.run_bytes - d.p0);
+    if (FRAMES) {
+      // transition i: obs1 = frames i-S+1 .. i, obs2 = i-S+2 .. i+1; Philox draws an AGE u in [0, size - S) counted from the
+      // oldest frame, so no window crosses the write head (ring position = base + S-1 + u)
+      if (a.idx_mode == IDX_INJECT) d.src = a.idx_in[d.b];
+      else {
+        d.src = a.base + (a.stack - 1) + (int64_t)philox_index((uint64_t)d.b, a.seed, a.counter, a.rng_stream, (uint64_t)(a.size - a.stack));
+        if (d.src >= a.cap) d.src -= a.cap;
+      }
+    } else {
+      d.src = a.idx_mode == IDX_INJECT ? a.idx_in[d.b]
+              : (a.idx_mode == IDX_PHILOX ? (int64_t)philox_index((uint64_t)d.b, a.seed, a.counter, a.rng_stream, (uint64_t)a.size) : d.b);
+    }
+    return d;
+  };
+  auto issue = [&](int64_t u, int slot) {   // lane 0 only
+    const Unit d = decode(u);
+    int64_t row = d.src;
+    if (FRAMES) { row = d.src - (a.stack - 1) + d.f; row %= a.cap; if (row < 0) row += a.cap; }
+    mbar_arrive_expect_tx(&bar[slot], (uint32_t)d.bytes);
+    bulk_g2s(tg_smem + (size_t)slot * slot_stride, a.src + row * a.src_stride + d.p0, (uint32_t)d.bytes, &bar[slot]);
+  };
+
+  int64_t u_load = blockIdx.x;
+  for (int s = 0; s < TG_STAGES; ++s, u_load += G)
+    if (u_load < nunits && lane == 0) issue(u_load, s);
+  int k = 0;
+  for (int64_t u = blockIdx.x; u < nunits; u += G, ++k) {
+    const int slot = k % TG_STAGES;
+    mbar_wait(&bar[slot], (uint32_t)((k / TG_STAGES) & 1));
+    const Unit d = decode(u);
+    unsigned char* sm = tg_smem + (size_t)slot * slot_stride;
+    if (FRAMES) {
+      if (d.f == 0 && d.p0 == 0) {
+        if (lane == 0) { a.oa[d.b] = a.act[d.src]; if (a.oidx) a.oidx[d.b] = d.src; }
+        if (lane == 1) a.orw[d.b] = a.rew[d.src];
+        if (lane == 2) a.od[d.b] = a.done[d.src];
+      }
+      if (lane == 0) {
+        const int64_t ob = (int64_t)a.stack * a.obs_bytes;
+        if (d.f < a.stack) bulk_s2g(a.o1 + d.b * ob + (int64_t)d.f * a.obs_bytes + d.p0, sm, (uint32_t)d.bytes);
+        if (d.f >= 1) bulk_s2g(a.o2 + d.b * ob + (int64_t)(d.f - 1) * a.obs_bytes + d.p0, sm, (uint32_t)d.bytes);
+        bulk_commit();
+      }
+    } else {
+      const int OB = a.obs_bytes, p1 = d.p0 + d.bytes;
+      // tail: acts (A), rew, done — floats at byte 2 * OB of the run
+      for (int t = lane; t < a.A + 2; t += 32) {
+        const int pos = 2 * OB + 4 * t;
+        if (pos >= d.p0 && pos < p1) {
+          const float v = *reinterpret_cast<const float*>(sm + (pos - d.p0));
+          if (t < a.A) a.oa[d.b * a.A + t] = v;
+          else if (t == a.A) a.orw[d.b] = v;
+          else a.od[d.b] = v;
+        }
+      }
+      if (lane == 0) {
+        if (a.oidx && d.p0 == 0) a.oidx[d.b] = d.src;
+        int lo = d.p0, hi = min(p1, OB);
+        if (lo < hi) bulk_s2g(a.o1 + d.b * OB + lo, sm + (lo - d.p0), (uint32_t)(hi - lo));
+        lo = max(d.p0, OB); hi = min(p1, 2 * OB);
+        if (lo < hi) bulk_s2g(a.o2 + d.b * OB + (lo - OB), sm + (lo - d.p0), (uint32_t)(hi - lo));
+        bulk_commit();
+      }
+    }
+    __syncwarp();
+    // the slot consumed in the PREVIOUS iteration is free once its stores have read shared memory
+    if (k >= 1 && u_load < nunits) {
+      if (lane == 0) { bulk_wait_read<1>(); issue(u_load, (k - 1) % TG_STAGES); }
+      u_load += G;
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();
+}
+
 // ---- frame-deduplicated stack gather (Atari-shaped replay, BASELINE config C4) ------------------
 // The frame ring holds ONE frame (frame_f4 x 16 bytes) per env step; transition i is
 // obs1 = frames[i-S+1 .. i], obs2 = frames[i-S+2 .. i+1]  (S = stack depth), i.e. S+1 consecutive frames

@@ -33,3 +33,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _fresh_ray_shim():
+    """The in-process Ray stand-in keeps module-level state (stop flag, substitutions, actor / task lists): a test that
+    ran a reference driver to its stop() must not leak that into the next one."""
+    from ddrl_b200 import ray_shim
+    ray_shim.reset()
+    yield
+    ray_shim.reset()
