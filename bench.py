@@ -427,46 +427,118 @@ class Bench:
                pin((g.random(B) < 0.01).astype(np.float32))]
         sink = []
 
+        # the reference's learner loop (algos/sac1/sac1.py:136-151): `batch = cache.q1.get(); agent.train(batch)` — host numpy
+        # batches from the prefetching Cache (here: sample_batch issued `depth` calls ahead on its own CUDA stream, D2H into
+        # pinned blocks), fed back as host arrays; plus this step's B new transitions from the rollout side and the fetched losses
+        from ddrl_b200 import Cache
+        cache = Cache(rb, B, depth=2)
+        cache.start()
+
         def step_e2e():
-            batch = rb.sample_batch(B)                            # D2H: the reference returns host arrays
+            batch = cache.q1.get()                                # D2H: host numpy arrays, prefetched like the reference's Cache
             res = learner.train(batch)                            # H2D: host batch fed like feed_dict
             rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side
             sink.append(res["scalars"].cpu())                     # D2H: the fetched losses
 
+        def step_e2e_blocking():                                  # the same without a prefetcher (example/model.py:92-101)
+            batch = rb.sample_batch(B)
+            res = learner.train(batch)
+            rb.store_batch(*new)
+            sink.append(res["scalars"].cpu())
+
         e2e_steps = max(5, min(steps, 200 if primary else 60))
         sec_e2e, _ = self.timed(step_e2e, e2e_steps, max(3, min(warmup, 10)))
+        cache.end()
+        sec_blk, _ = self.timed(step_e2e_blocking, e2e_steps, max(3, min(warmup, 10)))
         out["e2e"] = dict(value=self.world * B * e2e_steps / sec_e2e, unit="transitions/s", h2d_bytes_per_step=2 * B * row_bytes,
                           d2h_bytes_per_step=B * row_bytes + 16, steps=e2e_steps, ms_per_step=sec_e2e / e2e_steps * 1e3,
-                          path="sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host, B new rows) -> losses.cpu()")
+                          path="Cache(replay_buffer).q1.get() -> numpy batch -> Learner.train(numpy) -> store_batch(host, B new rows) "
+                               "-> losses.cpu(); the Cache keeps 2 sample_batch calls in flight on its own stream (the reference's "
+                               "Cache process keeps a Queue(10) filled)",
+                          blocking=dict(value=self.world * B * e2e_steps / sec_blk, ms_per_step=sec_blk / e2e_steps * 1e3,
+                                        path="sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host) -> losses.cpu(), "
+                                             "no prefetch (example/model.py:92-101 shape)"))
         extra = {}
         if primary:
-            # (2b) config C5 flavour: 256 vectorised rollout producers store every step, weights are pushed to the
-            #      actors' parameter-server replica every 300 learner steps (sac1.py:149) by ONE broadcast
+            # (2b) config C5 flavour: 256 vectorised rollout producers store CONCURRENTLY with the learner — a producer
+            #      thread on its own CUDA stream pushes one host row per producer (pinned host arrays -> H2D -> store kernel)
+            #      for every learner step while the learner's stream runs sample -> update; weights go to the actors'
+            #      parameter-server replica every 300 learner steps (sac1.py:149) by ONE broadcast
+            import threading
             from ddrl_b200.dist import DistributedParameterServer
             producers = 256
             rows_per_rank = max(1, producers // self.world)
-            f32d = dict(dtype=torch.float32, device=self.dev)
-            prod = [torch.randn((rows_per_rank, D), **f32d), torch.rand((rows_per_rank, A), **f32d) * 2 - 1,
-                    torch.randn(rows_per_rank, **f32d), torch.randn((rows_per_rank, D), **f32d), torch.zeros(rows_per_rank, **f32d)]
+            prod = [pin(g.standard_normal((rows_per_rank, D), dtype=np.float32)), pin(g.uniform(-1, 1, (rows_per_rank, A)).astype(np.float32)),
+                    pin(g.standard_normal(rows_per_rank, dtype=np.float32)), pin(g.standard_normal((rows_per_rank, D), dtype=np.float32)),
+                    pin(np.zeros(rows_per_rank, np.float32))]
             keys, values = learner.get_weights()
             ps = DistributedParameterServer(keys, values, src=0, device=self.dev)
-            st = dict(i=0)
+            st = dict(i=0, stored=0, err=None)
+            permits, done_evt, quit_evt = threading.Semaphore(0), threading.Event(), threading.Event()
+            pstream = torch.cuda.Stream(device=self.dev)
+
+            def producer_loop():
+                try:
+                    with torch.cuda.stream(pstream):
+                        while True:
+                            permits.acquire()
+                            if quit_evt.is_set():
+                                return
+                            rb.store_batch(*prod)                 # H2D + store kernel on the producers' stream
+                            st["stored"] += rows_per_rank
+                except BaseException as e:                        # noqa: BLE001
+                    st["err"] = e
+                finally:
+                    done_evt.set()
+
+            th = threading.Thread(target=producer_loop, daemon=True)
+            th.start()
 
             def step_c5():
-                rb.store_batch(*prod)                             # this rank's share of the 256 producers, one row each
+                permits.release()                                 # this step's 256 / N transitions arrive from the rollout side
                 learner.train_from_buffer(rb, B)
                 st["i"] += 1
                 if st["i"] % 300 == 0:
                     ps.push_flat(learner.get_flat_weights())      # device-to-device, then one NCCL broadcast of 0.88 MB
                     ps.sync()
 
+            def drain():                                          # producers have issued everything they were asked for
+                while st["stored"] < st["i"] * rows_per_rank and st["err"] is None:
+                    time.sleep(0)
+                pstream.synchronize()
+
             c5_steps = max(300, min(steps, 600))
-            sec_c5, _ = self.timed(step_c5, c5_steps, max(3, min(warmup, 10)))
+            c5_warm = max(3, min(warmup, 10))
+            for _ in range(c5_warm):
+                step_c5()
+            drain()
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(c5_steps):
+                step_c5()
+            drain()                                               # the timed region ends when learner AND producers are done
+            e1.record()
+            self.barrier()
+            wall = time.perf_counter() - t0
+            sec_c5 = e0.elapsed_time(e1) / 1e3
+            if self.world > 1:
+                t = torch.tensor([sec_c5], device=self.dev)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+                sec_c5 = float(t.item())
+            quit_evt.set(); permits.release(); th.join(5)
+            if st["err"] is not None:
+                raise st["err"]
             extra["c5"] = dict(value=self.world * B * c5_steps / sec_c5, unit="transitions/s", ms_per_step=sec_c5 / c5_steps * 1e3,
                                steps=c5_steps, producers=producers, stored_rows_per_step=rows_per_rank * self.world,
+                               stored_transitions_per_s=self.world * rows_per_rank * c5_steps / sec_c5,
+                               h2d_bytes_per_step=rows_per_rank * row_bytes, wall_ms_per_step=wall / c5_steps * 1e3,
                                ps_broadcast_every=300,
-                               note="config 5 flavour of the same loop: every step each rank also stores its share of 256 "
-                                    "producers' transitions; every 300 steps the flat weights are broadcast to the "
+                               note="config 5 flavour of the same loop, end to end on the producer side: a producer thread per rank "
+                                    "stores its share of 256 producers' transitions from pinned HOST arrays on its own CUDA "
+                                    "stream (reservation serialised by the buffer, kernels ordered by events) while the learner "
+                                    "stream samples and updates; every 300 steps the flat weights are broadcast to the "
                                     "parameter-server replicas")
         # (3) the gather / store kernels alone against rows per launch
         out["replay"] = self.replay_sweep(rb, cfg, sweep=(1, 8, 64, 512, 2048) if primary else (1, 64, 2048))
@@ -566,6 +638,31 @@ class Bench:
         return res
 
 
+def measure_frames_sharded(b):
+    """C4 as configured: 1e6 Atari-shaped transitions sharded over the N GPUs of the node (frame-deduplicated ring, one
+    shard per rank, local sampling — no data-path collective), batch 512 per learner; whole-job transitions/s, max over ranks."""
+    from ddrl_b200.dist import ShardedFrameReplayBuffer
+    torch = b.torch
+    fbytes = C4["frame"][0] * C4["frame"][1]
+    rb = ShardedFrameReplayBuffer(C4["frame"], C4["stack"], 1_000_000, mode="dedup", device=b.local, seed=1)
+    shard = rb.map.cap
+    z = torch.zeros(25_000, device=b.dev)
+    for lo in range(0, shard, 25_000):
+        n = min(25_000, shard - lo)
+        rb.store_frames(torch.randint(0, 256, (n, fbytes), dtype=torch.uint8, device=b.dev), z[:n], z[:n], z[:n])
+    out = {}
+    for nb in (C4["B"], 8192):
+        sec, launches = b.timed(lambda: rb.sample_batch(nb), 50, 5)
+        alg = nb * (5 * fbytes + 12 + 2 * 4 * fbytes + 12)
+        out[str(nb)] = dict(batch_per_gpu=nb, value=b.world * nb * 50 / sec, unit="transitions/s", us_per_call=sec / 50 * 1e6,
+                            gbs_per_gpu=alg * 50 / sec / 1e9, frac=alg * 50 / sec / 1e9 / b.peaks["hbm_gbs"], gpu_launches=int(launches))
+    del rb
+    torch.cuda.empty_cache()
+    return dict(workload="C4: Atari-shaped uint8 84x84x4 frame replay, 1e6 transitions sharded over %d GPU(s) (%d per shard), "
+                         "frame-deduplicated ring, sample_batch through the host API back to back" % (b.world, shard),
+                shard_transitions=shard, bytes_per_transition=5 * fbytes + 12 + 2 * 4 * fbytes + 12, batches=out, scaling="weak")
+
+
 def run_ours(args):
     b = Bench(args)
     torch, dist = b.torch, b.dist
@@ -580,6 +677,7 @@ def run_ours(args):
             configs[name], _ = b.measure(name, steps, max(3, min(args.warmup, 20)), primary=False)
             configs[name]["cpu_replay_1thread"] = cpu_replay_only(CONFIGS[name], budget_s=1.0)
         configs.update(b.measure_frames())
+    c4_sharded = measure_frames_sharded(b) if not args.only_primary else None
     if b.world > 1:
         dist.barrier()
     if b.rank != 0:
@@ -624,6 +722,7 @@ def run_ours(args):
                              transitions_per_s=rep["transitions_per_s"], peak_source=b.peaks["source"],
                              store_gbs=sto["gbs"], store_frac=sto["frac"], store_rows_per_launch=sto["rows_per_launch"]),
         configs=configs if world == 1 else None,
+        c4_sharded=c4_sharded,
     )
     # ---- CPU baseline on this box's cores (N = 1 only) -------------------------------------------
     if world == 1 and not args.no_cpu_baseline:

@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -479,65 +481,67 @@ __global__ void __launch_bounds__(32) rb_gather_tma(const TmaGatherArgs a, int s
   if (lane == 0) bulk_wait_read<0>();
 }
 
-// ---- frame-deduplicated stack gather (Atari-shaped replay, BASELINE config C4) ------------------
-// The frame ring holds ONE frame (frame_f4 x 16 bytes) per env step; transition i is
-// obs1 = frames[i-S+1 .. i], obs2 = frames[i-S+2 .. i+1]  (S = stack depth), i.e. S+1 consecutive frames
-// instead of the 2S a naive obs1/obs2 row stores.  One warp per sampled transition streams the two
-// overlapping windows to the output rows; the S-1 shared frames are read twice but hit L1/L2.
-struct FrameArgs {
-  const float4* frames;     // [cap, frame_f4]
-  const float* act; const float* rew; const float* done;   // [cap] per-transition scalars
-  int frame_f4, stack;
-  int64_t cap, size, total;
-  const int64_t* idx_in;
-  int idx_mode;
-  uint64_t seed, counter;
-  uint32_t rng_stream;
-  float4 *o1, *o2;          // [total, stack*frame_f4]
-  float *oa, *orw, *od;
-  int64_t* oidx;
+// ---- frame-deduplicated ring (Atari-shaped replay, BASELINE config C4) ---------------------------------------
+// The frame ring holds ONE frame per env step; transition i is obs1 = frames[i-S+1 .. i], obs2 = frames[i-S+2 .. i+1]
+// (S = stack depth), i.e. S+1 consecutive frames instead of the 2S a naive obs1/obs2 row stores.  Sampling is
+// rb_gather_tma<true> above: each of the S+1 frames is read ONCE and lands in obs1 and / or obs2.
+// ---- stores of the frame ring and of the N-step sequence ring -------------------------------------------------
+// store_frames: frame i of the input lands in ring slot (ptr0 + i) % cap (one CTA per frame, 128-bit copies, all of a
+// frame's loads of a thread in flight before its stores); the transition scalars of the step that produced frame i
+// belong to the PREVIOUS slot (transition j = stack ending at frame j -> stack ending at j + 1).
+struct FrameStoreArgs {
+  float4* ring; const float4* in;
+  int frame_f4;
+  int64_t cap, ptr0, first, n;      // frames [first, n) of the input are written (first > 0 iff n > cap)
+  const float *act, *rew, *done;    // [n]
+  float *ract, *rrew, *rdone;       // [cap]
 };
+__global__ void __launch_bounds__(256) fb_store_frames(const FrameStoreArgs a) {
+  for (int64_t i = a.first + blockIdx.x; i < a.n; i += gridDim.x) {
+    const int64_t pos = (a.ptr0 + i) % a.cap;
+    const float4* src = a.in + i * a.frame_f4;
+    float4* dst = a.ring + pos * a.frame_f4;
+    for (int c0 = threadIdx.x; c0 < a.frame_f4; c0 += 256 * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (c0 + 256 * k < a.frame_f4) v[k] = ld_nc_f4(src + c0 + 256 * k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (c0 + 256 * k < a.frame_f4) st_f4(dst + c0 + 256 * k, v[k]);
+    }
+    if (threadIdx.x == 0) {
+      const int64_t prev = pos == 0 ? a.cap - 1 : pos - 1;
+      a.ract[prev] = a.act[i]; a.rrew[prev] = a.rew[i]; a.rdone[prev] = a.done[i];
+    }
+  }
+}
 
-__global__ void __launch_bounds__(256, 4) fb_gather_frames(const FrameArgs a) {
+// seg_store: the inverse of rb_gather_segments — nseg dense inputs [n, w_s] -> packed rows [obs | acts | rews | done | 0-pad]
+// at ring slots (ptr0 + i) % cap; one warp per row, every lane assembles whole 16-byte chunks of the packed row.
+struct SegStoreArgs {
+  float4* ring;
+  int row_f4, nseg;
+  int off[8], w[8];
+  const float* in[8];
+  int64_t cap, ptr0, first, n;
+};
+__global__ void __launch_bounds__(256) seg_store_rows(const SegStoreArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int row_f4 = a.stack * a.frame_f4;
-  for (int64_t b = warp; b < a.total; b += nwarps) {
-    int64_t i;
-    if (a.idx_mode == IDX_INJECT) i = a.idx_in[b];
-    else {  // valid stack windows only: i in [stack-1, size-2]
-      const uint64_t span = (uint64_t)(a.size - a.stack);
-      i = (a.stack - 1) + philox_index((uint64_t)b, a.seed, a.counter, a.rng_stream, span);
-    }
-    if (lane == 0) {
-      if (a.oidx) a.oidx[b] = i;
-      a.oa[b] = a.act[i]; a.orw[b] = a.rew[i]; a.od[b] = a.done[i];
-    }
-    const int64_t first = i - (a.stack - 1);          // oldest frame of obs1 (ring position, may wrap)
-    for (int c0 = lane; c0 < 2 * row_f4; c0 += 32 * 4) {
-      float4 v[4];
+  for (int64_t i = a.first + warp; i < a.n; i += nwarps) {
+    float4* dst = a.ring + ((a.ptr0 + i) % a.cap) * a.row_f4;
+    for (int c = lane; c < a.row_f4; c += 32) {
+      float x[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = c0 + 32 * k;
-        if (c < 2 * row_f4) {
-          const int which = c >= row_f4;               // 0: obs1, 1: obs2 (window shifted by one frame)
-          const int cc = c - which * row_f4;
-          const int f = cc / a.frame_f4, within = cc - f * a.frame_f4;
-          int64_t fr = first + f + which;
-          fr %= a.cap; if (fr < 0) fr += a.cap;
-          v[k] = ld_nc_f4(a.frames + fr * a.frame_f4 + within);
-        }
-      }
+      for (int j = 0; j < 4; ++j) {
+        const int f = 4 * c + j;
+        float v = 0.0f;                                   // row padding / gaps between segments
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = c0 + 32 * k;
-        if (c < 2 * row_f4) {
-          const int which = c >= row_f4;
-          const int cc = c - which * row_f4;
-          st_f4((which ? a.o2 : a.o1) + b * row_f4 + cc, v[k]);
-        }
+        for (int s = 0; s < 8; ++s)
+          if (s < a.nseg && f >= a.off[s] && f < a.off[s] + a.w[s]) v = __ldg(a.in[s] + i * a.w[s] + (f - a.off[s]));
+        x[j] = v;
       }
+      st_f4(dst + c, make_float4(x[0], x[1], x[2], x[3]));
     }
   }
 }
@@ -794,17 +798,75 @@ struct Staging {
 
 }  // namespace ddrl
 
+// Cross-stream ordering of ring accesses.  Producers may store from their own threads / streams while the learner samples
+// on another (BASELINE config 5; the reference's fire-and-forget `replay_buffer.store.remote`, algos/sac1/sac1.py:195).
+// The handle serialises the RESERVATION (ptr / size advance under a mutex, so the ring always equals some serial order
+// of the calls, as a Ray actor gives the reference) and orders the KERNELS with events: a sample waits for every earlier
+// store issued on another stream, a store waits for every earlier sample and store issued on another stream.  While
+// every call arrives on one stream (the common case) no event is recorded at all.
+struct StreamDep { cudaStream_t s = nullptr; cudaEvent_t ev = nullptr; bool valid = false; };
+struct StagingSet { ddrl::Staging in, out, idx; };
+
 struct ddrl_rb {
   int device = 0, D = 0, A = 0, row_f = 0, row_f4 = 0, used_f4 = 0, sms = 148, gather_u = 8;
-  int gather_mode = 0;            // 0 auto, 1 always bulk-async, 2 never (DDRL_GATHER_MODE)
+  int gather_mode = 0;            // 0 auto, 1 always bulk-async + register drain, 2 register kernels, 3 TMA-only for wide rows
   int64_t bulk_min_bytes = 4 << 20;
   int64_t cap = 0, ptr = 0, size = 0, steps = 0, sample_times = 0;
   float* ring = nullptr;
-  ddrl::Staging st_in, st_out, st_idx;
+  std::recursive_mutex mu;
+  bool have_home = false, multi = false;
+  cudaStream_t home = nullptr;
+  static constexpr int NDEP = 8;
+  StreamDep writers[NDEP], readers[NDEP];
+  std::map<cudaStream_t, StagingSet> staging;     // device staging of the host-array entry points, per calling stream
   int nshards = 0, my_shard = 0;
   const float4* peer[8] = {};
   bool peer_opened[8] = {};
 };
+
+namespace ddrl {
+using RbLock = std::unique_lock<std::recursive_mutex>;
+
+static int dep_record(StreamDep* tab, cudaStream_t s) {
+  StreamDep* slot = nullptr;
+  for (int i = 0; i < ddrl_rb::NDEP && !slot; ++i) if (tab[i].ev && tab[i].s == s) slot = &tab[i];
+  for (int i = 0; i < ddrl_rb::NDEP && !slot; ++i) if (!tab[i].valid) slot = &tab[i];
+  if (!slot) {                       // more concurrent streams than slots: retire the first one on the host
+    slot = &tab[0];
+    DDRL_CUDA(cudaEventSynchronize(slot->ev));
+  }
+  if (!slot->ev) DDRL_CUDA(cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming));
+  slot->s = s; slot->valid = true;
+  DDRL_CUDA(cudaEventRecord(slot->ev, s));
+  return 0;
+}
+// before launching a ring access on stream s (caller holds rb->mu)
+static int order_before(ddrl_rb* rb, cudaStream_t s, bool is_write) {
+  if (!rb->have_home) { rb->have_home = true; rb->home = s; return 0; }
+  if (!rb->multi) {
+    if (s == rb->home) return 0;
+    rb->multi = true;                // first call from a second stream: everything issued so far on the home stream
+    int rc = dep_record(rb->writers, rb->home);
+    if (rc) return rc;
+  }
+  for (auto& w : rb->writers)
+    if (w.valid) {
+      if (w.s != s) DDRL_CUDA(cudaStreamWaitEvent(s, w.ev, 0));
+      if (is_write) w.valid = false;     // superseded: later accesses order against THIS store
+    }
+  if (is_write)
+    for (auto& r : rb->readers)
+      if (r.valid) {
+        if (r.s != s) DDRL_CUDA(cudaStreamWaitEvent(s, r.ev, 0));
+        r.valid = false;
+      }
+  return 0;
+}
+static int order_after(ddrl_rb* rb, cudaStream_t s, bool is_write) {
+  if (!rb->multi) return 0;
+  return dep_record(is_write ? rb->writers : rb->readers, s);
+}
+}  // namespace ddrl
 
 using namespace ddrl;
 
@@ -838,8 +900,47 @@ static int launch_gather_bulk(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st)
   return 0;
 }
 
+// parts of <= 8 KB (multiples of 16 bytes), slot stride a multiple of 128 bytes, grid = as many one-warp CTAs as the
+// shared memory of the chip holds (each with TG_STAGES slots), capped by the number of units
+static void tma_geometry(int run_bytes, int* part_bytes, int* nparts, int* slot_stride, size_t* smem) {
+  const int np = (run_bytes + 8191) / 8192;
+  const int pb = ((run_bytes + np - 1) / np + 15) / 16 * 16;
+  *nparts = (run_bytes + pb - 1) / pb; *part_bytes = pb;
+  *slot_stride = (pb + 127) / 128 * 128;
+  *smem = (size_t)TG_STAGES * *slot_stride + TG_STAGES * sizeof(uint64_t);
+}
+static int tma_grid(int sms, size_t smem, int64_t units) {
+  int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+  if (per_sm > 24) per_sm = 24;
+  if (per_sm < 1) per_sm = 1;
+  return (int)std::min<int64_t>(units, (int64_t)sms * per_sm);
+}
+static bool tma_gather_ok(const ddrl_rb* rb, const GatherArgs& a) {
+  return a.nshards == 0 && (rb->D & 3) == 0 && ((((uintptr_t)a.o1) | ((uintptr_t)a.o2)) & 15) == 0;
+}
+static int launch_gather_tma(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
+  TmaGatherArgs t{};
+  t.src = reinterpret_cast<const char*>(a.ring);
+  t.src_stride = (int64_t)rb->row_f4 * 16;
+  t.run_bytes = rb->used_f4 * 16;
+  t.obs_bytes = rb->D * 4; t.stack = 1; t.A = rb->A;
+  t.cap = rb->cap; t.size = (int64_t)a.size; t.base = 0; t.total = a.total;
+  t.idx_in = a.idx_in; t.idx_mode = a.idx_mode; t.seed = a.seed; t.counter = a.counter; t.rng_stream = a.rng_stream;
+  t.o1 = reinterpret_cast<char*>(a.o1); t.o2 = reinterpret_cast<char*>(a.o2);
+  t.oa = a.oa; t.orw = a.orw; t.od = a.od; t.oidx = a.oidx;
+  int slot = 0; size_t smem = 0;
+  tma_geometry(t.run_bytes, &t.part_bytes, &t.nparts, &slot, &smem);
+  DDRL_CUDA(cudaFuncSetAttribute(rb_gather_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  rb_gather_tma<false><<<tma_grid(rb->sms, smem, a.total * t.nparts), 32, smem, st>>>(t, slot);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
   if (a.total <= 0) return 0;
+  // rows of >= 32 KB (frame observations) and, on request (DDRL_GATHER_MODE=3), every row wider than 512 B: TMA only
+  if (tma_gather_ok(rb, a) && rb->used_f4 > 32 && (rb->gather_mode == 3 || (rb->gather_mode == 0 && rb->used_f4 >= 2 * XW_SEG)))
+    return launch_gather_tma(rb, a, st);
   // bulk-async pipeline for anything big enough to fill the chip; register path for small launches
   // (measured on B200, C2 rows: 5.5 TB/s bulk vs 4.5 TB/s registers; C3 rows: 5.4 vs 5.65 TB/s, so wide
   // rows keep the one-warp-per-row register kernel)
@@ -990,7 +1091,9 @@ int ddrl_rb_destroy(ddrl_rb_t rb) {
   cudaDeviceSynchronize();
   for (int s = 0; s < 8; ++s) if (rb->peer_opened[s]) cudaIpcCloseMemHandle(const_cast<float4*>(rb->peer[s]));
   if (rb->ring) cudaFree(rb->ring);
-  rb->st_in.release(); rb->st_out.release(); rb->st_idx.release();
+  for (auto& kv : rb->staging) { kv.second.in.release(); kv.second.out.release(); kv.second.idx.release(); }
+  for (auto* tab : {rb->writers, rb->readers})
+    for (int i = 0; i < ddrl_rb::NDEP; ++i) if (tab[i].ev) cudaEventDestroy(tab[i].ev);
   delete rb;
   return 0;
 }
@@ -998,14 +1101,15 @@ int ddrl_rb_destroy(ddrl_rb_t rb) {
 static int store_common(ddrl_rb_t rb, const void* obs, const void* act, const void* rew,
                         const void* nxt, const void* done, int64_t n, int in_dtype,
                         cudaStream_t st) {
-  int rc;
+  int rc = order_before(rb, st, true);
+  if (rc) return rc;
   if (in_dtype == DDRL_F32) rc = launch_store<float>(rb, obs, act, rew, nxt, done, rb->ptr, n, st);
   else rc = launch_store<double>(rb, obs, act, rew, nxt, done, rb->ptr, n, st);
   if (rc) return rc;
   rb->ptr = (rb->ptr + n) % rb->cap;
   rb->size = (rb->size + n < rb->cap) ? rb->size + n : rb->cap;
   rb->steps += n;
-  return 0;
+  return order_after(rb, st, true);
 }
 
 int ddrl_rb_store_batch(ddrl_rb_t rb, const void* d_obs, const void* d_act, const void* d_rew,
@@ -1019,7 +1123,18 @@ int ddrl_rb_store_batch(ddrl_rb_t rb, const void* d_obs, const void* d_act, cons
   if (!d_obs || !d_act || !d_rew || !d_next_obs || !d_done)
     return fail(DDRL_EINVAL, "ddrl_rb_store_batch: NULL input array");
   DeviceGuard guard(rb->device);
+  RbLock lock(rb->mu);
   return store_common(rb, d_obs, d_act, d_rew, d_next_obs, d_done, n, in_dtype, (cudaStream_t)stream);
+}
+
+// device staging of one host store: five 256-byte aligned sub-arrays obs | next_obs | acts | rews | done
+struct HostStoreLayout { size_t b_obs, b_act, b_s, total; };
+static HostStoreLayout host_store_layout(const ddrl_rb* rb, int64_t n, size_t es) {
+  auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
+  HostStoreLayout L;
+  L.b_obs = up256((size_t)n * rb->D * es); L.b_act = up256((size_t)n * rb->A * es); L.b_s = up256((size_t)n * es);
+  L.total = 2 * L.b_obs + L.b_act + 2 * L.b_s;
+  return L;
 }
 
 int ddrl_rb_store_batch_host(ddrl_rb_t rb, const void* h_obs, const void* h_act, const void* h_rew,
@@ -1033,34 +1148,52 @@ int ddrl_rb_store_batch_host(ddrl_rb_t rb, const void* h_obs, const void* h_act,
   if (!h_obs || !h_act || !h_rew || !h_next_obs || !h_done)
     return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host: NULL input array");
   DeviceGuard guard(rb->device);
+  RbLock lock(rb->mu);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t es = in_dtype == DDRL_F32 ? 4 : 8;
-  auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
-  const size_t b_obs = up256((size_t)n * rb->D * es), b_act = up256((size_t)n * rb->A * es),
-               b_s = up256((size_t)n * es);
+  const HostStoreLayout L = host_store_layout(rb, n, es);
   // the staging block may still be read by a previous store on this stream: stream order protects
   // re-use, growth (cudaFree) synchronises the device.
-  int rc = rb->st_in.ensure(2 * b_obs + b_act + 2 * b_s);
+  Staging& st_in = rb->staging[st].in;
+  int rc = st_in.ensure(L.total);
   if (rc) return rc;
-  char* base = (char*)rb->st_in.p;
-  char* d_obs = base;
-  char* d_nxt = d_obs + b_obs;
-  char* d_act = d_nxt + b_obs;
-  char* d_rew = d_act + b_act;
-  char* d_done = d_rew + b_s;
-  const char* hb = (const char*)h_obs;
-  if ((const char*)h_next_obs == hb + b_obs && (const char*)h_act == hb + 2 * b_obs && (const char*)h_rew == hb + 2 * b_obs + b_act &&
-      (const char*)h_done == hb + 2 * b_obs + b_act + b_s) {
-    // the caller staged the five arrays in one block with this very layout (ddrl_b200.ReplayBuffer does): ONE copy
-    DDRL_CUDA(cudaMemcpyAsync(d_obs, h_obs, 2 * b_obs + b_act + b_s + (size_t)n * es, cudaMemcpyHostToDevice, st));
-  } else {
-    DDRL_CUDA(cudaMemcpyAsync(d_obs, h_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
-    DDRL_CUDA(cudaMemcpyAsync(d_nxt, h_next_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
-    DDRL_CUDA(cudaMemcpyAsync(d_act, h_act, (size_t)n * rb->A * es, cudaMemcpyHostToDevice, st));
-    DDRL_CUDA(cudaMemcpyAsync(d_rew, h_rew, (size_t)n * es, cudaMemcpyHostToDevice, st));
-    DDRL_CUDA(cudaMemcpyAsync(d_done, h_done, (size_t)n * es, cudaMemcpyHostToDevice, st));
-  }
+  char* d_obs = (char*)st_in.p;
+  char* d_nxt = d_obs + L.b_obs;
+  char* d_act = d_nxt + L.b_obs;
+  char* d_rew = d_act + L.b_act;
+  char* d_done = d_rew + L.b_s;
+  DDRL_CUDA(cudaMemcpyAsync(d_obs, h_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_nxt, h_next_obs, (size_t)n * rb->D * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_act, h_act, (size_t)n * rb->A * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_rew, h_rew, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  DDRL_CUDA(cudaMemcpyAsync(d_done, h_done, (size_t)n * es, cudaMemcpyHostToDevice, st));
   return store_common(rb, d_obs, d_act, d_rew, d_nxt, d_done, n, in_dtype, st);
+}
+
+int64_t ddrl_rb_store_block_bytes(ddrl_rb_t rb, int64_t n, int in_dtype) {
+  if (!rb || n < 0 || (in_dtype != DDRL_F32 && in_dtype != DDRL_F64)) return -1;
+  return (int64_t)host_store_layout(rb, n, in_dtype == DDRL_F32 ? 4 : 8).total;
+}
+
+int ddrl_rb_store_block_host(ddrl_rb_t rb, const void* h_block, int64_t n, int in_dtype, void* stream) {
+  if (!rb || !h_block) return fail(DDRL_EINVAL, "ddrl_rb_store_block_host: NULL argument");
+  if (n < 0) return fail(DDRL_EINVAL, "ddrl_rb_store_block_host: n=%lld < 0", (long long)n);
+  if (in_dtype != DDRL_F32 && in_dtype != DDRL_F64)
+    return fail(DDRL_EINVAL, "ddrl_rb_store_block_host: in_dtype must be DDRL_F32 or DDRL_F64");
+  if (n == 0) return 0;
+  DeviceGuard guard(rb->device);
+  RbLock lock(rb->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = in_dtype == DDRL_F32 ? 4 : 8;
+  const HostStoreLayout L = host_store_layout(rb, n, es);
+  Staging& st_in = rb->staging[st].in;
+  int rc = st_in.ensure(L.total);
+  if (rc) return rc;
+  char* d_obs = (char*)st_in.p;
+  // the caller's block has the layout of the device staging: ONE copy (up to the last used byte)
+  DDRL_CUDA(cudaMemcpyAsync(d_obs, h_block, 2 * L.b_obs + L.b_act + L.b_s + (size_t)n * es, cudaMemcpyHostToDevice, st));
+  return store_common(rb, d_obs, d_obs + 2 * L.b_obs, d_obs + 2 * L.b_obs + L.b_act, d_obs + L.b_obs,
+                      d_obs + 2 * L.b_obs + L.b_act + L.b_s, n, in_dtype, st);
 }
 
 static int sample_check(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const char* who) {
@@ -1079,6 +1212,8 @@ int ddrl_rb_sample(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t
                    uint64_t seed, uint64_t counter, uint32_t rng_stream, float* d_out_obs1,
                    float* d_out_obs2, float* d_out_acts, float* d_out_rews, float* d_out_done,
                    int64_t* d_out_idx, void* stream) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_sample: NULL handle");
+  RbLock lock(rb->mu);
   int rc = sample_check(rb, batch, n_batches, "ddrl_rb_sample");
   if (rc) return rc;
   const int64_t total = batch * n_batches;
@@ -1094,10 +1229,11 @@ int ddrl_rb_sample(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t
   a.o1 = d_out_obs1; a.o2 = d_out_obs2; a.oa = d_out_acts; a.orw = d_out_rews; a.od = d_out_done;
   a.oidx = d_out_idx;
   a.nshards = 0;
+  if ((rc = order_before(rb, (cudaStream_t)stream, false))) return rc;
   rc = launch_gather(rb, a, (cudaStream_t)stream);
   if (rc) return rc;
   rb->sample_times += n_batches;
-  return 0;
+  return order_after(rb, (cudaStream_t)stream, false);
 }
 
 int64_t ddrl_rb_sample_block_bytes(ddrl_rb_t rb, int64_t n) {
@@ -1110,6 +1246,18 @@ int64_t ddrl_rb_sample_block_bytes(ddrl_rb_t rb, int64_t n) {
 int ddrl_rb_sample_host(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_idx_in,
                         uint64_t seed, uint64_t counter, uint32_t rng_stream, void* h_out_block,
                         int64_t block_bytes, void* stream) {
+  int rc = ddrl_rb_sample_host_async(rb, batch, n_batches, h_idx_in, seed, counter, rng_stream, h_out_block, block_bytes, stream);
+  if (rc) return rc;
+  DeviceGuard guard(rb->device);
+  DDRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int ddrl_rb_sample_host_async(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_idx_in,
+                              uint64_t seed, uint64_t counter, uint32_t rng_stream, void* h_out_block,
+                              int64_t block_bytes, void* stream) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_sample_host: NULL handle");
+  RbLock lock(rb->mu);
   int rc = sample_check(rb, batch, n_batches, "ddrl_rb_sample_host");
   if (rc) return rc;
   const int64_t n = batch * n_batches;
@@ -1120,26 +1268,29 @@ int ddrl_rb_sample_host(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const in
   if (n == 0) return 0;
   DeviceGuard guard(rb->device);
   cudaStream_t st = (cudaStream_t)stream;
-  rc = rb->st_out.ensure((size_t)need);
+  StagingSet& sg = rb->staging[st];
+  rc = sg.out.ensure((size_t)need);
   if (rc) return rc;
   const int64_t* d_idx_in = nullptr;
   if (h_idx_in) {
-    rc = rb->st_idx.ensure((size_t)n * 8);
+    rc = sg.idx.ensure((size_t)n * 8);
     if (rc) return rc;
-    DDRL_CUDA(cudaMemcpyAsync(rb->st_idx.p, h_idx_in, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    d_idx_in = (const int64_t*)rb->st_idx.p;
+    DDRL_CUDA(cudaMemcpyAsync(sg.idx.p, h_idx_in, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    d_idx_in = (const int64_t*)sg.idx.p;
   }
-  float* o1 = (float*)rb->st_out.p;
+  void* stage = sg.out.p;
+  float* o1 = (float*)stage;
   float* o2 = o1 + n * rb->D;
   float* oa = o2 + n * rb->D;
   float* orw = oa + n * rb->A;
   float* od = orw + n;
-  int64_t* oidx = (int64_t*)((char*)rb->st_out.p + (need - n * 8));
+  int64_t* oidx = (int64_t*)((char*)stage + (need - n * 8));
   rc = ddrl_rb_sample(rb, batch, n_batches, d_idx_in, seed, counter, rng_stream, o1, o2, oa, orw, od,
                       oidx, stream);
   if (rc) return rc;
-  DDRL_CUDA(cudaMemcpyAsync(h_out_block, rb->st_out.p, (size_t)need, cudaMemcpyDeviceToHost, st));
-  DDRL_CUDA(cudaStreamSynchronize(st));
+  // the block is complete when `stream` reaches this point: the caller synchronises (ddrl_rb_sample_host does; a
+  // prefetcher records an event and keeps going).  The device staging of this stream is reused by its next call.
+  DDRL_CUDA(cudaMemcpyAsync(h_out_block, stage, (size_t)need, cudaMemcpyDeviceToHost, st));
   return 0;
 }
 
@@ -1201,40 +1352,93 @@ int ddrl_rb_sample_global(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const 
   a.seed = seed; a.counter = counter; a.rng_stream = rng_stream;
   a.o1 = d_out_obs1; a.o2 = d_out_obs2; a.oa = d_out_acts; a.orw = d_out_rews; a.od = d_out_done; a.oidx = d_out_idx;
   DeviceGuard guard(rb->device);
-  int rc = launch_gather(rb, a, (cudaStream_t)stream);
+  RbLock lock(rb->mu);
+  int rc = order_before(rb, (cudaStream_t)stream, false);
+  if (rc) return rc;
+  rc = launch_gather(rb, a, (cudaStream_t)stream);
   if (rc) return rc;
   rb->sample_times += n_batches;
-  return 0;
+  return order_after(rb, (cudaStream_t)stream, false);
 }
 
 int ddrl_fb_sample_stack(int device, const void* d_frames, int64_t frame_bytes, int stack, int64_t capacity, int64_t size,
-                         const float* d_act, const float* d_rew, const float* d_done, int64_t batch,
+                         int64_t oldest, const float* d_act, const float* d_rew, const float* d_done, int64_t batch,
                          const int64_t* d_idx_in, uint64_t seed, uint64_t counter, uint32_t rng_stream,
                          void* d_out_obs1, void* d_out_obs2, float* d_out_acts, float* d_out_rews, float* d_out_done,
                          int64_t* d_out_idx, void* stream) {
   if (!d_frames || !d_act || !d_rew || !d_done || !d_out_obs1 || !d_out_obs2 || !d_out_acts || !d_out_rews || !d_out_done)
     return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: NULL array");
   if (frame_bytes < 16 || frame_bytes % 16 != 0) return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: frame_bytes must be a multiple of 16");
-  if (stack < 1 || capacity < stack + 1 || size > capacity || batch < 0)
-    return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: bad stack / capacity / size / batch");
+  if (stack < 1 || capacity < stack + 1 || size > capacity || batch < 0 || oldest < 0 || oldest >= capacity)
+    return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: bad stack / capacity / size / oldest / batch");
   if (size < stack + 1 && batch > 0)
     return fail(DDRL_EEMPTY, "ddrl_fb_sample_stack: fewer than stack+1 frames stored");
+  if (((((uintptr_t)d_frames) | ((uintptr_t)d_out_obs1) | ((uintptr_t)d_out_obs2)) & 15) != 0)
+    return fail(DDRL_EINVAL, "ddrl_fb_sample_stack: frame ring and stacked outputs must be 16-byte aligned");
   if (batch == 0) return 0;
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DDRL_ECUDA, "ddrl_fb_sample_stack: cannot select device %d", device);
-  FrameArgs a;
-  a.frames = reinterpret_cast<const float4*>(d_frames);
-  a.act = d_act; a.rew = d_rew; a.done = d_done;
-  a.frame_f4 = (int)(frame_bytes / 16); a.stack = stack;
-  a.cap = capacity; a.size = size; a.total = batch;
-  a.idx_in = d_idx_in; a.idx_mode = d_idx_in ? IDX_INJECT : IDX_PHILOX;
-  a.seed = seed; a.counter = counter; a.rng_stream = rng_stream;
-  a.o1 = reinterpret_cast<float4*>(d_out_obs1); a.o2 = reinterpret_cast<float4*>(d_out_obs2);
-  a.oa = d_out_acts; a.orw = d_out_rews; a.od = d_out_done; a.oidx = d_out_idx;
-  const int sms = sm_count(device);
-  int64_t blocks = (batch + 7) / 8;
-  if (blocks > sms * 8) blocks = sms * 8;
-  fb_gather_frames<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  TmaGatherArgs t{};
+  t.src = reinterpret_cast<const char*>(d_frames);
+  t.src_stride = frame_bytes; t.run_bytes = (int)frame_bytes; t.obs_bytes = (int)frame_bytes; t.stack = stack; t.A = 0;
+  t.cap = capacity; t.size = size; t.base = oldest; t.total = batch;
+  t.idx_in = d_idx_in; t.idx_mode = d_idx_in ? IDX_INJECT : IDX_PHILOX;
+  t.seed = seed; t.counter = counter; t.rng_stream = rng_stream;
+  t.o1 = reinterpret_cast<char*>(d_out_obs1); t.o2 = reinterpret_cast<char*>(d_out_obs2);
+  t.oa = d_out_acts; t.orw = d_out_rews; t.od = d_out_done; t.oidx = d_out_idx;
+  t.act = d_act; t.rew = d_rew; t.done = d_done;
+  int slot = 0; size_t smem = 0;
+  tma_geometry(t.run_bytes, &t.part_bytes, &t.nparts, &slot, &smem);
+  DDRL_CUDA(cudaFuncSetAttribute(rb_gather_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  rb_gather_tma<true><<<tma_grid(sm_count(device), smem, batch * (stack + 1) * t.nparts), 32, smem, (cudaStream_t)stream>>>(t, slot);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ddrl_fb_store_frames(int device, void* d_frames, int64_t frame_bytes, int64_t capacity, int64_t ptr, float* d_act,
+                         float* d_rew, float* d_done, const void* d_in_frames, const float* d_in_act, const float* d_in_rew,
+                         const float* d_in_done, int64_t n, void* stream) {
+  if (!d_frames || !d_act || !d_rew || !d_done || !d_in_frames || !d_in_act || !d_in_rew || !d_in_done)
+    return fail(DDRL_EINVAL, "ddrl_fb_store_frames: NULL array");
+  if (frame_bytes < 16 || frame_bytes % 16 != 0 || ((((uintptr_t)d_frames) | ((uintptr_t)d_in_frames)) & 15) != 0)
+    return fail(DDRL_EINVAL, "ddrl_fb_store_frames: frames must be 16-byte aligned multiples of 16 bytes");
+  if (capacity < 1 || ptr < 0 || ptr >= capacity || n < 0) return fail(DDRL_EINVAL, "ddrl_fb_store_frames: bad capacity / ptr / n");
+  if (n == 0) return 0;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DDRL_ECUDA, "ddrl_fb_store_frames: cannot select device %d", device);
+  FrameStoreArgs a;
+  a.ring = reinterpret_cast<float4*>(d_frames); a.in = reinterpret_cast<const float4*>(d_in_frames);
+  a.frame_f4 = (int)(frame_bytes / 16); a.cap = capacity; a.ptr0 = ptr;
+  a.first = n > capacity ? n - capacity : 0; a.n = n;
+  a.act = d_in_act; a.rew = d_in_rew; a.done = d_in_done; a.ract = d_act; a.rrew = d_rew; a.rdone = d_done;
+  const int64_t blocks = std::min<int64_t>(n - a.first, (int64_t)sm_count(device) * 8);
+  fb_store_frames<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ddrl_seg_store(int device, float* d_ring, int row_floats, int64_t capacity, int64_t ptr, int nseg, const int* h_seg_off,
+                   const int* h_seg_w, const float* const* h_d_in, int64_t n, void* stream) {
+  if (!d_ring || !h_seg_off || !h_seg_w || !h_d_in) return fail(DDRL_EINVAL, "ddrl_seg_store: NULL argument");
+  if (row_floats < 4 || row_floats % 4 != 0) return fail(DDRL_EINVAL, "ddrl_seg_store: row_floats must be a positive multiple of 4");
+  if (nseg < 1 || nseg > 8) return fail(DDRL_EINVAL, "ddrl_seg_store: 1..8 segments");
+  if (capacity < 1 || ptr < 0 || ptr >= capacity || n < 0) return fail(DDRL_EINVAL, "ddrl_seg_store: bad capacity / ptr / n");
+  if (n == 0) return 0;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DDRL_ECUDA, "ddrl_seg_store: cannot select device %d", device);
+  SegStoreArgs a{};
+  a.ring = reinterpret_cast<float4*>(d_ring);
+  a.row_f4 = row_floats / 4; a.nseg = nseg;
+  int prev_end = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (h_seg_off[s] < prev_end || h_seg_w[s] < 1 || h_seg_off[s] + h_seg_w[s] > row_floats || !h_d_in[s])
+      return fail(DDRL_EINVAL, "ddrl_seg_store: segment %d is out of order, outside the row or has no input", s);
+    a.off[s] = h_seg_off[s]; a.w[s] = h_seg_w[s]; a.in[s] = h_d_in[s];
+    prev_end = h_seg_off[s] + h_seg_w[s];
+  }
+  a.cap = capacity; a.ptr0 = ptr; a.first = n > capacity ? n - capacity : 0; a.n = n;
+  const int64_t blocks = std::min<int64_t>((n - a.first + 7) / 8, (int64_t)sm_count(device) * 8);
+  seg_store_rows<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
   DDRL_LAUNCH_CHECK();
   return 0;
 }
@@ -1272,6 +1476,7 @@ int ddrl_seg_sample(int device, const float* d_ring, int row_floats, int64_t siz
 int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity, int64_t* steps,
                    int64_t* sample_times) {
   if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_counts: NULL handle");
+  RbLock lock(rb->mu);
   if (ptr) *ptr = rb->ptr;
   if (size) *size = rb->size;
   if (capacity) *capacity = rb->cap;
@@ -1282,8 +1487,30 @@ int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity,
 
 int ddrl_rb_note_samples(ddrl_rb_t rb, int64_t n_batches) {
   if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_note_samples: NULL handle");
+  RbLock lock(rb->mu);
   rb->sample_times += n_batches;
   return 0;
+}
+
+/* A consumer that reads the ring from its OWN kernel (the fused sample -> update step, ddrl_sac_step_from_buffer) brackets
+ * the launch of that kernel: read_begin takes the handle's lock, makes `stream` wait for every earlier store issued on
+ * another stream and reports the sampling range; read_end counts the samples, records the read for later stores and
+ * releases the lock. */
+int ddrl_rb_read_begin(ddrl_rb_t rb, void* stream, int64_t* size) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_read_begin: NULL handle");
+  rb->mu.lock();
+  int rc = order_before(rb, (cudaStream_t)stream, false);
+  if (rc) { rb->mu.unlock(); return rc; }
+  if (size) *size = rb->size;
+  return 0;
+}
+
+int ddrl_rb_read_end(ddrl_rb_t rb, void* stream, int64_t n_batches) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_read_end: NULL handle");
+  rb->sample_times += n_batches;
+  int rc = order_after(rb, (cudaStream_t)stream, false);
+  rb->mu.unlock();
+  return rc;
 }
 
 int ddrl_rb_layout(ddrl_rb_t rb, int* obs_dim, int* act_dim, int* row_floats, void** d_ring) {
@@ -1301,6 +1528,9 @@ int ddrl_rb_export(ddrl_rb_t rb, float* d_obs1, float* d_obs2, float* d_acts, fl
   if (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done)
     return fail(DDRL_EINVAL, "ddrl_rb_export: NULL output array");
   DeviceGuard guard(rb->device);
+  RbLock lock(rb->mu);
+  int rc = order_before(rb, (cudaStream_t)stream, false);
+  if (rc) return rc;
   GatherArgs a;
   a.ring = reinterpret_cast<const float4*>(rb->ring);
   a.D = rb->D; a.A = rb->A; a.row_f4 = rb->row_f4; a.used_f4 = rb->used_f4;
@@ -1309,7 +1539,8 @@ int ddrl_rb_export(ddrl_rb_t rb, float* d_obs1, float* d_obs2, float* d_acts, fl
   a.seed = a.counter = 0; a.rng_stream = 0;
   a.o1 = d_obs1; a.o2 = d_obs2; a.oa = d_acts; a.orw = d_rews; a.od = d_done; a.oidx = nullptr;
   a.nshards = 0;
-  return launch_gather(rb, a, (cudaStream_t)stream);
+  if ((rc = launch_gather(rb, a, (cudaStream_t)stream))) return rc;
+  return order_after(rb, (cudaStream_t)stream, false);
 }
 
 int ddrl_rb_import(ddrl_rb_t rb, const float* d_obs1, const float* d_obs2, const float* d_acts,
@@ -1322,11 +1553,13 @@ int ddrl_rb_import(ddrl_rb_t rb, const float* d_obs1, const float* d_obs2, const
     return fail(DDRL_EINVAL, "ddrl_rb_import: inconsistent counters ptr=%lld size=%lld cap=%lld",
                 (long long)ptr, (long long)size, (long long)rb->cap);
   DeviceGuard guard(rb->device);
-  int rc = launch_store<float>(rb, d_obs1, d_acts, d_rews, d_obs2, d_done, 0, rb->cap,
-                               (cudaStream_t)stream);
+  RbLock lock(rb->mu);
+  int rc = order_before(rb, (cudaStream_t)stream, true);
+  if (rc) return rc;
+  rc = launch_store<float>(rb, d_obs1, d_acts, d_rews, d_obs2, d_done, 0, rb->cap, (cudaStream_t)stream);
   if (rc) return rc;
   rb->ptr = ptr; rb->size = size; rb->steps = steps; rb->sample_times = sample_times;
-  return 0;
+  return order_after(rb, (cudaStream_t)stream, true);
 }
 
 }  // extern "C"

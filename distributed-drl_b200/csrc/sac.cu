@@ -1352,6 +1352,8 @@ struct ddrl_sac {
   unsigned long long* dp_trace = nullptr;   // DDRL_DP_TRACE=1: 8 phase time stamps of k_adam_dp's CTA 0 (ddrl_sac_dp_trace)
   bool dp_v1 = false;                   // DDRL_DP_V1=1: first form of the fused data-parallel step (reduce kernel + full peer read)
   bool narrow_w1 = false;               // policy W1 gradient (K = D <= 32) by k_wgrad_narrow instead of a tensor-core stage
+  float* host_stage = nullptr;          // device copy of a host batch block (ddrl_sac_step_host), maxB * (2D + A + 2) floats
+  float* host_scal = nullptr;           // its 4 output scalars before the D2H copy
   float* Gn = nullptr;                  // its per-slice partial blocks [ceil(maxB / 64)][(D + 1) * h1]
   uint32_t* H1bits[8] = {};             // relu'(H1) of each pass as bit masks [maxB][ldbits] (written by the L1 epilogue)
   int ldbits = 0;
@@ -2288,9 +2290,14 @@ int ddrl_sac_step_from_buffer(ddrl_sac_t h, ddrl_rb_t rb, int batch, uint64_t rb
   if (rc) return rc;
   if (D != h->D || A != h->A)
     return fail(DDRL_EINVAL, "ddrl_sac_step_from_buffer: buffer rows are (obs %d, act %d), learner expects (%d, %d)", D, A, h->D, h->A);
-  int64_t ptr = 0, size = 0, cap = 0, steps = 0, samples = 0;
-  if ((rc = ddrl_rb_counts(rb, &ptr, &size, &cap, &steps, &samples))) return rc;
-  if (size == 0) return fail(DDRL_EEMPTY, "ddrl_sac_step_from_buffer: ring is empty (the reference raises ValueError: high <= 0)");
+  // the ring is read by this step's first kernel: order it after stores issued on other streams (read_begin holds the
+  // buffer's lock until read_end, so no store can slip between the size snapshot and the launch)
+  int64_t size = 0;
+  if ((rc = ddrl_rb_read_begin(rb, stream, &size))) return rc;
+  if (size == 0) {
+    ddrl_rb_read_end(rb, stream, 0);
+    return fail(DDRL_EEMPTY, "ddrl_sac_step_from_buffer: ring is empty (the reference raises ValueError: high <= 0)");
+  }
   RingSrc rs;
   rs.ring = (const float*)ring; rs.row_f = row_f; rs.stream = rb_stream; rs.seed = rb_seed; rs.counter = rb_counter;
   rs.size = (uint64_t)size;
@@ -2298,8 +2305,37 @@ int ddrl_sac_step_from_buffer(ddrl_sac_t h, ddrl_rb_t rb, int batch, uint64_t rb
   const float gs = h->pc.world > 1 ? 1.0f / (float)h->pc.world : 1.0f;
   rc = step_common(h, mode, nullptr, nullptr, nullptr, nullptr, nullptr, batch, d_noise, seed, gs, d_out_scalars, d_out_q1,
                    d_out_q2, d_out_logp, stream, "ddrl_sac_step_from_buffer", &rs);
+  const int rc2 = ddrl_rb_read_end(rb, stream, rc ? 0 : 1);
+  return rc ? rc : rc2;
+}
+
+int ddrl_sac_step_host(ddrl_sac_t h, const void* h_block, int batch, uint64_t seed, float* h_out_scalars, float* d_out_q1,
+                       float* d_out_q2, float* d_out_logp, void* stream) {
+  if (!h || !h_block) return fail(DDRL_EINVAL, "ddrl_sac_step_host: NULL argument");
+  if (batch < 1 || batch > h->maxB) return fail(DDRL_EINVAL, "ddrl_sac_step_host: batch=%d not in [1, %d]", batch, h->maxB);
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t row = (size_t)(2 * h->D + h->A + 2);
+  if (!h->host_stage) {
+    int rc = dalloc(h, &h->host_stage, (size_t)h->maxB * row);
+    if (!rc) rc = dalloc(h, &h->host_scal, 4);
+    if (rc) return rc;
+  }
+  // one H2D copy of the block (stream order protects the staging: the previous step's prologue has consumed it), the
+  // step, one D2H copy of the four scalars; nothing here waits for the GPU
+  const size_t B = (size_t)batch;
+  DDRL_CUDA(cudaMemcpyAsync(h->host_stage, h_block, B * row * sizeof(float), cudaMemcpyHostToDevice, s));
+  float* x = h->host_stage;
+  float* x2 = x + B * h->D;
+  float* a = x2 + B * h->D;
+  float* r = a + B * h->A;
+  float* d = r + B;
+  const bool dp = h->pc.world > 1;
+  int rc = step_common(h, dp ? MODE_DP : MODE_FULL, x, x2, a, r, d, batch, nullptr, seed, dp ? 1.0f / (float)h->pc.world : 1.0f,
+                       h->host_scal, d_out_q1, d_out_q2, d_out_logp, stream, "ddrl_sac_step_host");
   if (rc) return rc;
-  return ddrl_rb_note_samples(rb, 1);
+  if (h_out_scalars) DDRL_CUDA(cudaMemcpyAsync(h_out_scalars, h->host_scal, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return 0;
 }
 
 int ddrl_sac_grad_buffer(ddrl_sac_t h, float** d_grads, int64_t* count, float** d_alpha_stat) {

@@ -37,13 +37,18 @@ SIGNATURES = {
     "ddrl_rb_destroy": (_int, [_vp]),
     "ddrl_rb_store_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "ddrl_rb_store_batch_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "ddrl_rb_store_block_bytes": (_i64, [_vp, _i64, _int]),
+    "ddrl_rb_store_block_host": (_int, [_vp, _vp, _i64, _int, _vp]),
     "ddrl_rb_sample": (_int, [_vp, _i64, _i64, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ddrl_rb_sample_host": (_int, [_vp, _i64, _i64, _vp, _u64, _u64, _u32, _vp, _i64, _vp]),
+    "ddrl_rb_sample_host_async": (_int, [_vp, _i64, _i64, _vp, _u64, _u64, _u32, _vp, _i64, _vp]),
     "ddrl_rb_sample_block_bytes": (_i64, [_vp, _i64]),
     "ddrl_rb_ipc_export": (_int, [_vp, _vp]),
     "ddrl_rb_peer_attach": (_int, [_vp, _int, _int, _vp]),
     "ddrl_rb_sample_global": (_int, [_vp, _i64, _i64, _vp, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "ddrl_fb_sample_stack": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_fb_sample_stack": (_int, [_int, _vp, _i64, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_fb_store_frames": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "ddrl_seg_store": (_int, [_int, _vp, _int, _i64, _i64, _int, _pint, _pint, C.POINTER(_vp), _i64, _vp]),
     "ddrl_seg_sample": (_int, [_int, _vp, _int, _i64, _int, _pint, _pint, C.POINTER(_vp), _i64, _vp, _u64, _u64, _u32, _vp, _vp]),
     "ddrl_rb_counts": (_int, [_vp, _pi64, _pi64, _pi64, _pi64, _pi64]),
     "ddrl_rb_layout": (_int, [_vp, _pint, _pint, _pint, C.POINTER(_vp)]),
@@ -60,7 +65,10 @@ SIGNATURES = {
     "ddrl_sac_apply_grads": (_int, [_vp, _int, _vp]),
     "ddrl_sac_step_dp": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _u64, _f, _vp, _vp, _vp, _vp, _vp]),
     "ddrl_sac_step_from_buffer": (_int, [_vp, _vp, _int, _u64, _u64, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "ddrl_sac_step_host": (_int, [_vp, _vp, _int, _u64, _vp, _vp, _vp, _vp, _vp]),
     "ddrl_rb_note_samples": (_int, [_vp, _i64]),
+    "ddrl_rb_read_begin": (_int, [_vp, _vp, _pi64]),
+    "ddrl_rb_read_end": (_int, [_vp, _vp, _i64]),
     "ddrl_sac_comm_export": (_int, [_vp, _vp]),
     "ddrl_sac_comm_attach": (_int, [_vp, _int, _int, _vp]),
     "ddrl_sac_comm_error": (_int, [_vp, _pint]),

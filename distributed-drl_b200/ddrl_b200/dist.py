@@ -228,3 +228,41 @@ class ShardedReplayBuffer:
         if not device:
             out = {k: v.cpu().numpy() for k, v in out.items()}
         return out
+
+
+class ShardedFrameReplayBuffer:
+    """BASELINE.json config 4 as configured: an Atari-shaped uint8 frame replay of `total_size` transitions sharded over
+    the GPUs of a node (1e6 transitions over 8 B200 = 125 000 per shard, 0.9 GB deduplicated / 7 GB naive per GPU).
+
+    The path shards with NO data-path collective: every rank owns a FrameReplayBuffer of ceil(total / world) slots, its
+    rollout producers store into it and its learner samples from it — the reference's one-shard-per-call behaviour
+    (algos/sac1/sac_ray.py:137-141).  `get_counts(global_=True)` is the only collective (an all-reduce of three integers)."""
+
+    def __init__(self, frame_shape=(84, 84), stack=4, total_size=1_000_000, *, mode="dedup", group=None, device=None,
+                 seed=None):
+        from .frames import FrameReplayBuffer
+        self.group = group
+        self.world, self.rank = world_size(group), rank(group)
+        self.map = ShardMap(total_size, self.world)
+        self.local = FrameReplayBuffer(frame_shape, stack, self.map.cap, mode=mode, device=device, seed=seed,
+                                       rng_stream=self.rank)
+
+    def store(self, *a):
+        return self.local.store(*a)
+
+    def store_batch(self, *a):
+        return self.local.store_batch(*a)
+
+    def store_frames(self, *a):
+        return self.local.store_frames(*a)
+
+    def sample_batch(self, batch_size=512, **kw):
+        return self.local.sample_batch(batch_size, **kw)
+
+    def get_counts(self, global_=False):
+        c = self.local.get_counts()
+        if not global_ or self.world == 1:
+            return c
+        t = torch.tensor(list(c), dtype=torch.int64, device=self.local._dev if dist.get_backend(self.group) == "nccl" else "cpu")
+        dist.all_reduce(t, group=self.group)
+        return tuple(int(x) for x in t.tolist())

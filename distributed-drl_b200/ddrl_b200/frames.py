@@ -10,7 +10,9 @@ The reference has no uint8 frame buffer: its dqn-family 
       (a bit copy, so gathers are exact by construction);
   FrameReplayBuffer(mode="dedup")  stores ONE new frame per transition and rebuilds the two stacks at
       sample time from stack+1 consecutive frames (ddrl_fb_sample_stack): 8x less HBM per transition.
-      Like most Atari replays it ignores episode boundaries inside a stack.
+      Like most Atari replays it ignores episode boundaries inside a stack; sampled windows never cross the write head.
+
+ShardedFrameReplayBuffer (ddrl_b200.dist) is the configured C4 shape: 1e6 transitions as one shard per GPU.
 """
 from __future__ import annotations
 
@@ -75,15 +77,24 @@ class FrameReplayBuffer:
     def store_frames(self, frames, act, rew, done):
         """dedup layout: append n frames (frame t+1 of each transition) and the transition scalars of
         the step that produced them; transition i = (stack ending at frame i) -> (stack ending at i+1),
-        so act/rew/done of that step are stored at slot i = position of the previous frame."""
+        so act/rew/done of that step are stored at slot i = position of the previous frame.  One launch of
+        fb_store_frames (ddrl_fb_store_frames); host arrays are uploaded first, CUDA tensors are consumed in place."""
         fr = self._u8(frames, -1, self.frame_bytes)
         n = int(fr.shape[0])
-        f = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(-1).to(self._dev) if not isinstance(v, torch.Tensor) else v.reshape(-1).to(self._dev, torch.float32)
-        skip = max(0, n - self.max_size)           # more rows than slots: only the last `capacity` survive
-        pos = (self.ptr + torch.arange(skip, n, device=self._dev)) % self.max_size
-        prev = (pos - 1) % self.max_size
-        self.frames[pos] = fr[skip:]
-        self.act[prev], self.rew[prev], self.done[prev] = f(act)[skip:], f(rew)[skip:], f(done)[skip:]
+        if n == 0:
+            return
+        f = lambda v: (torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(-1).to(self._dev) if not isinstance(v, torch.Tensor)
+                       else v.reshape(-1).to(self._dev, torch.float32)).contiguous()
+        a, r, d = f(act), f(rew), f(done)
+        if not (a.numel() == r.numel() == d.numel() == n):
+            raise ValueError("store_frames: frames / act / rew / done disagree on n")
+        s = torch.cuda.current_stream(self.device)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        N.check(self._lib.ddrl_fb_store_frames(self.device, p(self.frames), self.frame_bytes, self.max_size, self.ptr,
+                                               p(self.act), p(self.rew), p(self.done), p(fr), p(a), p(r), p(d), n,
+                                               C.c_void_p(s.cuda_stream)))
+        for t in (fr, a, r, d):
+            t.record_stream(s)
         self.ptr = (self.ptr + n) % self.max_size
         self.size = min(self.size + n, self.max_size)
         self.steps += n
@@ -114,8 +125,9 @@ class FrameReplayBuffer:
             self._seed = int(np.random.randint(0, 2 ** 31 - 1))
         s = torch.cuda.current_stream(self.device)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        N.check(self._lib.ddrl_fb_sample_stack(self.device, p(self.frames), self.frame_bytes, self.stack, self.max_size,
-                                               self.size, p(self.act), p(self.rew), p(self.done), B, p(di), self._seed,
+        oldest = self.ptr if self.size == self.max_size else 0     # Philox draws ages from the oldest frame: no window
+        N.check(self._lib.ddrl_fb_sample_stack(self.device, p(self.frames), self.frame_bytes, self.stack, self.max_size,    # crosses the write head
+                                               self.size, oldest, p(self.act), p(self.rew), p(self.done), B, p(di), self._seed,
                                                self._counter, self._rng_stream, p(o1), p(o2), p(oa), p(orw), p(od), p(oi),
                                                C.c_void_p(s.cuda_stream)))
         if idxs is None:

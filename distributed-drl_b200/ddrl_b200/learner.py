@@ -15,6 +15,7 @@ the backward and the optimiser), which the reference stubs out (:144-148).
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
 from collections import OrderedDict
@@ -119,6 +120,8 @@ class Learner(object):
         self._pg = process_group
         self._fused = False
         self._outs = None
+        self._hscal, self._hscal_event = None, None
+        self._inflight = collections.deque()
         self._stage = {}
         self.steps = 0
         init = glorot_init(self.obs_dim, self.act_dim, self.hidden, self.seed)
@@ -336,6 +339,10 @@ class Learner(object):
         three normal draws (parity tests); default: drawn on the GPU.  Returns the reference's fetch
         list as a dict of CUDA tensors (pi_loss, q1_loss, q2_loss, alpha in `scalars`; q1, q2,
         logp_pi), valid until the next call, without synchronising."""
+        blk = getattr(batch, "block", None)
+        if (blk is not None and noise is None and not split and (self._world() == 1 or self._fused)
+                and self._views_of_block(batch, blk)):
+            return self._train_host_block(batch, blk, sync_outputs)
         x, x2, a, r, d = self._to_device(batch)
         B = int(r.shape[0])
         if B > self.max_batch:
@@ -379,6 +386,48 @@ class Learner(object):
         if sync_outputs:
             s.synchronize()
         return o
+
+    def _train_host_block(self, batch, blk, sync_outputs):
+        """train() on a HostBatch that still IS the pinned block sample_batch() returned: one native call
+        (ddrl_sac_step_host) queues the H2D copy of the block, the update, and the D2H copy of the four scalars into a
+        pinned host array — no torch op, no wait.  `losses()` reads the scalars back."""
+        B = int(batch.n)
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch} (pass max_batch= to Learner)")
+        if self._outs is None or self._outs["q1"].shape[0] != B:
+            f = dict(dtype=torch.float32, device=self._dev)
+            self._outs = dict(scalars=torch.zeros(4, **f), q1=torch.empty(B, **f), q2=torch.empty(B, **f),
+                              logp_pi=torch.empty(B, **f))
+        if self._hscal is None:
+            self._hscal = torch.zeros(4, dtype=torch.float32, pin_memory=True)
+        o = self._outs
+        s = self._stream()
+        world = self._world()
+        N.check(self._lib.ddrl_sac_step_host(
+            self._h, C.c_void_p(blk.data_ptr()), B, self._noise_seed() if world > 1 else self.seed,
+            C.c_void_p(self._hscal.data_ptr()), *[C.c_void_p(o[k].data_ptr()) for k in ("q1", "q2", "logp_pi")],
+            C.c_void_p(s.cuda_stream)))
+        ev = torch.cuda.Event()
+        ev.record(s)
+        # the pinned block must stay allocated until its copy has run: keep it until a later step's event has fired
+        self._inflight.append((ev, blk))
+        while len(self._inflight) > 1 and self._inflight[0][0].query():
+            self._inflight.popleft()
+        self._hscal_event = ev
+        self.steps += 1
+        if sync_outputs:
+            s.synchronize()
+        out = dict(o)
+        out["scalars"] = _LazyScalars(self)
+        return out
+
+    def losses(self):
+        """(pi_loss, q1_loss, q2_loss, alpha) of the last train() that took the host-block path, as a numpy array: waits for
+        that step only (an event), not for the stream."""
+        if self._hscal_event is None:
+            raise RuntimeError("losses(): no host-block train() call yet")
+        self._hscal_event.synchronize()
+        return self._hscal.numpy().copy()
 
     def train_from_buffer(self, replay_buffer, batch_size, noise=None, sync_outputs=False):
         """`batch = replay_buffer.sample_batch(B); agent.train(batch)` as ONE native call (example/model.py:92-101's
@@ -430,6 +479,26 @@ class Learner(object):
 
     def apply_gradients(self, gradients):
         pass
+
+
+class _LazyScalars:
+    """`train()`'s `scalars` entry on the host-block path: behaves like the 4-float tensor of the other paths for the two
+    things callers do with it — `.cpu()` (waits for that step's event and returns a CPU tensor) and indexing."""
+
+    def __init__(self, learner):
+        self._l = learner
+
+    def cpu(self):
+        return torch.from_numpy(self._l.losses())
+
+    def numpy(self):
+        return self._l.losses()
+
+    def __getitem__(self, i):
+        return self.cpu()[i]
+
+    def tolist(self):
+        return self._l.losses().tolist()
 
 
 class Actor(object):

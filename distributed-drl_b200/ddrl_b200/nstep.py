@@ -33,19 +33,6 @@ def row_layout(Ln, D, A):
     return widths, offsets, used, (used + 3) // 4 * 4
 
 
-def pack_rows(obs, acts, rews, done, Ln, D, A):
-    """[n, Ln+1, ...], [n, Ln, ...], [n, Ln], [n, Ln] -> packed float32 rows [n, row_f] (numpy assignment casts, as the
-    reference's `buffer[ptr] = np.array(..., dtype=np.float32)` does)."""
-    widths, o, _, row_f = row_layout(Ln, D, A)
-    n = int(np.asarray(rews).shape[0])
-    rows = np.zeros((n, row_f), dtype=np.float32)
-    rows[:, o[0]:o[0] + widths[0]] = np.asarray(obs).reshape(n, -1)
-    rows[:, o[1]:o[1] + widths[1]] = np.asarray(acts).reshape(n, -1)
-    rows[:, o[2]:o[2] + Ln] = np.asarray(rews).reshape(n, -1)
-    rows[:, o[3]:o[3] + Ln] = np.asarray(done).reshape(n, -1)
-    return rows
-
-
 class NStepReplayBuffer:
     def __init__(self, opt, *, device=None, seed=None, rng_stream=0, index_source="philox"):
         if not torch.cuda.is_available():
@@ -70,21 +57,32 @@ class NStepReplayBuffer:
         self._rng_stream, self._counter = int(rng_stream) & 0xFFFFFFFF, 0
 
     # ---- store -----------------------------------------------------------------------------------
-    def _pack(self, obs, acts, rews, done):
-        return pack_rows(obs, acts, rews, done, self.Ln, self.D, self.A)
-
     def store_batch(self, obs, acts, rews, done):
-        """n sequences at once (== n store() calls in row order); only the last `capacity` survive."""
-        rows = torch.from_numpy(self._pack(obs, acts, rews, done))
-        n = int(rows.shape[0])
-        skip = max(0, n - self.max_size)
-        rows = rows[skip:].to(self._dev)
-        m = n - skip
-        start = (self.ptr + skip) % self.max_size
-        first = min(m, self.max_size - start)
-        self.ring[start:start + first].copy_(rows[:first])              # contiguous device copies, wrap-around split
-        if m > first:
-            self.ring[:m - first].copy_(rows[first:])
+        """n sequences at once (== n store() calls in row order); only the last `capacity` survive.  The four dense
+        arrays ([n, Ln+1, ...], [n, Ln, ...], [n, Ln], [n, Ln]; numpy or CUDA tensors) are packed into ring rows by ONE
+        launch of seg_store_rows (ddrl_seg_store); host arrays are cast to float32 (numpy assignment semantics, as the
+        reference's `buffer[ptr] = np.array(..., dtype=np.float32)`) and uploaded, CUDA tensors are consumed in place."""
+        ins = []
+        for x, w in zip((obs, acts, rews, done), self.widths):
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                t = x.to(self._dev, torch.float32).reshape(-1, w).contiguous()
+            else:
+                x = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+                t = torch.from_numpy(np.ascontiguousarray(x.reshape(-1, w), dtype=np.float32)).to(self._dev)
+            ins.append(t)
+        n = int(ins[2].shape[0])
+        if any(int(t.shape[0]) != n for t in ins):
+            raise ValueError("store_batch: obs / acts / rews / done disagree on n")
+        if n == 0:
+            return
+        s = torch.cuda.current_stream(self.device)
+        off = (C.c_int * 4)(*self.offsets)
+        wid = (C.c_int * 4)(*self.widths)
+        ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in ins])
+        N.check(self._lib.ddrl_seg_store(self.device, C.c_void_p(self.ring.data_ptr()), self.row_f, self.max_size, self.ptr, 4,
+                                         off, wid, ptrs, n, C.c_void_p(s.cuda_stream)))
+        for t in ins:
+            t.record_stream(s)
         self.ptr = (self.ptr + n) % self.max_size
         self.size = min(self.size + n, self.max_size)
         self.steps += n * self.num_buffers
@@ -130,6 +128,18 @@ class NStepReplayBuffer:
         if not device:
             out = {k: v.cpu().numpy() for k, v in out.items()}
         return out
+
+    def prefetch(self, depth=8, batch_size=None):
+        """Bounded prefetch of the learner loop (the reference's Cache thread + Queue(maxsize) in front of the sequence
+        buffers, algos/sac1/sac_ray.py:86-145): an iterator that keeps up to `depth` sampled batches queued on the GPU —
+        `depth` sample_batch launches are issued ahead of the consumer, on the current stream, and each batch is handed
+        out in sampling order; batches never leave HBM, so no thread and no host queue are needed."""
+        from collections import deque
+        q = deque()
+        while True:
+            while len(q) < max(1, int(depth)):
+                q.append(self.sample_batch(batch_size, device=True))
+            yield q.popleft()
 
     def get_counts(self):
         return self.sample_times, self.steps, self.size

@@ -14,6 +14,8 @@ sample_many (several batches per launch), device=True outputs (no D2H), injected
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import threading
 import os
 
 import numpy as np
@@ -55,6 +57,102 @@ class HostBatch(dict):
     n = 0             # rows
 
 
+class PendingBatch:
+    """A sample_batch_async() result: `wait()` returns the HostBatch once its D2H copy has completed."""
+
+    def __init__(self, event, batch):
+        self._event, self._batch = event, batch
+
+    def ready(self):
+        return self._event.query()
+
+    def wait(self):
+        self._event.synchronize()
+        return self._batch
+
+
+class Cache:
+    """The learner-side prefetcher of the reference (algos/sac1/sac1.py:103-130: a process that keeps Queue(10) filled with
+    `sample_batch(opt.batch_size)` results so that `batch = cache.q1.get()` never waits for the replay actor, and that
+    forwards `cache.q2.put(agent.get_weights())` to the parameter server).  Same surface — Cache(replay_buffer), .start(),
+    .end(), .q1.get(), .q2.put((keys, values)) — without a process or a host queue: `depth` samples are kept IN FLIGHT on a
+    dedicated CUDA stream (gather kernel + D2H copy into pinned blocks), so batch k+1 crosses PCIe while the learner's
+    stream runs update k.  Batches are drawn up to `depth` calls ahead of the stores that precede their consumption — the
+    reference's queue is up to 10 batches stale in the same way."""
+
+    class _Q1:
+        def __init__(self, cache):
+            self._c = cache
+
+        def get(self):
+            return self._c._next()
+
+        def qsize(self):
+            return sum(1 for p in self._c._pending if p.ready())
+
+        def empty(self):
+            return self.qsize() == 0
+
+    class _Q2:
+        def __init__(self, cache):
+            self._c = cache
+
+        def put(self, kv):
+            if self._c.ps is not None:
+                keys, values = kv
+                self._c.ps.push(keys, values)
+
+        def qsize(self):
+            return 0
+
+        def empty(self):
+            return True
+
+    def __init__(self, replay_buffer, batch_size=None, *, depth=2, ps=None):
+        from collections import deque
+        self.replay_buffer, self.ps = replay_buffer, ps
+        self.batch_size = batch_size
+        self.depth = max(1, int(depth))
+        self._pending = deque()
+        self._stream = None
+        self.q1, self.q2 = Cache._Q1(self), Cache._Q2(self)
+
+    def start(self, batch_size=None):
+        if batch_size is not None:
+            self.batch_size = batch_size
+        if self.batch_size is None:
+            raise ValueError("Cache needs a batch size (the reference reads the global opt.batch_size)")
+        self._stream = torch.cuda.Stream(device=self.replay_buffer.device)
+        self._fill()
+
+    def _fill(self):
+        while len(self._pending) < self.depth:
+            self._pending.append(self.replay_buffer.sample_batch_async(self.batch_size, stream=self._stream))
+
+    def _next(self):
+        if self._stream is None:
+            self.start()
+        batch = self._pending.popleft().wait()
+        self._fill()
+        return batch
+
+    def end(self):
+        if self._stream is not None:
+            self._stream.synchronize()
+        self._pending.clear()
+
+
+def _locked(fn):
+    """Serialise a method on the buffer's lock: producers (store / store_batch from rollout threads, each on its own CUDA
+    stream) and the learner (sample_batch / train_from_buffer) may call one buffer concurrently, as the reference's
+    workers call one Ray actor (algos/sac1/sac1.py:195); the host-side staging and counters are shared state."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with self._lock:
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class ReplayBuffer:
     """Drop-in for the reference ReplayBuffer.
 
@@ -80,6 +178,7 @@ class ReplayBuffer:
         if index_source not in ("philox", "numpy"):
             raise ValueError(f"unknown index_source {index_source!r}")
         self._lib = N.lib()
+        self._lock = threading.RLock()
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.flavor = flavor
         self.obs_dim = int(obs_dim)
@@ -131,6 +230,7 @@ class ReplayBuffer:
     # ------------------------------------------------------------------------------------------
     # store
     # ------------------------------------------------------------------------------------------
+    @_locked
     def store(self, obs, act, rew, next_obs, done):
         """One transition (reference signature).  Arguments are captured by value at call time
         (numpy assignment into pinned staging performs the same casts as the reference's
@@ -150,6 +250,7 @@ class ReplayBuffer:
         if self._staged == self._stage_rows:
             self.flush()
 
+    @_locked
     def flush(self):
         """Push staged single-transition stores to the GPU ring."""
         k = self._staged
@@ -166,6 +267,7 @@ class ReplayBuffer:
         self._staged = 0
         self._cur ^= 1
 
+    @_locked
     def store_batch(self, obs, act, rew, next_obs, done):
         """n transitions at once (== n sequential store() calls in row order).  Accepts numpy
         arrays (copied through pinned staging by the library call) or torch tensors; CUDA tensors
@@ -192,7 +294,7 @@ class ReplayBuffer:
         if n <= self._bstage_rows:
             # by-value capture into our own pinned staging (numpy assignment = the reference's cast), then ONE
             # asynchronous H2D copy: the block has the layout of the library's device staging (256-byte aligned
-            # sub-arrays obs | next_obs | acts | rews | done for THIS n), which ddrl_rb_store_batch_host recognises;
+            # sub-arrays obs | next_obs | acts | rews | done for THIS n, ddrl_rb_store_block_host);
             # no stream synchronisation on the producer's call path
             st = self._bstages[self._bcur]
             self._bcur ^= 1
@@ -206,8 +308,7 @@ class ReplayBuffer:
             for off, a, sh in zip(offs, np_arrs, shapes):
                 cnt = int(np.prod(sh))
                 np.copyto(raw[off:off + 4 * cnt].view(np.float32).reshape(sh), a.reshape(sh), casting="unsafe")
-            N.check(self._lib.ddrl_rb_store_batch_host(
-                self._h, *[C.c_void_p(base + off) for off in offs], n, N.F32, C.c_void_p(s.cuda_stream)))
+            N.check(self._lib.ddrl_rb_store_block_host(self._h, C.c_void_p(base), n, N.F32, C.c_void_p(s.cuda_stream)))
             ev = torch.cuda.Event()
             ev.record(s)
             st["event"] = ev
@@ -253,6 +354,7 @@ class ReplayBuffer:
         lead = (n_batches, batch) if many else (batch,)
         return lead
 
+    @_locked
     def _sample(self, batch_size, n_batches, idxs, device, many, return_idxs):
         self.flush()
         batch_size, n_batches = int(batch_size), int(n_batches)
@@ -303,21 +405,54 @@ class ReplayBuffer:
             N.check(self._lib.ddrl_rb_sample_host(
                 self._h, batch_size, n_batches, C.c_void_p(h_idx.ctypes.data) if h_idx is not None else None,
                 seed, counter, self._rng_stream, _ptr(block), nbytes, C.c_void_p(s.cuda_stream)))
-            raw = block.numpy()
-            nf = n * (2 * D + A + 2)
-            f = raw[: nf * 4].view(np.float32)
-            o = 0
-            out = HostBatch()
-            out.block, out.n = block, n
-            for key, width, shape in (("obs1", D, lead + (D,)), ("obs2", D, lead + (D,)),
-                                      ("acts", A, act_shape), ("rews", 1, lead), ("done", 1, lead)):
-                out[key] = f[o:o + n * width].reshape(shape)
-                o += n * width
-            if return_idxs:
-                out["idxs"] = raw[nbytes - n * 8:].view(np.int64).reshape(lead)
+            out = self._host_batch(block, nbytes, n, lead, act_shape, return_idxs)
         if idxs is None:
             self._counter += 1
         return out
+
+    def _host_batch(self, block, nbytes, n, lead, act_shape, return_idxs):
+        D, A = self.obs_dim, self.act_dim
+        raw = block.numpy()
+        f = raw[: n * (2 * D + A + 2) * 4].view(np.float32)
+        o = 0
+        out = HostBatch()
+        out.block, out.n = block, n
+        for key, width, shape in (("obs1", D, lead + (D,)), ("obs2", D, lead + (D,)),
+                                  ("acts", A, act_shape), ("rews", 1, lead), ("done", 1, lead)):
+            out[key] = f[o:o + n * width].reshape(shape)
+            o += n * width
+        if return_idxs:
+            out["idxs"] = raw[nbytes - n * 8:].view(np.int64).reshape(lead)
+        return out
+
+    @_locked
+    def sample_batch_async(self, batch_size=128, *, stream=None):
+        """sample_batch() issued AHEAD of its consumer: the gather and the D2H copy into a fresh pinned block are queued on
+        `stream` (default: the current stream) and the call returns at once with a PendingBatch; `.wait()` blocks until
+        the block has arrived and returns the usual dict of numpy arrays.  The index stream advances exactly as for
+        sample_batch(), so a sequence of async calls returns the same batches as the same sequence of blocking calls —
+        each drawn from the ring as it was when ITS turn came on the stream."""
+        self.flush()
+        B = int(batch_size)
+        if self.size == 0:
+            raise ValueError("high <= 0")
+        idxs = np.random.randint(0, self.size, size=B) if self.index_source == "numpy" else None
+        s = stream if stream is not None else self._stream()
+        h_idx = np.ascontiguousarray(idxs, dtype=np.int64) if idxs is not None else None
+        nbytes = int(self._lib.ddrl_rb_sample_block_bytes(self._h, B))
+        block = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        N.check(self._lib.ddrl_rb_sample_host_async(
+            self._h, B, 1, C.c_void_p(h_idx.ctypes.data) if h_idx is not None else None,
+            0 if idxs is not None else self._philox_seed(), self._counter, self._rng_stream, _ptr(block), nbytes,
+            C.c_void_p(s.cuda_stream)))
+        if h_idx is not None:
+            s.synchronize()              # the pageable index array was read by an asynchronous copy
+        else:
+            self._counter += 1
+        ev = torch.cuda.Event()
+        ev.record(s)
+        act_shape = (B,) if self._scalar_act else (B, self.act_dim)
+        return PendingBatch(ev, self._host_batch(block, nbytes, B, (B,), act_shape, False))
 
     def sample_batch(self, batch_size=128, *, idxs=None, device=False, return_idxs=False):
         """Reference signature.  Returns dict(obs1, obs2, acts, rews, done): float32 numpy arrays
@@ -352,6 +487,7 @@ class ReplayBuffer:
 
     rollout_steps = steps  # example/dsac.py naming
 
+    @_locked
     def get_counts(self):
         p, size, cap, steps, samples = self._counts_native()
         steps += self._staged
@@ -360,6 +496,7 @@ class ReplayBuffer:
             return steps                      # example/dsac.py:47-48
         return samples, steps, size           # algos/sac1/sac1.py:62-63 ; dqn: (learner_steps, actor_steps, size)
 
+    @_locked
     def ring_arrays(self):
         """The reference's five arrays (obs1_buf, obs2_buf, acts_buf, rews_buf, done_buf) as numpy,
         unpacked from the GPU ring — for checkpoints and parity tests, not a hot path."""
@@ -379,6 +516,7 @@ class ReplayBuffer:
         return dict(obs1_buf=o1.cpu().numpy(), obs2_buf=o2.cpu().numpy(), acts_buf=acts,
                     rews_buf=orw.cpu().numpy(), done_buf=od.cpu().numpy())
 
+    @_locked
     def load_ring_arrays(self, obs1_buf, obs2_buf, acts_buf, rews_buf, done_buf, ptr, size, steps=0,
                          sample_times=0):
         self.flush()

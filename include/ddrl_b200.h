@@ -80,6 +80,12 @@ int ddrl_rb_store_batch(ddrl_rb_t rb, const void* d_obs, const void* d_act, cons
 int ddrl_rb_store_batch_host(ddrl_rb_t rb, const void* h_obs, const void* h_act, const void* h_rew,
                              const void* h_next_obs, const void* h_done, int64_t n, int in_dtype,
                              void* stream);
+/* same from ONE host block laid out like the handle's device staging — five sub-arrays obs | next_obs | acts | rews |
+ * done, each starting at a 256-byte multiple (sizes n*D, n*D, n*A, n, n elements of in_dtype rounded up to 256 bytes;
+ * ddrl_rb_store_block_bytes gives the block size): a single H2D copy.  Vectorised producers stage their rows in such a
+ * pinned block (the by-value capture of `replay_buffer.store.remote`, algos/sac1/sac1.py:195). */
+int64_t ddrl_rb_store_block_bytes(ddrl_rb_t rb, int64_t n, int in_dtype);
+int ddrl_rb_store_block_host(ddrl_rb_t rb, const void* h_block, int64_t n, int in_dtype, void* stream);
 
 /* n_batches x ReplayBuffer.sample_batch(batch)  (example/dsac.py:39-45; algos/sac1/sac1.py:53-60)
  * in one launch.  Index stream, uniform on [0,size) with replacement like np.random.randint:
@@ -101,6 +107,13 @@ int ddrl_rb_sample(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t
 int ddrl_rb_sample_host(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_idx_in,
                         uint64_t seed, uint64_t counter, uint32_t rng_stream,
                         void* h_out_block, int64_t block_bytes, void* stream);
+/* same without the final synchronisation: the block is complete when `stream` has executed the call (record an event
+ * after it).  This is what a prefetcher uses — the reference's Cache process samples ahead of the learner into a
+ * Queue(10) (algos/sac1/sac1.py:103-130); here the gather and the D2H copy of batch k+1 run on the prefetcher's stream
+ * while the learner's stream runs update k. */
+int ddrl_rb_sample_host_async(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_idx_in,
+                              uint64_t seed, uint64_t counter, uint32_t rng_stream,
+                              void* h_out_block, int64_t block_bytes, void* stream);
 /* bytes ddrl_rb_sample_host writes for n = batch*n_batches rows */
 int64_t ddrl_rb_sample_block_bytes(ddrl_rb_t rb, int64_t n);
 
@@ -128,14 +141,23 @@ int ddrl_rb_sample_global(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const 
  * FrameStack algos/trading_env.py:289-325).  Frames live in a caller-owned ring d_frames[capacity]
  * of frame_bytes each (one frame per env step) with per-transition scalars d_act/d_rew/d_done[capacity];
  * transition i is obs1 = frames[i-stack+1..i], obs2 = frames[i-stack+2..i+1] (ring positions, no
- * episode-boundary handling).  Gathers `batch` transitions: injected indices (caller guarantees
- * stack-1 <= i <= size-2 when the ring has not wrapped) or Philox-drawn uniformly over that range.
- * Outputs: obs1, obs2 [batch, stack*frame_bytes] bytes; acts, rews, done [batch] f32. */
+ * episode-boundary handling).  Gathers `batch` transitions: injected ring positions (caller's responsibility that the
+ * window does not cross the write head) or Philox-drawn: an age u uniform over [0, size - stack) counted from the OLDEST
+ * frame, i = (oldest + stack-1 + u) % capacity — `oldest` is 0 until the ring wraps and the write pointer afterwards, so
+ * no drawn window straddles the write head.  Outputs: obs1, obs2 [batch, stack*frame_bytes] bytes; acts, rews, done
+ * [batch] f32.  One bulk copy global -> shared per frame and one or two shared -> global (TMA engine, no register pass);
+ * the ring and the stacked outputs must be 16-byte aligned. */
 int ddrl_fb_sample_stack(int device, const void* d_frames, int64_t frame_bytes, int stack, int64_t capacity,
-                         int64_t size, const float* d_act, const float* d_rew, const float* d_done,
+                         int64_t size, int64_t oldest, const float* d_act, const float* d_rew, const float* d_done,
                          int64_t batch, const int64_t* d_idx_in, uint64_t seed, uint64_t counter,
                          uint32_t rng_stream, void* d_out_obs1, void* d_out_obs2, float* d_out_acts,
                          float* d_out_rews, float* d_out_done, int64_t* d_out_idx, void* stream);
+/* store side of the same ring: frame j of d_in_frames [n, frame_bytes] goes to slot (ptr + j) % capacity, the scalars of
+ * the env step that produced it (d_in_act/rew/done [n]) to the slot before it; n > capacity keeps the last `capacity`
+ * frames, like n sequential stores of the dqn-family ring (algos/dqn/train.py:60-67).  The caller advances ptr / size. */
+int ddrl_fb_store_frames(int device, void* d_frames, int64_t frame_bytes, int64_t capacity, int64_t ptr, float* d_act,
+                         float* d_rew, float* d_done, const void* d_in_frames, const float* d_in_act,
+                         const float* d_in_rew, const float* d_in_done, int64_t n, void* stream);
 
 /* N-step sequence replay — sample_batch of the SQN_N_STEP ring (algos/sac1/sac_ray.py:34-83: rows of obs [Ln+1, D],
  * acts [Ln, A], rews [Ln], done [Ln]).  The ring is a caller-owned device array [capacity, row_floats] whose rows are
@@ -146,6 +168,12 @@ int ddrl_seg_sample(int device, const float* d_ring, int row_floats, int64_t siz
                     const int* h_seg_w, float* const* h_d_out, int64_t batch, const int64_t* d_idx_in, uint64_t seed,
                     uint64_t counter, uint32_t rng_stream, int64_t* d_out_idx, void* stream);
 
+/* store side of the N-step ring (algos/sac1/sac_ray.py:52-68: `buffer[ptr] = ...` per field): row j of the dense inputs
+ * h_d_in[s] [n, h_seg_w[s]] is packed into ring slot (ptr + j) % capacity (gaps and row padding are zero-filled; segments
+ * in ascending offset order); n > capacity keeps the last `capacity` rows.  The caller advances ptr / size. */
+int ddrl_seg_store(int device, float* d_ring, int row_floats, int64_t capacity, int64_t ptr, int nseg, const int* h_seg_off,
+                   const int* h_seg_w, const float* const* h_d_in, int64_t n, void* stream);
+
 /* ReplayBuffer.get_counts()  (algos/sac1/sac1.py:62-63) plus ptr / capacity.  Any out may be NULL. */
 int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity, int64_t* steps,
                    int64_t* sample_times);
@@ -154,6 +182,15 @@ int ddrl_rb_counts(ddrl_rb_t rb, int64_t* ptr, int64_t* size, int64_t* capacity,
 int ddrl_rb_layout(ddrl_rb_t rb, int* obs_dim, int* act_dim, int* row_floats, void** d_ring);
 /* sample_times += n_batches for a consumer that gathered from the ring itself (the fused sample->update step) */
 int ddrl_rb_note_samples(ddrl_rb_t rb, int64_t n_batches);
+/* Concurrency contract of a ddrl_rb_t (the Ray-actor semantics of the reference's ReplayBuffer, example/dsac.py:13,
+ * algos/sac1/sac1.py:27, 195): every entry point may be called from any host thread on any stream.  Reservations are
+ * serialised by the handle, so the ring always equals SOME serial order of the calls; kernels issued on different streams
+ * are ordered with events (a sample waits for earlier stores, a store for earlier samples and stores), so producers'
+ * copies and store kernels overlap the learner's stream.  A consumer that reads the ring from its own kernel brackets the
+ * launch with read_begin (takes the handle's lock, orders `stream`, reports the sampling range) / read_end (counts
+ * n_batches samples, records the read, releases the lock). */
+int ddrl_rb_read_begin(ddrl_rb_t rb, void* stream, int64_t* size);
+int ddrl_rb_read_end(ddrl_rb_t rb, void* stream, int64_t n_batches);
 
 /* ring <-> the reference's five arrays ([capacity,D],[capacity,D],[capacity,A],[capacity],[capacity]
  * f32, device memory): the on-disk format of algos/dqn/train.py:82-108 (save/load) goes through
@@ -226,6 +263,14 @@ int ddrl_sac_grad_buffer(ddrl_sac_t sac, float** d_grads, int64_t* count, float*
 int ddrl_sac_step_from_buffer(ddrl_sac_t sac, ddrl_rb_t rb, int batch, uint64_t rb_seed, uint64_t rb_counter,
                               uint32_t rb_stream, const float* d_noise, uint64_t seed, float* d_out_scalars,
                               float* d_out_q1, float* d_out_q2, float* d_out_logp, void* stream);
+/* `agent.train(batch)` with the batch in HOST memory, as the reference feeds it (feed_dict of numpy arrays,
+ * algos/sac1/actor_learner.py:135-142): h_block is ONE block [obs1 | obs2 | acts | rews | done] f32 for `batch` rows —
+ * the layout ddrl_rb_sample_host delivers (pinned memory recommended).  One H2D copy, the update, one D2H copy of
+ * (pi_loss, q1_loss, q2_loss, alpha) into h_out_scalars (nullable; pinned); nothing waits for the GPU — the scalars are
+ * valid once `stream` has executed the call.  Policy noise is drawn on the device.  Uses the fused data-parallel
+ * exchange when peers are attached. */
+int ddrl_sac_step_host(ddrl_sac_t sac, const void* h_block, int batch, uint64_t seed, float* h_out_scalars,
+                       float* d_out_q1, float* d_out_q2, float* d_out_logp, void* stream);
 int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
 /* Fused data-parallel mode (one process per GPU of one node, 2..8 ranks; replaces the NCCL all-reduce between
  * compute_grads and apply_grads, i.e. what `north_star` asks of algos/sac1's multi-learner setup, sac1.py:273-276):

@@ -28,6 +28,12 @@ class FrameRingOracle:
             self.ptr = (self.ptr + 1) % self.max_size
             self.size = min(self.size + 1, self.max_size)
 
+    def drawn_indices(self, ages):
+        """Ring positions of the transitions whose AGE (0 = the oldest complete window) is given: the sampler draws ages
+        uniformly over [0, size - S) so that no window crosses the write head once the ring has wrapped."""
+        oldest = self.ptr if self.size == self.max_size else 0
+        return (oldest + (self.stack - 1) + np.asarray(ages)) % self.max_size
+
     def sample_batch(self, idxs):
         S, cap = self.stack, self.max_size
         idxs = np.asarray(idxs)

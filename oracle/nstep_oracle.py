@@ -57,3 +57,19 @@ def make_sequences(opt, n, seed):
               for _ in range(opt.Ln)]
         out.append((oq, aq))
     return out
+
+
+def pack_rows(obs, acts, rews, done, Ln, D, A):
+    """Expected ring rows of ddrl_b200.NStepReplayBuffer: [n, Ln+1, ...], [n, Ln, ...], [n, Ln], [n, Ln] -> packed float32
+    rows [n, row_f] = [obs | acts | rews | done | 0-pad to 4 floats] (numpy assignment casts, as the reference's
+    `buffer[ptr] = np.array(..., dtype=np.float32)` does, sac_ray.py:52-68)."""
+    widths = [(Ln + 1) * D, Ln * A, Ln, Ln]
+    o = [0, widths[0], widths[0] + widths[1], widths[0] + widths[1] + Ln]
+    row_f = (sum(widths) + 3) // 4 * 4
+    n = int(np.asarray(rews).shape[0])
+    rows = np.zeros((n, row_f), dtype=np.float32)
+    rows[:, o[0]:o[0] + widths[0]] = np.asarray(obs).reshape(n, -1)
+    rows[:, o[1]:o[1] + widths[1]] = np.asarray(acts).reshape(n, -1)
+    rows[:, o[2]:o[2] + Ln] = np.asarray(rews).reshape(n, -1)
+    rows[:, o[3]:o[3] + Ln] = np.asarray(done).reshape(n, -1)
+    return rows

@@ -33,6 +33,9 @@ def test_reference_driver_runs_unchanged_against_ddrl_b200(ref_scripts, script, 
     out = compat.run_reference_script(path, argv, budget_s=12.0, time_scale=0.002, substitute=True)
     torch.cuda.synchronize()
     print(f"{script}: reference file sha256 {sha}; tasks {[(n, type(e).__name__ if e else None) for n, e in out['tasks']]}")
+    for n, e in out["tasks"]:
+        if e is not None:
+            print(f"  task {n} raised {type(e).__name__}: {e}")
     assert out["error"] is None, repr(out["error"])
     names = [n for n, _ in out["tasks"]]
     assert names.count("worker_rollout") >= 1 and "worker_train" in names and "worker_test" in names

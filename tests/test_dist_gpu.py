@@ -137,3 +137,50 @@ def test_global_uniform_gather_reads_peer_shards_over_p2p():
         for k in want:
             assert np.array_equal(out[k].view(np.uint32), want[k].view(np.uint32)), (r, k)
         assert drawn.min() >= 0 and drawn.max() < 520
+
+
+def _frames_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from ddrl_b200.dist import ShardedFrameReplayBuffer
+    from oracle.frames_oracle import FrameRingOracle
+    from oracle.replay_oracle import philox_indices
+    H, W, S, total, n = 16, 16, 4, 60, 45 + 10 * rank            # shard capacity 30: both shards wrap
+    g = np.random.Generator(np.random.PCG64(70 + rank))
+    frames = g.integers(0, 256, (n, H * W), dtype=np.uint8)
+    act, rew, done = g.integers(0, 5, n).astype(np.float32), g.standard_normal(n).astype(np.float32), (g.random(n) < 0.1).astype(np.float32)
+    srb = ShardedFrameReplayBuffer((H, W), S, total, mode="dedup", device=rank, seed=21)
+    ora = FrameRingOracle(H * W, S, srb.map.cap)
+    srb.store_frames(frames, act, rew, done)
+    ora.store_frames(frames, act, rew, done)
+    got = srb.sample_batch(64, return_idxs=True)
+    idx = got["idxs"].cpu().numpy()
+    want = ora.sample_batch(idx)
+    ok = np.array_equal(idx, ora.drawn_indices(philox_indices(64, ora.size - S, 21, 0, rank)))      # rng_stream = rank
+    ok = ok and all(np.array_equal(got[k].cpu().numpy().reshape(64, S, -1), want[k]) for k in ("obs1", "obs2"))
+    ok = ok and all(np.array_equal(got[k].cpu().numpy(), want[k]) for k in ("acts", "rews", "done"))
+    ret[rank] = (bool(ok), srb.get_counts(), srb.get_counts(global_=True), srb.map.cap)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_frame_replay_two_gpus():
+    """C4 shape over 2 GPUs: one frame ring per rank, local Philox sampling on sub-stream = rank, bit-exact against the
+    per-shard oracle; the only collective is the counter all-reduce of get_counts(global_=True)."""
+    import torch.multiprocessing as mp
+    import __graft_entry__
+    __graft_entry__.build()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_frames_worker, args=(2, port, ret), nprocs=2, join=True)
+    for r in (0, 1):
+        ok, local, glob, cap = ret[r]
+        assert ok and cap == 30
+        assert local == (1, 45 + 10 * r, 30)
+        assert glob == (2, 100, 60)

@@ -63,9 +63,36 @@ def test_dedup_stack_gather_bit_exact(FB, H, W, S, cap, n):
     # overlapping stacks: obs2[:, :-1] is obs1[:, 1:]
     assert torch.equal(got["obs2"][:, :-1], got["obs1"][:, 1:])
     # Philox-drawn indices stay inside the valid window and follow the restated stream
-    drawn = fb.sample_batch(256, return_idxs=True)["idxs"].cpu().numpy()
-    assert np.array_equal(drawn, (S - 1) + philox_indices(256, fb.size - S, 11, 0, 0))
-    assert drawn.min() >= S - 1 and drawn.max() <= fb.size - 2
+    got = fb.sample_batch(256, return_idxs=True)
+    drawn = got["idxs"].cpu().numpy()
+    ages = philox_indices(256, fb.size - S, 11, 0, 0)
+    assert np.array_equal(drawn, ora.drawn_indices(ages))
+    # no drawn window touches the write head: frames i-S+1 .. i+1 are S+1 consecutive AGES, all older than the newest frame
+    assert ages.min() >= 0 and ages.max() + S <= fb.size - 1
+    want = ora.sample_batch(drawn)
+    for k in ("obs1", "obs2"):
+        assert np.array_equal(got[k].cpu().numpy().reshape(256, S, -1), want[k]), k
+    for k in ("acts", "rews", "done"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+
+
+def test_dedup_store_device_tensors_and_overflow(FB):
+    """store_frames from CUDA tensors, more frames than slots in one call (only the last `capacity` survive)."""
+    H, W, S, cap, n = 16, 16, 3, 24, 61
+    g = np.random.Generator(np.random.PCG64(9))
+    frames = g.integers(0, 256, (n, H * W), dtype=np.uint8)
+    act, rew, done = g.integers(0, 4, n).astype(np.float32), g.standard_normal(n).astype(np.float32), (g.random(n) < 0.2).astype(np.float32)
+    fb, ora = FB((H, W), S, cap, mode="dedup", seed=3), FrameRingOracle(H * W, S, cap)
+    dev = torch.device("cuda")
+    fb.store_frames(torch.from_numpy(frames[:5]).to(dev), torch.from_numpy(act[:5]).to(dev), torch.from_numpy(rew[:5]).to(dev),
+                    torch.from_numpy(done[:5]).to(dev))
+    fb.store_frames(torch.from_numpy(frames[5:]).to(dev), torch.from_numpy(act[5:]).to(dev), torch.from_numpy(rew[5:]).to(dev),
+                    torch.from_numpy(done[5:]).to(dev))
+    ora.store_frames(frames, act, rew, done)
+    assert (fb.ptr, fb.size) == (ora.ptr, ora.size)
+    assert np.array_equal(fb.frames.cpu().numpy(), ora.frames)
+    for k in ("act", "rew", "done"):
+        assert np.array_equal(getattr(fb, k).cpu().numpy(), getattr(ora, k)), k
 
 
 def test_dedup_needs_a_full_stack(FB):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.nstep_oracle import NStepRingOracle, make_sequences
+from oracle.nstep_oracle import NStepRingOracle, make_sequences, pack_rows
 from oracle.replay_oracle import philox_indices
 
 pytestmark = pytest.mark.gpu
@@ -70,6 +70,37 @@ def test_store_batch_equals_stores_and_philox_stream(NB):
         want = ora.sample_batch(idxs=want_idx)
         for k in KEYS:
             assert same(got[k], want[k]), (call, k)
+
+
+def test_store_kernel_ring_rows_device_inputs_overflow_and_prefetch(NB):
+    """seg_store_rows: ring rows bit-equal to the expected packed rows for host AND CUDA-tensor inputs, wrap-around, a single
+    call with more rows than slots (only the last `capacity` survive, in order); prefetch() hands out sample_batch() in order."""
+    opt = SimpleNamespace(Ln=3, obs_shape=(5,), act_shape=(3,), buffer_size=16, batch_size=8, num_buffers=1)
+    seqs = make_sequences(opt, 70, 4)
+    obs = np.stack([np.stack([o[0] for o in oq]) for oq, _ in seqs]).astype(np.float32)
+    act = np.stack([np.stack([a for a, _, _ in aq]) for _, aq in seqs]).astype(np.float32)
+    rew = np.array([[r for _, r, _ in aq] for _, aq in seqs], dtype=np.float32)
+    done = np.array([[d for _, _, d in aq] for _, aq in seqs], dtype=np.float32)
+    rows = pack_rows(obs, act, rew, done, 3, 5, 3)
+    dev = torch.device("cuda")
+    rb = NB(opt, seed=1)
+    rb.store_batch(obs[:10], act[:10], rew[:10], done[:10])                                        # host arrays
+    rb.store_batch(*[torch.from_numpy(x[10:21]).to(dev) for x in (obs, act, rew, done)])           # CUDA tensors, wraps
+    want = np.zeros((16, rows.shape[1]), np.float32)
+    for i in range(21):
+        want[i % 16] = rows[i]
+    assert (rb.ptr, rb.size, rb.steps) == (21 % 16, 16, 21)
+    assert np.array_equal(rb.ring.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    rb.store_batch(obs[21:], act[21:], rew[21:], done[21:])                                        # 49 rows into 16 slots
+    for i in range(21, 70):
+        want[i % 16] = rows[i]
+    assert (rb.ptr, rb.size, rb.steps) == (70 % 16, 16, 70)
+    assert np.array_equal(rb.ring.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    ora_idx = [philox_indices(8, 16, 1, c, 0) for c in range(5)]
+    it = rb.prefetch(depth=3, batch_size=8)
+    for c in range(5):
+        got = next(it)
+        assert np.array_equal(got["rews"].cpu().numpy(), want[ora_idx[c]][:, 29:32]), c
 
 
 def test_empty_raises_like_the_reference(NB):

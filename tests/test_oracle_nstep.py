@@ -75,11 +75,13 @@ def test_vector_actions_and_empty():
 
 
 def test_packed_row_layout_round_trips_the_oracle_arrays():
-    """Host logic of ddrl_b200.NStepReplayBuffer (no GPU): the packed row [obs | acts | rews | done] holds exactly the
-    oracle's four arrays at the segment offsets ddrl_seg_sample is given, float64 / bool inputs cast like numpy assignment."""
+    """Row layout of ddrl_b200.NStepReplayBuffer (no GPU): the packed row [obs | acts | rews | done] the GPU tests expect in
+    the ring holds exactly the oracle's four arrays at the segment offsets ddrl_seg_store / ddrl_seg_sample are given,
+    float64 / bool inputs cast like numpy assignment."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "distributed-drl_b200"))
-    from ddrl_b200.nstep import pack_rows, row_layout
+    from ddrl_b200.nstep import row_layout
+    from oracle.nstep_oracle import pack_rows
     opt = SimpleNamespace(Ln=3, obs_shape=(5,), act_shape=(2,), buffer_size=8, batch_size=4, num_buffers=1)
     ora = NStepRingOracle(opt)
     seqs = make_sequences(opt, 6, 2)

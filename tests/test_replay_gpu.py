@@ -248,3 +248,133 @@ def test_full_size_round_trip_and_gather(RB, D, A, cap, B):
     rb.store_batch(obs[-100:], act[-100:], rew[-100:], nxt[-100:], done[-100:])
     first = rb.sample_batch(100, idxs=torch.arange(100, device=dev), device=True)
     assert torch.equal(first["obs1"], obs[-100:]) and rb.ptr == 100
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("D,A,cap,B,nb", [(24, 4, 200_000, 1024, 32), (376, 17, 50_000, 4096, 2), (8, 2, 300_000, 256, 512)])
+def test_every_gather_kernel_with_philox_indices(RB, monkeypatch, mode, D, A, cap, B, nb):
+    """DDRL_GATHER_MODE picks the kernel family (0 auto, 1 bulk-async + register drain, 2 register kernels, 3 TMA-only for
+    rows wider than 512 B): every one must return, for the Philox-drawn index stream, exactly the rows torch indexing does."""
+    monkeypatch.setenv("DDRL_GATHER_MODE", str(mode))
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(100 + D)
+    obs, nxt = torch.randn((cap, D), device=dev, generator=gen), torch.randn((cap, D), device=dev, generator=gen)
+    act, rew = torch.rand((cap, A), device=dev, generator=gen), torch.randn(cap, device=dev, generator=gen)
+    done = (torch.rand(cap, device=dev, generator=gen) < 0.05).float()
+    rb = RB(D, A, cap, seed=77, rng_stream=3)
+    rb.store_batch(obs, act, rew, nxt, done)
+    for call in range(2):
+        out = rb.sample_many(nb, B, return_idxs=True)
+        idx = out["idxs"].reshape(-1)
+        assert np.array_equal(idx.cpu().numpy(), philox_indices(nb * B, cap, 77, call, 3))
+        assert torch.equal(out["obs1"].reshape(-1, D), obs[idx]) and torch.equal(out["obs2"].reshape(-1, D), nxt[idx])
+        assert torch.equal(out["acts"].reshape(-1, A), act[idx])
+        assert torch.equal(out["rews"].reshape(-1), rew[idx]) and torch.equal(out["done"].reshape(-1), done[idx])
+    small = rb.sample_batch(B, device=True, return_idxs=True)            # one plain batch through the same family
+    assert torch.equal(small["obs1"], obs[small["idxs"]]) and torch.equal(small["rews"], rew[small["idxs"]])
+
+
+def test_c3_ring_at_the_configured_1e7_rows(RB):
+    """BASELINE.json configs[2]: obs 376, act 17, replay 1e7 rows (30.9 GB ring), batch 4096.  Inputs are regenerated
+    chunk by chunk from a counter-based recipe, so the check costs no second copy of the ring."""
+    D, A, cap, B, chunk = 376, 17, 10_000_000, 4096, 500_000
+    free, _ = torch.cuda.mem_get_info()
+    if free < 48e9:
+        pytest.skip("needs ~45 GB of free HBM")
+    dev = torch.device("cuda")
+
+    def make(lo, n):
+        gen = torch.Generator(device=dev).manual_seed(7_000 + lo // chunk)
+        return (torch.randn((n, D), device=dev, generator=gen), torch.rand((n, A), device=dev, generator=gen) * 2 - 1,
+                torch.randn(n, device=dev, generator=gen), torch.randn((n, D), device=dev, generator=gen),
+                (torch.rand(n, device=dev, generator=gen) < 0.01).float())
+
+    rb = RB(D, A, cap, seed=9)
+    for lo in range(0, cap, chunk):
+        rb.store_batch(*make(lo, chunk))
+    assert (rb.ptr, rb.size) == (0, cap) and rb.get_counts()[1] == cap
+    out = rb.sample_many(16, B, return_idxs=True)
+    idx = out["idxs"].reshape(-1)
+    assert np.array_equal(idx.cpu().numpy(), philox_indices(16 * B, cap, 9, 0, 0))
+    assert int(idx.max()) > 9_000_000                   # the draw really spans the 1e7 rows
+    o1, o2, ac, rw, dn = (out[k].reshape(16 * B, -1) for k in KEYS)
+    checked = 0
+    for lo in range(0, cap, chunk):
+        sel = ((idx >= lo) & (idx < lo + chunk)).nonzero().reshape(-1)
+        if sel.numel() == 0:
+            continue
+        obs, act, rew, nxt, done = make(lo, chunk)
+        j = idx[sel] - lo
+        assert torch.equal(o1[sel], obs[j]) and torch.equal(o2[sel], nxt[j]) and torch.equal(ac[sel], act[j])
+        assert torch.equal(rw[sel, 0], rew[j]) and torch.equal(dn[sel, 0], done[j])
+        checked += int(sel.numel())
+    assert checked == 16 * B
+
+
+def test_concurrent_producers_and_learner_equal_some_serial_order(RB):
+    """BASELINE config 5 / algos/sac1/sac1.py:195: many rollout workers store while the learner samples.  Four producer
+    threads, each on its own CUDA stream, store tagged batches (host arrays and CUDA tensors) into one buffer while the main
+    thread samples on a fifth stream.  Afterwards the ring must equal SOME serial order of the calls: every batch occupies
+    consecutive slots in its own row order, batches of one producer appear in call order, counters add up; and every row
+    a concurrent sample returned is a whole row some call stored (no torn rows)."""
+    import threading
+    D, A, cap, nprod, calls, nrows = 12, 3, 4096, 4, 60, 64
+    rb = RB(D, A, cap, seed=1)
+    dev = torch.device("cuda")
+
+    def rows(key0, n):                      # row fields are all functions of ONE key: a torn row is detectable
+        key = np.arange(key0, key0 + n, dtype=np.float32)
+        return (np.repeat(key[:, None], D, 1), np.repeat(-key[:, None], A, 1), key * 2, np.repeat(key[:, None] + 0.5, D, 1),
+                (key % 2).astype(np.float32))
+
+    rb.store_batch(*rows(1_000_000, 256))             # something to sample from the start
+    errors, stop = [], threading.Event()
+
+    def producer(p):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for c in range(calls):
+                    batch = rows(p * 100_000 + c * nrows, nrows)
+                    if (p + c) % 2:
+                        batch = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in batch]
+                    rb.store_batch(*batch)
+        except BaseException as e:          # noqa: BLE001
+            errors.append(e)
+
+    sampled = []
+    threads = [threading.Thread(target=producer, args=(p,)) for p in range(nprod)]
+    with torch.cuda.stream(torch.cuda.Stream()):
+        for t in threads:
+            t.start()
+        while any(t.is_alive() for t in threads):
+            sampled.append(rb.sample_batch(128, device=True))
+        for t in threads:
+            t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    total = 256 + nprod * calls * nrows
+    assert rb.get_counts()[1:] == (total, cap) and rb.ptr == total % cap
+    for s in sampled:                       # no torn rows
+        k = s["rews"] / 2
+        assert torch.equal(s["obs1"], k[:, None].expand(-1, D)) and torch.equal(s["obs2"], (k + 0.5)[:, None].expand(-1, D))
+        assert torch.equal(s["acts"], (-k)[:, None].expand(-1, A)) and torch.equal(s["done"], k % 2)
+    ring = rb.ring_arrays()
+    key = ring["rews_buf"] / 2
+    assert np.array_equal(ring["obs1_buf"], np.repeat(key[:, None], D, 1)) and np.array_equal(ring["acts_buf"], np.repeat(-key[:, None], A, 1))
+    # walk the ring from the oldest slot: whole batches, consecutive keys inside a batch, per-producer call order
+    order = np.roll(key, -rb.ptr).astype(np.int64)
+    last_call = {}
+    i = 0
+    while i < cap and order[i] >= 1_000_000:         # tail of the seed rows that survived (cap < total: they are gone)
+        i += 1
+    first = True
+    while i < cap:
+        p, c, j = order[i] // 100_000, (order[i] % 100_000) // nrows, (order[i] % 100_000) % nrows
+        n = nrows - j
+        assert first or j == 0, "a batch does not start at its first row"      # only the oldest batch may be cut by the wrap
+        run = order[i:i + n]
+        assert np.array_equal(run, order[i] + np.arange(len(run))), "rows of one batch are not consecutive"
+        assert c > last_call.get(p, -1), "batches of one producer out of call order"
+        last_call[p] = c
+        i += len(run)
+        first = False

@@ -234,6 +234,49 @@ def test_train_from_buffer_equals_sample_then_train(L):
     assert res[0][3] == res[1][3]          # sample_times / steps / size advance identically
 
 
+def test_host_block_path_and_cache_prefetch_equal_the_plain_calls(L):
+    """The reference-shaped host loop `batch = cache.q1.get(); agent.train(batch)` (algos/sac1/sac1.py:146-148): batches from
+    the prefetching Cache are the batches sample_batch() returns in the same order, and train() on such a host batch (one
+    native H2D + update + scalar read-back call) is bit-identical to train() on the same rows as CUDA tensors; a host batch
+    whose entry was REPLACED by the caller takes the generic path and trains on the new values."""
+    from ddrl_b200 import Cache, ReplayBuffer
+    D, A, hidden, B, n = 24, 4, (128, 128), 256, 3000
+    params = conditioned_params(D, A, hidden, seed=21)
+    g = np.random.Generator(np.random.PCG64(22))
+    rows = [g.standard_normal((n, D), dtype=np.float32), g.uniform(-1, 1, (n, A)).astype(np.float32),
+            g.standard_normal(n, dtype=np.float32), g.standard_normal((n, D), dtype=np.float32),
+            (g.random(n) < 0.05).astype(np.float32)]
+    res = []
+    for mode in ("device", "host-cache", "host-rebound"):
+        rb = ReplayBuffer(D, A, 4096, seed=5, rng_stream=1)
+        rb.store_batch(*rows)
+        learner = L(make_opt(D, A, hidden, B), "learner")
+        learner.set_weights(list(params), list(params.values()))
+        cache = Cache(rb, B, depth=3)
+        if mode != "device":
+            cache.start()
+        losses = []
+        for it in range(4):
+            if mode == "device":
+                batch = rb.sample_batch(B, device=True)
+                batch["rews"] = batch["rews"] * (2.0 if it == 2 else 1.0)
+            else:
+                batch = cache.q1.get()
+                assert isinstance(batch["obs1"], np.ndarray) and batch["obs1"].shape == (B, D)
+                if it == 2:
+                    if mode == "host-rebound":
+                        batch["rews"] = batch["rews"] * 2.0          # a NEW array: the pinned block is stale for this entry
+                    else:
+                        batch["rews"] *= 2.0                          # in place: still the block
+            out = learner.train(batch)
+            losses.append(out["scalars"].cpu().numpy().copy())
+        cache.end()
+        res.append((np.stack(losses), out["q1"].cpu().numpy().copy(), learner.get_flat_weights("main").cpu().numpy()))
+    for other in (1, 2):
+        assert np.array_equal(res[0][0], res[other][0]), other
+        assert np.array_equal(res[0][1], res[other][1]) and np.array_equal(res[0][2], res[other][2]), other
+
+
 @pytest.mark.parametrize("D,A,B,scale", [(24, 4, 1024, 1.0), (376, 17, 4096, 0.4)], ids=["C2-full", "C3-full"])
 def test_full_size_step_matches_oracle(L, D, A, B, scale):
     """BASELINE.json's full batch sizes (C2: 1024, C3: 4096 rows of the Humanoid shape) through the default tcgen05 path:

@@ -28,9 +28,19 @@ res = []
 shard, B, fb = 125_000, 512, 84 * 84
 # dedup: one frame per transition
 rb = FrameReplayBuffer((84, 84), 4, shard, mode="dedup", seed=1)
+z25 = torch.zeros(25_000, device=dev)
 for lo in range(0, shard, 25_000):
-    rb.store_frames(torch.randint(0, 256, (25_000, fb), dtype=torch.uint8, device=dev), torch.zeros(25_000, device=dev),
-                    torch.zeros(25_000, device=dev), torch.zeros(25_000, device=dev))
+    fr = torch.randint(0, 256, (25_000, fb), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); rb.store_frames(fr, z25, z25, z25); e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+res.append(dict(cfg="C4 dedup store_frames", rows=25_000, us=t * 1e6, GBs=2 * 25_000 * (fb + 12) / t / 1e9, frac=2 * 25_000 * (fb + 12) / t / 1e9 / peak))
+print(res[-1], flush=True)
+for n_small in (256, 2048):
+    t = timeit(lambda: rb.store_frames(fr[:n_small], z25[:n_small], z25[:n_small], z25[:n_small]))
+    res.append(dict(cfg="C4 dedup store_frames", rows=n_small, us=t * 1e6, GBs=2 * n_small * (fb + 12) / t / 1e9, frac=2 * n_small * (fb + 12) / t / 1e9 / peak))
+    print(res[-1], flush=True)
 for nb in (512, 8192):
     t = timeit(lambda: rb.sample_batch(nb))
     bytes_alg = nb * (5 * fb + 12 + 2 * 4 * fb + 12)      # read 5 frames + scalars, write two stacks + scalars
@@ -55,6 +65,13 @@ g = np.random.Generator(np.random.PCG64(0))
 for lo in range(0, 1_000_000, 100_000):
     nb_.store_batch(g.standard_normal((100_000, 9, 24), dtype=np.float32), g.standard_normal((100_000, 8, 4), dtype=np.float32),
                     g.standard_normal((100_000, 8), dtype=np.float32), np.zeros((100_000, 8), np.float32))
+dobs, dact, drew, ddone = (torch.randn((100_000, 9, 24), device=dev), torch.randn((100_000, 8, 4), device=dev), torch.randn((100_000, 8), device=dev),
+                           torch.zeros((100_000, 8), device=dev))
+for n_ in (1024, 100_000):
+    t = timeit(lambda: nb_.store_batch(dobs[:n_], dact[:n_], drew[:n_], ddone[:n_]))
+    bytes_alg = n_ * 2 * 4 * nb_.used
+    res.append(dict(cfg="N3 nstep store_batch (device rows)", rows=n_, us=t * 1e6, GBs=bytes_alg / t / 1e9, frac=bytes_alg / t / 1e9 / peak))
+    print(res[-1], flush=True)
 for B_ in (1024, 262144):
     t = timeit(lambda: nb_.sample_batch(B_, device=True))
     bytes_alg = B_ * 2 * 4 * nb_.used
