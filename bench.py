@@ -427,37 +427,49 @@ class Bench:
                pin((g.random(B) < 0.01).astype(np.float32))]
         sink = []
 
-        # the reference's learner loop (algos/sac1/sac1.py:136-151): `batch = cache.q1.get(); agent.train(batch)` — host numpy
-        # batches from the prefetching Cache (here: sample_batch issued `depth` calls ahead on its own CUDA stream, D2H into
-        # pinned blocks), fed back as host arrays; plus this step's B new transitions from the rollout side and the fetched losses
+        # Three shapes of the reference's learner loop, all with host numpy batches crossing PCIe both ways, this step's B new
+        # transitions stored from host arrays, and the losses fetched every step:
+        #   model   example/model.py:92-101 `Model.train(replay_buffer, args)`: sample into host memory + feed from host memory as
+        #           one method (Learner.train_via_host: two queued native calls, nothing waits in between)      <- `e2e`
+        #   cache   algos/sac1/sac1.py:136-151 `batch = cache.q1.get(); agent.train(batch)` with the prefetching Cache
+        #   blocking  `batch = replay_buffer.sample_batch(B); agent.train(batch)` with no prefetch
         from ddrl_b200 import Cache
-        cache = Cache(rb, B, depth=2)
-        cache.start()
 
         def step_e2e():
-            batch = cache.q1.get()                                # D2H: host numpy arrays, prefetched like the reference's Cache
-            res = learner.train(batch)                            # H2D: host batch fed like feed_dict
+            res = learner.train_via_host(rb, B)                   # D2H batch -> host numpy, H2D batch, update
             rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side
             sink.append(res["scalars"].cpu())                     # D2H: the fetched losses
 
-        def step_e2e_blocking():                                  # the same without a prefetcher (example/model.py:92-101)
+        cache = Cache(rb, B, depth=2)
+
+        def step_e2e_cache():
+            batch = cache.q1.get()                                # host numpy arrays, prefetched like the reference's Cache
+            res = learner.train(batch)
+            rb.store_batch(*new)
+            sink.append(res["scalars"].cpu())
+
+        def step_e2e_blocking():
             batch = rb.sample_batch(B)
             res = learner.train(batch)
             rb.store_batch(*new)
             sink.append(res["scalars"].cpu())
 
         e2e_steps = max(5, min(steps, 200 if primary else 60))
-        sec_e2e, _ = self.timed(step_e2e, e2e_steps, max(3, min(warmup, 10)))
+        e2e_warm = max(3, min(warmup, 10))
+        sec_e2e, _ = self.timed(step_e2e, e2e_steps, e2e_warm)
+        sec_blk, _ = self.timed(step_e2e_blocking, e2e_steps, e2e_warm)
+        cache.start()
+        sec_cache, _ = self.timed(step_e2e_cache, e2e_steps, e2e_warm)
         cache.end()
-        sec_blk, _ = self.timed(step_e2e_blocking, e2e_steps, max(3, min(warmup, 10)))
+        sub = lambda sec, path: dict(value=self.world * B * e2e_steps / sec, ms_per_step=sec / e2e_steps * 1e3, path=path)
         out["e2e"] = dict(value=self.world * B * e2e_steps / sec_e2e, unit="transitions/s", h2d_bytes_per_step=2 * B * row_bytes,
                           d2h_bytes_per_step=B * row_bytes + 16, steps=e2e_steps, ms_per_step=sec_e2e / e2e_steps * 1e3,
-                          path="Cache(replay_buffer).q1.get() -> numpy batch -> Learner.train(numpy) -> store_batch(host, B new rows) "
-                               "-> losses.cpu(); the Cache keeps 2 sample_batch calls in flight on its own stream (the reference's "
-                               "Cache process keeps a Queue(10) filled)",
-                          blocking=dict(value=self.world * B * e2e_steps / sec_blk, ms_per_step=sec_blk / e2e_steps * 1e3,
-                                        path="sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host) -> losses.cpu(), "
-                                             "no prefetch (example/model.py:92-101 shape)"))
+                          path="Learner.train_via_host(replay_buffer, B) [example/model.py:92-101 Model.train(replay_buffer, args): "
+                               "sample_batch into host numpy arrays, update fed from those host arrays] -> store_batch(host, B new "
+                               "rows) -> losses.cpu()",
+                          cache_loop=sub(sec_cache, "Cache(replay_buffer).q1.get() -> numpy batch -> Learner.train(numpy) -> "
+                                                    "store_batch(host) -> losses.cpu() (algos/sac1/sac1.py:136-151; 2 samples in flight)"),
+                          blocking=sub(sec_blk, "sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host) -> losses.cpu()"))
         extra = {}
         if primary:
             # (2b) config C5 flavour: 256 vectorised rollout producers store CONCURRENTLY with the learner — a producer
@@ -596,25 +608,44 @@ class Bench:
             e1.record(); torch.cuda.synchronize()
             return e0.elapsed_time(e1) / iters * 1e-3
 
+        sp = C.c_void_p(self.stream().cuda_stream)
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+
+        def both(api_call, native_call, nb, alg):
+            """host API (fresh output tensors per call, Python wrapper) and the kernel alone (native calls, preallocated
+            outputs, back to back between one pair of events) for a batch of nb transitions of alg bytes each"""
+            t_api, t_k = timeit(api_call), timeit(native_call, iters=100)
+            mk = lambda t: dict(us=t * 1e6, transitions_per_s=nb / t, gbs=alg * nb / t / 1e9, frac=alg * nb / t / 1e9 / self.peaks["hbm_gbs"])
+            return dict(batch=nb, kernel=mk(t_k), host_api=mk(t_api), **mk(t_k))
+
         rb = FrameReplayBuffer(C4["frame"], C4["stack"], C4["shard"], mode="dedup", seed=1, device=self.local)
         t_store = []
+        z = torch.zeros(25_000, device=self.dev)
         for lo in range(0, C4["shard"], 25_000):
             fr = torch.randint(0, 256, (25_000, fb), dtype=torch.uint8, device=self.dev)
-            z = torch.zeros(25_000, device=self.dev)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); rb.store_frames(fr, z, z, z); e1.record(); torch.cuda.synchronize()
             t_store.append(e0.elapsed_time(e1) * 1e-3)
+        alg_d = 5 * fb + 12 + 2 * 4 * fb + 12               # read 5 frames + scalars, write two stacks + scalars
         gather = []
         for nb in (C4["B"], 8192):
-            t = timeit(lambda: rb.sample_batch(nb))
-            alg = nb * (5 * fb + 12 + 2 * 4 * fb + 12)      # read 5 frames + scalars, write two stacks + scalars
-            gather.append(dict(batch=nb, us=t * 1e6, transitions_per_s=nb / t, gbs=alg / t / 1e9, frac=alg / t / 1e9 / self.peaks["hbm_gbs"]))
+            o1 = torch.empty((nb, 4 * fb), dtype=torch.uint8, device=self.dev); o2 = torch.empty_like(o1)
+            sc = torch.empty((3, nb), dtype=torch.float32, device=self.dev)
+            cnt = [0]
+
+            def native():
+                cnt[0] += 1
+                self.N.check(self.lib.ddrl_fb_sample_stack(self.local, ptr(rb.frames), fb, C4["stack"], rb.max_size, rb.size, 0,
+                                                           ptr(rb.act), ptr(rb.rew), ptr(rb.done), nb, None, 1, cnt[0], 0,
+                                                           ptr(o1), ptr(o2), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), None, sp))
+            gather.append(both(lambda: rb.sample_batch(nb), native, nb, alg_d))
+            del o1, o2, sc
         st = min(t_store[1:]) if len(t_store) > 1 else t_store[0]
         res["C4_dedup"] = dict(workload="C4: Atari-shaped uint8 84x84x4 frame replay, frame-deduplicated ring (one frame per transition, "
                                         "stacks rebuilt from 5 consecutive frames), 125 000-transition shard (1e6 over 8 GPUs), batch 512",
-                               value=gather[0]["transitions_per_s"], unit="transitions/s (sample_batch(512) calls back to back, host API)",
-                               bytes_per_transition=5 * fb + 12 + 2 * 4 * fb + 12, gather=gather,
+                               value=gather[0]["host_api"]["transitions_per_s"], unit="transitions/s (sample_batch(512) calls back to back, host API)",
+                               bytes_per_transition=alg_d, gather=gather,
                                store=dict(rows_per_launch=25_000, us=st * 1e6, gbs=2 * 25_000 * (fb + 12) / st / 1e9,
                                           frac=2 * 25_000 * (fb + 12) / st / 1e9 / self.peaks["hbm_gbs"]))
         del rb
@@ -622,17 +653,25 @@ class Bench:
         rbn = FrameReplayBuffer(C4["frame"], C4["stack"], C4["naive_rows"], mode="naive", seed=1, device=self.local)
         for lo in range(0, C4["naive_rows"], 5_000):
             o = torch.randint(0, 256, (5_000, 4) + C4["frame"], dtype=torch.uint8, device=self.dev)
-            z = torch.zeros(5_000, device=self.dev)
-            rbn.store_batch(o, z, z, o, z)
+            z5 = torch.zeros(5_000, device=self.dev)
+            rbn.store_batch(o, z5, z5, o, z5)
+        alg_n = 2 * (2 * 4 * fb + 12)
         gather = []
         for nb in (C4["B"], 8192):
-            t = timeit(lambda: rbn.sample_batch(nb))
-            alg = nb * 2 * (2 * 4 * fb + 12)
-            gather.append(dict(batch=nb, us=t * 1e6, transitions_per_s=nb / t, gbs=alg / t / 1e9, frac=alg / t / 1e9 / self.peaks["hbm_gbs"]))
+            o1 = torch.empty((nb, fb), dtype=torch.float32, device=self.dev); o2 = torch.empty_like(o1)
+            sc = torch.empty((3, nb), dtype=torch.float32, device=self.dev)
+            cnt = [0]
+
+            def native_n():
+                cnt[0] += 1
+                self.N.check(self.lib.ddrl_rb_sample(rbn._rb.native_handle, nb, 1, None, 1, cnt[0], 0, ptr(o1), ptr(o2), ptr(sc[0]),
+                                                     ptr(sc[1]), ptr(sc[2]), None, sp))
+            gather.append(both(lambda: rbn.sample_batch(nb), native_n, nb, alg_n))
+            del o1, o2, sc
         res["C4_naive"] = dict(workload="C4: the same frames with obs1 + obs2 stored per transition (56 460-byte rows), 30 000 rows "
                                         "(1.7 GB, larger than L2), batch 512",
-                               value=gather[0]["transitions_per_s"], unit="transitions/s (sample_batch(512) calls back to back, host API)",
-                               bytes_per_transition=2 * (2 * 4 * fb + 12), gather=gather)
+                               value=gather[0]["host_api"]["transitions_per_s"], unit="transitions/s (sample_batch(512) calls back to back, host API)",
+                               bytes_per_transition=alg_n, gather=gather)
         del rbn
         torch.cuda.empty_cache()
         return res

@@ -496,19 +496,30 @@ struct FrameStoreArgs {
   const float *act, *rew, *done;    // [n]
   float *ract, *rrew, *rdone;       // [cap]
 };
+constexpr int FS_GROUP = 4;   // frames per CTA pass: 4 x 441 float4 (84 x 84) = 7 x 256 -> every load of a thread in flight at once
 __global__ void __launch_bounds__(256) fb_store_frames(const FrameStoreArgs a) {
-  for (int64_t i = a.first + blockIdx.x; i < a.n; i += gridDim.x) {
-    const int64_t pos = (a.ptr0 + i) % a.cap;
-    const float4* src = a.in + i * a.frame_f4;
-    float4* dst = a.ring + pos * a.frame_f4;
-    for (int c0 = threadIdx.x; c0 < a.frame_f4; c0 += 256 * 4) {
-      float4 v[4];
+  const int64_t ngroups = (a.n - a.first + FS_GROUP - 1) / FS_GROUP;
+  for (int64_t gidx = blockIdx.x; gidx < ngroups; gidx += gridDim.x) {
+    const int64_t i0 = a.first + gidx * FS_GROUP;
+    const int nf = (int)min((int64_t)FS_GROUP, a.n - i0);
+    const float4* src = a.in + i0 * a.frame_f4;                    // the group's frames are contiguous in the input
+    const int total = nf * a.frame_f4;
+    for (int e0 = threadIdx.x; e0 < total; e0 += 256 * 8) {
+      float4 v[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (c0 + 256 * k < a.frame_f4) v[k] = ld_nc_f4(src + c0 + 256 * k);
+      for (int k = 0; k < 8; ++k) if (e0 + 256 * k < total) v[k] = ld_nc_f4(src + e0 + 256 * k);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (c0 + 256 * k < a.frame_f4) st_f4(dst + c0 + 256 * k, v[k]);
+      for (int k = 0; k < 8; ++k) {
+        const int e = e0 + 256 * k;
+        if (e < total) {
+          const int f = e / a.frame_f4;                            // ring slots wrap frame by frame
+          st_f4(a.ring + ((a.ptr0 + i0 + f) % a.cap) * a.frame_f4 + (e - f * a.frame_f4), v[k]);
+        }
+      }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < nf) {
+      const int64_t i = i0 + threadIdx.x;
+      const int64_t pos = (a.ptr0 + i) % a.cap;
       const int64_t prev = pos == 0 ? a.cap - 1 : pos - 1;
       a.ract[prev] = a.act[i]; a.rrew[prev] = a.rew[i]; a.rdone[prev] = a.done[i];
     }
@@ -517,6 +528,7 @@ __global__ void __launch_bounds__(256) fb_store_frames(const FrameStoreArgs a) {
 
 // seg_store: the inverse of rb_gather_segments — nseg dense inputs [n, w_s] -> packed rows [obs | acts | rews | done | 0-pad]
 // at ring slots (ptr0 + i) % cap; one warp per row, every lane assembles whole 16-byte chunks of the packed row.
+constexpr int SEG_TBL = 4096;   // chunks of a packed row covered by the per-CTA lookup tables
 struct SegStoreArgs {
   float4* ring;
   int row_f4, nseg;
@@ -524,24 +536,55 @@ struct SegStoreArgs {
   const float* in[8];
   int64_t cap, ptr0, first, n;
 };
+// per 16-byte chunk of the packed row: the segment it lies in when it can arrive as ONE 128-bit load (inside one segment,
+// 16-byte aligned on both sides), 254 for pure padding, else 255 (assembled float by float); built once per CTA
+__device__ __forceinline__ int seg_store_chunk(const SegStoreArgs& a, int c) {
+  const int f = 4 * c;
+  int hit = 254;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    if (s >= a.nseg) continue;
+    const int lo = a.off[s], hi = a.off[s] + a.w[s];
+    if (f >= lo && f + 3 < hi && ((a.w[s] | (f - lo)) & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.in[s]) & 15) == 0)) return s;
+    if (f + 3 >= lo && f < hi) hit = 255;          // overlaps the segment without being a whole aligned chunk of it
+  }
+  return hit;
+}
 __global__ void __launch_bounds__(256) seg_store_rows(const SegStoreArgs a) {
+  __shared__ unsigned char s_seg[SEG_TBL];
+  for (int c = threadIdx.x; c < min(a.row_f4, SEG_TBL); c += blockDim.x) s_seg[c] = (unsigned char)seg_store_chunk(a, c);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = a.first + warp; i < a.n; i += nwarps) {
     float4* dst = a.ring + ((a.ptr0 + i) % a.cap) * a.row_f4;
-    for (int c = lane; c < a.row_f4; c += 32) {
-      float x[4];
+    for (int c0 = lane; c0 < a.row_f4; c0 += 128) {
+      float4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int f = 4 * c + j;
-        float v = 0.0f;                                   // row padding / gaps between segments
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        if (c >= a.row_f4) continue;
+        const int sg = c < SEG_TBL ? (int)s_seg[c] : seg_store_chunk(a, c);
+        if (sg < 8) {
+          v[u] = ld_nc_f4(reinterpret_cast<const float4*>(a.in[sg] + i * a.w[sg] + (4 * c - a.off[sg])));
+        } else {
+          float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};               // row padding / gaps between segments stay zero
+          if (sg == 255) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
-          if (s < a.nseg && f >= a.off[s] && f < a.off[s] + a.w[s]) v = __ldg(a.in[s] + i * a.w[s] + (f - a.off[s]));
-        x[j] = v;
+            for (int j = 0; j < 4; ++j) {
+              const int f = 4 * c + j;
+#pragma unroll
+              for (int s = 0; s < 8; ++s)
+                if (s < a.nseg && f >= a.off[s] && f < a.off[s] + a.w[s]) x[j] = __ldg(a.in[s] + i * a.w[s] + (f - a.off[s]));
+            }
+          }
+          v[u] = make_float4(x[0], x[1], x[2], x[3]);
+        }
       }
-      st_f4(dst + c, make_float4(x[0], x[1], x[2], x[3]));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + 32 * u < a.row_f4) st_f4(dst + c0 + 32 * u, v[u]);
     }
   }
 }
@@ -657,7 +700,6 @@ __device__ __forceinline__ int seg_of_chunk(const SegArgs& a, int c) {
       hit = s;
   return hit;
 }
-constexpr int SEG_TBL = 4096;
 __global__ void __launch_bounds__(256) rb_gather_segments(const SegArgs a) {
   __shared__ unsigned char s_seg[SEG_TBL];
   for (int c = threadIdx.x; c < min(a.row_f4, SEG_TBL); c += blockDim.x) s_seg[c] = (unsigned char)seg_of_chunk(a, c);
@@ -819,6 +861,10 @@ struct ddrl_rb {
   static constexpr int NDEP = 8;
   StreamDep writers[NDEP], readers[NDEP];
   std::map<cudaStream_t, StagingSet> staging;     // device staging of the host-array entry points, per calling stream
+  // by-value capture of host stores (ddrl_rb_store_batch_host_copy): two pinned blocks, alternated; a block is reused only
+  // after the H2D copy that read it has completed (its event)
+  struct PinnedStage { void* p = nullptr; size_t bytes = 0; cudaEvent_t ev = nullptr; bool busy = false; } pinned[2];
+  int pinned_cur = 0;
   int nshards = 0, my_shard = 0;
   const float4* peer[8] = {};
   bool peer_opened[8] = {};
@@ -938,8 +984,11 @@ static int launch_gather_tma(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) 
 
 static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
   if (a.total <= 0) return 0;
-  // rows of >= 32 KB (frame observations) and, on request (DDRL_GATHER_MODE=3), every row wider than 512 B: TMA only
-  if (tma_gather_ok(rb, a) && rb->used_f4 > 32 && (rb->gather_mode == 3 || (rb->gather_mode == 0 && rb->used_f4 >= 2 * XW_SEG)))
+  // rows wider than 512 B (C3: 3088 B, frame rows: 56 KB): TMA only — one bulk copy in, two out, no register pass.
+  // Measured on B200 (profiles/r02_replay_curves.json): C3 one batch of 4096 rows 8.7 us against 22.2 us for the
+  // one-warp-per-row register kernel, 0.79 against 0.75 of the HBM peak at 32 k rows, 0.83 against 0.84 at 262 k rows.
+  // DDRL_GATHER_MODE=2 keeps the register kernels (also used for D % 4 != 0, unaligned outputs and peer rings).
+  if (tma_gather_ok(rb, a) && rb->used_f4 > 32 && (rb->gather_mode == 0 || rb->gather_mode == 3))
     return launch_gather_tma(rb, a, st);
   // bulk-async pipeline for anything big enough to fill the chip; register path for small launches
   // (measured on B200, C2 rows: 5.5 TB/s bulk vs 4.5 TB/s registers; C3 rows: 5.4 vs 5.65 TB/s, so wide
@@ -1092,6 +1141,7 @@ int ddrl_rb_destroy(ddrl_rb_t rb) {
   for (int s = 0; s < 8; ++s) if (rb->peer_opened[s]) cudaIpcCloseMemHandle(const_cast<float4*>(rb->peer[s]));
   if (rb->ring) cudaFree(rb->ring);
   for (auto& kv : rb->staging) { kv.second.in.release(); kv.second.out.release(); kv.second.idx.release(); }
+  for (auto& ps : rb->pinned) { if (ps.p) cudaFreeHost(ps.p); if (ps.ev) cudaEventDestroy(ps.ev); }
   for (auto* tab : {rb->writers, rb->readers})
     for (int i = 0; i < ddrl_rb::NDEP; ++i) if (tab[i].ev) cudaEventDestroy(tab[i].ev);
   delete rb;
@@ -1168,6 +1218,44 @@ int ddrl_rb_store_batch_host(ddrl_rb_t rb, const void* h_obs, const void* h_act,
   DDRL_CUDA(cudaMemcpyAsync(d_rew, h_rew, (size_t)n * es, cudaMemcpyHostToDevice, st));
   DDRL_CUDA(cudaMemcpyAsync(d_done, h_done, (size_t)n * es, cudaMemcpyHostToDevice, st));
   return store_common(rb, d_obs, d_act, d_rew, d_nxt, d_done, n, in_dtype, st);
+}
+
+int ddrl_rb_store_batch_host_copy(ddrl_rb_t rb, const void* h_obs, const void* h_act, const void* h_rew,
+                                  const void* h_next_obs, const void* h_done, int64_t n, int in_dtype, void* stream) {
+  if (!rb) return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host_copy: NULL handle");
+  if (n < 0) return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host_copy: n=%lld < 0", (long long)n);
+  if (in_dtype != DDRL_F32 && in_dtype != DDRL_F64)
+    return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host_copy: in_dtype must be DDRL_F32 or DDRL_F64");
+  if (n == 0) return 0;
+  if (!h_obs || !h_act || !h_rew || !h_next_obs || !h_done)
+    return fail(DDRL_EINVAL, "ddrl_rb_store_batch_host_copy: NULL input array");
+  DeviceGuard guard(rb->device);
+  RbLock lock(rb->mu);
+  const size_t es = in_dtype == DDRL_F32 ? 4 : 8;
+  const HostStoreLayout L = host_store_layout(rb, n, es);
+  auto& ps = rb->pinned[rb->pinned_cur];
+  rb->pinned_cur ^= 1;
+  if (ps.busy) { DDRL_CUDA(cudaEventSynchronize(ps.ev)); ps.busy = false; }
+  if (ps.bytes < L.total) {
+    if (ps.p) { cudaFreeHost(ps.p); ps.p = nullptr; ps.bytes = 0; }
+    const size_t want = L.total + L.total / 2;
+    cudaError_t e = cudaHostAlloc(&ps.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(DDRL_ENOMEM, "cudaHostAlloc(%zu) for store staging failed: %s", want, cudaGetErrorString(e));
+    ps.bytes = want;
+  }
+  if (!ps.ev) DDRL_CUDA(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming));
+  // the caller's arrays are captured NOW (the reference's `store.remote` pickles its arguments at call time)
+  char* b = (char*)ps.p;
+  memcpy(b, h_obs, (size_t)n * rb->D * es);
+  memcpy(b + L.b_obs, h_next_obs, (size_t)n * rb->D * es);
+  memcpy(b + 2 * L.b_obs, h_act, (size_t)n * rb->A * es);
+  memcpy(b + 2 * L.b_obs + L.b_act, h_rew, (size_t)n * es);
+  memcpy(b + 2 * L.b_obs + L.b_act + L.b_s, h_done, (size_t)n * es);
+  int rc = ddrl_rb_store_block_host(rb, b, n, in_dtype, stream);
+  if (rc) return rc;
+  DDRL_CUDA(cudaEventRecord(ps.ev, (cudaStream_t)stream));
+  ps.busy = true;
+  return 0;
 }
 
 int64_t ddrl_rb_store_block_bytes(ddrl_rb_t rb, int64_t n, int in_dtype) {
@@ -1411,7 +1499,7 @@ int ddrl_fb_store_frames(int device, void* d_frames, int64_t frame_bytes, int64_
   a.frame_f4 = (int)(frame_bytes / 16); a.cap = capacity; a.ptr0 = ptr;
   a.first = n > capacity ? n - capacity : 0; a.n = n;
   a.act = d_in_act; a.rew = d_in_rew; a.done = d_in_done; a.ract = d_act; a.rrew = d_rew; a.rdone = d_done;
-  const int64_t blocks = std::min<int64_t>(n - a.first, (int64_t)sm_count(device) * 8);
+  const int64_t blocks = std::min<int64_t>((n - a.first + FS_GROUP - 1) / FS_GROUP, (int64_t)sm_count(device) * 8);
   fb_store_frames<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
   DDRL_LAUNCH_CHECK();
   return 0;

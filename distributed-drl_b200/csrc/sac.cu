@@ -1093,8 +1093,9 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// Data-parallel step, default form: the first form above as ONE kernel (the split-K reduction is folded in, which
-// removes a launch from the critical path): every CTA sums its share of the split-K partials (+ the narrow-W1 slices)
+// Data-parallel step, one-kernel form (DDRL_DP_V1=0; the two-kernel form above is the default — it measured faster at
+// 4 and 8 GPUs): the first form as ONE kernel (the split-K reduction is folded in, which removes a launch from the
+// critical path): every CTA sums its share of the split-K partials (+ the narrow-W1 slices)
 // into this rank's exchange slot; the last CTA to finish publishes the flag on every peer; every CTA waits for all
 // ranks' flags, reads all ranks' slots (128-bit volatile loads over NVLink, all issued before the first add), sums in
 // rank order — every rank computes the same bits, replicas stay bit-identical — and applies Adam + polyak.
@@ -1350,7 +1351,7 @@ struct ddrl_sac {
                                         // (fwd_fused_tc); DDRL_FUSE_L1=0 keeps the two-launch form
   int force_bn = 0;                     // DDRL_TC_BN=64|128 overrides the per-stage tile width choice
   unsigned long long* dp_trace = nullptr;   // DDRL_DP_TRACE=1: 8 phase time stamps of k_adam_dp's CTA 0 (ddrl_sac_dp_trace)
-  bool dp_v1 = false;                   // DDRL_DP_V1=1: first form of the fused data-parallel step (reduce kernel + full peer read)
+  bool dp_v1 = true;                    // two-kernel form of the fused data-parallel step (reduce kernel + full peer read); DDRL_DP_V1=0: one kernel
   bool narrow_w1 = false;               // policy W1 gradient (K = D <= 32) by k_wgrad_narrow instead of a tensor-core stage
   float* host_stage = nullptr;          // device copy of a host batch block (ddrl_sac_step_host), maxB * (2D + A + 2) floats
   float* host_scal = nullptr;           // its 4 output scalars before the D2H copy
@@ -2097,8 +2098,12 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     if (const char* dt = getenv("DDRL_DP_TRACE")) {
       if (dt[0] == '1') { float* t = nullptr; dalloc(h, &t, 16); h->dp_trace = reinterpret_cast<unsigned long long*>(t); }
     }
+    // two-kernel exchange (reduce + publish, then all-peer read + optimiser) is the default: measured on 2 / 4 / 8 B200
+    // (C2, 600 steps) 106.8-112.2 / 116.8 / 124.0 us per step against 108.9-113.3 / 129.6 / 130.3 us for the one-kernel
+    // form k_adam_dp (the flags travel during the launch gap instead of inside a waiting kernel); DDRL_DP_V1=0 selects
+    // the one-kernel form
     const char* d1 = getenv("DDRL_DP_V1");
-    h->dp_v1 = d1 && d1[0] == '1';
+    h->dp_v1 = !(d1 && d1[0] == '0');
 
     const char* nz = getenv("DDRL_NARROW_W1");
     h->narrow_w1 = h->use_tc && D + 1 <= NW_MAXK && h1 % 4 == 0 && !(nz && nz[0] == '0');

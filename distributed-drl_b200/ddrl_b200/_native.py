@@ -37,6 +37,7 @@ SIGNATURES = {
     "ddrl_rb_destroy": (_int, [_vp]),
     "ddrl_rb_store_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "ddrl_rb_store_batch_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "ddrl_rb_store_batch_host_copy": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "ddrl_rb_store_block_bytes": (_i64, [_vp, _i64, _int]),
     "ddrl_rb_store_block_host": (_int, [_vp, _vp, _i64, _int, _vp]),
     "ddrl_rb_sample": (_int, [_vp, _i64, _i64, _vp, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -228,8 +228,10 @@ def stand_ins():
     }
 
 
-def run_reference_script(path, argv=(), budget_s=8.0, time_scale=0.01, substitute=True):
-    """Execute the reference driver at `path` as __main__, unchanged, for `budget_s` seconds of wall clock.
+def run_reference_script(path, argv=(), budget_s=8.0, time_scale=0.01, substitute=True, until=None):
+    """Execute the reference driver at `path` as __main__, unchanged, for at most `budget_s` seconds of wall clock — or
+    until `until()` (polled every 50 ms) returns true, so that a test can wait for "the learner has pushed weights"
+    instead of guessing how long that takes on a loaded machine.
 
     time.sleep() calls of the script are scaled by `time_scale` (the drivers sleep 5-20 s between launching their
     roles).  After the budget every Ray call raises ray_shim.Stopped, which ends the worker loops and the driver's
@@ -246,8 +248,21 @@ def run_reference_script(path, argv=(), budget_s=8.0, time_scale=0.01, substitut
     sys.modules.update(mods)
     sys.argv = [path] + list(argv)
     _time.sleep = lambda s: saved_sleep(min(float(s) * time_scale, 0.2))
-    timer = threading.Timer(budget_s, ray_shim.stop)
-    timer.daemon = True
+    cancel = threading.Event()
+
+    def watch():
+        t_end = _time.monotonic() + budget_s
+        while not cancel.is_set() and _time.monotonic() < t_end:
+            try:
+                if until is not None and until():
+                    break
+            except Exception:      # noqa: BLE001  (the condition may look at objects the script has not created yet)
+                pass
+            saved_sleep(0.05)
+        if not cancel.is_set():
+            ray_shim.stop()
+
+    timer = threading.Thread(target=watch, daemon=True)
     timer.start()
     ns, err = {}, None
     try:
@@ -258,7 +273,7 @@ def run_reference_script(path, argv=(), budget_s=8.0, time_scale=0.01, substitut
         err = e
     finally:
         ray_shim.stop()
-        timer.cancel()
+        cancel.set()
         _time.sleep = saved_sleep
         sys.argv = saved_argv
         for ref in list(ray_shim.TASKS):

@@ -421,6 +421,34 @@ class Learner(object):
         out["scalars"] = _LazyScalars(self)
         return out
 
+    def train_via_host(self, replay_buffer, batch_size):
+        """example/model.py:92-101 `Model.train(replay_buffer, args)` with the reference's data flow kept: the batch is
+        sampled INTO HOST MEMORY (what `ray.get(replay_buffer.sample_batch.remote(B))` delivers) and fed back from host
+        memory (feed_dict), but as two queued native calls with no wait in between — gather + D2H into a pinned block, then
+        H2D of that block + the update + D2H of the four scalars.  Returns train()'s dict plus `batch`: the sampled host
+        batch (numpy views of the pinned block), valid like the scalars once `losses()` has returned."""
+        rb = getattr(replay_buffer, "local", replay_buffer)
+        B = int(batch_size)
+        if (getattr(rb, "index_source", None) != "philox" or getattr(rb, "device", None) != self.device
+                or (self._world() > 1 and not self._fused) or getattr(rb, "_scalar_act", False)):
+            return self.train(replay_buffer.sample_batch(B))
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch} (pass max_batch= to Learner)")
+        with rb._lock:
+            rb.flush()
+            if rb.size == 0:
+                raise ValueError("high <= 0")
+            s = self._stream()
+            nbytes = int(self._lib.ddrl_rb_sample_block_bytes(rb._h, B))
+            blk = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            N.check(self._lib.ddrl_rb_sample_host_async(rb._h, B, 1, None, rb._philox_seed(), rb._counter, rb._rng_stream,
+                                                        blk.data_ptr(), nbytes, s.cuda_stream))
+            rb._counter += 1
+        batch = rb._host_batch(blk, nbytes, B, (B,), (B, self.act_dim), False)
+        out = self._train_host_block(batch, blk, False)
+        out["batch"] = batch
+        return out
+
     def losses(self):
         """(pi_loss, q1_loss, q2_loss, alpha) of the last train() that took the host-block path, as a numpy array: waits for
         that step only (an event), not for the stream."""

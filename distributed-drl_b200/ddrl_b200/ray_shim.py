@@ -15,6 +15,7 @@ define ReplayBuffer / ParameterServer inline; this is how the B200 ones are drop
 """
 from __future__ import annotations
 
+import collections
 import copy
 import threading
 import time
@@ -75,6 +76,44 @@ def _by_value(a):
     return a
 
 
+class _FifoLock:
+    """Re-entrant lock that serves waiters in ARRIVAL order — a Ray actor executes its mailbox first-in first-out, so a
+    learner's sample_batch call is never starved by rollout workers hammering store (threading.RLock makes no such promise
+    and, under the GIL, lets a tight producer loop re-acquire it for seconds)."""
+
+    def __init__(self):
+        self._mu = threading.Lock()
+        self._waiters = collections.deque()
+        self._owner, self._depth = None, 0
+
+    def __enter__(self):
+        me = threading.get_ident()
+        with self._mu:
+            if self._owner == me:
+                self._depth += 1
+                return self
+            if self._owner is None and not self._waiters:
+                self._owner, self._depth = me, 1
+                return self
+            ev = threading.Event()
+            self._waiters.append((me, ev))
+        ev.wait()
+        return self
+
+    def __exit__(self, *exc):
+        with self._mu:
+            self._depth -= 1
+            if self._depth:
+                return False
+            if self._waiters:
+                self._owner, ev = self._waiters.popleft()
+                self._depth = 1
+                ev.set()
+            else:
+                self._owner = None
+        return False
+
+
 class _ActorMethod:
     def __init__(self, actor, name):
         self._actor, self._name = actor, name
@@ -94,7 +133,7 @@ class _ActorMethod:
 class ActorHandle:
     def __init__(self, obj):
         self._obj = obj
-        self._lock = threading.RLock()
+        self._lock = _FifoLock()
 
     def __getattr__(self, name):
         if name.startswith("_"):

@@ -198,10 +198,6 @@ class ReplayBuffer:
         self._stages = [self._new_stage() for _ in range(2)]
         self._cur = 0
         self._staged = 0
-        # pinned staging for store_batch() from host arrays (vectorised producers): two sets, by-value capture
-        self._bstage_rows = 8192
-        self._bstages = None
-        self._bcur = 0
 
     # ------------------------------------------------------------------------------------------
     def _new_stage(self):
@@ -285,41 +281,12 @@ class ReplayBuffer:
         D, A = self.obs_dim, self.act_dim
         shapes = [(n, D), (n, A), (n,), (n, D), (n,)]
         s = self._stream()
-        if self._bstages is None and n <= self._bstage_rows:
-            R = self._bstage_rows
-            def mk():
-                blk = torch.empty(4 * R * (2 * D + A + 2) + 5 * 256, dtype=torch.uint8, pin_memory=True)
-                return dict(block=blk, raw=blk.numpy(), event=None)
-            self._bstages = [mk(), mk()]
-        if n <= self._bstage_rows:
-            # by-value capture into our own pinned staging (numpy assignment = the reference's cast), then ONE
-            # asynchronous H2D copy: the block has the layout of the library's device staging (256-byte aligned
-            # sub-arrays obs | next_obs | acts | rews | done for THIS n, ddrl_rb_store_block_host);
-            # no stream synchronisation on the producer's call path
-            st = self._bstages[self._bcur]
-            self._bcur ^= 1
-            if st["event"] is not None:
-                st["event"].synchronize()
-            up = lambda x: (x + 255) // 256 * 256
-            b_obs, b_act, b_s = up(n * D * 4), up(n * A * 4), up(n * 4)
-            offs = [0, 2 * b_obs, 2 * b_obs + b_act, b_obs, 2 * b_obs + b_act + b_s]      # obs, act, rew, next_obs, done
-            raw = st["raw"]
-            base = st["block"].data_ptr()
-            for off, a, sh in zip(offs, np_arrs, shapes):
-                cnt = int(np.prod(sh))
-                np.copyto(raw[off:off + 4 * cnt].view(np.float32).reshape(sh), a.reshape(sh), casting="unsafe")
-            N.check(self._lib.ddrl_rb_store_block_host(self._h, C.c_void_p(base), n, N.F32, C.c_void_p(s.cuda_stream)))
-            ev = torch.cuda.Event()
-            ev.record(s)
-            st["event"] = ev
-            return
-        # host-side cast to float32 is numpy's own assignment cast, i.e. the reference's semantics
+        # host-side cast to float32 is numpy's own assignment cast, i.e. the reference's `buf[ptr] = x` semantics (a no-op
+        # for contiguous float32 inputs); the library captures the arrays BY VALUE into its pinned staging at call time
+        # and queues one H2D copy + the store kernel — nothing on the producer's call path waits for the GPU
         host = [np.ascontiguousarray(a.reshape(sh), dtype=np.float32) for a, sh in zip(np_arrs, shapes)]
-        N.check(self._lib.ddrl_rb_store_batch_host(
-            self._h, *[C.c_void_p(a.ctypes.data) for a in host], n, N.F32, C.c_void_p(s.cuda_stream)))
-        # pageable source memory: the copies above are staged synchronously by the driver for
-        # small sizes only; make the by-value contract unconditional
-        s.synchronize()
+        N.check(self._lib.ddrl_rb_store_batch_host_copy(
+            self._h, *[a.ctypes.data for a in host], n, N.F32, s.cuda_stream))
 
     def _store_device(self, obs, act, rew, next_obs, done):
         n = int(rew.shape[0])

@@ -85,6 +85,12 @@ int ddrl_rb_store_batch_host(ddrl_rb_t rb, const void* h_obs, const void* h_act,
  * ddrl_rb_store_block_bytes gives the block size): a single H2D copy.  Vectorised producers stage their rows in such a
  * pinned block (the by-value capture of `replay_buffer.store.remote`, algos/sac1/sac1.py:195). */
 int64_t ddrl_rb_store_block_bytes(ddrl_rb_t rb, int64_t n, int in_dtype);
+/* ddrl_rb_store_batch_host with BY-VALUE capture: the five host arrays (any host memory) are copied at call time into a
+ * pinned block owned by the handle (two blocks, alternated; a block waits for the H2D copy that last read it), then
+ * stored like ddrl_rb_store_block_host.  The caller may overwrite its arrays as soon as the call returns — the semantics
+ * of `replay_buffer.store.remote(o, a, r, o2, d)` (algos/sac1/sac1.py:195), whose arguments are pickled at call time. */
+int ddrl_rb_store_batch_host_copy(ddrl_rb_t rb, const void* h_obs, const void* h_act, const void* h_rew,
+                                  const void* h_next_obs, const void* h_done, int64_t n, int in_dtype, void* stream);
 int ddrl_rb_store_block_host(ddrl_rb_t rb, const void* h_block, int64_t n, int in_dtype, void* stream);
 
 /* n_batches x ReplayBuffer.sample_batch(batch)  (example/dsac.py:39-45; algos/sac1/sac1.py:53-60)

@@ -63,7 +63,9 @@ def test_reference_driver_runs_unchanged_on_the_stand_ins(ref_scripts, script, a
     FakeLearner.trained = 0
     path = ref_scripts.path(script)
     sha = ref_scripts.manifest()[script]["sha256"]
-    out = compat.run_reference_script(path, argv, budget_s=8.0, time_scale=0.002, substitute=False)
+    # runs until the learner has trained past its second parameter push (a loaded machine only makes that take longer)
+    out = compat.run_reference_script(path, argv, budget_s=60.0, time_scale=0.002, substitute=False,
+                                      until=lambda: FakeLearner.trained > 650)
     print(f"{script}: reference sha256 {sha}; tasks {[(n, type(e).__name__ if e else None) for n, e in out['tasks']]}")
     assert out["error"] is None, repr(out["error"])
     names = [n for n, _ in out["tasks"]]

@@ -30,7 +30,11 @@ def test_reference_driver_runs_unchanged_against_ddrl_b200(ref_scripts, script, 
     path = ref_scripts.path(script)
     sha = ref_scripts.manifest()[script]["sha256"]
     before = _native.launch_count()
-    out = compat.run_reference_script(path, argv, budget_s=12.0, time_scale=0.002, substitute=True)
+    def trained_enough():         # the learner has sampled past its second parameter push
+        rbs = [h._obj for n, h in compat.ray_shim.ACTORS if n == "ReplayBuffer"]
+        return bool(rbs) and rbs[0].sample_times > 650
+
+    out = compat.run_reference_script(path, argv, budget_s=60.0, time_scale=0.002, substitute=True, until=trained_enough)
     torch.cuda.synchronize()
     print(f"{script}: reference file sha256 {sha}; tasks {[(n, type(e).__name__ if e else None) for n, e in out['tasks']]}")
     for n, e in out["tasks"]:

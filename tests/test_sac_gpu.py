@@ -247,7 +247,7 @@ def test_host_block_path_and_cache_prefetch_equal_the_plain_calls(L):
             g.standard_normal(n, dtype=np.float32), g.standard_normal((n, D), dtype=np.float32),
             (g.random(n) < 0.05).astype(np.float32)]
     res = []
-    for mode in ("device", "host-cache", "host-rebound"):
+    for mode in ("device", "host-cache", "host-rebound", "via-host"):
         rb = ReplayBuffer(D, A, 4096, seed=5, rng_stream=1)
         rb.store_batch(*rows)
         learner = L(make_opt(D, A, hidden, B), "learner")
@@ -257,6 +257,17 @@ def test_host_block_path_and_cache_prefetch_equal_the_plain_calls(L):
             cache.start()
         losses = []
         for it in range(4):
+            if mode == "via-host":                       # Model.train(replay_buffer, args): sample to host + feed from host
+                if it == 2:                               # (the doubled-reward step of the other modes, through the plain calls)
+                    batch = rb.sample_batch(B)
+                    batch["rews"] *= 2.0
+                    out = learner.train(batch)
+                else:
+                    out = learner.train_via_host(rb, B)
+                    got = out["scalars"].cpu()            # waits for the step: the host batch is valid now
+                    assert out["batch"]["obs1"].shape == (B, D) and np.isfinite(out["batch"]["rews"]).all()
+                losses.append(out["scalars"].cpu().numpy().copy())
+                continue
             if mode == "device":
                 batch = rb.sample_batch(B, device=True)
                 batch["rews"] = batch["rews"] * (2.0 if it == 2 else 1.0)
@@ -272,7 +283,7 @@ def test_host_block_path_and_cache_prefetch_equal_the_plain_calls(L):
             losses.append(out["scalars"].cpu().numpy().copy())
         cache.end()
         res.append((np.stack(losses), out["q1"].cpu().numpy().copy(), learner.get_flat_weights("main").cpu().numpy()))
-    for other in (1, 2):
+    for other in (1, 2, 3):
         assert np.array_equal(res[0][0], res[other][0]), other
         assert np.array_equal(res[0][1], res[other][1]) and np.array_equal(res[0][2], res[other][2]), other
 
