@@ -246,6 +246,11 @@ def run_reference_script(path, argv=(), budget_s=8.0, time_scale=0.01, substitut
     saved = {k: sys.modules.get(k) for k in mods}
     saved_argv, saved_sleep = sys.argv, _time.sleep
     sys.modules.update(mods)
+    # every Ray role is a thread of THIS process here: with CPython's default 5 ms switch interval each hand-over of an
+    # actor's lock to a waiting thread costs up to 5 ms whenever another role (worker_test's evaluation loop) is computing,
+    # which throttles the learner to a few updates per second; 0.2 ms keeps the roles interleaved like separate processes
+    saved_switch = sys.getswitchinterval()
+    sys.setswitchinterval(2e-4)
     sys.argv = [path] + list(argv)
     _time.sleep = lambda s: saved_sleep(min(float(s) * time_scale, 0.2))
     cancel = threading.Event()
@@ -275,6 +280,7 @@ def run_reference_script(path, argv=(), budget_s=8.0, time_scale=0.01, substitut
         ray_shim.stop()
         cancel.set()
         _time.sleep = saved_sleep
+        sys.setswitchinterval(saved_switch)
         sys.argv = saved_argv
         for ref in list(ray_shim.TASKS):
             t = getattr(ref, "_thread", None)
