@@ -448,6 +448,16 @@ class Bench:
             rb.store_batch(*new)
             sink.append(res["scalars"].cpu())
 
+        prev = [None]
+
+        def step_e2e_pipelined():                                 # the cache loop with the losses of step k fetched after step
+            batch = cache.q1.get()                                # k + 1 has been queued (one read-back per step, one step late)
+            res = learner.train(batch)
+            rb.store_batch(*new)
+            if prev[0] is not None:
+                sink.append(prev[0]())                        # waits for step k - 1 only
+            prev[0] = learner.losses_async()
+
         def step_e2e_blocking():
             batch = rb.sample_batch(B)
             res = learner.train(batch)
@@ -460,6 +470,7 @@ class Bench:
         sec_blk, _ = self.timed(step_e2e_blocking, e2e_steps, e2e_warm)
         cache.start()
         sec_cache, _ = self.timed(step_e2e_cache, e2e_steps, e2e_warm)
+        sec_pipe, _ = self.timed(step_e2e_pipelined, e2e_steps, e2e_warm)
         cache.end()
         sub = lambda sec, path: dict(value=self.world * B * e2e_steps / sec, ms_per_step=sec / e2e_steps * 1e3, path=path)
         out["e2e"] = dict(value=self.world * B * e2e_steps / sec_e2e, unit="transitions/s", h2d_bytes_per_step=2 * B * row_bytes,
@@ -469,6 +480,8 @@ class Bench:
                                "rows) -> losses.cpu()",
                           cache_loop=sub(sec_cache, "Cache(replay_buffer).q1.get() -> numpy batch -> Learner.train(numpy) -> "
                                                     "store_batch(host) -> losses.cpu() (algos/sac1/sac1.py:136-151; 2 samples in flight)"),
+                          pipelined=sub(sec_pipe, "the cache loop with each step's losses read back after the NEXT step has been "
+                                                  "queued (still one D2H loss read per step): the GPU never waits for the host"),
                           blocking=sub(sec_blk, "sample_batch() -> numpy -> Learner.train(numpy) -> store_batch(host) -> losses.cpu()"))
         extra = {}
         if primary:

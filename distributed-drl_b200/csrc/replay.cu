@@ -1373,6 +1373,9 @@ int ddrl_rb_sample_host_async(ddrl_rb_t rb, int64_t batch, int64_t n_batches, co
   float* orw = oa + n * rb->A;
   float* od = orw + n;
   int64_t* oidx = (int64_t*)((char*)stage + (need - n * 8));
+  const int64_t fbytes = n * (2 * (int64_t)rb->D + rb->A + 2) * 4;
+  if (need - n * 8 > fbytes)      // the 4 alignment bytes in front of the index array: defined contents for the D2H copy
+    DDRL_CUDA(cudaMemsetAsync((char*)stage + fbytes, 0, (size_t)(need - n * 8 - fbytes), st));
   rc = ddrl_rb_sample(rb, batch, n_batches, d_idx_in, seed, counter, rng_stream, o1, o2, oa, orw, od,
                       oidx, stream);
   if (rc) return rc;

@@ -120,7 +120,7 @@ class Learner(object):
         self._pg = process_group
         self._fused = False
         self._outs = None
-        self._hscal, self._hscal_event = None, None
+        self._hscal, self._hscal_event, self._hscal_ring = None, None, None
         self._inflight = collections.deque()
         self._stage = {}
         self.steps = 0
@@ -398,8 +398,9 @@ class Learner(object):
             f = dict(dtype=torch.float32, device=self._dev)
             self._outs = dict(scalars=torch.zeros(4, **f), q1=torch.empty(B, **f), q2=torch.empty(B, **f),
                               logp_pi=torch.empty(B, **f))
-        if self._hscal is None:
-            self._hscal = torch.zeros(4, dtype=torch.float32, pin_memory=True)
+        if self._hscal_ring is None:
+            self._hscal_ring = torch.zeros((8, 4), dtype=torch.float32, pin_memory=True)
+        self._hscal = self._hscal_ring[self.steps % 8]          # a deferred read (losses_async) may lag a few steps
         o = self._outs
         s = self._stream()
         world = self._world()
@@ -448,6 +449,18 @@ class Learner(object):
         out = self._train_host_block(batch, blk, False)
         out["batch"] = batch
         return out
+
+    def losses_async(self):
+        """A handle on the losses of the last host-block train(): a callable that waits for THAT step and returns its four
+        scalars (each step gets its own pinned slot, so the handle stays valid while later steps are queued)."""
+        ev, slot = self._hscal_event, self._hscal
+        if ev is None:
+            raise RuntimeError("losses_async(): no host-block train() call yet")
+
+        def result():
+            ev.synchronize()
+            return slot.numpy().copy()
+        return result
 
     def losses(self):
         """(pi_loss, q1_loss, q2_loss, alpha) of the last train() that took the host-block path, as a numpy array: waits for

@@ -253,7 +253,7 @@ def test_host_block_path_and_cache_prefetch_equal_the_plain_calls(L):
         learner = L(make_opt(D, A, hidden, B), "learner")
         learner.set_weights(list(params), list(params.values()))
         cache = Cache(rb, B, depth=3)
-        if mode != "device":
+        if mode.startswith("host-"):
             cache.start()
         losses = []
         for it in range(4):
