@@ -195,7 +195,8 @@ struct GemmGroup {
   GemmProb p[GEMM_MAX_PROBS];
 };
 
-__global__ void __launch_bounds__(256, 3) gemm_grouped_f32(const __grid_constant__ GemmGroup grp) {
+// internal linkage: the header is compiled into sac.cu (SAC1 step) and qlearn.cu (DDQN / SQN steps)
+static __global__ void __launch_bounds__(256, 3) gemm_grouped_f32(const __grid_constant__ GemmGroup grp) {
   __shared__ __align__(16) float smem_raw[GEMM_SMEM_FLOATS];
   pdl_trigger();
   pdl_wait();

@@ -74,6 +74,13 @@ SIGNATURES = {
     "ddrl_sac_comm_attach": (_int, [_vp, _int, _int, _vp]),
     "ddrl_sac_comm_error": (_int, [_vp, _pint]),
     "ddrl_sac_dp_trace": (_int, [_vp, C.POINTER(C.c_uint64)]),
+    "ddrl_ql_create": (_int, [_int, _int, _int, _int, _int, _int, _int, _f, _f, _f, _f, C.POINTER(_vp)]),
+    "ddrl_ql_destroy": (_int, [_vp]),
+    "ddrl_ql_param_count": (_i64, [_vp]),
+    "ddrl_ql_set_weights": (_int, [_vp, _vp, _int, _vp]),
+    "ddrl_ql_get_weights": (_int, [_vp, _vp, _int, _vp]),
+    "ddrl_ql_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "ddrl_ql_forward": (_int, [_vp, _vp, _int, _int, _vp, _vp]),
     "ddrl_sac_act": (_int, [_vp, _vp, _int, _int, _vp, _u64, _u64, _vp, _vp]),
     "ddrl_sac_debug_stage": (_int, [_vp, _int, _int, _int, _vp]),
     "ddrl_debug_tc_gemm": (_int, [_int, _vp, _int, _int, _int, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _int, _vp]),

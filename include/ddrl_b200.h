@@ -321,6 +321,32 @@ int ddrl_sac_trace_stage(ddrl_sac_t sac, int batch, int stage, unsigned long lon
 /* optimiser step counters and log_alpha (synchronises `stream`).  Any out may be NULL. */
 int ddrl_sac_state(ddrl_sac_t sac, int* t_pi, int* t_q, int* t_alpha, float* log_alpha, void* stream);
 
+/* ---- discrete-action learners: DDQN (algos/dqn/actor_learner.py:20-130) and SQN (algos/sqn/actor_learner.py:20-125) ----
+ * n_nets = 1: DDQN — q = mlp(x) -> [B, n_actions] (hidden h1, h2, relu; algos/dqn/core.py:53-63); loss
+ *             0.5 * mean((r + gamma (1-d) q_target(x2)[argmax_a q_main(x2)] - q(x)[a])^2)   (actor_learner.py:41-55)
+ * n_nets = 2: SQN  — q1, q2; backup r + gamma (1-d) (min(max_a q1_target(x2), max_a q2_target(x2)) - alpha * sum_a p log p),
+ *             p = softmax(q1_main(x2) / alpha) (algos/sqn/core.py:30-45, actor_learner.py:43-58); loss = q1_loss + q2_loss.
+ * Both: tf.train.AdamOptimizer(lr) on the main networks, then polyak averaging of every main variable into its target
+ * (actor_learner.py:59-67).  Flat parameter vector = the reference's variable order, per network dense/kernel [D,h1],
+ * dense/bias [h1], dense_1/kernel [h1,h2], dense_1/bias, dense_2/kernel [h2,n_actions], dense_2/bias. */
+typedef struct ddrl_ql* ddrl_ql_t;
+int ddrl_ql_create(int device, int obs_dim, int n_actions, int h1, int h2, int max_batch, int n_nets, float gamma,
+                   float polyak, float lr, float alpha, ddrl_ql_t* out);
+int ddrl_ql_destroy(ddrl_ql_t ql);
+int64_t ddrl_ql_param_count(ddrl_ql_t ql);
+/* Learner.set_weights (assign main; also_target = the reference's target_init) / get_weights; which: 0 main, 1 target,
+ * 2 Adam m, 3 Adam v, 4 the last step's gradient */
+int ddrl_ql_set_weights(ddrl_ql_t ql, const float* d_flat, int also_target, void* stream);
+int ddrl_ql_get_weights(ddrl_ql_t ql, float* d_flat, int which, void* stream);
+/* Learner.train(batch, cnt): one update on device arrays obs1, obs2 [batch, obs_dim], acts (action indices stored as
+ * floats, as the dqn-family ring keeps them), rews, done [batch].  d_out_loss (nullable): n_nets per-network losses then
+ * their sum; d_out_q (nullable): q(x) of each network, [n_nets, batch, n_actions] — the reference's fetch list. */
+int ddrl_ql_step(ddrl_ql_t ql, const float* d_obs1, const float* d_obs2, const float* d_acts, const float* d_rews,
+                 const float* d_done, int batch, float* d_out_loss, float* d_out_q, void* stream);
+/* Actor side (algos/dqn/actor_learner.py:190-200, algos/sqn/core.py:30-45): main network `net`'s Q values for n
+ * observations; the caller takes the argmax / epsilon-greedy / softmax(q / alpha) sample. */
+int ddrl_ql_forward(ddrl_ql_t ql, const float* d_obs, int n, int net, float* d_out_q, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
