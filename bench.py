@@ -690,6 +690,35 @@ class Bench:
         return res
 
 
+def measure_qlearn(b):
+    """Row N4: the DDQN / SQN learner steps at the reference's default shape (hidden [400, 300], batch 256; obs 115 = the
+    dqn family's trading observation, 3 actions), device-resident, with the float32 torch-CPU restatement beside them."""
+    from types import SimpleNamespace
+    from ddrl_b200 import DQNLearner, SQNLearner
+    from oracle.qlearn_oracle import DDQNOracle, SQNOracle, init_q_params, make_q_batch
+    torch = b.torch
+    D, nA, hidden, B = 115, 3, (400, 300), 256
+    opt = SimpleNamespace(obs_dim=D, act_dim=nA, hidden_size=list(hidden), gamma=0.99, lr=1e-3, polyak=0.995, seed=0, batch_size=B, alpha=0.1)
+    batch = {k: torch.from_numpy(v).to(b.dev) for k, v in make_q_batch(D, nA, B, seed=1).items()}
+    out = {}
+    for name, cls, ocls, nn in (("ddqn", DQNLearner, DDQNOracle, 1), ("sqn", SQNLearner, SQNOracle, 2)):
+        L = cls(opt, "learner", device=b.local)
+        sec, launches = b.timed(lambda: L.train(batch), 300, 10)
+        ora = ocls(init_q_params(D, nA, hidden, nn, seed=2), alpha=0.1, dtype=torch.float32)
+        hb = make_q_batch(D, nA, B, seed=1)
+        torch.set_num_threads(os.cpu_count() or 1)
+        ora.step(hb)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ora.step(hb)
+        cpu = (time.perf_counter() - t0) / 20
+        out[name] = dict(us_per_step=sec / 300 * 1e6, transitions_per_s=B * 300 / sec, gpu_launches_per_step=launches / 300,
+                         cpu_port_us_per_step=cpu * 1e6, cpu_cores=os.cpu_count())
+        del L
+    return dict(workload="N4: DDQN (algos/dqn) and SQN (algos/sqn) learner steps, obs 115, 3 actions, hidden 400x300, batch 256, fp32 FFMA",
+                **out)
+
+
 def measure_frames_sharded(b):
     """C4 as configured: 1e6 Atari-shaped transitions sharded over the N GPUs of the node (frame-deduplicated ring, one
     shard per rank, local sampling — no data-path collective), batch 512 per learner; whole-job transitions/s, max over ranks."""
@@ -729,6 +758,7 @@ def run_ours(args):
             configs[name], _ = b.measure(name, steps, max(3, min(args.warmup, 20)), primary=False)
             configs[name]["cpu_replay_1thread"] = cpu_replay_only(CONFIGS[name], budget_s=1.0)
         configs.update(b.measure_frames())
+        configs["N4_qlearn"] = measure_qlearn(b)
     c4_sharded = measure_frames_sharded(b) if not args.only_primary else None
     if b.world > 1:
         dist.barrier()
