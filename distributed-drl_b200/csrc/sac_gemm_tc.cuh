@@ -36,13 +36,13 @@ namespace tc {
 
 constexpr int BM = 128, BK = 32;                      // BK tf32 = 128 bytes = one swizzle row
 constexpr int TILE_BYTES = 128 * 128;                 // one A plane tile (128 rows x 32 tf32)
-// TMEM accumulators per tile: MMA j of a k-block adds into accumulator j % NACC and the epilogue sums them with
-// round-to-nearest adds.  The tensor core adds every product into its fp32 accumulator with truncation, a bias that
-// grows with the number of additions (measured: 2e-5 gradient error at K ~ 400 with ONE accumulator against 1e-7 for
-// FFMA); NACC accumulators divide it by NACC.  (Rotating accumulators does not change the speed of the main loop:
-// 4.86 us per 8 k-blocks with 1, 2 or 4 of them, with 128 x 128 and 128 x 64 tiles, with 128 or 16 CTAs on the chip
-// — the loop is bound by shared-memory bandwidth: per k-block the 3xTF32 products read A three times and B three
-// times from shared memory while TMA writes the next stage.)
+// TMEM accumulators per tile: NACC = 4 blocks of BN columns = two sets of (hi . hi | cross terms); the k-steps of a
+// k-block alternate between the sets and the epilogue sums the four blocks with round-to-nearest adds.  The tensor core
+// adds every product into its fp32 accumulator with truncation, a bias that grows with the number of additions
+// (measured: 2e-5 gradient error at K ~ 400 with ONE accumulator against 1e-7 for FFMA); splitting the chain divides
+// it.  (The number of accumulators does not change the speed of the main loop, which is bound by shared-memory
+// bandwidth: the products re-read the A and B tiles from shared memory while TMA writes the next stage — hence the
+// [B_hi | B_lo] descriptor of the MMA issuer below, which reads A twice per k-step instead of three times.)
 constexpr int NACC = 4;
 constexpr int MAX_PROBS = 10;
 // Tile width BN is a template parameter of the kernel: 128 x 128 tiles when they fill the chip on their own, 128 x 64
@@ -288,26 +288,31 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
     }
   } else if (warp == 1) {
     // ---- MMA issuer (the whole warp walks the loop; one elected lane issues) ----
-    const uint32_t idesc = make_idesc(a_mn, b_mn, BN);
+    // Two MMAs per k-step instead of three: the B_lo plane tile follows the B_hi tile in the stage at the descriptor's own
+    // block stride (K-major: 8-row groups 1024 B apart; MN-major: 32-column blocks 4096 B apart), so ONE descriptor of
+    // N = 2 BN addresses [B_hi | B_lo]:
+    //     acc[2s]   += A_hi . B_hi      acc[2s+1] += A_hi . B_lo        (one MMA, N = 2 BN, into two adjacent accumulators)
+    //     acc[2s+1] += A_lo . B_hi                                      (one MMA, N = BN)
+    // with s alternating per k-step.  A is read from shared memory twice per k-step instead of three times (the loop is
+    // bound by shared-memory bandwidth), and the cross terms never meet the truncating accumulation of the hi . hi sums.
+    const uint32_t idesc = make_idesc(a_mn, b_mn, BN), idesc_w = make_idesc(a_mn, b_mn, 2 * BN);
+    static_assert(NACC == 4 && 2 * BN <= 256, "two sets of (hi.hi | cross) accumulators");
     const int a_step = a_mn ? 1024 : 32, b_step = b_mn ? 1024 : 32;   // bytes per 8 tf32 of K
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       bar_wait(&full[s], (kb / STAGES) & 1);
       if (kb == 0) TC_STAMP(2);     // first stage landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = s_addr(base + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES,
-                     b_lo = b_hi + B_TILE;
-      // 12 MMAs per k-block, MMA j into accumulator j % NACC
-      const uint64_t da_lo = make_sdesc(a_lo, a_mn), da_hi = make_sdesc(a_hi, a_mn), db_lo = make_sdesc(b_lo, b_mn),
-                     db_hi = make_sdesc(b_hi, b_mn);
+      const uint32_t a_hi = s_addr(base + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES;
+      // 8 MMAs per k-block: k-step ks into accumulator set ks & 1 (blocks 2s = hi . hi, 2s + 1 = cross terms)
+      const uint64_t da_lo = make_sdesc(a_lo, a_mn), da_hi = make_sdesc(a_hi, a_mn), db_hi = make_sdesc(b_hi, b_mn);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint64_t ao = (uint64_t)((ks * a_step) >> 4), bo = (uint64_t)((ks * b_step) >> 4);   // descriptor address field
-          const int j = 3 * ks;
-          mma_tf32(tmem_d + (uint32_t)((j % NACC) * BN), da_lo + ao, db_hi + bo, idesc, (kb > 0 || j >= NACC) ? 1u : 0u);
-          mma_tf32(tmem_d + (uint32_t)(((j + 1) % NACC) * BN), da_hi + ao, db_lo + bo, idesc, (kb > 0 || j + 1 >= NACC) ? 1u : 0u);
-          mma_tf32(tmem_d + (uint32_t)(((j + 2) % NACC) * BN), da_hi + ao, db_hi + bo, idesc, (kb > 0 || j + 2 >= NACC) ? 1u : 0u);
+          const uint32_t d0 = tmem_d + (uint32_t)(2 * (ks & 1) * BN);
+          mma_tf32(d0, da_hi + ao, db_hi + bo, idesc_w, (kb > 0 || ks >= 2) ? 1u : 0u);
+          mma_tf32(d0 + (uint32_t)BN, da_lo + ao, db_hi + bo, idesc, 1u);
         }
         mma_commit(&empty[s]);          // frees the stage when these MMAs have read it
         if (kb == nkb - 1) mma_commit(acc_ready);   // covers every MMA issued before it
@@ -444,11 +449,13 @@ __global__ void __launch_bounds__(256, 1) gemm_grouped_tc(const __grid_constant_
 // bound by the tensor pipe.  The four CTAs of a row block recompute the (cheap, one k-block) first layer; each of
 // them writes a quarter of H1's k-blocks (hi / lo planes by TMA store, relu bit masks) for the passes the backward needs.
 //   warp 0 / lane 0    TMA producer: [x|a] and W1 (once), then the W2 k-block ring (4 stages of 16 KB)
-//   warp 1 / lane 0    MMA issuer: first layer (<= 4 k-steps x 3 products, N = h1), then per k-block 12 MMAs (N = 64)
+//   warp 1 / lane 0    MMA issuer: first layer (<= 4 k-steps x 3 products, N = h1), then per k-block 8 MMAs
+//                      (4 k-steps x [N = 128 against W2_hi|W2_lo, N = 64 against W2_hi])
 //   warps 2..9         converters (two groups of four warps = the four TMEM lane quadrants; even / odd k-blocks),
 //                      then the H2 epilogue (bias, relu, TMA store)
-// TMEM columns: [0, 256) layer-1 accumulator -> hi plane; [256, 384) lo ring (4 x 32); [384, 512) two 64-column
-// layer-2 accumulators (alternate k-blocks, summed in the epilogue: halves the accumulation truncation bias).
+// TMEM columns: [0, 256) layer-1 accumulator -> hi plane; [256, 384) lo ring (4 x 32); [384, 448) layer-2 accumulator of
+// the hi . hi products, [448, 512) of the two cross products (hi . lo + lo . hi), summed by the epilogue with a
+// round-to-nearest add (the small terms never meet the truncating accumulation of the large ones).
 // =====================================================================================================================
 constexpr int FZ_THREADS = 320;
 constexpr int FZ_BN = 64;
@@ -597,7 +604,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
       }
       __syncwarp();
     }
-    const uint32_t idesc2 = make_idesc(0, 1, FZ_BN);
+    // Two MMAs per k-step instead of three: the W2 stage holds the hi plane's two 32-column blocks followed by the lo
+    // plane's (uniform 4096-byte LBO), so ONE descriptor of N = 128 addresses [W2_hi | W2_lo] and
+    //     acc[0, 64)   += H1_hi . W2_hi          acc[64, 128) += H1_hi . W2_lo      (one MMA, N = 128)
+    //     acc[64, 128) += H1_lo . W2_hi                                             (one MMA, N = 64)
+    // The A operand (tensor memory) is read twice per k-step instead of three times — the second layer was paced by
+    // those reads plus the converters' tcgen05.ld on the same port (512 ns per k-block for 384 cycles of tensor math).
+    const uint32_t idesc2 = make_idesc(0, 1, FZ_BN), idesc2w = make_idesc(0, 1, 2 * FZ_BN);
     for (int kb = 0; kb < nkb; ++kb) {
       const int sa = kb % FZ_SA, sb = kb % FZ_SB;
       bar_wait(&fullB[sb], (kb / FZ_SB) & 1);
@@ -606,16 +619,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = tmem_d + (uint32_t)(kb * BK), a_lo = tmem_d + (uint32_t)(FZ_LO_COL + sa * BK);
       const uint32_t b_hi = s_addr(bring + sb * FZ_B_STAGE), b_lo = b_hi + FZ_B_STAGE / 2;
-      const uint32_t acc = tmem_d + (uint32_t)(FZ_ACC_COL + (kb % FZ_NACC) * FZ_BN);
-      const uint64_t db_lo = make_sdesc(b_lo, true), db_hi = make_sdesc(b_hi, true);
+      const uint32_t acc = tmem_d + (uint32_t)FZ_ACC_COL;
+      const uint64_t db_hi = make_sdesc(b_hi, true);
+      static_assert(FZ_B_STAGE / 2 == (FZ_BN / 32) * 4096, "the lo plane's blocks continue the hi plane's at the descriptor's LBO");
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint64_t bo = (uint64_t)((ks * 1024) >> 4);
           const uint32_t ac = (uint32_t)(ks * 8);                 // 8 tf32 of K = 8 TMEM columns
-          mma_tf32_ts(acc, a_lo + ac, db_hi + bo, idesc2, (kb >= FZ_NACC || ks) ? 1u : 0u);
-          mma_tf32_ts(acc, a_hi + ac, db_lo + bo, idesc2, 1u);
-          mma_tf32_ts(acc, a_hi + ac, db_hi + bo, idesc2, 1u);
+          mma_tf32_ts(acc, a_hi + ac, db_hi + bo, idesc2w, (kb || ks) ? 1u : 0u);
+          mma_tf32_ts(acc + FZ_BN, a_lo + ac, db_hi + bo, idesc2, 1u);
         }
         mma_commit(&emptyA[sa]);
         mma_commit(&emptyB[sb]);
@@ -699,11 +712,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
     const int c0 = 32 * cg, n_base = n0 + c0;
     if (n_base < h2) {                           // warp-uniform
       float v[32], v2[32];
-      tmem_ld32_nowait(trow + (uint32_t)(FZ_ACC_COL + c0), v);
-      if (nkb > 1) tmem_ld32_nowait(trow + (uint32_t)(FZ_ACC_COL + FZ_BN + c0), v2);
+      tmem_ld32_nowait(trow + (uint32_t)(FZ_ACC_COL + c0), v);                 // hi . hi
+      tmem_ld32_nowait(trow + (uint32_t)(FZ_ACC_COL + FZ_BN + c0), v2);        // hi . lo + lo . hi
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaxf((nkb > 1 ? v[i] + v2[i] : v[i]) + s_bias2[c0 + i], 0.0f);
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf((v[i] + v2[i]) + s_bias2[c0 + i], 0.0f);
       // staging in the W2 ring: every W2 load has been consumed
       unsigned char* blk = bring + cw * 4096;
       stage_row(blk, lane, v);

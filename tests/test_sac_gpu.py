@@ -8,6 +8,8 @@ float32 for ANY implementation, the reference included).  The oracle is unpinned
 (TensorFlow absent): this is parity with the restated algorithm."""
 from types import SimpleNamespace
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -76,7 +78,7 @@ def test_one_step_matches_oracle(L, D, A, hidden, B, scale, gemm):
     for k in ("q1", "q2", "logp_pi"):
         assert rel(got[k].cpu().numpy(), want[k]) <= TOL, k
     got_g = learner.get_flat_weights("grad").cpu().numpy()
-    assert rel(got_g, want_g) <= 2 * TOL
+    assert rel(got_g, want_g) <= TOL
     got_w, want_w = learner.get_flat_weights("main").cpu().numpy(), oracle.flat("main")
     # (1) optimiser in isolation: float64 TF1-Adam applied to the KERNEL's gradient reproduces the
     #     kernel's weights to float32 rounding
@@ -89,10 +91,12 @@ def test_one_step_matches_oracle(L, D, A, hidden, B, scale, gemm):
     #     step is lr*g/(|g| + 1e-8*sqrt(1000)...): for |g| within a few orders of 1e-8 a 1e-7 relative
     #     gradient difference moves the update by more than 1e-5*|w| in ANY float32 evaluation
     #     (the float32 oracle itself is 0.96e-5 away from float64 on the Humanoid-shaped case).
-    #     The epsilon-dominated remainder gets a stated 5e-5 (FFMA) / 1e-4 (3xTF32: products carry ~2^-22 instead
-    #     of 2^-24 relative error, which the same Adam amplification turns into a 2x looser bound).
+    #     The epsilon-dominated remainder gets a stated 2e-5, the same for both GEMM modes: the worst of these small
+    #     cases measures 1.25e-5 in 3xTF32 mode and 1.15e-5 in plain-FFMA mode (the Humanoid row shape at B = 300), i.e. the
+    #     limit is float32 itself, not the tensor-core path.  At BASELINE.json's full sizes every weight is within 1e-5
+    #     (test_full_size_step_matches_oracle; measured margins per tensor group: profiles/r02_parity_margins.json).
     solid = np.abs(want_g) > 1e-4 * np.abs(want_g).max()
-    loose = 1e-4 if gemm == "tc" else 5 * TOL
+    loose = 2 * TOL
     assert rel(got_w[solid], want_w[solid]) <= TOL
     assert rel(got_w, want_w) <= loose
     got_t, want_t = learner.get_flat_weights("target").cpu().numpy(), oracle.flat("target")
@@ -304,7 +308,8 @@ def test_full_size_step_matches_oracle(L, D, A, B, scale):
         assert abs(sc[i] - float(want[k])) <= TOL * abs(float(want[k])), (k, sc[i], float(want[k]))
     for k in ("q1", "q2", "logp_pi"):
         assert rel(got[k].cpu().numpy(), want[k]) <= TOL, k
-    assert rel(learner.get_flat_weights("grad").cpu().numpy(), want_g) <= 2 * TOL
+    assert rel(learner.get_flat_weights("grad").cpu().numpy(), want_g) <= TOL
     got_w, want_w = learner.get_flat_weights("main").cpu().numpy(), oracle.flat("main")
     solid = np.abs(want_g) > 1e-4 * np.abs(want_g).max()
     assert rel(got_w[solid], want_w[solid]) <= TOL
+    assert rel(got_w, want_w) <= TOL                     # every weight, at the bar north_star states
