@@ -571,14 +571,20 @@ class Bench:
         s = self.stream()
         sp = C.c_void_p(s.cuda_stream)
         reps = 100
-        self.N.check(self.lib.ddrl_sac_debug_stage(learner._h, B, 1, 10, sp))
-        torch.cuda.synchronize()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0e.record(s)
-        self.N.check(self.lib.ddrl_sac_debug_stage(learner._h, B, 1, reps, sp))
-        t1e.record(s)
-        torch.cuda.synchronize()
-        tc_s = t0e.elapsed_time(t1e) / 1e3 / reps
+
+        def stage_time(r):      # r > 0: back-to-back stream launches; r < 0: the same launches as the nodes of one graph
+            self.N.check(self.lib.ddrl_sac_debug_stage(learner._h, B, 1, r, sp))        # warm-up (r < 0: also builds the graph)
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record(s)
+            self.N.check(self.lib.ddrl_sac_debug_stage(learner._h, B, 1, r, sp))
+            t1e.record(s)
+            torch.cuda.synchronize()
+            return t0e.elapsed_time(t1e) / 1e3 / abs(r)
+
+        # the step runs as ONE CUDA graph, so the kernel is timed as graph nodes; as separate stream launches every kernel is
+        # rounded up to the next ~2.05 us completion tick of stream-order launches (tools/probes/tick_probe.cu)
+        tc_s, tc_stream_s = stage_time(-reps), stage_time(reps)
         h1, h2 = hidden
         fused = D + A <= 32 and h1 <= 256 and h1 % 32 == 0 and h2 % 4 == 0
         if fused:   # passes a, c (policy, K1 = D) and d, e (Q, K1 = D + A): first + second layer
@@ -592,7 +598,9 @@ class Bench:
         out["roofline"] = dict(kernel=kname, bound="tensor", achieved=flops / tc_s / 1e12, peak=self.peaks["bf16_tf"], unit="TFLOP/s",
                                frac=flops / tc_s / 1e12 / self.peaks["bf16_tf"], traffic=tr.get("dram_bytes"),
                                tensor_pipe_active_pct=tr.get("tensor_pipe_active_pct"), traffic_source=tr.get("source"),
-                               us_per_launch=tc_s * 1e6, flops_per_launch=flops, tensor_pipe_flops_per_launch=3 * flops,
+                               us_per_launch=tc_s * 1e6, us_per_stream_launch=tc_stream_s * 1e6, timed_as="nodes of one CUDA graph "
+                               "(how the step runs them); us_per_stream_launch = the same kernel as back-to-back stream launches",
+                               flops_per_launch=flops, tensor_pipe_flops_per_launch=3 * flops,
                                peak_source=self.peaks["source"])
         fl = flops_per_update(D, A, h1, h2, B)
         tf = fl * (steps / sec) / 1e12

@@ -1313,6 +1313,12 @@ struct Plan {
   std::vector<std::vector<Group>> stages;  // ordered stages; element-wise kernels sit between them
   cudaGraphExec_t exec_full = nullptr, exec_grads = nullptr, exec_apply = nullptr, exec_dp = nullptr;
   int64_t kernels[4] = {0, 0, 0, 0};  // kernels inside each captured graph (for the launch counter)
+  // The prologue is the graph's FIRST node: its per-step values travel as kernel parameters, patched into the
+  // instantiated graph before every launch (cudaGraphExecKernelNodeSetParams).  Launched on its own in front of the graph
+  // it cost two stream-order hand-overs per step instead of one (measured with tools/probes/tick_probe.cu: ~1.6 us and a
+  // 2.05 us completion granularity per stream-order dependent launch, against 0.75 us between the nodes of a graph).
+  cudaGraph_t graph[4] = {nullptr, nullptr, nullptr, nullptr};       // kept alive: the node handles below belong to them
+  cudaGraphNode_t prologue_node[4] = {nullptr, nullptr, nullptr, nullptr};
   bool fused = false;              // first + second layer of every forward pass in ONE tcgen05 launch (fwd_fused_tc)
   bool fold_b = false;             // pass b's policy head is evaluated inside k_qheads_losses (narrow heads)
   ColsumGroup colsum[8] = {};      // tensor-core mode: bias-gradient column sums per stage (side stream)
@@ -1353,6 +1359,8 @@ struct ddrl_sac {
   unsigned long long* dp_trace = nullptr;   // DDRL_DP_TRACE=1: 8 phase time stamps of k_adam_dp's CTA 0 (ddrl_sac_dp_trace)
   bool dp_v1 = true;                    // two-kernel form of the fused data-parallel step (reduce kernel + full peer read); DDRL_DP_V1=0: one kernel
   bool narrow_w1 = false;               // policy W1 gradient (K = D <= 32) by k_wgrad_narrow instead of a tensor-core stage
+  cudaGraphExec_t dbg_exec = nullptr;   // ddrl_sac_debug_stage(reps < 0): the last measurement graph
+  int dbg_key[3] = {0, 0, 0};           // its (batch, stage, reps)
   float* host_stage = nullptr;          // device copy of a host batch block (ddrl_sac_step_host), maxB * (2D + A + 2) floats
   float* host_scal = nullptr;           // its 4 output scalars before the D2H copy
   float* Gn = nullptr;                  // its per-slice partial blocks [ceil(maxB / 64)][(D + 1) * h1]
@@ -1820,13 +1828,28 @@ XaOut xa_out(const ddrl_sac* h) {
   return h->use_tc ? XaOut{h->XA[0], h->XA[1], h->XA[2], h->ldx, h->lox} : XaOut{nullptr, nullptr, nullptr, 0, 0};
 }
 
+int prologue_blocks(const ddrl_sac* h, int B) {
+  const int64_t work = std::max<int64_t>((int64_t)B * h->D, 3LL * B * h->A);
+  return (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
+}
 int launch_prologue(ddrl_sac* h, const Plan& pl, const StepDyn& dyn, cudaStream_t s) {
   const int B = pl.B, D = h->D, A = h->A;
-  const int64_t work = std::max<int64_t>((int64_t)B * D, 3LL * B * A);
-  const int blocks = (int)std::min<int64_t>((work + 255) / 256, h->sms * 4);
-  DDRL_CUDA(launch_pdl(k_prologue, dim3(blocks), dim3(256), 0, s, h->st, dyn, B, D, A, h->X, h->X2, h->ACT, h->R, h->DN,
-                       h->NOISE, xa_out(h)));
+  DDRL_CUDA(launch_pdl(k_prologue, dim3(prologue_blocks(h, B)), dim3(256), 0, s, h->st, dyn, B, D, A, h->X, h->X2, h->ACT, h->R,
+                       h->DN, h->NOISE, xa_out(h)));
   DDRL_LAUNCH_CHECK();
+  return 0;
+}
+// this step's values into the prologue node of an instantiated graph
+int patch_prologue(ddrl_sac* h, const Plan& pl, cudaGraphExec_t exec, cudaGraphNode_t node, const StepDyn& dyn) {
+  int B = pl.B, D = h->D, A = h->A;
+  StepDyn d = dyn;
+  XaOut xa = xa_out(h);
+  void* args[] = {&h->st, &d, &B, &D, &A, &h->X, &h->X2, &h->ACT, &h->R, &h->DN, &h->NOISE, &xa};
+  cudaKernelNodeParams np{};
+  np.func = (void*)k_prologue;
+  np.gridDim = dim3(prologue_blocks(h, B)); np.blockDim = dim3(256);
+  np.sharedMemBytes = 0; np.kernelParams = args; np.extra = nullptr;
+  DDRL_CUDA(cudaGraphExecKernelNodeSetParams(exec, node, &np));
   return 0;
 }
 bool narrow_heads(const ddrl_sac* h) { return 2 * h->A <= 16 && (h->h2 & 3) == 0; }
@@ -1989,24 +2012,45 @@ int enqueue_mode(ddrl_sac* h, const Plan& pl, int mode, cudaStream_t s) {
   return enqueue_apply(h, 1, h->G, s);
 }
 
-int run_mode(ddrl_sac* h, Plan& pl, int mode, cudaStream_t s) {
+int run_mode(ddrl_sac* h, Plan& pl, int mode, cudaStream_t s, const StepDyn* dyn) {
   cudaGraphExec_t* slot = mode == MODE_FULL ? &pl.exec_full : mode == MODE_GRADS ? &pl.exec_grads
                           : mode == MODE_APPLY ? &pl.exec_apply : &pl.exec_dp;
-  if (!h->use_graph) return enqueue_mode(h, pl, mode, s);
+  const int gi = mode == MODE_FULL ? 0 : mode == MODE_GRADS ? 1 : mode == MODE_APPLY ? 2 : 3;
+  if (!h->use_graph) {
+    if (dyn) { int rc = launch_prologue(h, pl, *dyn, s); if (rc) return rc; }
+    return enqueue_mode(h, pl, mode, s);
+  }
   if (!*slot) {
     cudaGraph_t graph = nullptr;
     if (!h->cap_stream) DDRL_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const int64_t before = g_launches.load();
     DDRL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_mode(h, pl, mode, h->cap_stream);
+    int rc = dyn ? launch_prologue(h, pl, *dyn, h->cap_stream) : 0;
+    if (!rc) rc = enqueue_mode(h, pl, mode, h->cap_stream);
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     pl.kernels[mode] = g_launches.load() - before;
     g_launches.store(before);  // captured, not executed
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    if (dyn) {      // the prologue's node: its parameters are replaced before every launch
+      size_t n = 0;
+      DDRL_CUDA(cudaGraphGetNodes(graph, nullptr, &n));
+      std::vector<cudaGraphNode_t> nodes(n);
+      DDRL_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n));
+      for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == (void*)k_prologue) { pl.prologue_node[gi] = nd; break; }
+      }
+      if (!pl.prologue_node[gi]) { cudaGraphDestroy(graph); return fail(DDRL_ECUDA, "captured step has no prologue node"); }
+    }
     e = cudaGraphInstantiate(slot, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail(DDRL_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    pl.graph[gi] = graph;
+  } else if (dyn) {
+    int rc = patch_prologue(h, pl, *slot, pl.prologue_node[gi], *dyn);
+    if (rc) return rc;
   }
   DDRL_CUDA(cudaGraphLaunch(*slot, s));
   g_launches.fetch_add(pl.kernels[mode], std::memory_order_relaxed);
@@ -2183,7 +2227,9 @@ int ddrl_sac_destroy(ddrl_sac_t h) {
   for (auto& kv : h->plans) {
     Plan& pl = kv.second;
     for (auto ex : {pl.exec_full, pl.exec_grads, pl.exec_apply, pl.exec_dp}) if (ex) cudaGraphExecDestroy(ex);
+    for (auto g : pl.graph) if (g) cudaGraphDestroy(g);
   }
+  if (h->dbg_exec) cudaGraphExecDestroy(h->dbg_exec);
   for (int r = 0; r < 8; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->pc.buf[r]);
   if (h->comm) cudaFree(h->comm);
   if (h->d_err) cudaFree(h->d_err);
@@ -2256,10 +2302,10 @@ static int step_common(ddrl_sac_t h, int mode, const float* d_obs1, const float*
     dyn.lr_pi = dyn.lr_q = (float)((double)h->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
     dyn.noise_counter = (unsigned long long)h->t_host;
     h->last_dyn = dyn;
-    // the prologue carries the per-step values by value, so it is launched directly; the rest of the step is a graph
-    if ((rc = launch_prologue(h, *pl, dyn, s))) return rc;
+    // the prologue carries the per-step values as kernel parameters of the graph's first node
+    return run_mode(h, *pl, mode, s, &dyn);
   }
-  return run_mode(h, *pl, mode, s);
+  return run_mode(h, *pl, mode, s, nullptr);
 }
 
 int ddrl_sac_step(ddrl_sac_t h, const float* d_obs1, const float* d_obs2, const float* d_acts, const float* d_rews,
@@ -2450,6 +2496,32 @@ int ddrl_sac_debug_stage(ddrl_sac_t h, int batch, int stage, int reps, void* str
   // backward rows, 11 optimiser (state advances!), 12..14: side-stream work of BQ / BP / BP3
   if (stage < 0 || stage > 14) return fail(DDRL_EINVAL, "ddrl_sac_debug_stage: stage %d not in [0,14]", stage);
   cudaStream_t s = (cudaStream_t)stream;
+  if (reps < 0) {
+    // -reps launches as the nodes of ONE graph: what a kernel costs inside the step's graph.  (Back-to-back launches on
+    // a stream complete on a ~2.05 us grid — tools/probes/tick_probe.cu — which rounds every kernel up to the next tick.)
+    // the graph of the last (batch, stage, reps) is kept: call once to build + warm up, then time a second call
+    if (h->dbg_exec && h->dbg_key[0] == batch && h->dbg_key[1] == stage && h->dbg_key[2] == reps) {
+      DDRL_CUDA(cudaGraphLaunch(h->dbg_exec, s));
+      g_launches.fetch_add(-reps, std::memory_order_relaxed);
+      return 0;
+    }
+    if (h->dbg_exec) { cudaGraphExecDestroy(h->dbg_exec); h->dbg_exec = nullptr; }
+    h->dbg_key[0] = batch; h->dbg_key[1] = stage; h->dbg_key[2] = reps;
+    if (!h->cap_stream) DDRL_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    const int64_t before = g_launches.load();
+    DDRL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = ddrl_sac_debug_stage(h, batch, stage, -reps, h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    g_launches.store(before + (rc ? 0 : g_launches.load() - before));
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->dbg_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(DDRL_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    DDRL_CUDA(cudaGraphLaunch(h->dbg_exec, s));
+    return 0;
+  }
   for (int i = 0; i < reps; ++i) {
     if (stage < ST_COUNT) rc = run_stage(*pl, stage, s, h->use_tc);
     else if (stage == 7) rc = launch_prologue(h, *pl, h->last_dyn, s);

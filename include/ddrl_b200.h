@@ -305,7 +305,9 @@ int ddrl_sac_act(ddrl_sac_t sac, const float* d_obs, int n, int deterministic, c
                  uint64_t seed, uint64_t counter, float* d_out_act, void* stream);
 /* profiling aid: enqueue one phase of the step `reps` times (0..6: GEMM stages L1, L2, QL1, QL2, BQ, BP, BP3 — with
  * narrow inputs L1 / QL1 are empty and L2 / QL2 are the fused first + second layer launches;
- * 7 prologue, 8 policy heads, 9 Q heads + losses, 10 policy backward rows, 11 optimiser, 12..14 side-stream work) */
+ * 7 prologue, 8 policy heads, 9 Q heads + losses, 10 policy backward rows, 11 optimiser, 12..14 side-stream work).
+ * reps < 0: the -reps launches run as the nodes of ONE CUDA graph (what a kernel costs inside the step's graph; the graph
+ * of the last (batch, stage, reps) is cached, so call once to build it and time the second call). */
 int ddrl_sac_debug_stage(ddrl_sac_t sac, int batch, int stage, int reps, void* stream);
 /* Test entry for the tcgen05 3xTF32 GEMM alone: C[M,N] (splits > 1: `splits` partial outputs M*N floats apart)
  * = opA . opB from dense row-major fp32 device matrices A [a_rows,a_cols], B [b_rows,b_cols]; a_mn / b_mn = 1

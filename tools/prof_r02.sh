@@ -15,11 +15,23 @@ cap() { # name, kernel regex, skip, script...
 cap fwd_c2 fwd_fused_tc 4 python tools/prof_stage.py C2 1 6
 cap fwd_c1 fwd_fused_tc 4 python tools/prof_stage.py C1 1 6
 cap fwd_c3 gemm_grouped_tc 9 python tools/prof_stage.py C3 1 6
+cap l1_c3 gemm_grouped_tc 9 python tools/prof_stage.py C3 0 6
 cap bq_c2 gemm_grouped_tc 4 python tools/prof_stage.py C2 4 6
 cap gather_c1 rb_gather 2 python tools/prof_replay.py C1
 cap gather_c2 rb_gather 2 python tools/prof_replay.py C2
 cap gather_c3 rb_gather 2 python tools/prof_replay.py C3 64
 cap store_c2 rb_store_staged 2 python tools/prof_replay.py C2
+cap gather_c4_dedup rb_gather_tma 6 python tools/micro_frames.py
+cap store_c4_frames fb_store_frames 2 python tools/micro_frames.py
+cap store_n3 seg_store_rows 14 python tools/micro_frames.py
+DDRL_GATHER_MODE=2 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rb_gather_wide -s 2 -c 1 -f -o gpurun_out/${R}_gather_c3_regs python tools/prof_replay.py C3 64 > gpurun_out/${R}_gather_c3_regs.log 2>&1
+timeout 300 python tools/parity_margins.py > gpurun_out/${R}_parity_margins.log 2>&1
+for c in C1 C2 C3; do timeout 200 python tools/replay_curve.py $c default > gpurun_out/${R}_curve_$c.log 2>&1; done
+timeout 200 python tools/stage_times.py C2 > gpurun_out/${R}_stage_times_C2.log 2>&1
+timeout 200 python tools/stage_times.py C3 > gpurun_out/${R}_stage_times_C3.log 2>&1
+timeout 200 python tools/tc_trace.py C2 1 > gpurun_out/${R}_tc_trace_fused_c2.log 2>&1
+timeout 200 python tools/tc_trace.py C2 4 > gpurun_out/${R}_tc_trace_bq_c2.log 2>&1
+./tools/probes/tick_probe > gpurun_out/${R}_tick_probe.log 2>&1
 ls -la gpurun_out/${R}_*.ncu-rep
 python - <<'PY'
 import json

@@ -27,4 +27,10 @@ for st, nm in enumerate(names):
     e0.record()
     _native.check(lib.ddrl_sac_debug_stage(L._h, B, st, reps, C.c_void_p(s.cuda_stream)))
     e1.record(); torch.cuda.synchronize()
-    print(f"{os.environ.get('DDRL_GEMM','simt'):5s} {cfg} stage {nm:8s}: {e0.elapsed_time(e1)/reps*1e3:8.1f} us", flush=True)
+    t_stream = e0.elapsed_time(e1) / reps * 1e3
+    _native.check(lib.ddrl_sac_debug_stage(L._h, B, st, -reps, C.c_void_p(s.cuda_stream)))      # builds the graph + warm-up
+    torch.cuda.synchronize()
+    e0.record()
+    _native.check(lib.ddrl_sac_debug_stage(L._h, B, st, -reps, C.c_void_p(s.cuda_stream)))
+    e1.record(); torch.cuda.synchronize()
+    print(f"{cfg} stage {nm:8s}: {t_stream:8.1f} us as stream launches, {e0.elapsed_time(e1)/reps*1e3:8.1f} us as graph nodes", flush=True)
