@@ -171,6 +171,43 @@ __global__ void __launch_bounds__(256, (U >= 8 || LANES <= 4) ? 2 : ((LANES == 8
   }
 }
 
+// ---- narrow rows whose float4 count is far from a power of two (C1: 5 chunks of 16 B -> 3 of 8 lanes idle above) ------
+// Same warp-level scheme (32 rows per pass, one index per lane), but the 32 * used_f4 chunks of the pass are dealt to the
+// lanes FLAT: chunk e = 32 * it + lane belongs to row e / used_f4, so every lane moves data in every iteration.
+__global__ void __launch_bounds__(256, 4) rb_gather_flat(const GatherArgs a, uint32_t magic) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool aligned = (a.D & 3) == 0;
+  const int used = a.used_f4;
+  for (int64_t base = warp * 32; base < a.total; base += nwarps * 32) {
+    const int64_t mine = base + lane;
+    int64_t myidx = 0;
+    if (mine < a.total) {
+      myidx = draw_index(a, mine);
+      if (a.oidx) a.oidx[mine] = myidx;
+    }
+    const int rows_here = (int)min((int64_t)32, a.total - base);
+    const int chunks = rows_here * used;
+#pragma unroll 1
+    for (int e0 = lane; e0 < 32 * used; e0 += 32 * 4) {      // all lanes walk the loop (shuffles); `chunks` masks the tail
+      float4 v[4];
+      int r[4], c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + 32 * u;
+        r[u] = (int)(((uint64_t)e * magic) >> 32);            // e / used (exact: e < 1024, magic = ceil(2^32 / used))
+        c[u] = e - r[u] * used;
+        const int64_t src = shfl_i64(myidx, r[u] & 31);
+        if (e < chunks) v[u] = ld_nc_f4(row_ptr(a, src) + c[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + 32 * u < chunks) route_chunk(a, aligned, base + r[u], c[u], v[u]);
+    }
+  }
+}
+
 // ---- wide rows: one warp per row ------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) rb_gather_wide(const GatherArgs a) {
   const int lane = threadIdx.x & 31;
@@ -851,6 +888,7 @@ struct StagingSet { ddrl::Staging in, out, idx; };
 
 struct ddrl_rb {
   int device = 0, D = 0, A = 0, row_f = 0, row_f4 = 0, used_f4 = 0, sms = 148, gather_u = 8;
+  int gather_flat = 1;            // DDRL_GATHER_FLAT=0: keep the power-of-two lane groups for every narrow row
   int gather_mode = 0;            // 0 auto, 1 always bulk-async + register drain, 2 register kernels, 3 TMA-only for wide rows
   int64_t bulk_min_bytes = 4 << 20;
   int64_t cap = 0, ptr = 0, size = 0, steps = 0, sample_times = 0;
@@ -990,13 +1028,13 @@ static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
   // DDRL_GATHER_MODE=2 keeps the register kernels (also used for D % 4 != 0, unaligned outputs and peer rings).
   if (tma_gather_ok(rb, a) && rb->used_f4 > 32 && (rb->gather_mode == 0 || rb->gather_mode == 3))
     return launch_gather_tma(rb, a, st);
-  // bulk-async pipeline for anything big enough to fill the chip; register path for small launches
-  // (measured on B200, C2 rows: 5.5 TB/s bulk vs 4.5 TB/s registers; C3 rows: 5.4 vs 5.65 TB/s, so wide
-  // rows keep the one-warp-per-row register kernel)
+  // bulk-async pipeline for launches big enough to fill the chip when a row is at least 128 B (measured on B200, C2 rows:
+  // 5.5 TB/s bulk vs 4.5 TB/s registers); shorter rows (C1: 80 B) are bound by the rate of bulk-copy operations — one
+  // 80-byte copy per row — and stay on the register kernels (0.48 vs 0.41 of the HBM peak at 524 k rows per launch)
   // peer (NVLink) rows go through the register kernels: plain ld.global on the mapped peer pointer
   if (a.nshards == 0 &&
       (rb->gather_mode == 1 ||
-       (rb->gather_mode == 0 && rb->used_f4 <= 32 && a.total * rb->used_f4 * 16 >= (int64_t)rb->bulk_min_bytes)))
+       (rb->gather_mode == 0 && rb->used_f4 <= 32 && rb->used_f4 >= 8 && a.total * rb->used_f4 * 16 >= (int64_t)rb->bulk_min_bytes)))
     return launch_gather_bulk(rb, a, st);
   const int threads = 256;
   const int max_blocks = rb->sms * 8;
@@ -1007,6 +1045,13 @@ static int launch_gather(ddrl_rb* rb, const GatherArgs& a, cudaStream_t st) {
     int64_t blocks = (a.total + rows_per_block - 1) / rows_per_block;
     if (blocks > max_blocks) blocks = max_blocks;
     const bool u8 = rb->gather_u >= 8;
+    // a quarter or more of the lanes of the power-of-two kernel would idle (5, 6 of 8; 9..12 of 16; 17..24 of 32): flat map
+    if (rb->used_f4 * 4 <= lanes * 3 && rb->gather_flat) {
+      const uint32_t magic = (uint32_t)((0x100000000ull + rb->used_f4 - 1) / rb->used_f4);
+      rb_gather_flat<<<(int)blocks, threads, 0, st>>>(a, magic);
+      DDRL_LAUNCH_CHECK();
+      return 0;
+    }
     switch (lanes) {
       case 2: rb_gather_narrow<2, 2><<<(int)blocks, threads, 0, st>>>(a); break;
       case 4: rb_gather_narrow<4, 4><<<(int)blocks, threads, 0, st>>>(a); break;
@@ -1113,6 +1158,7 @@ int ddrl_rb_create(int device, int obs_dim, int act_dim, int64_t capacity, ddrl_
     rb->row_f = rb->row_f4 * 4;
     if (const char* e = getenv("DDRL_GATHER_U")) rb->gather_u = atoi(e);
     if (const char* e = getenv("DDRL_GATHER_MODE")) rb->gather_mode = atoi(e);
+    if (const char* e = getenv("DDRL_GATHER_FLAT")) rb->gather_flat = atoi(e);
     if (const char* e = getenv("DDRL_BULK_MIN_BYTES")) rb->bulk_min_bytes = atoll(e);
   }
   rb->cap = capacity;

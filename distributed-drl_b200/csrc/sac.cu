@@ -57,7 +57,18 @@ struct StepState {  // persistent
   int auto_alpha;
   float alpha_const;
   float lr, lr_pi, lr_q;  // base rate and TF1 Adam's bias-corrected rates for this step
+  unsigned long long* trace;  // DDRL_DP_TRACE=1: %globaltimer stamps of the step's exchange (tools/dp_trace.py), else null
 };
+// step trace slots (two-kernel data-parallel exchange): 0 reduce kernel start, 1 its flag published, 2 optimiser kernel
+// start, 3 all flags seen, 4 optimiser kernel end, 6 this step's prologue start, 7 the previous step's
+__device__ __forceinline__ void step_stamp(const StepState* st, int slot) {
+  if (st->trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (slot == 6) st->trace[7] = st->trace[6];
+    st->trace[slot] = t;
+  }
+}
 
 // copy the external batch into the learner's own buffers and materialise the noise
 // tensor-core mode: the three concatenated inputs [x|a], [x|a1], [x2|a3] as pre-split hi/lo planes
@@ -153,6 +164,7 @@ __global__ void __launch_bounds__(256) k_prologue(StepState* st, const __grid_co
                                                   float* X2, float* ACT, float* R, float* DN, float* NOISE, XaOut xa) {
   pdl_trigger();
   pdl_wait();
+  step_stamp(st, 6);
   d_prologue(blockIdx.x, gridDim.x, st, dyn, B, D, A, X, X2, ACT, R, DN, NOISE, xa);
 }
 
@@ -1011,17 +1023,36 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 // Poll with RELAXED loads and take one acquire fence when the flag is seen: an ld.acquire.sys in the spin loop
 // invalidates the SM's L1 on every iteration, which slowed the kernels running next to a waiting exchange kernel
 // threefold (measured on the narrow-W1 kernel: 5 -> 16 us).  The data behind the flags is read with volatile loads.
-__device__ __forceinline__ void wait_flags(const unsigned int* flags, int world, unsigned int epoch, int* err) {
-  if ((int)threadIdx.x < world) {
-    const unsigned int* f = flags + threadIdx.x;
+// Wait until every rank has published `epoch`.  ONE CTA polls the peer-written flags at system scope and re-publishes the
+// epoch on a local word at GPU scope; every other CTA waits on that word.  Measured (tools/probes/flag_probe.cu, 2 B200,
+// 216 CTAs): 6.9 us per exchange round against 18.5 us when every CTA polled the remote-written flags and issued its own
+// fence.acq_rel.sys — system-scope fences are ~1.6 us each and serialise when hundreds are in flight.  CTA 0 never waits
+// on another CTA, and the launches that call this keep the whole grid resident.
+__device__ __forceinline__ void wait_flags(const unsigned int* flags, unsigned int* relay, int world, unsigned int epoch, int* err) {
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < world) {
+      const unsigned int* f = flags + threadIdx.x;
+      const long long t0 = clock64();
+      unsigned int v;
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > 20000000000LL) { *err = 1; break; }   // ~10 s: a peer died; do not hang the GPU
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("fence.acq_rel.sys;" ::: "memory");              // acquire side of the peers' st.release.sys
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(relay), "r"(epoch) : "memory");
+    }
+  } else if (threadIdx.x == 0) {
     const long long t0 = clock64();
     unsigned int v;
     for (;;) {
-      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(relay) : "memory");
       if (v >= epoch) break;
-      if (clock64() - t0 > 20000000000LL) { *err = 1; break; }   // ~10 s: a peer died; do not hang the GPU
+      if (clock64() - t0 > 20000000000LL) { *err = 1; break; }
     }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
   __syncthreads();
 }
@@ -1030,12 +1061,14 @@ struct PeerComm {
   unsigned int* flags[8];   // rank r's arrival flags: flags[r][i] = last step whose gradient rank i has published
   int world, rank, nslice;
   long long Pc;             // floats per slot (P + 4, multiple of 4)
+  unsigned int* relay;      // local word: the last epoch whose flags CTA 0 has seen (wait_flags)
 };
 __global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __restrict__ st, int64_t P, int S,
                                                           const float* __restrict__ Gp, const float* __restrict__ SCAL,
                                                           const __grid_constant__ PeerComm pc, unsigned int* ticket, NarrowGrad ng) {
   pdl_trigger();
   pdl_wait();
+  step_stamp(st, 0);
   float* G = pc.buf[pc.rank] + (size_t)(st->t_pi & 1) * pc.Pc;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < P; i += stride)
@@ -1050,9 +1083,11 @@ __global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __res
   __syncthreads();
   if (s_last && threadIdx.x < pc.world) {
     if (threadIdx.x == 0) *ticket = 0u;
-    __threadfence_system();
+    // release at system scope: cumulative over every CTA's writes (each fenced before its ticket increment); one fence
+    // per publishing thread, no separate __threadfence_system()
     const unsigned int epoch = (unsigned int)st->t_pi;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc.flags[threadIdx.x] + pc.rank), "r"(epoch) : "memory");
+    if (threadIdx.x == 0 && st->trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); st->trace[1] = t; }
   }
 }
 __device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
@@ -1066,8 +1101,10 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
                                                           const __grid_constant__ PeerComm pc, int* err) {
   pdl_trigger();
   pdl_wait();
+  step_stamp(st, 2);
   const unsigned int epoch = (unsigned int)st->t_pi;
-  wait_flags(pc.flags[pc.rank], pc.world, epoch, err);     // (this rank's own flag was published by k_grad_reduce_comm)
+  wait_flags(pc.flags[pc.rank], pc.relay, pc.world, epoch, err);     // (this rank's own flag was published by k_grad_reduce_comm)
+  step_stamp(st, 3);
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
   const size_t slot = (size_t)(epoch & 1u) * pc.Pc;
@@ -1090,12 +1127,12 @@ __global__ void __launch_bounds__(256) k_adam_polyak_peer(StepState* st, int64_t
     for (int r = 0; r < world; ++r) lp += *reinterpret_cast<volatile const float*>(pc.buf[r] + slot + P);
     alpha_step(st, lr, lp * gs, target_entropy);          // mean over the global batch (equal batch per rank)
   }
+  step_stamp(st, 4);      // (CTA 0's end: the other CTAs run the same loop length)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Data-parallel step, one-kernel form (DDRL_DP_V1=0; the two-kernel form above is the default — it measured faster at
-// 4 and 8 GPUs): the first form as ONE kernel (the split-K reduction is folded in, which removes a launch from the
-// critical path): every CTA sums its share of the split-K partials (+ the narrow-W1 slices)
+// Data-parallel step, default form: the two-kernel form above as ONE kernel (the split-K reduction is folded in, which
+// removes a launch from the critical path): every CTA sums its share of the split-K partials (+ the narrow-W1 slices)
 // into this rank's exchange slot; the last CTA to finish publishes the flag on every peer; every CTA waits for all
 // ranks' flags, reads all ranks' slots (128-bit volatile loads over NVLink, all issued before the first add), sums in
 // rank order — every rank computes the same bits, replicas stay bit-identical — and applies Adam + polyak.
@@ -1136,7 +1173,7 @@ __global__ void __launch_bounds__(256) k_adam_dp(StepState* st, int64_t P, int64
     if (threadIdx.x == 0) *ticket = 0u;
     st_release_sys(pc.flags[threadIdx.x] + pc.rank, epoch);   // release: cumulative over the CTAs' writes above
   }
-  wait_flags(pc.flags[pc.rank], world, epoch, err);
+  wait_flags(pc.flags[pc.rank], pc.relay, world, epoch, err);
   stamp(2);
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
@@ -1357,7 +1394,7 @@ struct ddrl_sac {
                                         // (fwd_fused_tc); DDRL_FUSE_L1=0 keeps the two-launch form
   int force_bn = 0;                     // DDRL_TC_BN=64|128 overrides the per-stage tile width choice
   unsigned long long* dp_trace = nullptr;   // DDRL_DP_TRACE=1: 8 phase time stamps of k_adam_dp's CTA 0 (ddrl_sac_dp_trace)
-  bool dp_v1 = true;                    // two-kernel form of the fused data-parallel step (reduce kernel + full peer read); DDRL_DP_V1=0: one kernel
+  bool dp_v1 = false;                   // DDRL_DP_V1=1: two-kernel form of the fused data-parallel step (reduce kernel, then full peer read + optimiser)
   bool narrow_w1 = false;               // policy W1 gradient (K = D <= 32) by k_wgrad_narrow instead of a tensor-core stage
   cudaGraphExec_t dbg_exec = nullptr;   // ddrl_sac_debug_stage(reps < 0): the last measurement graph
   int dbg_key[3] = {0, 0, 0};           // its (batch, stage, reps)
@@ -2142,12 +2179,13 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     if (const char* dt = getenv("DDRL_DP_TRACE")) {
       if (dt[0] == '1') { float* t = nullptr; dalloc(h, &t, 16); h->dp_trace = reinterpret_cast<unsigned long long*>(t); }
     }
-    // two-kernel exchange (reduce + publish, then all-peer read + optimiser) is the default: measured on 2 / 4 / 8 B200
-    // (C2, 600 steps) 106.8-112.2 / 116.8 / 124.0 us per step against 108.9-113.3 / 129.6 / 130.3 us for the one-kernel
-    // form k_adam_dp (the flags travel during the launch gap instead of inside a waiting kernel); DDRL_DP_V1=0 selects
-    // the one-kernel form
+    // one-kernel exchange (split-K reduce + publish + wait + all-peer read + optimiser, k_adam_dp) is the default; DDRL_DP_V1=1
+    // selects the two-kernel form (reduce + publish, then wait + all-peer read + optimiser).  Measured on 2 / 4 / 8 B200 (C2,
+    // 1000 steps, single-GPU step 92.8 us), with the single-poller wait_flags: one kernel 105.7 / 110.7 / 118.0 us per step,
+    // two kernels 108.0 / 113.2 / 120.9 us, NCCL all-reduce 121.0 us at 2 GPUs.  (Before wait_flags polled from one CTA only
+    // the order was the opposite: every CTA's own system-scope fence cost more inside the waiting kernel.)
     const char* d1 = getenv("DDRL_DP_V1");
-    h->dp_v1 = !(d1 && d1[0] == '0');
+    h->dp_v1 = d1 && d1[0] == '1';
 
     const char* nz = getenv("DDRL_NARROW_W1");
     h->narrow_w1 = h->use_tc && D + 1 <= NW_MAXK && h1 % 4 == 0 && !(nz && nz[0] == '0');
@@ -2171,7 +2209,7 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
     h->partials = reinterpret_cast<double*>(tmp);
     tmp = nullptr;
     A_(&tmp, 8);
-    h->ticket = reinterpret_cast<unsigned int*>(tmp);   // [0] Q-heads kernel, [1] reduce kernel (first form), [2] k_adam_dp
+    h->ticket = reinterpret_cast<unsigned int*>(tmp);   // [0] Q-heads kernel, [1] reduce kernel (first form), [2] k_adam_dp, [3] wait_flags relay
   }
   A_(&h->X, M * D); A_(&h->X2, M * D); A_(&h->ACT, M * A); A_(&h->R, M); A_(&h->DN, M); A_(&h->NOISE, 3 * M * A + 4);
   for (int p = 0; p < 8; ++p) { A_(&h->H1[p], planes * M * h->ld1); A_(&h->H2[p], M * h2); }
@@ -2214,6 +2252,7 @@ int ddrl_sac_create(int device, int obs_dim, int act_dim, int h1, int h2, int ma
   init.alpha_const = alpha;
   init.alpha_cur = h->auto_alpha ? 1.0f : alpha;
   init.lr = lr;
+  init.trace = h->dp_trace;
   cudaError_t e = cudaMemcpy(h->st, &init, sizeof(init), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { ddrl_sac_destroy(h); return fail(DDRL_ECUDA, "init state: %s", cudaGetErrorString(e)); }
   *out = h;
@@ -2442,6 +2481,7 @@ int ddrl_sac_comm_attach(ddrl_sac_t h, int world, int rank, const void* h_handle
     h->pc.flags[r] = reinterpret_cast<unsigned int*>((float*)p + 2 * h->pc.Pc);
   }
   h->pc.world = world; h->pc.rank = rank;
+  h->pc.relay = h->ticket + 3;
   // graphs captured before the attach hold the single-GPU kernels
   for (auto& kv : h->plans)
     for (cudaGraphExec_t* ex : {&kv.second.exec_full, &kv.second.exec_grads, &kv.second.exec_apply, &kv.second.exec_dp})

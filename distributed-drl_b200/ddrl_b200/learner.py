@@ -451,11 +451,12 @@ class Learner(object):
         return out
 
     def losses_async(self):
-        """A handle on the losses of the last host-block train(): a callable that waits for THAT step and returns its four
-        scalars (each step gets its own pinned slot, so the handle stays valid while later steps are queued)."""
+        """A handle on the losses of the last train(): a callable that waits for THAT step and returns its four scalars (on
+        the host-block path each step gets its own pinned slot, so the handle stays valid while later steps are queued)."""
         ev, slot = self._hscal_event, self._hscal
-        if ev is None:
-            raise RuntimeError("losses_async(): no host-block train() call yet")
+        if ev is None:                      # the last train() took another path: snapshot its device scalars on the stream
+            snap = self._outs["scalars"].clone()
+            return lambda: snap.cpu().numpy()
 
         def result():
             ev.synchronize()

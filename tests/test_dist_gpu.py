@@ -51,18 +51,18 @@ def _worker(rank, world, port, ret, fused=False):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["nccl", "peer-fused", "peer-fused-one-kernel"])
+@pytest.mark.parametrize("mode", ["nccl", "peer-fused", "peer-fused-two-kernels"])
 def test_two_gpu_step_equals_single_gpu_on_concatenated_batch(mode, monkeypatch):
-    """peer-fused (Learner.connect_peers, no NCCL call on the step path): the reduce kernel leaves this rank's gradient in
-    its exchange slot and publishes a flag on every peer, the optimiser kernel waits for all flags, reads every peer's
-    gradient over NVLink peer memory and applies Adam; peer-fused-one-kernel (DDRL_DP_V1=0): the same in ONE kernel; nccl:
-    torch.distributed.all_reduce between compute_grads and apply_grads."""
+    """peer-fused (Learner.connect_peers, no NCCL call on the step path): ONE kernel sums the split-K partials into this
+    rank's exchange slot, publishes a flag on every peer, waits for all flags, reads every peer's gradient over NVLink peer
+    memory and applies Adam; peer-fused-two-kernels (DDRL_DP_V1=1): the same as a reduce + publish kernel followed by the
+    optimiser kernel; nccl: torch.distributed.all_reduce between compute_grads and apply_grads."""
     import torch.multiprocessing as mp
     import __graft_entry__
     __graft_entry__.build()
     fused = mode != "nccl"
-    if mode == "peer-fused-one-kernel":
-        monkeypatch.setenv("DDRL_DP_V1", "0")       # inherited by the spawned ranks
+    if mode == "peer-fused-two-kernels":
+        monkeypatch.setenv("DDRL_DP_V1", "1")       # inherited by the spawned ranks
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]

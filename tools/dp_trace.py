@@ -18,6 +18,21 @@ assert L.connect_peers()
 dev = torch.device("cuda", local)
 batch = dict(obs1=torch.randn(B, D, device=dev), obs2=torch.randn(B, D, device=dev), acts=torch.rand(B, A, device=dev) * 2 - 1,
              rews=torch.randn(B, device=dev), done=torch.zeros(B, device=dev))
+# steady state: 300 steps queued without any host synchronisation, then the stamps of the LAST step (two-kernel exchange:
+# slots 0 reduce start, 1 flag published, 2 optimiser start, 3 all flags seen, 4 optimiser end, 6 / 7 this / previous prologue start)
+if os.environ.get("DDRL_DP_V1", "0") == "1":
+    for it in range(300):
+        L.train(batch)
+    out = (C.c_uint64 * 8)()
+    _native.check(_native.lib().ddrl_sac_dp_trace(L._h, out))
+    t = np.array(list(out), dtype=np.float64)
+    rel = lambda i: t[i] - t[6]
+    print(f"rank {rank}/{world} last step (ns after its prologue start): reduce kernel start {rel(0):.0f}, flag published {rel(1):.0f}, "
+          f"optimiser kernel start {rel(2):.0f}, all flags seen {rel(3):.0f}, optimiser end {rel(4):.0f}; step period {t[6] - t[7]:.0f}; "
+          f"absolute prologue start {t[6]:.0f}, publish {t[1]:.0f}, flags seen {t[3]:.0f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 rows = []
 exs = []
 for it in range(60):
