@@ -306,7 +306,7 @@ class Bench:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
-    def timed(self, fn, steps, warmup):
+    def timed(self, fn, steps, warmup, also_wait=()):
         torch = self.torch
         for _ in range(warmup):
             fn()
@@ -316,6 +316,8 @@ class Bench:
         e0.record()
         for _ in range(steps):
             fn()
+        for side in also_wait:                  # work queued on other streams belongs to the timed region
+            torch.cuda.current_stream(self.local).wait_stream(side)
         e1.record()
         self.barrier()
         ms = e0.elapsed_time(e1)
@@ -435,9 +437,17 @@ class Bench:
         #   blocking  `batch = replay_buffer.sample_batch(B); agent.train(batch)` with no prefetch
         from ddrl_b200 import Cache
 
+        # the rollout side stores on ITS OWN stream, as the reference's workers are their own processes: the buffer orders
+        # the store kernel against the learner's samples with events, so the H2D copy of the new rows overlaps the update
+        rollout_stream = torch.cuda.Stream(device=self.dev)
+
+        def store_new():
+            with torch.cuda.stream(rollout_stream):
+                rb.store_batch(*new)                              # H2D: B new transitions from the rollout side
+
         def step_e2e():
             res = learner.train_via_host(rb, B)                   # D2H batch -> host numpy, H2D batch, update
-            rb.store_batch(*new)                                  # H2D: B new transitions from the rollout side
+            store_new()
             sink.append(res["scalars"].cpu())                     # D2H: the fetched losses
 
         cache = Cache(rb, B, depth=2)
@@ -445,7 +455,7 @@ class Bench:
         def step_e2e_cache():
             batch = cache.q1.get()                                # host numpy arrays, prefetched like the reference's Cache
             res = learner.train(batch)
-            rb.store_batch(*new)
+            store_new()
             sink.append(res["scalars"].cpu())
 
         prev = [None]
@@ -453,7 +463,7 @@ class Bench:
         def step_e2e_pipelined():                                 # the cache loop with the losses of step k fetched after step
             batch = cache.q1.get()                                # k + 1 has been queued (one read-back per step, one step late)
             res = learner.train(batch)
-            rb.store_batch(*new)
+            store_new()
             if prev[0] is not None:
                 sink.append(prev[0]())                        # waits for step k - 1 only
             prev[0] = learner.losses_async()
@@ -461,23 +471,24 @@ class Bench:
         def step_e2e_blocking():
             batch = rb.sample_batch(B)
             res = learner.train(batch)
-            rb.store_batch(*new)
+            store_new()
             sink.append(res["scalars"].cpu())
 
         e2e_steps = max(5, min(steps, 200 if primary else 60))
         e2e_warm = max(3, min(warmup, 10))
-        sec_e2e, _ = self.timed(step_e2e, e2e_steps, e2e_warm)
-        sec_blk, _ = self.timed(step_e2e_blocking, e2e_steps, e2e_warm)
+        sec_e2e, _ = self.timed(step_e2e, e2e_steps, e2e_warm, also_wait=(rollout_stream,))
+        sec_blk, _ = self.timed(step_e2e_blocking, e2e_steps, e2e_warm, also_wait=(rollout_stream,))
         cache.start()
-        sec_cache, _ = self.timed(step_e2e_cache, e2e_steps, e2e_warm)
-        sec_pipe, _ = self.timed(step_e2e_pipelined, e2e_steps, e2e_warm)
+        sec_cache, _ = self.timed(step_e2e_cache, e2e_steps, e2e_warm, also_wait=(rollout_stream,))
+        sec_pipe, _ = self.timed(step_e2e_pipelined, e2e_steps, e2e_warm, also_wait=(rollout_stream,))
         cache.end()
         sub = lambda sec, path: dict(value=self.world * B * e2e_steps / sec, ms_per_step=sec / e2e_steps * 1e3, path=path)
         out["e2e"] = dict(value=self.world * B * e2e_steps / sec_e2e, unit="transitions/s", h2d_bytes_per_step=2 * B * row_bytes,
                           d2h_bytes_per_step=B * row_bytes + 16, steps=e2e_steps, ms_per_step=sec_e2e / e2e_steps * 1e3,
                           path="Learner.train_via_host(replay_buffer, B) [example/model.py:92-101 Model.train(replay_buffer, args): "
                                "sample_batch into host numpy arrays, update fed from those host arrays] -> store_batch(host, B new "
-                               "rows) -> losses.cpu()",
+                               "rows, on the rollout side's own CUDA stream) -> losses.cpu(); batches of <= 2 MB cross PCIe inside the gather kernel / the "
+                               "step's first kernel (the pinned block's device mapping) instead of as separate DMA copies",
                           cache_loop=sub(sec_cache, "Cache(replay_buffer).q1.get() -> numpy batch -> Learner.train(numpy) -> "
                                                     "store_batch(host) -> losses.cpu() (algos/sac1/sac1.py:136-151; 2 samples in flight)"),
                           pipelined=sub(sec_pipe, "the cache loop with each step's losses read back after the NEXT step has been "

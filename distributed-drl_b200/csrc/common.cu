@@ -37,6 +37,13 @@ int sm_count(int device) {
   return n;
 }
 
+void* host_device_pointer(const void* host_ptr) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return at.devicePointer;
+}
+
 }  // namespace ddrl
 
 extern "C" {

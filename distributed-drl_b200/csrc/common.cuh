@@ -55,6 +55,9 @@ struct DeviceGuard {
 };
 
 int sm_count(int device);
+// device-side address of a host pointer when it is pinned, mapped host memory the current device can access directly
+// (cudaHostAlloc / cudaHostRegister under unified addressing), else nullptr
+void* host_device_pointer(const void* host_ptr);
 
 #ifdef __CUDACC__
 extern bool g_use_pdl;   // DDRL_PDL=1 turns programmatic dependent launch on (off by default: slower inside graphs)

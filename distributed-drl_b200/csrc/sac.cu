@@ -2411,20 +2411,28 @@ int ddrl_sac_step_host(ddrl_sac_t h, const void* h_block, int batch, uint64_t se
     if (!rc) rc = dalloc(h, &h->host_scal, 4);
     if (rc) return rc;
   }
-  // one H2D copy of the block (stream order protects the staging: the previous step's prologue has consumed it), the
-  // step, one D2H copy of the four scalars; nothing here waits for the GPU
+  // Small blocks in PINNED host memory are read by the step's first kernel straight through the block's device mapping
+  // (the prologue is a copy kernel anyway), and the four scalars are written straight into the caller's pinned array:
+  // no H2D / D2H DMA launches (~10 us of latency each) on the critical path.  Otherwise: one H2D copy of the block
+  // (stream order protects the staging: the previous step's prologue has consumed it), the step, one D2H copy of the
+  // scalars.  Nothing here waits for the GPU.
+  static const bool zero_copy = [] { const char* e = getenv("DDRL_ZERO_COPY"); return !(e && e[0] == '0'); }();
   const size_t B = (size_t)batch;
-  DDRL_CUDA(cudaMemcpyAsync(h->host_stage, h_block, B * row * sizeof(float), cudaMemcpyHostToDevice, s));
-  float* x = h->host_stage;
+  float* x = zero_copy && B * row * sizeof(float) <= (2u << 20) ? (float*)host_device_pointer(h_block) : nullptr;
+  float* scal = x && h_out_scalars ? (float*)host_device_pointer(h_out_scalars) : nullptr;
+  if (!x) {
+    DDRL_CUDA(cudaMemcpyAsync(h->host_stage, h_block, B * row * sizeof(float), cudaMemcpyHostToDevice, s));
+    x = h->host_stage;
+  }
   float* x2 = x + B * h->D;
   float* a = x2 + B * h->D;
   float* r = a + B * h->A;
   float* d = r + B;
   const bool dp = h->pc.world > 1;
   int rc = step_common(h, dp ? MODE_DP : MODE_FULL, x, x2, a, r, d, batch, nullptr, seed, dp ? 1.0f / (float)h->pc.world : 1.0f,
-                       h->host_scal, d_out_q1, d_out_q2, d_out_logp, stream, "ddrl_sac_step_host");
+                       scal ? scal : h->host_scal, d_out_q1, d_out_q2, d_out_logp, stream, "ddrl_sac_step_host");
   if (rc) return rc;
-  if (h_out_scalars) DDRL_CUDA(cudaMemcpyAsync(h_out_scalars, h->host_scal, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_out_scalars && !scal) DDRL_CUDA(cudaMemcpyAsync(h_out_scalars, h->host_scal, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 

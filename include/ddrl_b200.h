@@ -109,7 +109,9 @@ int ddrl_rb_sample(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t
                    float* d_out_done, int64_t* d_out_idx, void* stream);
 /* same, result delivered to ONE host block (pinned recommended) laid out as
  *     [obs1 | obs2 | acts | rews | done] f32, each segment n*width floats, then [idx] int64 at the
- * next 8-byte boundary;  h_idx_in (nullable) is a HOST index stream.  Synchronises `stream`. */
+ * next 8-byte boundary;  h_idx_in (nullable) is a HOST index stream.  Synchronises `stream`.
+ * When the block is pinned host memory and the result is <= 2 MB of rows <= 512 B, the gather kernel writes it directly
+ * through the block's device mapping (no staging, no DMA copy; DDRL_ZERO_COPY=0 disables). */
 int ddrl_rb_sample_host(ddrl_rb_t rb, int64_t batch, int64_t n_batches, const int64_t* h_idx_in,
                         uint64_t seed, uint64_t counter, uint32_t rng_stream,
                         void* h_out_block, int64_t block_bytes, void* stream);
@@ -274,7 +276,8 @@ int ddrl_sac_step_from_buffer(ddrl_sac_t sac, ddrl_rb_t rb, int batch, uint64_t 
  * the layout ddrl_rb_sample_host delivers (pinned memory recommended).  One H2D copy, the update, one D2H copy of
  * (pi_loss, q1_loss, q2_loss, alpha) into h_out_scalars (nullable; pinned); nothing waits for the GPU — the scalars are
  * valid once `stream` has executed the call.  Policy noise is drawn on the device.  Uses the fused data-parallel
- * exchange when peers are attached. */
+ * exchange when peers are attached.  A pinned block of <= 2 MB is read by the step's first kernel through its device
+ * mapping and the scalars are written straight to the pinned h_out_scalars (no DMA copies; DDRL_ZERO_COPY=0 disables). */
 int ddrl_sac_step_host(ddrl_sac_t sac, const void* h_block, int batch, uint64_t seed, float* h_out_scalars,
                        float* d_out_q1, float* d_out_q2, float* d_out_logp, void* stream);
 int ddrl_sac_apply_grads(ddrl_sac_t sac, int batch, void* stream);
