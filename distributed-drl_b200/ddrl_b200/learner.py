@@ -121,6 +121,7 @@ class Learner(object):
         self._fused = False
         self._outs = None
         self._hscal, self._hscal_event, self._hscal_ring = None, None, None
+        self._via_host_key, self._via_host_nbytes = None, 0
         self._inflight = collections.deque()
         self._stage = {}
         self.steps = 0
@@ -387,11 +388,11 @@ class Learner(object):
             s.synchronize()
         return o
 
-    def _train_host_block(self, batch, blk, sync_outputs):
+    def _train_host_block(self, batch, blk, sync_outputs, B=None):
         """train() on a HostBatch that still IS the pinned block sample_batch() returned: one native call
         (ddrl_sac_step_host) queues the H2D copy of the block, the update, and the D2H copy of the four scalars into a
         pinned host array — no torch op, no wait.  `losses()` reads the scalars back."""
-        B = int(batch.n)
+        B = int(batch.n) if B is None else B
         if B > self.max_batch:
             raise ValueError(f"batch {B} > max_batch {self.max_batch} (pass max_batch= to Learner)")
         if self._outs is None or self._outs["q1"].shape[0] != B:
@@ -440,14 +441,19 @@ class Learner(object):
             if rb.size == 0:
                 raise ValueError("high <= 0")
             s = self._stream()
-            nbytes = int(self._lib.ddrl_rb_sample_block_bytes(rb._h, B))
+            key = (B, rb.obs_dim, rb.act_dim)
+            if self._via_host_key != key:
+                self._via_host_key = key
+                self._via_host_nbytes = int(self._lib.ddrl_rb_sample_block_bytes(rb._h, B))
+            nbytes = self._via_host_nbytes
             blk = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
             N.check(self._lib.ddrl_rb_sample_host_async(rb._h, B, 1, None, rb._philox_seed(), rb._counter, rb._rng_stream,
                                                         blk.data_ptr(), nbytes, s.cuda_stream))
             rb._counter += 1
-        batch = rb._host_batch(blk, nbytes, B, (B,), (B, self.act_dim), False)
-        out = self._train_host_block(batch, blk, False)
-        out["batch"] = batch
+        # the update is queued right behind the gather; the numpy views of the block are built afterwards, off the GPU's
+        # critical path
+        out = self._train_host_block(None, blk, False, B=B)
+        out["batch"] = rb._host_batch(blk, nbytes, B, (B,), (B, self.act_dim), False)
         return out
 
     def losses_async(self):
