@@ -378,3 +378,35 @@ def test_concurrent_producers_and_learner_equal_some_serial_order(RB):
         last_call[p] = c
         i += len(run)
         first = False
+
+
+def test_host_sample_into_pageable_and_pinned_blocks_agree(RB):
+    """ddrl_rb_sample_host through the raw C ABI: a pinned block is written by the gather kernel itself (device mapping of
+    the block), a pageable numpy block goes through device staging + cudaMemcpyAsync; both must hold the same bytes, and
+    DDRL_ZERO_COPY=0 must not change them."""
+    from ddrl_b200 import _native
+    lib = _native.lib()
+    D, A, cap, B = 24, 4, 5000, 1000
+    g = np.random.Generator(np.random.PCG64(31))
+    rows = [g.standard_normal((cap, D), dtype=np.float32), g.uniform(-1, 1, (cap, A)).astype(np.float32),
+            g.standard_normal(cap, dtype=np.float32), g.standard_normal((cap, D), dtype=np.float32), (g.random(cap) < 0.1).astype(np.float32)]
+    blocks = []
+    for zero_copy in ("1", "0"):
+        os.environ["DDRL_ZERO_COPY"] = zero_copy
+        try:
+            rb = RB(D, A, cap, seed=8)
+        finally:
+            os.environ.pop("DDRL_ZERO_COPY", None)
+        rb.store_batch(*rows)
+        n = int(lib.ddrl_rb_sample_block_bytes(rb.native_handle, B))
+        pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        pageable = np.empty(n, np.uint8)
+        s = torch.cuda.current_stream()
+        for ptr in (pinned.data_ptr(), pageable.ctypes.data):
+            _native.check(lib.ddrl_rb_sample_host(rb.native_handle, B, 1, None, 8, 5, 0, ptr, n, s.cuda_stream))
+        assert np.array_equal(pinned.numpy(), pageable)
+        blocks.append(pageable.copy())
+        want = philox_indices(B, cap, 8, 5, 0)
+        assert np.array_equal(pageable[n - 8 * B:].view(np.int64), want)
+        assert np.array_equal(pageable[:B * D * 4].view(np.float32).reshape(B, D), rows[0][want])
+    assert np.array_equal(blocks[0], blocks[1])
