@@ -7,12 +7,15 @@
 //
 // They reuse the SAC1 learner's building blocks: the grouped fp32 GEMM (sac_gemm.cuh: virtual [x|1] operand so a layer is
 // one [K+1, N] block = kernel rows + bias row, relu / relu-mask epilogues, split-K weight gradients), one row-wise loss
-// kernel, and one reduce + Adam + polyak pass over the flat parameter buffer.  A step is 7 launches:
-//   L1, L2, L3 (all forward passes of a layer in ONE grouped launch) -> k_ql_loss -> B3 {dW3, dH2} -> B2 {dW2, dH1} ->
-//   B1 {dW1} -> k_ql_adam.
+// kernel, and one reduce + Adam + polyak pass over the flat parameter buffer.  A step is ONE CUDA graph of 10 kernels:
+//   k_ql_ingest (the caller's batch -> the handle's buffers; its arguments are patched per step) -> L1, L2, L3 (all forward
+//   passes of a layer in ONE grouped launch) -> k_ql_loss -> B3 {dW3, dH2} -> B2 {dW2, dH1} -> B1 {dW1} -> k_ql_adam ->
+//   k_ql_emit (losses and Q values to the caller's arrays; patched per step).
 // The flat parameter layout IS the reference's variable order (per network: dense/kernel, dense/bias, dense_1/kernel, ...),
 // so get / set weights are plain copies.
 #include <cmath>
+#include <cstdlib>
+#include <map>
 #include <vector>
 
 #include "sac_gemm.cuh"
@@ -31,7 +34,6 @@ struct QlLossArgs {
   double* partial;                   // [nnets][blocks] per-CTA loss sums
   unsigned int* ticket;
   float* out_loss;                   // [nnets + 1]: per-network losses, then their sum (device scalars)
-  float* user_loss;                  // nullable copy for the caller
 };
 
 // one thread per row; per-CTA partial sums in fp64, summed in CTA order by the last CTA (deterministic)
@@ -99,18 +101,17 @@ __global__ void __launch_bounds__(256) k_ql_loss(const QlLossArgs a) {
       const float lk = (float)(v / (double)a.B);
       a.out_loss[k] = lk;
       total += lk;
-      if (a.user_loss) a.user_loss[k] = lk;
     }
     a.out_loss[a.nnets] = total;
-    if (a.user_loss) a.user_loss[a.nnets] = total;
     *a.ticket = 0u;
   }
 }
 
 // split-K partial gradients -> Adam (TF1) -> polyak, one pass over the flat buffers
-__global__ void __launch_bounds__(256) k_ql_adam(int64_t P, int S, const float* __restrict__ Gp, float* G, float lr_t, float polyak,
-                                                 float* W, float* Wt, float* Mo, float* Vo) {
+__global__ void __launch_bounds__(256) k_ql_adam(int64_t P, int S, const float* __restrict__ Gp, float* G, const float* __restrict__ lr_dev,
+                                                 float polyak, float* W, float* Wt, float* Mo, float* Vo) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float lr_t = *lr_dev;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
     float g = 0.0f;
     for (int s = 0; s < S; ++s) g += Gp[(size_t)s * P + i];
@@ -121,6 +122,33 @@ __global__ void __launch_bounds__(256) k_ql_adam(int64_t P, int S, const float* 
     Mo[i] = m; Vo[i] = v; W[i] = w;
     Wt[i] = polyak * Wt[i] + (1.0f - polyak) * w;
   }
+}
+
+// First and last node of the step's graph: their arguments are the only per-step values of a step (the caller's batch
+// arrays, this step's bias-corrected learning rate, the caller's output arrays) and are patched into the instantiated
+// graph before every launch; everything in between reads and writes buffers owned by the handle.
+struct QlIngest {
+  const float *obs1, *obs2, *acts, *rews, *done;
+  float *X1, *X2, *ACTS, *R, *DN, *lr_dev;
+  float lr_t;
+  int B, D;
+};
+__global__ void __launch_bounds__(256) k_ql_ingest(const QlIngest a) {
+  const int64_t n = (int64_t)a.B * a.D, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { a.X1[i] = a.obs1[i]; a.X2[i] = a.obs2[i]; }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += stride) { a.ACTS[i] = a.acts[i]; a.R[i] = a.rews[i]; a.DN[i] = a.done[i]; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.lr_dev = a.lr_t;
+}
+struct QlEmit {
+  const float* loss; float* out_loss; int nloss;
+  const float* q[QL_MAX_NETS]; float* out_q; int nnets; int64_t per_net;
+};
+__global__ void __launch_bounds__(256) k_ql_emit(const QlEmit a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.out_loss && tid < a.nloss) a.out_loss[tid] = a.loss[tid];
+  if (a.out_q)
+    for (int k = 0; k < a.nnets; ++k)
+      for (int64_t i = tid; i < a.per_net; i += stride) a.out_q[(size_t)k * a.per_net + i] = a.q[k][i];
 }
 
 __global__ void k_ql_copy(int64_t n, const float* __restrict__ src, float* dst, float* dst2) {
@@ -145,10 +173,15 @@ struct ddrl_ql {
   float *W = nullptr, *Wt = nullptr, *Mo = nullptr, *Vo = nullptr, *G = nullptr, *Gp = nullptr;
   float *H1[QL_MAX_PASSES] = {}, *H2[QL_MAX_PASSES] = {}, *Q[QL_MAX_PASSES] = {};
   float *dQ[QL_MAX_NETS] = {}, *dH2[QL_MAX_NETS] = {}, *dH1[QL_MAX_NETS] = {};
+  float *X1 = nullptr, *X2 = nullptr, *ACTS = nullptr, *R = nullptr, *DN = nullptr, *lr_dev = nullptr;   // the step's own copy of the batch
   float* loss = nullptr;
   double* partial = nullptr;
   unsigned int* ticket = nullptr;
   int64_t t = 0;
+  bool use_graph = true;                // DDRL_NO_GRAPH=1: plain stream launches (profilers)
+  cudaStream_t cap_stream = nullptr;
+  struct StepGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; cudaGraphNode_t ingest = nullptr, emit = nullptr; int64_t kernels = 0; };
+  std::map<int, StepGraph> graphs;      // per batch size
   std::vector<void*> allocs;
 };
 
@@ -235,6 +268,8 @@ int ddrl_ql_create(int device, int obs_dim, int n_actions, int h1, int h2, int m
   A_(&h->W, P); A_(&h->Wt, P); A_(&h->Mo, P); A_(&h->Vo, P); A_(&h->G, P); A_(&h->Gp, P * h->Smax);
   for (int p = 0; p < npass; ++p) { A_(&h->H1[p], M * h1); A_(&h->H2[p], M * h2); A_(&h->Q[p], M * n_actions); }
   for (int k = 0; k < n_nets; ++k) { A_(&h->dQ[k], M * n_actions); A_(&h->dH2[k], M * h2); A_(&h->dH1[k], M * h1); }
+  A_(&h->X1, M * obs_dim); A_(&h->X2, M * obs_dim); A_(&h->ACTS, M); A_(&h->R, M); A_(&h->DN, M); A_(&h->lr_dev, 1);
+  { const char* e = getenv("DDRL_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   A_(&h->loss, 4);
   float* tmp = nullptr;
   A_(&tmp, 2 * (size_t)QL_MAX_NETS * ((M + 255) / 256) + 2);
@@ -250,6 +285,8 @@ int ddrl_ql_destroy(ddrl_ql_t h) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
+  for (auto& kv : h->graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); if (kv.second.graph) cudaGraphDestroy(kv.second.graph); }
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return 0;
@@ -294,25 +331,20 @@ static int ql_forward(ddrl_ql* h, int B, const float* const* x_of_pass, const in
   return ql_launch(v, s);
 }
 
-int ddrl_ql_step(ddrl_ql_t h, const float* d_obs1, const float* d_obs2, const float* d_acts, const float* d_rews,
-                 const float* d_done, int batch, float* d_out_loss, float* d_out_q, void* stream) {
-  if (!h) return fail(DDRL_EINVAL, "ddrl_ql_step: NULL handle");
-  if (batch < 1 || batch > h->maxB) return fail(DDRL_EINVAL, "ddrl_ql_step: batch=%d not in [1, %d]", batch, h->maxB);
-  if (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done) return fail(DDRL_EINVAL, "ddrl_ql_step: NULL batch array");
-  DeviceGuard guard(h->device);
-  cudaStream_t s = (cudaStream_t)stream;
-  const int B = batch, D = h->D, h1 = h->h1, h2 = h->h2, nA = h->nA, K = h->nnets;
+// everything of a step between the ingest and the emit kernels: reads the handle's copy of the batch, static pointers only
+static int ql_step_body(ddrl_ql* h, int B, cudaStream_t s) {
+  const int D = h->D, h1 = h->h1, h2 = h->h2, nA = h->nA, K = h->nnets;
   // forward passes.  DDQN: main@x, main@x2, target@x2.  SQN: q1 main@x, q2 main@x, q1 main@x2, q1 target@x2, q2 target@x2
   const float* xs[QL_MAX_PASSES];
   int net[QL_MAX_PASSES], targ[QL_MAX_PASSES], npass;
   if (h->mode == 0) {
     npass = 3;
-    xs[0] = d_obs1; xs[1] = d_obs2; xs[2] = d_obs2;
+    xs[0] = h->X1; xs[1] = h->X2; xs[2] = h->X2;
     net[0] = net[1] = net[2] = 0;
     targ[0] = 0; targ[1] = 0; targ[2] = 1;
   } else {
     npass = 5;
-    xs[0] = d_obs1; xs[1] = d_obs1; xs[2] = d_obs2; xs[3] = d_obs2; xs[4] = d_obs2;
+    xs[0] = h->X1; xs[1] = h->X1; xs[2] = h->X2; xs[3] = h->X2; xs[4] = h->X2;
     net[0] = 0; net[1] = 1; net[2] = 0; net[3] = 0; net[4] = 1;
     targ[0] = targ[1] = targ[2] = 0; targ[3] = targ[4] = 1;
   }
@@ -320,15 +352,12 @@ int ddrl_ql_step(ddrl_ql_t h, const float* d_obs1, const float* d_obs2, const fl
   if (rc) return rc;
   QlLossArgs la{};
   la.B = B; la.nA = nA; la.mode = h->mode; la.nnets = K; la.gamma = h->gamma; la.alpha = h->alpha;
-  la.acts = d_acts; la.rews = d_rews; la.done = d_done;
+  la.acts = h->ACTS; la.rews = h->R; la.done = h->DN;
   for (int p = 0; p < npass; ++p) la.Q[p] = h->Q[p];
   for (int k = 0; k < K; ++k) la.dQ[k] = h->dQ[k];
-  la.partial = h->partial; la.ticket = h->ticket; la.out_loss = h->loss; la.user_loss = d_out_loss;
+  la.partial = h->partial; la.ticket = h->ticket; la.out_loss = h->loss;
   k_ql_loss<<<(B + 255) / 256, 256, 0, s>>>(la);
   DDRL_LAUNCH_CHECK();
-  if (d_out_q)      // the reference fetches q (DDQN) / q1, q2 (SQN) of the sampled states
-    for (int k = 0; k < K; ++k)
-      DDRL_CUDA(cudaMemcpyAsync(d_out_q + (size_t)k * B * nA, h->Q[k], (size_t)B * nA * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // backward of the differentiated passes (pass k = network k at x): weight gradients as split-K partials over the batch
   const int S = (B + 255) / 256, kps = 256;
   auto wg = [&](GemmProb p) { p.splits = S; p.k_per_split = kps; p.c_split_stride = h->P; return p; };
@@ -356,12 +385,79 @@ int ddrl_ql_step(ddrl_ql_t h, const float* d_obs1, const float* d_obs2, const fl
   for (int k = 0; k < K; ++k)
     v.push_back(wg(ql_prob(xs[k], D, D, 1, h->dH1[k], h1, 0, h->Gp + (int64_t)k * h->Pnet + h->o1, h1, D + 1, h1, B)));   // d[W1;b1] = [x|1]^T dH1
   if ((rc = ql_launch(v, s))) return rc;
+  const int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
+  k_ql_adam<<<blocks, 256, 0, s>>>(h->P, S, h->Gp, h->G, h->lr_dev, h->polyak, h->W, h->Wt, h->Mo, h->Vo);
+  DDRL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ddrl_ql_step(ddrl_ql_t h, const float* d_obs1, const float* d_obs2, const float* d_acts, const float* d_rews,
+                 const float* d_done, int batch, float* d_out_loss, float* d_out_q, void* stream) {
+  if (!h) return fail(DDRL_EINVAL, "ddrl_ql_step: NULL handle");
+  if (batch < 1 || batch > h->maxB) return fail(DDRL_EINVAL, "ddrl_ql_step: batch=%d not in [1, %d]", batch, h->maxB);
+  if (!d_obs1 || !d_obs2 || !d_acts || !d_rews || !d_done) return fail(DDRL_EINVAL, "ddrl_ql_step: NULL batch array");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = batch;
   h->t += 1;
   const double t = (double)h->t;
-  const float lr_t = (float)((double)h->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
-  const int blocks = (int)std::min<int64_t>((h->P + 255) / 256, h->sms * 8);
-  k_ql_adam<<<blocks, 256, 0, s>>>(h->P, S, h->Gp, h->G, lr_t, h->polyak, h->W, h->Wt, h->Mo, h->Vo);
-  DDRL_LAUNCH_CHECK();
+  QlIngest in{d_obs1, d_obs2, d_acts, d_rews, d_done, h->X1, h->X2, h->ACTS, h->R, h->DN, h->lr_dev,
+              (float)((double)h->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t))), B, h->D};
+  QlEmit out{};
+  out.loss = h->loss; out.out_loss = d_out_loss; out.nloss = h->nnets + 1;
+  for (int k = 0; k < h->nnets; ++k) out.q[k] = h->Q[k];       // the reference fetches q (DDQN) / q1, q2 (SQN) of the sampled states
+  out.out_q = d_out_q; out.nnets = h->nnets; out.per_net = (int64_t)B * h->nA;
+  const dim3 gin((unsigned)std::min<int64_t>(((int64_t)B * h->D + 255) / 256, h->sms * 4)), gout((unsigned)std::min<int64_t>((out.per_net + 255) / 256, h->sms * 2));
+  auto enqueue = [&](cudaStream_t st) -> int {
+    k_ql_ingest<<<gin, 256, 0, st>>>(in);
+    DDRL_LAUNCH_CHECK();
+    int rc = ql_step_body(h, B, st);
+    if (rc) return rc;
+    k_ql_emit<<<gout, 256, 0, st>>>(out);
+    DDRL_LAUNCH_CHECK();
+    return 0;
+  };
+  if (!h->use_graph) return enqueue(s);
+  // the whole step is one CUDA graph per batch size (stream-order launches cost ~1.6 us each and complete on a 2.05 us
+  // grid, tools/probes/tick_probe.cu); the first and last node carry this call's pointers and learning rate
+  ddrl_ql::StepGraph& g = h->graphs[B];
+  if (!g.exec) {
+    if (!h->cap_stream) DDRL_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const int64_t before = g_launches.load();
+    DDRL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue(h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g.graph);
+    g.kernels = g_launches.load() - before;
+    g_launches.store(before);      // captured, not executed
+    if (rc) { if (g.graph) cudaGraphDestroy(g.graph); h->graphs.erase(B); return rc; }
+    if (e != cudaSuccess) { h->graphs.erase(B); return fail(DDRL_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); }
+    size_t n = 0;
+    DDRL_CUDA(cudaGraphGetNodes(g.graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    DDRL_CUDA(cudaGraphGetNodes(g.graph, nodes.data(), &n));
+    for (cudaGraphNode_t nd : nodes) {
+      cudaGraphNodeType ty;
+      cudaKernelNodeParams kp{};
+      if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+      if (kp.func == (void*)k_ql_ingest) g.ingest = nd;
+      if (kp.func == (void*)k_ql_emit) g.emit = nd;
+    }
+    if (!g.ingest || !g.emit) { cudaGraphDestroy(g.graph); h->graphs.erase(B); return fail(DDRL_ECUDA, "captured step lacks its ingest / emit node"); }
+    e = cudaGraphInstantiate(&g.exec, g.graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g.graph); h->graphs.erase(B); return fail(DDRL_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+  } else {
+    void* a_in[] = {&in};
+    void* a_out[] = {&out};
+    cudaKernelNodeParams np{};
+    np.blockDim = dim3(256); np.sharedMemBytes = 0; np.extra = nullptr;
+    np.func = (void*)k_ql_ingest; np.gridDim = gin; np.kernelParams = a_in;
+    DDRL_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.ingest, &np));
+    np.func = (void*)k_ql_emit; np.gridDim = gout; np.kernelParams = a_out;
+    DDRL_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.emit, &np));
+  }
+  DDRL_CUDA(cudaGraphLaunch(g.exec, s));
+  g_launches.fetch_add(g.kernels, std::memory_order_relaxed);
   return 0;
 }
 

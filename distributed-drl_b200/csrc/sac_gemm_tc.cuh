@@ -467,7 +467,7 @@ constexpr int FZ_IN_BYTES = 2 * TILE_BYTES + 2 * (FZ_MAX_H1 / 32) * 4096;   // [
 constexpr int FZ_SMEM_BYTES = FZ_IN_BYTES + FZ_SB * FZ_B_STAGE + 1024 /*align*/ + 256 /*barriers, tmem ptr*/ +
                               4 * FZ_MAX_H1 + 4 * FZ_BN;
 constexpr int FZ_TMEM_COLS = 512;
-constexpr int FZ_LO_COL = FZ_MAX_H1, FZ_ACC_COL = FZ_MAX_H1 + FZ_SA * BK, FZ_NACC = 2;
+constexpr int FZ_LO_COL = FZ_MAX_H1, FZ_ACC_COL = FZ_MAX_H1 + FZ_SA * BK;
 constexpr int FZ_MAX_PROBS = 4;
 struct alignas(64) FusedProb {
   CUtensorMap tx;              // [x|a] planes, K-major, box 32 x 128
