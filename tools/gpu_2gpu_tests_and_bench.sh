@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/r02_dist_tests_2gpu.log
 timeout 600 python -m pytest tests/test_dist_gpu.py tests/test_sac_gpu.py::test_host_block_path_and_cache_prefetch_equal_the_plain_calls -v 2>&1 | grep -E "PASSED|FAILED|SKIPPED|passed|failed|Error" >> gpurun_out/r02_dist_tests_2gpu.log; cat gpurun_out/r02_dist_tests_2gpu.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 1000 --warmup 50 --only-primary > gpurun_out/u_bench2.json 2> gpurun_out/u_bench2.err; echo "bench2 rc=$?"; tail -3 gpurun_out/u_bench2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 1000 --warmup 50 > gpurun_out/u_bench2.json 2> gpurun_out/u_bench2.err; echo "bench2 rc=$?"; tail -3 gpurun_out/u_bench2.err
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/u_bench2.json").read().strip().splitlines()[-1])
