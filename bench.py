@@ -406,7 +406,7 @@ class Bench:
         if self.world > 1:
             dp_mode = "nccl"
             if os.environ.get("DDRL_DP", "fused") != "nccl" and learner.connect_peers():
-                dp_mode = "peer-fused"
+                dp_mode = "peer-fused-nvls" if getattr(learner, "nvls", False) else "peer-fused"
         torch.cuda.synchronize()
 
         # (1) device-resident hot loop: sample_batch(B) + train(batch) as one native call (the step's first kernel gathers
@@ -798,7 +798,8 @@ def run_ours(args):
                     replay_rows_per_gpu=prim["replay_rows_per_gpu"], replay_bytes_per_gpu=prim["replay_bytes_per_gpu"],
                     row_bytes=prim["row_bytes"], row_stride_bytes=prim["row_stride_bytes"],
                     parallelism=(f"dp{world}: replay sharded per GPU, gradient all-reduce "
-                                 + ("fused into the optimiser kernel over NVLink peer memory (CUDA IPC)" if extra["dp_mode"] == "peer-fused"
+                                 + ("fused into the optimiser kernel: multimem.ld_reduce over an NVLS multicast mapping (the NVSwitch adds)" if extra["dp_mode"] == "peer-fused-nvls"
+                                    else "fused into the optimiser kernel over NVLink peer memory (CUDA IPC)" if extra["dp_mode"] == "peer-fused"
                                     else "by NCCL")) if world > 1 else "single GPU",
                     l2="replay ring larger than L2, rows drawn at random; weights (3.5 MB) are L2-resident by design",
                     noise="Philox on device", index_source="Philox on device"),

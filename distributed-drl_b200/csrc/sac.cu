@@ -1062,7 +1062,16 @@ struct PeerComm {
   int world, rank, nslice;
   long long Pc;             // floats per slot (P + 4, multiple of 4)
   unsigned int* relay;      // local word: the last epoch whose flags CTA 0 has seen (wait_flags)
+  const float* mc;          // nullable: NVLS multicast mapping of the same buffers (ddrl_sac_comm_attach_ptrs): one
+                            // multimem.ld_reduce returns the sum over all ranks, added inside the NVSwitch
 };
+// sum over all ranks of the 4 floats at the same offset of every rank's buffer, reduced in the switch
+__device__ __forceinline__ float4 mc_ld_reduce_f4(const float* p) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __global__ void __launch_bounds__(256) k_grad_reduce_comm(const StepState* __restrict__ st, int64_t P, int S,
                                                           const float* __restrict__ Gp, const float* __restrict__ SCAL,
                                                           const __grid_constant__ PeerComm pc, unsigned int* ticket, NarrowGrad ng) {
@@ -1178,16 +1187,22 @@ __global__ void __launch_bounds__(256) k_adam_dp(StepState* st, int64_t P, int64
   const float lr_pi = st->lr_pi, lr_q = st->lr_q;
   const float gs = st->dyn.grad_scale;
   const SplitMap* mpp = Wsp ? &mp : nullptr;
-  for (int64_t i = gtid * 4; i < P; i += gthreads * 4) {
-    float4 q[8];
+  if (pc.mc) {
+    // NVLS: ONE load per 16 bytes; the switch reads every rank's slot and adds (traffic per rank: P instead of (N-1) P)
+    for (int64_t i = gtid * 4; i < P; i += gthreads * 4)
+      adam4(i, mc_ld_reduce_f4(pc.mc + slot + i), gs, i < P_pi ? lr_pi : lr_q, polyak, W, Wt, Mo, Vo, mpp, Wsp, Wtsp);
+  } else {
+    for (int64_t i = gtid * 4; i < P; i += gthreads * 4) {
+      float4 q[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < world) q[r] = ld_volatile_f4(pc.buf[r] + slot + i);
-    float4 g = q[0];
+      for (int r = 0; r < 8; ++r)
+        if (r < world) q[r] = ld_volatile_f4(pc.buf[r] + slot + i);
+      float4 g = q[0];
 #pragma unroll
-    for (int r = 1; r < 8; ++r)
-      if (r < world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
-    adam4(i, g, gs, i < P_pi ? lr_pi : lr_q, polyak, W, Wt, Mo, Vo, mpp, Wsp, Wtsp);
+      for (int r = 1; r < 8; ++r)
+        if (r < world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
+      adam4(i, g, gs, i < P_pi ? lr_pi : lr_q, polyak, W, Wt, Mo, Vo, mpp, Wsp, Wtsp);
+    }
   }
   if (gtid == 0 && st->auto_alpha) {
     float lp = 0.0f;
@@ -2466,6 +2481,41 @@ int ddrl_sac_comm_export(ddrl_sac_t h, void* h_handle64) {
   cudaIpcMemHandle_t hd;
   DDRL_CUDA(cudaIpcGetMemHandle(&hd, h->comm));
   memcpy(h_handle64, &hd, 64);
+  return 0;
+}
+
+static long long comm_pc(const ddrl_sac* h) { return (h->P + 4 + 3) / 4 * 4; }
+
+int64_t ddrl_sac_comm_bytes(ddrl_sac_t h) {
+  if (!h) return -1;
+  return (int64_t)((size_t)2 * comm_pc(h) * sizeof(float) + (8 + 8) * sizeof(unsigned int));
+}
+
+int ddrl_sac_comm_attach_ptrs(ddrl_sac_t h, int world, int rank, void* const* d_bufs, const void* d_multicast) {
+  if (!h || !d_bufs) return fail(DDRL_EINVAL, "ddrl_sac_comm_attach_ptrs: NULL argument");
+  if (world < 2 || world > 8 || rank < 0 || rank >= world)
+    return fail(DDRL_EINVAL, "ddrl_sac_comm_attach_ptrs: rank %d of %d (2..8 ranks of one node)", rank, world);
+  if (h->t_host != 0) return fail(DDRL_ESTATE, "ddrl_sac_comm_attach_ptrs: attach before the first update (ranks step in lockstep)");
+  for (int r = 0; r < world; ++r)
+    if (!d_bufs[r] || ((uintptr_t)d_bufs[r] & 15)) return fail(DDRL_EINVAL, "ddrl_sac_comm_attach_ptrs: buffer %d is NULL or not 16-byte aligned", r);
+  if (((uintptr_t)d_multicast & 15)) return fail(DDRL_EINVAL, "ddrl_sac_comm_attach_ptrs: multicast pointer not 16-byte aligned");
+  DeviceGuard guard(h->device);
+  h->pc.nslice = 1;
+  h->pc.Pc = comm_pc(h);
+  if (!h->d_err) {
+    DDRL_CUDA(cudaMalloc((void**)&h->d_err, sizeof(int)));
+    DDRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+  }
+  for (int r = 0; r < world; ++r) {
+    h->pc.buf[r] = (float*)d_bufs[r];
+    h->pc.flags[r] = reinterpret_cast<unsigned int*>((float*)d_bufs[r] + 2 * h->pc.Pc);
+  }
+  h->pc.mc = (const float*)d_multicast;
+  h->pc.world = world; h->pc.rank = rank;
+  h->pc.relay = h->ticket + 3;
+  for (auto& kv : h->plans)
+    for (cudaGraphExec_t* ex : {&kv.second.exec_full, &kv.second.exec_grads, &kv.second.exec_apply, &kv.second.exec_dp})
+      if (*ex) { cudaGraphExecDestroy(*ex); *ex = nullptr; }
   return 0;
 }
 

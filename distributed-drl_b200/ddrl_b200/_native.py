@@ -72,6 +72,8 @@ SIGNATURES = {
     "ddrl_rb_read_end": (_int, [_vp, _vp, _i64]),
     "ddrl_sac_comm_export": (_int, [_vp, _vp]),
     "ddrl_sac_comm_attach": (_int, [_vp, _int, _int, _vp]),
+    "ddrl_sac_comm_bytes": (_i64, [_vp]),
+    "ddrl_sac_comm_attach_ptrs": (_int, [_vp, _int, _int, C.POINTER(_vp), _vp]),
     "ddrl_sac_comm_error": (_int, [_vp, _pint]),
     "ddrl_sac_dp_trace": (_int, [_vp, C.POINTER(C.c_uint64)]),
     "ddrl_ql_create": (_int, [_int, _int, _int, _int, _int, _int, _int, _f, _f, _f, _f, C.POINTER(_vp)]),

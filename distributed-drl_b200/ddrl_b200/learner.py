@@ -18,6 +18,7 @@ from __future__ import annotations
 import collections
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -120,6 +121,7 @@ class Learner(object):
         self._pg = process_group
         self._fused = False
         self._outs = None
+        self.nvls = False
         self._hscal, self._hscal_event, self._hscal_ring = None, None, None
         self._via_host_key, self._via_host_nbytes = None, 0
         self._inflight = collections.deque()
@@ -155,6 +157,12 @@ class Learner(object):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world < 2:
             return False
+        # NVLS first (measured on 8 B200: 116.4 vs 118.4 us per C2 step, replicas bit-identical after 200 steps —
+        # tools/dp_replica_check.py); CUDA IPC + peer reads when multicast is unavailable, with DDRL_DP_NVLS=0, or for the
+        # two-kernel form of the exchange
+        if (os.environ.get("DDRL_DP_NVLS", "1") != "0" and os.environ.get("DDRL_DP_V1", "0") != "1"
+                and self._connect_symmetric(group, world, rank)):
+            return True
         buf = (C.c_ubyte * 64)()
         N.check(self._lib.ddrl_sac_comm_export(self._h, buf))
         handles = [None] * world
@@ -163,6 +171,37 @@ class Learner(object):
         N.check(self._lib.ddrl_sac_comm_attach(self._h, world, rank, C.c_char_p(blob)))
         self._pg = group
         self._fused = True
+        dist.barrier(group)
+        return True
+
+    def _connect_symmetric(self, group, world, rank):
+        """Exchange buffers from torch's symmetric-memory allocator (device memory plumbing): every rank's buffer mapped in
+        every process AND, where the NVSwitch supports it, one multicast (NVLS) mapping of all of them, through which the
+        optimiser kernel reads the sum of the ranks' gradients with multimem.ld_reduce.  Returns False (after agreeing with
+        the other ranks) when the allocator or the multicast mapping is unavailable; the caller then uses CUDA IPC."""
+        import torch.distributed as dist
+        ok, hdl, t = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            n = int(self._lib.ddrl_sac_comm_bytes(self._h))
+            t = symm.empty((n + 3) // 4, dtype=torch.float32, device=self._dev)
+            t.zero_()
+            torch.cuda.synchronize(self.device)
+            hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            if int(hdl.multicast_ptr) == 0:
+                ok = 0
+        except Exception:       # noqa: BLE001  (allocator / driver without fabric or multicast support)
+            ok = 0
+        flag = torch.tensor([ok], device=self._dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)        # all ranks take the same path
+        if int(flag.item()) == 0:
+            return False
+        ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+        N.check(self._lib.ddrl_sac_comm_attach_ptrs(self._h, world, rank, ptrs, C.c_void_p(int(hdl.multicast_ptr))))
+        self._symm = (t, hdl)       # keeps the allocation and its mappings alive
+        self._pg = group
+        self._fused = True
+        self.nvls = True
         dist.barrier(group)
         return True
 

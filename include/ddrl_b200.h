@@ -296,6 +296,13 @@ int ddrl_sac_step_dp(ddrl_sac_t sac, const float* d_obs1, const float* d_obs2, c
                      float grad_scale, float* d_out_scalars, float* d_out_q1, float* d_out_q2, float* d_out_logp,
                      void* stream);
 int ddrl_sac_comm_attach(ddrl_sac_t sac, int world, int rank, const void* h_handles);
+/* The same attachment from pointers the caller already holds: d_bufs[r] = rank r's exchange buffer as mapped in THIS
+ * process (ddrl_sac_comm_bytes bytes each, zero-filled, 16-byte aligned; e.g. a symmetric-memory allocation), and
+ * optionally d_multicast = the NVLS multicast mapping of those buffers: the optimiser kernel then fetches the sum of all
+ * ranks' gradients with ONE multimem.ld_reduce per 16 bytes — the NVSwitch adds — instead of reading every peer
+ * ((N-1) P bytes per rank become P).  The one-kernel exchange only (DDRL_DP_V1 unset). */
+int64_t ddrl_sac_comm_bytes(ddrl_sac_t sac);
+int ddrl_sac_comm_attach_ptrs(ddrl_sac_t sac, int world, int rank, void* const* d_bufs, const void* d_multicast);
 int ddrl_sac_comm_error(ddrl_sac_t sac, int* out_error);
 /* profiling aid (handle created with DDRL_DP_TRACE=1 in the environment): %globaltimer stamps (ns) of the last fused
  * data-parallel optimiser launch, CTA 0: start, own gradient written, all gradients published, slice scattered, all

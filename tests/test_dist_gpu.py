@@ -45,17 +45,18 @@ def _worker(rank, world, port, ret, fused=False):
         ps.push_flat(L.get_flat_weights() * 0 + 3.0)
     ps.sync()
     ret[rank] = (L.get_flat_weights("main").cpu().numpy(), L.get_flat_weights("target").cpu().numpy(),
-                 float(ps.pull_flat().min()), float(ps.pull_flat().max()), L.comm_error())
+                 float(ps.pull_flat().min()), float(ps.pull_flat().max()), L.comm_error(), bool(L.nvls))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["nccl", "peer-fused", "peer-fused-two-kernels"])
+@pytest.mark.parametrize("mode", ["nccl", "peer-fused", "peer-fused-two-kernels", "peer-fused-nvls"])
 def test_two_gpu_step_equals_single_gpu_on_concatenated_batch(mode, monkeypatch):
     """peer-fused (Learner.connect_peers, no NCCL call on the step path): ONE kernel sums the split-K partials into this
     rank's exchange slot, publishes a flag on every peer, waits for all flags, reads every peer's gradient over NVLink peer
-    memory and applies Adam; peer-fused-two-kernels (DDRL_DP_V1=1): the same as a reduce + publish kernel followed by the
+    memory and applies Adam; peer-fused-nvls: the same kernel fetches the sum of all ranks' gradients with
+    multimem.ld_reduce over an NVLS multicast mapping of the exchange buffers (the NVSwitch adds); peer-fused-two-kernels (DDRL_DP_V1=1): the same as a reduce + publish kernel followed by the
     optimiser kernel; nccl: torch.distributed.all_reduce between compute_grads and apply_grads."""
     import torch.multiprocessing as mp
     import __graft_entry__
@@ -63,6 +64,9 @@ def test_two_gpu_step_equals_single_gpu_on_concatenated_batch(mode, monkeypatch)
     fused = mode != "nccl"
     if mode == "peer-fused-two-kernels":
         monkeypatch.setenv("DDRL_DP_V1", "1")       # inherited by the spawned ranks
+    # peer-fused-nvls: multimem.ld_reduce over a multicast mapping (the default when the NVSwitch offers it; falls back to
+    # IPC peer reads otherwise); "peer-fused" pins the IPC form
+    monkeypatch.setenv("DDRL_DP_NVLS", "1" if mode == "peer-fused-nvls" else "0")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -84,6 +88,8 @@ def test_two_gpu_step_equals_single_gpu_on_concatenated_batch(mode, monkeypatch)
         assert np.abs(ret[r][1] - want_t).max() <= 2e-5 * np.abs(want_t).max()
         assert ret[r][2] == 3.0 and ret[r][3] == 3.0
         assert ret[r][4] == 0            # no peer time-out seen by the fused kernel
+    print(f"{mode}: NVLS multicast in use: {ret[0][5]}")
+    assert ret[0][5] == ret[1][5] and (ret[0][5] is False or mode == "peer-fused-nvls")
 
 
 def _global_worker(rank, world, port, ret):
