@@ -72,3 +72,30 @@ def test_parameter_server_as_actor():
     assert np.all(ray.get(ps.pull.remote(["k"]))[0] == 2.0)
     ps2 = PS._remote(args=[["k"], [np.zeros(1, np.float32)]], resources={"node0": 1})
     assert ray.get(ps2.get_weights.remote())["k"].shape == (1,)
+
+
+def test_actor_lock_is_fifo_and_reentrant():
+    """A Ray actor serves its mailbox in arrival order: the shim's per-actor lock hands over to waiters first-in
+    first-out (a learner's sample_batch is not starved by producers re-acquiring the lock) and is re-entrant."""
+    import threading
+    from ddrl_b200.ray_shim import _FifoLock
+    lock, order, started = _FifoLock(), [], []
+
+    def waiter(i):
+        started.append(i)
+        with lock:
+            with lock:                      # re-entrant
+                order.append(i)
+                time.sleep(0.002)
+
+    with lock:
+        threads = []
+        for i in range(6):
+            t = threading.Thread(target=waiter, args=(i,))
+            t.start()
+            while len(started) <= i or len(lock._waiters) <= i:      # thread i is queued before thread i + 1 starts
+                time.sleep(0.0005)
+            threads.append(t)
+    for t in threads:
+        t.join()
+    assert order == list(range(6))
