@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256, (U >= 8 || LANES <= 4) ? 2 : ((LANES == 8
 // ---- narrow rows whose float4 count is far from a power of two (C1: 5 chunks of 16 B -> 3 of 8 lanes idle above) ------
 // Same warp-level scheme (32 rows per pass, one index per lane), but the 32 * used_f4 chunks of the pass are dealt to the
 // lanes FLAT: chunk e = 32 * it + lane belongs to row e / used_f4, so every lane moves data in every iteration.
-__global__ void __launch_bounds__(256, 4) rb_gather_flat(const GatherArgs a, uint32_t magic) {
+__global__ void __launch_bounds__(256, 6) rb_gather_flat(const GatherArgs a, uint32_t magic) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
