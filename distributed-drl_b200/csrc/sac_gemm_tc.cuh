@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fwd_fused_tc(const __grid_const
       TC_STAMP(8 + kb);             // operands of k-block kb ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = tmem_d + (uint32_t)(kb * BK), a_lo = tmem_d + (uint32_t)(FZ_LO_COL + sa * BK);
-      const uint32_t b_hi = s_addr(bring + sb * FZ_B_STAGE), b_lo = b_hi + FZ_B_STAGE / 2;
+      const uint32_t b_hi = s_addr(bring + sb * FZ_B_STAGE);      // the lo plane follows at + FZ_B_STAGE / 2
       const uint32_t acc = tmem_d + (uint32_t)FZ_ACC_COL;
       const uint64_t db_hi = make_sdesc(b_hi, true);
       static_assert(FZ_B_STAGE / 2 == (FZ_BN / 32) * 4096, "the lo plane's blocks continue the hi plane's at the descriptor's LBO");

@@ -48,3 +48,10 @@ if full[:, 24:].any():
             cg, np.median(full[:, c + 1] - full[:, c]), np.median(full[:, c + 2] - full[:, c + 1]), np.median(full[:, c + 3] - full[:, c + 2])))
 print("  per-CTA durations (median ns): setup %.0f, load latency %.0f, mainloop issue %.0f, MMA drain %.0f, epilogue %.0f, join %.0f" % tuple(
     np.median(t[:, i + 1] - t[:, i]) for i in range(6)))
+# per tile: first stage landed -> accumulator complete (the MMA main loop), in launch order: the problems of a stage are laid
+# out one after the other, so populations with different operand layouts (dgrad: K-major B; wgrad: MN-major A and B) show
+if os.environ.get("TC_TRACE_TILES"):
+    ml = t[:, 4] - t[:, 2]
+    print("  main loop per tile (ns), 16 tiles per line:")
+    for i in range(0, len(ml), 16):
+        print("   ", " ".join(f"{x:5.0f}" for x in ml[i:i + 16]))
